@@ -1,0 +1,82 @@
+/*
+ * dvode_oracle.h -- CPU restatement of jacobwilliams/dvode (REAL64) in plain C.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is the parity oracle for the B200 batched
+ * VODE path.  Nothing in the product path (dvode_b200/, include/) may call,
+ * link or import it; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs do.
+ *
+ * Parity pin: the restatement is pinned against the reference's own golden
+ * transcript test/dvdemo.txt (all 24 runs: printed digits, NQ, H, RWORK/IWORK
+ * sizes and all counters) and against test/example.f90's trailing comment
+ * (Robertson).  See tests/test_oracle_golden.py.  The reference itself cannot
+ * be compiled here (no Fortran compiler in the image).
+ *
+ * Citations below are file:line into /root/reference (M = src/dvode_module.F90,
+ * LP = src/dvode_linpack_module.F90, BL = src/dvode_blas_module.F90).
+ */
+#ifndef DVODE_ORACLE_H
+#define DVODE_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* user callbacks, M:316-334.  ctx replaces the Fortran `me` host association. */
+typedef void (*dvo_f_fn)(void *ctx, int neq, double t, const double *y, double *ydot);
+typedef void (*dvo_jac_fn)(void *ctx, int neq, double t, double *y, int ml, int mu,
+                           double *pd, int nrowpd);
+
+/* dvode_data_t (M:40-153) + dvode_t (M:251-270) */
+typedef struct dvo_solver {
+    /* ex-common dvod01 */
+    double acnrm, ccmxj, conp, crate, drc, el[14], eta, etamax, h, hmin, hmxi, hnew,
+           hscal, prl1, rc, rl1, tau[14], tq[6], tn, uround;
+    int icf, init, ipup, jcur, jstart, jsv, kflag, kuth, l, lmax, lyh, lewt, lacor,
+        lsavf, lwm, liwm, locjs, maxord, meth, miter, msbj, mxhnil, mxstep, n, newh,
+        newq, nhnil, nq, nqnyh, nqwait, nslj, nslp, nyh;
+    /* ex-common dvod02 */
+    double hu;
+    int ncfn, netf, nfe, nje, nlu, nni, nqu, nst;
+    /* dvode_t */
+    double etaq, etaqm1;
+    dvo_f_fn f;
+    dvo_jac_fn jac;
+    void *ctx;
+    int last_msg;     /* number of the last xerrwd message (M:3351), 0 if none */
+    int pow_mode;     /* 0 = libm pow (reference semantics); 1 = portable pow (dvo_ppow) */
+} dvo_solver;
+
+/* initialize, M:377-505 (dewset/dvnorm overrides are not part of the oracle) */
+void dvo_initialize(dvo_solver *s, dvo_f_fn f, dvo_jac_fn jac, void *ctx);
+
+/* dvode / solve, M:604-1725.  rwork and iwork are 1-based in the reference;
+ * here the caller passes plain C arrays of length lrw / liw and slot k of the
+ * reference is element [k-1]. */
+void dvo_solve(dvo_solver *s, int neq, double *y, double *t, double tout, int itol,
+               const double *rtol, const double *atol, int itask, int *istate, int iopt,
+               double *rwork, int lrw, int *iwork, int liw, int mf);
+
+/* dvindy, M:1878-1959.  yh = &rwork[20] (rwork(21)), ldyh = nyh. */
+void dvo_dvindy(dvo_solver *s, double t, int k, const double *yh, int ldyh, double *dky,
+                int *iflag);
+
+/* dvsrco, M:3198-3216 */
+void dvo_dvsrco(dvo_solver *s, dvo_solver *sav, int job);
+
+/* LINPACK, LP:46-522 (job = 0 branches), column-major, 1-based pivots. */
+void dvo_dgefa(double *a, int lda, int n, int *ipvt, int *info);
+void dvo_dgesl(const double *a, int lda, int n, const int *ipvt, double *b);
+void dvo_dgbfa(double *abd, int lda, int n, int ml, int mu, int *ipvt, int *info);
+void dvo_dgbsl(const double *abd, int lda, int n, int ml, int mu, const int *ipvt, double *b);
+
+/* x**n for integer n the way gfortran lowers it (__powidf2: binary powering). */
+double dvo_powi(double x, int n);
+/* portable, deterministic x**y (x>0) built from + - * / only; mirrored on the device
+ * by the strict build so that GPU and oracle can be compared bit for bit. */
+double dvo_ppow(double x, double y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,275 @@
+/*
+ * problems.c -- CPU restatement of the reference's test problems, plus the batch
+ * driver that runs one independent oracle solver instance per system.
+ *
+ * TEST INFRASTRUCTURE ONLY (see dvode_oracle.h).
+ *
+ *   problem 0  Robertson kinetics         /root/reference/test/example.f90:79-109
+ *   problem 1  Van der Pol                /root/reference/test/dvdemo.f90:207-228
+ *   problem 2  banded 2-D advection       /root/reference/test/dvdemo.f90:230-274
+ *   problem 3  synthetic 32-species mass-action network (builder-defined, not in
+ *              the reference; tables shared with the device build through
+ *              include/bvode_mech32.h)
+ */
+#include "dvode_oracle.h"
+#include "oracle_batch.h"
+#include "../include/bvode_mech32.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---------------------------------------------------------- Robertson ---- */
+/* par = (k1, k2, k3); reference values 0.04, 1e4, 3e7 (example.f90:87-89) */
+static void rob_f(void *ctx, int neq, double t, const double *y, double *ydot)
+{
+    const double *k = (const double *)ctx;
+    (void)neq; (void)t;
+    ydot[0] = -k[0] * y[0] + k[1] * y[1] * y[2];
+    ydot[2] = k[2] * y[1] * y[1];
+    ydot[1] = -ydot[0] - ydot[2];
+}
+static void rob_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+                    int nrowpd)
+{
+    const double *k = (const double *)ctx;
+    (void)neq; (void)t; (void)ml; (void)mu;
+#define PD(i, j) pd[((i)-1) + ((j)-1) * nrowpd]
+    PD(1, 1) = -k[0];
+    PD(1, 2) = k[1] * y[2];
+    PD(1, 3) = k[1] * y[1];
+    PD(2, 1) = k[0];
+    PD(2, 3) = -PD(1, 3);
+    PD(3, 2) = (2.0 * k[2]) * y[1];
+    PD(2, 2) = -PD(1, 2) - PD(3, 2);
+}
+
+/* -------------------------------------------------------- Van der Pol ---- */
+/* par = (eta), reference value 3 (dvdemo.f90:214,227) */
+static void vdp_f(void *ctx, int neq, double t, const double *y, double *ydot)
+{
+    const double *p = (const double *)ctx;
+    (void)neq; (void)t;
+    ydot[0] = y[1];
+    ydot[1] = p[0] * (1.0 - y[0] * y[0]) * y[1] - y[0];
+}
+static void vdp_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+                    int nrowpd)
+{
+    const double *p = (const double *)ctx;
+    (void)neq; (void)t; (void)ml; (void)mu;
+    PD(1, 1) = 0.0;
+    PD(1, 2) = 1.0;
+    PD(2, 1) = -(2.0 * p[0]) * y[0] * y[1] - 1.0;
+    PD(2, 2) = p[0] * (1.0 - y[0] * y[0]);
+}
+
+/* ---------------------------------------------------- banded advection --- */
+/* par = (alph1, alph2), reference 1, 1; ng = 5 (dvdemo.f90:236-238) */
+#define NG 5
+static void adv_f(void *ctx, int neq, double t, const double *y, double *ydot)
+{
+    const double *p = (const double *)ctx;
+    (void)neq; (void)t;
+    for (int j = 1; j <= NG; j++)
+        for (int i = 1; i <= NG; i++) {
+            int k = i + (j - 1) * NG;
+            double d = -2.0 * y[k - 1];
+            if (i != 1) d = d + y[k - 2] * p[0];
+            if (j != 1) d = d + y[k - NG - 1] * p[1];
+            ydot[k - 1] = d;
+        }
+}
+static void adv_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+                    int nrowpd)
+{
+    const double *p = (const double *)ctx;
+    (void)t; (void)y;
+    int mband = ml + mu + 1, mu1 = mu + 1, mu2 = mu + 2;
+    for (int j = 1; j <= neq; j++) {
+        PD(mu1, j) = -2.0;
+        PD(mu2, j) = p[0];
+        PD(mband, j) = p[1];
+    }
+    for (int j = NG; j <= neq; j += NG) PD(mu2, j) = 0.0;
+}
+
+/* ------------------------------------------- synthetic 32-species network - */
+/* par = 64 rate constants.  ydot_i = sum over the species' entry list, in
+ * reaction order, of sign * rate_r (same order as the device functor). */
+static void mech_f(void *ctx, int neq, double t, const double *y, double *ydot)
+{
+    const double *k = (const double *)ctx;
+    double rate[BVODE_MECH_NR];
+    (void)neq; (void)t;
+    for (int r = 0; r < BVODE_MECH_NR; r++) {
+        double q = k[r] * y[bvode_mech_ra[r]];
+        if (bvode_mech_rb[r] >= 0) q = q * y[bvode_mech_rb[r]];
+        rate[r] = q;
+    }
+    for (int i = 0; i < BVODE_MECH_NS; i++) {
+        double d = 0.0;
+        for (int e = 0; e < BVODE_MECH_MAXE; e++) {
+            int r = bvode_mech_ent_r[i][e];
+            if (r < 0) break;
+            d = d + bvode_mech_ent_s[i][e] * rate[r];
+        }
+        ydot[i] = d;
+    }
+}
+#undef PD
+
+int dvo_problem_info(int problem, int *neq, int *npar)
+{
+    switch (problem) {
+    case 0: *neq = 3; *npar = 3; return 0;
+    case 1: *neq = 2; *npar = 1; return 0;
+    case 2: *neq = NG * NG; *npar = 2; return 0;
+    case 3: *neq = BVODE_MECH_NS; *npar = BVODE_MECH_NR; return 0;
+    default: return -1;
+    }
+}
+
+static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
+{
+    switch (problem) {
+    case 0: *f = rob_f; *jac = rob_jac; return 0;
+    case 1: *f = vdp_f; *jac = vdp_jac; return 0;
+    case 2: *f = adv_f; *jac = adv_jac; return 0;
+    case 3: *f = mech_f; *jac = NULL; return 0;
+    default: return -1;
+    }
+}
+
+void dvo_problem_f(int problem, const double *par, double t, const double *y, double *ydot)
+{
+    dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
+    if (problem_fns(problem, &f, &jac) || dvo_problem_info(problem, &neq, &npar)) return;
+    f((void *)par, neq, t, y, ydot);
+}
+
+/* work array sizes, M:1246-1273 */
+void dvo_work_sizes(int neq, int mf, int ml, int mu, int maxord_in, int *lrw, int *liw)
+{
+    int jsv = mf >= 0 ? 1 : -1, mfa = mf < 0 ? -mf : mf, meth = mfa / 10,
+        miter = mfa - 10 * meth;
+    int maxord = (meth == 1) ? 12 : 5;
+    if (maxord_in > 0 && maxord_in < maxord) maxord = maxord_in;
+    int jco = jsv > 0 ? 1 : 0, lenwm = 0;
+    switch (miter) {
+    case 0: lenwm = 0; break;
+    case 1: case 2: lenwm = 2 + (1 + jco) * neq * neq; break;
+    case 3: lenwm = 2 + neq; break;
+    default: lenwm = 2 + (2 * ml + mu + 1) * neq + jco * (ml + mu + 1) * neq; break;
+    }
+    *lrw = 20 + neq * (maxord + 1) + lenwm + 3 * neq;
+    *liw = (miter == 0 || miter == 3) ? 30 : 30 + neq;
+}
+
+/* One independent solver instance per system, replaying the reference's call
+ * sequence (example.f90:56-66): for each tout, one dvode call with itask as
+ * configured; istate carried between calls; stop at the first negative istate. */
+int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, const double *y0,
+                    double t0, int nout, const double *touts, const double *rtol,
+                    const double *atol, double *y_out, double *t_out, int *istate_out,
+                    double *rstats, int *istats, int nthreads)
+{
+    dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
+    if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
+        return -1;
+    int lrw, liw;
+    dvo_work_sizes(neq, cfg->mf, cfg->ml, cfg->mu, cfg->iopt ? cfg->maxord : 0, &lrw, &liw);
+    if (liw < 30) liw = 30;
+    int fail = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
+        int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
+        double *y = (double *)malloc(sizeof(double) * (size_t)neq);
+        double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int s = 0; s < nsys; s++) {
+            dvo_solver sol;
+            memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
+            dvo_initialize(&sol, f, jac, par);
+            sol.pow_mode = cfg->pow_mode;
+            memset(rwork, 0, sizeof(double) * (size_t)lrw);
+            memset(iwork, 0, sizeof(int) * (size_t)liw);
+            memcpy(y, y0 + (size_t)s * neq, sizeof(double) * (size_t)neq);
+            iwork[0] = cfg->ml;
+            iwork[1] = cfg->mu;
+            if (cfg->iopt) {
+                rwork[4] = cfg->h0; rwork[5] = cfg->hmax; rwork[6] = cfg->hmin;
+                iwork[4] = cfg->maxord; iwork[5] = cfg->mxstep; iwork[6] = cfg->mxhnil;
+            }
+            rwork[0] = cfg->tcrit;
+            double t = t0;
+            int istate = 1;
+            for (int io = 0; io < nout; io++) {
+                if (istate >= 0)
+                    dvo_solve(&sol, neq, y, &t, touts[io], cfg->itol, rtol, atol, cfg->itask,
+                              &istate, cfg->iopt, rwork, lrw, iwork, liw, cfg->mf);
+                size_t o = (size_t)s * nout + io;
+                memcpy(y_out + o * neq, y, sizeof(double) * (size_t)neq);
+                if (t_out) t_out[o] = t;
+                if (istate_out) istate_out[o] = istate;
+                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(double) * 4);
+                if (istats) memcpy(istats + o * 12, iwork + 10, sizeof(int) * 12);
+            }
+            if (istate < 0) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+                fail++;
+            }
+        }
+        free(rwork); free(iwork); free(y); free(par);
+    }
+    return fail;
+}
+
+/* dvindy at user points after the last solve of a single system: convenience
+ * used by the dense-output parity tests.  Integrates system 0 of the batch to
+ * tout with one call, then evaluates derivative order k at each tq. */
+int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const double *y0, double t0,
+                     double tout, const double *rtol, const double *atol, int k, int nq,
+                     const double *tqs, double *dky_out, int *iflag_out, double *tcur,
+                     double *hu)
+{
+    dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
+    if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
+        return -1;
+    int lrw, liw;
+    dvo_work_sizes(neq, cfg->mf, cfg->ml, cfg->mu, cfg->iopt ? cfg->maxord : 0, &lrw, &liw);
+    double *rwork = (double *)calloc((size_t)lrw, sizeof(double));
+    int *iwork = (int *)calloc((size_t)liw, sizeof(int));
+    double *y = (double *)malloc(sizeof(double) * (size_t)neq);
+    double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
+    memcpy(par, par_in, sizeof(double) * (size_t)npar);
+    memcpy(y, y0, sizeof(double) * (size_t)neq);
+    dvo_solver sol;
+    dvo_initialize(&sol, f, jac, par);
+    sol.pow_mode = cfg->pow_mode;
+    iwork[0] = cfg->ml; iwork[1] = cfg->mu;
+    if (cfg->iopt) {
+        rwork[4] = cfg->h0; rwork[5] = cfg->hmax; rwork[6] = cfg->hmin;
+        iwork[4] = cfg->maxord; iwork[5] = cfg->mxstep; iwork[6] = cfg->mxhnil;
+    }
+    double t = t0;
+    int istate = 1;
+    dvo_solve(&sol, neq, y, &t, tout, cfg->itol, rtol, atol, cfg->itask, &istate, cfg->iopt,
+              rwork, lrw, iwork, liw, cfg->mf);
+    if (tcur) *tcur = rwork[12];
+    if (hu) *hu = rwork[10];
+    for (int q = 0; q < nq; q++)
+        dvo_dvindy(&sol, tqs[q], k, rwork + 20, neq, dky_out + (size_t)q * neq, iflag_out + q);
+    free(rwork); free(iwork); free(y); free(par);
+    return istate;
+}

@@ -1,0 +1,119 @@
+"""ctypes wrapper around the CPU oracle (oracle/_build/liboracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(dvode_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
+
+PROBLEMS = {"robertson": 0, "vdp": 1, "advection": 2, "mech32": 3}
+
+
+class BatchCfg(C.Structure):
+    _fields_ = [("problem", C.c_int), ("mf", C.c_int), ("itol", C.c_int), ("itask", C.c_int),
+                ("iopt", C.c_int), ("ml", C.c_int), ("mu", C.c_int), ("maxord", C.c_int),
+                ("mxstep", C.c_int), ("mxhnil", C.c_int), ("h0", C.c_double),
+                ("hmax", C.c_double), ("hmin", C.c_double), ("tcrit", C.c_double),
+                ("pow_mode", C.c_int)]
+
+
+def build(force=False):
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in
+            ("dvode_oracle.c", "problems.c", "dvode_oracle.h", "oracle_batch.h", "Makefile")]
+    srcs.append(os.path.join(_ROOT, "include", "bvode_mech32.h"))
+    stale = force or not os.path.exists(_SO) or any(
+        os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s))
+    if stale:
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        _lib.dvo_batch_solve.restype = C.c_int
+        _lib.dvo_batch_solve.argtypes = [C.POINTER(BatchCfg), C.c_int, dp, dp, C.c_double,
+                                         C.c_int, dp, dp, dp, dp, dp, ip, dp, ip, C.c_int]
+        _lib.dvo_single_dense.restype = C.c_int
+        _lib.dvo_single_dense.argtypes = [C.POINTER(BatchCfg), dp, dp, C.c_double, C.c_double,
+                                          dp, dp, C.c_int, C.c_int, dp, dp, ip, dp, dp]
+        _lib.dvo_problem_info.argtypes = [C.c_int, ip, ip]
+        _lib.dvo_problem_f.argtypes = [C.c_int, dp, C.c_double, dp, dp]
+        _lib.dvo_work_sizes.argtypes = [C.c_int] * 5 + [ip, ip]
+        _lib.dvo_powi.restype = C.c_double
+        _lib.dvo_powi.argtypes = [C.c_double, C.c_int]
+        _lib.dvo_ppow.restype = C.c_double
+        _lib.dvo_ppow.argtypes = [C.c_double, C.c_double]
+        for name in ("dvo_dgefa", "dvo_dgesl", "dvo_dgbfa", "dvo_dgbsl"):
+            getattr(_lib, name).restype = None
+        _lib.dvo_dgefa.argtypes = [dp, C.c_int, C.c_int, ip, ip]
+        _lib.dvo_dgesl.argtypes = [dp, C.c_int, C.c_int, ip, dp]
+        _lib.dvo_dgbfa.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+        _lib.dvo_dgbsl.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, dp]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def problem_info(problem):
+    neq, npar = C.c_int(), C.c_int()
+    assert lib().dvo_problem_info(PROBLEMS[problem], C.byref(neq), C.byref(npar)) == 0
+    return neq.value, npar.value
+
+
+def work_sizes(neq, mf, ml=0, mu=0, maxord=0):
+    lrw, liw = C.c_int(), C.c_int()
+    lib().dvo_work_sizes(neq, mf, ml, mu, maxord, C.byref(lrw), C.byref(liw))
+    return lrw.value, liw.value
+
+
+def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1, iopt=0,
+                ml=0, mu=0, maxord=0, mxstep=0, mxhnil=0, h0=0.0, hmax=0.0, hmin=0.0,
+                tcrit=0.0, pow_mode=0, nthreads=0):
+    """Run the oracle on a batch.  Returns dict(y[nsys,nout,neq], t, istate, rstats, istats)."""
+    neq, npar = problem_info(problem)
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(npar, 1)))
+    nsys = params.shape[0]
+    y0 = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=np.float64), (nsys, neq)))
+    touts = np.ascontiguousarray(np.asarray(touts, dtype=np.float64).reshape(-1))
+    nout = touts.size
+    rtol = np.ascontiguousarray(np.atleast_1d(np.asarray(rtol, dtype=np.float64)))
+    atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=np.float64)))
+    cfg = BatchCfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, mxhnil,
+                   h0, hmax, hmin, tcrit, pow_mode)
+    y = np.zeros((nsys, nout, neq))
+    t = np.zeros((nsys, nout))
+    ist = np.zeros((nsys, nout), dtype=np.int32)
+    rst = np.zeros((nsys, nout, 4))
+    ista = np.zeros((nsys, nout, 12), dtype=np.int32)
+    nfail = lib().dvo_batch_solve(C.byref(cfg), nsys, _dp(params), _dp(y0), float(t0), nout,
+                                  _dp(touts), _dp(rtol), _dp(atol), _dp(y), _dp(t), _ip(ist),
+                                  _dp(rst), _ip(ista), nthreads)
+    assert nfail >= 0
+    return {"y": y, "t": t, "istate": ist, "rstats": rst, "istats": ista, "nfail": nfail}
+
+
+# iwork(11:22) slot names in istats[..., k]
+ISTAT = {"nst": 0, "nfe": 1, "nje": 2, "nqu": 3, "nqcur": 4, "imxer": 5, "lenrw": 6, "leniw": 7,
+         "nlu": 8, "nni": 9, "ncfn": 10, "netf": 11}
+RSTAT = {"hu": 0, "hcur": 1, "tcur": 2, "tolsf": 3}
