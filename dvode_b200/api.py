@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's `dvode_t` type over the C ABI (include/bvode.h).
+
+Reference interface mirrored here (file:line into /root/reference/src/dvode_module.F90):
+    call solver%initialize(f, jac)                                   :377
+    call solver%solve(neq,y,t,tout,itol,rtol,atol,itask,istate,
+                      iopt,rwork,lrw,iwork,liw,mf)                    :604
+    call solver%dvindy(t,k,yh,ldyh,dky,iflag)                        :1878
+    call solver%dvsrco(sav,job)                                      :3198
+Same argument names, meaning and error behaviour (per-system `istate`), for a batch of
+`nsys` independent systems.  Arrays are numpy arrays modified in place, like the Fortran
+intent(inout) arguments.  The f / jac callbacks are __device__ functors compiled into the
+library; `initialize` selects them by problem name.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libbvode.so")
+
+
+class BvodeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bvode error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            "dvode_b200: %s is missing. Build it with `python -m dvode_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    lib.bvode_last_error.restype = C.c_char_p
+    lib.bvode_problem_lookup.argtypes = [C.c_char_p]
+    lib.bvode_problem_info.argtypes = [C.c_int, ip, ip, C.POINTER(C.c_char_p)]
+    lib.bvode_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_uint]
+    lib.bvode_destroy.argtypes = [vp]
+    lib.bvode_destroy.restype = None
+    lib.bvode_set_params.argtypes = [vp, vp]
+    lib.bvode_set_params_device.argtypes = [vp, vp]
+    lib.bvode_solve.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp,
+                                C.c_int, vp, C.c_int, vp, C.c_int, C.c_int]
+    lib.bvode_solve_schedule.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp,
+                                         C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int,
+                                         vp]
+    lib.bvode_solve_schedule_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp,
+                                                C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.bvode_dvindy.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    lib.bvode_get_stats.argtypes = [vp, vp, vp]
+    lib.bvode_state_bytes.argtypes = [vp]
+    lib.bvode_state_bytes.restype = C.c_longlong
+    lib.bvode_dvsrco.argtypes = [vp, vp, C.c_int]
+    lib.bvode_last_launch_count.argtypes = [vp]
+    lib.bvode_measure_fp64_peak.argtypes = [C.c_int, dp]
+    return lib
+
+
+_lib = _load()
+
+FLAG_STRICT = 1
+ISTAT = {"nst": 0, "nfe": 1, "nje": 2, "nqu": 3, "nqcur": 4, "imxer": 5, "lenrw": 6, "leniw": 7,
+         "nlu": 8, "nni": 9, "ncfn": 10, "netf": 11}
+RSTAT = {"hu": 0, "hcur": 1, "tcur": 2, "tolsf": 3}
+
+
+def _check(rc):
+    if rc != 0:
+        raise BvodeError(rc, (_lib.bvode_last_error() or b"").decode())
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def problem_names():
+    out = []
+    for i in range(_lib.bvode_problem_count()):
+        name = C.c_char_p()
+        _lib.bvode_problem_info(i, None, None, C.byref(name))
+        out.append(name.value.decode())
+    return out
+
+
+def problem_info(name):
+    pid = _lib.bvode_problem_lookup(name.encode())
+    if pid < 0:
+        raise BvodeError(-1, "unknown problem %r (have %s)" % (name, problem_names()))
+    neq, npar = C.c_int(), C.c_int()
+    _check(_lib.bvode_problem_info(pid, C.byref(neq), C.byref(npar), None))
+    return pid, neq.value, npar.value
+
+
+def fp64_peak_tflops(device=0):
+    v = C.c_double()
+    _check(_lib.bvode_measure_fp64_peak(device, C.byref(v)))
+    return v.value
+
+
+class dvode_t:
+    """Batched counterpart of the reference's `type(dvode_t)` (M:251-314)."""
+
+    def __init__(self):
+        self._h = None
+        self.nsys = self.neq = self.npar = 0
+
+    # -- initialize(f, jac) -> initialize(problem, nsys, params) ------------------------
+    def initialize(self, problem, nsys, params=None, device=0, strict=False):
+        self.close()
+        pid, self.neq, self.npar = problem_info(problem)
+        h = C.c_void_p()
+        _check(_lib.bvode_create(C.byref(h), pid, int(nsys), int(device),
+                                 FLAG_STRICT if strict else 0))
+        self._h = h
+        self.nsys = int(nsys)
+        self.device = device
+        if params is not None:
+            self.set_params(params)
+        return self
+
+    def set_params(self, params):
+        p = _f64(params, (self.nsys, max(self.npar, 1)))
+        _check(_lib.bvode_set_params(self._h, _ptr(p)))
+
+    def set_params_device(self, ptr):
+        _check(_lib.bvode_set_params_device(self._h, C.c_void_p(ptr)))
+
+    def close(self):
+        if self._h is not None:
+            _lib.bvode_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- solve(neq,y,t,tout,itol,rtol,atol,itask,istate,iopt,rwork,lrw,iwork,liw,mf) ---
+    def solve(self, neq, y, t, tout, itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork,
+              liw, mf):
+        """y[nsys,neq], t[nsys], istate[nsys] (int32) are updated in place.  tout: scalar or
+        array[nsys].  rwork[nsys,lrw] / iwork[nsys,liw] (or None) carry the optional
+        inputs (row 0) and receive the optional outputs (every row)."""
+        self._chk_arrays(y, t, istate, rwork, iwork, lrw, liw)
+        tout = _f64(tout).reshape(-1)
+        per = 1 if tout.size > 1 else 0
+        if per and tout.size != self.nsys:
+            raise BvodeError(-1, "tout must be a scalar or have nsys entries")
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        _check(_lib.bvode_solve(self._h, int(neq), _ptr(y), _ptr(t), _ptr(tout), per, int(itol),
+                                _ptr(rtol), _ptr(atol), int(itask), _ptr(istate), int(iopt),
+                                _ptr(rwork), int(lrw), _ptr(iwork), int(liw), int(mf)))
+
+    def solve_schedule(self, neq, y, t, touts, itol, rtol, atol, itask, istate, iopt, rwork, lrw,
+                       iwork, liw, mf, y_out=None):
+        """The reference's `do iout = 1, nout; call solve(...); tout = ...` loop as one call.
+        y_out[nout,nsys,neq] (optional) receives every output point."""
+        self._chk_arrays(y, t, istate, rwork, iwork, lrw, liw)
+        touts = _f64(touts).reshape(-1)
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        if y_out is not None:
+            assert y_out.dtype == np.float64 and y_out.flags.c_contiguous
+            assert y_out.shape == (touts.size, self.nsys, self.neq)
+        _check(_lib.bvode_solve_schedule(self._h, int(neq), _ptr(y), _ptr(t), touts.size,
+                                         _ptr(touts), int(itol), _ptr(rtol), _ptr(atol),
+                                         int(itask), _ptr(istate), int(iopt), _ptr(rwork),
+                                         int(lrw), _ptr(iwork), int(liw), int(mf), _ptr(y_out)))
+
+    def solve_schedule_device(self, neq, y_ptr, t_ptr, touts, itol, rtol, atol, itask, istate_ptr,
+                              iopt, rwork_opts, iwork_opts, mf, y_out_ptr=0, stream=0):
+        """Device-resident variant: *_ptr are raw device addresses, SoA layout (bvode.h)."""
+        touts = _f64(touts).reshape(-1)
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        _check(_lib.bvode_solve_schedule_device(
+            self._h, int(neq), C.c_void_p(y_ptr), C.c_void_p(t_ptr), touts.size, _ptr(touts),
+            int(itol), _ptr(rtol), _ptr(atol), int(itask), C.c_void_p(istate_ptr), int(iopt),
+            _ptr(rwork_opts), _ptr(iwork_opts), int(mf),
+            C.c_void_p(y_out_ptr) if y_out_ptr else None, C.c_void_p(stream) if stream else None))
+
+    # -- dvindy(t, k, yh, ldyh, dky, iflag): yh/ldyh are the handle's device state -------
+    def dvindy(self, t, k):
+        t = _f64(t).reshape(-1)
+        per = 1 if t.size > 1 else 0
+        dky = np.zeros((self.nsys, self.neq))
+        iflag = np.zeros(self.nsys, dtype=np.int32)
+        _check(_lib.bvode_dvindy(self._h, _ptr(t), per, int(k), _ptr(dky), _ptr(iflag)))
+        return dky, iflag
+
+    # -- dvsrco(sav, job) -------------------------------------------------------------------
+    def dvsrco(self, sav, job):
+        if job == 1:
+            n = _lib.bvode_state_bytes(self._h)
+            sav = np.zeros(n, dtype=np.uint8)
+        _check(_lib.bvode_dvsrco(self._h, _ptr(sav), int(job)))
+        return sav
+
+    def stats(self):
+        """Optional outputs: (rwork(11:14)[nsys,4], iwork(11:22)[nsys,12])."""
+        r = np.zeros((self.nsys, 4))
+        i = np.zeros((self.nsys, 12), dtype=np.int32)
+        _check(_lib.bvode_get_stats(self._h, _ptr(r), _ptr(i)))
+        return r, i
+
+    def last_launch_count(self):
+        return _lib.bvode_last_launch_count(self._h)
+
+    def _chk_arrays(self, y, t, istate, rwork, iwork, lrw, liw):
+        if self._h is None:
+            raise BvodeError(-1, "initialize() has not been called")
+        ok = (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous and
+              y.size == self.nsys * self.neq and isinstance(t, np.ndarray) and
+              t.dtype == np.float64 and t.size == self.nsys and isinstance(istate, np.ndarray) and
+              istate.dtype == np.int32 and istate.size == self.nsys)
+        if rwork is not None:
+            ok = ok and rwork.dtype == np.float64 and rwork.flags.c_contiguous and \
+                rwork.size == self.nsys * lrw
+        if iwork is not None:
+            ok = ok and iwork.dtype == np.int32 and iwork.flags.c_contiguous and \
+                iwork.size == self.nsys * liw
+        if not ok:
+            raise BvodeError(-1, "y/t/istate/rwork/iwork must be contiguous numpy arrays of "
+                                 "float64/float64/int32/float64/int32 with nsys rows")

@@ -1,0 +1,56 @@
+"""Synthetic parameter-perturbed batches.
+
+System i of a batch gets parameters p_j = p0_j * (1 + amp * u_ij) with
+u_ij in [-1, 1) taken from splitmix64(seed + npar*i + j): a pure integer hash, so the
+same batch can be regenerated bit for bit anywhere (host, device, oracle side).
+"""
+import numpy as np
+
+SEED = 20261019
+_M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    """Vectorised splitmix64 finaliser of the uint64 array x (state increment included)."""
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def uniform_pm1(nsys, npar, seed=SEED, first=0):
+    """u[nsys, npar] in [-1, 1): top 53 bits of the hash / 2^53 * 2 - 1."""
+    idx = (np.arange(first, first + nsys, dtype=np.uint64)[:, None] * np.uint64(npar) +
+           np.arange(npar, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        z = splitmix64(idx + np.uint64(seed))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53) * 2.0 - 1.0
+
+
+def perturbed(base, nsys, amp=0.1, seed=SEED, first=0):
+    base = np.asarray(base, dtype=np.float64)
+    return base[None, :] * (1.0 + amp * uniform_pm1(nsys, base.size, seed, first))
+
+
+ROBERTSON_K = (0.04, 1.0e4, 3.0e7)           # example.f90:87-89
+ROBERTSON_Y0 = (1.0, 0.0, 0.0)               # example.f90:38-40
+ROBERTSON_TOUTS = tuple(0.4 * 10.0 ** k for k in range(12))
+
+
+def robertson_touts():
+    """tout = 0.4, then tout = tout*10 eleven times, accumulated like example.f90:66."""
+    t, out = 0.4, []
+    for _ in range(12):
+        out.append(t)
+        t = t * 10.0
+    return np.array(out)
+
+
+def robertson_batch(nsys, amp=0.1, seed=SEED, first=0):
+    return perturbed(ROBERTSON_K, nsys, amp, seed, first)
+
+
+# tolerances: the reference's own (example.f90:44-47) and the tightened headline set
+ROBERTSON_TOL_REF = dict(itol=2, rtol=[1e-4], atol=[1e-8, 1e-14, 1e-6])
+ROBERTSON_TOL_HEADLINE = dict(itol=2, rtol=[1e-6], atol=[1e-10, 1e-16, 1e-8])

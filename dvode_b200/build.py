@@ -1,0 +1,69 @@
+"""Build libbvode.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Two builds of the kernels are linked into one library:
+  fast   : default code generation (FMA contraction), CUDA pow()  -- the product
+  strict : -fmad=false + portable pow                             -- bit-for-bit parity runs
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libbvode.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def _nvcc():
+    nv = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nv):
+        raise RuntimeError("nvcc not found; the bvode kernels cannot be built")
+    return nv
+
+
+def _sources():
+    out = [os.path.join(HERE, "..", "include", "bvode.h"), os.path.join(HERE, "..", "include", "bvode_mech32.h")]
+    for f in sorted(os.listdir(CSRC)):
+        out.append(os.path.join(CSRC, f))
+    return [p for p in out if os.path.exists(p)]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _sources())
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    nv = _nvcc()
+    units = [
+        ("reg_fast.o", "bvode_registry.cu", ["-DBVODE_STRICT=0"]),
+        ("reg_strict.o", "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false"]),
+        ("capi.o", "bvode_capi.cu", []),
+    ]
+    procs = []
+    for obj, src, extra in units:
+        cmd = [nv] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out.decode())
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = [nv] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,585 @@
+// bvode_capi.cu -- the C ABI declared in include/bvode.h: handle management, argument
+// checking (the reference's blocks A and B, M:1073-1303, done once for the batch on the
+// host), host <-> device staging, and kernel dispatch.  No integration arithmetic here.
+#include "../../include/bvode.h"
+#include "bvode_internal.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+extern "C" const ProblemEntry *bvode_registry_fast(int *n);
+extern "C" const ProblemEntry *bvode_registry_strict(int *n);
+
+static thread_local std::string g_err;
+const char *bvode_last_error(void) { return g_err.c_str(); }
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            g_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+            return BVODE_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+struct bvode_solver {
+    int problem = 0, nsys = 0, device = 0, neq = 0, npar = 0;
+    unsigned flags = 0;
+    const ProblemEntry *pe = nullptr;
+    cudaStream_t stream = nullptr;
+    // state (allocated at the first istate = 1 call, when mf / ml / mu are known)
+    int mf = 0, ml = 0, mu = 0, nd = 0, ni = 0;
+    double *d_state = nullptr;
+    int *i_state = nullptr;
+    // batch buffers, SoA on the device
+    double *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
+           *d_rout = nullptr, *d_aos = nullptr, *d_yout = nullptr, *d_tout_ps = nullptr;
+    int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
+    size_t aos_cap = 0, yout_cap = 0;
+    bool params_external = false;
+    int last_launches = 0;
+};
+
+// ---------------------------------------------------------------- small kernels ----
+// host layout [nsys][n]  <->  device layout [n][nsys]
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int nsys,
+                             int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    for (int i = 0; i < n; i++) soa[(size_t)i * nsys + s] = aos[(size_t)s * n + i];
+}
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, int nsys,
+                             int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    for (int i = 0; i < n; i++) aos[(size_t)s * n + i] = soa[(size_t)i * nsys + s];
+}
+__global__ void k_isoa_to_aos(const int *__restrict__ soa, int *__restrict__ aos, int nsys,
+                              int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    for (int i = 0; i < n; i++) aos[(size_t)s * n + i] = soa[(size_t)i * nsys + s];
+}
+// DFMA peak: 8 independent chains per thread, 1024 threads per block, 4 blocks per SM
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
+           a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// -------------------------------------------------------------------- registry ----
+static const ProblemEntry *registry(unsigned flags, int *n) {
+    return (flags & BVODE_FLAG_STRICT) ? bvode_registry_strict(n) : bvode_registry_fast(n);
+}
+int bvode_problem_count(void) {
+    int n;
+    bvode_registry_fast(&n);
+    return n;
+}
+int bvode_problem_lookup(const char *name) {
+    int n;
+    const ProblemEntry *e = bvode_registry_fast(&n);
+    for (int i = 0; i < n; i++)
+        if (strcmp(e[i].name, name) == 0) return i;
+    return -1;
+}
+int bvode_problem_info(int problem, int *neq, int *npar, const char **name) {
+    int n;
+    const ProblemEntry *e = bvode_registry_fast(&n);
+    if (problem < 0 || problem >= n) return BVODE_EINVAL;
+    if (neq) *neq = e[problem].neq;
+    if (npar) *npar = e[problem].npar;
+    if (name) *name = e[problem].name;
+    return BVODE_OK;
+}
+
+// -------------------------------------------------------------------- lifetime ----
+int bvode_create(bvode_solver **out, int problem, int nsys, int device, unsigned flags) {
+    if (!out || nsys <= 0) return BVODE_EINVAL;
+    int n;
+    const ProblemEntry *e = registry(flags, &n);
+    if (problem < 0 || problem >= n) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(device));
+    bvode_solver *s = new bvode_solver();
+    s->problem = problem;
+    s->nsys = nsys;
+    s->device = device;
+    s->flags = flags;
+    s->pe = &e[problem];
+    s->neq = s->pe->neq;
+    s->npar = s->pe->npar;
+    const size_t ns = (size_t)nsys;
+    cudaError_t err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_params, sizeof(double) * ns * (s->npar > 0 ? s->npar : 1));
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_y, sizeof(double) * ns * s->neq);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_t, sizeof(double) * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_tout_ps, sizeof(double) * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_tol, sizeof(double) * 2 * s->neq);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_rout, sizeof(double) * 4 * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_istate, sizeof(int) * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_iout, sizeof(int) * 12 * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_iaos, sizeof(int) * 12 * ns);
+    s->aos_cap = ns * (size_t)(s->neq > s->npar ? s->neq : s->npar);
+    if (s->aos_cap < 4 * ns) s->aos_cap = 4 * ns;
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_aos, sizeof(double) * s->aos_cap);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_rout, 0, sizeof(double) * 4 * ns, s->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_iout, 0, sizeof(int) * 12 * ns, s->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_params, 0, sizeof(double) * ns * (s->npar > 0 ? s->npar : 1), s->stream);
+    if (err != cudaSuccess) {
+        g_err = std::string("bvode_create: ") + cudaGetErrorString(err);
+        bvode_destroy(s);
+        return err == cudaErrorMemoryAllocation ? BVODE_ENOMEM : BVODE_ECUDA;
+    }
+    *out = s;
+    return BVODE_OK;
+}
+
+void bvode_destroy(bvode_solver *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_state); cudaFree(s->i_state);
+    if (!s->params_external) cudaFree(s->d_params);
+    cudaFree(s->d_y); cudaFree(s->d_t); cudaFree(s->d_tol); cudaFree(s->d_rout);
+    cudaFree(s->d_aos); cudaFree(s->d_yout); cudaFree(s->d_tout_ps); cudaFree(s->d_istate);
+    cudaFree(s->d_iout); cudaFree(s->d_iaos);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int bvode_set_params(bvode_solver *s, const double *params) {
+    if (!s || (!params && s->npar > 0)) return BVODE_EINVAL;
+    if (s->npar == 0) return BVODE_OK;
+    if (s->params_external) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t ns = (size_t)s->nsys;
+    CUDA_TRY(cudaMemcpyAsync(s->d_aos, params, sizeof(double) * ns * s->npar, cudaMemcpyHostToDevice, s->stream));
+    k_aos_to_soa<<<cdiv(s->nsys, 256), 256, 0, s->stream>>>(s->d_aos, s->d_params, s->nsys, s->npar);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return BVODE_OK;
+}
+
+int bvode_set_params_device(bvode_solver *s, const double *params_device) {
+    if (!s || !params_device) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemcpyAsync(s->d_params, params_device, sizeof(double) * (size_t)s->nsys * s->npar,
+                             cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return BVODE_OK;
+}
+
+// ------------------------------------------------- argument checks (blocks A, B) ----
+struct Checked {
+    BvOpts o;
+    int lenrw, leniw;
+    std::vector<double> tol;  // rtol[neq] then atol[neq], expanded according to itol
+};
+
+// Work-array lengths the reference would need, M:1246-1273 (reported in iwork(17:18)).
+static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, int *leniw) {
+    const int jsv = mf >= 0 ? 1 : -1, mfa = mf < 0 ? -mf : mf, meth = mfa / 10,
+              miter = mfa - 10 * meth, jco = jsv > 0 ? 1 : 0;
+    int lenwm = 0;
+    switch (miter) {
+    case 0: lenwm = 0; break;
+    case 1: case 2: lenwm = 2 + (1 + jco) * neq * neq; break;
+    case 3: lenwm = 2 + neq; break;
+    default: lenwm = 2 + (2 * ml + mu + 1) * neq + jco * (ml + mu + 1) * neq; break;
+    }
+    *lenrw = 20 + neq * (maxord + 1) + lenwm + 3 * neq;
+    *leniw = (miter == 0 || miter == 3) ? 30 : 30 + neq;
+}
+
+// Returns BVODE_OK, or the error class; mirrors M:1092-1303 for the batch-uniform inputs.
+static int check_args(const bvode_solver *s, int neq, int itol, const double *rtol,
+                      const double *atol, int itask, int iopt, const double *rwork0,
+                      const int *iwork0, int lrw, int liw, bool have_headers, int mf,
+                      Checked *c) {
+    if (neq != s->neq) { g_err = "neq does not match the problem"; return BVODE_EINVAL; }
+    if (itask < 1 || itask > 5) { g_err = "itask illegal"; return BVODE_EINVAL; }
+    if (itask != 1) { g_err = "itask 2-5 not built yet"; return BVODE_ENOTIMPL; }
+    if (itol < 1 || itol > 4) { g_err = "itol illegal"; return BVODE_EINVAL; }
+    if (iopt < 0 || iopt > 1) { g_err = "iopt illegal"; return BVODE_EINVAL; }
+    if (!rtol || !atol) { g_err = "rtol/atol null"; return BVODE_EINVAL; }
+    const int mfa = mf < 0 ? -mf : mf, meth = mfa / 10, miter = mfa - 10 * meth;
+    if (meth < 1 || meth > 2 || miter < 0 || miter > 5) { g_err = "mf illegal"; return BVODE_EINVAL; }
+    int ml = 0, mu = 0;
+    if (miter > 3) {
+        if (!iwork0) { g_err = "band method needs iwork(1:2) = ml, mu"; return BVODE_EINVAL; }
+        ml = iwork0[0];
+        mu = iwork0[1];
+        if (ml < 0 || ml >= neq) { g_err = "ml illegal"; return BVODE_EINVAL; }
+        if (mu < 0 || mu >= neq) { g_err = "mu illegal"; return BVODE_EINVAL; }
+    }
+    if (have_headers && (lrw < 20 || liw < 30)) { g_err = "lrw < 20 or liw < 30"; return BVODE_EINVAL; }
+    if (!s->pe->supports(mf, ml, mu)) {
+        g_err = "this mf (or ml/mu) is not built for this problem";
+        return BVODE_ENOTIMPL;
+    }
+    BvOpts &o = c->o;
+    o.itol = itol;
+    o.ml = ml;
+    o.mu = mu;
+    const int mord = (meth == 1) ? 12 : 5;
+    if (iopt == 1) {
+        if (!rwork0 || !iwork0) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
+        o.maxord = iwork0[4];
+        if (o.maxord < 0) { g_err = "maxord < 0"; return BVODE_EINVAL; }
+        if (o.maxord == 0) o.maxord = 100;
+        if (o.maxord > mord) o.maxord = mord;
+        o.mxstep = iwork0[5];
+        if (o.mxstep < 0) { g_err = "mxstep < 0"; return BVODE_EINVAL; }
+        if (o.mxstep == 0) o.mxstep = 500;
+        o.mxhnil = iwork0[6];
+        if (o.mxhnil < 0) { g_err = "mxhnil < 0"; return BVODE_EINVAL; }
+        if (o.mxhnil == 0) o.mxhnil = 10;
+        o.h0 = rwork0[4];
+        const double hmax = rwork0[5];
+        if (hmax < 0.0) { g_err = "hmax < 0"; return BVODE_EINVAL; }
+        o.hmax_inv = hmax > 0.0 ? 1.0 / hmax : 0.0;
+        o.hmin = rwork0[6];
+        if (o.hmin < 0.0) { g_err = "hmin < 0"; return BVODE_EINVAL; }
+    } else {
+        o.maxord = mord;
+        o.mxstep = 500;
+        o.mxhnil = 10;
+        o.h0 = 0.0;
+        o.hmax_inv = 0.0;
+        o.hmin = 0.0;
+    }
+    c->tol.resize(2 * (size_t)neq);
+    for (int i = 0; i < neq; i++) {
+        const double r = (itol >= 3) ? rtol[i] : rtol[0];
+        const double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        if (r < 0.0) { g_err = "rtol < 0"; return BVODE_EINVAL; }
+        if (a < 0.0) { g_err = "atol < 0"; return BVODE_EINVAL; }
+        c->tol[i] = r;
+        c->tol[neq + i] = a;
+    }
+    work_sizes(neq, mf, ml, mu, o.maxord, &c->lenrw, &c->leniw);
+    return BVODE_OK;
+}
+
+static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
+    if (s->d_state && s->mf == mf && s->ml == ml && s->mu == mu) return BVODE_OK;
+    cudaFree(s->d_state);
+    cudaFree(s->i_state);
+    s->d_state = nullptr;
+    s->i_state = nullptr;
+    s->pe->state_size(mf, &s->nd, &s->ni);
+    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
+    CUDA_TRY(cudaMalloc(&s->d_state, sizeof(double) * ns * s->nd));
+    CUDA_TRY(cudaMalloc(&s->i_state, sizeof(int) * ns * s->ni));
+    CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(double) * ns * s->nd, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->i_state, 0, sizeof(int) * ns * s->ni, s->stream));
+    s->mf = mf;
+    s->ml = ml;
+    s->mu = mu;
+    return BVODE_OK;
+}
+
+// Launch the integration for touts[0..nout) on device-resident SoA buffers.
+static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, double *d_t,
+                      int *d_istate, int nout, const double *touts, const double *d_tout_ps,
+                      double *d_yout, cudaStream_t st) {
+    int rc = ensure_state(s, mf, c.o.ml, c.o.mu);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
+                             cudaMemcpyHostToDevice, st));
+    for (int k0 = 0; k0 < nout; k0 += BVODE_MAX_NOUT) {
+        KArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nsys = s->nsys;
+        a.nout = (nout - k0 < BVODE_MAX_NOUT) ? nout - k0 : BVODE_MAX_NOUT;
+        for (int k = 0; k < a.nout; k++) a.touts[k] = touts[k0 + k];
+        a.tout_ps = d_tout_ps;
+        a.dstate = s->d_state;
+        a.istate_store = s->i_state;
+        a.params = s->d_params;
+        a.y = d_y;
+        a.t = d_t;
+        a.istate = d_istate;
+        a.rtol = s->d_tol;
+        a.atol = s->d_tol + s->neq;
+        a.o = c.o;
+        a.y_out = d_yout ? d_yout + (size_t)k0 * s->neq * s->nsys : nullptr;
+        a.rout = s->d_rout;
+        a.iout = s->d_iout;
+        a.lenrw = c.lenrw;
+        a.leniw = c.leniw;
+        const int e = s->pe->launch(mf, a, st);
+        if (e == -1000) { g_err = "mf not built for this problem"; return BVODE_ENOTIMPL; }
+        if (e != 0) { g_err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e); return BVODE_ECUDA; }
+        s->last_launches++;
+    }
+    return BVODE_OK;
+}
+
+static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
+                      const double *touts, const double *tout_ps, int itol, const double *rtol,
+                      const double *atol, int itask, int *istate, int iopt, double *rwork,
+                      int lrw, int *iwork, int liw, int mf, double *y_out) {
+    if (!s || !y || !t || !istate || nout < 1 || (!touts && !tout_ps)) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int nsys = s->nsys;
+    const size_t ns = (size_t)nsys;
+    s->last_launches = 0;
+    // block A (M:1073-1109): istate legality, per system
+    bool any_first = false;
+    for (int i = 0; i < nsys; i++) {
+        if (istate[i] == 1) any_first = true;
+        else if (istate[i] == 3) { g_err = "istate = 3 not built yet"; return BVODE_ENOTIMPL; }
+        else if (istate[i] < 0) { g_err = "negative istate on input (the reference aborts the run here)"; return BVODE_EISTATE; }
+        else if (istate[i] != 2) { for (int j = 0; j < nsys; j++) istate[j] = -3; g_err = "istate illegal"; return BVODE_EINVAL; }
+    }
+    Checked c;
+    const bool have_headers = rwork && iwork;
+    int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c);
+    if (rc != BVODE_OK) {
+        if (rc == BVODE_EINVAL) for (int j = 0; j < nsys; j++) istate[j] = -3;
+        return rc;
+    }
+    if (!any_first && (s->mf != mf || !s->d_state)) {
+        for (int j = 0; j < nsys; j++) istate[j] = -3;  // M:1102-1106
+        g_err = "istate = 2 but the solver was not initialised with this mf";
+        return BVODE_EINVAL;
+    }
+    cudaStream_t st = s->stream;
+    const int TB = 256;
+    // host -> device.  On continuation calls y and t are outputs only (M:608-618).
+    CUDA_TRY(cudaMemcpyAsync(s->d_istate, istate, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
+    if (any_first) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_aos, y, sizeof(double) * ns * neq, cudaMemcpyHostToDevice, st));
+        k_aos_to_soa<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_aos, s->d_y, nsys, neq);
+        s->last_launches++;
+        CUDA_TRY(cudaMemcpyAsync(s->d_t, t, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    }
+    const double *d_tout_ps = nullptr;
+    if (tout_ps) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, tout_ps, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+        d_tout_ps = s->d_tout_ps;
+    }
+    double *d_yout = nullptr;
+    if (y_out) {
+        const size_t need = ns * neq * nout;
+        if (need > s->yout_cap) {
+            cudaFree(s->d_yout);
+            s->d_yout = nullptr;
+            s->yout_cap = 0;
+            CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(double) * need));
+            s->yout_cap = need;
+        }
+        d_yout = s->d_yout;
+    }
+    double tout1 = 0.0;
+    rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, st);
+    if (rc != BVODE_OK) return rc;
+    // device -> host
+    k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_y, s->d_aos, nsys, neq);
+    s->last_launches++;
+    CUDA_TRY(cudaMemcpyAsync(y, s->d_aos, sizeof(double) * ns * neq, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(t, s->d_t, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(istate, s->d_istate, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
+    if (y_out) {
+        for (int k = 0; k < nout; k++) {
+            CUDA_TRY(cudaStreamSynchronize(st));  // d_aos is reused per output point
+            k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(d_yout + (size_t)k * neq * ns, s->d_aos, nsys, neq);
+            s->last_launches++;
+            CUDA_TRY(cudaMemcpyAsync(y_out + (size_t)k * neq * ns, s->d_aos, sizeof(double) * ns * neq, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (have_headers) {
+        std::vector<double> ro(4 * ns);
+        std::vector<int> io(12 * ns);
+        CUDA_TRY(cudaMemcpy(ro.data(), s->d_rout, sizeof(double) * 4 * ns, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(io.data(), s->d_iout, sizeof(int) * 12 * ns, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ns; i++) {
+            for (int k = 0; k < 4; k++) rwork[i * lrw + 10 + k] = ro[(size_t)k * ns + i];
+            for (int k = 0; k < 12; k++) iwork[i * liw + 10 + k] = io[(size_t)k * ns + i];
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BVODE_OK;
+}
+
+int bvode_solve(bvode_solver *s, int neq, double *y, double *t, const double *tout,
+                int tout_per_system, int itol, const double *rtol, const double *atol, int itask,
+                int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw, int mf) {
+    if (!tout) return BVODE_EINVAL;
+    return solve_host(s, neq, y, t, 1, tout_per_system ? nullptr : tout,
+                      tout_per_system ? tout : nullptr, itol, rtol, atol, itask, istate, iopt,
+                      rwork, lrw, iwork, liw, mf, nullptr);
+}
+
+int bvode_solve_schedule(bvode_solver *s, int neq, double *y, double *t, int nout,
+                         const double *touts, int itol, const double *rtol, const double *atol,
+                         int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork,
+                         int liw, int mf, double *y_out) {
+    return solve_host(s, neq, y, t, nout, touts, nullptr, itol, rtol, atol, itask, istate, iopt,
+                      rwork, lrw, iwork, liw, mf, y_out);
+}
+
+int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, double *t_device,
+                                int nout, const double *touts, int itol, const double *rtol,
+                                const double *atol, int itask, int *istate_device, int iopt,
+                                const double *rwork_opts, const int *iwork_opts, int mf,
+                                double *y_out_device, void *stream) {
+    if (!s || !y_device || !t_device || !istate_device || !touts || nout < 1) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    Checked c;
+    int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, 20, 30,
+                        false, mf, &c);
+    if (rc != BVODE_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    rc = run_device(s, c, mf, y_device, t_device, istate_device, nout, touts, nullptr,
+                    y_out_device, st);
+    if (rc != BVODE_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return BVODE_OK;
+}
+
+int bvode_last_launch_count(const bvode_solver *s) { return s ? s->last_launches : 0; }
+
+int bvode_get_stats(bvode_solver *s, double *rout, int *iout) {
+    if (!s) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t ns = (size_t)s->nsys;
+    const int TB = 256;
+    if (rout) {
+        k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, s->stream>>>(s->d_rout, s->d_aos, s->nsys, 4);
+        CUDA_TRY(cudaMemcpyAsync(rout, s->d_aos, sizeof(double) * 4 * ns, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (iout) {
+        k_isoa_to_aos<<<cdiv(s->nsys, TB), TB, 0, s->stream>>>(s->d_iout, s->d_iaos, s->nsys, 12);
+        CUDA_TRY(cudaMemcpyAsync(iout, s->d_iaos, sizeof(int) * 12 * ns, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return BVODE_OK;
+}
+
+int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, double *dky,
+                 int *iflag) {
+    if (!s || !t || !dky || !iflag) return BVODE_EINVAL;
+    if (!s->d_state) { g_err = "dvindy before any successful solve"; return BVODE_EINVAL; }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t ns = (size_t)s->nsys;
+    const int TB = 256;
+    cudaStream_t st = s->stream;
+    DkyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nsys = s->nsys;
+    a.k = k;
+    if (t_per_system) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, t, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+        a.t_ps = s->d_tout_ps;
+    } else {
+        a.t = t[0];
+    }
+    a.dstate = s->d_state;
+    a.istate_store = s->i_state;
+    // dky goes through d_y-sized scratch: reuse d_yout (allocated on demand)
+    const size_t need = ns * s->neq;
+    if (need > s->yout_cap) {
+        cudaFree(s->d_yout);
+        s->d_yout = nullptr;
+        s->yout_cap = 0;
+        CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(double) * need));
+        s->yout_cap = need;
+    }
+    a.dky = s->d_yout;
+    a.iflag = s->d_iaos;
+    const int e = s->pe->launch_dky(s->mf, a, st);
+    if (e != 0) { g_err = "dvindy kernel launch failed"; return e == -1000 ? BVODE_ENOTIMPL : BVODE_ECUDA; }
+    k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, st>>>(s->d_yout, s->d_aos, s->nsys, s->neq);
+    CUDA_TRY(cudaMemcpyAsync(dky, s->d_aos, sizeof(double) * ns * s->neq, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(iflag, s->d_iaos, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return BVODE_OK;
+}
+
+// ---- dvsrco (M:3198-3216): the whole batch state as one host blob ------------------
+struct SavHeader {
+    int magic, problem, nsys, mf, ml, mu, nd, ni;
+};
+long long bvode_state_bytes(const bvode_solver *s) {
+    if (!s || !s->d_state) return 0;
+    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
+    return (long long)(sizeof(SavHeader) + sizeof(double) * ns * s->nd + sizeof(int) * ns * s->ni +
+                       sizeof(double) * 4 * s->nsys + sizeof(int) * 12 * s->nsys);
+}
+int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
+    if (!s || !sav || (job != 1 && job != 2)) return BVODE_EINVAL;  // M:3212-3213 `error stop`
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    char *p = (char *)sav;
+    if (job == 1) {
+        if (!s->d_state) return BVODE_EINVAL;
+        SavHeader h{0x62766f64, s->problem, s->nsys, s->mf, s->ml, s->mu, s->nd, s->ni};
+        memcpy(p, &h, sizeof(h));
+    } else {
+        SavHeader h;
+        memcpy(&h, p, sizeof(h));
+        if (h.magic != 0x62766f64 || h.problem != s->problem || h.nsys != s->nsys) return BVODE_EINVAL;
+        int rc = ensure_state(s, h.mf, h.ml, h.mu);
+        if (rc) return rc;
+        if (h.nd != s->nd || h.ni != s->ni) return BVODE_EINVAL;
+    }
+    p += sizeof(SavHeader);
+    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
+    const cudaMemcpyKind kind = (job == 1) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    struct { void *d; size_t n; } parts[4] = {
+        {s->d_state, sizeof(double) * ns * s->nd}, {s->i_state, sizeof(int) * ns * s->ni},
+        {s->d_rout, sizeof(double) * 4 * s->nsys}, {s->d_iout, sizeof(int) * 12 * s->nsys}};
+    for (auto &q : parts) {
+        if (job == 1) CUDA_TRY(cudaMemcpy(p, q.d, q.n, kind));
+        else CUDA_TRY(cudaMemcpy(q.d, p, q.n, kind));
+        p += q.n;
+    }
+    return BVODE_OK;
+}
+
+int bvode_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, tpb = 256, iters = 1 << 16;
+    double *out;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * blocks * tpb));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    k_dfma_peak<<<blocks, tpb>>>(out, 1 << 12);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, tpb>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * tpb;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return BVODE_OK;
+}

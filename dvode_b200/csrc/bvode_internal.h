@@ -1,0 +1,54 @@
+// bvode_internal.h -- plain structs shared by the two kernel builds (fast / strict) and the
+// C-ABI layer.  Nothing here is namespaced per build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#define BVODE_MAX_NOUT 16
+
+// Batch-uniform solver options: optional inputs after defaulting (M:729-751, 1174-1238).
+struct BvOpts {
+    double h0, hmax_inv, hmin;   // rwork(5), 1/rwork(6) (0 = no limit), rwork(7)
+    int maxord, mxstep, mxhnil;  // iwork(5:7)
+    int itol;
+    int ml, mu;                  // iwork(1:2) (band problems)
+};
+
+// Arguments of one solve launch.  All pointers are device pointers, SoA layout.
+struct KArgs {
+    int nsys, nout;
+    double touts[BVODE_MAX_NOUT];  // output points of this launch (nout >= 1)
+    const double *tout_ps;         // per-system tout[nsys] (only with nout == 1) or nullptr
+    double *dstate;                // [nd][nsys] persistent real state  (the reference's rwork(21:))
+    int *istate_store;             // [ni][nsys] persistent integer state (iwork(31:) + dvode_data_t)
+    const double *params;          // [npar][nsys]
+    double *y;                     // [neq][nsys] in/out
+    double *t;                     // [nsys] in/out
+    int *istate;                   // [nsys] in/out
+    const double *rtol, *atol;     // [neq] each, already expanded according to itol
+    BvOpts o;
+    double *y_out;                 // [nout][neq][nsys] or nullptr
+    double *rout;                  // [4][nsys]  rwork(11:14)
+    int *iout;                     // [12][nsys] iwork(11:22)
+    int lenrw, leniw;              // iwork(17:18), M:1268-1273
+};
+
+struct DkyArgs {
+    int nsys, k;
+    double t;
+    const double *t_ps;
+    const double *dstate;
+    const int *istate_store;
+    double *dky;  // [neq][nsys]
+    int *iflag;   // [nsys]
+};
+
+struct ProblemEntry {
+    const char *name;
+    int neq, npar;
+    int mode;  // 0 = one system per thread, 1 = one system per warp
+    int (*supports)(int mf, int ml, int mu);
+    void (*state_size)(int mf, int *nd, int *ni);  // slots per system
+    int (*launch)(int mf, const KArgs &a, cudaStream_t st);
+    int (*launch_dky)(int mf, const DkyArgs &a, cudaStream_t st);
+};

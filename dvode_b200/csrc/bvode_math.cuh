@@ -1,0 +1,132 @@
+// bvode_math.cuh -- scalar helpers shared by every kernel of the batched VODE path.
+//
+// Two builds of the same source exist (see build.py):
+//   fast   : default nvcc FP64 code generation (FMA contraction on), CUDA pow().
+//   strict : -fmad=false and the portable pow below, so that every floating-point
+//            operation is individually rounded exactly like the CPU oracle built
+//            with -ffp-contract=off and pow_mode = 1.  The strict build exists to
+//            prove the logic bit for bit; the fast build is the product.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef BVODE_STRICT
+#define BVODE_STRICT 0
+#endif
+
+#if BVODE_STRICT
+#define BVODE_NS bvode_strict
+#else
+#define BVODE_NS bvode_fast
+#endif
+
+#define BV_DEV __device__ __forceinline__
+
+namespace BVODE_NS {
+
+constexpr double kUround = 2.220446049250313e-16;  // epsilon(1.0_real64), M:36
+
+BV_DEV double dmax2(double a, double b) { return a > b ? a : b; }
+BV_DEV double dmin2(double a, double b) { return a < b ? a : b; }
+BV_DEV double dsign(double a, double b) { return copysign(fabs(a), b); }
+
+// x**n for integer n the way gfortran lowers it (libgcc __powidf2), M:1956, M:2287.
+BV_DEV double powi(double x, int m) {
+    unsigned int n = m < 0 ? (unsigned int)(-m) : (unsigned int)m;
+    double y = (n & 1u) ? x : 1.0;
+    while (n >>= 1) {
+        x = x * x;
+        if (n & 1u) y *= x;
+    }
+    return m < 0 ? 1.0 / y : y;
+}
+
+// Portable x**y, x > 0: same operation sequence as dvo_ppow in oracle/dvode_oracle.c.
+// Only meaningful bit for bit when compiled with -fmad=false.
+__device__ __noinline__ double ppow(double x, double y) {
+    if (x == 0.0) return 0.0;
+    if (x == 1.0 || y == 0.0) return 1.0;
+    uint64_t u = (uint64_t)__double_as_longlong(x);
+    int e = (int)((u >> 52) & 0x7ff);
+    if (e == 0) {
+        x = x * 18014398509481984.0;
+        u = (uint64_t)__double_as_longlong(x);
+        e = (int)((u >> 52) & 0x7ff) - 54;
+    }
+    e -= 1023;
+    u = (u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m = __longlong_as_double((long long)u);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    double p = 1.0 / 25.0;
+    p = p * s2 + 1.0 / 23.0;
+    p = p * s2 + 1.0 / 21.0;
+    p = p * s2 + 1.0 / 19.0;
+    p = p * s2 + 1.0 / 17.0;
+    p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0;
+    p = p * s2 + 1.0 / 11.0;
+    p = p * s2 + 1.0 / 9.0;
+    p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0;
+    p = p * s2 + 1.0 / 3.0;
+    double lm = 2.0 * s + (2.0 * s) * (s2 * p);
+    const double ln2_hi = 6.93147180369123816490e-01;
+    const double ln2_lo = 1.90821492927058770002e-10;
+    double ed = (double)e;
+    double lx = (ed * ln2_hi + lm) + ed * ln2_lo;
+    double z = y * lx;
+    if (z > 709.0) return __longlong_as_double(0x7ff0000000000000LL);
+    if (z < -745.0) return 0.0;
+    double kd = z * 1.44269504088896338700e+00;
+    kd = (kd >= 0.0) ? (double)(long long)(kd + 0.5) : (double)(long long)(kd - 0.5);
+    double r = (z - kd * ln2_hi) - kd * ln2_lo;
+    r = r * 0.0625;
+    double q = 1.0 / 3628800.0;
+    q = q * r + 1.0 / 362880.0;
+    q = q * r + 1.0 / 40320.0;
+    q = q * r + 1.0 / 5040.0;
+    q = q * r + 1.0 / 720.0;
+    q = q * r + 1.0 / 120.0;
+    q = q * r + 1.0 / 24.0;
+    q = q * r + 1.0 / 6.0;
+    q = q * r + 0.5;
+    q = q * r + 1.0;
+    q = q * r;
+    q = 2.0 * q + q * q;
+    q = 2.0 * q + q * q;
+    q = 2.0 * q + q * q;
+    q = 2.0 * q + q * q;
+    double er = 1.0 + q;
+    int k = (int)kd;
+    int k1 = k / 2, k2 = k - k1;
+    double t1 = __longlong_as_double((long long)((uint64_t)(k1 + 1023) << 52));
+    double t2 = __longlong_as_double((long long)((uint64_t)(k2 + 1023) << 52));
+    return (er * t1) * t2;
+}
+
+// x**y with real y: the reference calls libm pow through gfortran (M:2201, 2275, 2282, 2292).
+BV_DEV double rpow(double x, double y) {
+#if BVODE_STRICT
+    return ppow(x, y);
+#else
+    return pow(x, y);
+#endif
+}
+
+// 1/(double)k for small k, as correctly rounded constants (same bits as an IEEE divide).
+BV_DEV double recip_int(int k) {
+    switch (k) {
+    case 1: return 1.0;
+    case 2: return 1.0 / 2.0;
+    case 3: return 1.0 / 3.0;
+    case 4: return 1.0 / 4.0;
+    case 5: return 1.0 / 5.0;
+    case 6: return 1.0 / 6.0;
+    case 7: return 1.0 / 7.0;
+    default: return 1.0 / (double)k;
+    }
+}
+
+}  // namespace BVODE_NS

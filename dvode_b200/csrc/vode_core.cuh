@@ -1,0 +1,748 @@
+// vode_core.cuh -- the batched VODE integrator core (device code).
+//
+// One Engine<POL> instance integrates ONE system.  The policy POL decides how the
+// system is mapped onto the machine:
+//   ThreadPolicy (policy_thread.cuh): one system per thread, every vector in registers
+//                                     (tiny systems: Robertson n = 3).
+//   WarpPolicy   (policy_warp.cuh)  : one system per warp, component i on lane i,
+//                                     scalars replicated on all lanes (n <= 32).
+// The scalar control path (step size / order selection, coefficient generation,
+// corrector logic) is written once, here, and is identical for both mappings.
+//
+// What is restated here, from /root/reference/src/dvode_module.F90 (M):
+//   driver blocks C, D (itask = 1), E, F, G      M:1304-1381, 1399-1468, 1496-1623, 1664-1723
+//   dvhin  M:1738-1851      dvindy (k = 0)  M:1878-1952     dvstep  M:1975-2377
+//   dvset  (BDF) M:2440-2490, 2559          dvjust (BDF)    M:2581-2651
+//   dvnlsd (chord) M:2703-2879              dewset/dvnorm   M:3238-3311
+// dvjac / dvsol and the LINPACK factor/solve live in the policies.
+//
+// Design differences from the reference (results are identical operation for operation):
+//  * The Nordsieck array keeps the invariant "columns above L are exactly zero"; the
+//    acor copy that the reference parks in yh(:,lmax) (M:2259, 2298) lives in its own
+//    vector `acsav`.  With that invariant the Pascal-triangle predict / retract, the
+//    rescale, the accept update and dvindy run at full order with no dependence on nq,
+//    so threads of a warp at different orders execute the same instruction stream
+//    (x + 0.0 == x, so the extra operations change nothing).
+//  * dvstep's GOTO retry network (labels 300/400) is one loop whose iteration is one
+//    step attempt; `entry` says where the attempt starts.  All lanes reconverge at the
+//    loop head, and a lane whose system finished simply drops out.
+#pragma once
+#include "bvode_internal.h"
+#include "bvode_math.cuh"
+
+namespace BVODE_NS {
+
+constexpr int kMaxOrdBdf = 5;       // mord(2), M:38
+constexpr int kLmax = kMaxOrdBdf + 1;
+
+// istate / error codes written per system (same integers as the reference, M:832-908)
+enum : int {
+    IST_FIRST = 1, IST_OK = 2,
+    IST_MXSTEP = -1, IST_TOLSF = -2, IST_ILLEGAL = -3, IST_ERRTEST = -4, IST_CONVFAIL = -5,
+    IST_EWT = -6
+};
+
+// Scalar per-system state: the members of dvode_data_t (M:40-153) that are not
+// batch-uniform.  el/tau/tq are 1-based like the reference (element 0 unused).
+struct Ctl {
+    double h, hscal, hnew, hu, eta, etamax, tn, rc, prl1, rl1, crate, drc, acnrm, conp;
+    double tau[kLmax + 1], el[kLmax + 1], tq[6];
+    int nq, L, nqwait, newq, newh, jstart, icf, ipup, jcur, kflag, nslj, nslp, nhnil, init;
+    int nst, nfe, nje, nlu, nni, ncfn, netf, nqu;
+};
+
+using Opts = ::BvOpts;  // batch-uniform optional inputs (M:729-751)
+
+template <int LO, int HI>
+BV_DEV double pick(const double *a, int idx) {
+    double r = a[LO];
+#pragma unroll
+    for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? a[i] : r;
+    return r;
+}
+
+// ---------------------------------------------------------------- dvset (BDF) ----
+// M:2440-2490, 2559.  Loops are unrolled to the compile-time maximum order and guarded
+// by nq, so el/tau stay in registers.
+BV_DEV void dvset_bdf(Ctl &c) {
+    const int nq = c.nq, L = c.L;
+    double *el = c.el, *tau = c.tau, *tq = c.tq;
+    const double h = c.h;
+#pragma unroll
+    for (int i = 3; i <= kLmax; i++) el[i] = 0.0;
+    el[1] = 1.0;
+    el[2] = 1.0;
+    double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
+    if (nq != 1) {
+#pragma unroll
+        for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
+            if (j <= nq - 2) {
+                hsum = hsum + tau[j];
+                rxi = h / hsum;
+                alph0 = alph0 - 1.0 / (double)(j + 1);
+#pragma unroll
+                for (int iback = 1; iback <= j + 1; iback++) {
+                    const int i = (j + 3) - iback;
+                    el[i] = el[i] + el[i - 1] * rxi;
+                }
+            }
+        }
+        alph0 = alph0 - recip_int(nq);
+        rxis = -el[2] - alph0;
+        hsum = hsum + pick<1, kMaxOrdBdf>(tau, nq - 1);
+        rxi = h / hsum;
+        ahatn0 = -el[2] - rxi;
+#pragma unroll
+        for (int i = kLmax; i >= 2; i--) {
+            if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
+        }
+    }
+    const double t1 = 1.0 - ahatn0 + alph0;
+    const double t2 = 1.0 + (double)nq * t1;
+    const double elL = pick<2, kLmax>(el, L);
+    tq[2] = fabs(alph0 * t2 / t1);
+    tq[5] = fabs(t2 / (elL * rxi / rxis));
+    if (c.nqwait == 1) {
+        const double cnqm1 = rxis / elL;
+        const double t3 = alph0 + recip_int(nq);
+        const double t4 = ahatn0 + rxi;
+        double elp = t3 / (1.0 - t4 + t3);
+        tq[1] = fabs(elp / cnqm1);
+        hsum = hsum + pick<1, kLmax>(tau, nq);
+        rxi = h / hsum;
+        const double t5 = alph0 - recip_int(nq + 1);
+        const double t6 = ahatn0 - rxi;
+        elp = t2 / (1.0 - t6 + t5);
+        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
+    }
+    tq[4] = 0.1 * tq[2];
+}
+
+// dvjust coefficient parts (the yh updates are done by the engine).  M:2589-2616, 2629-2643.
+// Returns t1 for the order increase.
+BV_DEV double dvjust_up_coeffs(Ctl &c) {
+    double *el = c.el, *tau = c.tau;
+    const int nq = c.nq;
+#pragma unroll
+    for (int j = 1; j <= kLmax; j++) el[j] = 0.0;
+    el[3] = 1.0;
+    double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0, hsum = c.hscal;
+    if (nq != 1) {
+#pragma unroll
+        for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
+            if (j <= nq - 1) {
+                const int jp1 = j + 1;
+                hsum = hsum + tau[jp1];
+                const double xi = hsum / c.hscal;
+                prod = prod * xi;
+                alph0 = alph0 - 1.0 / (double)jp1;
+                alph1 = alph1 + 1.0 / xi;
+#pragma unroll
+                for (int iback = 1; iback <= jp1; iback++) {
+                    const int i = (j + 4) - iback;
+                    el[i] = el[i] * xiold + el[i - 1];
+                }
+                xiold = xi;
+            }
+        }
+    }
+    return (-alph0 - alph1) / prod;
+}
+
+BV_DEV void dvjust_down_coeffs(Ctl &c) {
+    double *el = c.el, *tau = c.tau;
+    const int nq = c.nq;
+#pragma unroll
+    for (int j = 1; j <= kLmax; j++) el[j] = 0.0;
+    el[3] = 1.0;
+    double hsum = 0.0;
+#pragma unroll
+    for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
+        if (j <= nq - 2) {
+            hsum = hsum + tau[j];
+            const double xi = hsum / c.hscal;
+#pragma unroll
+            for (int iback = 1; iback <= j + 1; iback++) {
+                const int i = (j + 4) - iback;
+                el[i] = el[i] * xi + el[i - 1];
+            }
+        }
+    }
+}
+
+// =================================================================== Engine =====
+// POL provides:
+//   Prob, N (equations), NLOC (vector elements held by this thread),
+//   norm(v, w)                       weighted rms norm over the whole system (M:3295)
+//   all_le_zero(v)                   true if any component of the system is <= 0
+//   f(t, y, ydot, par)               the user's right-hand side
+//   Lin                              linear-algebra state (P = LU, pivots, saved J)
+//   jac_setup(eng, ierpj)            dvjac, M:2897-3104
+//   solve(lin, x)                    dvsol, M:3139-3191
+//   imxer(acor, ewt)                 index of the largest weighted error (M:1694-1706)
+template <class POL>
+struct Engine {
+    using POLICY = POL;
+    using Prob = typename POL::Prob;
+    static constexpr int N = POL::N;
+    static constexpr int NLOC = POL::NLOC;
+    static constexpr int MITER = POL::MITER;
+
+    Ctl c;
+    double yh[kLmax][NLOC];  // Nordsieck history, column j = h^j y^(j) / j!
+    double acsav[NLOC];      // the reference's yh(:,lmax) scratch use (M:2259, 2298)
+    double ewt[NLOC];        // stored inverted (M:1359, 1522)
+    double savf[NLOC], acor[NLOC], y[NLOC];
+    double rtol[NLOC], atol[NLOC];
+    double par[Prob::NPAR > 0 ? Prob::NPAR : 1];
+    typename POL::Lin lin;
+    Opts o;
+
+    // ---- small vector helpers --------------------------------------------------
+    BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
+        double e[NLOC];
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) e[i] = rtol[i] * fabs(yh[0][i]) + atol[i];
+        bad = POL::any_le_zero(e);
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) ewt[i] = 1.0 / e[i];
+    }
+
+    BV_DEV void predict() {  // M:2148-2154 at full order (zero-column invariant)
+#pragma unroll
+        for (int jb = 1; jb <= kMaxOrdBdf; jb++) {
+#pragma unroll
+            for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + yh[j][i];
+            }
+        }
+    }
+    BV_DEV void retract() {  // M:2181-2187, 2342-2348
+#pragma unroll
+        for (int jb = 1; jb <= kMaxOrdBdf; jb++) {
+#pragma unroll
+            for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] - yh[j][i];
+            }
+        }
+    }
+    BV_DEV void rescale() {  // label 300, M:2131-2139
+        double r = 1.0;
+#pragma unroll
+        for (int j = 2; j <= kLmax; j++) {
+            r = r * c.eta;
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) yh[j - 1][i] = r * yh[j - 1][i];
+        }
+        c.h = c.hscal * c.eta;
+        c.hscal = c.h;
+        c.rc = c.rc * c.eta;
+    }
+    // column `col` (1-based) of yh selected at run time
+    BV_DEV void get_col(int col, double (&out)[NLOC]) const {
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) out[i] = yh[0][i];
+#pragma unroll
+        for (int j = 2; j <= kLmax; j++) {
+            if (col == j) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) out[i] = yh[j - 1][i];
+            }
+        }
+    }
+
+    BV_DEV void order_down() {  // dvjust(iord = -1), M:2581, 2628-2650 (+ zero the freed column)
+        if (c.nq != 2) {
+            dvjust_down_coeffs(c);
+            double top[NLOC];
+            get_col(c.L, top);
+#pragma unroll
+            for (int j = 3; j <= kMaxOrdBdf; j++) {
+                if (j <= c.nq) {
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] - top[i] * c.el[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 3; j <= kLmax; j++) {
+            if (j == c.L) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = 0.0;
+            }
+        }
+    }
+    BV_DEV void order_up() {  // dvjust(iord = +1), M:2589-2626
+        const double t1 = dvjust_up_coeffs(c);
+        double newcol[NLOC];
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) newcol[i] = t1 * acsav[i];
+#pragma unroll
+        for (int j = 3; j <= kLmax; j++) {
+            if (j == c.L + 1) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = newcol[i];
+            }
+        }
+#pragma unroll
+        for (int j = 3; j <= kMaxOrdBdf; j++) {
+            if (j <= c.nq + 1) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * newcol[i];
+            }
+        }
+    }
+
+    // ---- dvindy, k = 0 (M:1905-1952).  iflag as in the reference. ----------------
+    BV_DEV int dvindy0(double t, double (&dky)[NLOC]) const {
+        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(c.hu), c.hu);
+        const double tp = c.tn - c.hu - tfuzz;
+        const double tn1 = c.tn + tfuzz;
+        if ((t - tp) * (t - tn1) > 0.0) return -2;
+        const double s = (t - c.tn) / c.h;
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) dky[i] = yh[kLmax - 1][i];
+#pragma unroll
+        for (int j = kLmax - 2; j >= 0; j--) {
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) dky[i] = yh[j][i] + s * dky[i];
+        }
+        return 0;
+    }
+
+    // ---- dvhin (M:1738-1851).  y0 = yh[0], ydot = yh[1]; scratch y, acor. ---------
+    BV_DEV int dvhin(double t0, double tout, double &h0, int &niter) {
+        niter = 0;
+        const double tdist = fabs(tout - t0);
+        const double tround = kUround * dmax2(fabs(t0), fabs(tout));
+        if (tdist < 2.0 * tround) return -1;
+        const double hlb = 100.0 * tround;
+        double hub = 0.1 * tdist;
+        hub = POL::hin_upper_bound(hub, yh[0], yh[1], atol);
+        int iter = 0;
+        double hg = sqrt(hlb * hub);
+        if (hub < hlb) {
+            h0 = hg;
+        } else {
+            double hnew;
+            for (;;) {
+                const double h = dsign(hg, tout - t0);
+                const double t1 = t0 + h;
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + h * yh[1][i];
+                POL::f(t1, y, acor, par);
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) acor[i] = (acor[i] - yh[1][i]) / h;
+                const double yddnrm = POL::norm(acor, ewt);
+                if (yddnrm * hub * hub > 2.0) hnew = sqrt(2.0 / yddnrm);
+                else hnew = sqrt(hg * hub);
+                iter = iter + 1;
+                if (iter < 4) {
+                    const double hrat = hnew / hg;
+                    if ((hrat <= 0.5) || (hrat >= 2.0)) {
+                        if ((iter >= 2) && (hnew > 2.0 * hg)) { hnew = hg; break; }
+                        hg = hnew;
+                        continue;
+                    }
+                }
+                break;
+            }
+            h0 = hnew * 0.5;
+            if (h0 < hlb) h0 = hlb;
+            if (h0 > hub) h0 = hub;
+        }
+        h0 = dsign(h0, tout - t0);
+        niter = iter;
+        return 0;
+    }
+
+    // ---- block C: first call for the problem (M:1312-1381) -----------------------
+    // y[] holds the initial values on entry.  Returns 0 or a negative istate.
+    BV_DEV int init_problem(double t, double tout) {
+        c.tn = t;
+        c.jstart = 0;
+        c.nhnil = 0;
+        c.nst = c.nje = c.nni = c.ncfn = c.netf = c.nlu = 0;
+        c.nslj = 0;
+        c.hu = 0.0;
+        c.nqu = 0;
+        c.init = 0;
+        c.icf = 0; c.ipup = 0; c.jcur = 0; c.kflag = 0; c.nslp = 0; c.newh = 0; c.newq = 0;
+        c.eta = 0.0; c.hnew = 0.0; c.conp = 0.0; c.crate = 0.0; c.drc = 0.0; c.acnrm = 0.0;
+        c.rl1 = 0.0; c.etamax = 0.0;
+#pragma unroll
+        for (int j = 0; j <= kLmax; j++) { c.tau[j] = 0.0; c.el[j] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < 6; j++) c.tq[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < kLmax; j++) {
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) yh[j][i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) { acsav[i] = 0.0; acor[i] = 0.0; savf[i] = 0.0; }
+        POL::lin_init(lin);
+        POL::f(t, y, yh[1], par);
+        c.nfe = 1;
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) yh[0][i] = y[i];
+        c.nq = 1;
+        c.L = 2;
+        c.h = 1.0;
+        bool bad;
+        dewset_invert(bad);
+        if (bad) return IST_ILLEGAL;  // message 21
+        double h0 = o.h0;
+        if (h0 == 0.0) {
+            int niter;
+            const int ier = dvhin(t, tout, h0, niter);
+            c.nfe = c.nfe + niter;
+            if (ier != 0) return IST_ILLEGAL;  // message 22
+        }
+        const double rh = fabs(h0) * o.hmax_inv;
+        if (rh > 1.0) h0 = h0 / rh;
+        c.h = h0;
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) yh[1][i] = h0 * yh[1][i];
+        return 0;
+    }
+
+    // ---- dvnlsd, chord iteration (M:2703-2879) -------------------------------------
+    BV_DEV int dvnlsd(int nflag) {
+        constexpr int maxcor = 3, msbp = 20;
+        constexpr double ccmax = 0.3, crdown = 0.3, rdiv = 2.0;
+        if (c.jstart == 0) c.nslp = 0;
+        if (nflag == 0) c.icf = 0;
+        if (nflag == -2) c.ipup = MITER;
+        if (c.jstart == 0) c.ipup = MITER;
+        c.drc = fabs(c.rc - 1.0);
+        if (c.drc > ccmax || c.nst >= c.nslp + msbp) c.ipup = MITER;
+
+        for (;;) {  // corrector passes
+            int m = 0;
+            double delp = 0.0, del = 0.0;
+            bool converged = false, singular = false;
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) y[i] = yh[0][i];
+            POL::f(c.tn, y, savf, par);
+            c.nfe = c.nfe + 1;
+            if (c.ipup > 0) {
+                int ierpj;
+                POL::jac_setup(*this, ierpj);
+                c.ipup = 0;
+                c.rc = 1.0;
+                c.drc = 0.0;
+                c.crate = 1.0;
+                c.nslp = c.nst;
+                singular = (ierpj != 0);
+            }
+            if (!singular) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
+                for (;;) {
+                    const double rl1h = c.rl1 * c.h;
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++)
+                        y[i] = rl1h * savf[i] - (c.rl1 * yh[1][i] + acor[i]);
+                    POL::solve(lin, y);
+                    c.nni = c.nni + 1;
+                    if (c.rc != 1.0) {
+                        const double cscale = 2.0 / (1.0 + c.rc);
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
+                    }
+                    del = POL::norm(y, ewt);
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) acor[i] = acor[i] + y[i];
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + acor[i];
+                    if (m != 0) c.crate = dmax2(crdown * c.crate, del / delp);
+                    const double dcon = del * dmin2(1.0, c.crate) / c.tq[4];
+                    if (dcon <= 1.0) { converged = true; break; }
+                    m = m + 1;
+                    if (m == maxcor) break;
+                    if (!(m < 2 || del <= rdiv * delp)) break;
+                    delp = del;
+                    POL::f(c.tn, y, savf, par);
+                    c.nfe = c.nfe + 1;
+                }
+            }
+            if (converged) {
+                c.jcur = 0;
+                c.icf = 0;
+                c.acnrm = (m == 0) ? del : POL::norm(acor, ewt);
+                return 0;
+            }
+            if (!singular && c.jcur != 1) {
+                c.icf = 1;
+                c.ipup = MITER;
+                continue;
+            }
+            break;
+        }
+        c.icf = 2;
+        c.ipup = MITER;
+        return -1;
+    }
+
+    // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
+    // Integrates until tout is passed (itask = 1), then interpolates into y.
+    // `first` is true on the call that also ran init_problem (goto 200, M:1381).
+    // Returns the output istate; t_out receives the output t.
+    BV_DEV int advance(double tout, bool first, double &t_out) {
+        constexpr int kfc = -3, kfh = -7, mxncf = 10;
+        constexpr double addon = 1.0e-6, bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
+                         etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
+                         etamx3 = 10.0, onepsm = 1.00001, thresh = 1.5;
+        enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2 };
+
+        const int nslast = c.nst;  // M:1399 (and 1337 on the first call)
+        if (!first) {
+            // block D, itask = 1 (M:1457-1467)
+            if (!((c.tn - tout) * c.h < 0.0)) {
+                const int iflag = dvindy0(tout, y);
+                if (iflag != 0) return IST_ILLEGAL;  // message 27
+                t_out = tout;
+                return IST_OK;
+            }
+        }
+
+        int entry = E_NEWSTEP;
+        bool skip_ewt = first;
+        double told = c.tn;
+        int ncf = 0, nflag = 0;
+        int istate = 0;
+
+        while (istate == 0) {
+            if (entry == E_NEWSTEP) {
+                // ---- label 100 / 200, M:1496-1543
+                if (!skip_ewt) {
+                    if ((c.nst - nslast) >= o.mxstep) { istate = IST_MXSTEP; break; }
+                    bool bad;
+                    dewset_invert(bad);
+                    if (bad) { istate = IST_EWT; break; }
+                }
+                skip_ewt = false;
+                const double tolsf = kUround * POL::norm(yh[0], ewt);
+                if (tolsf > 1.0) { istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF; break; }
+                if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
+                // ---- dvstep prologue, M:2024-2128
+                c.kflag = 0;
+                told = c.tn;
+                ncf = 0;
+                c.jcur = 0;
+                nflag = 0;
+                if (c.jstart == 0) {
+                    c.nq = 1;
+                    c.L = 2;
+                    c.tau[1] = c.h;
+                    c.prl1 = 1.0;
+                    c.rc = 0.0;
+                    c.etamax = etamx1;
+                    c.nqwait = 2;
+                    c.hscal = c.h;
+                    entry = E_PREDICT;
+                } else if (c.newh == 0) {
+                    entry = E_PREDICT;
+                } else {
+                    if (c.newq < c.nq) {
+                        order_down();
+                        c.nq = c.newq;
+                        c.L = c.nq + 1;
+                        c.nqwait = c.L;
+                    } else if (c.newq > c.nq) {
+                        order_up();
+                        c.nq = c.newq;
+                        c.L = c.nq + 1;
+                        c.nqwait = c.L;
+                    }
+                    entry = E_RESCALE;
+                }
+            }
+            if (entry == E_RESCALE) rescale();
+
+            // ---- label 400: predict, coefficients (M:2147-2158)
+            c.tn = c.tn + c.h;
+            predict();
+            dvset_bdf(c);
+            c.rl1 = 1.0 / c.el[2];
+            c.rc = c.rc * (c.rl1 / c.prl1);
+            c.prl1 = c.rl1;
+
+            nflag = dvnlsd(nflag);
+
+            if (nflag == 0) {
+                const double dsm = c.acnrm / c.tq[2];
+                if (dsm > 1.0) {
+                    // ---- error test failed (M:2177-2237)
+                    c.kflag = c.kflag - 1;
+                    c.netf = c.netf + 1;
+                    nflag = -2;
+                    c.tn = told;
+                    retract();
+                    if (fabs(c.h) <= o.hmin * onepsm) {
+                        c.kflag = -1;
+                        c.jstart = 1;
+                        istate = IST_ERRTEST;
+                    } else {
+                        c.etamax = 1.0;
+                        if (c.kflag > kfc) {
+                            c.eta = 1.0 / (rpow(bias2 * dsm, recip_int(c.L)) + addon);
+                            c.eta = dmax2(dmax2(c.eta, o.hmin / fabs(c.h)), etamin);
+                            if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
+                            entry = E_RESCALE;
+                        } else if (c.kflag == kfh) {
+                            c.kflag = -1;
+                            c.jstart = 1;
+                            istate = IST_ERRTEST;
+                        } else if (c.nq == 1) {
+                            c.eta = dmax2(etamin, o.hmin / fabs(c.h));
+                            c.h = c.h * c.eta;
+                            c.hscal = c.h;
+                            c.tau[1] = c.h;
+                            POL::f(c.tn, y, savf, par);
+                            c.nfe = c.nfe + 1;
+#pragma unroll
+                            for (int i = 0; i < NLOC; i++) yh[1][i] = c.h * savf[i];
+                            c.nqwait = 10;
+                            entry = E_PREDICT;
+                        } else {
+                            c.eta = dmax2(etamin, o.hmin / fabs(c.h));
+                            order_down();
+                            c.L = c.nq;
+                            c.nq = c.nq - 1;
+                            c.nqwait = c.L;
+                            entry = E_RESCALE;
+                        }
+                    }
+                } else {
+                    // ---- successful step (M:2245-2330, 2370-2375)
+                    c.kflag = 0;
+                    c.nst = c.nst + 1;
+                    c.hu = c.h;
+                    c.nqu = c.nq;
+#pragma unroll
+                    for (int i = kLmax; i >= 2; i--) {
+                        if (i <= c.nq + 1) c.tau[i] = c.tau[i - 1];
+                    }
+                    c.tau[1] = c.h;
+#pragma unroll
+                    for (int j = 1; j <= kLmax; j++) {
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * acor[i];
+                    }
+                    c.nqwait = c.nqwait - 1;
+                    if ((c.L != o.maxord + 1) && (c.nqwait == 1)) {
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) acsav[i] = acor[i];
+                        c.conp = c.tq[5];
+                    }
+                    if (c.etamax != 1.0) {
+                        const double etaq = 1.0 / (rpow(bias2 * dsm, recip_int(c.L)) + addon);
+                        bool decided = false;
+                        if (c.nqwait == 0) {
+                            c.nqwait = 2;
+                            double etaqm1 = 0.0;
+                            if (c.nq != 1) {
+                                double top[NLOC];
+                                get_col(c.L, top);
+                                const double ddn = POL::norm(top, ewt) / c.tq[1];
+                                etaqm1 = 1.0 / (rpow(bias1 * ddn, recip_int(c.L - 1)) + addon);
+                            }
+                            double etaqp1 = 0.0;
+                            if (c.L != o.maxord + 1) {
+                                const double cnquot =
+                                    (c.tq[5] / c.conp) * powi(c.h / c.tau[2], c.L);
+#pragma unroll
+                                for (int i = 0; i < NLOC; i++) savf[i] = acor[i] - cnquot * acsav[i];
+                                const double dup = POL::norm(savf, ewt) / c.tq[3];
+                                etaqp1 = 1.0 / (rpow(bias3 * dup, recip_int(c.L + 1)) + addon);
+                            }
+                            if (etaq < etaqp1) {
+                                if (etaqp1 <= etaqm1) {
+                                    c.eta = etaqm1;  // label 420
+                                    c.newq = c.nq - 1;
+                                } else {
+                                    c.eta = etaqp1;
+                                    c.newq = c.nq + 1;
+#pragma unroll
+                                    for (int i = 0; i < NLOC; i++) acsav[i] = acor[i];
+                                }
+                                decided = true;
+                            } else if (etaq < etaqm1) {
+                                c.eta = etaqm1;  // label 420
+                                c.newq = c.nq - 1;
+                                decided = true;
+                            }
+                        }
+                        if (!decided) {
+                            c.eta = etaq;
+                            c.newq = c.nq;
+                        }
+                        // label 450, M:2320-2330
+                        if (c.eta < thresh || c.etamax == 1.0) {
+                            c.newq = c.nq;
+                            c.newh = 0;
+                            c.eta = 1.0;
+                            c.hnew = c.h;
+                        } else {
+                            c.eta = dmin2(c.eta, c.etamax);
+                            c.eta = c.eta / dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
+                            c.newh = 1;
+                            c.hnew = c.h * c.eta;
+                        }
+                    } else {
+                        if (c.nqwait < 2) c.nqwait = 2;
+                        c.newq = c.nq;
+                        c.newh = 0;
+                        c.eta = 1.0;
+                        c.hnew = c.h;
+                    }
+                    // label 500
+                    c.etamax = etamx3;
+                    if (c.nst <= 10) c.etamax = etamx2;
+                    {
+                        const double r = 1.0 / c.tq[2];
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) acor[i] = r * acor[i];
+                    }
+                    c.jstart = 1;
+                    // ---- block F, itask = 1 (M:1586-1622)
+                    c.init = 1;
+                    if ((c.tn - tout) * c.h < 0.0) {
+                        entry = E_NEWSTEP;
+                    } else {
+                        dvindy0(tout, y);
+                        t_out = tout;
+                        return IST_OK;
+                    }
+                }
+            } else {
+                // ---- corrector failed to converge (M:2338-2367)
+                ncf = ncf + 1;
+                c.ncfn = c.ncfn + 1;
+                c.etamax = 1.0;
+                c.tn = told;
+                retract();
+                if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
+                    c.kflag = -2;
+                    c.jstart = 1;
+                    istate = IST_CONVFAIL;
+                } else {
+                    c.eta = dmax2(etacf, o.hmin / fabs(c.h));
+                    nflag = -1;
+                    entry = E_RESCALE;
+                }
+            }
+        }
+        // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) y[i] = yh[0][i];
+        t_out = c.tn;
+        return istate;
+    }
+};
+
+}  // namespace BVODE_NS

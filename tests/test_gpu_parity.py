@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * strict build (-fmad=false, portable pow) vs oracle(pow_mode=1): bit-for-bit -- every
+    output value and every counter of every system identical.
+  * fast build (the product) vs oracle (libm pow, the reference's arithmetic): every output
+    within 10x the rtol/atol-weighted error, and sum(nst), sum(nfe), sum(nje), sum(nlu)
+    over the batch within +-2 %.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _B():
+    import dvode_b200 as B
+    return B
+
+
+def gpu_schedule(problem, params, y0, t0, touts, rtol, atol, mf, itol, strict=False, iopt=0,
+                 rwork_opts=None, iwork_opts=None, per_call=False):
+    """Run a batch on the GPU; returns dict like oracle_lib.batch_solve."""
+    B = _B()
+    params = np.asarray(params, dtype=np.float64)
+    nsys = params.shape[0]
+    s = B.dvode_t().initialize(problem, nsys, params, strict=strict)
+    neq = s.neq
+    y = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=np.float64), (nsys, neq))).copy()
+    t = np.full(nsys, float(t0))
+    istate = np.ones(nsys, dtype=np.int32)
+    lrw, liw = 20, 30
+    rwork = np.zeros((nsys, lrw))
+    iwork = np.zeros((nsys, liw), dtype=np.int32)
+    if rwork_opts is not None:
+        rwork[0, :] = rwork_opts
+    if iwork_opts is not None:
+        iwork[0, :] = iwork_opts
+    touts = np.asarray(touts, dtype=np.float64)
+    nout = touts.size
+    yo = np.zeros((nout, nsys, neq))
+    to = np.zeros((nsys, nout))
+    isto = np.zeros((nsys, nout), dtype=np.int32)
+    rst = np.zeros((nsys, nout, 4))
+    ist = np.zeros((nsys, nout, 12), dtype=np.int32)
+    if per_call:
+        for k in range(nout):
+            if (istate > 0).all():
+                s.solve(neq, y, t, touts[k], itol, rtol, atol, 1, istate, iopt, rwork, lrw, iwork,
+                        liw, mf)
+            yo[k] = y
+            to[:, k] = t
+            isto[:, k] = istate
+            rst[:, k] = rwork[:, 10:14]
+            ist[:, k] = iwork[:, 10:22]
+    else:
+        s.solve_schedule(neq, y, t, touts, itol, rtol, atol, 1, istate, iopt, rwork, lrw, iwork,
+                         liw, mf, yo)
+        to[:, -1] = t
+        isto[:, -1] = istate
+        rst[:, -1] = rwork[:, 10:14]
+        ist[:, -1] = iwork[:, 10:22]
+    out = {"y": np.ascontiguousarray(yo.transpose(1, 0, 2)), "t": to, "istate": isto,
+           "rstats": rst, "istats": ist, "solver": s}
+    return out
+
+
+def weighted_err(y, yref, rtol, atol):
+    rtol = np.asarray(rtol, dtype=np.float64)
+    atol = np.asarray(atol, dtype=np.float64)
+    return np.abs(y - yref) / (rtol * np.abs(yref) + atol)
+
+
+ROB = dict(y0=[1.0, 0.0, 0.0], t0=0.0)
+
+
+def rob_touts():
+    return _B().batches.robertson_touts()
+
+
+@pytest.mark.parametrize("mf", [21, 22, -21, -22])
+def test_robertson_strict_bit_exact(mf):
+    B = _B()
+    nsys = 512
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    ref = O.batch_solve("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"],
+                        mf, itol=2, pow_mode=1)
+    got = gpu_schedule("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"],
+                       mf, 2, strict=True)
+    assert (got["istate"][:, -1] == 2).all()
+    assert np.array_equal(got["y"], ref["y"])
+    assert np.array_equal(got["istats"][:, -1], ref["istats"][:, -1])
+    assert np.array_equal(got["rstats"][:, -1], ref["rstats"][:, -1])
+
+
+def test_robertson_per_call_equals_schedule_and_oracle_per_decade():
+    """12 bvode_solve calls (the reference's loop) == one schedule call == oracle, including
+    the optional outputs after every call."""
+    B = _B()
+    nsys = 256
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    ref = O.batch_solve("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"],
+                        21, itol=2, pow_mode=1)
+    a = gpu_schedule("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"], 21,
+                     2, strict=True, per_call=True)
+    b = gpu_schedule("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"], 21,
+                     2, strict=True, per_call=False)
+    assert np.array_equal(a["y"], b["y"])
+    assert np.array_equal(a["y"], ref["y"])
+    assert np.array_equal(a["t"], ref["t"])
+    assert np.array_equal(a["istate"], ref["istate"])
+    assert np.array_equal(a["istats"], ref["istats"])
+    assert np.array_equal(a["rstats"], ref["rstats"])
+
+
+@pytest.mark.parametrize("tolname", ["ROBERTSON_TOL_REF", "ROBERTSON_TOL_HEADLINE"])
+def test_robertson_fast_parity(tolname):
+    B = _B()
+    nsys = 4096
+    par = B.batches.robertson_batch(nsys)
+    tol = getattr(B.batches, tolname)
+    ref = O.batch_solve("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"],
+                        21, itol=2, pow_mode=0)
+    got = gpu_schedule("robertson", par, ROB["y0"], 0.0, rob_touts(), tol["rtol"], tol["atol"],
+                       21, 2, strict=False)
+    assert (ref["istate"] == 2).all()
+    assert (got["istate"][:, -1] == 2).all()
+    # values: within 10 x the rtol-weighted error at every output point of every system
+    werr = weighted_err(got["y"], ref["y"], tol["rtol"], tol["atol"])
+    assert werr.max() <= 10.0, werr.max()
+    # counters: batch aggregates within +-2 %
+    for name in ("nst", "nfe", "nje", "nlu", "nni"):
+        a = got["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        b = ref["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        assert abs(a - b) <= 0.02 * b, (name, a, b)
+    # invariant: mass conservation
+    assert np.abs(got["y"].sum(axis=2) - 1.0).max() < 1e-3
+
+
+with open(os.path.join(GOLD, "dvdemo_golden.json")) as _fh:
+    _DV = json.load(_fh)
+
+
+def _fmt_d(x, d):
+    if x == 0.0:
+        return "0." + "0" * d + "D+00"
+    s = "%.*e" % (d - 1, abs(x))
+    mant, ex = s.split("e")
+    e = int(ex) + 1
+    return "%s0.%sD%s%02d" % ("-" if x < 0 else "", mant.replace(".", ""), "+" if e >= 0 else "-",
+                              abs(e))
+
+
+@pytest.mark.parametrize("mf", [21, 22, -21, -22])
+def test_vdp_golden_transcript_on_gpu(mf):
+    """The reference's own golden transcript (dvdemo.txt, Van der Pol, dense chord path)
+    replayed on the GPU with the reference's call sequence (4 solve calls)."""
+    run = [r for r in _DV["runs"] if r["problem"] == 1 and r["mf"] == mf][0]
+    touts = [1.39283880203]
+    for _ in range(3):
+        touts.append(touts[-1] + 2.214773875)
+    for strict in (True, False):
+        g = gpu_schedule("vdp", [[3.0]], [2.0, 0.0], 0.0, touts, [0.0], [1e-6], mf, 1,
+                         strict=strict, per_call=True)
+        st = {k: int(g["istats"][0, -1, O.ISTAT[k]]) for k in
+              ("lenrw", "leniw", "nst", "nfe", "nje", "nlu", "nni", "ncfn", "netf")}
+        gold = {k: run["stats"][k] for k in st}
+        rows = []
+        for io in range(4):
+            y = g["y"][0, io]
+            rows.append([_fmt_d(g["t"][0, io], 5), _fmt_d(y[0], 5), _fmt_d(y[1], 3),
+                         str(int(g["istats"][0, io, O.ISTAT["nqu"]])),
+                         _fmt_d(g["rstats"][0, io, O.RSTAT["hu"]], 3)])
+        if strict:
+            # bit-for-bit against the oracle with the same portable pow ...
+            ref = O.batch_solve("vdp", [[3.0]], [2.0, 0.0], 0.0, touts, 0.0, 1e-6, mf, itol=1,
+                                pow_mode=1)
+            assert np.array_equal(g["y"], ref["y"])
+            assert np.array_equal(g["istats"], ref["istats"])
+        # ... and close to the golden transcript (pow differs from libm by ulps, so a
+        # decision may flip: allow a few counts, require the printed x to 3 digits)
+        for k in gold:
+            assert abs(st[k] - gold[k]) <= max(2, 0.03 * gold[k]), (strict, k, st[k], gold[k])
+        for r, gr in zip(rows, run["rows"]):
+            assert r[0] == gr[0]
+            if abs(float(gr[1].replace("D", "e"))) > 1.0:
+                assert r[1][:7] == gr[1][:7], (r, gr)
+
+
+def test_dvindy_matches_oracle():
+    B = _B()
+    nsys = 64
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    g = gpu_schedule("robertson", par, ROB["y0"], 0.0, [40.0], tol["rtol"], tol["atol"], 21, 2,
+                     strict=True)
+    s = g["solver"]
+    r, i = s.stats()
+    tcur, hu = r[:, 2], r[:, 0]
+    for k in (0, 1, 2):
+        tq = tcur - 0.3 * hu
+        dky, iflag = s.dvindy(tq, k)
+        for j in range(0, nsys, 7):
+            import ctypes as C
+            cfg = O.BatchCfg(O.PROBLEMS["robertson"], 21, 2, 1, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0,
+                             0.0, 1)
+            out = np.zeros(3)
+            fl = np.zeros(1, dtype=np.int32)
+            tqs = np.array([tq[j]])
+            p = np.ascontiguousarray(par[j])
+            y0 = np.array(ROB["y0"])
+            rt = np.array(tol["rtol"], dtype=np.float64)
+            at = np.array(tol["atol"], dtype=np.float64)
+            ist = O.lib().dvo_single_dense(C.byref(cfg), O._dp(p), O._dp(y0), 0.0, 40.0,
+                                           O._dp(rt), O._dp(at), k, 1, O._dp(tqs), O._dp(out),
+                                           O._ip(fl), None, None)
+            assert ist == 2 and fl[0] == 0 and iflag[j] == 0
+            assert np.array_equal(out, dky[j]), (k, j, out, dky[j])
+    # illegal k and illegal t
+    _, iflag = s.dvindy(tcur, 9)
+    assert (iflag == -1).all()
+    _, iflag = s.dvindy(tcur + 10.0 * np.abs(hu), 0)
+    assert (iflag == -2).all()
+
+
+def test_checkpoint_resume_dvsrco():
+    """dvsrco(job=1) after 6 decades, restore into a fresh handle, continue: identical."""
+    B = _B()
+    nsys = 128
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    touts = rob_touts()
+    full = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21, 2)
+    half = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts[:6], tol["rtol"], tol["atol"], 21, 2)
+    sav = half["solver"].dvsrco(None, 1)
+    s2 = B.dvode_t().initialize("robertson", nsys, par)
+    s2.dvsrco(sav, 2)
+    y = half["y"][:, -1].copy()
+    t = half["t"][:, -1].copy()
+    istate = np.full(nsys, 2, dtype=np.int32)
+    yo = np.zeros((6, nsys, 3))
+    s2.solve_schedule(3, y, t, touts[6:], 2, tol["rtol"], tol["atol"], 1, istate, 0, None, 0, None,
+                      0, 21, yo)
+    assert (istate == 2).all()
+    assert np.array_equal(yo.transpose(1, 0, 2), full["y"][:, 6:])
+
+
+def test_error_paths_match_reference_semantics():
+    B = _B()
+    nsys = 32
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    s = B.dvode_t().initialize("robertson", nsys, par)
+    y = np.tile(np.array([1.0, 0.0, 0.0]), (nsys, 1))
+    t = np.zeros(nsys)
+    istate = np.ones(nsys, dtype=np.int32)
+    rwork = np.zeros((nsys, 20))
+    iwork = np.zeros((nsys, 30), dtype=np.int32)
+    # mxstep exhausted: one call straight to 4e10 with the default 500 steps -> istate = -1
+    s.solve(3, y, t, 4e10, 2, tol["rtol"], tol["atol"], 1, istate, 0, rwork, 20, iwork, 30, 21)
+    ref = O.batch_solve("robertson", par, [1.0, 0.0, 0.0], 0.0, [4e10], tol["rtol"], tol["atol"],
+                        21, itol=2)
+    assert (istate == -1).all() and (ref["istate"][:, 0] == -1).all()
+    assert (iwork[:, 10] == 500).all()
+    # with iopt = 1, mxstep = 100000 it gets there
+    y[:] = [1.0, 0.0, 0.0]
+    t[:] = 0.0
+    istate[:] = 1
+    iwork[0, 5] = 100000
+    s.solve(3, y, t, 4e10, 2, tol["rtol"], tol["atol"], 1, istate, 1, rwork, 20, iwork, 30, 21)
+    assert (istate == 2).all()
+    # illegal itol -> API error and istate = -3 for all
+    istate[:] = 1
+    with pytest.raises(B.BvodeError):
+        s.solve(3, y, t, 1.0, 7, tol["rtol"], tol["atol"], 1, istate, 0, rwork, 20, iwork, 30, 21)
+    assert (istate == -3).all()
+    # tout == t on the first call: immediate return, istate stays 1 (M:1101)
+    istate[:] = 1
+    t[:] = 0.0
+    s.solve(3, y, t, 0.0, 2, tol["rtol"], tol["atol"], 1, istate, 0, rwork, 20, iwork, 30, 21)
+    assert (istate == 1).all()
+    # negative atol -> ewt <= 0 at start -> istate = -3 per system (message 21)
+    istate[:] = 1
+    y[:] = [1.0, 0.0, 0.0]
+    s.solve(3, y, t, 0.4, 2, [0.0], [0.0, 0.0, 0.0], 1, istate, 0, rwork, 20, iwork, 30, 21)
+    assert (istate == -3).all()
