@@ -444,7 +444,7 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, doub
     int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, 20, 30,
                         false, mf, &c);
     if (rc != BVODE_OK) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // 0 = the legacy default stream, as documented
     rc = run_device(s, c, mf, y_device, t_device, istate_device, nout, touts, nullptr,
                     y_out_device, st);
     if (rc != BVODE_OK) return rc;

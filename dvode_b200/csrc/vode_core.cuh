@@ -420,7 +420,12 @@ struct Engine {
         c.drc = fabs(c.rc - 1.0);
         if (c.drc > ccmax || c.nst >= c.nslp + msbp) c.ipup = MITER;
 
-        for (;;) {  // corrector passes
+        // Single-exit loops only: a `return` or `break` out of a divergent region moves the
+        // warp's reconvergence point to the end of the function, and the 32 systems of a warp
+        // would then run one after the other for the rest of the integration.
+        int result = 1;  // 1 = another corrector pass is needed
+#pragma unroll 1
+        while (result == 1) {
             int m = 0;
             double delp = 0.0, del = 0.0;
             bool converged = false, singular = false;
@@ -441,7 +446,9 @@ struct Engine {
             if (!singular) {
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
-                for (;;) {
+                bool iterate = true;
+#pragma unroll 1
+                while (iterate) {
                     const double rl1h = c.rl1 * c.h;
 #pragma unroll
                     for (int i = 0; i < NLOC; i++)
@@ -460,31 +467,36 @@ struct Engine {
                     for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + acor[i];
                     if (m != 0) c.crate = dmax2(crdown * c.crate, del / delp);
                     const double dcon = del * dmin2(1.0, c.crate) / c.tq[4];
-                    if (dcon <= 1.0) { converged = true; break; }
-                    m = m + 1;
-                    if (m == maxcor) break;
-                    if (!(m < 2 || del <= rdiv * delp)) break;
-                    delp = del;
-                    POL::f(c.tn, y, savf, par);
-                    c.nfe = c.nfe + 1;
+                    if (dcon <= 1.0) {
+                        converged = true;
+                        iterate = false;
+                    } else {
+                        m = m + 1;
+                        if (m == maxcor || !(m < 2 || del <= rdiv * delp)) {
+                            iterate = false;
+                        } else {
+                            delp = del;
+                            POL::f(c.tn, y, savf, par);
+                            c.nfe = c.nfe + 1;
+                        }
+                    }
                 }
             }
             if (converged) {
                 c.jcur = 0;
                 c.icf = 0;
                 c.acnrm = (m == 0) ? del : POL::norm(acor, ewt);
-                return 0;
-            }
-            if (!singular && c.jcur != 1) {
+                result = 0;
+            } else if (!singular && c.jcur != 1) {
                 c.icf = 1;
                 c.ipup = MITER;
-                continue;
+            } else {
+                c.icf = 2;
+                c.ipup = MITER;
+                result = -1;
             }
-            break;
         }
-        c.icf = 2;
-        c.ipup = MITER;
-        return -1;
+        return result;
     }
 
     // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
@@ -499,13 +511,13 @@ struct Engine {
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2 };
 
         const int nslast = c.nst;  // M:1399 (and 1337 on the first call)
+        int istate = 0;  // 0 = keep stepping; the loop below has a single exit (see dvnlsd)
+        bool need_interp = false;
         if (!first) {
-            // block D, itask = 1 (M:1457-1467)
+            // block D, itask = 1 (M:1457-1467): tout already inside the last step
             if (!((c.tn - tout) * c.h < 0.0)) {
-                const int iflag = dvindy0(tout, y);
-                if (iflag != 0) return IST_ILLEGAL;  // message 27
-                t_out = tout;
-                return IST_OK;
+                need_interp = true;
+                istate = IST_OK;
             }
         }
 
@@ -513,20 +525,26 @@ struct Engine {
         bool skip_ewt = first;
         double told = c.tn;
         int ncf = 0, nflag = 0;
-        int istate = 0;
 
+#pragma unroll 1
         while (istate == 0) {
             if (entry == E_NEWSTEP) {
                 // ---- label 100 / 200, M:1496-1543
                 if (!skip_ewt) {
-                    if ((c.nst - nslast) >= o.mxstep) { istate = IST_MXSTEP; break; }
-                    bool bad;
-                    dewset_invert(bad);
-                    if (bad) { istate = IST_EWT; break; }
+                    if ((c.nst - nslast) >= o.mxstep) {
+                        istate = IST_MXSTEP;
+                    } else {
+                        bool bad;
+                        dewset_invert(bad);
+                        if (bad) istate = IST_EWT;
+                    }
                 }
                 skip_ewt = false;
-                const double tolsf = kUround * POL::norm(yh[0], ewt);
-                if (tolsf > 1.0) { istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF; break; }
+                if (istate == 0) {
+                    const double tolsf = kUround * POL::norm(yh[0], ewt);
+                    if (tolsf > 1.0) istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF;
+                }
+                if (istate == 0) {
                 if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
                 // ---- dvstep prologue, M:2024-2128
                 c.kflag = 0;
@@ -560,7 +578,9 @@ struct Engine {
                     }
                     entry = E_RESCALE;
                 }
+                }  // if (istate == 0)
             }
+            if (istate == 0) {
             if (entry == E_RESCALE) rescale();
 
             // ---- label 400: predict, coefficients (M:2147-2158)
@@ -711,12 +731,10 @@ struct Engine {
                     c.jstart = 1;
                     // ---- block F, itask = 1 (M:1586-1622)
                     c.init = 1;
-                    if ((c.tn - tout) * c.h < 0.0) {
-                        entry = E_NEWSTEP;
-                    } else {
-                        dvindy0(tout, y);
-                        t_out = tout;
-                        return IST_OK;
+                    entry = E_NEWSTEP;
+                    if (!((c.tn - tout) * c.h < 0.0)) {
+                        need_interp = true;
+                        istate = IST_OK;
                     }
                 }
             } else {
@@ -736,6 +754,14 @@ struct Engine {
                     entry = E_RESCALE;
                 }
             }
+            }  // if (istate == 0)
+        }
+        if (need_interp) {
+            // block G, itask = 1: interpolate to tout (M:1458-1465, 1619-1621)
+            const int iflag = dvindy0(tout, y);
+            t_out = tout;
+            if (first || iflag == 0) return IST_OK;  // block F ignores iflag (M:1619)
+            return IST_ILLEGAL;                       // block D: message 27
         }
         // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
 #pragma unroll

@@ -28,21 +28,26 @@ def build(force=False):
     srcs = [os.path.join(_ROOT, "oracle", f) for f in
             ("dvode_oracle.c", "problems.c", "dvode_oracle.h", "oracle_batch.h", "Makefile")]
     srcs.append(os.path.join(_ROOT, "include", "bvode_mech32.h"))
-    stale = force or not os.path.exists(_SO) or any(
-        os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s))
+    fma = _SO.replace("liboracle.so", "liboracle_fma.so")
+    stale = force or not os.path.exists(_SO) or not os.path.exists(fma) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(_SO), os.path.getmtime(fma))
+        for s in srcs if os.path.exists(s))
     if stale:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")],
                               stdout=subprocess.DEVNULL)
     return _SO
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
+def lib(variant=""):
+    """variant "" = the parity oracle (no FMA); "fma" = the FMA-contracted sensitivity yardstick."""
+    if variant not in _libs:
+        path = build()
+        if variant:
+            path = path.replace("liboracle.so", "liboracle_%s.so" % variant)
+        _lib = C.CDLL(path)
         dp = C.POINTER(C.c_double)
         ip = C.POINTER(C.c_int)
         _lib.dvo_batch_solve.restype = C.c_int
@@ -64,7 +69,8 @@ def lib():
         _lib.dvo_dgesl.argtypes = [dp, C.c_int, C.c_int, ip, dp]
         _lib.dvo_dgbfa.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
         _lib.dvo_dgbsl.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, dp]
-    return _lib
+        _libs[variant] = _lib
+    return _libs[variant]
 
 
 def _dp(a):
@@ -89,7 +95,7 @@ def work_sizes(neq, mf, ml=0, mu=0, maxord=0):
 
 def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1, iopt=0,
                 ml=0, mu=0, maxord=0, mxstep=0, mxhnil=0, h0=0.0, hmax=0.0, hmin=0.0,
-                tcrit=0.0, pow_mode=0, nthreads=0):
+                tcrit=0.0, pow_mode=0, nthreads=0, variant=""):
     """Run the oracle on a batch.  Returns dict(y[nsys,nout,neq], t, istate, rstats, istats)."""
     neq, npar = problem_info(problem)
     params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(npar, 1)))
@@ -106,7 +112,7 @@ def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1,
     ist = np.zeros((nsys, nout), dtype=np.int32)
     rst = np.zeros((nsys, nout, 4))
     ista = np.zeros((nsys, nout, 12), dtype=np.int32)
-    nfail = lib().dvo_batch_solve(C.byref(cfg), nsys, _dp(params), _dp(y0), float(t0), nout,
+    nfail = lib(variant).dvo_batch_solve(C.byref(cfg), nsys, _dp(params), _dp(y0), float(t0), nout,
                                   _dp(touts), _dp(rtol), _dp(atol), _dp(y), _dp(t), _ip(ist),
                                   _dp(rst), _ip(ista), nthreads)
     assert nfail >= 0
