@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libbvode.so")
+# BVODE_LIB lets experiments point at another build of the same library (never a fallback)
+_LIB_PATH = os.environ.get("BVODE_LIB") or os.path.join(_HERE, "libbvode.so")
 
 
 class BvodeError(RuntimeError):

@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nv = _nvcc()
     units = [
-        ("reg_fast.o", "bvode_registry.cu", ["-DBVODE_STRICT=0"]),
+        ("reg_fast.o", "bvode_registry.cu", ["-DBVODE_STRICT=0"] + os.environ.get("BVODE_EXTRA_NVCC", "").split()),
         ("reg_strict.o", "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false"]),
         ("capi.o", "bvode_capi.cu", []),
     ]

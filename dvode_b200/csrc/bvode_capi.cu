@@ -313,6 +313,10 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
         a.istate = d_istate;
         a.rtol = s->d_tol;
         a.atol = s->d_tol + s->neq;
+        for (int i = 0; i < s->neq && i < 8; i++) {
+            a.rtolv[i] = c.tol[i];
+            a.atolv[i] = c.tol[s->neq + i];
+        }
         a.o = c.o;
         a.y_out = d_yout ? d_yout + (size_t)k0 * s->neq * s->nsys : nullptr;
         a.rout = s->d_rout;

@@ -26,6 +26,7 @@ struct KArgs {
     double *t;                     // [nsys] in/out
     int *istate;                   // [nsys] in/out
     const double *rtol, *atol;     // [neq] each, already expanded according to itol
+    double rtolv[8], atolv[8];     // the same, by value, for thread-per-system kernels (neq <= 8)
     BvOpts o;
     double *y_out;                 // [nout][neq][nsys] or nullptr
     double *rout;                  // [4][nsys]  rwork(11:14)

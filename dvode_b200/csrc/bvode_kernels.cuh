@@ -20,8 +20,7 @@ BV_DEV void visit_state(ENG &e, V &v) {
     for (int j = 0; j < kLmax; j++)
 #pragma unroll
         for (int i = 0; i < ENG::NLOC; i++) v.d(e.yh[j][i]);
-#pragma unroll
-    for (int i = 0; i < ENG::NLOC; i++) v.d(e.acsav[i]);
+    ENG::POLICY::visit_acsav(e.acsav, v);
 #pragma unroll
     for (int i = 0; i < ENG::NLOC; i++) v.d(e.acor[i]);
     ENG::POLICY::visit_lin(e.lin, v);
@@ -42,6 +41,7 @@ struct Loader {
     int kd = 0, ki = 0;
     BV_DEV void d(double &x) { x = dp[(size_t)kd * stride]; kd++; }
     BV_DEV void i(int &x) { x = ip[(size_t)ki * stride]; ki++; }
+    BV_DEV void skip_d(int n) { kd += n; }
 };
 struct Storer {
     double *dp;
@@ -50,13 +50,17 @@ struct Storer {
     int kd = 0, ki = 0;
     BV_DEV void d(double &x) { dp[(size_t)kd * stride] = x; kd++; }
     BV_DEV void i(int &x) { ip[(size_t)ki * stride] = x; ki++; }
+    BV_DEV void skip_d(int n) { kd += n; }
 };
 
 // ------------------------------------------------------- thread-per-system ------
 constexpr int kThreadTPB = 128;
+#ifndef BVODE_MINBLOCKS
+#define BVODE_MINBLOCKS 2
+#endif
 
 template <class POL>
-__global__ void __launch_bounds__(kThreadTPB) vode_thread_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kernel(const __grid_constant__ KArgs a) {
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     int ist = a.istate[sys];
@@ -66,11 +70,12 @@ __global__ void __launch_bounds__(kThreadTPB) vode_thread_kernel(const KArgs a) 
 
     Engine<POL> e;
     e.o = a.o;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        e.rtol[i] = a.rtol[i];
-        e.atol[i] = a.atol[i];
-    }
+    e.tol.r = a.rtolv;
+    e.tol.a = a.atolv;
+    e.acsav.p = a.dstate + (size_t)POL::kSlotAcsav * a.nsys + sys;
+    e.acsav.stride = (size_t)a.nsys;
+    e.lin.wjs.p = a.dstate + (size_t)POL::kSlotWjs * a.nsys + sys;
+    e.lin.wjs.stride = (size_t)a.nsys;
 #pragma unroll
     for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * a.nsys + sys];
 
@@ -152,11 +157,13 @@ __global__ void __launch_bounds__(kThreadTPB) vode_thread_kernel(const KArgs a) 
 
 // dvindy for any k (M:1878-1959) from the stored state; one thread per system.
 template <class POL>
-__global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const DkyArgs a) {
+__global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_constant__ DkyArgs a) {
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     constexpr int N = POL::N;
     Engine<POL> e;
+    e.acsav.p = nullptr;
+    e.lin.wjs.p = nullptr;
     Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
     visit_state(e, ld);
     const Ctl &c = e.c;

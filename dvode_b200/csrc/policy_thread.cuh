@@ -25,10 +25,26 @@ struct ThreadPolicy {
     static constexpr bool SAVEJ = SAVEJ_;    // jsv = +1 (mf > 0): keep a copy of J
     static_assert(MITER == 1 || MITER == 2, "thread-per-system policy is dense only");
 
+    // Cold per-system data stays in its HBM state slot instead of registers: it is touched
+    // once per Jacobian / LU (every ~5-50 steps), and a warp's access is one coalesced line.
+    struct GlobalVec {
+        double *p;       // slot 0 of this system
+        size_t stride;   // distance between slots (= nsys)
+        BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
+        BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
+    };
+    using AcSav = GlobalVec;  // the reference's yh(:,lmax) parking place (M:2259, 2298)
+    struct Tol {              // rtol / atol expanded to N entries, in the kernel parameter bank
+        const double *r, *a;
+        BV_DEV double rtol(int i) const { return r[i]; }
+        BV_DEV double atol(int i) const { return a[i]; }
+    };
+
     struct Lin {
-        double p[N][N];              // P = I - h*rl1*J, then its LU factors (p[i][j] = row i, col j)
-        double wjs[SAVEJ ? N : 1][SAVEJ ? N : 1];  // saved Jacobian (wm(locjs))
-        int ipvt[N];                 // 0-based pivot rows
+        double p[N][N];   // P = I - h*rl1*J, then its LU factors (p[i][j] = row i, col j).
+                          // Fast build: the diagonal holds 1/u_kk after dgefa.
+        GlobalVec wjs;    // saved Jacobian wm(locjs), element (i,j) at slot i*N+j (mf > 0)
+        int ipvt[N];      // 0-based pivot rows
     };
 
     BV_DEV static void lin_init(Lin &l) {
@@ -38,26 +54,22 @@ struct ThreadPolicy {
 #pragma unroll
             for (int j = 0; j < N; j++) l.p[i][j] = 0.0;
         }
-        if (SAVEJ) {
-#pragma unroll
-            for (int i = 0; i < N; i++)
-#pragma unroll
-                for (int j = 0; j < N; j++) l.wjs[i][j] = 0.0;
-        }
     }
 
+    // state slots of one system, in visit order: yh, acsav*, acor, p, wjs*, tau, scalars
+    // (* = accessed in place through GlobalVec, skipped by the load / store visitors)
+    static constexpr int kSlotAcsav = kLmax * N;
+    static constexpr int kSlotWjs = kLmax * N + 2 * N + N * N;
+
+    template <class V>
+    BV_DEV static void visit_acsav(AcSav &, V &v) { v.skip_d(N); }
     template <class V>
     BV_DEV static void visit_lin(Lin &l, V &v) {
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
             for (int j = 0; j < N; j++) v.d(l.p[i][j]);
-        if (SAVEJ) {
-#pragma unroll
-            for (int i = 0; i < N; i++)
-#pragma unroll
-                for (int j = 0; j < N; j++) v.d(l.wjs[i][j]);
-        }
+        if (SAVEJ) v.skip_d(N * N);
 #pragma unroll
         for (int i = 0; i < N; i++) v.i(l.ipvt[i]);
     }
@@ -70,7 +82,11 @@ struct ThreadPolicy {
             const double p = v[i] * w[i];
             sum = sum + p * p;
         }
+#if BVODE_STRICT
         return sqrt(sum / (double)N);
+#else
+        return sqrt(sum * (1.0 / (double)N));
+#endif
     }
     BV_DEV static bool any_le_zero(const double (&v)[N]) {
         bool bad = false;
@@ -80,10 +96,10 @@ struct ThreadPolicy {
     }
     // dvhin's upper bound loop, M:1784-1790
     BV_DEV static double hin_upper_bound(double hub, const double (&y0)[N], const double (&ydot)[N],
-                                         const double (&atol)[N]) {
+                                         const Tol &tol) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double delyi = 0.1 * fabs(y0[i]) + atol[i];
+            const double delyi = 0.1 * fabs(y0[i]) + tol.atol(i);
             const double afi = fabs(ydot[i]);
             if (afi * hub > delyi) hub = delyi / afi;
         }
@@ -149,6 +165,11 @@ struct ThreadPolicy {
         }
         ipvt[N - 1] = N - 1;
         if (a[N - 1][N - 1] == 0.0) info = N;
+#if !BVODE_STRICT
+        // fast build: keep 1/u_kk on the diagonal so that dgesl multiplies instead of divides
+#pragma unroll
+        for (int k = 0; k < N; k++) a[k][k] = 1.0 / a[k][k];
+#endif
         return info;
     }
 
@@ -169,7 +190,11 @@ struct ThreadPolicy {
         }
 #pragma unroll
         for (int k = N - 1; k >= 0; k--) {
+#if BVODE_STRICT
             b[k] = b[k] / a[k][k];
+#else
+            b[k] = b[k] * a[k][k];
+#endif
             const double t = -b[k];
 #pragma unroll
             for (int i = 0; i < k; i++) b[i] = b[i] + t * a[i][k];
@@ -224,7 +249,7 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.wjs[i][j] = l.p[i][j];
+                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, l.p[i][j]);
             }
         } else {
             c.jcur = 0;
@@ -232,7 +257,7 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.p[i][j] = l.wjs[i][j];
+                    for (int j = 0; j < N; j++) l.p[i][j] = l.wjs.get(i * N + j);
             }
         }
         const double con = -hrl1;

@@ -172,14 +172,23 @@ BV_DEV void dvjust_down_coeffs(Ctl &c) {
 
 // =================================================================== Engine =====
 // POL provides:
-//   Prob, N (equations), NLOC (vector elements held by this thread),
+//   Prob, N (equations), NLOC (vector elements held by this thread), MITER
 //   norm(v, w)                       weighted rms norm over the whole system (M:3295)
-//   all_le_zero(v)                   true if any component of the system is <= 0
+//   any_le_zero(v)                   true if any component of the system is <= 0
 //   f(t, y, ydot, par)               the user's right-hand side
 //   Lin                              linear-algebra state (P = LU, pivots, saved J)
+//   AcSav                            storage of the acor copy (registers or HBM), get/set
+//   Tol                              rtol(i) / atol(i) of this thread's components
 //   jac_setup(eng, ierpj)            dvjac, M:2897-3104
 //   solve(lin, x)                    dvsol, M:3139-3191
 //   imxer(acor, ewt)                 index of the largest weighted error (M:1694-1706)
+//
+// Fast build only (BVODE_STRICT == 0), each mathematically equivalent to the reference
+// expression and differing from it by rounding only (like FMA contraction does):
+//   * the three step-ratio candidates etaq / etaqm1 / etaqp1 (M:2275-2292) are compared
+//     through log(x)/k instead of 1/(x**(1/k) + addon) (same ordering: both are monotone),
+//     and exp() is evaluated only for the winner when the ratio can exceed `thresh`;
+//   * a/tq(2), b/tq(4) use one shared reciprocal of tq(2).
 template <class POL>
 struct Engine {
     using POLICY = POL;
@@ -190,11 +199,11 @@ struct Engine {
 
     Ctl c;
     double yh[kLmax][NLOC];  // Nordsieck history, column j = h^j y^(j) / j!
-    double acsav[NLOC];      // the reference's yh(:,lmax) scratch use (M:2259, 2298)
     double ewt[NLOC];        // stored inverted (M:1359, 1522)
     double savf[NLOC], acor[NLOC], y[NLOC];
-    double rtol[NLOC], atol[NLOC];
     double par[Prob::NPAR > 0 ? Prob::NPAR : 1];
+    typename POL::AcSav acsav;  // the reference's yh(:,lmax) scratch use (M:2259, 2298)
+    typename POL::Tol tol;
     typename POL::Lin lin;
     Opts o;
 
@@ -202,7 +211,7 @@ struct Engine {
     BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
         double e[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) e[i] = rtol[i] * fabs(yh[0][i]) + atol[i];
+        for (int i = 0; i < NLOC; i++) e[i] = tol.rtol(i) * fabs(yh[0][i]) + tol.atol(i);
         bad = POL::any_le_zero(e);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) ewt[i] = 1.0 / e[i];
@@ -228,17 +237,20 @@ struct Engine {
             }
         }
     }
-    BV_DEV void rescale() {  // label 300, M:2131-2139
+    // label 300, M:2131-2139.  Runs on every attempt: lanes that enter at label 400 pass
+    // eta = 1, which changes nothing (x * 1.0 == x and h == hscal there), so the warp does
+    // not split on "was h changed?".
+    BV_DEV void rescale(double eta) {
         double r = 1.0;
 #pragma unroll
         for (int j = 2; j <= kLmax; j++) {
-            r = r * c.eta;
+            r = r * eta;
 #pragma unroll
             for (int i = 0; i < NLOC; i++) yh[j - 1][i] = r * yh[j - 1][i];
         }
-        c.h = c.hscal * c.eta;
+        c.h = c.hscal * eta;
         c.hscal = c.h;
-        c.rc = c.rc * c.eta;
+        c.rc = c.rc * eta;
     }
     // column `col` (1-based) of yh selected at run time
     BV_DEV void get_col(int col, double (&out)[NLOC]) const {
@@ -278,7 +290,7 @@ struct Engine {
         const double t1 = dvjust_up_coeffs(c);
         double newcol[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) newcol[i] = t1 * acsav[i];
+        for (int i = 0; i < NLOC; i++) newcol[i] = t1 * acsav.get(i);
 #pragma unroll
         for (int j = 3; j <= kLmax; j++) {
             if (j == c.L + 1) {
@@ -320,14 +332,16 @@ struct Engine {
         if (tdist < 2.0 * tround) return -1;
         const double hlb = 100.0 * tround;
         double hub = 0.1 * tdist;
-        hub = POL::hin_upper_bound(hub, yh[0], yh[1], atol);
+        hub = POL::hin_upper_bound(hub, yh[0], yh[1], tol);
         int iter = 0;
         double hg = sqrt(hlb * hub);
         if (hub < hlb) {
             h0 = hg;
         } else {
-            double hnew;
-            for (;;) {
+            double hnew = hg;
+            bool more = true;
+#pragma unroll 1
+            while (more) {
                 const double h = dsign(hg, tout - t0);
                 const double t1 = t0 + h;
 #pragma unroll
@@ -339,15 +353,18 @@ struct Engine {
                 if (yddnrm * hub * hub > 2.0) hnew = sqrt(2.0 / yddnrm);
                 else hnew = sqrt(hg * hub);
                 iter = iter + 1;
+                more = false;
                 if (iter < 4) {
                     const double hrat = hnew / hg;
                     if ((hrat <= 0.5) || (hrat >= 2.0)) {
-                        if ((iter >= 2) && (hnew > 2.0 * hg)) { hnew = hg; break; }
-                        hg = hnew;
-                        continue;
+                        if ((iter >= 2) && (hnew > 2.0 * hg)) {
+                            hnew = hg;
+                        } else {
+                            hg = hnew;
+                            more = true;
+                        }
                     }
                 }
-                break;
             }
             h0 = hnew * 0.5;
             if (h0 < hlb) h0 = hlb;
@@ -371,7 +388,7 @@ struct Engine {
         c.init = 0;
         c.icf = 0; c.ipup = 0; c.jcur = 0; c.kflag = 0; c.nslp = 0; c.newh = 0; c.newq = 0;
         c.eta = 0.0; c.hnew = 0.0; c.conp = 0.0; c.crate = 0.0; c.drc = 0.0; c.acnrm = 0.0;
-        c.rl1 = 0.0; c.etamax = 0.0;
+        c.rl1 = 0.0; c.etamax = 0.0; c.hscal = 0.0; c.rc = 0.0; c.prl1 = 0.0;
 #pragma unroll
         for (int j = 0; j <= kLmax; j++) { c.tau[j] = 0.0; c.el[j] = 0.0; }
 #pragma unroll
@@ -382,7 +399,7 @@ struct Engine {
             for (int i = 0; i < NLOC; i++) yh[j][i] = 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) { acsav[i] = 0.0; acor[i] = 0.0; savf[i] = 0.0; }
+        for (int i = 0; i < NLOC; i++) { acsav.set(i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
         POL::lin_init(lin);
         POL::f(t, y, yh[1], par);
         c.nfe = 1;
@@ -410,7 +427,10 @@ struct Engine {
     }
 
     // ---- dvnlsd, chord iteration (M:2703-2879) -------------------------------------
-    BV_DEV int dvnlsd(int nflag) {
+    // Single-exit loops only: a `return` or `break` out of a divergent region moves the
+    // warp's reconvergence point to the end of the function, and the 32 systems of a warp
+    // would then run one after the other for the rest of the integration.
+    BV_DEV int dvnlsd(int nflag, double rtq4) {
         constexpr int maxcor = 3, msbp = 20;
         constexpr double ccmax = 0.3, crdown = 0.3, rdiv = 2.0;
         if (c.jstart == 0) c.nslp = 0;
@@ -419,10 +439,8 @@ struct Engine {
         if (c.jstart == 0) c.ipup = MITER;
         c.drc = fabs(c.rc - 1.0);
         if (c.drc > ccmax || c.nst >= c.nslp + msbp) c.ipup = MITER;
+        (void)rtq4;
 
-        // Single-exit loops only: a `return` or `break` out of a divergent region moves the
-        // warp's reconvergence point to the end of the function, and the 32 systems of a warp
-        // would then run one after the other for the rest of the integration.
         int result = 1;  // 1 = another corrector pass is needed
 #pragma unroll 1
         while (result == 1) {
@@ -446,17 +464,19 @@ struct Engine {
             if (!singular) {
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
+                // 2/(1+rc), M:2813: rc is fixed during the iterations of one pass
+                const bool do_scale = (c.rc != 1.0);
+                const double cscale = 2.0 / (1.0 + c.rc);
+                const double rl1h = c.rl1 * c.h;
                 bool iterate = true;
 #pragma unroll 1
                 while (iterate) {
-                    const double rl1h = c.rl1 * c.h;
 #pragma unroll
                     for (int i = 0; i < NLOC; i++)
                         y[i] = rl1h * savf[i] - (c.rl1 * yh[1][i] + acor[i]);
                     POL::solve(lin, y);
                     c.nni = c.nni + 1;
-                    if (c.rc != 1.0) {
-                        const double cscale = 2.0 / (1.0 + c.rc);
+                    if (do_scale) {
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
                     }
@@ -466,7 +486,11 @@ struct Engine {
 #pragma unroll
                     for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + acor[i];
                     if (m != 0) c.crate = dmax2(crdown * c.crate, del / delp);
+#if BVODE_STRICT
                     const double dcon = del * dmin2(1.0, c.crate) / c.tq[4];
+#else
+                    const double dcon = del * dmin2(1.0, c.crate) * rtq4;
+#endif
                     if (dcon <= 1.0) {
                         converged = true;
                         iterate = false;
@@ -499,6 +523,11 @@ struct Engine {
         return result;
     }
 
+    // eta = 1 / (x**(1/k) + addon), M:2201, 2275, 2282, 2292
+    BV_DEV static double eta_of(double x, int k) {
+        return 1.0 / (rpow(x, recip_int(k)) + 1.0e-6);
+    }
+
     // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
     // Integrates until tout is passed (itask = 1), then interpolates into y.
     // `first` is true on the call that also ran init_problem (goto 200, M:1381).
@@ -508,9 +537,11 @@ struct Engine {
         constexpr double addon = 1.0e-6, bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
                          etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
                          etamx3 = 10.0, onepsm = 1.00001, thresh = 1.5;
-        enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2 };
+        (void)addon;
+        enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
         const int nslast = c.nst;  // M:1399 (and 1337 on the first call)
+        const int lmax = o.maxord + 1;
         int istate = 0;  // 0 = keep stepping; the loop below has a single exit (see dvnlsd)
         bool need_interp = false;
         if (!first) {
@@ -528,6 +559,7 @@ struct Engine {
 
 #pragma unroll 1
         while (istate == 0) {
+            int change = 0;  // pending order change: -1 / +1
             if (entry == E_NEWSTEP) {
                 // ---- label 100 / 200, M:1496-1543
                 if (!skip_ewt) {
@@ -545,63 +577,90 @@ struct Engine {
                     if (tolsf > 1.0) istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF;
                 }
                 if (istate == 0) {
-                if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
-                // ---- dvstep prologue, M:2024-2128
-                c.kflag = 0;
-                told = c.tn;
-                ncf = 0;
-                c.jcur = 0;
-                nflag = 0;
-                if (c.jstart == 0) {
-                    c.nq = 1;
-                    c.L = 2;
-                    c.tau[1] = c.h;
-                    c.prl1 = 1.0;
-                    c.rc = 0.0;
-                    c.etamax = etamx1;
-                    c.nqwait = 2;
-                    c.hscal = c.h;
-                    entry = E_PREDICT;
-                } else if (c.newh == 0) {
-                    entry = E_PREDICT;
-                } else {
-                    if (c.newq < c.nq) {
-                        order_down();
-                        c.nq = c.newq;
-                        c.L = c.nq + 1;
-                        c.nqwait = c.L;
-                    } else if (c.newq > c.nq) {
-                        order_up();
-                        c.nq = c.newq;
-                        c.L = c.nq + 1;
-                        c.nqwait = c.L;
+                    if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
+                    // ---- dvstep prologue, M:2024-2128
+                    c.kflag = 0;
+                    told = c.tn;
+                    ncf = 0;
+                    c.jcur = 0;
+                    nflag = 0;
+                    if (c.jstart == 0) {
+                        c.nq = 1;
+                        c.L = 2;
+                        c.tau[1] = c.h;
+                        c.prl1 = 1.0;
+                        c.rc = 0.0;
+                        c.etamax = etamx1;
+                        c.nqwait = 2;
+                        c.hscal = c.h;
+                        entry = E_PREDICT;
+                    } else if (c.newh == 0) {
+                        entry = E_PREDICT;
+                    } else {
+                        if (c.newq < c.nq) change = -1;
+                        else if (c.newq > c.nq) change = 1;
+                        entry = E_RESCALE;
                     }
-                    entry = E_RESCALE;
                 }
-                }  // if (istate == 0)
+            } else if (entry == E_DOWN_RESCALE) {
+                change = -1;  // third (or later) error-test failure, M:2230-2235
+                entry = E_RESCALE;
             }
             if (istate == 0) {
-            if (entry == E_RESCALE) rescale();
+                // order change: dvjust + the bookkeeping of M:2118-2128 / M:2231-2234
+                if (change == -1) {
+                    order_down();
+                    c.nq = c.nq - 1;
+                    c.L = c.nq + 1;
+                    c.nqwait = c.L;
+                } else if (change == 1) {
+                    order_up();
+                    c.nq = c.nq + 1;
+                    c.L = c.nq + 1;
+                    c.nqwait = c.L;
+                }
+                rescale(entry == E_RESCALE ? c.eta : 1.0);
 
-            // ---- label 400: predict, coefficients (M:2147-2158)
-            c.tn = c.tn + c.h;
-            predict();
-            dvset_bdf(c);
-            c.rl1 = 1.0 / c.el[2];
-            c.rc = c.rc * (c.rl1 / c.prl1);
-            c.prl1 = c.rl1;
+                // ---- label 400: predict, coefficients (M:2147-2158)
+                c.tn = c.tn + c.h;
+                predict();
+                dvset_bdf(c);
+                c.rl1 = 1.0 / c.el[2];
+                c.rc = c.rc * (c.rl1 / c.prl1);
+                c.prl1 = c.rl1;
+#if BVODE_STRICT
+                const double rtq2 = 0.0, rtq4 = 0.0;
+                (void)rtq2;
+#else
+                const double rtq2 = 1.0 / c.tq[2];
+                const double rtq4 = 10.0 * rtq2;  // tq(4) = 0.1 * tq(2), M:2559
+#endif
+                nflag = dvnlsd(nflag, rtq4);
 
-            nflag = dvnlsd(nflag);
-
-            if (nflag == 0) {
-                const double dsm = c.acnrm / c.tq[2];
-                if (dsm > 1.0) {
+                const bool conv = (nflag == 0);
+#if BVODE_STRICT
+                const double dsm = conv ? c.acnrm / c.tq[2] : 0.0;
+#else
+                const double dsm = conv ? c.acnrm * rtq2 : 0.0;
+#endif
+                const bool accept = conv && !(dsm > 1.0);
+                if (!accept) {  // both kinds of failure undo the prediction (M:2180-2187, 2341-2348)
+                    c.tn = told;
+                    retract();
+                }
+                // step-size ratio at the current order, used by both the accept path (M:2275)
+                // and the first two error-test failures (M:2201): one evaluation for both
+#if BVODE_STRICT
+                const double etaq = conv ? eta_of(bias2 * dsm, c.L) : 0.0;
+#else
+                const double lq = conv ? log(bias2 * dsm) * recip_int(c.L) : 0.0;
+                const double lthr = -0.40546660810860164;  // log(1/thresh - addon)
+#endif
+                if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
                     c.kflag = c.kflag - 1;
                     c.netf = c.netf + 1;
                     nflag = -2;
-                    c.tn = told;
-                    retract();
                     if (fabs(c.h) <= o.hmin * onepsm) {
                         c.kflag = -1;
                         c.jstart = 1;
@@ -609,7 +668,11 @@ struct Engine {
                     } else {
                         c.etamax = 1.0;
                         if (c.kflag > kfc) {
-                            c.eta = 1.0 / (rpow(bias2 * dsm, recip_int(c.L)) + addon);
+#if BVODE_STRICT
+                            c.eta = etaq;
+#else
+                            c.eta = 1.0 / (exp(lq) + addon);
+#endif
                             c.eta = dmax2(dmax2(c.eta, o.hmin / fabs(c.h)), etamin);
                             if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
                             entry = E_RESCALE;
@@ -630,12 +693,22 @@ struct Engine {
                             entry = E_PREDICT;
                         } else {
                             c.eta = dmax2(etamin, o.hmin / fabs(c.h));
-                            order_down();
-                            c.L = c.nq;
-                            c.nq = c.nq - 1;
-                            c.nqwait = c.L;
-                            entry = E_RESCALE;
+                            entry = E_DOWN_RESCALE;
                         }
+                    }
+                } else if (!conv) {
+                    // ---- corrector failed to converge (M:2338-2367)
+                    ncf = ncf + 1;
+                    c.ncfn = c.ncfn + 1;
+                    c.etamax = 1.0;
+                    if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
+                        c.kflag = -2;
+                        c.jstart = 1;
+                        istate = IST_CONVFAIL;
+                    } else {
+                        c.eta = dmax2(etacf, o.hmin / fabs(c.h));
+                        nflag = -1;
+                        entry = E_RESCALE;
                     }
                 } else {
                     // ---- successful step (M:2245-2330, 2370-2375)
@@ -654,61 +727,93 @@ struct Engine {
                         for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * acor[i];
                     }
                     c.nqwait = c.nqwait - 1;
-                    if ((c.L != o.maxord + 1) && (c.nqwait == 1)) {
+                    if ((c.L != lmax) && (c.nqwait == 1)) {
 #pragma unroll
-                        for (int i = 0; i < NLOC; i++) acsav[i] = acor[i];
+                        for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
                         c.conp = c.tq[5];
                     }
                     if (c.etamax != 1.0) {
-                        const double etaq = 1.0 / (rpow(bias2 * dsm, recip_int(c.L)) + addon);
-                        bool decided = false;
+                        int newq = c.nq;
+                        bool save_acor = false;
+#if BVODE_STRICT
+                        double eta = etaq;
+#else
+                        double lwin = lq;
+#endif
                         if (c.nqwait == 0) {
                             c.nqwait = 2;
-                            double etaqm1 = 0.0;
+                            double ddn = 0.0, dup = 0.0;
                             if (c.nq != 1) {
                                 double top[NLOC];
                                 get_col(c.L, top);
-                                const double ddn = POL::norm(top, ewt) / c.tq[1];
-                                etaqm1 = 1.0 / (rpow(bias1 * ddn, recip_int(c.L - 1)) + addon);
+                                ddn = POL::norm(top, ewt) / c.tq[1];
                             }
-                            double etaqp1 = 0.0;
-                            if (c.L != o.maxord + 1) {
+                            if (c.L != lmax) {
                                 const double cnquot =
                                     (c.tq[5] / c.conp) * powi(c.h / c.tau[2], c.L);
 #pragma unroll
-                                for (int i = 0; i < NLOC; i++) savf[i] = acor[i] - cnquot * acsav[i];
-                                const double dup = POL::norm(savf, ewt) / c.tq[3];
-                                etaqp1 = 1.0 / (rpow(bias3 * dup, recip_int(c.L + 1)) + addon);
+                                for (int i = 0; i < NLOC; i++)
+                                    savf[i] = acor[i] - cnquot * acsav.get(i);
+                                dup = POL::norm(savf, ewt) / c.tq[3];
                             }
+#if BVODE_STRICT
+                            const double etaqm1 = (c.nq != 1) ? eta_of(bias1 * ddn, c.L - 1) : 0.0;
+                            const double etaqp1 = (c.L != lmax) ? eta_of(bias3 * dup, c.L + 1) : 0.0;
                             if (etaq < etaqp1) {
                                 if (etaqp1 <= etaqm1) {
-                                    c.eta = etaqm1;  // label 420
-                                    c.newq = c.nq - 1;
+                                    eta = etaqm1;  // label 420
+                                    newq = c.nq - 1;
                                 } else {
-                                    c.eta = etaqp1;
-                                    c.newq = c.nq + 1;
-#pragma unroll
-                                    for (int i = 0; i < NLOC; i++) acsav[i] = acor[i];
+                                    eta = etaqp1;
+                                    newq = c.nq + 1;
+                                    save_acor = true;
                                 }
-                                decided = true;
                             } else if (etaq < etaqm1) {
-                                c.eta = etaqm1;  // label 420
-                                c.newq = c.nq - 1;
-                                decided = true;
+                                eta = etaqm1;  // label 420
+                                newq = c.nq - 1;
                             }
+#else
+                            // eta_a < eta_b  <=>  log(x_a)/k_a > log(x_b)/k_b ; a ratio of 0
+                            // (order not available) is log-ratio +infinity
+                            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+                            const double lm1 =
+                                (c.nq != 1) ? log(bias1 * ddn) * recip_int(c.L - 1) : inf;
+                            const double lp1 =
+                                (c.L != lmax) ? log(bias3 * dup) * recip_int(c.L + 1) : inf;
+                            if (lq > lp1) {
+                                if (lp1 >= lm1) {
+                                    lwin = lm1;
+                                    newq = c.nq - 1;
+                                } else {
+                                    lwin = lp1;
+                                    newq = c.nq + 1;
+                                    save_acor = true;
+                                }
+                            } else if (lq > lm1) {
+                                lwin = lm1;
+                                newq = c.nq - 1;
+                            }
+#endif
                         }
-                        if (!decided) {
-                            c.eta = etaq;
-                            c.newq = c.nq;
+                        if (save_acor) {
+#pragma unroll
+                            for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
                         }
-                        // label 450, M:2320-2330
-                        if (c.eta < thresh || c.etamax == 1.0) {
+                        // label 450, M:2320-2330 (etamax != 1 here)
+#if BVODE_STRICT
+                        const bool keep = (eta < thresh);
+#else
+                        const bool keep = (lwin > lthr);
+                        const double eta = keep ? 1.0 : 1.0 / (exp(lwin) + addon);
+#endif
+                        if (keep) {
                             c.newq = c.nq;
                             c.newh = 0;
                             c.eta = 1.0;
                             c.hnew = c.h;
                         } else {
-                            c.eta = dmin2(c.eta, c.etamax);
+                            c.newq = newq;
+                            c.eta = dmin2(eta, c.etamax);
                             c.eta = c.eta / dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
                             c.newh = 1;
                             c.hnew = c.h * c.eta;
@@ -724,7 +829,11 @@ struct Engine {
                     c.etamax = etamx3;
                     if (c.nst <= 10) c.etamax = etamx2;
                     {
+#if BVODE_STRICT
                         const double r = 1.0 / c.tq[2];
+#else
+                        const double r = rtq2;
+#endif
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) acor[i] = r * acor[i];
                     }
@@ -737,23 +846,6 @@ struct Engine {
                         istate = IST_OK;
                     }
                 }
-            } else {
-                // ---- corrector failed to converge (M:2338-2367)
-                ncf = ncf + 1;
-                c.ncfn = c.ncfn + 1;
-                c.etamax = 1.0;
-                c.tn = told;
-                retract();
-                if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
-                    c.kflag = -2;
-                    c.jstart = 1;
-                    istate = IST_CONVFAIL;
-                } else {
-                    c.eta = dmax2(etacf, o.hmin / fabs(c.h));
-                    nflag = -1;
-                    entry = E_RESCALE;
-                }
-            }
             }  // if (istate == 0)
         }
         if (need_interp) {
