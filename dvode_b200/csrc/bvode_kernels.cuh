@@ -105,20 +105,18 @@ __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kerne
         }
     }
 
-    int kout = 0;
-    for (; kout < a.nout; kout++) {
-        const double tout = (kout == 0) ? tout0 : a.touts[kout];
-        ist = e.advance(tout, first, t);
-        first = false;
-        if (a.y_out) {
+    int nemit = 0;
+    ist = e.run(
+        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
+        [&](int k, const double (&yk)[N]) {
+            nemit = k + 1;
+            if (a.y_out) {
 #pragma unroll
-            for (int i = 0; i < N; i++)
-                a.y_out[((size_t)kout * N + i) * a.nsys + sys] = e.y[i];
-        }
-        if (ist < 0) break;
-    }
-    if (a.y_out) {
-        for (int k2 = kout + 1; k2 < a.nout; k2++) {
+                for (int i = 0; i < N; i++) a.y_out[((size_t)k * N + i) * a.nsys + sys] = yk[i];
+            }
+        });
+    if (a.y_out) {  // a system that failed keeps its last state in the remaining output slots
+        for (int k2 = nemit; k2 < a.nout; k2++) {
 #pragma unroll
             for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * a.nsys + sys] = e.y[i];
         }

@@ -115,18 +115,26 @@ BV_DEV double rpow(double x, double y) {
 #endif
 }
 
-// 1/(double)k for small k, as correctly rounded constants (same bits as an IEEE divide).
-BV_DEV double recip_int(int k) {
-    switch (k) {
-    case 1: return 1.0;
-    case 2: return 1.0 / 2.0;
-    case 3: return 1.0 / 3.0;
-    case 4: return 1.0 / 4.0;
-    case 5: return 1.0 / 5.0;
-    case 6: return 1.0 / 6.0;
-    case 7: return 1.0 / 7.0;
-    default: return 1.0 / (double)k;
-    }
-}
+// 1/(double)k: __drcp_rn is the IEEE round-to-nearest reciprocal, i.e. the same bits as the
+// reference's `one/real(k)` divide, without a divergent switch or a full division.
+BV_DEV double recip_int(int k) { return __drcp_rn((double)k); }
+
+#if !BVODE_STRICT
+// Fast build: the step-size ratio eta = 1/(x**(1/k) + addon) (M:2201, 2275, 2282, 2292) is
+// evaluated as 1/(exp2(log2(x)/k) + addon) with the double-precision log2 / exp2 (rounding-
+// level difference from pow).  -DBVODE_ETA_F32 switches to the single-precision hardware
+// log2 / exp2 (relative error ~1e-7 in eta): faster, still a valid VODE since eta is a
+// heuristic factor and accuracy is controlled by the error test, but the trajectories then
+// separate from the reference's sooner, so it is not the default.
+#ifdef BVODE_ETA_F32
+typedef float lg_t;
+BV_DEV lg_t log2_fast(double x) { return __log2f((float)x); }
+BV_DEV double exp2_fast(lg_t l) { return (double)exp2f(l); }
+#else
+typedef double lg_t;
+BV_DEV lg_t log2_fast(double x) { return log2(x); }
+BV_DEV double exp2_fast(lg_t l) { return exp2(l); }
+#endif
+#endif
 
 }  // namespace BVODE_NS

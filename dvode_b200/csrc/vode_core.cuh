@@ -118,56 +118,40 @@ BV_DEV void dvset_bdf(Ctl &c) {
     tq[4] = 0.1 * tq[2];
 }
 
-// dvjust coefficient parts (the yh updates are done by the engine).  M:2589-2616, 2629-2643.
-// Returns t1 for the order increase.
-BV_DEV double dvjust_up_coeffs(Ctl &c) {
+// dvjust coefficient part for both directions (the yh updates are done by the engine):
+// builds el(3:) from the tau history, M:2589-2616 (iord = +1) and M:2629-2643 (iord = -1).
+// The two branches of the reference share the recurrence el(i) = el(i)*x + el(i-1); they are
+// one code path here so that lanes raising and lowering their order execute together.
+// Returns t1 = (-alph0 - alph1)/prod for the order increase.
+BV_DEV double dvjust_coeffs(Ctl &c, bool up) {
     double *el = c.el, *tau = c.tau;
     const int nq = c.nq;
 #pragma unroll
     for (int j = 1; j <= kLmax; j++) el[j] = 0.0;
     el[3] = 1.0;
-    double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0, hsum = c.hscal;
-    if (nq != 1) {
-#pragma unroll
-        for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
-            if (j <= nq - 1) {
-                const int jp1 = j + 1;
-                hsum = hsum + tau[jp1];
-                const double xi = hsum / c.hscal;
-                prod = prod * xi;
-                alph0 = alph0 - 1.0 / (double)jp1;
-                alph1 = alph1 + 1.0 / xi;
-#pragma unroll
-                for (int iback = 1; iback <= jp1; iback++) {
-                    const int i = (j + 4) - iback;
-                    el[i] = el[i] * xiold + el[i - 1];
-                }
-                xiold = xi;
-            }
-        }
-    }
-    return (-alph0 - alph1) / prod;
-}
-
-BV_DEV void dvjust_down_coeffs(Ctl &c) {
-    double *el = c.el, *tau = c.tau;
-    const int nq = c.nq;
-#pragma unroll
-    for (int j = 1; j <= kLmax; j++) el[j] = 0.0;
-    el[3] = 1.0;
-    double hsum = 0.0;
+    double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
+    double hsum = up ? c.hscal : 0.0;
+    const int jmax = up ? nq - 1 : nq - 2;
 #pragma unroll
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
-        if (j <= nq - 2) {
-            hsum = hsum + tau[j];
+        if (j <= jmax) {
+            hsum = hsum + (up ? tau[j + 1] : tau[j]);
             const double xi = hsum / c.hscal;
+            if (up) {
+                prod = prod * xi;
+                alph0 = alph0 - 1.0 / (double)(j + 1);
+                alph1 = alph1 + 1.0 / xi;
+            }
+            const double x = up ? xiold : xi;
 #pragma unroll
             for (int iback = 1; iback <= j + 1; iback++) {
                 const int i = (j + 4) - iback;
-                el[i] = el[i] * xi + el[i - 1];
+                el[i] = el[i] * x + el[i - 1];
             }
+            xiold = xi;
         }
     }
+    return (-alph0 - alph1) / prod;
 }
 
 // =================================================================== Engine =====
@@ -265,44 +249,32 @@ struct Engine {
         }
     }
 
-    BV_DEV void order_down() {  // dvjust(iord = -1), M:2581, 2628-2650 (+ zero the freed column)
-        if (c.nq != 2) {
-            dvjust_down_coeffs(c);
-            double top[NLOC];
-            get_col(c.L, top);
+    // dvjust, M:2568-2694 (BDF), both directions in one pass over yh.
+    //   down: yh(:,j) -= yh(:,L)*el(j), j = 3..nq   (nothing if nq == 2, M:2581); the freed
+    //         column L is zeroed to keep the zero-column invariant.
+    //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
+    BV_DEV void order_change(bool up) {
+        const double t1 = dvjust_coeffs(c, up);
+        double col[NLOC];
+        if (up) {
 #pragma unroll
-            for (int j = 3; j <= kMaxOrdBdf; j++) {
-                if (j <= c.nq) {
+            for (int i = 0; i < NLOC; i++) col[i] = t1 * acsav.get(i);
+        } else {
+            get_col(c.L, col);
 #pragma unroll
-                    for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] - top[i] * c.el[j];
-                }
-            }
+            for (int i = 0; i < NLOC; i++) col[i] = -col[i];
         }
+        const int jhi = up ? c.nq + 1 : ((c.nq == 2) ? 0 : c.nq);
+        const int jnew = up ? c.L + 1 : c.L;  // column written (up) or zeroed (down)
 #pragma unroll
         for (int j = 3; j <= kLmax; j++) {
-            if (j == c.L) {
+            if (j <= jhi) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = 0.0;
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * col[i];
             }
-        }
-    }
-    BV_DEV void order_up() {  // dvjust(iord = +1), M:2589-2626
-        const double t1 = dvjust_up_coeffs(c);
-        double newcol[NLOC];
+            if (j == jnew) {
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) newcol[i] = t1 * acsav.get(i);
-#pragma unroll
-        for (int j = 3; j <= kLmax; j++) {
-            if (j == c.L + 1) {
-#pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = newcol[i];
-            }
-        }
-#pragma unroll
-        for (int j = 3; j <= kMaxOrdBdf; j++) {
-            if (j <= c.nq + 1) {
-#pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * newcol[i];
+                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = up ? col[i] : 0.0;
             }
         }
     }
@@ -529,26 +501,39 @@ struct Engine {
     }
 
     // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
-    // Integrates until tout is passed (itask = 1), then interpolates into y.
-    // `first` is true on the call that also ran init_problem (goto 200, M:1381).
-    // Returns the output istate; t_out receives the output t.
-    BV_DEV int advance(double tout, bool first, double &t_out) {
+    // Runs the reference's usage loop `do k = 1, nout; call dvode(..., tout(k), itask = 1, ...)`
+    // for this system inside ONE loop: when an accepted step passes the current tout the
+    // solution is interpolated (block G), handed to `emit(k, y)`, and the next "call" starts
+    // (nslast = nst, M:1399; block D, M:1457-1467) without leaving the loop -- so the 32
+    // systems of a warp are never made to wait for each other at an output point.
+    // `first` is true when init_problem ran in this launch (goto 200, M:1381).
+    // Returns the output istate; t_out receives the output t; y the output solution.
+    template <class TOUT, class EMIT>
+    BV_DEV int run(int nout, TOUT tout_of, bool first, double &t_out, EMIT emit) {
         constexpr int kfc = -3, kfh = -7, mxncf = 10;
         constexpr double addon = 1.0e-6, bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
                          etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
-                         etamx3 = 10.0, onepsm = 1.00001, thresh = 1.5;
-        (void)addon;
+                         etamx3 = 10.0, onepsm = 1.00001;
+#if BVODE_STRICT
+        constexpr double thresh = 1.5;
+#else
+        const lg_t l2thr = (lg_t)-0.5849646647653407;  // log2(1/thresh - addon), thresh = 1.5
+#endif
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
-        const int nslast = c.nst;  // M:1399 (and 1337 on the first call)
+        int nslast = c.nst;  // M:1399 (and 1337 on the first call)
         const int lmax = o.maxord + 1;
-        int istate = 0;  // 0 = keep stepping; the loop below has a single exit (see dvnlsd)
-        bool need_interp = false;
-        if (!first) {
-            // block D, itask = 1 (M:1457-1467): tout already inside the last step
-            if (!((c.tn - tout) * c.h < 0.0)) {
-                need_interp = true;
-                istate = IST_OK;
+        int istate = 0;  // 0 = keep stepping; every loop below has a single exit (see dvnlsd)
+        int kout = 0;
+        double tout = tout_of(0);
+        // "reached": tout lies inside the step just taken -> interpolate instead of stepping
+        bool reached = !first && !((c.tn - tout) * c.h < 0.0);
+        if (reached) {
+            // block D on a continuation call checks dvindy's flag (message 27, M:1459-1464)
+            double dky[NLOC];
+            if (dvindy0(tout, dky) != 0) {
+                reached = false;
+                istate = IST_ILLEGAL;
             }
         }
 
@@ -559,63 +544,75 @@ struct Engine {
 
 #pragma unroll 1
         while (istate == 0) {
+            // ---- block G / D: output points reached by the last step (M:1457-1467, 1618-1622)
+#pragma unroll 1
+            while (reached) {
+                dvindy0(tout, y);
+                emit(kout, y);
+                kout = kout + 1;
+                if (kout < nout) {
+                    tout = tout_of(kout);
+                    nslast = c.nst;
+                    reached = !((c.tn - tout) * c.h < 0.0);
+                } else {
+                    reached = false;
+                    istate = IST_OK;
+                }
+            }
             int change = 0;  // pending order change: -1 / +1
-            if (entry == E_NEWSTEP) {
-                // ---- label 100 / 200, M:1496-1543
-                if (!skip_ewt) {
-                    if ((c.nst - nslast) >= o.mxstep) {
-                        istate = IST_MXSTEP;
-                    } else {
-                        bool bad;
-                        dewset_invert(bad);
-                        if (bad) istate = IST_EWT;
+            if (istate == 0) {
+                if (entry == E_NEWSTEP) {
+                    // ---- label 100 / 200, M:1496-1543
+                    if (!skip_ewt) {
+                        if ((c.nst - nslast) >= o.mxstep) {
+                            istate = IST_MXSTEP;
+                        } else {
+                            bool bad;
+                            dewset_invert(bad);
+                            if (bad) istate = IST_EWT;
+                        }
                     }
-                }
-                skip_ewt = false;
-                if (istate == 0) {
-                    const double tolsf = kUround * POL::norm(yh[0], ewt);
-                    if (tolsf > 1.0) istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF;
-                }
-                if (istate == 0) {
-                    if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
-                    // ---- dvstep prologue, M:2024-2128
-                    c.kflag = 0;
-                    told = c.tn;
-                    ncf = 0;
-                    c.jcur = 0;
-                    nflag = 0;
-                    if (c.jstart == 0) {
-                        c.nq = 1;
-                        c.L = 2;
-                        c.tau[1] = c.h;
-                        c.prl1 = 1.0;
-                        c.rc = 0.0;
-                        c.etamax = etamx1;
-                        c.nqwait = 2;
-                        c.hscal = c.h;
-                        entry = E_PREDICT;
-                    } else if (c.newh == 0) {
-                        entry = E_PREDICT;
-                    } else {
-                        if (c.newq < c.nq) change = -1;
-                        else if (c.newq > c.nq) change = 1;
-                        entry = E_RESCALE;
+                    skip_ewt = false;
+                    if (istate == 0) {
+                        const double tolsf = kUround * POL::norm(yh[0], ewt);
+                        if (tolsf > 1.0) istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF;
                     }
+                    if (istate == 0) {
+                        if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
+                        // ---- dvstep prologue, M:2024-2128
+                        c.kflag = 0;
+                        told = c.tn;
+                        ncf = 0;
+                        c.jcur = 0;
+                        nflag = 0;
+                        if (c.jstart == 0) {
+                            c.nq = 1;
+                            c.L = 2;
+                            c.tau[1] = c.h;
+                            c.prl1 = 1.0;
+                            c.rc = 0.0;
+                            c.etamax = etamx1;
+                            c.nqwait = 2;
+                            c.hscal = c.h;
+                            entry = E_PREDICT;
+                        } else if (c.newh == 0) {
+                            entry = E_PREDICT;
+                        } else {
+                            if (c.newq < c.nq) change = -1;
+                            else if (c.newq > c.nq) change = 1;
+                            entry = E_RESCALE;
+                        }
+                    }
+                } else if (entry == E_DOWN_RESCALE) {
+                    change = -1;  // third (or later) error-test failure, M:2230-2235
+                    entry = E_RESCALE;
                 }
-            } else if (entry == E_DOWN_RESCALE) {
-                change = -1;  // third (or later) error-test failure, M:2230-2235
-                entry = E_RESCALE;
             }
             if (istate == 0) {
                 // order change: dvjust + the bookkeeping of M:2118-2128 / M:2231-2234
-                if (change == -1) {
-                    order_down();
-                    c.nq = c.nq - 1;
-                    c.L = c.nq + 1;
-                    c.nqwait = c.L;
-                } else if (change == 1) {
-                    order_up();
-                    c.nq = c.nq + 1;
+                if (change != 0) {
+                    order_change(change > 0);
+                    c.nq = c.nq + change;
                     c.L = c.nq + 1;
                     c.nqwait = c.L;
                 }
@@ -653,8 +650,7 @@ struct Engine {
 #if BVODE_STRICT
                 const double etaq = conv ? eta_of(bias2 * dsm, c.L) : 0.0;
 #else
-                const double lq = conv ? log(bias2 * dsm) * recip_int(c.L) : 0.0;
-                const double lthr = -0.40546660810860164;  // log(1/thresh - addon)
+                const lg_t lq = conv ? log2_fast(bias2 * dsm) * (lg_t)recip_int(c.L) : (lg_t)0;
 #endif
                 if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
@@ -671,7 +667,7 @@ struct Engine {
 #if BVODE_STRICT
                             c.eta = etaq;
 #else
-                            c.eta = 1.0 / (exp(lq) + addon);
+                            c.eta = 1.0 / (exp2_fast(lq) + addon);
 #endif
                             c.eta = dmax2(dmax2(c.eta, o.hmin / fabs(c.h)), etamin);
                             if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
@@ -738,7 +734,7 @@ struct Engine {
 #if BVODE_STRICT
                         double eta = etaq;
 #else
-                        double lwin = lq;
+                        lg_t lwin = lq;
 #endif
                         if (c.nqwait == 0) {
                             c.nqwait = 2;
@@ -773,13 +769,13 @@ struct Engine {
                                 newq = c.nq - 1;
                             }
 #else
-                            // eta_a < eta_b  <=>  log(x_a)/k_a > log(x_b)/k_b ; a ratio of 0
+                            // eta_a < eta_b  <=>  log2(x_a)/k_a > log2(x_b)/k_b ; a ratio of 0
                             // (order not available) is log-ratio +infinity
-                            const double inf = __longlong_as_double(0x7ff0000000000000LL);
-                            const double lm1 =
-                                (c.nq != 1) ? log(bias1 * ddn) * recip_int(c.L - 1) : inf;
-                            const double lp1 =
-                                (c.L != lmax) ? log(bias3 * dup) * recip_int(c.L + 1) : inf;
+                            const lg_t inf = (lg_t)__int_as_float(0x7f800000);
+                            const lg_t lm1 = (c.nq != 1)
+                                ? log2_fast(bias1 * ddn) * (lg_t)recip_int(c.L - 1) : inf;
+                            const lg_t lp1 = (c.L != lmax)
+                                ? log2_fast(bias3 * dup) * (lg_t)recip_int(c.L + 1) : inf;
                             if (lq > lp1) {
                                 if (lp1 >= lm1) {
                                     lwin = lm1;
@@ -803,8 +799,8 @@ struct Engine {
 #if BVODE_STRICT
                         const bool keep = (eta < thresh);
 #else
-                        const bool keep = (lwin > lthr);
-                        const double eta = keep ? 1.0 : 1.0 / (exp(lwin) + addon);
+                        const bool keep = (lwin > l2thr);
+                        const double eta = 1.0 / (exp2_fast(lwin) + addon);
 #endif
                         if (keep) {
                             c.newq = c.nq;
@@ -841,19 +837,13 @@ struct Engine {
                     // ---- block F, itask = 1 (M:1586-1622)
                     c.init = 1;
                     entry = E_NEWSTEP;
-                    if (!((c.tn - tout) * c.h < 0.0)) {
-                        need_interp = true;
-                        istate = IST_OK;
-                    }
+                    reached = !((c.tn - tout) * c.h < 0.0);
                 }
             }  // if (istate == 0)
         }
-        if (need_interp) {
-            // block G, itask = 1: interpolate to tout (M:1458-1465, 1619-1621)
-            const int iflag = dvindy0(tout, y);
-            t_out = tout;
-            if (first || iflag == 0) return IST_OK;  // block F ignores iflag (M:1619)
-            return IST_ILLEGAL;                       // block D: message 27
+        if (istate == IST_OK) {
+            t_out = tout;  // y was interpolated by the last emit
+            return IST_OK;
         }
         // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
 #pragma unroll
