@@ -54,3 +54,56 @@ def robertson_batch(nsys, amp=0.1, seed=SEED, first=0):
 # tolerances: the reference's own (example.f90:44-47) and the tightened headline set
 ROBERTSON_TOL_REF = dict(itol=2, rtol=[1e-4], atol=[1e-8, 1e-14, 1e-6])
 ROBERTSON_TOL_HEADLINE = dict(itol=2, rtol=[1e-6], atol=[1e-10, 1e-16, 1e-8])
+
+
+# ---- dvdemo problem 2 (banded advection, neq = 25, ml = 5, mu = 0), dvdemo.f90:116-190 ----
+ADVECTION_PAR = (1.0, 1.0)
+
+
+def advection_y0():
+    y0 = np.zeros(25)
+    y0[0] = 1.0
+    return y0
+
+
+def advection_touts():
+    t, out = 0.01, []
+    for _ in range(5):
+        out.append(t)
+        t = t * 10.0
+    return np.array(out)
+
+
+def advection_batch(nsys, amp=0.1, seed=SEED, first=0):
+    return perturbed(ADVECTION_PAR, nsys, amp, seed, first)
+
+
+ADVECTION_TOL = dict(itol=1, rtol=[0.0], atol=[1e-6])
+
+
+# ---- synthetic 32-species mechanism (BASELINE.json config 4; builder-defined) ------------
+def _mech_k0():
+    import os
+    import re
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                       "bvode_mech32.h")
+    txt = open(hdr).read()
+    m = re.search(r"#define BVODE_MECH_K0_INIT \{([^}]*)\}", txt)
+    return np.array([float(x) for x in m.group(1).split(",")])
+
+
+def mech32_y0():
+    y0 = np.zeros(32)
+    y0[:4] = 0.25
+    return y0
+
+
+def mech32_touts():
+    return np.array([1.0, 10.0, 100.0, 1000.0])
+
+
+def mech32_batch(nsys, amp=0.1, seed=SEED, first=0):
+    return perturbed(_mech_k0(), nsys, amp, seed, first)
+
+
+MECH32_TOL = dict(itol=1, rtol=[1e-6], atol=[1e-12])

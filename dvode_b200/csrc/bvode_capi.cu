@@ -32,7 +32,8 @@ struct bvode_solver {
     const ProblemEntry *pe = nullptr;
     cudaStream_t stream = nullptr;
     // state (allocated at the first istate = 1 call, when mf / ml / mu are known)
-    int mf = 0, ml = 0, mu = 0, nd = 0, ni = 0;
+    int mf = 0, ml = 0, mu = 0;
+    size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
     double *d_state = nullptr;
     int *i_state = nullptr;
     // batch buffers, SoA on the device
@@ -278,12 +279,12 @@ static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
     cudaFree(s->i_state);
     s->d_state = nullptr;
     s->i_state = nullptr;
-    s->pe->state_size(mf, &s->nd, &s->ni);
-    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
-    CUDA_TRY(cudaMalloc(&s->d_state, sizeof(double) * ns * s->nd));
-    CUDA_TRY(cudaMalloc(&s->i_state, sizeof(int) * ns * s->ni));
-    CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(double) * ns * s->nd, s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->i_state, 0, sizeof(int) * ns * s->ni, s->stream));
+    s->pe->state_size(mf, ml, mu, (size_t)s->nsys, &s->nd, &s->ni);
+    CUDA_TRY(cudaMalloc(&s->d_state, sizeof(double) * s->nd));
+    CUDA_TRY(cudaMalloc(&s->i_state, sizeof(int) * s->ni));
+    CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(double) * s->nd, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->i_state, 0, sizeof(int) * s->ni, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->mf = mf;
     s->ml = ml;
     s->mu = mu;
@@ -487,6 +488,8 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
     memset(&a, 0, sizeof(a));
     a.nsys = s->nsys;
     a.k = k;
+    a.ml = s->ml;
+    a.mu = s->mu;
     if (t_per_system) {
         CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, t, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
         a.t_ps = s->d_tout_ps;
@@ -518,12 +521,12 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
 
 // ---- dvsrco (M:3198-3216): the whole batch state as one host blob ------------------
 struct SavHeader {
-    int magic, problem, nsys, mf, ml, mu, nd, ni;
+    int magic, problem, nsys, mf, ml, mu;
+    unsigned long long nd, ni;
 };
 long long bvode_state_bytes(const bvode_solver *s) {
     if (!s || !s->d_state) return 0;
-    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
-    return (long long)(sizeof(SavHeader) + sizeof(double) * ns * s->nd + sizeof(int) * ns * s->ni +
+    return (long long)(sizeof(SavHeader) + sizeof(double) * s->nd + sizeof(int) * s->ni +
                        sizeof(double) * 4 * s->nsys + sizeof(int) * 12 * s->nsys);
 }
 int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
@@ -533,7 +536,8 @@ int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
     char *p = (char *)sav;
     if (job == 1) {
         if (!s->d_state) return BVODE_EINVAL;
-        SavHeader h{0x62766f64, s->problem, s->nsys, s->mf, s->ml, s->mu, s->nd, s->ni};
+        SavHeader h{0x62766f64, s->problem, s->nsys, s->mf, s->ml, s->mu,
+                    (unsigned long long)s->nd, (unsigned long long)s->ni};
         memcpy(p, &h, sizeof(h));
     } else {
         SavHeader h;
@@ -544,10 +548,9 @@ int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
         if (h.nd != s->nd || h.ni != s->ni) return BVODE_EINVAL;
     }
     p += sizeof(SavHeader);
-    const size_t ns = (size_t)s->nsys * (s->pe->mode == 1 ? 32 : 1);
     const cudaMemcpyKind kind = (job == 1) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
     struct { void *d; size_t n; } parts[4] = {
-        {s->d_state, sizeof(double) * ns * s->nd}, {s->i_state, sizeof(int) * ns * s->ni},
+        {s->d_state, sizeof(double) * s->nd}, {s->i_state, sizeof(int) * s->ni},
         {s->d_rout, sizeof(double) * 4 * s->nsys}, {s->d_iout, sizeof(int) * 12 * s->nsys}};
     for (auto &q : parts) {
         if (job == 1) CUDA_TRY(cudaMemcpy(p, q.d, q.n, kind));

@@ -35,7 +35,7 @@ struct KArgs {
 };
 
 struct DkyArgs {
-    int nsys, k;
+    int nsys, k, ml, mu;
     double t;
     const double *t_ps;
     const double *dstate;
@@ -49,7 +49,8 @@ struct ProblemEntry {
     int neq, npar;
     int mode;  // 0 = one system per thread, 1 = one system per warp
     int (*supports)(int mf, int ml, int mu);
-    void (*state_size)(int mf, int *nd, int *ni);  // slots per system
+    // total doubles / ints of persistent state for a batch of nsys systems
+    void (*state_size)(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni);
     int (*launch)(int mf, const KArgs &a, cudaStream_t st);
     int (*launch_dky)(int mf, const DkyArgs &a, cudaStream_t st);
 };

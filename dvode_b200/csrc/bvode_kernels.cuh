@@ -3,6 +3,7 @@
 #pragma once
 #include "bvode_internal.h"
 #include "policy_thread.cuh"
+#include "policy_warp.cuh"
 #include "problems.cuh"
 
 namespace BVODE_NS {
@@ -19,10 +20,10 @@ BV_DEV void visit_state(ENG &e, V &v) {
 #pragma unroll
     for (int j = 0; j < kLmax; j++)
 #pragma unroll
-        for (int i = 0; i < ENG::NLOC; i++) v.d(e.yh[j][i]);
+        for (int i = 0; i < ENG::NLOC; i++) v.dv(e.yh[j][i]);
     ENG::POLICY::visit_acsav(e.acsav, v);
 #pragma unroll
-    for (int i = 0; i < ENG::NLOC; i++) v.d(e.acor[i]);
+    for (int i = 0; i < ENG::NLOC; i++) v.dv(e.acor[i]);
     ENG::POLICY::visit_lin(e.lin, v);
 #pragma unroll
     for (int j = 1; j <= kLmax; j++) v.d(c.tau[j]);
@@ -42,6 +43,8 @@ struct Loader {
     BV_DEV void d(double &x) { x = dp[(size_t)kd * stride]; kd++; }
     BV_DEV void i(int &x) { x = ip[(size_t)ki * stride]; ki++; }
     BV_DEV void skip_d(int n) { kd += n; }
+    BV_DEV void dv(double &x) { d(x); }  // thread-per-system: vector elements are plain slots
+    BV_DEV void iv(int &x) { i(x); }
 };
 struct Storer {
     double *dp;
@@ -51,6 +54,8 @@ struct Storer {
     BV_DEV void d(double &x) { dp[(size_t)kd * stride] = x; kd++; }
     BV_DEV void i(int &x) { ip[(size_t)ki * stride] = x; ki++; }
     BV_DEV void skip_d(int n) { kd += n; }
+    BV_DEV void dv(double &x) { d(x); }
+    BV_DEV void iv(int &x) { i(x); }
 };
 
 // ------------------------------------------------------- thread-per-system ------
@@ -164,62 +169,206 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
     e.lin.wjs.p = nullptr;
     Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
     visit_state(e, ld);
-    const Ctl &c = e.c;
-    const int nq = c.nq, L = nq + 1, k = a.k;
+    e.c.L = e.c.nq + 1;
     const double t = a.t_ps ? a.t_ps[sys] : a.t;
-    int iflag = 0;
     double dky[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) dky[i] = 0.0;
-    if (k < 0 || k > nq) {
-        iflag = -1;
-    } else {
-        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(c.hu), c.hu);
-        const double tp = c.tn - c.hu - tfuzz;
-        const double tn1 = c.tn + tfuzz;
-        if ((t - tp) * (t - tn1) > 0.0) {
-            iflag = -2;
-        } else {
-            const double s = (t - c.tn) / c.h;
-            int ic = 1;
-            if (k != 0)
-                for (int jj = L - k; jj <= nq; jj++) ic = ic * jj;
-            double cc = (double)ic;
-            double col[N];
-            e.get_col(L, col);
-#pragma unroll
-            for (int i = 0; i < N; i++) dky[i] = cc * col[i];
-            if (k != nq) {
-                for (int jb = 1; jb <= nq - k; jb++) {
-                    const int j = nq - jb, jp1 = j + 1;
-                    ic = 1;
-                    if (k != 0)
-                        for (int jj = jp1 - k; jj <= j; jj++) ic = ic * jj;
-                    cc = (double)ic;
-                    e.get_col(jp1, col);
-#pragma unroll
-                    for (int i = 0; i < N; i++) dky[i] = cc * col[i] + s * dky[i];
-                }
-            }
-            if (k != 0) {
-                const double r = powi(c.h, -k);
-#pragma unroll
-                for (int i = 0; i < N; i++) dky[i] = r * dky[i];
-            }
-        }
-    }
+    const int iflag = e.dvindy_k(t, a.k, dky);
 #pragma unroll
     for (int i = 0; i < N; i++) a.dky[(size_t)i * a.nsys + sys] = dky[i];
     a.iflag[sys] = iflag;
 }
 
-// --------------------------------------------------------------- launchers ------
-struct CountV {
-    int kd = 0, ki = 0;
-    void d(double &) { kd++; }
-    void i(int &) { ki++; }
+// ---------------------------------------------------------- warp-per-system ------
+// State layout in HBM for one-system-per-warp kernels (all in the same dstate / istate_store
+// allocations, regions in this order):
+//   scalars   [kScalarD][nsys]            one copy per system (lane 0 writes, all lanes read)
+//   per-lane  [kLaneSlots][nsys][32]      lane l of system s at (k*nsys + s)*32 + l: coalesced
+//   blocks    [nsys][nblock]              shared-memory image of the band arrays
+constexpr int kScalarD = kLmax + 11;  // tau(1:6) + the 11 scalars of visit_state
+constexpr int kScalarI = 19;
+constexpr int kWarpTPB = 128;         // 4 systems per block
+
+struct WarpLoader {
+    const double *ds, *dl, *db;
+    const int *is, *il;
+    size_t nsys, sys;
+    int ln, nblock;
+    int kd = 0, kl = 0, ki = 0, kil = 0;
+    BV_DEV void d(double &x) { x = ds[(size_t)kd * nsys + sys]; kd++; }
+    BV_DEV void i(int &x) { x = is[(size_t)ki * nsys + sys]; ki++; }
+    BV_DEV void dv(double &x) { x = dl[((size_t)kl * nsys + sys) * 32 + ln]; kl++; }
+    BV_DEV void iv(int &x) { x = il[((size_t)kil * nsys + sys) * 32 + ln]; kil++; }
+    BV_DEV void skip_dv(int n) { kl += n; }
+    BV_DEV void block(double *sm, int n) {
+        for (int k = ln; k < n; k += 32) sm[k] = db[sys * (size_t)nblock + k];
+        __syncwarp();
+    }
+};
+struct WarpStorer {
+    double *ds, *dl, *db;
+    int *is, *il;
+    size_t nsys, sys;
+    int ln, nblock;
+    int kd = 0, kl = 0, ki = 0, kil = 0;
+    BV_DEV void d(double &x) { if (ln == 0) ds[(size_t)kd * nsys + sys] = x; kd++; }
+    BV_DEV void i(int &x) { if (ln == 0) is[(size_t)ki * nsys + sys] = x; ki++; }
+    BV_DEV void dv(double &x) { dl[((size_t)kl * nsys + sys) * 32 + ln] = x; kl++; }
+    BV_DEV void iv(int &x) { il[((size_t)kil * nsys + sys) * 32 + ln] = x; kil++; }
+    BV_DEV void skip_dv(int n) { kl += n; }
+    BV_DEV void block(double *sm, int n) {
+        __syncwarp();
+        for (int k = ln; k < n; k += 32) db[sys * (size_t)nblock + k] = sm[k];
+    }
 };
 
+template <class POL>
+struct WarpLayout {
+    static constexpr int N = POL::N;
+    static int nblock(int ml, int mu) {
+        if constexpr (POL::kBand) return POL::smem_doubles(ml, mu, POL::SAVEJ);
+        else return 0;
+    }
+    static void sizes(int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+        *nd = nsys * ((size_t)kScalarD + (size_t)POL::kLaneSlots * 32 + (size_t)nblock(ml, mu));
+        *ni = nsys * ((size_t)kScalarI + (size_t)POL::kLaneIntSlots * 32);
+    }
+};
+
+template <class POL>
+BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, size_t nsys,
+                      size_t sys, int ln, int warp, int ml, int mu, double *smem,
+                      const double *&dl, const double *&db, const int *&il, int &nblock) {
+    dl = dstate + (size_t)kScalarD * nsys;
+    db = dl + (size_t)POL::kLaneSlots * nsys * 32;
+    il = istore + (size_t)kScalarI * nsys;
+    nblock = 0;
+    if constexpr (POL::kBand) {
+        nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
+        e.lin.ml = ml;
+        e.lin.mu = mu;
+        e.lin.ld = POL::band_ld(ml, mu);
+        e.lin.abd = smem + (size_t)warp * nblock;
+        e.lin.wjs = e.lin.abd + e.lin.ld * POL::N;
+    } else {
+        e.lin.wjs.p = const_cast<double *>(dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
+        e.lin.wjs.stride = nsys * 32;
+    }
+}
+
+template <class POL>
+__global__ void __launch_bounds__(kWarpTPB) vode_warp_kernel(const __grid_constant__ KArgs a) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
+    const size_t nsys = (size_t)a.nsys;
+    if (sys >= nsys) return;  // whole warp
+    int ist = a.istate[sys];
+    if (ist != 1 && ist != 2) return;
+    constexpr int N = POL::N;
+    using Prob = typename POL::Prob;
+
+    Engine<POL> e;
+    e.o = a.o;
+    e.tol.r = (ln < N) ? a.rtol[ln] : 0.0;
+    e.tol.a = (ln < N) ? a.atol[ln] : 1.0;  // padding lanes: finite weight, value always 0
+    Prob::load_par(e.par, a.params, nsys, sys, ln);
+    const double *dl, *db;
+    const int *il;
+    int nblock;
+    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.o.ml, a.o.mu, smem, dl, db, il,
+              nblock);
+
+    double t = a.t[sys];
+    double tolsf = 0.0;
+    bool first = false;
+    const double tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
+    if (ist == 1) {
+        if (tout0 == t) return;  // M:1101
+        e.y[0] = (ln < N) ? a.y[(size_t)ln * nsys + sys] : 0.0;
+        const int r = e.init_problem(t, tout0);
+        if (r < 0) {
+            if (ln == 0) a.istate[sys] = r;
+            return;
+        }
+        first = true;
+    } else {
+        WarpLoader ld{a.dstate, dl, db, a.istate_store, il, nsys, sys, ln, nblock};
+        visit_state(e, ld);
+        e.c.L = e.c.nq + 1;
+        e.c.kflag = 0;
+        e.c.jcur = 0;
+        if (e.c.init != 1) {
+            if (ln == 0) a.istate[sys] = IST_ILLEGAL;
+            return;
+        }
+    }
+
+    int nemit = 0;
+    ist = e.run(
+        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
+        [&](int k, const double (&yk)[1]) {
+            nemit = k + 1;
+            if (a.y_out && ln < N) a.y_out[((size_t)k * N + ln) * nsys + sys] = yk[0];
+        });
+    if (a.y_out && ln < N) {
+        for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
+    }
+    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.c.nst == 0))
+        tolsf = 2.0 * kUround * POL::norm(e.yh[0], e.ewt);
+    const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
+
+    if (ln < N) a.y[(size_t)ln * nsys + sys] = e.y[0];
+    {
+        WarpStorer st{a.dstate, const_cast<double *>(dl), const_cast<double *>(db),
+                      a.istate_store, const_cast<int *>(il), nsys, sys, ln, nblock};
+        visit_state(e, st);
+    }
+    if (ln == 0) {
+        a.t[sys] = t;
+        a.istate[sys] = ist;
+        a.rout[0 * nsys + sys] = e.c.hu;
+        a.rout[1 * nsys + sys] = (ist == IST_OK) ? e.c.hnew : e.c.h;
+        a.rout[2 * nsys + sys] = e.c.tn;
+        a.rout[3 * nsys + sys] = tolsf;
+        a.iout[0 * nsys + sys] = e.c.nst;
+        a.iout[1 * nsys + sys] = e.c.nfe;
+        a.iout[2 * nsys + sys] = e.c.nje;
+        a.iout[3 * nsys + sys] = e.c.nqu;
+        a.iout[4 * nsys + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
+        a.iout[5 * nsys + sys] = imx;
+        a.iout[6 * nsys + sys] = a.lenrw;
+        a.iout[7 * nsys + sys] = a.leniw;
+        a.iout[8 * nsys + sys] = e.c.nlu;
+        a.iout[9 * nsys + sys] = e.c.nni;
+        a.iout[10 * nsys + sys] = e.c.ncfn;
+        a.iout[11 * nsys + sys] = e.c.netf;
+    }
+}
+
+template <class POL>
+__global__ void __launch_bounds__(kWarpTPB) dvindy_warp_kernel(const __grid_constant__ DkyArgs a) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
+    const size_t nsys = (size_t)a.nsys;
+    if (sys >= nsys) return;
+    constexpr int N = POL::N;
+    Engine<POL> e;
+    const double *dl, *db;
+    const int *il;
+    int nblock;
+    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.ml, a.mu, smem, dl, db, il, nblock);
+    WarpLoader ld{a.dstate, dl, db, a.istate_store, il, nsys, sys, ln, nblock};
+    visit_state(e, ld);
+    e.c.L = e.c.nq + 1;
+    const double t = a.t_ps ? a.t_ps[sys] : a.t;
+    double dky[1];
+    const int iflag = e.dvindy_k(t, a.k, dky);
+    if (ln < N) a.dky[(size_t)ln * nsys + sys] = dky[0];
+    if (ln == 0) a.iflag[sys] = iflag;
+}
+
+// --------------------------------------------------------------- launchers ------
 template <class POL>
 static int launch_thread(const KArgs &a, cudaStream_t st) {
     const int grid = (a.nsys + kThreadTPB - 1) / kThreadTPB;
@@ -232,8 +381,28 @@ static int launch_dky_thread(const DkyArgs &a, cudaStream_t st) {
     dvindy_thread_kernel<POL><<<grid, kThreadTPB, 0, st>>>(a);
     return (int)cudaGetLastError();
 }
+template <class POL>
+static int launch_warp(const KArgs &a, cudaStream_t st) {
+    const int spb = kWarpTPB / 32;
+    const int grid = (a.nsys + spb - 1) / spb;
+    const size_t smem = sizeof(double) * spb * (size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(vode_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vode_warp_kernel<POL><<<grid, kWarpTPB, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+template <class POL>
+static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
+    const int spb = kWarpTPB / 32;
+    const int grid = (a.nsys + spb - 1) / spb;
+    const size_t smem = sizeof(double) * spb * (size_t)WarpLayout<POL>::nblock(a.ml, a.mu);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(dvindy_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dvindy_warp_kernel<POL><<<grid, kWarpTPB, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
 
-// thread-per-system problems support mf = +-21, +-22 (dense chord iteration, BDF)
+// ---- thread-per-system problems: mf = +-21, +-22 (dense chord iteration, BDF) ----------
 template <class PROB>
 static int thread_dispatch(int mf, const KArgs &a, cudaStream_t st) {
     switch (mf) {
@@ -251,22 +420,84 @@ static int thread_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
     return launch_dky_thread<ThreadPolicy<PROB, 1, false>>(a, st);
 }
 template <class PROB>
-static void thread_state_size(int mf, int *nd, int *ni) {
-    // dense: N*N for P plus N*N for the saved J when mf > 0
+static void thread_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+    (void)ml; (void)mu;
     constexpr int N = PROB::N;
-    *nd = kLmax * N + 2 * N + N * N + (mf > 0 ? N * N : 0) + kLmax + 11;
-    *ni = N + 19;
+    *nd = nsys * (size_t)(kLmax * N + 2 * N + N * N + (mf > 0 ? N * N : 0) + kLmax + 11);
+    *ni = nsys * (size_t)(N + 19);
 }
 template <class PROB>
 static int thread_supports(int mf, int ml, int mu) {
     (void)ml; (void)mu;
     return mf == 21 || mf == 22 || mf == -21 || mf == -22;
 }
-
 #define BVODE_THREAD_PROBLEM(NAME, PROB)                                                    \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 0, thread_supports<PROB>, thread_state_size<PROB>,       \
             thread_dispatch<PROB>, thread_dky_dispatch<PROB>                                \
+    }
+
+// ---- warp-per-system, dense FD Jacobian: mf = +-22 ----------------------------------------
+template <class PROB>
+static int wdense_dispatch(int mf, const KArgs &a, cudaStream_t st) {
+    switch (mf) {
+    case 22: return launch_warp<WarpDensePolicy<PROB, 2, true>>(a, st);
+    case -22: return launch_warp<WarpDensePolicy<PROB, 2, false>>(a, st);
+    default: return -1000;
+    }
+}
+template <class PROB>
+static int wdense_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
+    if (mf > 0) return launch_dky_warp<WarpDensePolicy<PROB, 2, true>>(a, st);
+    return launch_dky_warp<WarpDensePolicy<PROB, 2, false>>(a, st);
+}
+template <class PROB>
+static void wdense_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+    if (mf > 0) WarpLayout<WarpDensePolicy<PROB, 2, true>>::sizes(ml, mu, nsys, nd, ni);
+    else WarpLayout<WarpDensePolicy<PROB, 2, false>>::sizes(ml, mu, nsys, nd, ni);
+}
+template <class PROB>
+static int wdense_supports(int mf, int ml, int mu) {
+    (void)ml; (void)mu;
+    return mf == 22 || mf == -22;
+}
+#define BVODE_WARP_DENSE_FD_PROBLEM(NAME, PROB)                                             \
+    ProblemEntry {                                                                          \
+        NAME, PROB::N, PROB::NPAR, 1, wdense_supports<PROB>, wdense_state_size<PROB>,       \
+            wdense_dispatch<PROB>, wdense_dky_dispatch<PROB>                                \
+    }
+
+// ---- warp-per-system, banded: mf = +-24, +-25 ----------------------------------------------
+template <class PROB>
+static int wband_dispatch(int mf, const KArgs &a, cudaStream_t st) {
+    switch (mf) {
+    case 24: return launch_warp<WarpBandPolicy<PROB, 4, true>>(a, st);
+    case 25: return launch_warp<WarpBandPolicy<PROB, 5, true>>(a, st);
+    case -24: return launch_warp<WarpBandPolicy<PROB, 4, false>>(a, st);
+    case -25: return launch_warp<WarpBandPolicy<PROB, 5, false>>(a, st);
+    default: return -1000;
+    }
+}
+template <class PROB>
+static int wband_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
+    if (mf > 0) return launch_dky_warp<WarpBandPolicy<PROB, 4, true>>(a, st);
+    return launch_dky_warp<WarpBandPolicy<PROB, 4, false>>(a, st);
+}
+template <class PROB>
+static void wband_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+    if (mf > 0) WarpLayout<WarpBandPolicy<PROB, 4, true>>::sizes(ml, mu, nsys, nd, ni);
+    else WarpLayout<WarpBandPolicy<PROB, 4, false>>::sizes(ml, mu, nsys, nd, ni);
+}
+template <class PROB>
+static int wband_supports(int mf, int ml, int mu) {
+    const int a = mf < 0 ? -mf : mf;
+    return (a == 24 || a == 25) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 && ml < PROB::N &&
+           mu < PROB::N;
+}
+#define BVODE_WARP_BAND_PROBLEM(NAME, PROB)                                                 \
+    ProblemEntry {                                                                          \
+        NAME, PROB::N, PROB::NPAR, 1, wband_supports<PROB>, wband_state_size<PROB>,         \
+            wband_dispatch<PROB>, wband_dky_dispatch<PROB>                                  \
     }
 
 }  // namespace BVODE_NS

@@ -6,6 +6,8 @@ namespace BVODE_NS {
 static const ProblemEntry kEntries[] = {
     BVODE_THREAD_PROBLEM("robertson", Robertson),
     BVODE_THREAD_PROBLEM("vdp", VanDerPol),
+    BVODE_WARP_BAND_PROBLEM("advection", Advection25),
+    BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32),
 };
 }  // namespace BVODE_NS
 

@@ -27,6 +27,7 @@ struct ThreadPolicy {
 
     // Cold per-system data stays in its HBM state slot instead of registers: it is touched
     // once per Jacobian / LU (every ~5-50 steps), and a warp's access is one coalesced line.
+    typedef double Par[PROB::NPAR > 0 ? PROB::NPAR : 1];
     struct GlobalVec {
         double *p;       // slot 0 of this system
         size_t stride;   // distance between slots (= nsys)
@@ -105,8 +106,7 @@ struct ThreadPolicy {
         }
         return hub;
     }
-    BV_DEV static void f(double t, const double (&y)[N], double (&ydot)[N],
-                         const double (&par)[PROB::NPAR > 0 ? PROB::NPAR : 1]) {
+    BV_DEV static void f(double t, const double (&y)[N], double (&ydot)[N], const Par &par) {
         PROB::f(t, y, ydot, par);
     }
     // compute_imxer, M:1694-1706 (1-based index)

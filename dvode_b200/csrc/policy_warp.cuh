@@ -1,0 +1,524 @@
+// policy_warp.cuh -- one ODE system per warp (n <= 32): component i lives on lane i.
+//
+// Every vector of the system is ONE double per lane; the scalar control state (step size,
+// order, coefficients, counters) is replicated on all 32 lanes, so the control flow of the
+// engine is warp-uniform by construction: no divergence, no masks.  Reductions (norms, pivot
+// search) are warp shuffles; pivot-row swaps are lane exchanges.
+//
+//   WarpDensePolicy : dense Newton matrix, row i of P in lane i's registers (mf = +-21, +-22)
+//                     dvjac miter 1/2  M:2941-3001, dgefa LP:46-120, dgesl LP:206-225
+//   WarpBandPolicy  : LINPACK band storage in shared memory, one column per lane
+//                     (mf = +-24, +-25)  dvjac miter 4/5  M:3031-3104, dacopy M:3112,
+//                     dgbfa LP:275-396, dgbsl LP:494-519
+// idamax tie rule (BL:334): the FIRST index of the largest magnitude wins.
+//
+// Strict build: norms are summed in index order (a chain of 32 shuffles) so that the result
+// is bit-identical to the oracle's sequential loop; the fast build uses a butterfly.
+#pragma once
+#include "vode_core.cuh"
+
+namespace BVODE_NS {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+BV_DEV double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+BV_DEV double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+
+// Common pieces of the two warp policies.
+template <class PROB>
+struct WarpCommon {
+    static constexpr int N = PROB::N;
+    static_assert(N <= 32, "warp-per-system policy holds one component per lane");
+    static constexpr int NLOC = 1;
+    typedef double Par[PROB::NPAR_LANE > 0 ? PROB::NPAR_LANE : 1];
+
+    BV_DEV static int lane() { return threadIdx.x & 31; }
+
+    // Per-lane vector element kept in its HBM state slot (cold data).
+    struct GlobalVec {
+        double *p;      // this lane's element of slot 0
+        size_t stride;  // distance between slots (= nsys * 32)
+        BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
+        BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
+    };
+    struct AcSav {  // NLOC = 1: a register
+        double v;
+        BV_DEV double get(int) const { return v; }
+        BV_DEV void set(int, double x) { v = x; }
+    };
+    struct Tol {  // this lane's rtol / atol (0 for lanes >= N)
+        double r, a;
+        BV_DEV double rtol(int) const { return r; }
+        BV_DEV double atol(int) const { return a; }
+    };
+
+    // dvnorm_default, M:3295-3311.  Lanes >= N carry v = 0.
+    BV_DEV static double norm(const double (&v)[1], const double (&w)[1]) {
+        const double p = v[0] * w[0];
+        const double p2 = p * p;
+#if BVODE_STRICT
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) sum = sum + shfl_d(p2, i);
+        return sqrt(sum / (double)N);
+#else
+        double sum = (lane() < N) ? p2 : 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
+        return sqrt(sum * (1.0 / (double)N));
+#endif
+    }
+    BV_DEV static bool any_le_zero(const double (&v)[1]) {
+        return __any_sync(kFull, (lane() < N) && (v[0] <= 0.0)) != 0;
+    }
+    // dvhin's upper bound loop, M:1784-1790: sequential in i because hub feeds the test
+    BV_DEV static double hin_upper_bound(double hub, const double (&y0)[1], const double (&ydot)[1],
+                                         const Tol &tol) {
+        const double delyi = 0.1 * fabs(y0[0]) + tol.a;
+        const double afi = fabs(ydot[0]);
+#pragma unroll 1
+        for (int i = 0; i < N; i++) {
+            const double d = shfl_d(delyi, i), a = shfl_d(afi, i);
+            if (a * hub > d) hub = d / a;
+        }
+        return hub;
+    }
+    BV_DEV static void f(double t, const double (&y)[1], double (&ydot)[1], const Par &par) {
+        ydot[0] = PROB::f_lane(t, y[0], par, lane());
+        if (lane() >= N) ydot[0] = 0.0;
+    }
+    // compute_imxer, M:1694-1706: first index of the largest |acor*ewt| (strict '<')
+    BV_DEV static int imxer(const double (&acor)[1], const double (&ewt)[1]) {
+        double v = (lane() < N) ? fabs(acor[0] * ewt[0]) : -1.0;
+        int idx = lane();
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = shfl_xor_d(v, m);
+            const int oi = __shfl_xor_sync(kFull, idx, m);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        return (v > 0.0) ? idx + 1 : 1;
+    }
+    // idamax over lanes [lo, hi]: returns the lane of the first maximum of |x|
+    BV_DEV static int argmax_abs(double x, int lo, int hi) {
+        const int ln = lane();
+        double v = (ln >= lo && ln <= hi) ? fabs(x) : -1.0;
+        int idx = ln;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double ov = shfl_xor_d(v, m);
+            const int oi = __shfl_xor_sync(kFull, idx, m);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        return idx;
+    }
+    // FD increment of component `lane`, M:2966 / M:3065: r = max(srur*|y|, r0/ewt)
+    BV_DEV static double fd_r0(const Ctl &c, const double (&savf)[1], const double (&ewt)[1]) {
+        const double fac = norm(savf, ewt);
+        double r0 = 1000.0 * fabs(c.h) * kUround * (double)N * fac;
+        if (r0 == 0.0) r0 = 1.0;
+        return r0;
+    }
+};
+
+// =========================================================================== dense ====
+template <class PROB, int MITER_, bool SAVEJ_>
+struct WarpDensePolicy : WarpCommon<PROB> {
+    using Base = WarpCommon<PROB>;
+    using Prob = PROB;
+    using typename Base::GlobalVec;
+    using Base::lane;
+    static constexpr int N = PROB::N;
+    static constexpr int NLOC = 1;
+    static constexpr int MITER = MITER_;
+    static constexpr bool SAVEJ = SAVEJ_;
+    static constexpr bool kBand = false;
+    static_assert(MITER == 1 || MITER == 2, "dense policy");
+
+    struct Lin {
+        double p[N];    // row `lane` of P = I - h*rl1*J, then of its LU factors.
+                        // Fast build: lane k's p[k] holds 1/u_kk after dgefa.
+        GlobalVec wjs;  // row `lane` of the saved Jacobian, element j at slot j (mf > 0)
+        int ipv;        // lane k holds ipvt(k) (0-based row)
+    };
+    BV_DEV static void lin_init(Lin &l) {
+#pragma unroll
+        for (int j = 0; j < N; j++) l.p[j] = 0.0;
+        l.ipv = lane();
+    }
+    // per-lane double slots of one system, in visit order: yh[6], acsav, acor, p[N], wjs[N]*
+    static constexpr int kLaneSlotWjs = kLmax + 2 + N;
+    static constexpr int kLaneSlots = kLmax + 2 + N + (SAVEJ ? N : 0);
+    static constexpr int kLaneIntSlots = 1;
+    template <class V>
+    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class V>
+    BV_DEV static void visit_lin(Lin &l, V &v) {
+#pragma unroll
+        for (int j = 0; j < N; j++) v.dv(l.p[j]);
+        if (SAVEJ) v.skip_dv(N);
+        v.iv(l.ipv);
+    }
+
+    // ---- dgefa, LP:46-120, rows across lanes ----------------------------------------
+    BV_DEV static int dgefa(double (&p)[N], int &ipv) {
+        const int ln = lane();
+        int info = 0;
+#pragma unroll
+        for (int k = 0; k < N - 1; k++) {
+            const int l = Base::argmax_abs(p[k], k, N - 1);
+            if (ln == k) ipv = l;
+            const double alk = shfl_d(p[k], l);
+            if (alk == 0.0) {
+                info = k + 1;
+            } else {
+                const bool swap = (l != k);  // warp-uniform
+                if (swap) {
+                    const double akk = shfl_d(p[k], k);
+                    if (ln == l) p[k] = akk;
+                    if (ln == k) p[k] = alk;
+                }
+                const double t = -1.0 / alk;
+                if (ln > k) p[k] = t * p[k];
+#pragma unroll
+                for (int j = k + 1; j < N; j++) {
+                    const double tj = shfl_d(p[j], l);
+                    if (swap) {
+                        const double akj = shfl_d(p[j], k);
+                        if (ln == l) p[j] = akj;
+                        if (ln == k) p[j] = tj;
+                    }
+                    if (ln > k) p[j] = p[j] + tj * p[k];
+                }
+            }
+        }
+        if (ln == N - 1) ipv = N - 1;
+        if (shfl_d(p[N - 1], N - 1) == 0.0) info = N;
+#if !BVODE_STRICT
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (ln == k) p[k] = 1.0 / p[k];
+#endif
+        return info;
+    }
+
+    // ---- dgesl job = 0, LP:206-225 -------------------------------------------------------
+    BV_DEV static void solve(const Lin &lin, double (&x)[1]) {
+        const int ln = lane();
+        double b = x[0];
+#pragma unroll
+        for (int k = 0; k < N - 1; k++) {
+            const int l = __shfl_sync(kFull, lin.ipv, k);
+            const double t = shfl_d(b, l);
+            if (l != k) {
+                const double bk = shfl_d(b, k);
+                if (ln == l) b = bk;
+                if (ln == k) b = t;
+            }
+            if (ln > k && ln < N) b = b + t * lin.p[k];
+        }
+#pragma unroll
+        for (int k = N - 1; k >= 0; k--) {
+#if BVODE_STRICT
+            if (ln == k) b = b / lin.p[k];
+#else
+            if (ln == k) b = b * lin.p[k];
+#endif
+            const double t = -shfl_d(b, k);
+            if (ln < k) b = b + t * lin.p[k];
+        }
+        x[0] = b;
+    }
+
+    // ---- dvjac, miter 1 / 2 (M:2930-3001) ---------------------------------------------------
+    template <class ENG>
+    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+        Ctl &c = e.c;
+        Lin &l = e.lin;
+        const int ln = lane();
+        ierpj = 0;
+        const double hrl1 = c.h * c.rl1;
+        int jok = SAVEJ ? 1 : -1;
+        if (SAVEJ) {
+            if (c.nst == 0 || c.nst > c.nslj + 50) jok = -1;
+            if (c.icf == 1 && c.drc < 0.2) jok = -1;
+            if (c.icf == 2) jok = -1;
+        }
+        if (jok == -1) {
+            c.nje = c.nje + 1;
+            c.nslj = c.nst;
+            c.jcur = 1;
+            if constexpr (MITER == 1) {
+#pragma unroll
+                for (int j = 0; j < N; j++) l.p[j] = 0.0;
+                PROB::jac_row(c.tn, e.y[0], l.p, e.par, ln);
+            } else {
+                // finite differences, M:2959-2976: column j for all rows at once
+                const double r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const double srur = sqrt(kUround);
+                const double rmine = dmax2(srur * fabs(e.y[0]), r0 / e.ewt[0]);
+                const double ysave = e.y[0];
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    const double r = shfl_d(rmine, j);
+                    if (ln == j) e.y[0] = ysave + r;
+                    const double fac = 1.0 / r;
+                    Base::f(c.tn, e.y, e.acor, e.par);
+                    l.p[j] = (e.acor[0] - e.savf[0]) * fac;
+                    e.y[0] = ysave;
+                }
+                c.nfe = c.nfe + N;
+            }
+            if (SAVEJ) {
+#pragma unroll
+                for (int j = 0; j < N; j++) l.wjs.set(j, l.p[j]);
+            }
+        } else {
+            c.jcur = 0;
+            if (SAVEJ) {
+#pragma unroll
+                for (int j = 0; j < N; j++) l.p[j] = l.wjs.get(j);
+            }
+        }
+        const double con = -hrl1;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            l.p[j] = con * l.p[j];
+            if (ln == j) l.p[j] = l.p[j] + 1.0;
+        }
+        c.nlu = c.nlu + 1;
+        const int ier = dgefa(l.p, l.ipv);
+        if (ier != 0) ierpj = 1;
+    }
+};
+
+// ============================================================================ band ====
+// LINPACK band storage (LP:230-260) in shared memory: abd(i, j), i = 1..meband, j = 1..n at
+// abd[(j-1)*ld + (i-1)], meband = 2*ml + mu + 1, ld odd (bank-conflict-free column stride).
+// The saved Jacobian is the compact mband x n copy (M:3048, dacopy) in shared memory too.
+constexpr int kBandMaxRows = 2 * 12 + 12 + 1;  // sized at launch from ml, mu
+
+template <class PROB, int MITER_, bool SAVEJ_>
+struct WarpBandPolicy : WarpCommon<PROB> {
+    using Base = WarpCommon<PROB>;
+    using Prob = PROB;
+    using Base::lane;
+    static constexpr int N = PROB::N;
+    static constexpr int NLOC = 1;
+    static constexpr int MITER = MITER_;
+    static constexpr bool SAVEJ = SAVEJ_;
+    static constexpr bool kBand = true;
+    static_assert(MITER == 4 || MITER == 5, "band policy");
+
+    struct Lin {
+        double *abd;   // shared memory, ld x N
+        double *wjs;   // shared memory, mband x N (mf > 0)
+        int ml, mu, ld;
+        int ipv;       // lane k holds ipvt(k+1) as a 0-based row of the full matrix
+    };
+    BV_DEV static void lin_init(Lin &l) { l.ipv = lane(); }
+
+    BV_DEV static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
+    // doubles of shared memory one system needs
+    static int smem_doubles(int ml, int mu, bool savej) {
+        const int ld = (2 * ml + mu + 1) | 1;
+        return ld * N + (savej ? (ml + mu + 1) * N : 0);
+    }
+    static constexpr int kLaneSlots = kLmax + 2;  // yh[6], acsav, acor; the band arrays follow
+    static constexpr int kLaneIntSlots = 1;
+    template <class V>
+    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class V>
+    BV_DEV static void visit_lin(Lin &l, V &v) {
+        // band arrays: the whole shared-memory image of this system, cooperatively
+        const int nb = l.ld * N + (SAVEJ ? (l.ml + l.mu + 1) * N : 0);
+        v.block(l.abd, nb);
+        v.iv(l.ipv);
+    }
+
+#define ABD(i, j) l.abd[((j)-1) * l.ld + ((i)-1)]
+    // ---- dgbfa, LP:275-396 (1-based indices as in the reference) ------------------------
+    BV_DEV static int dgbfa(Lin &l) {
+        const int ln = lane();
+        const int n = N, ml = l.ml, mu = l.mu;
+        const int m = ml + mu + 1;
+        int info = 0;
+        // zero initial fill-in columns, LP:299-308: column jz = lane+1
+        const int j0 = mu + 2, j1 = (n < m ? n : m) - 1;
+        {
+            const int jz = ln + 1;
+            if (jz >= j0 && jz <= j1) {
+                for (int i = m + 1 - jz; i <= ml; i++) ABD(i, jz) = 0.0;
+            }
+        }
+        __syncwarp();
+        int jz = j1, ju = 0;
+#pragma unroll 1
+        for (int k = 1; k <= n - 1; k++) {
+            const int kp1 = k + 1;
+            jz = jz + 1;
+            if (jz <= n && ml >= 1) {
+                if (ln < ml) ABD(ln + 1, jz) = 0.0;  // LP:318-323
+            }
+            __syncwarp();
+            const int lm = (ml < n - k) ? ml : n - k;
+            // l = idamax(lm+1, abd(m,k)) + m - 1: lanes 0..lm look at rows m..m+lm of column k
+            const double cand = (ln <= lm) ? ABD(m + ln, k) : 0.0;
+            const int lrow = m + Base::argmax_abs(cand, 0, lm);  // 1-based row in abd
+            const int piv = lrow + k - m;                        // 1-based row of the matrix
+            if (ln == k - 1) l.ipv = piv - 1;
+            const double alk = shfl_d(cand, lrow - m);
+            if (alk == 0.0) {
+                info = k;
+            } else {
+                if (lrow != m && ln == 0) {  // interchange, LP:335-339
+                    const double t = ABD(lrow, k);
+                    ABD(lrow, k) = ABD(m, k);
+                    ABD(m, k) = t;
+                }
+                __syncwarp();
+                const double t = -1.0 / alk;
+                if (ln >= 1 && ln <= lm) ABD(m + ln, k) = t * ABD(m + ln, k);  // dscal, LP:343
+                const int jun = mu + piv;
+                ju = (ju > jun) ? ju : jun;
+                ju = (ju < n) ? ju : n;
+                __syncwarp();
+                // row elimination with column indexing, LP:347-361: column j = kp1 + lane
+                const int ncol = ju - kp1 + 1;
+                if (ln < ncol) {
+                    const int j = kp1 + ln;
+                    const int lj = lrow - (ln + 1), mm = m - (ln + 1);
+                    const double tj = ABD(lj, j);
+                    if (lj != mm) {
+                        ABD(lj, j) = ABD(mm, j);
+                        ABD(mm, j) = tj;
+                    }
+                    for (int i = 1; i <= lm; i++)
+                        ABD(mm + i, j) = ABD(mm + i, j) + tj * ABD(m + i, k);  // daxpy, LP:359
+                }
+                __syncwarp();
+            }
+        }
+        if (ln == n - 1) l.ipv = n - 1;
+        if (ABD(m, n) == 0.0) info = n;
+        __syncwarp();
+        return info;
+    }
+
+    // ---- dgbsl job = 0, LP:494-519: b_i in lane i-1 ------------------------------------------
+    BV_DEV static void solve(const Lin &l, double (&x)[1]) {
+        const int ln = lane();
+        const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
+        double b = x[0];
+        if (ml != 0) {
+#pragma unroll 1
+            for (int k = 1; k <= n - 1; k++) {
+                const int lm = (ml < n - k) ? ml : n - k;
+                const int lp = __shfl_sync(kFull, l.ipv, k - 1);  // 0-based
+                const double t = shfl_d(b, lp);
+                if (lp != k - 1) {
+                    const double bk = shfl_d(b, k - 1);
+                    if (ln == lp) b = bk;
+                    if (ln == k - 1) b = t;
+                }
+                const int i = ln + 1 - k;  // row offset below the diagonal
+                if (i >= 1 && i <= lm) b = b + t * ABD(m + i, k);
+            }
+        }
+#pragma unroll 1
+        for (int k = n; k >= 1; k--) {
+            if (ln == k - 1) b = b / ABD(m, k);
+            const int lm = ((k < m) ? k : m) - 1;
+            const int la = m - lm, lb = k - lm;
+            const double t = -shfl_d(b, k - 1);
+            const int i = ln + 1 - lb;  // 0..lm-1 for the rows lb..k-1
+            if (i >= 0 && i < lm) b = b + t * ABD(la + i, k);
+        }
+        x[0] = b;
+    }
+
+    // ---- dvjac, miter 4 / 5 (M:3031-3104) --------------------------------------------------
+    template <class ENG>
+    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+        Ctl &c = e.c;
+        Lin &l = e.lin;
+        const int ln = lane();
+        const int n = N, ml = l.ml, mu = l.mu;
+        const int mband = ml + mu + 1, meband = mband + ml;
+        ierpj = 0;
+        const double hrl1 = c.h * c.rl1;
+        int jok = SAVEJ ? 1 : -1;
+        if (SAVEJ) {
+            if (c.nst == 0 || c.nst > c.nslj + 50) jok = -1;
+            if (c.icf == 1 && c.drc < 0.2) jok = -1;
+            if (c.icf == 2) jok = -1;
+        }
+        __syncwarp();
+        if (jok == -1) {
+            c.nje = c.nje + 1;
+            c.nslj = c.nst;
+            c.jcur = 1;
+            if constexpr (MITER == 4) {
+                // zero wm(3:), then jac fills rows ml+1..meband of each column (M:3044-3047)
+                if (ln < n)
+                    for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = 0.0;
+                __syncwarp();
+                // pd(i - j + mu + 1, j) = df_i/dy_j with pd = abd rows ml+1.. (nrowpd = meband)
+                if (ln < n) PROB::jac_band_col(c.tn, e.y[0], &ABD(ml + 1, ln + 1), ml, mu, e.par, ln);
+            } else {
+                // banded finite differences, M:3056-3081
+                const int mba = (mband < n) ? mband : n;
+                const double r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const double srur = sqrt(kUround);
+                const double ysave = e.y[0];
+                // yh(:,1) is what the reference restores y from (M:3070); identical to ysave
+                const double rmine = dmax2(srur * fabs(ysave), r0 / e.ewt[0]);
+#pragma unroll 1
+                for (int j = 1; j <= mba; j++) {
+                    const bool mine = (ln < n) && (((ln + 1 - j) % mband) == 0) && (ln + 1 >= j);
+                    if (mine) e.y[0] = ysave + rmine;
+                    Base::f(c.tn, e.y, e.acor, e.par);
+                    e.y[0] = ysave;
+                    // column jj = j, j+mband, ...: rows i1..i2, stored at abd(i - jj + mband, jj)
+                    const double diff = e.acor[0] - e.savf[0];  // row ln+1
+                    const int i = ln + 1;
+                    // the perturbed column that covers row i in this group (bands do not overlap)
+#pragma unroll 1
+                    for (int jj = j; jj <= n; jj += mband) {
+                        const double r = shfl_d(rmine, jj - 1);
+                        const double fac = 1.0 / r;
+                        const int i1 = (jj - mu > 1) ? jj - mu : 1;
+                        const int i2 = (jj + ml < n) ? jj + ml : n;
+                        if (i >= i1 && i <= i2) ABD(i - jj + mband, jj) = diff * fac;
+                    }
+                }
+                c.nfe = c.nfe + mba;
+            }
+            __syncwarp();
+            if (SAVEJ) {  // dacopy(mband, n, wm(ml3), meband, wm(locjs), mband)
+                if (ln < n)
+                    for (int i = 1; i <= mband; i++) l.wjs[ln * mband + (i - 1)] = ABD(ml + i, ln + 1);
+            }
+        } else {
+            c.jcur = 0;
+            if (SAVEJ) {
+                if (ln < n)
+                    for (int i = 1; i <= mband; i++) ABD(ml + i, ln + 1) = l.wjs[ln * mband + (i - 1)];
+            }
+        }
+        __syncwarp();
+        // multiply by -h*rl1 (all meband rows, M:3093) and add the identity (M:3094-3098)
+        const double con = -hrl1;
+        if (ln < n) {
+            for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = con * ABD(i, ln + 1);
+            ABD(mband, ln + 1) = ABD(mband, ln + 1) + 1.0;
+        }
+        __syncwarp();
+        c.nlu = c.nlu + 1;
+        const int ier = dgbfa(l);
+        if (ier != 0) ierpj = 1;
+    }
+#undef ABD
+};
+
+}  // namespace BVODE_NS

@@ -48,3 +48,78 @@ struct VanDerPol {
 };
 
 }  // namespace BVODE_NS
+
+// ----------------------------------------------------------------------------------------
+// Warp-per-system problems: component i on lane i.  f_lane returns ydot of this lane's
+// component; neighbours' values come from warp shuffles (all 32 lanes must call).
+#include "../../include/bvode_mech32.h"
+
+namespace BVODE_NS {
+
+// dvdemo problem 2: ydot = A*y, 5x5-grid advection, neq = 25, banded with ml = 5, mu = 0
+// (/root/reference/test/dvdemo.f90:230-274).  par = (alph1, alph2), reference values 1, 1.
+struct Advection25 {
+    static constexpr int N = 25, NPAR = 2, NPAR_LANE = 2, NG = 5;
+    BV_DEV static void load_par(double (&par)[2], const double *params, size_t nsys, size_t sys, int) {
+        par[0] = params[sys];
+        par[1] = params[nsys + sys];
+    }
+    BV_DEV static double f_lane(double, double y, const double (&p)[2], int ln) {
+        const double ym1 = __shfl_up_sync(0xffffffffu, y, 1);
+        const double ymg = __shfl_up_sync(0xffffffffu, y, NG);
+        const int i = ln % NG, j = ln / NG;
+        double d = -2.0 * y;
+        if (i != 0) d = d + ym1 * p[0];
+        if (j != 0) d = d + ymg * p[1];
+        return d;
+    }
+    // column j = ln+1 of the band Jacobian; pd points at pd(1, j), pd(i-j+mu+1, j) = df_i/dy_j
+    BV_DEV static void jac_band_col(double, double, double *pd, int ml, int mu, const double (&p)[2],
+                                    int ln) {
+        const int mband = ml + mu + 1;
+        pd[mu] = -2.0;
+        pd[mu + 1] = p[0];
+        pd[mband - 1] = p[1];
+        if ((ln + 1) % NG == 0) pd[mu + 1] = 0.0;
+    }
+};
+
+// Synthetic 32-species mass-action network (BASELINE.json config 4; builder-defined, NOT in
+// the reference).  64 reactions: r < 32 unimolecular A -> B, r >= 32 bimolecular
+// A + B -> C + D; tables in include/bvode_mech32.h.  par = 64 rate constants; lane r holds
+// k_r and k_{r+32} and evaluates those two reaction rates; species i then sums its entry
+// list in reaction order (the same order as the oracle's mech_f).
+__device__ const int g_mech_ra[BVODE_MECH_NR] = BVODE_MECH_RA_INIT;
+__device__ const int g_mech_rb[BVODE_MECH_NR] = BVODE_MECH_RB_INIT;
+__device__ const int g_mech_ent_r[BVODE_MECH_NS][BVODE_MECH_MAXE] = BVODE_MECH_ENT_R_INIT;
+__device__ const double g_mech_ent_s[BVODE_MECH_NS][BVODE_MECH_MAXE] = BVODE_MECH_ENT_S_INIT;
+
+struct Mech32 {
+    static constexpr int N = 32, NPAR = 64, NPAR_LANE = 2;
+    BV_DEV static void load_par(double (&par)[2], const double *params, size_t nsys, size_t sys,
+                                int ln) {
+        par[0] = params[(size_t)ln * nsys + sys];
+        par[1] = params[(size_t)(ln + 32) * nsys + sys];
+    }
+    BV_DEV static double f_lane(double, double y, const double (&k)[2], int ln) {
+        const unsigned full = 0xffffffffu;
+        // this lane's two reactions
+        const double rate0 = k[0] * __shfl_sync(full, y, g_mech_ra[ln]);  // unimolecular
+        double rate1 = k[1] * __shfl_sync(full, y, g_mech_ra[ln + 32]);
+        rate1 = rate1 * __shfl_sync(full, y, g_mech_rb[ln + 32]);       // bimolecular
+        double d = 0.0;
+#pragma unroll
+        for (int e = 0; e < BVODE_MECH_MAXE; e++) {
+            const int r = g_mech_ent_r[ln][e];
+            const double s = g_mech_ent_s[ln][e];
+            const int src = r & 31;
+            const double v0 = __shfl_sync(full, rate0, src);
+            const double v1 = __shfl_sync(full, rate1, src);
+            const double q = (r >= 32) ? v1 : v0;
+            d = d + s * q;
+        }
+        return d;
+    }
+};
+
+}  // namespace BVODE_NS

@@ -185,7 +185,7 @@ struct Engine {
     double yh[kLmax][NLOC];  // Nordsieck history, column j = h^j y^(j) / j!
     double ewt[NLOC];        // stored inverted (M:1359, 1522)
     double savf[NLOC], acor[NLOC], y[NLOC];
-    double par[Prob::NPAR > 0 ? Prob::NPAR : 1];
+    typename POL::Par par;   // per-system parameters of f / jac, as this thread holds them
     typename POL::AcSav acsav;  // the reference's yh(:,lmax) scratch use (M:2259, 2298)
     typename POL::Tol tol;
     typename POL::Lin lin;
@@ -292,6 +292,46 @@ struct Engine {
         for (int j = kLmax - 2; j >= 0; j--) {
 #pragma unroll
             for (int i = 0; i < NLOC; i++) dky[i] = yh[j][i] + s * dky[i];
+        }
+        return 0;
+    }
+
+    // ---- dvindy for any k (M:1905-1957), from the current state --------------------------
+    BV_DEV int dvindy_k(double t, int k, double (&dky)[NLOC]) const {
+        const int nq = c.nq, L = nq + 1;
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) dky[i] = 0.0;
+        if (k < 0 || k > nq) return -1;
+        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(c.hu), c.hu);
+        const double tp = c.tn - c.hu - tfuzz;
+        const double tn1 = c.tn + tfuzz;
+        if ((t - tp) * (t - tn1) > 0.0) return -2;
+        const double s = (t - c.tn) / c.h;
+        int ic = 1;
+        if (k != 0)
+            for (int jj = L - k; jj <= nq; jj++) ic = ic * jj;
+        double cc = (double)ic;
+        double col[NLOC];
+        get_col(L, col);
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) dky[i] = cc * col[i];
+        if (k != nq) {
+#pragma unroll 1
+            for (int jb = 1; jb <= nq - k; jb++) {
+                const int j = nq - jb, jp1 = j + 1;
+                ic = 1;
+                if (k != 0)
+                    for (int jj = jp1 - k; jj <= j; jj++) ic = ic * jj;
+                cc = (double)ic;
+                get_col(jp1, col);
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) dky[i] = cc * col[i] + s * dky[i];
+            }
+        }
+        if (k != 0) {
+            const double r = powi(c.h, -k);
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) dky[i] = r * dky[i];
         }
         return 0;
     }

@@ -326,3 +326,164 @@ def test_error_paths_match_reference_semantics():
     y[:] = [1.0, 0.0, 0.0]
     s.solve(3, y, t, 0.4, 2, [0.0], [0.0, 0.0, 0.0], 1, istate, 0, rwork, 20, iwork, 30, 21)
     assert (istate == -3).all()
+
+
+# ------------------------------------------------------------------ warp-per-system ------
+def _iw(ml=0, mu=0, mxstep=0):
+    iw = np.zeros(30, dtype=np.int32)
+    iw[0], iw[1], iw[5] = ml, mu, mxstep
+    return iw
+
+
+@pytest.mark.parametrize("mf", [24, 25, -24, -25])
+def test_advection_golden_transcript_on_gpu(mf):
+    """dvdemo problem 2 (banded, ml = 5, mu = 0) replayed on the GPU with the reference's call
+    sequence: strict build bit-for-bit against the oracle; both builds against the golden
+    transcript's counters and NQ."""
+    B = _B()
+    run = [r for r in _DV["runs"] if r["problem"] == 2 and r["mf"] == mf][0]
+    touts = B.batches.advection_touts()
+    y0 = B.batches.advection_y0()
+    ref = O.batch_solve("advection", [[1.0, 1.0]], y0, 0.0, touts, 0.0, 1e-6, mf, itol=1, ml=5,
+                        mu=0, pow_mode=1)
+    for strict in (True, False):
+        g = gpu_schedule("advection", [[1.0, 1.0]], y0, 0.0, touts, [0.0], [1e-6], mf, 1,
+                         strict=strict, per_call=True, iwork_opts=_iw(5, 0))
+        assert (g["istate"] == 2).all()
+        if strict:
+            assert np.array_equal(g["y"], ref["y"])
+            assert np.array_equal(g["istats"], ref["istats"])
+            assert np.array_equal(g["rstats"], ref["rstats"])
+        st = {k: int(g["istats"][0, -1, O.ISTAT[k]]) for k in
+              ("lenrw", "leniw", "nst", "nfe", "nje", "nlu", "nni", "ncfn", "netf")}
+        for k in st:
+            assert abs(st[k] - run["stats"][k]) <= max(2, 0.03 * run["stats"][k]), (strict, k, st[k])
+        # analytic solution (dvdemo.f90:276-301): error below 1000 * atol like the reference's check
+        import math
+        for io, t in enumerate(touts):
+            ex = math.exp(-2.0 * t) if t <= 30 else 0.0
+            yt = np.array([t ** (i + j) * ex / (math.factorial(i) * math.factorial(j))
+                           for j in range(5) for i in range(5)])
+            assert np.abs(g["y"][0, io] - yt).max() <= 1e-3
+
+
+@pytest.mark.parametrize("mf,mu", [(24, 0), (25, 0), (24, 5), (25, 5), (-25, 5)])
+def test_advection_batch_strict_bit_exact(mf, mu):
+    B = _B()
+    nsys = 96
+    par = B.batches.advection_batch(nsys)
+    tol = B.batches.ADVECTION_TOL
+    touts = B.batches.advection_touts()
+    ref = O.batch_solve("advection", par, B.batches.advection_y0(), 0.0, touts, tol["rtol"],
+                        tol["atol"], mf, itol=1, ml=5, mu=mu, pow_mode=1)
+    got = gpu_schedule("advection", par, B.batches.advection_y0(), 0.0, touts, tol["rtol"],
+                       tol["atol"], mf, 1, strict=True, iwork_opts=_iw(5, mu))
+    assert (got["istate"][:, -1] == 2).all()
+    assert np.array_equal(got["y"], ref["y"])
+    assert np.array_equal(got["istats"][:, -1], ref["istats"][:, -1])
+    assert np.array_equal(got["rstats"][:, -1], ref["rstats"][:, -1])
+
+
+def test_advection_fast_parity():
+    B = _B()
+    nsys = 2048
+    par = B.batches.advection_batch(nsys)
+    tol = B.batches.ADVECTION_TOL
+    touts = B.batches.advection_touts()
+    for mf in (24, 25):
+        ref = O.batch_solve("advection", par, B.batches.advection_y0(), 0.0, touts, tol["rtol"],
+                            tol["atol"], mf, itol=1, ml=5, mu=0)
+        got = gpu_schedule("advection", par, B.batches.advection_y0(), 0.0, touts, tol["rtol"],
+                           tol["atol"], mf, 1, strict=False, iwork_opts=_iw(5, 0))
+        assert (got["istate"][:, -1] == 2).all()
+        # rtol = 0: the weight is atol; the problem is linear and benign, 10x holds pointwise
+        werr = np.abs(got["y"] - ref["y"]) / 1e-6
+        assert werr.max() <= 10.0, werr.max()
+        for name in ("nst", "nfe", "nje", "nlu", "nni"):
+            a = got["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+            b = ref["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+            assert abs(a - b) <= 0.02 * b, (mf, name, a, b)
+
+
+@pytest.mark.parametrize("mf", [22, -22])
+def test_mech32_strict_bit_exact(mf):
+    B = _B()
+    nsys = 64
+    par = B.batches.mech32_batch(nsys)
+    tol = B.batches.MECH32_TOL
+    touts = B.batches.mech32_touts()
+    ref = O.batch_solve("mech32", par, B.batches.mech32_y0(), 0.0, touts, tol["rtol"],
+                        tol["atol"], mf, itol=1, iopt=1, mxstep=100000, pow_mode=1)
+    got = gpu_schedule("mech32", par, B.batches.mech32_y0(), 0.0, touts, tol["rtol"],
+                       tol["atol"], mf, 1, strict=True, iopt=1, iwork_opts=_iw(0, 0, 100000))
+    assert (got["istate"][:, -1] == 2).all()
+    assert np.array_equal(got["y"], ref["y"])
+    assert np.array_equal(got["istats"][:, -1], ref["istats"][:, -1])
+
+
+def test_mech32_fast_parity():
+    B = _B()
+    nsys = 1024
+    par = B.batches.mech32_batch(nsys)
+    tol = B.batches.MECH32_TOL
+    touts = B.batches.mech32_touts()
+    kw = dict(itol=1, iopt=1, mxstep=100000)
+    ref = O.batch_solve("mech32", par, B.batches.mech32_y0(), 0.0, touts, tol["rtol"],
+                        tol["atol"], 22, **kw)
+    ref1 = O.batch_solve("mech32", par, B.batches.mech32_y0(), 0.0, touts, tol["rtol"],
+                         tol["atol"], 22, variant="fma", **kw)
+    got = gpu_schedule("mech32", par, B.batches.mech32_y0(), 0.0, touts, tol["rtol"],
+                       tol["atol"], 22, 1, strict=False, iopt=1, iwork_opts=_iw(0, 0, 100000))
+    assert (got["istate"][:, -1] == 2).all() and (ref["istate"] == 2).all()
+    w_gpu = weighted_err(got["y"], ref["y"], tol["rtol"], tol["atol"]).max(axis=2)
+    w_self = weighted_err(ref1["y"], ref["y"], tol["rtol"], tol["atol"]).max(axis=2)
+    for q in (50, 90, 99):
+        pg = np.percentile(w_gpu, q, axis=0)
+        ps = np.percentile(w_self, q, axis=0)
+        assert (pg <= 1.35 * ps + 0.5).all(), (q, pg, ps)
+    assert (w_gpu <= 10.0).mean() >= (w_self <= 10.0).mean() - 0.01
+    for name in ("nst", "nfe", "nje", "nlu", "nni"):
+        a = got["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        b = ref["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        assert abs(a - b) <= 0.02 * b, (name, a, b)
+    # invariant: every reaction conserves sum(y)
+    assert np.abs(got["y"].sum(axis=2) - 1.0).max() < 1e-5
+
+
+def test_warp_dvindy_and_checkpoint():
+    B = _B()
+    nsys = 40
+    par = B.batches.advection_batch(nsys)
+    tol = B.batches.ADVECTION_TOL
+    touts = B.batches.advection_touts()
+    full = gpu_schedule("advection", par, B.batches.advection_y0(), 0.0, touts, tol["rtol"],
+                        tol["atol"], 24, 1, iwork_opts=_iw(5, 0))
+    half = gpu_schedule("advection", par, B.batches.advection_y0(), 0.0, touts[:3], tol["rtol"],
+                        tol["atol"], 24, 1, iwork_opts=_iw(5, 0))
+    s = half["solver"]
+    r, _ = s.stats()
+    dky, iflag = s.dvindy(r[:, 2], 0)   # k = 0 at tcur reproduces yh(:,1)
+    assert (iflag == 0).all()
+    d1, iflag = s.dvindy(r[:, 2], 1)    # dy/dt at tcur ~ f(y) for this linear problem
+    assert (iflag == 0).all()
+    f = np.zeros_like(dky)
+    for j in range(nsys):
+        yy = dky[j]
+        for k in range(25):
+            i, jj = k % 5, k // 5
+            f[j, k] = -2 * yy[k] + (yy[k - 1] * par[j, 0] if i else 0) + (yy[k - 5] * par[j, 1] if jj else 0)
+    assert np.abs(d1 - f).max() < 1e-4
+    sav = s.dvsrco(None, 1)
+    s2 = B.dvode_t().initialize("advection", nsys, par)
+    s2.dvsrco(sav, 2)
+    y = half["y"][:, -1].copy()
+    t = half["t"][:, -1].copy()
+    istate = np.full(nsys, 2, dtype=np.int32)
+    iwork = np.zeros((nsys, 30), dtype=np.int32)
+    iwork[0, 0] = 5
+    rwork = np.zeros((nsys, 20))
+    yo = np.zeros((2, nsys, 25))
+    s2.solve_schedule(25, y, t, touts[3:], 1, tol["rtol"], tol["atol"], 1, istate, 0, rwork, 20,
+                      iwork, 30, 24, yo)
+    assert (istate == 2).all()
+    assert np.array_equal(yo.transpose(1, 0, 2), full["y"][:, 3:])
