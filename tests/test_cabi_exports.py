@@ -44,3 +44,24 @@ def test_batch_generator_is_deterministic_and_bounded():
     z = z ^ (z >> 31)
     u = (z >> 11) / float(1 << 53) * 2.0 - 1.0
     assert a[7, 1] == base[1] * (1.0 + 0.1 * u)
+
+
+def test_fortran_binding_names_are_exported():
+    """fortran/bvode_module.f90 cannot be compiled here (no Fortran compiler in the image): at
+    least every bind(C, name=...) in it must exist in the library."""
+    from dvode_b200 import build
+    lib = ctypes.CDLL(build.build())
+    src = open(os.path.join(ROOT, "fortran", "bvode_module.f90")).read()
+    names = set(re.findall(r"bind\(C,\s*name='(\w+)'\)", src))
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_host_mirror_rejects_bad_arrays_without_a_gpu():
+    import dvode_b200 as B
+    s = B.dvode_t()
+    import pytest
+    with pytest.raises(B.BvodeError):
+        s.solve(3, np.zeros((4, 3)), np.zeros(4), 1.0, 1, [1e-4], [1e-8], 1,
+                np.ones(4, dtype=np.int32), 0, None, 0, None, 0, 21)
