@@ -1,6 +1,7 @@
 // bvode_kernels.cuh -- kernel entry points, state load/store and the per-build registry.
 // Included by bvode_kernels_fast.cu and bvode_kernels_strict.cu (same source, two builds).
 #pragma once
+#include <stdlib.h>
 #include "bvode_internal.h"
 #include "policy_thread.cuh"
 #include "policy_warp.cuh"
@@ -20,19 +21,19 @@ BV_DEV void visit_state(ENG &e, V &v) {
 #pragma unroll
     for (int j = 0; j < kLmax; j++)
 #pragma unroll
-        for (int i = 0; i < ENG::NLOC; i++) v.dv(e.yh[j][i]);
+        for (int i = 0; i < ENG::NLOC; i++) v.dv(e.hot.yh(j, i));
     ENG::POLICY::visit_acsav(e.acsav, v);
 #pragma unroll
     for (int i = 0; i < ENG::NLOC; i++) v.dv(e.acor[i]);
-    ENG::POLICY::visit_lin(e.lin, v);
+    ENG::POLICY::visit_lin(e, v);
 #pragma unroll
-    for (int j = 1; j <= kLmax; j++) v.d(c.tau[j]);
-    v.d(c.h); v.d(c.hscal); v.d(c.hnew); v.d(c.hu); v.d(c.eta); v.d(c.etamax); v.d(c.tn);
-    v.d(c.rc); v.d(c.prl1); v.d(c.crate); v.d(c.conp);
+    for (int j = 1; j <= kLmax; j++) v.d(e.hot.tau(j));
+    v.d(c.h); v.d(c.hscal); v.d(e.hot.sd(SD_HNEW)); v.d(e.hot.sd(SD_HU)); v.d(c.eta); v.d(e.hot.sd(SD_ETAMAX)); v.d(c.tn);
+    v.d(c.rc); v.d(c.prl1); v.d(e.hot.sd(SD_CRATE)); v.d(e.hot.sd(SD_CONP));
     v.i(c.nq); v.i(c.nqwait); v.i(c.newq); v.i(c.newh); v.i(c.jstart); v.i(c.icf); v.i(c.ipup);
-    v.i(c.nslj); v.i(c.nslp); v.i(c.nhnil); v.i(c.init);
-    v.i(c.nst); v.i(c.nfe); v.i(c.nje); v.i(c.nlu); v.i(c.nni); v.i(c.ncfn); v.i(c.netf);
-    v.i(c.nqu);
+    v.i(e.hot.si(SI_NSLJ)); v.i(e.hot.si(SI_NSLP)); v.i(e.hot.si(SI_NHNIL)); v.i(e.hot.si(SI_INIT));
+    v.i(e.hot.si(SI_NST)); v.i(e.hot.si(SI_NFE)); v.i(e.hot.si(SI_NJE)); v.i(e.hot.si(SI_NLU)); v.i(e.hot.si(SI_NNI)); v.i(e.hot.si(SI_NCFN)); v.i(e.hot.si(SI_NETF));
+    v.i(e.hot.si(SI_NQU));
 }
 
 struct Loader {
@@ -66,6 +67,7 @@ constexpr int kThreadTPB = 128;
 
 template <class POL>
 __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kernel(const __grid_constant__ KArgs a) {
+    extern __shared__ double smem_thread[];
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     int ist = a.istate[sys];
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kerne
     using Prob = typename POL::Prob;
 
     Engine<POL> e;
+    e.hot.bind(smem_thread, threadIdx.x);
     e.o = a.o;
     e.tol.r = a.rtolv;
     e.tol.a = a.atolv;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kerne
         e.c.L = e.c.nq + 1;
         e.c.kflag = 0;
         e.c.jcur = 0;
-        if (e.c.init != 1) {  // M:1102-1106
+        if (e.hot.si(SI_INIT) != 1) {  // M:1102-1106
             a.istate[sys] = IST_ILLEGAL;
             return;
         }
@@ -126,8 +129,8 @@ __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kerne
             for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * a.nsys + sys] = e.y[i];
         }
     }
-    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.c.nst == 0))
-        tolsf = 2.0 * kUround * POL::norm(e.yh[0], e.ewt);  // M:1626, 1632, 1641
+    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
+        tolsf = 2.0 * kUround * e.norm_y0();  // M:1626, 1632, 1641
 
 #pragma unroll
     for (int i = 0; i < N; i++) a.y[(size_t)i * a.nsys + sys] = e.y[i];
@@ -139,32 +142,34 @@ __global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kerne
     }
     // optional outputs, M:1670-1684 (success) / M:1708-1723 (failure)
     const size_t ns = (size_t)a.nsys;
-    a.rout[0 * ns + sys] = e.c.hu;
-    a.rout[1 * ns + sys] = (ist == IST_OK) ? e.c.hnew : e.c.h;
+    a.rout[0 * ns + sys] = e.hot.sd(SD_HU);
+    a.rout[1 * ns + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
     a.rout[2 * ns + sys] = e.c.tn;
     a.rout[3 * ns + sys] = tolsf;
-    a.iout[0 * ns + sys] = e.c.nst;
-    a.iout[1 * ns + sys] = e.c.nfe;
-    a.iout[2 * ns + sys] = e.c.nje;
-    a.iout[3 * ns + sys] = e.c.nqu;
+    a.iout[0 * ns + sys] = e.hot.si(SI_NST);
+    a.iout[1 * ns + sys] = e.hot.si(SI_NFE);
+    a.iout[2 * ns + sys] = e.hot.si(SI_NJE);
+    a.iout[3 * ns + sys] = e.hot.si(SI_NQU);
     a.iout[4 * ns + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
     a.iout[5 * ns + sys] =
         (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
     a.iout[6 * ns + sys] = a.lenrw;
     a.iout[7 * ns + sys] = a.leniw;
-    a.iout[8 * ns + sys] = e.c.nlu;
-    a.iout[9 * ns + sys] = e.c.nni;
-    a.iout[10 * ns + sys] = e.c.ncfn;
-    a.iout[11 * ns + sys] = e.c.netf;
+    a.iout[8 * ns + sys] = e.hot.si(SI_NLU);
+    a.iout[9 * ns + sys] = e.hot.si(SI_NNI);
+    a.iout[10 * ns + sys] = e.hot.si(SI_NCFN);
+    a.iout[11 * ns + sys] = e.hot.si(SI_NETF);
 }
 
 // dvindy for any k (M:1878-1959) from the stored state; one thread per system.
 template <class POL>
 __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_constant__ DkyArgs a) {
+    extern __shared__ double smem_thread[];
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     constexpr int N = POL::N;
     Engine<POL> e;
+    e.hot.bind(smem_thread, threadIdx.x);
     e.acsav.p = nullptr;
     e.lin.wjs.p = nullptr;
     Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(kWarpTPB) vode_warp_kernel(const __grid_consta
         e.c.L = e.c.nq + 1;
         e.c.kflag = 0;
         e.c.jcur = 0;
-        if (e.c.init != 1) {
+        if (e.hot.si(SI_INIT) != 1) {
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
             return;
         }
@@ -313,8 +318,8 @@ __global__ void __launch_bounds__(kWarpTPB) vode_warp_kernel(const __grid_consta
     if (a.y_out && ln < N) {
         for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
     }
-    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.c.nst == 0))
-        tolsf = 2.0 * kUround * POL::norm(e.yh[0], e.ewt);
+    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
+        tolsf = 2.0 * kUround * e.norm_y0();
     const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
 
     if (ln < N) a.y[(size_t)ln * nsys + sys] = e.y[0];
@@ -326,22 +331,22 @@ __global__ void __launch_bounds__(kWarpTPB) vode_warp_kernel(const __grid_consta
     if (ln == 0) {
         a.t[sys] = t;
         a.istate[sys] = ist;
-        a.rout[0 * nsys + sys] = e.c.hu;
-        a.rout[1 * nsys + sys] = (ist == IST_OK) ? e.c.hnew : e.c.h;
+        a.rout[0 * nsys + sys] = e.hot.sd(SD_HU);
+        a.rout[1 * nsys + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
         a.rout[2 * nsys + sys] = e.c.tn;
         a.rout[3 * nsys + sys] = tolsf;
-        a.iout[0 * nsys + sys] = e.c.nst;
-        a.iout[1 * nsys + sys] = e.c.nfe;
-        a.iout[2 * nsys + sys] = e.c.nje;
-        a.iout[3 * nsys + sys] = e.c.nqu;
+        a.iout[0 * nsys + sys] = e.hot.si(SI_NST);
+        a.iout[1 * nsys + sys] = e.hot.si(SI_NFE);
+        a.iout[2 * nsys + sys] = e.hot.si(SI_NJE);
+        a.iout[3 * nsys + sys] = e.hot.si(SI_NQU);
         a.iout[4 * nsys + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
         a.iout[5 * nsys + sys] = imx;
         a.iout[6 * nsys + sys] = a.lenrw;
         a.iout[7 * nsys + sys] = a.leniw;
-        a.iout[8 * nsys + sys] = e.c.nlu;
-        a.iout[9 * nsys + sys] = e.c.nni;
-        a.iout[10 * nsys + sys] = e.c.ncfn;
-        a.iout[11 * nsys + sys] = e.c.netf;
+        a.iout[8 * nsys + sys] = e.hot.si(SI_NLU);
+        a.iout[9 * nsys + sys] = e.hot.si(SI_NNI);
+        a.iout[10 * nsys + sys] = e.hot.si(SI_NCFN);
+        a.iout[11 * nsys + sys] = e.hot.si(SI_NETF);
     }
 }
 
@@ -372,13 +377,20 @@ __global__ void __launch_bounds__(kWarpTPB) dvindy_warp_kernel(const __grid_cons
 template <class POL>
 static int launch_thread(const KArgs &a, cudaStream_t st) {
     const int grid = (a.nsys + kThreadTPB - 1) / kThreadTPB;
-    vode_thread_kernel<POL><<<grid, kThreadTPB, 0, st>>>(a);
+    static_assert(POL::kTPB == kThreadTPB, "shared-memory stride");
+    size_t smem = POL::kSmemBytes;
+    if (const char *pad = getenv("BVODE_PAD_SMEM")) smem += (size_t)atol(pad);  // occupancy experiments
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(vode_thread_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vode_thread_kernel<POL><<<grid, kThreadTPB, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 template <class POL>
 static int launch_dky_thread(const DkyArgs &a, cudaStream_t st) {
     const int grid = (a.nsys + kThreadTPB - 1) / kThreadTPB;
-    dvindy_thread_kernel<POL><<<grid, kThreadTPB, 0, st>>>(a);
+    if (POL::kSmemBytes > 48 * 1024)
+        cudaFuncSetAttribute(dvindy_thread_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL::kSmemBytes);
+    dvindy_thread_kernel<POL><<<grid, kThreadTPB, POL::kSmemBytes, st>>>(a);
     return (int)cudaGetLastError();
 }
 template <class POL>

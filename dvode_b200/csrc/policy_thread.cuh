@@ -41,20 +41,63 @@ struct ThreadPolicy {
         BV_DEV double atol(int i) const { return a[i]; }
     };
 
+    // Hot per-system arrays.  Default (BVODE_THREAD_SMEM = 0): registers.  = 1 keeps them in
+    // shared memory, element e of thread t at sm[e * TPB + t] (conflict-free, compile-time
+    // offsets).  Measured on B200 (2^20 Robertson systems): registers 305 ms; shared memory
+    // 328 ms at 8 warps/SM (231 registers: ptxas hoists the loads back into registers), and
+    // 436 ms / 506 ms when capped to 168 / 128 registers (spills) -- halving the resident
+    // warps costs 1.58x, so occupancy helps, but not through this route.  Kept as a knob.
+#ifndef BVODE_THREAD_SMEM
+#define BVODE_THREAD_SMEM 0
+#endif
+    static constexpr int kTPB = 128;
+    // doubles: yh[6][N], tau[6], p[N][N], el[6], tq[5], sd[SD_COUNT]; ints: si[SI_COUNT]
+    static constexpr int kOffTau = kLmax * N, kOffP = kOffTau + kLmax, kOffEl = kOffP + N * N,
+                         kOffTq = kOffEl + kLmax, kOffSd = kOffTq + 5,
+                         kHotDoubles = kOffSd + SD_COUNT;
+#if BVODE_THREAD_SMEM
+    struct Hot {
+        double *b;  // this thread's element 0 of the double region
+        int *bi;    // ... of the int region
+        BV_DEV double &yh(int j, int i) const { return b[(j * N + i) * kTPB]; }
+        BV_DEV double &tau(int i) const { return b[(kOffTau + (i - 1)) * kTPB]; }
+        BV_DEV double &p(int i, int j) const { return b[(kOffP + i * N + j) * kTPB]; }
+        BV_DEV double &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
+        BV_DEV double &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
+        BV_DEV double &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
+        BV_DEV int &si(int k) const { return bi[k * kTPB]; }
+        BV_DEV void bind(double *smem, int tid) {
+            b = smem + tid;
+            bi = reinterpret_cast<int *>(smem + (size_t)kHotDoubles * kTPB) + tid;
+        }
+    };
+    static constexpr size_t kSmemBytes = (sizeof(double) * kHotDoubles + sizeof(int) * SI_COUNT) * kTPB;
+#else
+    struct Hot {
+        double yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
+        int siv[SI_COUNT];
+        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV double &tau(int i) { return tauv[i]; }
+        BV_DEV double &p(int i, int j) { return pv[i][j]; }
+        BV_DEV double &el(int i) { return elv[i]; }
+        BV_DEV double &tq(int i) { return tqv[i]; }
+        BV_DEV double &sd(int k) { return sdv[k]; }
+        BV_DEV int &si(int k) { return siv[k]; }
+        BV_DEV void bind(double *, int) {}
+    };
+    static constexpr size_t kSmemBytes = 0;
+#endif
+
     struct Lin {
-        double p[N][N];   // P = I - h*rl1*J, then its LU factors (p[i][j] = row i, col j).
-                          // Fast build: the diagonal holds 1/u_kk after dgefa.
+        // P = I - h*rl1*J and then its LU factors are hot.p(i, j) (row i, col j); fast build:
+        // the diagonal holds 1/u_kk after dgefa.
         GlobalVec wjs;    // saved Jacobian wm(locjs), element (i,j) at slot i*N+j (mf > 0)
         int ipvt[N];      // 0-based pivot rows
     };
 
     BV_DEV static void lin_init(Lin &l) {
 #pragma unroll
-        for (int i = 0; i < N; i++) {
-            l.ipvt[i] = i;
-#pragma unroll
-            for (int j = 0; j < N; j++) l.p[i][j] = 0.0;
-        }
+        for (int i = 0; i < N; i++) l.ipvt[i] = i;
     }
 
     // state slots of one system, in visit order: yh, acsav*, acor, p, wjs*, tau, scalars
@@ -64,12 +107,13 @@ struct ThreadPolicy {
 
     template <class V>
     BV_DEV static void visit_acsav(AcSav &, V &v) { v.skip_d(N); }
-    template <class V>
-    BV_DEV static void visit_lin(Lin &l, V &v) {
+    template <class ENG, class V>
+    BV_DEV static void visit_lin(ENG &e, V &v) {
+        Lin &l = e.lin;
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
-            for (int j = 0; j < N; j++) v.d(l.p[i][j]);
+            for (int j = 0; j < N; j++) v.d(e.hot.p(i, j));
         if (SAVEJ) v.skip_d(N * N);
 #pragma unroll
         for (int i = 0; i < N; i++) v.i(l.ipvt[i]);
@@ -89,6 +133,18 @@ struct ThreadPolicy {
         return sqrt(sum * (1.0 / (double)N));
 #endif
     }
+#if !BVODE_STRICT
+    // mean square (norm^2) -- the fast build tests squares and keeps sqrt off the main path
+    BV_DEV static double msq(const double (&v)[N], const double (&w)[N]) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const double p = v[i] * w[i];
+            sum = sum + p * p;
+        }
+        return sum * (1.0 / (double)N);
+    }
+#endif
     BV_DEV static bool any_le_zero(const double (&v)[N]) {
         bool bad = false;
 #pragma unroll
@@ -122,59 +178,62 @@ struct ThreadPolicy {
     }
 
     // ---- dgefa, LP:46-120 ----------------------------------------------------------
-    BV_DEV static int dgefa(double (&a)[N][N], int (&ipvt)[N]) {
+    BV_DEV static int dgefa(Hot &hot, int (&ipvt)[N]) {
+#define a_(i, j) hot.p(i, j)
         int info = 0;
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
             // idamax over rows k..N-1 of column k
             int l = k;
-            double dmax = fabs(a[k][k]);
+            double dmax = fabs(a_(k, k));
 #pragma unroll
             for (int i = k + 1; i < N; i++) {
-                const double xmag = fabs(a[i][k]);
+                const double xmag = fabs(a_(i, k));
                 if (xmag > dmax) { l = i; dmax = xmag; }
             }
             ipvt[k] = l;
-            double alk = a[k][k];
+            double alk = a_(k, k);
 #pragma unroll
-            for (int i = k + 1; i < N; i++) alk = (l == i) ? a[i][k] : alk;
+            for (int i = k + 1; i < N; i++) alk = (l == i) ? a_(i, k) : alk;
             if (alk == 0.0) {
                 info = k + 1;
             } else {
                 // interchange a(l,k) <-> a(k,k)
-                const double akk = a[k][k];
+                const double akk = a_(k, k);
 #pragma unroll
-                for (int i = k + 1; i < N; i++) a[i][k] = (l == i) ? akk : a[i][k];
-                a[k][k] = alk;
+                for (int i = k + 1; i < N; i++) a_(i, k) = (l == i) ? akk : a_(i, k);
+                a_(k, k) = alk;
                 const double t = -1.0 / alk;
 #pragma unroll
-                for (int i = k + 1; i < N; i++) a[i][k] = t * a[i][k];
+                for (int i = k + 1; i < N; i++) a_(i, k) = t * a_(i, k);
 #pragma unroll
                 for (int j = k + 1; j < N; j++) {
-                    double tj = a[k][j];
+                    double tj = a_(k, j);
 #pragma unroll
-                    for (int i = k + 1; i < N; i++) tj = (l == i) ? a[i][j] : tj;
-                    const double akj = a[k][j];
+                    for (int i = k + 1; i < N; i++) tj = (l == i) ? a_(i, j) : tj;
+                    const double akj = a_(k, j);
 #pragma unroll
-                    for (int i = k + 1; i < N; i++) a[i][j] = (l == i) ? akj : a[i][j];
-                    a[k][j] = tj;
+                    for (int i = k + 1; i < N; i++) a_(i, j) = (l == i) ? akj : a_(i, j);
+                    a_(k, j) = tj;
 #pragma unroll
-                    for (int i = k + 1; i < N; i++) a[i][j] = a[i][j] + tj * a[i][k];
+                    for (int i = k + 1; i < N; i++) a_(i, j) = a_(i, j) + tj * a_(i, k);
                 }
             }
         }
         ipvt[N - 1] = N - 1;
-        if (a[N - 1][N - 1] == 0.0) info = N;
+        if (a_(N - 1, N - 1) == 0.0) info = N;
 #if !BVODE_STRICT
         // fast build: keep 1/u_kk on the diagonal so that dgesl multiplies instead of divides
 #pragma unroll
-        for (int k = 0; k < N; k++) a[k][k] = 1.0 / a[k][k];
+        for (int k = 0; k < N; k++) a_(k, k) = 1.0 / a_(k, k);
 #endif
         return info;
+#undef a_
     }
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------
-    BV_DEV static void dgesl(const double (&a)[N][N], const int (&ipvt)[N], double (&b)[N]) {
+    BV_DEV static void dgesl(Hot &hot, const int (&ipvt)[N], double (&b)[N]) {
+#define a_(i, j) hot.p(i, j)
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
             const int l = ipvt[k];
@@ -186,22 +245,24 @@ struct ThreadPolicy {
             for (int i = k + 1; i < N; i++) b[i] = (l == i) ? bk : b[i];
             b[k] = t;
 #pragma unroll
-            for (int i = k + 1; i < N; i++) b[i] = b[i] + t * a[i][k];
+            for (int i = k + 1; i < N; i++) b[i] = b[i] + t * a_(i, k);
         }
 #pragma unroll
         for (int k = N - 1; k >= 0; k--) {
 #if BVODE_STRICT
-            b[k] = b[k] / a[k][k];
+            b[k] = b[k] / a_(k, k);
 #else
-            b[k] = b[k] * a[k][k];
+            b[k] = b[k] * a_(k, k);
 #endif
             const double t = -b[k];
 #pragma unroll
-            for (int i = 0; i < k; i++) b[i] = b[i] + t * a[i][k];
+            for (int i = 0; i < k; i++) b[i] = b[i] + t * a_(i, k);
         }
+#undef a_
     }
 
-    BV_DEV static void solve(const Lin &l, double (&x)[N]) { dgesl(l.p, l.ipvt, x); }
+    template <class ENG>
+    BV_DEV static void solve(ENG &e, double (&x)[N]) { dgesl(e.hot, e.lin.ipvt, x); }
 
     // ---- dvjac, miter 1 / 2 (M:2930-3001) -------------------------------------------
     template <class ENG>
@@ -212,20 +273,31 @@ struct ThreadPolicy {
         const double hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
-            if (c.nst == 0 || c.nst > c.nslj + 50) jok = -1;      // msbj = 50, M:1328
+            if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;      // msbj = 50, M:1328
             if (c.icf == 1 && c.drc < 0.2) jok = -1;              // ccmxj = 0.2, M:1327
             if (c.icf == 2) jok = -1;
         }
         if (jok == -1) {
-            c.nje = c.nje + 1;
-            c.nslj = c.nst;
+            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if (MITER == 1) {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.p[i][j] = 0.0;
-                PROB::jac(c.tn, e.y, l.p, e.par);
+                    for (int j = 0; j < N; j++) e.hot.p(i, j) = 0.0;
+                {
+                    double pd[N][N];
+#pragma unroll
+                    for (int i = 0; i < N; i++)
+#pragma unroll
+                        for (int j = 0; j < N; j++) pd[i][j] = 0.0;
+                    PROB::jac(c.tn, e.y, pd, e.par);
+#pragma unroll
+                    for (int i = 0; i < N; i++)
+#pragma unroll
+                        for (int j = 0; j < N; j++) e.hot.p(i, j) = pd[i][j];
+                }
             } else {
                 // finite differences, M:2959-2976 (ftem = acor)
                 double fac = norm(e.savf, e.ewt);
@@ -240,16 +312,16 @@ struct ThreadPolicy {
                     fac = 1.0 / r;
                     f(c.tn, e.y, e.acor, e.par);
 #pragma unroll
-                    for (int i = 0; i < N; i++) l.p[i][j] = (e.acor[i] - e.savf[i]) * fac;
+                    for (int i = 0; i < N; i++) e.hot.p(i, j) = (e.acor[i] - e.savf[i]) * fac;
                     e.y[j] = yj;
                 }
-                c.nfe = c.nfe + N;
+                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
             }
             if (SAVEJ) {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, l.p[i][j]);
+                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, e.hot.p(i, j));
             }
         } else {
             c.jcur = 0;
@@ -257,18 +329,18 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.p[i][j] = l.wjs.get(i * N + j);
+                    for (int j = 0; j < N; j++) e.hot.p(i, j) = l.wjs.get(i * N + j);
             }
         }
         const double con = -hrl1;
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
-            for (int j = 0; j < N; j++) l.p[i][j] = con * l.p[i][j];
+            for (int j = 0; j < N; j++) e.hot.p(i, j) = con * e.hot.p(i, j);
 #pragma unroll
-        for (int i = 0; i < N; i++) l.p[i][i] = l.p[i][i] + 1.0;
-        c.nlu = c.nlu + 1;
-        const int ier = dgefa(l.p, l.ipvt);
+        for (int i = 0; i < N; i++) e.hot.p(i, i) = e.hot.p(i, i) + 1.0;
+        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
+        const int ier = dgefa(e.hot, l.ipvt);
         if (ier != 0) ierpj = 1;
     }
 };

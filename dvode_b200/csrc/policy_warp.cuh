@@ -41,6 +41,17 @@ struct WarpCommon {
         BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
         BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
     };
+    struct Hot {  // NLOC = 1: registers
+        double yhv[kLmax][1], tauv[kLmax + 1], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
+        int siv[SI_COUNT];
+        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV double &tau(int i) { return tauv[i]; }
+        BV_DEV double &el(int i) { return elv[i]; }
+        BV_DEV double &tq(int i) { return tqv[i]; }
+        BV_DEV double &sd(int k) { return sdv[k]; }
+        BV_DEV int &si(int k) { return siv[k]; }
+        BV_DEV void bind(double *, int) {}
+    };
     struct AcSav {  // NLOC = 1: a register
         double v;
         BV_DEV double get(int) const { return v; }
@@ -68,6 +79,15 @@ struct WarpCommon {
         return sqrt(sum * (1.0 / (double)N));
 #endif
     }
+#if !BVODE_STRICT
+    BV_DEV static double msq(const double (&v)[1], const double (&w)[1]) {
+        const double p = v[0] * w[0];
+        double sum = (lane() < N) ? p * p : 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
+        return sum * (1.0 / (double)N);
+    }
+#endif
     BV_DEV static bool any_le_zero(const double (&v)[1]) {
         return __any_sync(kFull, (lane() < N) && (v[0] <= 0.0)) != 0;
     }
@@ -127,6 +147,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     using Base = WarpCommon<PROB>;
     using Prob = PROB;
     using typename Base::GlobalVec;
+    using typename Base::Hot;
     using Base::lane;
     static constexpr int N = PROB::N;
     static constexpr int NLOC = 1;
@@ -152,8 +173,9 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     static constexpr int kLaneIntSlots = 1;
     template <class V>
     BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
-    template <class V>
-    BV_DEV static void visit_lin(Lin &l, V &v) {
+    template <class ENG, class V>
+    BV_DEV static void visit_lin(ENG &e, V &v) {
+        Lin &l = e.lin;
 #pragma unroll
         for (int j = 0; j < N; j++) v.dv(l.p[j]);
         if (SAVEJ) v.skip_dv(N);
@@ -203,7 +225,9 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     }
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------------
-    BV_DEV static void solve(const Lin &lin, double (&x)[1]) {
+    template <class ENG>
+    BV_DEV static void solve(ENG &e, double (&x)[1]) {
+        const Lin &lin = e.lin;
         const int ln = lane();
         double b = x[0];
 #pragma unroll
@@ -240,13 +264,13 @@ struct WarpDensePolicy : WarpCommon<PROB> {
         const double hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
-            if (c.nst == 0 || c.nst > c.nslj + 50) jok = -1;
+            if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;
             if (c.icf == 1 && c.drc < 0.2) jok = -1;
             if (c.icf == 2) jok = -1;
         }
         if (jok == -1) {
-            c.nje = c.nje + 1;
-            c.nslj = c.nst;
+            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if constexpr (MITER == 1) {
 #pragma unroll
@@ -267,7 +291,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
                     l.p[j] = (e.acor[0] - e.savf[0]) * fac;
                     e.y[0] = ysave;
                 }
-                c.nfe = c.nfe + N;
+                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
             }
             if (SAVEJ) {
 #pragma unroll
@@ -286,7 +310,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
             l.p[j] = con * l.p[j];
             if (ln == j) l.p[j] = l.p[j] + 1.0;
         }
-        c.nlu = c.nlu + 1;
+        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
         const int ier = dgefa(l.p, l.ipv);
         if (ier != 0) ierpj = 1;
     }
@@ -328,8 +352,9 @@ struct WarpBandPolicy : WarpCommon<PROB> {
     static constexpr int kLaneIntSlots = 1;
     template <class V>
     BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
-    template <class V>
-    BV_DEV static void visit_lin(Lin &l, V &v) {
+    template <class ENG, class V>
+    BV_DEV static void visit_lin(ENG &e, V &v) {
+        Lin &l = e.lin;
         // band arrays: the whole shared-memory image of this system, cooperatively
         const int nb = l.ld * N + (SAVEJ ? (l.ml + l.mu + 1) * N : 0);
         v.block(l.abd, nb);
@@ -406,7 +431,9 @@ struct WarpBandPolicy : WarpCommon<PROB> {
     }
 
     // ---- dgbsl job = 0, LP:494-519: b_i in lane i-1 ------------------------------------------
-    BV_DEV static void solve(const Lin &l, double (&x)[1]) {
+    template <class ENG>
+    BV_DEV static void solve(ENG &e, double (&x)[1]) {
+        const Lin &l = e.lin;
         const int ln = lane();
         const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
         double b = x[0];
@@ -449,14 +476,14 @@ struct WarpBandPolicy : WarpCommon<PROB> {
         const double hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
-            if (c.nst == 0 || c.nst > c.nslj + 50) jok = -1;
+            if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;
             if (c.icf == 1 && c.drc < 0.2) jok = -1;
             if (c.icf == 2) jok = -1;
         }
         __syncwarp();
         if (jok == -1) {
-            c.nje = c.nje + 1;
-            c.nslj = c.nst;
+            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if constexpr (MITER == 4) {
                 // zero wm(3:), then jac fills rows ml+1..meband of each column (M:3044-3047)
@@ -492,7 +519,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
                         if (i >= i1 && i <= i2) ABD(i - jj + mband, jj) = diff * fac;
                     }
                 }
-                c.nfe = c.nfe + mba;
+                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + mba;
             }
             __syncwarp();
             if (SAVEJ) {  // dacopy(mband, n, wm(ml3), meband, wm(locjs), mband)
@@ -514,7 +541,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
             ABD(mband, ln + 1) = ABD(mband, ln + 1) + 1.0;
         }
         __syncwarp();
-        c.nlu = c.nlu + 1;
+        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
         const int ier = dgbfa(l);
         if (ier != 0) ierpj = 1;
     }

@@ -44,12 +44,17 @@ enum : int {
 
 // Scalar per-system state: the members of dvode_data_t (M:40-153) that are not
 // batch-uniform.  el/tau/tq are 1-based like the reference (element 0 unused).
+// Hot scalars (touched several times per step attempt) stay in this struct, i.e. in registers.
+// The rest of dvode_data_t -- tau(1:6), el(1:6), tq(1:5), conp, hu, hnew, crate, etamax and
+// the counters -- is reached through the policy's `Hot` storage (shared memory for the
+// thread-per-system policy, registers for the warp policies) by the slot ids below.
 struct Ctl {
-    double h, hscal, hnew, hu, eta, etamax, tn, rc, prl1, rl1, crate, drc, acnrm, conp;
-    double tau[kLmax + 1], el[kLmax + 1], tq[6];
-    int nq, L, nqwait, newq, newh, jstart, icf, ipup, jcur, kflag, nslj, nslp, nhnil, init;
-    int nst, nfe, nje, nlu, nni, ncfn, netf, nqu;
+    double h, hscal, eta, tn, rc, prl1, rl1, drc, acnrm;
+    int nq, L, nqwait, newq, newh, jstart, icf, ipup, jcur, kflag;
 };
+enum : int { SD_CONP = 0, SD_HU, SD_HNEW, SD_CRATE, SD_ETAMAX, SD_COUNT };
+enum : int { SI_NST = 0, SI_NFE, SI_NJE, SI_NLU, SI_NNI, SI_NCFN, SI_NETF, SI_NQU, SI_NSLJ,
+             SI_NSLP, SI_NHNIL, SI_INIT, SI_COUNT };
 
 using Opts = ::BvOpts;  // batch-uniform optional inputs (M:729-751)
 
@@ -61,61 +66,76 @@ BV_DEV double pick(const double *a, int idx) {
     return r;
 }
 
+template <int LO, int HI, class HOT>
+BV_DEV double pick_el(HOT &hot, int idx) {
+    double r = hot.el(LO);
+#pragma unroll
+    for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? hot.el(i) : r;
+    return r;
+}
+template <int LO, int HI, class HOT>
+BV_DEV double pick_tau(HOT &hot, int idx) {
+    double r = hot.tau(LO);
+#pragma unroll
+    for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? hot.tau(i) : r;
+    return r;
+}
+
 // ---------------------------------------------------------------- dvset (BDF) ----
 // M:2440-2490, 2559.  Loops are unrolled to the compile-time maximum order and guarded
 // by nq, so el/tau stay in registers.
-BV_DEV void dvset_bdf(Ctl &c) {
+template <class HOT>
+BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const int nq = c.nq, L = c.L;
-    double *el = c.el, *tau = c.tau, *tq = c.tq;
     const double h = c.h;
 #pragma unroll
-    for (int i = 3; i <= kLmax; i++) el[i] = 0.0;
-    el[1] = 1.0;
-    el[2] = 1.0;
+    for (int i = 3; i <= kLmax; i++) hot.el(i) = 0.0;
+    hot.el(1) = 1.0;
+    hot.el(2) = 1.0;
     double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
     if (nq != 1) {
 #pragma unroll
         for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
             if (j <= nq - 2) {
-                hsum = hsum + tau[j];
+                hsum = hsum + hot.tau(j);
                 rxi = h / hsum;
                 alph0 = alph0 - 1.0 / (double)(j + 1);
 #pragma unroll
                 for (int iback = 1; iback <= j + 1; iback++) {
                     const int i = (j + 3) - iback;
-                    el[i] = el[i] + el[i - 1] * rxi;
+                    hot.el(i) = hot.el(i) + hot.el(i - 1) * rxi;
                 }
             }
         }
         alph0 = alph0 - recip_int(nq);
-        rxis = -el[2] - alph0;
-        hsum = hsum + pick<1, kMaxOrdBdf>(tau, nq - 1);
+        rxis = -hot.el(2) - alph0;
+        hsum = hsum + pick_tau<1, kMaxOrdBdf>(hot, nq - 1);
         rxi = h / hsum;
-        ahatn0 = -el[2] - rxi;
+        ahatn0 = -hot.el(2) - rxi;
 #pragma unroll
         for (int i = kLmax; i >= 2; i--) {
-            if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
+            if (i <= nq + 1) hot.el(i) = hot.el(i) + hot.el(i - 1) * rxis;
         }
     }
     const double t1 = 1.0 - ahatn0 + alph0;
     const double t2 = 1.0 + (double)nq * t1;
-    const double elL = pick<2, kLmax>(el, L);
-    tq[2] = fabs(alph0 * t2 / t1);
-    tq[5] = fabs(t2 / (elL * rxi / rxis));
+    const double elL = pick_el<2, kLmax>(hot, L);
+    hot.tq(2) = fabs(alph0 * t2 / t1);
+    hot.tq(5) = fabs(t2 / (elL * rxi / rxis));
     if (c.nqwait == 1) {
         const double cnqm1 = rxis / elL;
         const double t3 = alph0 + recip_int(nq);
         const double t4 = ahatn0 + rxi;
         double elp = t3 / (1.0 - t4 + t3);
-        tq[1] = fabs(elp / cnqm1);
-        hsum = hsum + pick<1, kLmax>(tau, nq);
+        hot.tq(1) = fabs(elp / cnqm1);
+        hsum = hsum + pick_tau<1, kLmax>(hot, nq);
         rxi = h / hsum;
         const double t5 = alph0 - recip_int(nq + 1);
         const double t6 = ahatn0 - rxi;
         elp = t2 / (1.0 - t6 + t5);
-        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
+        hot.tq(3) = fabs(elp * rxi * ((double)L + 1.0) * t5);
     }
-    tq[4] = 0.1 * tq[2];
+    hot.tq(4) = 0.1 * hot.tq(2);
 }
 
 // dvjust coefficient part for both directions (the yh updates are done by the engine):
@@ -123,19 +143,19 @@ BV_DEV void dvset_bdf(Ctl &c) {
 // The two branches of the reference share the recurrence el(i) = el(i)*x + el(i-1); they are
 // one code path here so that lanes raising and lowering their order execute together.
 // Returns t1 = (-alph0 - alph1)/prod for the order increase.
-BV_DEV double dvjust_coeffs(Ctl &c, bool up) {
-    double *el = c.el, *tau = c.tau;
+template <class HOT>
+BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up) {
     const int nq = c.nq;
 #pragma unroll
-    for (int j = 1; j <= kLmax; j++) el[j] = 0.0;
-    el[3] = 1.0;
+    for (int j = 1; j <= kLmax; j++) hot.el(j) = 0.0;
+    hot.el(3) = 1.0;
     double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
     double hsum = up ? c.hscal : 0.0;
     const int jmax = up ? nq - 1 : nq - 2;
 #pragma unroll
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
         if (j <= jmax) {
-            hsum = hsum + (up ? tau[j + 1] : tau[j]);
+            hsum = hsum + (up ? hot.tau(j + 1) : hot.tau(j));
             const double xi = hsum / c.hscal;
             if (up) {
                 prod = prod * xi;
@@ -146,7 +166,7 @@ BV_DEV double dvjust_coeffs(Ctl &c, bool up) {
 #pragma unroll
             for (int iback = 1; iback <= j + 1; iback++) {
                 const int i = (j + 4) - iback;
-                el[i] = el[i] * x + el[i - 1];
+                hot.el(i) = hot.el(i) * x + hot.el(i - 1);
             }
             xiold = xi;
         }
@@ -182,7 +202,8 @@ struct Engine {
     static constexpr int MITER = POL::MITER;
 
     Ctl c;
-    double yh[kLmax][NLOC];  // Nordsieck history, column j = h^j y^(j) / j!
+    typename POL::Hot hot;   // yh(j,i): Nordsieck history, column j = h^j y^(j)/j!; tau(1:6);
+                             // (thread policy) the Newton matrix -- registers or shared memory
     double ewt[NLOC];        // stored inverted (M:1359, 1522)
     double savf[NLOC], acor[NLOC], y[NLOC];
     typename POL::Par par;   // per-system parameters of f / jac, as this thread holds them
@@ -195,10 +216,25 @@ struct Engine {
     BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
         double e[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) e[i] = tol.rtol(i) * fabs(yh[0][i]) + tol.atol(i);
+        for (int i = 0; i < NLOC; i++) e[i] = tol.rtol(i) * fabs(hot.yh(0, i)) + tol.atol(i);
         bad = POL::any_le_zero(e);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) ewt[i] = 1.0 / e[i];
+    }
+
+#if !BVODE_STRICT
+    BV_DEV double msq_y0() {
+        double y0v[NLOC];
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
+        return POL::msq(y0v, ewt);
+    }
+#endif
+    BV_DEV double norm_y0() {  // dvnorm(yh(:,1), ewt), M:1525
+        double y0v[NLOC];
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
+        return POL::norm(y0v, ewt);
     }
 
     BV_DEV void predict() {  // M:2148-2154 at full order (zero-column invariant)
@@ -207,7 +243,7 @@ struct Engine {
 #pragma unroll
             for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + yh[j][i];
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.yh(j, i);
             }
         }
     }
@@ -217,7 +253,7 @@ struct Engine {
 #pragma unroll
             for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] - yh[j][i];
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) - hot.yh(j, i);
             }
         }
     }
@@ -230,21 +266,21 @@ struct Engine {
         for (int j = 2; j <= kLmax; j++) {
             r = r * eta;
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) yh[j - 1][i] = r * yh[j - 1][i];
+            for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = r * hot.yh(j - 1, i);
         }
         c.h = c.hscal * eta;
         c.hscal = c.h;
         c.rc = c.rc * eta;
     }
     // column `col` (1-based) of yh selected at run time
-    BV_DEV void get_col(int col, double (&out)[NLOC]) const {
+    BV_DEV void get_col(int col, double (&out)[NLOC]) {
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) out[i] = yh[0][i];
+        for (int i = 0; i < NLOC; i++) out[i] = hot.yh(0, i);
 #pragma unroll
         for (int j = 2; j <= kLmax; j++) {
             if (col == j) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) out[i] = yh[j - 1][i];
+                for (int i = 0; i < NLOC; i++) out[i] = hot.yh(j - 1, i);
             }
         }
     }
@@ -254,7 +290,7 @@ struct Engine {
     //         column L is zeroed to keep the zero-column invariant.
     //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
     BV_DEV void order_change(bool up) {
-        const double t1 = dvjust_coeffs(c, up);
+        const double t1 = dvjust_coeffs(c, hot, up);
         double col[NLOC];
         if (up) {
 #pragma unroll
@@ -270,40 +306,40 @@ struct Engine {
         for (int j = 3; j <= kLmax; j++) {
             if (j <= jhi) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * col[i];
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.el(j) * col[i];
             }
             if (j == jnew) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) yh[j - 1][i] = up ? col[i] : 0.0;
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = up ? col[i] : 0.0;
             }
         }
     }
 
     // ---- dvindy, k = 0 (M:1905-1952).  iflag as in the reference. ----------------
-    BV_DEV int dvindy0(double t, double (&dky)[NLOC]) const {
-        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(c.hu), c.hu);
-        const double tp = c.tn - c.hu - tfuzz;
+    BV_DEV int dvindy0(double t, double (&dky)[NLOC]) {
+        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
+        const double tp = c.tn - hot.sd(SD_HU) - tfuzz;
         const double tn1 = c.tn + tfuzz;
         if ((t - tp) * (t - tn1) > 0.0) return -2;
         const double s = (t - c.tn) / c.h;
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) dky[i] = yh[kLmax - 1][i];
+        for (int i = 0; i < NLOC; i++) dky[i] = hot.yh(kLmax - 1, i);
 #pragma unroll
         for (int j = kLmax - 2; j >= 0; j--) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) dky[i] = yh[j][i] + s * dky[i];
+            for (int i = 0; i < NLOC; i++) dky[i] = hot.yh(j, i) + s * dky[i];
         }
         return 0;
     }
 
     // ---- dvindy for any k (M:1905-1957), from the current state --------------------------
-    BV_DEV int dvindy_k(double t, int k, double (&dky)[NLOC]) const {
+    BV_DEV int dvindy_k(double t, int k, double (&dky)[NLOC]) {
         const int nq = c.nq, L = nq + 1;
 #pragma unroll
         for (int i = 0; i < NLOC; i++) dky[i] = 0.0;
         if (k < 0 || k > nq) return -1;
-        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(c.hu), c.hu);
-        const double tp = c.tn - c.hu - tfuzz;
+        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
+        const double tp = c.tn - hot.sd(SD_HU) - tfuzz;
         const double tn1 = c.tn + tfuzz;
         if ((t - tp) * (t - tn1) > 0.0) return -2;
         const double s = (t - c.tn) / c.h;
@@ -344,7 +380,12 @@ struct Engine {
         if (tdist < 2.0 * tround) return -1;
         const double hlb = 100.0 * tround;
         double hub = 0.1 * tdist;
-        hub = POL::hin_upper_bound(hub, yh[0], yh[1], tol);
+        {
+            double y0v[NLOC], ydv[NLOC];
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) { y0v[i] = hot.yh(0, i); ydv[i] = hot.yh(1, i); }
+            hub = POL::hin_upper_bound(hub, y0v, ydv, tol);
+        }
         int iter = 0;
         double hg = sqrt(hlb * hub);
         if (hub < hlb) {
@@ -357,10 +398,10 @@ struct Engine {
                 const double h = dsign(hg, tout - t0);
                 const double t1 = t0 + h;
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + h * yh[1][i];
+                for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + h * hot.yh(1, i);
                 POL::f(t1, y, acor, par);
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) acor[i] = (acor[i] - yh[1][i]) / h;
+                for (int i = 0; i < NLOC; i++) acor[i] = (acor[i] - hot.yh(1, i)) / h;
                 const double yddnrm = POL::norm(acor, ewt);
                 if (yddnrm * hub * hub > 2.0) hnew = sqrt(2.0 / yddnrm);
                 else hnew = sqrt(hg * hub);
@@ -392,31 +433,33 @@ struct Engine {
     BV_DEV int init_problem(double t, double tout) {
         c.tn = t;
         c.jstart = 0;
-        c.nhnil = 0;
-        c.nst = c.nje = c.nni = c.ncfn = c.netf = c.nlu = 0;
-        c.nslj = 0;
-        c.hu = 0.0;
-        c.nqu = 0;
-        c.init = 0;
-        c.icf = 0; c.ipup = 0; c.jcur = 0; c.kflag = 0; c.nslp = 0; c.newh = 0; c.newq = 0;
-        c.eta = 0.0; c.hnew = 0.0; c.conp = 0.0; c.crate = 0.0; c.drc = 0.0; c.acnrm = 0.0;
-        c.rl1 = 0.0; c.etamax = 0.0; c.hscal = 0.0; c.rc = 0.0; c.prl1 = 0.0;
+        hot.si(SI_NHNIL) = 0;
+        hot.si(SI_NST) = hot.si(SI_NJE) = hot.si(SI_NNI) = hot.si(SI_NCFN) = hot.si(SI_NETF) = hot.si(SI_NLU) = 0;
+        hot.si(SI_NSLJ) = 0;
+        hot.sd(SD_HU) = 0.0;
+        hot.si(SI_NQU) = 0;
+        hot.si(SI_INIT) = 0;
+        c.icf = 0; c.ipup = 0; c.jcur = 0; c.kflag = 0; hot.si(SI_NSLP) = 0; c.newh = 0; c.newq = 0;
+        c.eta = 0.0; hot.sd(SD_HNEW) = 0.0; hot.sd(SD_CONP) = 0.0; hot.sd(SD_CRATE) = 0.0; c.drc = 0.0; c.acnrm = 0.0;
+        c.rl1 = 0.0; hot.sd(SD_ETAMAX) = 0.0; c.hscal = 0.0; c.rc = 0.0; c.prl1 = 0.0;
 #pragma unroll
-        for (int j = 0; j <= kLmax; j++) { c.tau[j] = 0.0; c.el[j] = 0.0; }
+        for (int j = 1; j <= kLmax; j++) { hot.tau(j) = 0.0; hot.el(j) = 0.0; }
 #pragma unroll
-        for (int j = 0; j < 6; j++) c.tq[j] = 0.0;
+        for (int j = 1; j <= 5; j++) hot.tq(j) = 0.0;
 #pragma unroll
         for (int j = 0; j < kLmax; j++) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) yh[j][i] = 0.0;
+            for (int i = 0; i < NLOC; i++) hot.yh(j, i) = 0.0;
         }
 #pragma unroll
         for (int i = 0; i < NLOC; i++) { acsav.set(i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
         POL::lin_init(lin);
-        POL::f(t, y, yh[1], par);
-        c.nfe = 1;
+        POL::f(t, y, savf, par);
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) yh[0][i] = y[i];
+        for (int i = 0; i < NLOC; i++) hot.yh(1, i) = savf[i];
+        hot.si(SI_NFE) = 1;
+#pragma unroll
+        for (int i = 0; i < NLOC; i++) hot.yh(0, i) = y[i];
         c.nq = 1;
         c.L = 2;
         c.h = 1.0;
@@ -427,14 +470,14 @@ struct Engine {
         if (h0 == 0.0) {
             int niter;
             const int ier = dvhin(t, tout, h0, niter);
-            c.nfe = c.nfe + niter;
+            hot.si(SI_NFE) = hot.si(SI_NFE) + niter;
             if (ier != 0) return IST_ILLEGAL;  // message 22
         }
         const double rh = fabs(h0) * o.hmax_inv;
         if (rh > 1.0) h0 = h0 / rh;
         c.h = h0;
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) yh[1][i] = h0 * yh[1][i];
+        for (int i = 0; i < NLOC; i++) hot.yh(1, i) = h0 * hot.yh(1, i);
         return 0;
     }
 
@@ -445,12 +488,12 @@ struct Engine {
     BV_DEV int dvnlsd(int nflag, double rtq4) {
         constexpr int maxcor = 3, msbp = 20;
         constexpr double ccmax = 0.3, crdown = 0.3, rdiv = 2.0;
-        if (c.jstart == 0) c.nslp = 0;
+        if (c.jstart == 0) hot.si(SI_NSLP) = 0;
         if (nflag == 0) c.icf = 0;
         if (nflag == -2) c.ipup = MITER;
         if (c.jstart == 0) c.ipup = MITER;
         c.drc = fabs(c.rc - 1.0);
-        if (c.drc > ccmax || c.nst >= c.nslp + msbp) c.ipup = MITER;
+        if (c.drc > ccmax || hot.si(SI_NST) >= hot.si(SI_NSLP) + msbp) c.ipup = MITER;
         (void)rtq4;
 
         int result = 1;  // 1 = another corrector pass is needed
@@ -460,17 +503,17 @@ struct Engine {
             double delp = 0.0, del = 0.0;
             bool converged = false, singular = false;
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) y[i] = yh[0][i];
+            for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
             POL::f(c.tn, y, savf, par);
-            c.nfe = c.nfe + 1;
+            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
             if (c.ipup > 0) {
                 int ierpj;
                 POL::jac_setup(*this, ierpj);
                 c.ipup = 0;
                 c.rc = 1.0;
                 c.drc = 0.0;
-                c.crate = 1.0;
-                c.nslp = c.nst;
+                hot.sd(SD_CRATE) = 1.0;
+                hot.si(SI_NSLP) = hot.si(SI_NST);
                 singular = (ierpj != 0);
             }
             if (!singular) {
@@ -485,35 +528,45 @@ struct Engine {
                 while (iterate) {
 #pragma unroll
                     for (int i = 0; i < NLOC; i++)
-                        y[i] = rl1h * savf[i] - (c.rl1 * yh[1][i] + acor[i]);
-                    POL::solve(lin, y);
-                    c.nni = c.nni + 1;
+                        y[i] = rl1h * savf[i] - (c.rl1 * hot.yh(1, i) + acor[i]);
+                    POL::solve(*this, y);
+                    hot.si(SI_NNI) = hot.si(SI_NNI) + 1;
                     if (do_scale) {
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
                     }
+#if BVODE_STRICT
                     del = POL::norm(y, ewt);
+#else
+                    // fast build: `del` and `delp` hold the MEAN SQUARE (norm^2); the tests of
+                    // M:2842-2855 are applied to squares, sqrt only for the rate estimate
+                    del = POL::msq(y, ewt);
+#endif
 #pragma unroll
                     for (int i = 0; i < NLOC; i++) acor[i] = acor[i] + y[i];
 #pragma unroll
-                    for (int i = 0; i < NLOC; i++) y[i] = yh[0][i] + acor[i];
-                    if (m != 0) c.crate = dmax2(crdown * c.crate, del / delp);
+                    for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + acor[i];
 #if BVODE_STRICT
-                    const double dcon = del * dmin2(1.0, c.crate) / c.tq[4];
+                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), del / delp);
+                    const double dcon = del * dmin2(1.0, hot.sd(SD_CRATE)) / hot.tq(4);
+                    const bool diverging = !(m + 1 < 2 || del <= rdiv * delp);
 #else
-                    const double dcon = del * dmin2(1.0, c.crate) * rtq4;
+                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), sqrt(del / delp));
+                    const double cfac = dmin2(1.0, hot.sd(SD_CRATE)) * rtq4;
+                    const double dcon = del * (cfac * cfac);
+                    const bool diverging = !(m + 1 < 2 || del <= (rdiv * rdiv) * delp);
 #endif
                     if (dcon <= 1.0) {
                         converged = true;
                         iterate = false;
                     } else {
                         m = m + 1;
-                        if (m == maxcor || !(m < 2 || del <= rdiv * delp)) {
+                        if (m == maxcor || diverging) {
                             iterate = false;
                         } else {
                             delp = del;
                             POL::f(c.tn, y, savf, par);
-                            c.nfe = c.nfe + 1;
+                            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
                         }
                     }
                 }
@@ -521,7 +574,11 @@ struct Engine {
             if (converged) {
                 c.jcur = 0;
                 c.icf = 0;
+#if BVODE_STRICT
                 c.acnrm = (m == 0) ? del : POL::norm(acor, ewt);
+#else
+                c.acnrm = (m == 0) ? del : POL::msq(acor, ewt);  // squared, see above
+#endif
                 result = 0;
             } else if (!singular && c.jcur != 1) {
                 c.icf = 1;
@@ -561,7 +618,7 @@ struct Engine {
 #endif
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
-        int nslast = c.nst;  // M:1399 (and 1337 on the first call)
+        int nslast = hot.si(SI_NST);  // M:1399 (and 1337 on the first call)
         const int lmax = o.maxord + 1;
         int istate = 0;  // 0 = keep stepping; every loop below has a single exit (see dvnlsd)
         int kout = 0;
@@ -592,7 +649,7 @@ struct Engine {
                 kout = kout + 1;
                 if (kout < nout) {
                     tout = tout_of(kout);
-                    nslast = c.nst;
+                    nslast = hot.si(SI_NST);
                     reached = !((c.tn - tout) * c.h < 0.0);
                 } else {
                     reached = false;
@@ -604,7 +661,7 @@ struct Engine {
                 if (entry == E_NEWSTEP) {
                     // ---- label 100 / 200, M:1496-1543
                     if (!skip_ewt) {
-                        if ((c.nst - nslast) >= o.mxstep) {
+                        if ((hot.si(SI_NST) - nslast) >= o.mxstep) {
                             istate = IST_MXSTEP;
                         } else {
                             bool bad;
@@ -614,11 +671,17 @@ struct Engine {
                     }
                     skip_ewt = false;
                     if (istate == 0) {
-                        const double tolsf = kUround * POL::norm(yh[0], ewt);
-                        if (tolsf > 1.0) istate = (c.nst == 0) ? IST_ILLEGAL : IST_TOLSF;
+#if BVODE_STRICT
+                        const double tolsf = kUround * norm_y0();
+                        const bool too_much = (tolsf > 1.0);
+#else
+                        // tolsf > 1  <=>  uround^2 * mean-square > 1 (no sqrt on the main path)
+                        const bool too_much = ((kUround * kUround) * msq_y0() > 1.0);
+#endif
+                        if (too_much) istate = (hot.si(SI_NST) == 0) ? IST_ILLEGAL : IST_TOLSF;
                     }
                     if (istate == 0) {
-                        if ((c.tn + c.h) == c.tn) c.nhnil = c.nhnil + 1;
+                        if ((c.tn + c.h) == c.tn) hot.si(SI_NHNIL) = hot.si(SI_NHNIL) + 1;
                         // ---- dvstep prologue, M:2024-2128
                         c.kflag = 0;
                         told = c.tn;
@@ -628,10 +691,10 @@ struct Engine {
                         if (c.jstart == 0) {
                             c.nq = 1;
                             c.L = 2;
-                            c.tau[1] = c.h;
+                            hot.tau(1) = c.h;
                             c.prl1 = 1.0;
                             c.rc = 0.0;
-                            c.etamax = etamx1;
+                            hot.sd(SD_ETAMAX) = etamx1;
                             c.nqwait = 2;
                             c.hscal = c.h;
                             entry = E_PREDICT;
@@ -661,24 +724,24 @@ struct Engine {
                 // ---- label 400: predict, coefficients (M:2147-2158)
                 c.tn = c.tn + c.h;
                 predict();
-                dvset_bdf(c);
-                c.rl1 = 1.0 / c.el[2];
+                dvset_bdf(c, hot);
+                c.rl1 = 1.0 / hot.el(2);
                 c.rc = c.rc * (c.rl1 / c.prl1);
                 c.prl1 = c.rl1;
 #if BVODE_STRICT
                 const double rtq2 = 0.0, rtq4 = 0.0;
                 (void)rtq2;
 #else
-                const double rtq2 = 1.0 / c.tq[2];
+                const double rtq2 = 1.0 / hot.tq(2);
                 const double rtq4 = 10.0 * rtq2;  // tq(4) = 0.1 * tq(2), M:2559
 #endif
                 nflag = dvnlsd(nflag, rtq4);
 
                 const bool conv = (nflag == 0);
 #if BVODE_STRICT
-                const double dsm = conv ? c.acnrm / c.tq[2] : 0.0;
+                const double dsm = conv ? c.acnrm / hot.tq(2) : 0.0;
 #else
-                const double dsm = conv ? c.acnrm * rtq2 : 0.0;
+                const double dsm = conv ? c.acnrm * (rtq2 * rtq2) : 0.0;  // dsm^2
 #endif
                 const bool accept = conv && !(dsm > 1.0);
                 if (!accept) {  // both kinds of failure undo the prediction (M:2180-2187, 2341-2348)
@@ -690,19 +753,21 @@ struct Engine {
 #if BVODE_STRICT
                 const double etaq = conv ? eta_of(bias2 * dsm, c.L) : 0.0;
 #else
-                const lg_t lq = conv ? log2_fast(bias2 * dsm) * (lg_t)recip_int(c.L) : (lg_t)0;
+                // log2(bias2*dsm)/L from dsm^2: log2(bias2^2 * dsm^2) / (2L)
+                const lg_t lq = conv ? log2_fast((bias2 * bias2) * dsm) * (lg_t)(0.5 * recip_int(c.L))
+                                     : (lg_t)0;
 #endif
                 if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
                     c.kflag = c.kflag - 1;
-                    c.netf = c.netf + 1;
+                    hot.si(SI_NETF) = hot.si(SI_NETF) + 1;
                     nflag = -2;
                     if (fabs(c.h) <= o.hmin * onepsm) {
                         c.kflag = -1;
                         c.jstart = 1;
                         istate = IST_ERRTEST;
                     } else {
-                        c.etamax = 1.0;
+                        hot.sd(SD_ETAMAX) = 1.0;
                         if (c.kflag > kfc) {
 #if BVODE_STRICT
                             c.eta = etaq;
@@ -720,11 +785,11 @@ struct Engine {
                             c.eta = dmax2(etamin, o.hmin / fabs(c.h));
                             c.h = c.h * c.eta;
                             c.hscal = c.h;
-                            c.tau[1] = c.h;
+                            hot.tau(1) = c.h;
                             POL::f(c.tn, y, savf, par);
-                            c.nfe = c.nfe + 1;
+                            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
 #pragma unroll
-                            for (int i = 0; i < NLOC; i++) yh[1][i] = c.h * savf[i];
+                            for (int i = 0; i < NLOC; i++) hot.yh(1, i) = c.h * savf[i];
                             c.nqwait = 10;
                             entry = E_PREDICT;
                         } else {
@@ -735,8 +800,8 @@ struct Engine {
                 } else if (!conv) {
                     // ---- corrector failed to converge (M:2338-2367)
                     ncf = ncf + 1;
-                    c.ncfn = c.ncfn + 1;
-                    c.etamax = 1.0;
+                    hot.si(SI_NCFN) = hot.si(SI_NCFN) + 1;
+                    hot.sd(SD_ETAMAX) = 1.0;
                     if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
                         c.kflag = -2;
                         c.jstart = 1;
@@ -749,26 +814,26 @@ struct Engine {
                 } else {
                     // ---- successful step (M:2245-2330, 2370-2375)
                     c.kflag = 0;
-                    c.nst = c.nst + 1;
-                    c.hu = c.h;
-                    c.nqu = c.nq;
+                    hot.si(SI_NST) = hot.si(SI_NST) + 1;
+                    hot.sd(SD_HU) = c.h;
+                    hot.si(SI_NQU) = c.nq;
 #pragma unroll
                     for (int i = kLmax; i >= 2; i--) {
-                        if (i <= c.nq + 1) c.tau[i] = c.tau[i - 1];
+                        if (i <= c.nq + 1) hot.tau(i) = hot.tau(i - 1);
                     }
-                    c.tau[1] = c.h;
+                    hot.tau(1) = c.h;
 #pragma unroll
                     for (int j = 1; j <= kLmax; j++) {
 #pragma unroll
-                        for (int i = 0; i < NLOC; i++) yh[j - 1][i] = yh[j - 1][i] + c.el[j] * acor[i];
+                        for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.el(j) * acor[i];
                     }
                     c.nqwait = c.nqwait - 1;
                     if ((c.L != lmax) && (c.nqwait == 1)) {
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
-                        c.conp = c.tq[5];
+                        hot.sd(SD_CONP) = hot.tq(5);
                     }
-                    if (c.etamax != 1.0) {
+                    if (hot.sd(SD_ETAMAX) != 1.0) {
                         int newq = c.nq;
                         bool save_acor = false;
 #if BVODE_STRICT
@@ -782,15 +847,29 @@ struct Engine {
                             if (c.nq != 1) {
                                 double top[NLOC];
                                 get_col(c.L, top);
-                                ddn = POL::norm(top, ewt) / c.tq[1];
+#if BVODE_STRICT
+                                ddn = POL::norm(top, ewt) / hot.tq(1);
+#else
+                                {
+                                    const double r1 = 1.0 / hot.tq(1);
+                                    ddn = POL::msq(top, ewt) * (r1 * r1);  // ddn^2
+                                }
+#endif
                             }
                             if (c.L != lmax) {
                                 const double cnquot =
-                                    (c.tq[5] / c.conp) * powi(c.h / c.tau[2], c.L);
+                                    (hot.tq(5) / hot.sd(SD_CONP)) * powi(c.h / hot.tau(2), c.L);
 #pragma unroll
                                 for (int i = 0; i < NLOC; i++)
                                     savf[i] = acor[i] - cnquot * acsav.get(i);
-                                dup = POL::norm(savf, ewt) / c.tq[3];
+#if BVODE_STRICT
+                                dup = POL::norm(savf, ewt) / hot.tq(3);
+#else
+                                {
+                                    const double r3 = 1.0 / hot.tq(3);
+                                    dup = POL::msq(savf, ewt) * (r3 * r3);  // dup^2
+                                }
+#endif
                             }
 #if BVODE_STRICT
                             const double etaqm1 = (c.nq != 1) ? eta_of(bias1 * ddn, c.L - 1) : 0.0;
@@ -813,9 +892,9 @@ struct Engine {
                             // (order not available) is log-ratio +infinity
                             const lg_t inf = (lg_t)__int_as_float(0x7f800000);
                             const lg_t lm1 = (c.nq != 1)
-                                ? log2_fast(bias1 * ddn) * (lg_t)recip_int(c.L - 1) : inf;
+                                ? log2_fast((bias1 * bias1) * ddn) * (lg_t)(0.5 * recip_int(c.L - 1)) : inf;
                             const lg_t lp1 = (c.L != lmax)
-                                ? log2_fast(bias3 * dup) * (lg_t)recip_int(c.L + 1) : inf;
+                                ? log2_fast((bias3 * bias3) * dup) * (lg_t)(0.5 * recip_int(c.L + 1)) : inf;
                             if (lq > lp1) {
                                 if (lp1 >= lm1) {
                                     lwin = lm1;
@@ -846,27 +925,27 @@ struct Engine {
                             c.newq = c.nq;
                             c.newh = 0;
                             c.eta = 1.0;
-                            c.hnew = c.h;
+                            hot.sd(SD_HNEW) = c.h;
                         } else {
                             c.newq = newq;
-                            c.eta = dmin2(eta, c.etamax);
+                            c.eta = dmin2(eta, hot.sd(SD_ETAMAX));
                             c.eta = c.eta / dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
                             c.newh = 1;
-                            c.hnew = c.h * c.eta;
+                            hot.sd(SD_HNEW) = c.h * c.eta;
                         }
                     } else {
                         if (c.nqwait < 2) c.nqwait = 2;
                         c.newq = c.nq;
                         c.newh = 0;
                         c.eta = 1.0;
-                        c.hnew = c.h;
+                        hot.sd(SD_HNEW) = c.h;
                     }
                     // label 500
-                    c.etamax = etamx3;
-                    if (c.nst <= 10) c.etamax = etamx2;
+                    hot.sd(SD_ETAMAX) = etamx3;
+                    if (hot.si(SI_NST) <= 10) hot.sd(SD_ETAMAX) = etamx2;
                     {
 #if BVODE_STRICT
-                        const double r = 1.0 / c.tq[2];
+                        const double r = 1.0 / hot.tq(2);
 #else
                         const double r = rtq2;
 #endif
@@ -875,7 +954,7 @@ struct Engine {
                     }
                     c.jstart = 1;
                     // ---- block F, itask = 1 (M:1586-1622)
-                    c.init = 1;
+                    hot.si(SI_INIT) = 1;
                     entry = E_NEWSTEP;
                     reached = !((c.tn - tout) * c.h < 0.0);
                 }
@@ -887,7 +966,7 @@ struct Engine {
         }
         // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) y[i] = yh[0][i];
+        for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
         t_out = c.tn;
         return istate;
     }
