@@ -229,10 +229,7 @@ struct WarpStorer {
 template <class POL>
 struct WarpLayout {
     static constexpr int N = POL::N;
-    static int nblock(int ml, int mu) {
-        if constexpr (POL::kBand) return POL::smem_doubles(ml, mu, POL::SAVEJ);
-        else return 0;
-    }
+    static int nblock(int ml, int mu) { return POL::smem_doubles(ml, mu, POL::SAVEJ); }
     static void sizes(int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
         *nd = nsys * ((size_t)kScalarD + (size_t)POL::kLaneSlots * 32 + (size_t)nblock(ml, mu));
         *ni = nsys * ((size_t)kScalarI + (size_t)POL::kLaneIntSlots * 32);
@@ -255,13 +252,24 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
         e.lin.abd = smem + (size_t)warp * nblock;
         e.lin.wjs = e.lin.abd + e.lin.ld * POL::N;
     } else {
+        nblock = POL::N * POL::LDP;
+        e.lin.p = smem + (size_t)warp * nblock;
         e.lin.wjs.p = const_cast<double *>(dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
         e.lin.wjs.stride = nsys * 32;
     }
 }
 
+// One-system-per-warp kernels are latency-bound (dependent shuffle / FP64 chains, scalar
+// control replicated on 32 lanes): measured on B200, 65536 systems, mech32 / advection mf=24
+// systems/s at minBlocksPerSM = 2: 41.9k / 0.85M (206 / 168 registers, no spills); 4: 68.8k /
+// 0.91M; 6: 76.8k / 1.06M (85 registers, spills to L1); 8: 72.8k / 1.15M.  Resident warps
+// beat spills here.
+#ifndef BVODE_WARP_MINBLOCKS
+#define BVODE_WARP_MINBLOCKS 6
+#endif
 template <class POL>
-__global__ void __launch_bounds__(kWarpTPB) vode_warp_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(kWarpTPB, BVODE_WARP_MINBLOCKS)
+vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;

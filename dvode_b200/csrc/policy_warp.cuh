@@ -142,6 +142,12 @@ struct WarpCommon {
 };
 
 // =========================================================================== dense ====
+// Row i of the Newton matrix belongs to lane i; the matrix itself is in shared memory,
+// element (i, j) at p[i*LDP + j] with LDP odd, so "every lane reads its own row's column j"
+// and "every lane reads element (k, j)" (a broadcast) are both conflict-free.  All loops over
+// columns are run-time loops: the first version kept each row in registers with fully
+// unrolled loops (~20k instructions) and was bound by instruction fetch (ncu: 33 cycles of
+// no-instruction stall per issued instruction, profiles/r01_ncu_warp_dense_mech32_v1.txt).
 template <class PROB, int MITER_, bool SAVEJ_>
 struct WarpDensePolicy : WarpCommon<PROB> {
     using Base = WarpCommon<PROB>;
@@ -154,73 +160,80 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     static constexpr int MITER = MITER_;
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
+    static constexpr int LDP = N | 1;
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
     struct Lin {
-        double p[N];    // row `lane` of P = I - h*rl1*J, then of its LU factors.
-                        // Fast build: lane k's p[k] holds 1/u_kk after dgefa.
+        double *p;      // shared memory, N rows x LDP: P = I - h*rl1*J, then its LU factors.
+                        // Fast build: the diagonal holds 1/u_kk after dgefa.
         GlobalVec wjs;  // row `lane` of the saved Jacobian, element j at slot j (mf > 0)
         int ipv;        // lane k holds ipvt(k) (0-based row)
     };
-    BV_DEV static void lin_init(Lin &l) {
-#pragma unroll
-        for (int j = 0; j < N; j++) l.p[j] = 0.0;
-        l.ipv = lane();
-    }
-    // per-lane double slots of one system, in visit order: yh[6], acsav, acor, p[N], wjs[N]*
-    static constexpr int kLaneSlotWjs = kLmax + 2 + N;
-    static constexpr int kLaneSlots = kLmax + 2 + N + (SAVEJ ? N : 0);
+    BV_DEV static void lin_init(Lin &l) { l.ipv = lane(); }
+    static int smem_doubles(int, int, bool) { return N * LDP; }
+    // per-lane double slots of one system, in visit order: yh[6], acsav, acor, wjs[N]*
+    static constexpr int kLaneSlotWjs = kLmax + 2;
+    static constexpr int kLaneSlots = kLmax + 2 + (SAVEJ ? N : 0);
     static constexpr int kLaneIntSlots = 1;
     template <class V>
     BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
         Lin &l = e.lin;
-#pragma unroll
-        for (int j = 0; j < N; j++) v.dv(l.p[j]);
         if (SAVEJ) v.skip_dv(N);
+        v.block(l.p, N * LDP);
         v.iv(l.ipv);
     }
 
     // ---- dgefa, LP:46-120, rows across lanes ----------------------------------------
-    BV_DEV static int dgefa(double (&p)[N], int &ipv) {
+    BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();
+        double *row = lin.p + ln * LDP;  // lanes >= N never touch memory
         int info = 0;
-#pragma unroll
+        __syncwarp();
+#pragma unroll 1
         for (int k = 0; k < N - 1; k++) {
-            const int l = Base::argmax_abs(p[k], k, N - 1);
-            if (ln == k) ipv = l;
-            const double alk = shfl_d(p[k], l);
+            const double v = (ln < N) ? row[k] : 0.0;
+            const int l = Base::argmax_abs(v, k, N - 1);
+            if (ln == k) lin.ipv = l;
+            const double alk = shfl_d(v, l);
             if (alk == 0.0) {
                 info = k + 1;
             } else {
                 const bool swap = (l != k);  // warp-uniform
+                // interchange a(l,k) <-> a(k,k), then scale the multipliers (LP:96-104)
+                double m = v;
                 if (swap) {
-                    const double akk = shfl_d(p[k], k);
-                    if (ln == l) p[k] = akk;
-                    if (ln == k) p[k] = alk;
+                    const double akk = shfl_d(v, k);
+                    if (ln == l) m = akk;
+                    if (ln == k) m = alk;
                 }
                 const double t = -1.0 / alk;
-                if (ln > k) p[k] = t * p[k];
-#pragma unroll
+                if (ln > k && ln < N) m = t * m;
+                if (ln >= k && ln < N) row[k] = m;
+                __syncwarp();
+#pragma unroll 1
                 for (int j = k + 1; j < N; j++) {
-                    const double tj = shfl_d(p[j], l);
+                    const double tj = lin.p[l * LDP + j];    // a(l,j): broadcast
                     if (swap) {
-                        const double akj = shfl_d(p[j], k);
-                        if (ln == l) p[j] = akj;
-                        if (ln == k) p[j] = tj;
+                        const double akj = lin.p[k * LDP + j];
+                        __syncwarp();
+                        if (ln == l) row[j] = akj;
+                        if (ln == k) row[j] = tj;
+                        __syncwarp();
                     }
-                    if (ln > k) p[j] = p[j] + tj * p[k];
+                    if (ln > k && ln < N) row[j] = row[j] + tj * m;
                 }
+                __syncwarp();
             }
         }
-        if (ln == N - 1) ipv = N - 1;
-        if (shfl_d(p[N - 1], N - 1) == 0.0) info = N;
+        if (ln == N - 1) lin.ipv = N - 1;
+        if (lin.p[(N - 1) * LDP + (N - 1)] == 0.0) info = N;
 #if !BVODE_STRICT
-#pragma unroll
-        for (int k = 0; k < N; k++)
-            if (ln == k) p[k] = 1.0 / p[k];
+        __syncwarp();
+        if (ln < N) row[ln] = 1.0 / row[ln];
 #endif
+        __syncwarp();
         return info;
     }
 
@@ -229,8 +242,9 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     BV_DEV static void solve(ENG &e, double (&x)[1]) {
         const Lin &lin = e.lin;
         const int ln = lane();
+        const double *row = lin.p + ln * LDP;
         double b = x[0];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < N - 1; k++) {
             const int l = __shfl_sync(kFull, lin.ipv, k);
             const double t = shfl_d(b, l);
@@ -239,17 +253,17 @@ struct WarpDensePolicy : WarpCommon<PROB> {
                 if (ln == l) b = bk;
                 if (ln == k) b = t;
             }
-            if (ln > k && ln < N) b = b + t * lin.p[k];
+            if (ln > k && ln < N) b = b + t * row[k];
         }
-#pragma unroll
+#pragma unroll 1
         for (int k = N - 1; k >= 0; k--) {
 #if BVODE_STRICT
-            if (ln == k) b = b / lin.p[k];
+            if (ln == k) b = b / row[k];
 #else
-            if (ln == k) b = b * lin.p[k];
+            if (ln == k) b = b * row[k];
 #endif
             const double t = -shfl_d(b, k);
-            if (ln < k) b = b + t * lin.p[k];
+            if (ln < k) b = b + t * row[k];
         }
         x[0] = b;
     }
@@ -260,6 +274,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
         Ctl &c = e.c;
         Lin &l = e.lin;
         const int ln = lane();
+        double *row = l.p + ln * LDP;
         ierpj = 0;
         const double hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
@@ -268,50 +283,53 @@ struct WarpDensePolicy : WarpCommon<PROB> {
             if (c.icf == 1 && c.drc < 0.2) jok = -1;
             if (c.icf == 2) jok = -1;
         }
+        __syncwarp();
         if (jok == -1) {
             e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if constexpr (MITER == 1) {
-#pragma unroll
-                for (int j = 0; j < N; j++) l.p[j] = 0.0;
-                PROB::jac_row(c.tn, e.y[0], l.p, e.par, ln);
+                if (ln < N) {
+#pragma unroll 1
+                    for (int j = 0; j < N; j++) row[j] = 0.0;
+                    PROB::jac_row(c.tn, e.y[0], row, e.par, ln);
+                }
             } else {
                 // finite differences, M:2959-2976: column j for all rows at once
                 const double r0 = Base::fd_r0(c, e.savf, e.ewt);
                 const double srur = sqrt(kUround);
                 const double rmine = dmax2(srur * fabs(e.y[0]), r0 / e.ewt[0]);
                 const double ysave = e.y[0];
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < N; j++) {
                     const double r = shfl_d(rmine, j);
                     if (ln == j) e.y[0] = ysave + r;
                     const double fac = 1.0 / r;
                     Base::f(c.tn, e.y, e.acor, e.par);
-                    l.p[j] = (e.acor[0] - e.savf[0]) * fac;
+                    if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
                     e.y[0] = ysave;
                 }
                 e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
             }
-            if (SAVEJ) {
-#pragma unroll
-                for (int j = 0; j < N; j++) l.wjs.set(j, l.p[j]);
+            if (SAVEJ && ln < N) {
+#pragma unroll 1
+                for (int j = 0; j < N; j++) l.wjs.set(j, row[j]);
             }
         } else {
             c.jcur = 0;
-            if (SAVEJ) {
-#pragma unroll
-                for (int j = 0; j < N; j++) l.p[j] = l.wjs.get(j);
+            if (SAVEJ && ln < N) {
+#pragma unroll 1
+                for (int j = 0; j < N; j++) row[j] = l.wjs.get(j);
             }
         }
         const double con = -hrl1;
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            l.p[j] = con * l.p[j];
-            if (ln == j) l.p[j] = l.p[j] + 1.0;
+        if (ln < N) {
+#pragma unroll 1
+            for (int j = 0; j < N; j++) row[j] = con * row[j];
+            row[ln] = row[ln] + 1.0;
         }
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
-        const int ier = dgefa(l.p, l.ipv);
+        const int ier = dgefa(l);
         if (ier != 0) ierpj = 1;
     }
 };
