@@ -115,9 +115,40 @@ BV_DEV double rpow(double x, double y) {
 #endif
 }
 
-// 1/(double)k: __drcp_rn is the IEEE round-to-nearest reciprocal, i.e. the same bits as the
-// reference's `one/real(k)` divide, without a divergent switch or a full division.
-BV_DEV double recip_int(int k) { return __drcp_rn((double)k); }
+// a/b and 1/b on the step loop.  Strict build: the IEEE operations.  Fast build: the
+// hardware reciprocal seed (MUFU.RCP64H, relative error 2^-23) refined by one cubic step
+// (error^3 -> below 2^-53) and, for a/b, one residual correction -- faithfully rounded
+// (<= 1 ulp, equal to the IEEE quotient in all but a few per cent of cases), 6-7 FP64
+// instructions, no range test and no out-of-line slow path (CUDA's `/` is ~15 instructions
+// plus a call per site; the kernel has ~70 sites and the loop body must fit the instruction
+// cache).  Valid for normal, finite divisors with |b| in [2^-1000, 2^1000]: step sizes, error
+// weights and the order coefficients of a running integration are all far inside that.
+#if BVODE_STRICT
+BV_DEV double qrcp(double b) { return 1.0 / b; }
+BV_DEV double qdiv(double a, double b) { return a / b; }
+#else
+BV_DEV double qrcp(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+BV_DEV double qdiv(double a, double b) {
+    const double r = qrcp(b);
+    const double q = a * r;
+    const double rem = fma(-b, q, a);
+    return fma(rem, r, q);
+}
+#endif
+
+// 1/(double)k for the small integers of the order logic (k = 0..15): the same bits as the
+// reference's `one/real(k)` divide, from a constant-bank table (one indexed LDC; lanes at
+// different orders cost one replay per distinct k) -- no divide, no divergent switch.
+__constant__ double kRecipTab[16] = {0.0,        1.0,        1.0 / 2.0,  1.0 / 3.0,  1.0 / 4.0,  1.0 / 5.0,
+                                     1.0 / 6.0,  1.0 / 7.0,  1.0 / 8.0,  1.0 / 9.0,  1.0 / 10.0, 1.0 / 11.0,
+                                     1.0 / 12.0, 1.0 / 13.0, 1.0 / 14.0, 1.0 / 15.0};
+BV_DEV double recip_int(int k) { return kRecipTab[k & 15]; }
 
 #if !BVODE_STRICT
 // Fast build: the step-size ratio eta = 1/(x**(1/k) + addon) (M:2201, 2275, 2282, 2292) is
@@ -142,7 +173,7 @@ BV_DEV lg_t log2_fast(double x) {
     u = (u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
     double m = __longlong_as_double((long long)u);
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    const double s = (m - 1.0) / (m + 1.0), z = s * s;
+    const double s = qdiv(m - 1.0, m + 1.0), z = s * s;
     double p = 1.0 / 21.0;
     p = fma(p, z, 1.0 / 19.0);
     p = fma(p, z, 1.0 / 17.0);

@@ -202,8 +202,16 @@ struct ThreadPolicy {
                 const double akk = a_(k, k);
 #pragma unroll
                 for (int i = k + 1; i < N; i++) a_(i, k) = (l == i) ? akk : a_(i, k);
+#if BVODE_STRICT
                 a_(k, k) = alk;
                 const double t = -1.0 / alk;
+#else
+                // fast build: the diagonal keeps 1/u_kk so that dgesl multiplies; one reciprocal
+                // serves both the multipliers and the back substitution
+                const double rp = qrcp(alk);
+                a_(k, k) = rp;
+                const double t = -rp;
+#endif
 #pragma unroll
                 for (int i = k + 1; i < N; i++) a_(i, k) = t * a_(i, k);
 #pragma unroll
@@ -223,9 +231,7 @@ struct ThreadPolicy {
         ipvt[N - 1] = N - 1;
         if (a_(N - 1, N - 1) == 0.0) info = N;
 #if !BVODE_STRICT
-        // fast build: keep 1/u_kk on the diagonal so that dgesl multiplies instead of divides
-#pragma unroll
-        for (int k = 0; k < N; k++) a_(k, k) = 1.0 / a_(k, k);
+        a_(N - 1, N - 1) = qrcp(a_(N - 1, N - 1));
 #endif
         return info;
 #undef a_
@@ -307,9 +313,9 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int j = 0; j < N; j++) {
                     const double yj = e.y[j];
-                    const double r = dmax2(srur * fabs(yj), r0 / e.ewt[j]);
+                    const double r = dmax2(srur * fabs(yj), qdiv(r0, e.ewt[j]));
                     e.y[j] = e.y[j] + r;
-                    fac = 1.0 / r;
+                    fac = qrcp(r);
                     f(c.tn, e.y, e.acor, e.par);
 #pragma unroll
                     for (int i = 0; i < N; i++) e.hot.p(i, j) = (e.acor[i] - e.savf[i]) * fac;

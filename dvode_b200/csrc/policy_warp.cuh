@@ -208,7 +208,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
                     if (ln == l) m = akk;
                     if (ln == k) m = alk;
                 }
-                const double t = -1.0 / alk;
+                const double t = -qrcp(alk);
                 if (ln > k && ln < N) m = t * m;
                 if (ln >= k && ln < N) row[k] = m;
                 __syncwarp();
@@ -231,7 +231,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
         if (lin.p[(N - 1) * LDP + (N - 1)] == 0.0) info = N;
 #if !BVODE_STRICT
         __syncwarp();
-        if (ln < N) row[ln] = 1.0 / row[ln];
+        if (ln < N) row[ln] = qrcp(row[ln]);
 #endif
         __syncwarp();
         return info;
@@ -298,13 +298,13 @@ struct WarpDensePolicy : WarpCommon<PROB> {
                 // finite differences, M:2959-2976: column j for all rows at once
                 const double r0 = Base::fd_r0(c, e.savf, e.ewt);
                 const double srur = sqrt(kUround);
-                const double rmine = dmax2(srur * fabs(e.y[0]), r0 / e.ewt[0]);
+                const double rmine = dmax2(srur * fabs(e.y[0]), qdiv(r0, e.ewt[0]));
                 const double ysave = e.y[0];
 #pragma unroll 1
                 for (int j = 0; j < N; j++) {
                     const double r = shfl_d(rmine, j);
                     if (ln == j) e.y[0] = ysave + r;
-                    const double fac = 1.0 / r;
+                    const double fac = qrcp(r);
                     Base::f(c.tn, e.y, e.acor, e.par);
                     if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
                     e.y[0] = ysave;
@@ -420,7 +420,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
                     ABD(m, k) = t;
                 }
                 __syncwarp();
-                const double t = -1.0 / alk;
+                const double t = -qrcp(alk);
                 if (ln >= 1 && ln <= lm) ABD(m + ln, k) = t * ABD(m + ln, k);  // dscal, LP:343
                 const int jun = mu + piv;
                 ju = (ju > jun) ? ju : jun;
@@ -445,6 +445,11 @@ struct WarpBandPolicy : WarpCommon<PROB> {
         if (ln == n - 1) l.ipv = n - 1;
         if (ABD(m, n) == 0.0) info = n;
         __syncwarp();
+#if !BVODE_STRICT
+        // fast build: the diagonal keeps 1/u_kk so that dgbsl multiplies
+        if (ln < n) ABD(m, ln + 1) = qrcp(ABD(m, ln + 1));
+        __syncwarp();
+#endif
         return info;
     }
 
@@ -472,7 +477,11 @@ struct WarpBandPolicy : WarpCommon<PROB> {
         }
 #pragma unroll 1
         for (int k = n; k >= 1; k--) {
+#if BVODE_STRICT
             if (ln == k - 1) b = b / ABD(m, k);
+#else
+            if (ln == k - 1) b = b * ABD(m, k);
+#endif
             const int lm = ((k < m) ? k : m) - 1;
             const int la = m - lm, lb = k - lm;
             const double t = -shfl_d(b, k - 1);
@@ -517,7 +526,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
                 const double srur = sqrt(kUround);
                 const double ysave = e.y[0];
                 // yh(:,1) is what the reference restores y from (M:3070); identical to ysave
-                const double rmine = dmax2(srur * fabs(ysave), r0 / e.ewt[0]);
+                const double rmine = dmax2(srur * fabs(ysave), qdiv(r0, e.ewt[0]));
 #pragma unroll 1
                 for (int j = 1; j <= mba; j++) {
                     const bool mine = (ln < n) && (((ln + 1 - j) % mband) == 0) && (ln + 1 >= j);
@@ -531,7 +540,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
 #pragma unroll 1
                     for (int jj = j; jj <= n; jj += mband) {
                         const double r = shfl_d(rmine, jj - 1);
-                        const double fac = 1.0 / r;
+                        const double fac = qrcp(r);
                         const int i1 = (jj - mu > 1) ? jj - mu : 1;
                         const int i2 = (jj + ml < n) ? jj + ml : n;
                         if (i >= i1 && i <= i2) ABD(i - jj + mband, jj) = diff * fac;

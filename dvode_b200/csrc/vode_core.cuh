@@ -98,7 +98,7 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
         for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
             if (j <= nq - 2) {
                 hsum = hsum + hot.tau(j);
-                rxi = h / hsum;
+                rxi = qdiv(h, hsum);
                 alph0 = alph0 - 1.0 / (double)(j + 1);
 #pragma unroll
                 for (int iback = 1; iback <= j + 1; iback++) {
@@ -110,7 +110,7 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
         alph0 = alph0 - recip_int(nq);
         rxis = -hot.el(2) - alph0;
         hsum = hsum + pick_tau<1, kMaxOrdBdf>(hot, nq - 1);
-        rxi = h / hsum;
+        rxi = qdiv(h, hsum);
         ahatn0 = -hot.el(2) - rxi;
 #pragma unroll
         for (int i = kLmax; i >= 2; i--) {
@@ -120,19 +120,19 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const double t1 = 1.0 - ahatn0 + alph0;
     const double t2 = 1.0 + (double)nq * t1;
     const double elL = pick_el<2, kLmax>(hot, L);
-    hot.tq(2) = fabs(alph0 * t2 / t1);
-    hot.tq(5) = fabs(t2 / (elL * rxi / rxis));
+    hot.tq(2) = fabs(qdiv(alph0 * t2, t1));
+    hot.tq(5) = fabs(qdiv(t2, qdiv(elL * rxi, rxis)));
     if (c.nqwait == 1) {
-        const double cnqm1 = rxis / elL;
+        const double cnqm1 = qdiv(rxis, elL);
         const double t3 = alph0 + recip_int(nq);
         const double t4 = ahatn0 + rxi;
-        double elp = t3 / (1.0 - t4 + t3);
-        hot.tq(1) = fabs(elp / cnqm1);
+        double elp = qdiv(t3, 1.0 - t4 + t3);
+        hot.tq(1) = fabs(qdiv(elp, cnqm1));
         hsum = hsum + pick_tau<1, kLmax>(hot, nq);
-        rxi = h / hsum;
+        rxi = qdiv(h, hsum);
         const double t5 = alph0 - recip_int(nq + 1);
         const double t6 = ahatn0 - rxi;
-        elp = t2 / (1.0 - t6 + t5);
+        elp = qdiv(t2, 1.0 - t6 + t5);
         hot.tq(3) = fabs(elp * rxi * ((double)L + 1.0) * t5);
     }
     hot.tq(4) = 0.1 * hot.tq(2);
@@ -156,11 +156,11 @@ BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up) {
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
         if (j <= jmax) {
             hsum = hsum + (up ? hot.tau(j + 1) : hot.tau(j));
-            const double xi = hsum / c.hscal;
+            const double xi = qdiv(hsum, c.hscal);
             if (up) {
                 prod = prod * xi;
                 alph0 = alph0 - 1.0 / (double)(j + 1);
-                alph1 = alph1 + 1.0 / xi;
+                alph1 = alph1 + qrcp(xi);
             }
             const double x = up ? xiold : xi;
 #pragma unroll
@@ -171,7 +171,7 @@ BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up) {
             xiold = xi;
         }
     }
-    return (-alph0 - alph1) / prod;
+    return qdiv(-alph0 - alph1, prod);
 }
 
 // =================================================================== Engine =====
@@ -219,7 +219,7 @@ struct Engine {
         for (int i = 0; i < NLOC; i++) e[i] = tol.rtol(i) * fabs(hot.yh(0, i)) + tol.atol(i);
         bad = POL::any_le_zero(e);
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) ewt[i] = 1.0 / e[i];
+        for (int i = 0; i < NLOC; i++) ewt[i] = qrcp(e[i]);
     }
 
 #if !BVODE_STRICT
@@ -321,7 +321,7 @@ struct Engine {
         const double tp = c.tn - hot.sd(SD_HU) - tfuzz;
         const double tn1 = c.tn + tfuzz;
         if ((t - tp) * (t - tn1) > 0.0) return -2;
-        const double s = (t - c.tn) / c.h;
+        const double s = qdiv(t - c.tn, c.h);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) dky[i] = hot.yh(kLmax - 1, i);
 #pragma unroll
@@ -521,7 +521,7 @@ struct Engine {
                 for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
                 // 2/(1+rc), M:2813: rc is fixed during the iterations of one pass
                 const bool do_scale = (c.rc != 1.0);
-                const double cscale = 2.0 / (1.0 + c.rc);
+                const double cscale = qdiv(2.0, 1.0 + c.rc);
                 const double rl1h = c.rl1 * c.h;
                 bool iterate = true;
 #pragma unroll 1
@@ -547,11 +547,11 @@ struct Engine {
 #pragma unroll
                     for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + acor[i];
 #if BVODE_STRICT
-                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), del / delp);
-                    const double dcon = del * dmin2(1.0, hot.sd(SD_CRATE)) / hot.tq(4);
+                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), qdiv(del, delp));
+                    const double dcon = qdiv(del * dmin2(1.0, hot.sd(SD_CRATE)), hot.tq(4));
                     const bool diverging = !(m + 1 < 2 || del <= rdiv * delp);
 #else
-                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), sqrt(del / delp));
+                    if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), sqrt(qdiv(del, delp)));
                     const double cfac = dmin2(1.0, hot.sd(SD_CRATE)) * rtq4;
                     const double dcon = del * (cfac * cfac);
                     const bool diverging = !(m + 1 < 2 || del <= (rdiv * rdiv) * delp);
@@ -594,7 +594,7 @@ struct Engine {
 
     // eta = 1 / (x**(1/k) + addon), M:2201, 2275, 2282, 2292
     BV_DEV static double eta_of(double x, int k) {
-        return 1.0 / (rpow(x, recip_int(k)) + 1.0e-6);
+        return qrcp(rpow(x, recip_int(k)) + 1.0e-6);
     }
 
     // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
@@ -725,21 +725,21 @@ struct Engine {
                 c.tn = c.tn + c.h;
                 predict();
                 dvset_bdf(c, hot);
-                c.rl1 = 1.0 / hot.el(2);
-                c.rc = c.rc * (c.rl1 / c.prl1);
+                c.rl1 = qrcp(hot.el(2));
+                c.rc = c.rc * qdiv(c.rl1, c.prl1);
                 c.prl1 = c.rl1;
 #if BVODE_STRICT
                 const double rtq2 = 0.0, rtq4 = 0.0;
                 (void)rtq2;
 #else
-                const double rtq2 = 1.0 / hot.tq(2);
+                const double rtq2 = qrcp(hot.tq(2));
                 const double rtq4 = 10.0 * rtq2;  // tq(4) = 0.1 * tq(2), M:2559
 #endif
                 nflag = dvnlsd(nflag, rtq4);
 
                 const bool conv = (nflag == 0);
 #if BVODE_STRICT
-                const double dsm = conv ? c.acnrm / hot.tq(2) : 0.0;
+                const double dsm = conv ? qdiv(c.acnrm, hot.tq(2)) : 0.0;
 #else
                 const double dsm = conv ? c.acnrm * (rtq2 * rtq2) : 0.0;  // dsm^2
 #endif
@@ -772,9 +772,9 @@ struct Engine {
 #if BVODE_STRICT
                             c.eta = etaq;
 #else
-                            c.eta = 1.0 / (exp2_fast(lq) + addon);
+                            c.eta = qrcp(exp2_fast(lq) + addon);
 #endif
-                            c.eta = dmax2(dmax2(c.eta, o.hmin / fabs(c.h)), etamin);
+                            c.eta = dmax2(dmax2(c.eta, qdiv(o.hmin, fabs(c.h))), etamin);
                             if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
                             entry = E_RESCALE;
                         } else if (c.kflag == kfh) {
@@ -782,7 +782,7 @@ struct Engine {
                             c.jstart = 1;
                             istate = IST_ERRTEST;
                         } else if (c.nq == 1) {
-                            c.eta = dmax2(etamin, o.hmin / fabs(c.h));
+                            c.eta = dmax2(etamin, qdiv(o.hmin, fabs(c.h)));
                             c.h = c.h * c.eta;
                             c.hscal = c.h;
                             hot.tau(1) = c.h;
@@ -793,7 +793,7 @@ struct Engine {
                             c.nqwait = 10;
                             entry = E_PREDICT;
                         } else {
-                            c.eta = dmax2(etamin, o.hmin / fabs(c.h));
+                            c.eta = dmax2(etamin, qdiv(o.hmin, fabs(c.h)));
                             entry = E_DOWN_RESCALE;
                         }
                     }
@@ -807,7 +807,7 @@ struct Engine {
                         c.jstart = 1;
                         istate = IST_CONVFAIL;
                     } else {
-                        c.eta = dmax2(etacf, o.hmin / fabs(c.h));
+                        c.eta = dmax2(etacf, qdiv(o.hmin, fabs(c.h)));
                         nflag = -1;
                         entry = E_RESCALE;
                     }
@@ -848,25 +848,25 @@ struct Engine {
                                 double top[NLOC];
                                 get_col(c.L, top);
 #if BVODE_STRICT
-                                ddn = POL::norm(top, ewt) / hot.tq(1);
+                                ddn = qdiv(POL::norm(top, ewt), hot.tq(1));
 #else
                                 {
-                                    const double r1 = 1.0 / hot.tq(1);
+                                    const double r1 = qrcp(hot.tq(1));
                                     ddn = POL::msq(top, ewt) * (r1 * r1);  // ddn^2
                                 }
 #endif
                             }
                             if (c.L != lmax) {
                                 const double cnquot =
-                                    (hot.tq(5) / hot.sd(SD_CONP)) * powi(c.h / hot.tau(2), c.L);
+                                    qdiv(hot.tq(5), hot.sd(SD_CONP)) * powi(qdiv(c.h, hot.tau(2)), c.L);
 #pragma unroll
                                 for (int i = 0; i < NLOC; i++)
                                     savf[i] = acor[i] - cnquot * acsav.get(i);
 #if BVODE_STRICT
-                                dup = POL::norm(savf, ewt) / hot.tq(3);
+                                dup = qdiv(POL::norm(savf, ewt), hot.tq(3));
 #else
                                 {
-                                    const double r3 = 1.0 / hot.tq(3);
+                                    const double r3 = qrcp(hot.tq(3));
                                     dup = POL::msq(savf, ewt) * (r3 * r3);  // dup^2
                                 }
 #endif
@@ -919,7 +919,7 @@ struct Engine {
                         const bool keep = (eta < thresh);
 #else
                         const bool keep = (lwin > l2thr);
-                        const double eta = 1.0 / (exp2_fast(lwin) + addon);
+                        const double eta = qrcp(exp2_fast(lwin) + addon);
 #endif
                         if (keep) {
                             c.newq = c.nq;
@@ -929,7 +929,7 @@ struct Engine {
                         } else {
                             c.newq = newq;
                             c.eta = dmin2(eta, hot.sd(SD_ETAMAX));
-                            c.eta = c.eta / dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
+                            c.eta = qdiv(c.eta, dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta));
                             c.newh = 1;
                             hot.sd(SD_HNEW) = c.h * c.eta;
                         }
@@ -945,7 +945,7 @@ struct Engine {
                     if (hot.si(SI_NST) <= 10) hot.sd(SD_ETAMAX) = etamx2;
                     {
 #if BVODE_STRICT
-                        const double r = 1.0 / hot.tq(2);
+                        const double r = qrcp(hot.tq(2));
 #else
                         const double r = rtq2;
 #endif
