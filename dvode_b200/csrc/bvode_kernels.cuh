@@ -36,37 +36,35 @@ BV_DEV void visit_state(ENG &e, V &v) {
     v.i(e.hot.si(SI_NQU));
 }
 
+// (T is double / int, or their volatile forms for fields a policy parks in shared memory)
 struct Loader {
     const double *dp;
     const int *ip;
     size_t stride;
     int kd = 0, ki = 0;
-    BV_DEV void d(double &x) { x = dp[(size_t)kd * stride]; kd++; }
-    BV_DEV void i(int &x) { x = ip[(size_t)ki * stride]; ki++; }
+    template <class T> BV_DEV void d(T &x) { x = dp[(size_t)kd * stride]; kd++; }
+    template <class T> BV_DEV void i(T &x) { x = ip[(size_t)ki * stride]; ki++; }
     BV_DEV void skip_d(int n) { kd += n; }
-    BV_DEV void dv(double &x) { d(x); }  // thread-per-system: vector elements are plain slots
-    BV_DEV void iv(int &x) { i(x); }
+    template <class T> BV_DEV void dv(T &x) { d(x); }  // thread-per-system: vector elements are plain slots
+    template <class T> BV_DEV void iv(T &x) { i(x); }
 };
 struct Storer {
     double *dp;
     int *ip;
     size_t stride;
     int kd = 0, ki = 0;
-    BV_DEV void d(double &x) { dp[(size_t)kd * stride] = x; kd++; }
-    BV_DEV void i(int &x) { ip[(size_t)ki * stride] = x; ki++; }
+    template <class T> BV_DEV void d(T &x) { dp[(size_t)kd * stride] = x; kd++; }
+    template <class T> BV_DEV void i(T &x) { ip[(size_t)ki * stride] = x; ki++; }
     BV_DEV void skip_d(int n) { kd += n; }
-    BV_DEV void dv(double &x) { d(x); }
-    BV_DEV void iv(int &x) { i(x); }
+    template <class T> BV_DEV void dv(T &x) { d(x); }
+    template <class T> BV_DEV void iv(T &x) { i(x); }
 };
 
 // ------------------------------------------------------- thread-per-system ------
 constexpr int kThreadTPB = 128;
-#ifndef BVODE_MINBLOCKS
-#define BVODE_MINBLOCKS 2
-#endif
 
 template <class POL>
-__global__ void __launch_bounds__(kThreadTPB, BVODE_MINBLOCKS) vode_thread_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem_thread[];
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;

@@ -41,41 +41,47 @@ struct ThreadPolicy {
         BV_DEV double atol(int i) const { return a[i]; }
     };
 
-    // Hot per-system arrays.  Default (BVODE_THREAD_SMEM = 0): registers.  = 1 keeps them in
-    // shared memory, element e of thread t at sm[e * TPB + t] (conflict-free, compile-time
-    // offsets).  Measured on B200 (2^20 Robertson systems): registers 305 ms; shared memory
-    // 328 ms at 8 warps/SM (231 registers: ptxas hoists the loads back into registers), and
-    // 436 ms / 506 ms when capped to 168 / 128 registers (spills) -- halving the resident
-    // warps costs 1.58x, so occupancy helps, but not through this route.  Kept as a knob.
+    // Hot per-system data.  The Nordsieck array always lives in registers.  Everything that is
+    // produced in one part of a step attempt and consumed in another -- tau(1:6), the LU factors
+    // and pivots, el / tq (dvset -> accept update / order selection), conp, hu, hnew, crate,
+    // etamax and the counters -- is parked in shared memory (BVODE_THREAD_SMEM = 1, default),
+    // element e of thread t at sm[e * TPB + t] (conflict-free, compile-time offsets): that cuts
+    // the registers live across the corrector from ~250 to the 168 that let three blocks (12
+    // warps) share an SM instead of two.  The accesses are volatile so that the compiler does
+    // not promote them back into registers across the step loop.  BVODE_THREAD_SMEM = 0 keeps
+    // everything in registers (255, 8 warps / SM).
 #ifndef BVODE_THREAD_SMEM
-#define BVODE_THREAD_SMEM 0
+#define BVODE_THREAD_SMEM 1
 #endif
     static constexpr int kTPB = 128;
-    // doubles: yh[6][N], tau[6], p[N][N], el[6], tq[5], sd[SD_COUNT]; ints: si[SI_COUNT]
-    static constexpr int kOffTau = kLmax * N, kOffP = kOffTau + kLmax, kOffEl = kOffP + N * N,
+    // doubles: tau[6], p[N][N], el[6], tq[5], sd[SD_COUNT]; ints: si[SI_COUNT], ipvt[N]
+    static constexpr int kOffTau = 0, kOffP = kOffTau + kLmax, kOffEl = kOffP + N * N,
                          kOffTq = kOffEl + kLmax, kOffSd = kOffTq + 5,
-                         kHotDoubles = kOffSd + SD_COUNT;
+                         kHotDoubles = kOffSd + SD_COUNT, kHotInts = SI_COUNT + N;
 #if BVODE_THREAD_SMEM
     struct Hot {
-        double *b;  // this thread's element 0 of the double region
-        int *bi;    // ... of the int region
-        BV_DEV double &yh(int j, int i) const { return b[(j * N + i) * kTPB]; }
-        BV_DEV double &tau(int i) const { return b[(kOffTau + (i - 1)) * kTPB]; }
-        BV_DEV double &p(int i, int j) const { return b[(kOffP + i * N + j) * kTPB]; }
-        BV_DEV double &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
-        BV_DEV double &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
-        BV_DEV double &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
-        BV_DEV int &si(int k) const { return bi[k * kTPB]; }
+        double yhv[kLmax][N];
+        volatile double *b;  // this thread's element 0 of the double region
+        volatile int *bi;    // ... of the int region
+        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV volatile double &tau(int i) const { return b[(kOffTau + (i - 1)) * kTPB]; }
+        BV_DEV volatile double &p(int i, int j) const { return b[(kOffP + i * N + j) * kTPB]; }
+        BV_DEV volatile double &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
+        BV_DEV volatile double &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
+        BV_DEV volatile double &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
+        BV_DEV volatile int &si(int k) const { return bi[k * kTPB]; }
+        BV_DEV volatile int &ipvt(int i) const { return bi[(SI_COUNT + i) * kTPB]; }
         BV_DEV void bind(double *smem, int tid) {
             b = smem + tid;
             bi = reinterpret_cast<int *>(smem + (size_t)kHotDoubles * kTPB) + tid;
         }
     };
-    static constexpr size_t kSmemBytes = (sizeof(double) * kHotDoubles + sizeof(int) * SI_COUNT) * kTPB;
+    static constexpr size_t kSmemBytes = (sizeof(double) * kHotDoubles + sizeof(int) * kHotInts) * kTPB;
+    static constexpr int kMinBlocks = 3;
 #else
     struct Hot {
         double yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
-        int siv[SI_COUNT];
+        int siv[SI_COUNT], ipv[N];
         BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
         BV_DEV double &tau(int i) { return tauv[i]; }
         BV_DEV double &p(int i, int j) { return pv[i][j]; }
@@ -83,21 +89,23 @@ struct ThreadPolicy {
         BV_DEV double &tq(int i) { return tqv[i]; }
         BV_DEV double &sd(int k) { return sdv[k]; }
         BV_DEV int &si(int k) { return siv[k]; }
+        BV_DEV int &ipvt(int i) { return ipv[i]; }
         BV_DEV void bind(double *, int) {}
     };
     static constexpr size_t kSmemBytes = 0;
+    static constexpr int kMinBlocks = 2;
 #endif
 
     struct Lin {
-        // P = I - h*rl1*J and then its LU factors are hot.p(i, j) (row i, col j); fast build:
-        // the diagonal holds 1/u_kk after dgefa.
+        // P = I - h*rl1*J and then its LU factors are hot.p(i, j) (row i, col j), the pivot rows
+        // hot.ipvt(k) (0-based); fast build: the diagonal holds 1/u_kk after dgefa.
         GlobalVec wjs;    // saved Jacobian wm(locjs), element (i,j) at slot i*N+j (mf > 0)
-        int ipvt[N];      // 0-based pivot rows
     };
 
-    BV_DEV static void lin_init(Lin &l) {
+    template <class ENG>
+    BV_DEV static void lin_init(ENG &e) {
 #pragma unroll
-        for (int i = 0; i < N; i++) l.ipvt[i] = i;
+        for (int i = 0; i < N; i++) e.hot.ipvt(i) = i;
     }
 
     // state slots of one system, in visit order: yh, acsav*, acor, p, wjs*, tau, scalars
@@ -109,14 +117,13 @@ struct ThreadPolicy {
     BV_DEV static void visit_acsav(AcSav &, V &v) { v.skip_d(N); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
-        Lin &l = e.lin;
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
             for (int j = 0; j < N; j++) v.d(e.hot.p(i, j));
         if (SAVEJ) v.skip_d(N * N);
 #pragma unroll
-        for (int i = 0; i < N; i++) v.i(l.ipvt[i]);
+        for (int i = 0; i < N; i++) v.i(e.hot.ipvt(i));
     }
 
     // dvnorm_default, M:3295-3311: sequential sum in index order, like the reference.
@@ -178,8 +185,8 @@ struct ThreadPolicy {
     }
 
     // ---- dgefa, LP:46-120 ----------------------------------------------------------
-    BV_DEV static int dgefa(Hot &hot, int (&ipvt)[N]) {
-#define a_(i, j) hot.p(i, j)
+    BV_DEV static int dgefa(double (&a)[N][N], int (&ipvt)[N]) {
+#define a_(i, j) a[i][j]
         int info = 0;
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
@@ -238,8 +245,8 @@ struct ThreadPolicy {
     }
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------
-    BV_DEV static void dgesl(Hot &hot, const int (&ipvt)[N], double (&b)[N]) {
-#define a_(i, j) hot.p(i, j)
+    BV_DEV static void dgesl(const double (&a)[N][N], const int (&ipvt)[N], double (&b)[N]) {
+#define a_(i, j) a[i][j]
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
             const int l = ipvt[k];
@@ -268,7 +275,17 @@ struct ThreadPolicy {
     }
 
     template <class ENG>
-    BV_DEV static void solve(ENG &e, double (&x)[N]) { dgesl(e.hot, e.lin.ipvt, x); }
+    BV_DEV static void solve(ENG &e, double (&x)[N]) {
+        double a[N][N];
+        int ipvt[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < N; j++) a[i][j] = e.hot.p(i, j);
+            ipvt[i] = e.hot.ipvt(i);
+        }
+        dgesl(a, ipvt, x);
+    }
 
     // ---- dvjac, miter 1 / 2 (M:2930-3001) -------------------------------------------
     template <class ENG>
@@ -283,6 +300,7 @@ struct ThreadPolicy {
             if (c.icf == 1 && c.drc < 0.2) jok = -1;              // ccmxj = 0.2, M:1327
             if (c.icf == 2) jok = -1;
         }
+        double P[N][N];
         if (jok == -1) {
             e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
@@ -291,19 +309,8 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) e.hot.p(i, j) = 0.0;
-                {
-                    double pd[N][N];
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-#pragma unroll
-                        for (int j = 0; j < N; j++) pd[i][j] = 0.0;
-                    PROB::jac(c.tn, e.y, pd, e.par);
-#pragma unroll
-                    for (int i = 0; i < N; i++)
-#pragma unroll
-                        for (int j = 0; j < N; j++) e.hot.p(i, j) = pd[i][j];
-                }
+                    for (int j = 0; j < N; j++) P[i][j] = 0.0;  // M:2947-2949
+                PROB::jac(c.tn, e.y, P, e.par);
             } else {
                 // finite differences, M:2959-2976 (ftem = acor)
                 double fac = norm(e.savf, e.ewt);
@@ -318,7 +325,7 @@ struct ThreadPolicy {
                     fac = qrcp(r);
                     f(c.tn, e.y, e.acor, e.par);
 #pragma unroll
-                    for (int i = 0; i < N; i++) e.hot.p(i, j) = (e.acor[i] - e.savf[i]) * fac;
+                    for (int i = 0; i < N; i++) P[i][j] = (e.acor[i] - e.savf[i]) * fac;
                     e.y[j] = yj;
                 }
                 e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
@@ -327,7 +334,7 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, e.hot.p(i, j));
+                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, P[i][j]);
             }
         } else {
             c.jcur = 0;
@@ -335,19 +342,26 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) e.hot.p(i, j) = l.wjs.get(i * N + j);
+                    for (int j = 0; j < N; j++) P[i][j] = l.wjs.get(i * N + j);
             }
         }
         const double con = -hrl1;
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
-            for (int j = 0; j < N; j++) e.hot.p(i, j) = con * e.hot.p(i, j);
+            for (int j = 0; j < N; j++) P[i][j] = con * P[i][j];
 #pragma unroll
-        for (int i = 0; i < N; i++) e.hot.p(i, i) = e.hot.p(i, i) + 1.0;
+        for (int i = 0; i < N; i++) P[i][i] = P[i][i] + 1.0;
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
-        const int ier = dgefa(e.hot, l.ipvt);
+        int ipvt[N];
+        const int ier = dgefa(P, ipvt);
         if (ier != 0) ierpj = 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < N; j++) e.hot.p(i, j) = P[i][j];
+            e.hot.ipvt(i) = ipvt[i];
+        }
     }
 };
 

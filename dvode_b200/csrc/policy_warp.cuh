@@ -169,7 +169,8 @@ struct WarpDensePolicy : WarpCommon<PROB> {
         GlobalVec wjs;  // row `lane` of the saved Jacobian, element j at slot j (mf > 0)
         int ipv;        // lane k holds ipvt(k) (0-based row)
     };
-    BV_DEV static void lin_init(Lin &l) { l.ipv = lane(); }
+    template <class ENG>
+    BV_DEV static void lin_init(ENG &e) { e.lin.ipv = lane(); }
     static int smem_doubles(int, int, bool) { return N * LDP; }
     // per-lane double slots of one system, in visit order: yh[6], acsav, acor, wjs[N]*
     static constexpr int kLaneSlotWjs = kLmax + 2;
@@ -358,7 +359,8 @@ struct WarpBandPolicy : WarpCommon<PROB> {
         int ml, mu, ld;
         int ipv;       // lane k holds ipvt(k+1) as a 0-based row of the full matrix
     };
-    BV_DEV static void lin_init(Lin &l) { l.ipv = lane(); }
+    template <class ENG>
+    BV_DEV static void lin_init(ENG &e) { e.lin.ipv = lane(); }
 
     BV_DEV static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
     // doubles of shared memory one system needs

@@ -67,13 +67,6 @@ BV_DEV double pick(const double *a, int idx) {
 }
 
 template <int LO, int HI, class HOT>
-BV_DEV double pick_el(HOT &hot, int idx) {
-    double r = hot.el(LO);
-#pragma unroll
-    for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? hot.el(i) : r;
-    return r;
-}
-template <int LO, int HI, class HOT>
 BV_DEV double pick_tau(HOT &hot, int idx) {
     double r = hot.tau(LO);
 #pragma unroll
@@ -83,79 +76,102 @@ BV_DEV double pick_tau(HOT &hot, int idx) {
 
 // ---------------------------------------------------------------- dvset (BDF) ----
 // M:2440-2490, 2559.  Loops are unrolled to the compile-time maximum order and guarded
-// by nq, so el/tau stay in registers.
+// by nq.  el / tq are built in local registers and committed to the policy's storage once at
+// the end (a policy may keep them in shared memory: they are produced here and consumed after
+// the corrector, and registers across the corrector are what limits occupancy).
 template <class HOT>
 BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const int nq = c.nq, L = c.L;
     const double h = c.h;
+    double el[kLmax + 1], tq[6];
 #pragma unroll
-    for (int i = 3; i <= kLmax; i++) hot.el(i) = 0.0;
-    hot.el(1) = 1.0;
-    hot.el(2) = 1.0;
+    for (int i = 3; i <= kLmax; i++) el[i] = 0.0;
+    el[1] = 1.0;
+    el[2] = 1.0;
+    double tauv[kLmax + 1];
+#pragma unroll
+    for (int i = 1; i <= kLmax; i++) tauv[i] = hot.tau(i);
     double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
     if (nq != 1) {
 #pragma unroll
         for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
             if (j <= nq - 2) {
-                hsum = hsum + hot.tau(j);
+                hsum = hsum + tauv[j];
                 rxi = qdiv(h, hsum);
                 alph0 = alph0 - 1.0 / (double)(j + 1);
 #pragma unroll
                 for (int iback = 1; iback <= j + 1; iback++) {
                     const int i = (j + 3) - iback;
-                    hot.el(i) = hot.el(i) + hot.el(i - 1) * rxi;
+                    el[i] = el[i] + el[i - 1] * rxi;
                 }
             }
         }
         alph0 = alph0 - recip_int(nq);
-        rxis = -hot.el(2) - alph0;
-        hsum = hsum + pick_tau<1, kMaxOrdBdf>(hot, nq - 1);
+        rxis = -el[2] - alph0;
+        hsum = hsum + pick<1, kMaxOrdBdf>(tauv, nq - 1);
         rxi = qdiv(h, hsum);
-        ahatn0 = -hot.el(2) - rxi;
+        ahatn0 = -el[2] - rxi;
 #pragma unroll
         for (int i = kLmax; i >= 2; i--) {
-            if (i <= nq + 1) hot.el(i) = hot.el(i) + hot.el(i - 1) * rxis;
+            if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
         }
     }
     const double t1 = 1.0 - ahatn0 + alph0;
     const double t2 = 1.0 + (double)nq * t1;
-    const double elL = pick_el<2, kLmax>(hot, L);
-    hot.tq(2) = fabs(qdiv(alph0 * t2, t1));
-    hot.tq(5) = fabs(qdiv(t2, qdiv(elL * rxi, rxis)));
+    const double elL = pick<2, kLmax>(el, L);
+    tq[2] = fabs(qdiv(alph0 * t2, t1));
+    tq[5] = fabs(qdiv(t2, qdiv(elL * rxi, rxis)));
+    tq[1] = 0.0;
+    tq[3] = 0.0;
     if (c.nqwait == 1) {
         const double cnqm1 = qdiv(rxis, elL);
         const double t3 = alph0 + recip_int(nq);
         const double t4 = ahatn0 + rxi;
         double elp = qdiv(t3, 1.0 - t4 + t3);
-        hot.tq(1) = fabs(qdiv(elp, cnqm1));
-        hsum = hsum + pick_tau<1, kLmax>(hot, nq);
+        tq[1] = fabs(qdiv(elp, cnqm1));
+        hsum = hsum + pick<1, kLmax>(tauv, nq);
         rxi = qdiv(h, hsum);
         const double t5 = alph0 - recip_int(nq + 1);
         const double t6 = ahatn0 - rxi;
         elp = qdiv(t2, 1.0 - t6 + t5);
-        hot.tq(3) = fabs(elp * rxi * ((double)L + 1.0) * t5);
+        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
     }
-    hot.tq(4) = 0.1 * hot.tq(2);
+    tq[4] = 0.1 * tq[2];
+#pragma unroll
+    for (int i = 1; i <= kLmax; i++) hot.el(i) = el[i];
+    // tq(1), tq(3) are only read by the order selection of the step whose dvset ran with
+    // nqwait == 1 (M:2272-2292), so they need no storage otherwise
+    hot.tq(2) = tq[2];
+    hot.tq(4) = tq[4];
+    hot.tq(5) = tq[5];
+    if (c.nqwait == 1) {
+        hot.tq(1) = tq[1];
+        hot.tq(3) = tq[3];
+    }
 }
 
 // dvjust coefficient part for both directions (the yh updates are done by the engine):
 // builds el(3:) from the tau history, M:2589-2616 (iord = +1) and M:2629-2643 (iord = -1).
 // The two branches of the reference share the recurrence el(i) = el(i)*x + el(i-1); they are
 // one code path here so that lanes raising and lowering their order execute together.
-// Returns t1 = (-alph0 - alph1)/prod for the order increase.
+// el is returned in a local array (the reference leaves it in el(:), which dvset overwrites
+// before its next use).  Returns t1 = (-alph0 - alph1)/prod for the order increase.
 template <class HOT>
-BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up) {
+BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up, double (&el)[kLmax + 1]) {
     const int nq = c.nq;
 #pragma unroll
-    for (int j = 1; j <= kLmax; j++) hot.el(j) = 0.0;
-    hot.el(3) = 1.0;
+    for (int j = 0; j <= kLmax; j++) el[j] = 0.0;
+    el[3] = 1.0;
     double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
     double hsum = up ? c.hscal : 0.0;
     const int jmax = up ? nq - 1 : nq - 2;
+    double tauv[kLmax + 1];
+#pragma unroll
+    for (int i = 1; i <= kLmax; i++) tauv[i] = hot.tau(i);
 #pragma unroll
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
         if (j <= jmax) {
-            hsum = hsum + (up ? hot.tau(j + 1) : hot.tau(j));
+            hsum = hsum + (up ? tauv[j + 1] : tauv[j]);
             const double xi = qdiv(hsum, c.hscal);
             if (up) {
                 prod = prod * xi;
@@ -166,7 +182,7 @@ BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up) {
 #pragma unroll
             for (int iback = 1; iback <= j + 1; iback++) {
                 const int i = (j + 4) - iback;
-                hot.el(i) = hot.el(i) * x + hot.el(i - 1);
+                el[i] = el[i] * x + el[i - 1];
             }
             xiold = xi;
         }
@@ -290,7 +306,8 @@ struct Engine {
     //         column L is zeroed to keep the zero-column invariant.
     //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
     BV_DEV void order_change(bool up) {
-        const double t1 = dvjust_coeffs(c, hot, up);
+        double el[kLmax + 1];
+        const double t1 = dvjust_coeffs(c, hot, up, el);
         double col[NLOC];
         if (up) {
 #pragma unroll
@@ -306,7 +323,7 @@ struct Engine {
         for (int j = 3; j <= kLmax; j++) {
             if (j <= jhi) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.el(j) * col[i];
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + el[j] * col[i];
             }
             if (j == jnew) {
 #pragma unroll
@@ -453,7 +470,7 @@ struct Engine {
         }
 #pragma unroll
         for (int i = 0; i < NLOC; i++) { acsav.set(i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
-        POL::lin_init(lin);
+        POL::lin_init(*this);
         POL::f(t, y, savf, par);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) hot.yh(1, i) = savf[i];
