@@ -152,16 +152,8 @@ BV_DEV double recip_int(int k) { return kRecipTab[k & 15]; }
 
 #if !BVODE_STRICT
 // Fast build: the step-size ratio eta = 1/(x**(1/k) + addon) (M:2201, 2275, 2282, 2292) is
-// evaluated as 1/(exp2(log2(x)/k) + addon) with the double-precision log2 / exp2 (rounding-
-// level difference from pow).  -DBVODE_ETA_F32 switches to the single-precision hardware
-// log2 / exp2 (relative error ~1e-7 in eta): faster, still a valid VODE since eta is a
-// heuristic factor and accuracy is controlled by the error test, but the trajectories then
-// separate from the reference's sooner, so it is not the default.
-#ifdef BVODE_ETA_F32
-typedef float lg_t;
-BV_DEV lg_t log2_fast(double x) { return __log2f((float)x); }
-BV_DEV double exp2_fast(lg_t l) { return (double)exp2f(l); }
-#else
+// evaluated as 1/(exp2(log2(x)/k) + addon) with the double-precision log2 / exp2 below
+// (rounding-level difference from pow).
 typedef double lg_t;
 // log2 / exp2 in double precision, ~2 ulp (checked against libm over 2e6 random arguments:
 // max relative error 4.3e-16 / 2.2e-16), about a third of the instructions of CUDA's
@@ -187,6 +179,16 @@ BV_DEV lg_t log2_fast(double x) {
     const double t = s * 2.8853900817779268;  // 2/ln 2
     return fma(t * z, p, t) + (double)e;
 }
+// log2 of a positive normal double in single precision: exponent exactly, mantissa through the
+// hardware lg2 (absolute error < 3e-7 + 6e-8 |log2 x|).  Only used to ORDER step-ratio
+// candidates that are far apart; near_f32 says when two such values are too close to call.
+BV_DEV float log2_f32(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const int e = (int)(hi >> 20) - 1023;
+    const float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
+    return (float)e + __log2f(m);
+}
+BV_DEV bool near_f32(float a, float b) { return fabsf(a - b) <= 1.0e-5f * (1.0f + fabsf(a) + fabsf(b)); }
 BV_DEV double exp2_fast(lg_t l) {
     const double n = rint(l), f = l - n;
     double p = 1.369148885390412888e-12;
@@ -208,7 +210,6 @@ BV_DEV double exp2_fast(lg_t l) {
     if (ni > 1020) return __longlong_as_double(0x7ff0000000000000LL);
     return p * __longlong_as_double((long long)(ni + 1023) << 52);
 }
-#endif
 #endif
 
 }  // namespace BVODE_NS

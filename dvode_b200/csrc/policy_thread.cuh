@@ -77,7 +77,10 @@ struct ThreadPolicy {
         }
     };
     static constexpr size_t kSmemBytes = (sizeof(double) * kHotDoubles + sizeof(int) * kHotInts) * kTPB;
-    static constexpr int kMinBlocks = 3;
+#ifndef BVODE_THREAD_MINBLOCKS
+#define BVODE_THREAD_MINBLOCKS 3
+#endif
+    static constexpr int kMinBlocks = BVODE_THREAD_MINBLOCKS;
 #else
     struct Hot {
         double yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];

@@ -190,6 +190,26 @@ BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up, double (&el)[kLmax + 1]) 
     return qdiv(-alph0 - alph1, prod);
 }
 
+#if !BVODE_STRICT
+// Which step-ratio candidate wins (M:2294-2317), from log-ratios l = log2(x)/k (smaller l =
+// larger eta): 0 = current order, 1 = order - 1, 2 = order + 1.
+template <class T>
+BV_DEV int choose_ratio(T lq, T lm, T lp) {
+    if (lq > lp) return (lp >= lm) ? 1 : 2;
+    return (lq > lm) ? 1 : 0;
+}
+// The same decision from double-precision logs: the rare case where the single-precision
+// screen is too close to call.  Out of line to keep the step loop small.
+__device__ __noinline__ int choose_ratio_f64(double xq, double xm, double xp, double scq, double scm,
+                                             double scp, bool has_m, bool has_p) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double lq = log2_fast(xq) * scq;
+    const double lm = has_m ? log2_fast(xm) * scm : inf;
+    const double lp = has_p ? log2_fast(xp) * scp : inf;
+    return choose_ratio(lq, lm, lp);
+}
+#endif
+
 // =================================================================== Engine =====
 // POL provides:
 //   Prob, N (equations), NLOC (vector elements held by this thread), MITER
@@ -765,15 +785,25 @@ struct Engine {
                     c.tn = told;
                     retract();
                 }
-                // step-size ratio at the current order, used by both the accept path (M:2275)
-                // and the first two error-test failures (M:2201): one evaluation for both
+                // ---- step-size ratio candidates (M:2201, 2275, 2282, 2292).
+                // Strict build: eta = 1/(x**(1/k) + addon) evaluated where the reference does.
+                // Fast build: the candidates are ordered through log2(x)/k, first in single
+                // precision (hardware lg2; a decision is only taken from it when the margin is
+                // far above its error, else the double-precision logs decide -- so the choices
+                // are those of the double-precision comparison), and ONE double log2 / exp2 pair
+                // per attempt serves whichever lane needs a ratio: the failed error test, or
+                // the accepted step whose ratio reaches `thresh` (phase B below).
 #if BVODE_STRICT
                 const double etaq = conv ? eta_of(bias2 * dsm, c.L) : 0.0;
 #else
-                // log2(bias2*dsm)/L from dsm^2: log2(bias2^2 * dsm^2) / (2L)
-                const lg_t lq = conv ? log2_fast((bias2 * bias2) * dsm) * (lg_t)(0.5 * recip_int(c.L))
-                                     : (lg_t)0;
+                const double xq = (bias2 * bias2) * dsm;  // dsm holds dsm^2: log2(x)/(2L)
+                int pend = 0;  // 1: ratio for a failed error test, 2: ratio after an accepted step
+                int wsel = 0;  // winning candidate: 0 current order, 1 order - 1, 2 order + 1
+                double xsel = xq, scsel = 0.5 * recip_int(c.L);
+                float lwf = 0.0f;
 #endif
+                // hmin/|h| of the failure paths (M:2202, 2221, 2360), one evaluation for all
+                const double hmr = accept ? 0.0 : qdiv(o.hmin, fabs(c.h));
                 if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
                     c.kflag = c.kflag - 1;
@@ -788,18 +818,18 @@ struct Engine {
                         if (c.kflag > kfc) {
 #if BVODE_STRICT
                             c.eta = etaq;
-#else
-                            c.eta = qrcp(exp2_fast(lq) + addon);
-#endif
-                            c.eta = dmax2(dmax2(c.eta, qdiv(o.hmin, fabs(c.h))), etamin);
+                            c.eta = dmax2(dmax2(c.eta, hmr), etamin);
                             if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
+#else
+                            pend = 1;
+#endif
                             entry = E_RESCALE;
                         } else if (c.kflag == kfh) {
                             c.kflag = -1;
                             c.jstart = 1;
                             istate = IST_ERRTEST;
                         } else if (c.nq == 1) {
-                            c.eta = dmax2(etamin, qdiv(o.hmin, fabs(c.h)));
+                            c.eta = dmax2(etamin, hmr);
                             c.h = c.h * c.eta;
                             c.hscal = c.h;
                             hot.tau(1) = c.h;
@@ -810,7 +840,7 @@ struct Engine {
                             c.nqwait = 10;
                             entry = E_PREDICT;
                         } else {
-                            c.eta = dmax2(etamin, qdiv(o.hmin, fabs(c.h)));
+                            c.eta = dmax2(etamin, hmr);
                             entry = E_DOWN_RESCALE;
                         }
                     }
@@ -824,7 +854,7 @@ struct Engine {
                         c.jstart = 1;
                         istate = IST_CONVFAIL;
                     } else {
-                        c.eta = dmax2(etacf, qdiv(o.hmin, fabs(c.h)));
+                        c.eta = dmax2(etacf, hmr);
                         nflag = -1;
                         entry = E_RESCALE;
                     }
@@ -841,8 +871,9 @@ struct Engine {
                     hot.tau(1) = c.h;
 #pragma unroll
                     for (int j = 1; j <= kLmax; j++) {
+                        const double elj = hot.el(j);
 #pragma unroll
-                        for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.el(j) * acor[i];
+                        for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + elj * acor[i];
                     }
                     c.nqwait = c.nqwait - 1;
                     if ((c.L != lmax) && (c.nqwait == 1)) {
@@ -856,7 +887,9 @@ struct Engine {
 #if BVODE_STRICT
                         double eta = etaq;
 #else
-                        lg_t lwin = lq;
+                        pend = 2;
+                        const float scqf = (float)scsel;
+                        lwf = log2_f32(xq) * scqf;
 #endif
                         if (c.nqwait == 0) {
                             c.nqwait = 2;
@@ -905,40 +938,31 @@ struct Engine {
                                 newq = c.nq - 1;
                             }
 #else
-                            // eta_a < eta_b  <=>  log2(x_a)/k_a > log2(x_b)/k_b ; a ratio of 0
-                            // (order not available) is log-ratio +infinity
-                            const lg_t inf = (lg_t)__int_as_float(0x7f800000);
-                            const lg_t lm1 = (c.nq != 1)
-                                ? log2_fast((bias1 * bias1) * ddn) * (lg_t)(0.5 * recip_int(c.L - 1)) : inf;
-                            const lg_t lp1 = (c.L != lmax)
-                                ? log2_fast((bias3 * bias3) * dup) * (lg_t)(0.5 * recip_int(c.L + 1)) : inf;
-                            if (lq > lp1) {
-                                if (lp1 >= lm1) {
-                                    lwin = lm1;
-                                    newq = c.nq - 1;
-                                } else {
-                                    lwin = lp1;
-                                    newq = c.nq + 1;
-                                    save_acor = true;
-                                }
-                            } else if (lq > lm1) {
-                                lwin = lm1;
-                                newq = c.nq - 1;
+                            // eta_a < eta_b  <=>  log2(x_a)/k_a > log2(x_b)/k_b ; an order that is
+                            // not available (ratio 0) has log-ratio +infinity
+                            const bool has_m = (c.nq != 1), has_p = (c.L != lmax);
+                            const double xm = (bias1 * bias1) * ddn, xp = (bias3 * bias3) * dup;
+                            const double scm = 0.5 * recip_int(c.L - 1), scp = 0.5 * recip_int(c.L + 1);
+                            auto choose = [](float lq_, float lm_, float lp_) -> int {
+                                return choose_ratio(lq_, lm_, lp_);
+                            };
+                            const float lmf = has_m ? log2_f32(xm) * (float)scm : 1.0e30f;
+                            const float lpf = has_p ? log2_f32(xp) * (float)scp : 1.0e30f;
+                            wsel = choose(lwf, lmf, lpf);
+                            if (near_f32(lwf, lpf) || near_f32(lpf, lmf) || near_f32(lwf, lmf)) {
+                                wsel = choose_ratio_f64(xq, xm, xp, scsel, scm, scp, has_m, has_p);
                             }
+                            if (wsel == 1) { newq = c.nq - 1; xsel = xm; scsel = scm; lwf = lmf; }
+                            if (wsel == 2) { newq = c.nq + 1; xsel = xp; scsel = scp; lwf = lpf; save_acor = true; }
 #endif
                         }
                         if (save_acor) {
 #pragma unroll
                             for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
                         }
-                        // label 450, M:2320-2330 (etamax != 1 here)
 #if BVODE_STRICT
-                        const bool keep = (eta < thresh);
-#else
-                        const bool keep = (lwin > l2thr);
-                        const double eta = qrcp(exp2_fast(lwin) + addon);
-#endif
-                        if (keep) {
+                        // label 450, M:2320-2330 (etamax != 1 here)
+                        if (eta < thresh) {
                             c.newq = c.nq;
                             c.newh = 0;
                             c.eta = 1.0;
@@ -950,6 +974,10 @@ struct Engine {
                             c.newh = 1;
                             hot.sd(SD_HNEW) = c.h * c.eta;
                         }
+#else
+                        c.newq = newq;  // the candidate; phase B resets it when the step size is kept
+                        c.eta = hot.sd(SD_ETAMAX);  // ... and needs this step's etamax, reset below
+#endif
                     } else {
                         if (c.nqwait < 2) c.nqwait = 2;
                         c.newq = c.nq;
@@ -975,6 +1003,35 @@ struct Engine {
                     entry = E_NEWSTEP;
                     reached = !((c.tn - tout) * c.h < 0.0);
                 }
+#if !BVODE_STRICT
+                // ---- phase B: the one ratio evaluation of this attempt
+                if (pend != 0) {
+                    const float l2thr_f = -0.58496466f;
+                    const bool keepf = (lwf > l2thr_f);
+                    const bool unsure = (pend == 2) && near_f32(lwf, l2thr_f);
+                    double lsel = 0.0;
+                    if (pend == 1 || !keepf || unsure) lsel = log2_fast(xsel) * scsel;
+                    const bool keep = (pend == 2) && (unsure ? (lsel > l2thr) : keepf);
+                    if (keep) {  // label 450, M:2320-2324
+                        c.newq = c.nq;
+                        c.newh = 0;
+                        c.eta = 1.0;
+                        hot.sd(SD_HNEW) = c.h;
+                    } else {
+                        const double eta = qrcp(exp2_fast(lsel) + addon);
+                        if (pend == 1) {  // M:2201-2204
+                            c.eta = dmax2(dmax2(eta, hmr), etamin);
+                            if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
+                        } else {  // M:2325-2330; c.eta holds this step's etamax
+                            c.eta = dmin2(eta, c.eta);
+                            const double d = dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
+                            if (d != 1.0) c.eta = qdiv(c.eta, d);
+                            c.newh = 1;
+                            hot.sd(SD_HNEW) = c.h * c.eta;
+                        }
+                    }
+                }
+#endif
             }  // if (istate == 0)
         }
         if (istate == IST_OK) {
