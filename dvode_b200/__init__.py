@@ -3,11 +3,20 @@
 The product is the CUDA library `libbvode.so` (sources in dvode_b200/csrc, C ABI in
 include/bvode.h).  This package is the thin host-side mirror of the reference's
 `dvode_t` interface (initialize / solve / dvindy / dvsrco) over that C ABI.  There is
-no CPU fallback: importing `dvode_b200.api` fails loudly if the library is missing.
+no CPU fallback: touching any solver name (`dvode_b200.dvode_t`, `dvode_b200.api`, ...)
+fails loudly if the library is missing.  Only `dvode_b200.build` (the nvcc recipe) and
+`dvode_b200.batches` / `dvode_b200.sharding` (pure host helpers) import without it.
 """
-from .api import (BvodeError, dvode_t, fp64_peak_tflops, library_path, problem_info,  # noqa: F401
-                  problem_names)
-from . import batches  # noqa: F401
+import importlib
 
-__all__ = ["dvode_t", "BvodeError", "problem_info", "problem_names", "fp64_peak_tflops",
-           "library_path", "batches"]
+_API_NAMES = ("BvodeError", "dvode_t", "fp64_peak_tflops", "library_path", "problem_info",
+              "problem_names")
+__all__ = list(_API_NAMES) + ["api", "batches", "build", "sharding"]
+
+
+def __getattr__(name):
+    if name in _API_NAMES:
+        return getattr(importlib.import_module(".api", __name__), name)
+    if name in ("api", "batches", "build", "sharding"):
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -44,11 +44,11 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nv = _nvcc()
-    units = [
-        ("reg_fast.o", "bvode_registry.cu", ["-DBVODE_STRICT=0"] + os.environ.get("BVODE_EXTRA_NVCC", "").split()),
-        ("reg_strict.o", "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false"]),
-        ("capi.o", "bvode_capi.cu", []),
-    ]
+    fast_extra = os.environ.get("BVODE_EXTRA_NVCC", "").split()
+    units = [("capi.o", "bvode_capi.cu", [])]
+    for u in range(4):  # one translation unit per problem and build, compiled in parallel
+        units.append(("reg_fast_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=0", "-DBVODE_UNIT=%d" % u] + fast_extra))
+        units.append(("reg_strict_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false", "-DBVODE_UNIT=%d" % u]))
     procs = []
     for obj, src, extra in units:
         cmd = [nv] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + [

@@ -11,8 +11,40 @@
 #include <string>
 #include <vector>
 
-extern "C" const ProblemEntry *bvode_registry_fast(int *n);
-extern "C" const ProblemEntry *bvode_registry_strict(int *n);
+// one entry per (build, problem), each from its own translation unit (bvode_registry.cu)
+#define BVODE_NPROBLEMS 4
+extern "C" {
+const ProblemEntry *bvode_entry_fast_0(void);
+const ProblemEntry *bvode_entry_fast_1(void);
+const ProblemEntry *bvode_entry_fast_2(void);
+const ProblemEntry *bvode_entry_fast_3(void);
+const ProblemEntry *bvode_entry_strict_0(void);
+const ProblemEntry *bvode_entry_strict_1(void);
+const ProblemEntry *bvode_entry_strict_2(void);
+const ProblemEntry *bvode_entry_strict_3(void);
+}
+static const ProblemEntry *bvode_registry_fast(int *n) {
+    static ProblemEntry tab[BVODE_NPROBLEMS];
+    static bool init = false;
+    if (!init) {
+        tab[0] = *bvode_entry_fast_0(); tab[1] = *bvode_entry_fast_1();
+        tab[2] = *bvode_entry_fast_2(); tab[3] = *bvode_entry_fast_3();
+        init = true;
+    }
+    *n = BVODE_NPROBLEMS;
+    return tab;
+}
+static const ProblemEntry *bvode_registry_strict(int *n) {
+    static ProblemEntry tab[BVODE_NPROBLEMS];
+    static bool init = false;
+    if (!init) {
+        tab[0] = *bvode_entry_strict_0(); tab[1] = *bvode_entry_strict_1();
+        tab[2] = *bvode_entry_strict_2(); tab[3] = *bvode_entry_strict_3();
+        init = true;
+    }
+    *n = BVODE_NPROBLEMS;
+    return tab;
+}
 
 static thread_local std::string g_err;
 const char *bvode_last_error(void) { return g_err.c_str(); }

@@ -19,7 +19,7 @@ template <class ENG, class V>
 BV_DEV void visit_state(ENG &e, V &v) {
     Ctl &c = e.c;
 #pragma unroll
-    for (int j = 0; j < kLmax; j++)
+    for (int j = 0; j < ENG::kLmax; j++)
 #pragma unroll
         for (int i = 0; i < ENG::NLOC; i++) v.dv(e.hot.yh(j, i));
     ENG::POLICY::visit_acsav(e.acsav, v);
@@ -27,7 +27,7 @@ BV_DEV void visit_state(ENG &e, V &v) {
     for (int i = 0; i < ENG::NLOC; i++) v.dv(e.acor[i]);
     ENG::POLICY::visit_lin(e, v);
 #pragma unroll
-    for (int j = 1; j <= kLmax; j++) v.d(e.hot.tau(j));
+    for (int j = 1; j <= ENG::kLmax; j++) v.d(e.hot.tau(j));
     v.d(c.h); v.d(c.hscal); v.d(e.hot.sd(SD_HNEW)); v.d(e.hot.sd(SD_HU)); v.d(c.eta); v.d(e.hot.sd(SD_ETAMAX)); v.d(c.tn);
     v.d(c.rc); v.d(c.prl1); v.d(e.hot.sd(SD_CRATE)); v.d(e.hot.sd(SD_CONP));
     v.i(c.nq); v.i(c.nqwait); v.i(c.newq); v.i(c.newh); v.i(c.jstart); v.i(c.icf); v.i(c.ipup);
@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
 //   scalars   [kScalarD][nsys]            one copy per system (lane 0 writes, all lanes read)
 //   per-lane  [kLaneSlots][nsys][32]      lane l of system s at (k*nsys + s)*32 + l: coalesced
 //   blocks    [nsys][nblock]              shared-memory image of the band arrays
-constexpr int kScalarD = kLmax + 11;  // tau(1:6) + the 11 scalars of visit_state
+template <class POL>
+__host__ __device__ constexpr int scalar_d() { return POL::kLmax + 11; }  // tau(1:lmax) + the 11 scalars of visit_state
 constexpr int kScalarI = 19;
 constexpr int kWarpTPB = 128;         // 4 systems per block
 
@@ -229,7 +230,7 @@ struct WarpLayout {
     static constexpr int N = POL::N;
     static int nblock(int ml, int mu) { return POL::smem_doubles(ml, mu, POL::SAVEJ); }
     static void sizes(int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
-        *nd = nsys * ((size_t)kScalarD + (size_t)POL::kLaneSlots * 32 + (size_t)nblock(ml, mu));
+        *nd = nsys * ((size_t)scalar_d<POL>() + (size_t)POL::kLaneSlots * 32 + (size_t)nblock(ml, mu));
         *ni = nsys * ((size_t)kScalarI + (size_t)POL::kLaneIntSlots * 32);
     }
 };
@@ -238,7 +239,7 @@ template <class POL>
 BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, size_t nsys,
                       size_t sys, int ln, int warp, int ml, int mu, double *smem,
                       const double *&dl, const double *&db, const int *&il, int &nblock) {
-    dl = dstate + (size_t)kScalarD * nsys;
+    dl = dstate + (size_t)scalar_d<POL>() * nsys;
     db = dl + (size_t)POL::kLaneSlots * nsys * 32;
     il = istore + (size_t)kScalarI * nsys;
     nblock = 0;
@@ -249,6 +250,8 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
         e.lin.ld = POL::band_ld(ml, mu);
         e.lin.abd = smem + (size_t)warp * nblock;
         e.lin.wjs = e.lin.abd + e.lin.ld * POL::N;
+    } else if constexpr (POL::kPlain) {
+        (void)ml; (void)mu; (void)smem; (void)warp; (void)sys; (void)ln;
     } else {
         nblock = POL::N * POL::LDP;
         e.lin.p = smem + (size_t)warp * nblock;
@@ -420,34 +423,66 @@ static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-// ---- thread-per-system problems: mf = +-21, +-22 (dense chord iteration, BDF) ----------
-template <class PROB>
-static int thread_dispatch(int mf, const KArgs &a, cudaStream_t st) {
-    switch (mf) {
-    case 21: return launch_thread<ThreadPolicy<PROB, 1, true>>(a, st);
-    case 22: return launch_thread<ThreadPolicy<PROB, 2, true>>(a, st);
-    case -21: return launch_thread<ThreadPolicy<PROB, 1, false>>(a, st);
-    case -22: return launch_thread<ThreadPolicy<PROB, 2, false>>(a, st);
+// ------------------------------------------------------------------ dispatch ------
+// mf = jsv * (10*meth + miter), M:999-1046.  jsv only matters where a Jacobian is stored
+// (miter 1, 2, 4, 5).
+struct MfParts {
+    int meth, miter;
+    bool savej;
+};
+static inline MfParts mf_parts(int mf) {
+    const int a = mf < 0 ? -mf : mf;
+    MfParts p;
+    p.meth = a / 10;
+    p.miter = a - 10 * p.meth;
+    p.savej = (mf > 0) && (p.miter == 1 || p.miter == 2 || p.miter == 4 || p.miter == 5);
+    return p;
+}
+
+// ---- thread-per-system problems: meth 1, 2; miter 0 (functional), 1, 2 (dense), 3 (diagonal)
+template <class PROB, int METH>
+static int thread_dispatch_m(const MfParts &m, const KArgs &a, cudaStream_t st) {
+    switch (m.miter) {
+    case 0: return launch_thread<ThreadPolicy<PROB, 0, false, METH>>(a, st);
+    case 1: return m.savej ? launch_thread<ThreadPolicy<PROB, 1, true, METH>>(a, st)
+                           : launch_thread<ThreadPolicy<PROB, 1, false, METH>>(a, st);
+    case 2: return m.savej ? launch_thread<ThreadPolicy<PROB, 2, true, METH>>(a, st)
+                           : launch_thread<ThreadPolicy<PROB, 2, false, METH>>(a, st);
+    case 3: return launch_thread<ThreadPolicy<PROB, 3, false, METH>>(a, st);
     default: return -1000;
     }
 }
 template <class PROB>
+static int thread_dispatch(int mf, const KArgs &a, cudaStream_t st) {
+    const MfParts m = mf_parts(mf);
+    if (m.meth == 1) return thread_dispatch_m<PROB, 1>(m, a, st);
+    if (m.meth == 2) return thread_dispatch_m<PROB, 2>(m, a, st);
+    return -1000;
+}
+template <class PROB>
 static int thread_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
-    // the state layout depends on SAVEJ only through the Lin block; MITER does not matter
-    if (mf > 0) return launch_dky_thread<ThreadPolicy<PROB, 1, true>>(a, st);
-    return launch_dky_thread<ThreadPolicy<PROB, 1, false>>(a, st);
+    // the state layout depends on meth (lmax) and on SAVEJ through the Lin block only
+    const MfParts m = mf_parts(mf);
+    if (m.meth == 1)
+        return m.savej ? launch_dky_thread<ThreadPolicy<PROB, 1, true, 1>>(a, st)
+                       : launch_dky_thread<ThreadPolicy<PROB, 1, false, 1>>(a, st);
+    return m.savej ? launch_dky_thread<ThreadPolicy<PROB, 1, true, 2>>(a, st)
+                   : launch_dky_thread<ThreadPolicy<PROB, 1, false, 2>>(a, st);
 }
 template <class PROB>
 static void thread_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
     (void)ml; (void)mu;
     constexpr int N = PROB::N;
-    *nd = nsys * (size_t)(kLmax * N + 2 * N + N * N + (mf > 0 ? N * N : 0) + kLmax + 11);
+    const MfParts m = mf_parts(mf);
+    const int lm = kLmaxOf(m.meth);
+    *nd = nsys * (size_t)(lm * N + 2 * N + N * N + (m.savej ? N * N : 0) + lm + 11);
     *ni = nsys * (size_t)(N + 19);
 }
 template <class PROB>
 static int thread_supports(int mf, int ml, int mu) {
     (void)ml; (void)mu;
-    return mf == 21 || mf == 22 || mf == -21 || mf == -22;
+    const MfParts m = mf_parts(mf);
+    return (m.meth == 1 || m.meth == 2) && m.miter >= 0 && m.miter <= 3;
 }
 #define BVODE_THREAD_PROBLEM(NAME, PROB)                                                    \
     ProblemEntry {                                                                          \
@@ -455,67 +490,91 @@ static int thread_supports(int mf, int ml, int mu) {
             thread_dispatch<PROB>, thread_dky_dispatch<PROB>                                \
     }
 
-// ---- warp-per-system, dense FD Jacobian: mf = +-22 ----------------------------------------
-template <class PROB>
-static int wdense_dispatch(int mf, const KArgs &a, cudaStream_t st) {
-    switch (mf) {
-    case 22: return launch_warp<WarpDensePolicy<PROB, 2, true>>(a, st);
-    case -22: return launch_warp<WarpDensePolicy<PROB, 2, false>>(a, st);
+// ---- warp-per-system problems ---------------------------------------------------------------
+// KIND 1: dense finite-difference Jacobian available (miter 2); KIND 2: banded (miter 4, 5).
+// Both kinds also run miter 0 (functional iteration) and 3 (diagonal approximation).
+template <class PROB, int KIND, int METH>
+static int warp_dispatch_m(const MfParts &m, const KArgs &a, cudaStream_t st) {
+    switch (m.miter) {
+    case 0: return launch_warp<WarpPlainPolicy<PROB, 0, METH>>(a, st);
+    case 3: return launch_warp<WarpPlainPolicy<PROB, 3, METH>>(a, st);
+    case 2:
+        if constexpr (KIND == 1)
+            return m.savej ? launch_warp<WarpDensePolicy<PROB, 2, true, METH>>(a, st)
+                           : launch_warp<WarpDensePolicy<PROB, 2, false, METH>>(a, st);
+        return -1000;
+    case 4:
+        if constexpr (KIND == 2)
+            return m.savej ? launch_warp<WarpBandPolicy<PROB, 4, true, METH>>(a, st)
+                           : launch_warp<WarpBandPolicy<PROB, 4, false, METH>>(a, st);
+        return -1000;
+    case 5:
+        if constexpr (KIND == 2)
+            return m.savej ? launch_warp<WarpBandPolicy<PROB, 5, true, METH>>(a, st)
+                           : launch_warp<WarpBandPolicy<PROB, 5, false, METH>>(a, st);
+        return -1000;
     default: return -1000;
     }
 }
-template <class PROB>
-static int wdense_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
-    if (mf > 0) return launch_dky_warp<WarpDensePolicy<PROB, 2, true>>(a, st);
-    return launch_dky_warp<WarpDensePolicy<PROB, 2, false>>(a, st);
+template <class PROB, int KIND>
+static int warp_dispatch(int mf, const KArgs &a, cudaStream_t st) {
+    const MfParts m = mf_parts(mf);
+    if (m.meth == 1) return warp_dispatch_m<PROB, KIND, 1>(m, a, st);
+    if (m.meth == 2) return warp_dispatch_m<PROB, KIND, 2>(m, a, st);
+    return -1000;
 }
-template <class PROB>
-static void wdense_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
-    if (mf > 0) WarpLayout<WarpDensePolicy<PROB, 2, true>>::sizes(ml, mu, nsys, nd, ni);
-    else WarpLayout<WarpDensePolicy<PROB, 2, false>>::sizes(ml, mu, nsys, nd, ni);
+// F is a generic functor called with a policy tag whose state layout matches this mf
+template <class PROB, int KIND, int METH, class F>
+static int warp_layout_m(const MfParts &m, F &&fn) {
+    if (m.miter == 0 || m.miter == 3) return fn(WarpPlainPolicy<PROB, 0, METH>{});
+    if constexpr (KIND == 1) {
+        if (m.miter == 2)
+            return m.savej ? fn(WarpDensePolicy<PROB, 2, true, METH>{})
+                           : fn(WarpDensePolicy<PROB, 2, false, METH>{});
+    } else {
+        if (m.miter == 4 || m.miter == 5)
+            return m.savej ? fn(WarpBandPolicy<PROB, 4, true, METH>{})
+                           : fn(WarpBandPolicy<PROB, 4, false, METH>{});
+    }
+    return -1000;
 }
-template <class PROB>
-static int wdense_supports(int mf, int ml, int mu) {
-    (void)ml; (void)mu;
-    return mf == 22 || mf == -22;
+template <class PROB, int KIND, class F>
+static int warp_layout(int mf, F &&fn) {
+    const MfParts m = mf_parts(mf);
+    if (m.meth == 1) return warp_layout_m<PROB, KIND, 1>(m, fn);
+    if (m.meth == 2) return warp_layout_m<PROB, KIND, 2>(m, fn);
+    return -1000;
+}
+template <class PROB, int KIND>
+static int warp_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
+    return warp_layout<PROB, KIND>(mf, [&](auto pol) { return launch_dky_warp<decltype(pol)>(a, st); });
+}
+template <class PROB, int KIND>
+static void warp_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+    *nd = *ni = 0;
+    warp_layout<PROB, KIND>(mf, [&](auto pol) {
+        WarpLayout<decltype(pol)>::sizes(ml, mu, nsys, nd, ni);
+        return 0;
+    });
+}
+template <class PROB, int KIND>
+static int warp_supports(int mf, int ml, int mu) {
+    const MfParts m = mf_parts(mf);
+    if (m.meth != 1 && m.meth != 2) return 0;
+    if (m.miter == 0 || m.miter == 3) return 1;
+    if (KIND == 1) return m.miter == 2;
+    return (m.miter == 4 || m.miter == 5) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 &&
+           ml < PROB::N && mu < PROB::N;
 }
 #define BVODE_WARP_DENSE_FD_PROBLEM(NAME, PROB)                                             \
     ProblemEntry {                                                                          \
-        NAME, PROB::N, PROB::NPAR, 1, wdense_supports<PROB>, wdense_state_size<PROB>,       \
-            wdense_dispatch<PROB>, wdense_dky_dispatch<PROB>                                \
+        NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 1>, warp_state_size<PROB, 1>,     \
+            warp_dispatch<PROB, 1>, warp_dky_dispatch<PROB, 1>                              \
     }
-
-// ---- warp-per-system, banded: mf = +-24, +-25 ----------------------------------------------
-template <class PROB>
-static int wband_dispatch(int mf, const KArgs &a, cudaStream_t st) {
-    switch (mf) {
-    case 24: return launch_warp<WarpBandPolicy<PROB, 4, true>>(a, st);
-    case 25: return launch_warp<WarpBandPolicy<PROB, 5, true>>(a, st);
-    case -24: return launch_warp<WarpBandPolicy<PROB, 4, false>>(a, st);
-    case -25: return launch_warp<WarpBandPolicy<PROB, 5, false>>(a, st);
-    default: return -1000;
-    }
-}
-template <class PROB>
-static int wband_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
-    if (mf > 0) return launch_dky_warp<WarpBandPolicy<PROB, 4, true>>(a, st);
-    return launch_dky_warp<WarpBandPolicy<PROB, 4, false>>(a, st);
-}
-template <class PROB>
-static void wband_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
-    if (mf > 0) WarpLayout<WarpBandPolicy<PROB, 4, true>>::sizes(ml, mu, nsys, nd, ni);
-    else WarpLayout<WarpBandPolicy<PROB, 4, false>>::sizes(ml, mu, nsys, nd, ni);
-}
-template <class PROB>
-static int wband_supports(int mf, int ml, int mu) {
-    const int a = mf < 0 ? -mf : mf;
-    return (a == 24 || a == 25) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 && ml < PROB::N &&
-           mu < PROB::N;
-}
 #define BVODE_WARP_BAND_PROBLEM(NAME, PROB)                                                 \
     ProblemEntry {                                                                          \
-        NAME, PROB::N, PROB::NPAR, 1, wband_supports<PROB>, wband_state_size<PROB>,         \
-            wband_dispatch<PROB>, wband_dky_dispatch<PROB>                                  \
+        NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 2>, warp_state_size<PROB, 2>,     \
+            warp_dispatch<PROB, 2>, warp_dky_dispatch<PROB, 2>                              \
     }
 
 }  // namespace BVODE_NS

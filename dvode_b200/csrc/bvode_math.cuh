@@ -43,7 +43,7 @@ BV_DEV double powi(double x, int m) {
 
 // Portable x**y, x > 0: same operation sequence as dvo_ppow in oracle/dvode_oracle.c.
 // Only meaningful bit for bit when compiled with -fmad=false.
-__device__ __noinline__ double ppow(double x, double y) {
+static __device__ __noinline__ double ppow(double x, double y) {
     if (x == 0.0) return 0.0;
     if (x == 1.0 || y == 0.0) return 1.0;
     uint64_t u = (uint64_t)__double_as_longlong(x);

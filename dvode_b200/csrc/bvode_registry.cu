@@ -1,22 +1,31 @@
-// bvode_registry.cu -- instantiates every kernel of one build and exports its problem table.
-// Compiled twice: -DBVODE_STRICT=0 (fast, the product) and -DBVODE_STRICT=1 -fmad=false.
+// bvode_registry.cu -- instantiates every kernel of ONE problem for one build and exports its
+// table entry.  Compiled once per (build, problem): -DBVODE_STRICT=0 (fast, the product) or
+// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..3.
 #include "bvode_kernels.cuh"
 
+#ifndef BVODE_UNIT
+#error "compile with -DBVODE_UNIT=<problem index>"
+#endif
+
 namespace BVODE_NS {
-static const ProblemEntry kEntries[] = {
-    BVODE_THREAD_PROBLEM("robertson", Robertson),
-    BVODE_THREAD_PROBLEM("vdp", VanDerPol),
-    BVODE_WARP_BAND_PROBLEM("advection", Advection25),
-    BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32),
-};
+#if BVODE_UNIT == 0
+static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("robertson", Robertson);
+#elif BVODE_UNIT == 1
+static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp", VanDerPol);
+#elif BVODE_UNIT == 2
+static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection", Advection25);
+#elif BVODE_UNIT == 3
+static const ProblemEntry kEntry = BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32);
+#endif
 }  // namespace BVODE_NS
 
+#define BV_CAT2(a, b) a##b
+#define BV_CAT(a, b) BV_CAT2(a, b)
 #if BVODE_STRICT
-extern "C" const ProblemEntry *bvode_registry_strict(int *n)
+extern "C" const ProblemEntry *BV_CAT(bvode_entry_strict_, BVODE_UNIT)(void)
 #else
-extern "C" const ProblemEntry *bvode_registry_fast(int *n)
+extern "C" const ProblemEntry *BV_CAT(bvode_entry_fast_, BVODE_UNIT)(void)
 #endif
 {
-    *n = (int)(sizeof(BVODE_NS::kEntries) / sizeof(BVODE_NS::kEntries[0]));
-    return BVODE_NS::kEntries;
+    return &BVODE_NS::kEntry;
 }

@@ -16,14 +16,18 @@
 
 namespace BVODE_NS {
 
-template <class PROB, int MITER_, bool SAVEJ_>
+template <class PROB, int MITER_, bool SAVEJ_, int METH_ = 2>
 struct ThreadPolicy {
     using Prob = PROB;
     static constexpr int N = PROB::N;
     static constexpr int NLOC = N;
-    static constexpr int MITER = MITER_;     // 1 analytic dense J, 2 finite-difference dense J
-    static constexpr bool SAVEJ = SAVEJ_;    // jsv = +1 (mf > 0): keep a copy of J
-    static_assert(MITER == 1 || MITER == 2, "thread-per-system policy is dense only");
+    static constexpr int MITER = MITER_;     // 0 functional iteration, 1 analytic dense J,
+                                             // 2 finite-difference dense J, 3 diagonal approximation
+    static constexpr int METH = METH_;       // 1 Adams, 2 BDF
+    static constexpr bool SAVEJ = SAVEJ_;    // jsv = +1 (mf > 0): keep a copy of J (miter 1, 2)
+    static constexpr int kLmax = kLmaxOf(METH);
+    static_assert(MITER >= 0 && MITER <= 3, "thread-per-system policy: miter 0..3");
+    static_assert(N >= 2, "miter = 3 keeps wm(2) and the diagonal in the N x N matrix slots");
 
     // Cold per-system data stays in its HBM state slot instead of registers: it is touched
     // once per Jacobian / LU (every ~5-50 steps), and a warp's access is one coalesced line.
@@ -277,22 +281,86 @@ struct ThreadPolicy {
 #undef a_
     }
 
+    // dvsol, M:3139-3191 (returns iersl)
     template <class ENG>
-    BV_DEV static void solve(ENG &e, double (&x)[N]) {
-        double a[N][N];
-        int ipvt[N];
+    BV_DEV static int solve(ENG &e, double (&x)[N]) {
+        if constexpr (MITER == 3) {
+            // diagonal approximation, M:3164-3181: wm(2) = hrl1 of the last update is
+            // hot.p(1, 0), the inverted diagonal wm(3:) is hot.p(0, i)
+            const double phrl1 = e.hot.p(1, 0);
+            const double hrl1 = e.c.h * e.c.rl1;
+            e.hot.p(1, 0) = hrl1;
+            int iersl = 0;
+            if (hrl1 != phrl1) {
+                const double r = hrl1 / phrl1;
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    if (iersl == 0) {
+                        const double di = 1.0 - r * (1.0 - 1.0 / e.hot.p(0, i));
+                        if (fabs(di) == 0.0) iersl = 1;
+                        else e.hot.p(0, i) = 1.0 / di;
+                    }
+                }
+            }
+            if (iersl == 0) {
+#pragma unroll
+                for (int i = 0; i < N; i++) x[i] = e.hot.p(0, i) * x[i];
+            }
+            return iersl;
+        } else {
+            double a[N][N];
+            int ipvt[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+#pragma unroll
+                for (int j = 0; j < N; j++) a[i][j] = e.hot.p(i, j);
+                ipvt[i] = e.hot.ipvt(i);
+            }
+            dgesl(a, ipvt, x);
+            return 0;
+        }
+    }
+
+    // ---- dvjac, miter = 3 (M:3004-3028) ------------------------------------------------
+    template <class ENG>
+    BV_DEV static void jac_setup_diag(ENG &e, int &ierpj) {
+        Ctl &c = e.c;
+        ierpj = 0;
+        const double hrl1 = c.h * c.rl1;
+        // M:3004-3028: diagonal Jacobian approximation from one extra f evaluation
+        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        c.jcur = 1;
+        e.hot.p(1, 0) = hrl1;  // wm(2)
+        const double r = c.rl1 * 0.1;
+#pragma unroll
+        for (int i = 0; i < N; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
+        double w[N];
+        f(c.tn, e.y, w, e.par);
+        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
 #pragma unroll
         for (int i = 0; i < N; i++) {
-#pragma unroll
-            for (int j = 0; j < N; j++) a[i][j] = e.hot.p(i, j);
-            ipvt[i] = e.hot.ipvt(i);
+            if (ierpj == 0) {
+                const double r0 = c.h * e.savf[i] - e.hot.yh(1, i);
+                const double di = 0.1 * r0 - c.h * (w[i] - e.savf[i]);
+                double wi = 1.0;
+                if (fabs(r0) >= kUround / e.ewt[i]) {
+                    if (fabs(di) == 0.0) ierpj = 1;
+                    else wi = 0.1 * r0 / di;
+                }
+                if (ierpj == 0) e.hot.p(0, i) = wi;
+            }
         }
-        dgesl(a, ipvt, x);
+    }
+
+    template <class ENG>
+    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+        if constexpr (MITER == 3) jac_setup_diag(e, ierpj);
+        else jac_setup_dense(e, ierpj);
     }
 
     // ---- dvjac, miter 1 / 2 (M:2930-3001) -------------------------------------------
     template <class ENG>
-    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+    BV_DEV static void jac_setup_dense(ENG &e, int &ierpj) {
         Ctl &c = e.c;
         Lin &l = e.lin;
         ierpj = 0;

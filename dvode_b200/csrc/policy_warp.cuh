@@ -25,9 +25,11 @@ BV_DEV double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 BV_DEV double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
 // Common pieces of the two warp policies.
-template <class PROB>
+template <class PROB, int METH_>
 struct WarpCommon {
     static constexpr int N = PROB::N;
+    static constexpr int METH = METH_;  // 1 Adams, 2 BDF
+    static constexpr int kLmax = kLmaxOf(METH);
     static_assert(N <= 32, "warp-per-system policy holds one component per lane");
     static constexpr int NLOC = 1;
     typedef double Par[PROB::NPAR_LANE > 0 ? PROB::NPAR_LANE : 1];
@@ -148,9 +150,11 @@ struct WarpCommon {
 // columns are run-time loops: the first version kept each row in registers with fully
 // unrolled loops (~20k instructions) and was bound by instruction fetch (ncu: 33 cycles of
 // no-instruction stall per issued instruction, profiles/r01_ncu_warp_dense_mech32_v1.txt).
-template <class PROB, int MITER_, bool SAVEJ_>
-struct WarpDensePolicy : WarpCommon<PROB> {
-    using Base = WarpCommon<PROB>;
+template <class PROB, int MITER_, bool SAVEJ_, int METH_ = 2>
+struct WarpDensePolicy : WarpCommon<PROB, METH_> {
+    using Base = WarpCommon<PROB, METH_>;
+    static constexpr int METH = METH_;
+    static constexpr int kLmax = Base::kLmax;
     using Prob = PROB;
     using typename Base::GlobalVec;
     using typename Base::Hot;
@@ -160,6 +164,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     static constexpr int MITER = MITER_;
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
+    static constexpr bool kPlain = false;
     static constexpr int LDP = N | 1;
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
@@ -240,7 +245,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------------
     template <class ENG>
-    BV_DEV static void solve(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve(ENG &e, double (&x)[1]) {
         const Lin &lin = e.lin;
         const int ln = lane();
         const double *row = lin.p + ln * LDP;
@@ -267,6 +272,7 @@ struct WarpDensePolicy : WarpCommon<PROB> {
             if (ln < k) b = b + t * row[k];
         }
         x[0] = b;
+        return 0;
     }
 
     // ---- dvjac, miter 1 / 2 (M:2930-3001) ---------------------------------------------------
@@ -335,15 +341,99 @@ struct WarpDensePolicy : WarpCommon<PROB> {
     }
 };
 
+// =========================================================================== plain ====
+// No Newton matrix: functional iteration (miter = 0, M:2822-2837) or the diagonal Jacobian
+// approximation (miter = 3: dvjac M:3004-3028, dvsol M:3164-3181), one diagonal entry per lane.
+template <class PROB, int MITER_, int METH_ = 2>
+struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
+    using Base = WarpCommon<PROB, METH_>;
+    using Prob = PROB;
+    using Base::lane;
+    static constexpr int N = PROB::N;
+    static constexpr int NLOC = 1;
+    static constexpr int MITER = MITER_;
+    static constexpr int METH = METH_;
+    static constexpr int kLmax = Base::kLmax;
+    static constexpr bool SAVEJ = false;
+    static constexpr bool kBand = false;
+    static constexpr bool kPlain = true;
+    static_assert(MITER == 0 || MITER == 3, "plain policy");
+
+    struct Lin {
+        double diag;   // wm(2 + lane): inverted diagonal of P (miter = 3)
+        double phrl1;  // wm(2): h*rl1 at the last update (replicated on all lanes)
+    };
+    template <class ENG>
+    BV_DEV static void lin_init(ENG &e) { e.lin.diag = 1.0; e.lin.phrl1 = 0.0; }
+    static int smem_doubles(int, int, bool) { return 0; }
+    static constexpr int kLaneSlots = kLmax + 2 + 2;  // yh, acsav, acor, diag, phrl1
+    static constexpr int kLaneIntSlots = 1;
+    template <class V>
+    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class ENG, class V>
+    BV_DEV static void visit_lin(ENG &e, V &v) {
+        v.dv(e.lin.diag);
+        v.dv(e.lin.phrl1);
+        int dummy = 0;
+        v.iv(dummy);
+    }
+
+    template <class ENG>
+    BV_DEV static int solve(ENG &e, double (&x)[1]) {
+        Lin &l = e.lin;
+        const double hrl1 = e.c.h * e.c.rl1;
+        const double phrl1 = l.phrl1;
+        l.phrl1 = hrl1;
+        if (hrl1 != phrl1) {
+            const double r = hrl1 / phrl1;
+            const double di = 1.0 - r * (1.0 - 1.0 / l.diag);
+            const bool zero = (lane() < N) && (fabs(di) == 0.0);
+            // the reference stops at the first zero: entries before it are already updated
+            const unsigned zmask = __ballot_sync(kFull, zero);
+            const int first = zmask ? (__ffs((int)zmask) - 1) : 32;
+            if (lane() < first) l.diag = 1.0 / di;
+            if (zmask) return 1;
+        }
+        x[0] = l.diag * x[0];
+        return 0;
+    }
+
+    template <class ENG>
+    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+        Ctl &c = e.c;
+        Lin &l = e.lin;
+        ierpj = 0;
+        const double hrl1 = c.h * c.rl1;
+        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        c.jcur = 1;
+        l.phrl1 = hrl1;
+        const double r = c.rl1 * 0.1;
+        e.y[0] = e.y[0] + r * (c.h * e.savf[0] - e.hot.yh(1, 0));
+        double w[1];
+        Base::f(c.tn, e.y, w, e.par);
+        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
+        const double r0 = c.h * e.savf[0] - e.hot.yh(1, 0);
+        const double di = 0.1 * r0 - c.h * (w[0] - e.savf[0]);
+        const bool big = (lane() < N) && (fabs(r0) >= kUround / e.ewt[0]);
+        const bool zero = big && (fabs(di) == 0.0);
+        const unsigned zmask = __ballot_sync(kFull, zero);
+        const int first = zmask ? (__ffs((int)zmask) - 1) : 32;
+        if (lane() < first) l.diag = big ? 0.1 * r0 / di : 1.0;
+        if (zmask) ierpj = 1;
+    }
+};
+
 // ============================================================================ band ====
 // LINPACK band storage (LP:230-260) in shared memory: abd(i, j), i = 1..meband, j = 1..n at
 // abd[(j-1)*ld + (i-1)], meband = 2*ml + mu + 1, ld odd (bank-conflict-free column stride).
 // The saved Jacobian is the compact mband x n copy (M:3048, dacopy) in shared memory too.
 constexpr int kBandMaxRows = 2 * 12 + 12 + 1;  // sized at launch from ml, mu
 
-template <class PROB, int MITER_, bool SAVEJ_>
-struct WarpBandPolicy : WarpCommon<PROB> {
-    using Base = WarpCommon<PROB>;
+template <class PROB, int MITER_, bool SAVEJ_, int METH_ = 2>
+struct WarpBandPolicy : WarpCommon<PROB, METH_> {
+    using Base = WarpCommon<PROB, METH_>;
+    static constexpr int METH = METH_;
+    static constexpr int kLmax = Base::kLmax;
     using Prob = PROB;
     using Base::lane;
     static constexpr int N = PROB::N;
@@ -351,6 +441,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
     static constexpr int MITER = MITER_;
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = true;
+    static constexpr bool kPlain = false;
     static_assert(MITER == 4 || MITER == 5, "band policy");
 
     struct Lin {
@@ -457,7 +548,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
 
     // ---- dgbsl job = 0, LP:494-519: b_i in lane i-1 ------------------------------------------
     template <class ENG>
-    BV_DEV static void solve(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve(ENG &e, double (&x)[1]) {
         const Lin &l = e.lin;
         const int ln = lane();
         const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
@@ -491,6 +582,7 @@ struct WarpBandPolicy : WarpCommon<PROB> {
             if (i >= 0 && i < lm) b = b + t * ABD(la + i, k);
         }
         x[0] = b;
+        return 0;
     }
 
     // ---- dvjac, miter 4 / 5 (M:3031-3104) --------------------------------------------------

@@ -32,8 +32,13 @@
 
 namespace BVODE_NS {
 
-constexpr int kMaxOrdBdf = 5;       // mord(2), M:38
-constexpr int kLmax = kMaxOrdBdf + 1;
+// mord = [12, 5] (M:38): maximum order of the Adams (meth = 1) and BDF (meth = 2) families.
+// Every array that the reference dimensions by maxord is sized at compile time from the
+// method: lmax = 13 (Adams) or 6 (BDF).
+constexpr int kMaxOrdBdf = 5;
+__host__ __device__ constexpr int kMaxOrdOf(int meth) { return meth == 1 ? 12 : 5; }
+__host__ __device__ constexpr int kLmaxOf(int meth) { return kMaxOrdOf(meth) + 1; }
+constexpr int kLmaxBdf = kMaxOrdBdf + 1;
 
 // istate / error codes written per system (same integers as the reference, M:832-908)
 enum : int {
@@ -83,14 +88,14 @@ template <class HOT>
 BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const int nq = c.nq, L = c.L;
     const double h = c.h;
-    double el[kLmax + 1], tq[6];
+    double el[kLmaxBdf + 1], tq[6];
 #pragma unroll
-    for (int i = 3; i <= kLmax; i++) el[i] = 0.0;
+    for (int i = 3; i <= kLmaxBdf; i++) el[i] = 0.0;
     el[1] = 1.0;
     el[2] = 1.0;
-    double tauv[kLmax + 1];
+    double tauv[kLmaxBdf + 1];
 #pragma unroll
-    for (int i = 1; i <= kLmax; i++) tauv[i] = hot.tau(i);
+    for (int i = 1; i <= kLmaxBdf; i++) tauv[i] = hot.tau(i);
     double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
     if (nq != 1) {
 #pragma unroll
@@ -112,13 +117,13 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
         rxi = qdiv(h, hsum);
         ahatn0 = -el[2] - rxi;
 #pragma unroll
-        for (int i = kLmax; i >= 2; i--) {
+        for (int i = kLmaxBdf; i >= 2; i--) {
             if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
         }
     }
     const double t1 = 1.0 - ahatn0 + alph0;
     const double t2 = 1.0 + (double)nq * t1;
-    const double elL = pick<2, kLmax>(el, L);
+    const double elL = pick<2, kLmaxBdf>(el, L);
     tq[2] = fabs(qdiv(alph0 * t2, t1));
     tq[5] = fabs(qdiv(t2, qdiv(elL * rxi, rxis)));
     tq[1] = 0.0;
@@ -129,7 +134,7 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
         const double t4 = ahatn0 + rxi;
         double elp = qdiv(t3, 1.0 - t4 + t3);
         tq[1] = fabs(qdiv(elp, cnqm1));
-        hsum = hsum + pick<1, kLmax>(tauv, nq);
+        hsum = hsum + pick<1, kLmaxBdf>(tauv, nq);
         rxi = qdiv(h, hsum);
         const double t5 = alph0 - recip_int(nq + 1);
         const double t6 = ahatn0 - rxi;
@@ -138,7 +143,7 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     }
     tq[4] = 0.1 * tq[2];
 #pragma unroll
-    for (int i = 1; i <= kLmax; i++) hot.el(i) = el[i];
+    for (int i = 1; i <= kLmaxBdf; i++) hot.el(i) = el[i];
     // tq(1), tq(3) are only read by the order selection of the step whose dvset ran with
     // nqwait == 1 (M:2272-2292), so they need no storage otherwise
     hot.tq(2) = tq[2];
@@ -157,17 +162,17 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
 // el is returned in a local array (the reference leaves it in el(:), which dvset overwrites
 // before its next use).  Returns t1 = (-alph0 - alph1)/prod for the order increase.
 template <class HOT>
-BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up, double (&el)[kLmax + 1]) {
+BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf + 1]) {
     const int nq = c.nq;
 #pragma unroll
-    for (int j = 0; j <= kLmax; j++) el[j] = 0.0;
+    for (int j = 0; j <= kLmaxBdf; j++) el[j] = 0.0;
     el[3] = 1.0;
     double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
     double hsum = up ? c.hscal : 0.0;
     const int jmax = up ? nq - 1 : nq - 2;
-    double tauv[kLmax + 1];
+    double tauv[kLmaxBdf + 1];
 #pragma unroll
-    for (int i = 1; i <= kLmax; i++) tauv[i] = hot.tau(i);
+    for (int i = 1; i <= kLmaxBdf; i++) tauv[i] = hot.tau(i);
 #pragma unroll
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
         if (j <= jmax) {
@@ -190,6 +195,111 @@ BV_DEV double dvjust_coeffs(Ctl &c, HOT &hot, bool up, double (&el)[kLmax + 1]) 
     return qdiv(-alph0 - alph1, prod);
 }
 
+// ---------------------------------------------------------------- dvset (Adams) ----
+// M:2492-2558.  Run-time loops over the order (up to 12): the Adams family is a coverage
+// path, not the tuned one, so el / em live in local arrays indexed at run time.
+template <class HOT>
+BV_DEV void dvset_adams(Ctl &c, HOT &hot) {
+    constexpr int LM = kLmaxOf(1);
+    const int nq = c.nq, L = c.L, nqm1 = nq - 1;
+    const double h = c.h;
+    double el[LM + 1], em[LM + 2], tq[6], tauv[LM + 1];
+    for (int i = 1; i <= LM; i++) { tauv[i] = hot.tau(i); el[i] = 0.0; }  // el above L: zero (see accept update)
+    tq[1] = 0.0; tq[2] = 0.0; tq[3] = 0.0; tq[5] = 0.0;
+    const double flotl = (double)L;
+    if (nq != 1) {
+        double hsum = h;
+        em[1] = 1.0;
+        const double flotnq = flotl - 1.0;
+        for (int i = 2; i <= L; i++) em[i] = 0.0;
+        for (int j = 1; j <= nqm1; j++) {
+            if ((j == nqm1) && (c.nqwait == 1)) {
+                double s = 1.0, csum = 0.0;
+                for (int i = 1; i <= nqm1; i++) {
+                    csum = csum + s * em[i] / (double)(i + 1);
+                    s = -s;
+                }
+                tq[1] = em[nqm1] / (flotnq * csum);
+            }
+            const double rxi = h / hsum;
+            for (int iback = 1; iback <= j; iback++) {
+                const int i = (j + 2) - iback;
+                em[i] = em[i] + em[i - 1] * rxi;
+            }
+            hsum = hsum + tauv[j];
+        }
+        double s = 1.0, em0 = 0.0, csum = 0.0;
+        for (int i = 1; i <= nq; i++) {
+            const double floti = (double)i;
+            em0 = em0 + s * em[i] / floti;
+            csum = csum + s * em[i] / (floti + 1.0);
+            s = -s;
+        }
+        s = 1.0 / em0;
+        el[1] = 1.0;
+        for (int i = 1; i <= nq; i++) el[i + 1] = s * em[i] / (double)i;
+        const double xi = hsum / h;
+        tq[2] = xi * em0 / csum;
+        tq[5] = xi / el[L];
+        if (c.nqwait == 1) {
+            const double rxi = 1.0 / xi;
+            for (int iback = 1; iback <= nq; iback++) {
+                const int i = (L + 1) - iback;
+                em[i] = em[i] + em[i - 1] * rxi;
+            }
+            s = 1.0;
+            csum = 0.0;
+            for (int i = 1; i <= L; i++) {
+                csum = csum + s * em[i] / (double)(i + 1);
+                s = -s;
+            }
+            tq[3] = flotl * em0 / csum;
+        }
+    } else {
+        el[1] = 1.0;
+        el[2] = 1.0;
+        tq[1] = 1.0;
+        tq[2] = 2.0;
+        tq[3] = 6.0 * tq[2];
+        tq[5] = 1.0;
+    }
+    tq[4] = 0.1 * tq[2];
+    for (int i = 1; i <= LM; i++) hot.el(i) = el[i];
+    hot.tq(2) = tq[2];
+    hot.tq(4) = tq[4];
+    hot.tq(5) = tq[5];
+    if (c.nqwait == 1 || nq == 1) {
+        hot.tq(1) = tq[1];
+        hot.tq(3) = tq[3];
+    }
+}
+
+// dvjust, Adams order decrease (M:2669-2692): el(3:nq) such that yh(:,j) -= yh(:,L)*el(j).
+// (The Adams order increase only zeroes the new column, M:2661-2666.)
+template <class HOT>
+BV_DEV void dvjust_coeffs_adams_down(Ctl &c, HOT &hot, double (&el)[kLmaxOf(1) + 1]) {
+    constexpr int LM = kLmaxOf(1);
+    const int nq = c.nq;
+    for (int j = 0; j <= LM; j++) el[j] = 0.0;
+    el[2] = 1.0;
+    double hsum = 0.0;
+    for (int j = 1; j <= nq - 2; j++) {
+        hsum = hsum + hot.tau(j);
+        const double xi = hsum / c.hscal;
+        for (int iback = 1; iback <= j + 1; iback++) {
+            const int i = (j + 3) - iback;
+            el[i] = el[i] * xi + el[i - 1];
+        }
+    }
+    for (int j = 2; j <= nq - 1; j++) el[j + 1] = (double)nq * el[j] / (double)j;
+}
+
+template <int METH, class HOT>
+BV_DEV void dvset(Ctl &c, HOT &hot) {
+    if constexpr (METH == 2) dvset_bdf(c, hot);
+    else dvset_adams(c, hot);
+}
+
 #if !BVODE_STRICT
 // Which step-ratio candidate wins (M:2294-2317), from log-ratios l = log2(x)/k (smaller l =
 // larger eta): 0 = current order, 1 = order - 1, 2 = order + 1.
@@ -200,7 +310,7 @@ BV_DEV int choose_ratio(T lq, T lm, T lp) {
 }
 // The same decision from double-precision logs: the rare case where the single-precision
 // screen is too close to call.  Out of line to keep the step loop small.
-__device__ __noinline__ int choose_ratio_f64(double xq, double xm, double xp, double scq, double scm,
+static __device__ __noinline__ int choose_ratio_f64(double xq, double xm, double xp, double scq, double scm,
                                              double scp, bool has_m, bool has_p) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double lq = log2_fast(xq) * scq;
@@ -235,7 +345,10 @@ struct Engine {
     using Prob = typename POL::Prob;
     static constexpr int N = POL::N;
     static constexpr int NLOC = POL::NLOC;
-    static constexpr int MITER = POL::MITER;
+    static constexpr int MITER = POL::MITER;   // 0 functional, 1/2 dense, 3 diagonal, 4/5 banded
+    static constexpr int METH = POL::METH;     // 1 Adams, 2 BDF
+    static constexpr int kMaxOrd = kMaxOrdOf(METH);
+    static constexpr int kLmax = kLmaxOf(METH);
 
     Ctl c;
     typename POL::Hot hot;   // yh(j,i): Nordsieck history, column j = h^j y^(j)/j!; tau(1:6);
@@ -275,9 +388,9 @@ struct Engine {
 
     BV_DEV void predict() {  // M:2148-2154 at full order (zero-column invariant)
 #pragma unroll
-        for (int jb = 1; jb <= kMaxOrdBdf; jb++) {
+        for (int jb = 1; jb <= kMaxOrd; jb++) {
 #pragma unroll
-            for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
+            for (int j = kMaxOrd + 1 - jb; j <= kMaxOrd; j++) {
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + hot.yh(j, i);
             }
@@ -285,9 +398,9 @@ struct Engine {
     }
     BV_DEV void retract() {  // M:2181-2187, 2342-2348
 #pragma unroll
-        for (int jb = 1; jb <= kMaxOrdBdf; jb++) {
+        for (int jb = 1; jb <= kMaxOrd; jb++) {
 #pragma unroll
-            for (int j = kMaxOrdBdf + 1 - jb; j <= kMaxOrdBdf; j++) {
+            for (int j = kMaxOrd + 1 - jb; j <= kMaxOrd; j++) {
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) - hot.yh(j, i);
             }
@@ -327,17 +440,29 @@ struct Engine {
     //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
     BV_DEV void order_change(bool up) {
         double el[kLmax + 1];
-        const double t1 = dvjust_coeffs(c, hot, up, el);
+        double t1 = 0.0;
+        if constexpr (METH == 2) {
+            t1 = dvjust_coeffs_bdf(c, hot, up, el);
+        } else {
+            // Adams (M:2656-2692): raising the order only zeroes the new column, which the
+            // zero-column invariant already guarantees; lowering it needs el(3:nq)
+            if (up) {
+#pragma unroll
+                for (int j = 0; j <= kLmax; j++) el[j] = 0.0;
+            } else {
+                dvjust_coeffs_adams_down(c, hot, el);
+            }
+        }
         double col[NLOC];
         if (up) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) col[i] = t1 * acsav.get(i);
+            for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * acsav.get(i) : 0.0;
         } else {
             get_col(c.L, col);
 #pragma unroll
             for (int i = 0; i < NLOC; i++) col[i] = -col[i];
         }
-        const int jhi = up ? c.nq + 1 : ((c.nq == 2) ? 0 : c.nq);
+        const int jhi = up ? ((METH == 2) ? c.nq + 1 : 0) : ((c.nq == 2) ? 0 : c.nq);
         const int jnew = up ? c.L + 1 : c.L;  // column written (up) or zeroed (down)
 #pragma unroll
         for (int j = 3; j <= kLmax; j++) {
@@ -529,8 +654,12 @@ struct Engine {
         if (nflag == 0) c.icf = 0;
         if (nflag == -2) c.ipup = MITER;
         if (c.jstart == 0) c.ipup = MITER;
-        c.drc = fabs(c.rc - 1.0);
-        if (c.drc > ccmax || hot.si(SI_NST) >= hot.si(SI_NSLP) + msbp) c.ipup = MITER;
+        if constexpr (MITER == 0) {
+            hot.sd(SD_CRATE) = 1.0;  // M:2751
+        } else {
+            c.drc = fabs(c.rc - 1.0);
+            if (c.drc > ccmax || hot.si(SI_NST) >= hot.si(SI_NSLP) + msbp) c.ipup = MITER;
+        }
         (void)rtq4;
 
         int result = 1;  // 1 = another corrector pass is needed
@@ -543,46 +672,74 @@ struct Engine {
             for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
             POL::f(c.tn, y, savf, par);
             hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
-            if (c.ipup > 0) {
-                int ierpj;
-                POL::jac_setup(*this, ierpj);
-                c.ipup = 0;
-                c.rc = 1.0;
-                c.drc = 0.0;
-                hot.sd(SD_CRATE) = 1.0;
-                hot.si(SI_NSLP) = hot.si(SI_NST);
-                singular = (ierpj != 0);
+            if constexpr (MITER != 0) {
+                if (c.ipup > 0) {
+                    int ierpj;
+                    POL::jac_setup(*this, ierpj);
+                    c.ipup = 0;
+                    c.rc = 1.0;
+                    c.drc = 0.0;
+                    hot.sd(SD_CRATE) = 1.0;
+                    hot.si(SI_NSLP) = hot.si(SI_NST);
+                    singular = (ierpj != 0);
+                }
             }
             if (!singular) {
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
                 // 2/(1+rc), M:2813: rc is fixed during the iterations of one pass
-                const bool do_scale = (c.rc != 1.0);
-                const double cscale = qdiv(2.0, 1.0 + c.rc);
+                // 2/(1+rc), BDF only (M:2813): rc is fixed during the iterations of one pass
+                const bool do_scale = (METH == 2) && (c.rc != 1.0);
+                const double cscale = (METH == 2) ? qdiv(2.0, 1.0 + c.rc) : 1.0;
                 const double rl1h = c.rl1 * c.h;
                 bool iterate = true;
 #pragma unroll 1
                 while (iterate) {
+                    int iersl = 0;
+                    if constexpr (MITER != 0) {
+                        // chord iteration, M:2800-2821
 #pragma unroll
-                    for (int i = 0; i < NLOC; i++)
-                        y[i] = rl1h * savf[i] - (c.rl1 * hot.yh(1, i) + acor[i]);
-                    POL::solve(*this, y);
-                    hot.si(SI_NNI) = hot.si(SI_NNI) + 1;
-                    if (do_scale) {
-#pragma unroll
-                        for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
+                        for (int i = 0; i < NLOC; i++)
+                            y[i] = rl1h * savf[i] - (c.rl1 * hot.yh(1, i) + acor[i]);
+                        iersl = POL::solve(*this, y);
+                        hot.si(SI_NNI) = hot.si(SI_NNI) + 1;
                     }
+                    if (iersl > 0) {  // dvsol failed (diagonal approximation, M:2806)
+                        iterate = false;
+                        continue;
+                    }
+                    if constexpr (MITER != 0) {
+                        if (do_scale) {
+#pragma unroll
+                            for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
+                        }
 #if BVODE_STRICT
-                    del = POL::norm(y, ewt);
+                        del = POL::norm(y, ewt);
 #else
-                    // fast build: `del` and `delp` hold the MEAN SQUARE (norm^2); the tests of
-                    // M:2842-2855 are applied to squares, sqrt only for the rate estimate
-                    del = POL::msq(y, ewt);
+                        // fast build: `del` and `delp` hold the MEAN SQUARE (norm^2); the tests
+                        // of M:2842-2855 are applied to squares, sqrt only for the rate estimate
+                        del = POL::msq(y, ewt);
 #endif
 #pragma unroll
-                    for (int i = 0; i < NLOC; i++) acor[i] = acor[i] + y[i];
+                        for (int i = 0; i < NLOC; i++) acor[i] = acor[i] + y[i];
 #pragma unroll
-                    for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + acor[i];
+                        for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + acor[i];
+                    } else {
+                        // functional iteration, M:2822-2837
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) savf[i] = c.rl1 * (c.h * savf[i] - hot.yh(1, i));
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) y[i] = savf[i] - acor[i];
+#if BVODE_STRICT
+                        del = POL::norm(y, ewt);
+#else
+                        del = POL::msq(y, ewt);
+#endif
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + savf[i];
+#pragma unroll
+                        for (int i = 0; i < NLOC; i++) acor[i] = savf[i];
+                    }
 #if BVODE_STRICT
                     if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), qdiv(del, delp));
                     const double dcon = qdiv(del * dmin2(1.0, hot.sd(SD_CRATE)), hot.tq(4));
@@ -617,7 +774,7 @@ struct Engine {
                 c.acnrm = (m == 0) ? del : POL::msq(acor, ewt);  // squared, see above
 #endif
                 result = 0;
-            } else if (!singular && c.jcur != 1) {
+            } else if (MITER != 0 && !singular && c.jcur != 1) {
                 c.icf = 1;
                 c.ipup = MITER;
             } else {
@@ -645,7 +802,8 @@ struct Engine {
     template <class TOUT, class EMIT>
     BV_DEV int run(int nout, TOUT tout_of, bool first, double &t_out, EMIT emit) {
         constexpr int kfc = -3, kfh = -7, mxncf = 10;
-        constexpr double addon = 1.0e-6, bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
+        [[maybe_unused]] constexpr double addon = 1.0e-6;
+        constexpr double bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
                          etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
                          etamx3 = 10.0, onepsm = 1.00001;
 #if BVODE_STRICT
@@ -761,7 +919,7 @@ struct Engine {
                 // ---- label 400: predict, coefficients (M:2147-2158)
                 c.tn = c.tn + c.h;
                 predict();
-                dvset_bdf(c, hot);
+                dvset<METH>(c, hot);
                 c.rl1 = qrcp(hot.el(2));
                 c.rc = c.rc * qdiv(c.rl1, c.prl1);
                 c.prl1 = c.rl1;

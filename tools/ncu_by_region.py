@@ -3,36 +3,33 @@
 usage: ncu_by_region.py <src.csv> <nvdisasm_lines.txt> <mangled-kernel-substring>"""
 import csv, re, sys, collections
 src_csv, dis, key = sys.argv[1], sys.argv[2], sys.argv[3]
-REG = [
-    ("vode_core.cuh", 61, 83, "pick helpers"),
-    ("vode_core.cuh", 84, 140, "dvset_bdf"),
-    ("vode_core.cuh", 141, 176, "dvjust_coeffs"),
-    ("vode_core.cuh", 215, 239, "dewset/norm_y0"),
-    ("vode_core.cuh", 240, 249, "predict"),
-    ("vode_core.cuh", 250, 259, "retract"),
-    ("vode_core.cuh", 260, 274, "rescale"),
-    ("vode_core.cuh", 275, 287, "get_col"),
-    ("vode_core.cuh", 288, 317, "order_change"),
-    ("vode_core.cuh", 318, 334, "dvindy0"),
-    ("vode_core.cuh", 375, 483, "dvhin/init"),
-    ("vode_core.cuh", 484, 594, "dvnlsd"),
-    ("vode_core.cuh", 595, 760, "run: head..dsm"),
-    ("vode_core.cuh", 760, 814, "run: failure paths"),
-    ("vode_core.cuh", 815, 836, "run: accept update"),
-    ("vode_core.cuh", 836, 943, "run: order/eta select"),
-    ("vode_core.cuh", 943, 975, "run: tail"),
-    ("bvode_math.cuh", 25, 45, "powi"),
-    ("bvode_math.cuh", 110, 125, "rpow/recip_int"),
-    ("bvode_math.cuh", 126, 162, "log2_fast"),
-    ("bvode_math.cuh", 163, 190, "exp2_fast"),
-    ("policy_thread.cuh", 30, 45, "GlobalVec/Tol"),
-    ("policy_thread.cuh", 120, 180, "norm/msq/etc"),
-    ("policy_thread.cuh", 181, 233, "dgefa"),
-    ("policy_thread.cuh", 234, 266, "dgesl"),
-    ("policy_thread.cuh", 267, 348, "jac_setup"),
-    ("problems.cuh", 0, 999, "f/jac"),
-    ("bvode_kernels.cuh", 0, 999, "kernel shell"),
-]
+import os
+def _regions():
+    """(file, first line, last line, name) of every device function in dvode_b200/csrc, plus the
+    marked sections of Engine::run ('// ----' comments)."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dvode_b200", "csrc")
+    out = []
+    for fn in sorted(os.listdir(root)):
+        if not fn.endswith((".cuh", ".cu", ".h")): continue
+        starts = []
+        inrun = False
+        for n, ln in enumerate(open(os.path.join(root, fn)), 1):
+            m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:BV_DEV|__device__|__global__)[^;(]*?\b([A-Za-z_]\w*)\s*\(", ln)
+            if m and not ln.strip().startswith("//"):
+                name = m.group(1)
+                if name in ("__launch_bounds__", "__noinline__"):
+                    m2 = re.search(r"\b([A-Za-z_]\w*)\s*\($", ln.rstrip().rstrip("{").rstrip())
+                    continue
+                starts.append((n, name)); inrun = (name == "run")
+                continue
+            if inrun:
+                m = re.match(r"\s*// ---- (.{3,40})", ln)
+                if m: starts.append((n, "run/" + m.group(1).strip()[:34]))
+        for k, (n, name) in enumerate(starts):
+            end = starts[k + 1][0] - 1 if k + 1 < len(starts) else 10 ** 9
+            out.append((fn, n, end, name))
+    return out
+REG = _regions()
 lines = []; cur = None; infn = False
 for ln in open(dis):
     if ln.startswith(".text."):
