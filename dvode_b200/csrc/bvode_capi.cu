@@ -65,6 +65,7 @@ struct bvode_solver {
     cudaStream_t stream = nullptr;
     // state (allocated at the first istate = 1 call, when mf / ml / mu are known)
     int mf = 0, ml = 0, mu = 0;
+    int maxord = 0;  // of the last call (istate = 3 may change it)
     size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
     double *d_state = nullptr;
     int *i_state = nullptr;
@@ -242,7 +243,7 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
                       Checked *c) {
     if (neq != s->neq) { g_err = "neq does not match the problem"; return BVODE_EINVAL; }
     if (itask < 1 || itask > 5) { g_err = "itask illegal"; return BVODE_EINVAL; }
-    if (itask != 1) { g_err = "itask 2-5 not built yet"; return BVODE_ENOTIMPL; }
+    if ((itask == 4 || itask == 5) && !rwork0) { g_err = "itask 4/5 needs rwork(1) = tcrit"; return BVODE_EINVAL; }
     if (itol < 1 || itol > 4) { g_err = "itol illegal"; return BVODE_EINVAL; }
     if (iopt < 0 || iopt > 1) { g_err = "iopt illegal"; return BVODE_EINVAL; }
     if (!rtol || !atol) { g_err = "rtol/atol null"; return BVODE_EINVAL; }
@@ -265,6 +266,9 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
     o.itol = itol;
     o.ml = ml;
     o.mu = mu;
+    o.itask = itask;
+    o.tcrit = (itask == 4 || itask == 5) ? rwork0[0] : 0.0;
+    o.jreset = 0;
     const int mord = (meth == 1) ? 12 : 5;
     if (iopt == 1) {
         if (!rwork0 || !iwork0) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
@@ -326,7 +330,11 @@ static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
 // Launch the integration for touts[0..nout) on device-resident SoA buffers.
 static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, double *d_t,
                       int *d_istate, int nout, const double *touts, const double *d_tout_ps,
-                      double *d_yout, cudaStream_t st) {
+                      double *d_yout, cudaStream_t st, bool general) {
+    if (nout > 1 && !(c.o.itask == 1 || c.o.itask == 4)) {
+        g_err = "a tout schedule (nout > 1) needs itask 1 or 4: itask 2, 3, 5 return at mesh points, one call at a time";
+        return BVODE_EINVAL;
+    }
     int rc = ensure_state(s, mf, c.o.ml, c.o.mu);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
@@ -356,6 +364,7 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
         a.iout = s->d_iout;
         a.lenrw = c.lenrw;
         a.leniw = c.leniw;
+        a.general = general ? 1 : 0;
         const int e = s->pe->launch(mf, a, st);
         if (e == -1000) { g_err = "mf not built for this problem"; return BVODE_ENOTIMPL; }
         if (e != 0) { g_err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e); return BVODE_ECUDA; }
@@ -375,12 +384,18 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     s->last_launches = 0;
     // block A (M:1073-1109): istate legality, per system
     bool any_first = false;
+    int n3 = 0;
     for (int i = 0; i < nsys; i++) {
         if (istate[i] == 1) any_first = true;
-        else if (istate[i] == 3) { g_err = "istate = 3 not built yet"; return BVODE_ENOTIMPL; }
+        else if (istate[i] == 3) n3++;
         else if (istate[i] < 0) { g_err = "negative istate on input (the reference aborts the run here)"; return BVODE_EISTATE; }
         else if (istate[i] != 2) { for (int j = 0; j < nsys; j++) istate[j] = -3; g_err = "istate illegal"; return BVODE_EINVAL; }
     }
+    // istate = 3 (M:1382-1390): the optional inputs are batch-uniform, so a restart with changed
+    // parameters applies to the whole batch; mf / ml / mu select the kernel and the state layout
+    // and cannot change without a new handle
+    if (n3 != 0 && n3 != nsys) { g_err = "istate = 3 must be given for every system of the batch"; return BVODE_EINVAL; }
+    if (n3 != 0 && (!s->d_state || s->mf != mf)) { g_err = "istate = 3 with a different mf is not built (the state layout is per method flag)"; return BVODE_ENOTIMPL; }
     Checked c;
     const bool have_headers = rwork && iwork;
     int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c);
@@ -388,6 +403,8 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         if (rc == BVODE_EINVAL) for (int j = 0; j < nsys; j++) istate[j] = -3;
         return rc;
     }
+    if (n3 != 0 && (c.o.ml != s->ml || c.o.mu != s->mu)) { g_err = "istate = 3 with different ml / mu is not built"; return BVODE_ENOTIMPL; }
+    if (n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
     if (!any_first && (s->mf != mf || !s->d_state)) {
         for (int j = 0; j < nsys; j++) istate[j] = -3;  // M:1102-1106
         g_err = "istate = 2 but the solver was not initialised with this mf";
@@ -421,8 +438,10 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         d_yout = s->d_yout;
     }
     double tout1 = 0.0;
-    rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, st);
+    rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, st,
+                    itask != 1 || n3 != 0);
     if (rc != BVODE_OK) return rc;
+    s->maxord = c.o.maxord;
     // device -> host
     k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_y, s->d_aos, nsys, neq);
     s->last_launches++;
@@ -482,9 +501,11 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, doub
                         false, mf, &c);
     if (rc != BVODE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;  // 0 = the legacy default stream, as documented
+    // (device-resident istate: istate = 3 is only accepted through the host-buffer entry points)
     rc = run_device(s, c, mf, y_device, t_device, istate_device, nout, touts, nullptr,
-                    y_out_device, st);
+                    y_out_device, st, itask != 1);
     if (rc != BVODE_OK) return rc;
+    s->maxord = c.o.maxord;
     CUDA_TRY(cudaGetLastError());
     return BVODE_OK;
 }

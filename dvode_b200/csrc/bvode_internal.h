@@ -12,6 +12,11 @@ struct BvOpts {
     int maxord, mxstep, mxhnil;  // iwork(5:7)
     int itol;
     int ml, mu;                  // iwork(1:2) (band problems)
+    int itask;                   // 1..5 (M:811-831)
+    int jreset;                  // istate = 3 with a changed maxord and a saved Jacobian: the saved
+                                 // copy is not trusted (the reference's work-array segments move,
+                                 // M:1246-1268, and its copy is lost) -> re-evaluate at the next dvjac
+    double tcrit;                // rwork(1), itask 4 / 5
 };
 
 // Arguments of one solve launch.  All pointers are device pointers, SoA layout.
@@ -32,6 +37,7 @@ struct KArgs {
     double *rout;                  // [4][nsys]  rwork(11:14)
     int *iout;                     // [12][nsys] iwork(11:22)
     int lenrw, leniw;              // iwork(17:18), M:1268-1273
+    int general;                   // 1: full-driver kernel (itask 2-5, istate = 3); 0: lean itask = 1
 };
 
 struct DkyArgs {

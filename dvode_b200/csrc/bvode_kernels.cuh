@@ -30,6 +30,7 @@ BV_DEV void visit_state(ENG &e, V &v) {
     for (int j = 1; j <= ENG::kLmax; j++) v.d(e.hot.tau(j));
     v.d(c.h); v.d(c.hscal); v.d(e.hot.sd(SD_HNEW)); v.d(e.hot.sd(SD_HU)); v.d(c.eta); v.d(e.hot.sd(SD_ETAMAX)); v.d(c.tn);
     v.d(c.rc); v.d(c.prl1); v.d(e.hot.sd(SD_CRATE)); v.d(e.hot.sd(SD_CONP));
+    v.d(e.hot.sd(SD_ETAQ)); v.d(e.hot.sd(SD_ETAQM1)); v.d(e.hot.tq(1));
     v.i(c.nq); v.i(c.nqwait); v.i(c.newq); v.i(c.newh); v.i(c.jstart); v.i(c.icf); v.i(c.ipup);
     v.i(e.hot.si(SI_NSLJ)); v.i(e.hot.si(SI_NSLP)); v.i(e.hot.si(SI_NHNIL)); v.i(e.hot.si(SI_INIT));
     v.i(e.hot.si(SI_NST)); v.i(e.hot.si(SI_NFE)); v.i(e.hot.si(SI_NJE)); v.i(e.hot.si(SI_NLU)); v.i(e.hot.si(SI_NNI)); v.i(e.hot.si(SI_NCFN)); v.i(e.hot.si(SI_NETF));
@@ -63,13 +64,13 @@ struct Storer {
 // ------------------------------------------------------- thread-per-system ------
 constexpr int kThreadTPB = 128;
 
-template <class POL>
+template <class POL, bool GENERAL>
 __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem_thread[];
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     int ist = a.istate[sys];
-    if (ist != 1 && ist != 2) return;  // a failed / illegal system is left untouched
+    if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return;  // failed / illegal: left untouched
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -109,10 +110,11 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
             a.istate[sys] = IST_ILLEGAL;
             return;
         }
+        if (GENERAL && ist == 3) e.restart_istate3(true);  // M:1383-1390
     }
 
     int nemit = 0;
-    ist = e.run(
+    ist = e.template run<GENERAL>(
         a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
         [&](int k, const double (&yk)[N]) {
             nemit = k + 1;
@@ -121,6 +123,11 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
                 for (int i = 0; i < N; i++) a.y_out[((size_t)k * N + i) * a.nsys + sys] = yk[i];
             }
         });
+    if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
+        a.istate[sys] = IST_ILLEGAL;
+        if (nemit == 0) return;      // nothing was done: y, t and the state stay as they were
+        ist = IST_ILLEGAL;
+    }
     if (a.y_out) {  // a system that failed keeps its last state in the remaining output slots
         for (int k2 = nemit; k2 < a.nout; k2++) {
 #pragma unroll
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
 //   per-lane  [kLaneSlots][nsys][32]      lane l of system s at (k*nsys + s)*32 + l: coalesced
 //   blocks    [nsys][nblock]              shared-memory image of the band arrays
 template <class POL>
-__host__ __device__ constexpr int scalar_d() { return POL::kLmax + 11; }  // tau(1:lmax) + the 11 scalars of visit_state
+__host__ __device__ constexpr int scalar_d() { return POL::kLmax + 14; }  // tau(1:lmax) + the 14 scalars of visit_state
 constexpr int kScalarI = 19;
 constexpr int kWarpTPB = 128;         // 4 systems per block
 
@@ -268,7 +275,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
 #ifndef BVODE_WARP_MINBLOCKS
 #define BVODE_WARP_MINBLOCKS 6
 #endif
-template <class POL>
+template <class POL, bool GENERAL>
 __global__ void __launch_bounds__(kWarpTPB, BVODE_WARP_MINBLOCKS)
 vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem[];
@@ -277,7 +284,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
     const size_t nsys = (size_t)a.nsys;
     if (sys >= nsys) return;  // whole warp
     int ist = a.istate[sys];
-    if (ist != 1 && ist != 2) return;
+    if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return;
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -315,15 +322,21 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
             return;
         }
+        if (GENERAL && ist == 3) e.restart_istate3(ln == 0);
     }
 
     int nemit = 0;
-    ist = e.run(
+    ist = e.template run<GENERAL>(
         a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
         [&](int k, const double (&yk)[1]) {
             nemit = k + 1;
             if (a.y_out && ln < N) a.y_out[((size_t)k * N + ln) * nsys + sys] = yk[0];
         });
+    if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
+        if (ln == 0) a.istate[sys] = IST_ILLEGAL;
+        if (nemit == 0) return;
+        ist = IST_ILLEGAL;
+    }
     if (a.y_out && ln < N) {
         for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
     }
@@ -389,9 +402,15 @@ static int launch_thread(const KArgs &a, cudaStream_t st) {
     static_assert(POL::kTPB == kThreadTPB, "shared-memory stride");
     size_t smem = POL::kSmemBytes;
     if (const char *pad = getenv("BVODE_PAD_SMEM")) smem += (size_t)atol(pad);  // occupancy experiments
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(vode_thread_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vode_thread_kernel<POL><<<grid, kThreadTPB, smem, st>>>(a);
+    if (a.general) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(vode_thread_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        vode_thread_kernel<POL, true><<<grid, kThreadTPB, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(vode_thread_kernel<POL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        vode_thread_kernel<POL, false><<<grid, kThreadTPB, smem, st>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 template <class POL>
@@ -407,9 +426,15 @@ static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = kWarpTPB / 32;
     const int grid = (a.nsys + spb - 1) / spb;
     const size_t smem = sizeof(double) * spb * (size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(vode_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vode_warp_kernel<POL><<<grid, kWarpTPB, smem, st>>>(a);
+    if (a.general) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(vode_warp_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        vode_warp_kernel<POL, true><<<grid, kWarpTPB, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(vode_warp_kernel<POL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        vode_warp_kernel<POL, false><<<grid, kWarpTPB, smem, st>>>(a);
+    }
     return (int)cudaGetLastError();
 }
 template <class POL>
@@ -475,7 +500,7 @@ static void thread_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, s
     constexpr int N = PROB::N;
     const MfParts m = mf_parts(mf);
     const int lm = kLmaxOf(m.meth);
-    *nd = nsys * (size_t)(lm * N + 2 * N + N * N + (m.savej ? N * N : 0) + lm + 11);
+    *nd = nsys * (size_t)(lm * N + 2 * N + N * N + (m.savej ? N * N : 0) + lm + 14);
     *ni = nsys * (size_t)(N + 19);
 }
 template <class PROB>

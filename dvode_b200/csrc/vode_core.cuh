@@ -44,7 +44,8 @@ constexpr int kLmaxBdf = kMaxOrdBdf + 1;
 enum : int {
     IST_FIRST = 1, IST_OK = 2,
     IST_MXSTEP = -1, IST_TOLSF = -2, IST_ILLEGAL = -3, IST_ERRTEST = -4, IST_CONVFAIL = -5,
-    IST_EWT = -6
+    IST_EWT = -6,
+    IST_ILLEGAL_ENTRY = -30  // internal: istate = -3 detected at call entry (y, t untouched)
 };
 
 // Scalar per-system state: the members of dvode_data_t (M:40-153) that are not
@@ -57,7 +58,11 @@ struct Ctl {
     double h, hscal, eta, tn, rc, prl1, rl1, drc, acnrm;
     int nq, L, nqwait, newq, newh, jstart, icf, ipup, jcur, kflag;
 };
-enum : int { SD_CONP = 0, SD_HU, SD_HNEW, SD_CRATE, SD_ETAMAX, SD_COUNT };
+// SD_ETAQ / SD_ETAQM1: the reference's etaq / etaqm1 (M:258-259), which only an istate = 3 call
+// that lowers maxord below a pending order increase reads back (M:2059-2063).  Strict build:
+// the values; fast build: the arguments xq = (bias2*dsm)^2, xm = (bias1*ddn)^2 of the step that
+// chose the increase (the ratios are evaluated from them if they are ever needed).
+enum : int { SD_CONP = 0, SD_HU, SD_HNEW, SD_CRATE, SD_ETAMAX, SD_ETAQ, SD_ETAQM1, SD_COUNT };
 enum : int { SI_NST = 0, SI_NFE, SI_NJE, SI_NLU, SI_NNI, SI_NCFN, SI_NETF, SI_NQU, SI_NSLJ,
              SI_NSLP, SI_NHNIL, SI_INIT, SI_COUNT };
 
@@ -434,6 +439,29 @@ struct Engine {
         }
     }
 
+    // istate = 3, M:1383-1390 (the optional inputs were re-read on the host; this is the device
+    // part).  `first_comp`: this thread holds component 1 of the system.
+    // Two consequences of the reference's work-array layout are mirrored / resolved here: with a
+    // lowered maxord the segment pointer lwm = lyh + (maxord+1)*nyh moves INTO the old yh, and
+    //  * M:1386 `rwork(lwm) = sqrt(uround)` (miter > 0) lands on yh(1, maxord+2) before dvstep's
+    //    dvjust(-1) reads that column (case maxord = nq-1, M:2060-2068) -- mirrored, since the
+    //    results depend on it;
+    //  * a saved Jacobian (mf > 0) is then read from memory that holds other data -- resolved
+    //    by re-evaluating it (o.jreset, set by the host when maxord changed).
+    BV_DEV void restart_istate3(bool first_comp) {
+        c.jstart = -1;
+        if (c.nq > o.maxord) {
+            get_col(o.maxord + 2, savf);
+            if (MITER > 0 && first_comp) {
+#pragma unroll
+                for (int j = 2; j <= kLmax; j++) {
+                    if (j == o.maxord + 2) hot.yh(j - 1, 0) = sqrt(kUround);
+                }
+            }
+        }
+        if (o.jreset) hot.si(SI_NSLJ) = hot.si(SI_NST) - 51;  // forces jok = -1 (msbj = 50)
+    }
+
     // dvjust, M:2568-2694 (BDF), both directions in one pass over yh.
     //   down: yh(:,j) -= yh(:,L)*el(j), j = 3..nq   (nothing if nq == 2, M:2581); the freed
     //         column L is zeroed to keep the zero-column invariant.
@@ -629,6 +657,11 @@ struct Engine {
         dewset_invert(bad);
         if (bad) return IST_ILLEGAL;  // message 21
         double h0 = o.h0;
+        if ((tout - t) * h0 < 0.0) return IST_ILLEGAL;  // message 14, M:1214
+        if (o.itask == 4 || o.itask == 5) {  // M:1314-1323
+            if ((o.tcrit - tout) * (tout - t) < 0.0) return IST_ILLEGAL;  // message 25
+            if (h0 != 0.0 && (t + h0 - o.tcrit) * h0 > 0.0) h0 = o.tcrit - t;
+        }
         if (h0 == 0.0) {
             int niter;
             const int ier = dvhin(t, tout, h0, niter);
@@ -653,7 +686,7 @@ struct Engine {
         if (c.jstart == 0) hot.si(SI_NSLP) = 0;
         if (nflag == 0) c.icf = 0;
         if (nflag == -2) c.ipup = MITER;
-        if (c.jstart == 0) c.ipup = MITER;
+        if (c.jstart == 0 || c.jstart == -1) c.ipup = MITER;  // M:2748
         if constexpr (MITER == 0) {
             hot.sd(SD_CRATE) = 1.0;  // M:2751
         } else {
@@ -799,7 +832,11 @@ struct Engine {
     // systems of a warp are never made to wait for each other at an output point.
     // `first` is true when init_problem ran in this launch (goto 200, M:1381).
     // Returns the output istate; t_out receives the output t; y the output solution.
-    template <class TOUT, class EMIT>
+    //
+    // GENERAL = false is the lean instantiation for itask = 1 (the hot path).  GENERAL = true
+    // adds the rest of the driver: itask 2-5 with tcrit / kuth (blocks D and F, M:1399-1483,
+    // 1586-1623; dvstep M:2100-2103) and the istate = 3 restart (jstart = -1, M:2031-2079).
+    template <bool GENERAL, class TOUT, class EMIT>
     BV_DEV int run(int nout, TOUT tout_of, bool first, double &t_out, EMIT emit) {
         constexpr int kfc = -3, kfh = -7, mxncf = 10;
         [[maybe_unused]] constexpr double addon = 1.0e-6;
@@ -819,14 +856,81 @@ struct Engine {
         int kout = 0;
         double tout = tout_of(0);
         // "reached": tout lies inside the step just taken -> interpolate instead of stepping
-        bool reached = !first && !((c.tn - tout) * c.h < 0.0);
+        bool reached = !GENERAL && !first && !((c.tn - tout) * c.h < 0.0);
         if (reached) {
             // block D on a continuation call checks dvindy's flag (message 27, M:1459-1464)
             double dky[NLOC];
             if (dvindy0(tout, dky) != 0) {
                 reached = false;
-                istate = IST_ILLEGAL;
+                istate = IST_ILLEGAL_ENTRY;
             }
+        }
+        // ---- GENERAL: what the current call does next (blocks D and F for every itask)
+        enum { ACT_STEP = 0, ACT_RET_INTERP = 1, ACT_RET_YH = 2, ACT_ILLEGAL = 3 };
+        [[maybe_unused]] int act = ACT_STEP, kuth = 0;
+        [[maybe_unused]] bool ihit = false;
+        [[maybe_unused]] double t_emit = tout;
+        const int itask = GENERAL ? o.itask : 1;
+        // tcrit handling shared by blocks D and F (M:1469-1483, 1600-1612): true = return now
+        auto tcrit_logic = [&]() -> bool {
+            const double hmx = fabs(c.tn) + fabs(c.h);
+            ihit = fabs(c.tn - o.tcrit) <= 100.0 * kUround * hmx;
+            if (ihit) return true;
+            const double tnext = c.tn + hot.sd(SD_HNEW) * (1.0 + 4.0 * kUround);
+            if ((tnext - o.tcrit) * c.h > 0.0) {
+                c.h = (o.tcrit - c.tn) * (1.0 - 4.0 * kUround);
+                kuth = 1;
+            }
+            return false;
+        };
+        // block D, M:1399-1483: entry of a continuation call
+        auto block_d = [&](double to) -> int {
+            nslast = hot.si(SI_NST);
+            kuth = 0;
+            ihit = false;
+            if (itask == 2) return ACT_STEP;
+            if (itask == 3) {
+                const double tp = c.tn - hot.sd(SD_HU) * (1.0 + 100.0 * kUround);
+                if ((tp - to) * c.h > 0.0) return ACT_ILLEGAL;  // message 23
+                if ((c.tn - to) * c.h >= 0.0) return ACT_RET_YH;
+                return ACT_STEP;
+            }
+            if (itask == 4 || itask == 5) {
+                if ((c.tn - o.tcrit) * c.h > 0.0) return ACT_ILLEGAL;  // message 24
+                if (itask == 4) {
+                    if ((o.tcrit - to) * c.h < 0.0) return ACT_ILLEGAL;  // message 25
+                    if ((c.tn - to) * c.h >= 0.0) {
+                        double dky[NLOC];
+                        if (dvindy0(to, dky) != 0) return ACT_ILLEGAL;  // message 27
+                        return ACT_RET_INTERP;
+                    }
+                }
+                return tcrit_logic() ? ACT_RET_YH : ACT_STEP;
+            }
+            if ((c.tn - to) * c.h < 0.0) return ACT_STEP;
+            double dky[NLOC];
+            if (dvindy0(to, dky) != 0) return ACT_ILLEGAL;  // message 27
+            return ACT_RET_INTERP;
+        };
+        // block F, M:1586-1623: after a successful step
+        auto block_f = [&](double to) -> int {
+            kuth = 0;
+            ihit = false;
+            if (itask == 2) return ACT_RET_YH;
+            if (itask == 3) return ((c.tn - to) * c.h < 0.0) ? ACT_STEP : ACT_RET_YH;
+            if (itask == 4) {
+                if ((c.tn - to) * c.h < 0.0) return tcrit_logic() ? ACT_RET_YH : ACT_STEP;
+                return ACT_RET_INTERP;
+            }
+            if (itask == 5) {
+                const double hmx = fabs(c.tn) + fabs(c.h);
+                ihit = fabs(c.tn - o.tcrit) <= 100.0 * kUround * hmx;
+                return ACT_RET_YH;
+            }
+            return ((c.tn - to) * c.h < 0.0) ? ACT_STEP : ACT_RET_INTERP;
+        };
+        if constexpr (GENERAL) {
+            if (!first) act = block_d(tout);
         }
 
         int entry = E_NEWSTEP;
@@ -849,6 +953,32 @@ struct Engine {
                 } else {
                     reached = false;
                     istate = IST_OK;
+                }
+            }
+            if constexpr (GENERAL) {
+                // ---- returns of the current call (block G, M:1648-1652) and the next call's entry
+#pragma unroll 1
+                while (act != ACT_STEP && istate == 0) {
+                    if (act == ACT_ILLEGAL) {
+                        istate = IST_ILLEGAL_ENTRY;
+                    } else {
+                        if (act == ACT_RET_INTERP) {
+                            dvindy0(tout, y);
+                            t_emit = tout;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
+                            t_emit = ihit ? o.tcrit : c.tn;
+                        }
+                        emit(kout, y);
+                        kout = kout + 1;
+                        if (kout < nout) {
+                            tout = tout_of(kout);
+                            act = block_d(tout);
+                        } else {
+                            istate = IST_OK;
+                        }
+                    }
                 }
             }
             int change = 0;  // pending order change: -1 / +1
@@ -893,12 +1023,58 @@ struct Engine {
                             c.nqwait = 2;
                             c.hscal = c.h;
                             entry = E_PREDICT;
-                        } else if (c.newh == 0) {
-                            entry = E_PREDICT;
                         } else {
-                            if (c.newq < c.nq) change = -1;
-                            else if (c.newq > c.nq) change = 1;
-                            entry = E_RESCALE;
+                            if constexpr (GENERAL) {
+                                if (c.jstart == -1) {
+                                    // ---- istate = 3 restart, M:2044-2079 (savf holds the old
+                                    // yh(:, maxord + 2) when nq > maxord, M:1385)
+                                    const int maxord = o.maxord;
+                                    if (c.newq > maxord) {
+                                        const double flotl = (double)lmax;
+                                        if (maxord < c.nq - 1 || (maxord == c.nq - 1 && c.newq == c.nq)) {
+                                            const double ddn = POL::norm(savf, ewt) / hot.tq(1);
+                                            c.eta = 1.0 / (rpow(bias1 * ddn, 1.0 / flotl) + addon);
+                                        }
+#if BVODE_STRICT
+                                        if (maxord == c.nq && c.newq == c.nq + 1) c.eta = hot.sd(SD_ETAQ);
+                                        if (maxord == c.nq - 1 && c.newq == c.nq + 1) c.eta = hot.sd(SD_ETAQM1);
+#else
+                                        if (maxord == c.nq && c.newq == c.nq + 1)
+                                            c.eta = 1.0 / (rpow(hot.sd(SD_ETAQ), 0.5 * recip_int(c.L)) + addon);
+                                        if (maxord == c.nq - 1 && c.newq == c.nq + 1)
+                                            c.eta = 1.0 / (rpow(hot.sd(SD_ETAQM1), 0.5 * recip_int(c.L - 1)) + addon);
+#endif
+                                        if (maxord == c.nq - 1) order_change(false);  // dvjust(-1)
+                                        c.eta = dmin2(c.eta, 1.0);
+                                        c.nq = maxord;
+                                        c.L = lmax;
+                                        // columns above the new order: zero-column invariant
+#pragma unroll
+                                        for (int j = 2; j <= kLmax; j++) {
+                                            if (j > lmax) {
+#pragma unroll
+                                                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = 0.0;
+                                            }
+                                        }
+                                        c.newq = c.nq;  // (the reference jumps to label 300 here)
+                                    }
+                                    if (kuth == 1) c.eta = dmin2(c.eta, fabs(c.h / c.hscal));
+                                    if (kuth == 0) c.eta = dmax2(c.eta, o.hmin / fabs(c.hscal));
+                                    c.eta = c.eta / dmax2(1.0, fabs(c.hscal) * o.hmax_inv * c.eta);
+                                    c.newh = 1;
+                                    c.nqwait = c.L;
+                                } else if (kuth == 1) {  // h was cut to land on tcrit, M:2100-2103
+                                    c.eta = dmin2(c.eta, c.h / c.hscal);
+                                    c.newh = 1;
+                                }
+                            }
+                            if (c.newh == 0) {
+                                entry = E_PREDICT;
+                            } else {
+                                if (c.newq < c.nq) change = -1;
+                                else if (c.newq > c.nq) change = 1;
+                                entry = E_RESCALE;
+                            }
                         }
                     }
                 } else if (entry == E_DOWN_RESCALE) {
@@ -1044,6 +1220,7 @@ struct Engine {
                         bool save_acor = false;
 #if BVODE_STRICT
                         double eta = etaq;
+                        hot.sd(SD_ETAQ) = etaq;
 #else
                         pend = 2;
                         const float scqf = (float)scsel;
@@ -1082,6 +1259,7 @@ struct Engine {
 #if BVODE_STRICT
                             const double etaqm1 = (c.nq != 1) ? eta_of(bias1 * ddn, c.L - 1) : 0.0;
                             const double etaqp1 = (c.L != lmax) ? eta_of(bias3 * dup, c.L + 1) : 0.0;
+                            hot.sd(SD_ETAQM1) = etaqm1;
                             if (etaq < etaqp1) {
                                 if (etaqp1 <= etaqm1) {
                                     eta = etaqm1;  // label 420
@@ -1111,7 +1289,11 @@ struct Engine {
                                 wsel = choose_ratio_f64(xq, xm, xp, scsel, scm, scp, has_m, has_p);
                             }
                             if (wsel == 1) { newq = c.nq - 1; xsel = xm; scsel = scm; lwf = lmf; }
-                            if (wsel == 2) { newq = c.nq + 1; xsel = xp; scsel = scp; lwf = lpf; save_acor = true; }
+                            if (wsel == 2) {
+                                newq = c.nq + 1; xsel = xp; scsel = scp; lwf = lpf; save_acor = true;
+                                hot.sd(SD_ETAQ) = xq;
+                                hot.sd(SD_ETAQM1) = xm;
+                            }
 #endif
                         }
                         if (save_acor) {
@@ -1159,7 +1341,7 @@ struct Engine {
                     // ---- block F, itask = 1 (M:1586-1622)
                     hot.si(SI_INIT) = 1;
                     entry = E_NEWSTEP;
-                    reached = !((c.tn - tout) * c.h < 0.0);
+                    if constexpr (!GENERAL) reached = !((c.tn - tout) * c.h < 0.0);
                 }
 #if !BVODE_STRICT
                 // ---- phase B: the one ratio evaluation of this attempt
@@ -1190,11 +1372,19 @@ struct Engine {
                     }
                 }
 #endif
+                // block F of the full driver (after dvstep has set hnew, which it reads)
+                if constexpr (GENERAL) {
+                    if (accept) act = block_f(tout);
+                }
             }  // if (istate == 0)
         }
         if (istate == IST_OK) {
-            t_out = tout;  // y was interpolated by the last emit
+            t_out = GENERAL ? t_emit : tout;  // y was set by the last emit
             return IST_OK;
+        }
+        if (istate == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry: that call changes nothing
+            if (GENERAL && kout > 0) t_out = t_emit;
+            return istate;
         }
         // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
 #pragma unroll

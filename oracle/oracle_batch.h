@@ -30,6 +30,12 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
                     const double *atol, double *y_out, double *t_out, int *istate_out,
                     double *rstats, int *istats, int nthreads);
 
+int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int nsplit, int nsys,
+                     const double *params, const double *y0, double t0, int nout,
+                     const double *touts, const double *rtol, const double *atol,
+                     const double *rtol2, const double *atol2, double *y_out, double *t_out,
+                     int *istate_out, double *rstats, int *istats, int nthreads);
+
 int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par, const double *y0, double t0,
                      double tout, const double *rtol, const double *atol, int k, int nq,
                      const double *tqs, double *dky_out, int *iflag_out, double *tcur,

@@ -235,6 +235,75 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
     return fail;
 }
 
+/* Two-phase run: outputs [0, nsplit) with cfg / rtol / atol, then ONE call with istate = 3 and
+ * cfg2 / rtol2 / atol2 (same mf; the reference's "parameter change" restart, M:1382-1390) and
+ * ordinary continuation calls for the remaining outputs. */
+int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int nsplit, int nsys,
+                     const double *params, const double *y0, double t0, int nout,
+                     const double *touts, const double *rtol, const double *atol,
+                     const double *rtol2, const double *atol2, double *y_out, double *t_out,
+                     int *istate_out, double *rstats, int *istats, int nthreads)
+{
+    dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
+    if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
+        return -1;
+    int lrw, liw;
+    dvo_work_sizes(neq, cfg->mf, cfg->ml, cfg->mu, cfg->iopt ? cfg->maxord : 0, &lrw, &liw);
+    if (liw < 30) liw = 30;
+    int fail = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
+        int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
+        double *y = (double *)malloc(sizeof(double) * (size_t)neq);
+        double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int s = 0; s < nsys; s++) {
+            dvo_solver sol;
+            memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
+            dvo_initialize(&sol, f, jac, par);
+            sol.pow_mode = cfg->pow_mode;
+            memset(rwork, 0, sizeof(double) * (size_t)lrw);
+            memset(iwork, 0, sizeof(int) * (size_t)liw);
+            memcpy(y, y0 + (size_t)s * neq, sizeof(double) * (size_t)neq);
+            double t = t0;
+            int istate = 1;
+            for (int io = 0; io < nout; io++) {
+                const dvo_batch_cfg *c = (io < nsplit) ? cfg : cfg2;
+                const double *rt = (io < nsplit) ? rtol : rtol2, *at = (io < nsplit) ? atol : atol2;
+                if (io == nsplit && istate == 2) istate = 3;
+                iwork[0] = c->ml;
+                iwork[1] = c->mu;
+                rwork[4] = c->h0; rwork[5] = c->hmax; rwork[6] = c->hmin;
+                iwork[4] = c->maxord; iwork[5] = c->mxstep; iwork[6] = c->mxhnil;
+                rwork[0] = c->tcrit;
+                if (istate >= 0)
+                    dvo_solve(&sol, neq, y, &t, touts[io], c->itol, rt, at, c->itask, &istate,
+                              c->iopt, rwork, lrw, iwork, liw, c->mf);
+                size_t o = (size_t)s * nout + io;
+                memcpy(y_out + o * neq, y, sizeof(double) * (size_t)neq);
+                if (t_out) t_out[o] = t;
+                if (istate_out) istate_out[o] = istate;
+                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(double) * 4);
+                if (istats) memcpy(istats + o * 12, iwork + 10, sizeof(int) * 12);
+            }
+            if (istate < 0) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+                fail++;
+            }
+        }
+        free(rwork); free(iwork); free(y); free(par);
+    }
+    return fail;
+}
+
 /* dvindy at user points after the last solve of a single system: convenience
  * used by the dense-output parity tests.  Integrates system 0 of the batch to
  * tout with one call, then evaluates derivative order k at each tq. */

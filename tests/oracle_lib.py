@@ -119,6 +119,40 @@ def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1,
     return {"y": y, "t": t, "istate": ist, "rstats": rst, "istats": ista, "nfail": nfail}
 
 
+def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, atol2, itol=1,
+                 itol2=None, itask=1, itask2=None, iopt=0, iopt2=None, ml=0, mu=0, maxord=0,
+                 maxord2=0, mxstep=0, mxstep2=0, hmax=0.0, hmax2=0.0, hmin=0.0, hmin2=0.0,
+                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant=""):
+    """Outputs [0, nsplit) with the first parameter set, then an istate = 3 call with the second
+    set (same mf) and continuation calls: the reference's parameter-change restart."""
+    neq, npar = problem_info(problem)
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(npar, 1)))
+    nsys = params.shape[0]
+    y0 = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=np.float64), (nsys, neq)))
+    touts = np.ascontiguousarray(np.asarray(touts, dtype=np.float64).reshape(-1))
+    nout = touts.size
+    arr = lambda a: np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64)))
+    rtol, atol, rtol2, atol2 = arr(rtol), arr(atol), arr(rtol2), arr(atol2)
+    pick = lambda a, b: b if b is not None else a
+    cfg = BatchCfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, 0, 0.0, hmax,
+                   hmin, tcrit, pow_mode)
+    cfg2 = BatchCfg(PROBLEMS[problem], mf, pick(itol, itol2), pick(itask, itask2), pick(iopt, iopt2),
+                    ml, mu, maxord2, mxstep2, 0, 0.0, hmax2, hmin2, tcrit2, pow_mode)
+    y = np.zeros((nsys, nout, neq))
+    t = np.zeros((nsys, nout))
+    ist = np.zeros((nsys, nout), dtype=np.int32)
+    rst = np.zeros((nsys, nout, 4))
+    ista = np.zeros((nsys, nout, 12), dtype=np.int32)
+    L = lib(variant)
+    L.dvo_batch_solve2.restype = C.c_int
+    nfail = L.dvo_batch_solve2(C.byref(cfg), C.byref(cfg2), int(nsplit), nsys, _dp(params), _dp(y0),
+                               C.c_double(float(t0)), nout, _dp(touts), _dp(rtol), _dp(atol),
+                               _dp(rtol2), _dp(atol2), _dp(y), _dp(t), _ip(ist), _dp(rst), _ip(ista),
+                               nthreads)
+    assert nfail >= 0
+    return {"y": y, "t": t, "istate": ist, "rstats": rst, "istats": ista, "nfail": nfail}
+
+
 # iwork(11:22) slot names in istats[..., k]
 ISTAT = {"nst": 0, "nfe": 1, "nje": 2, "nqu": 3, "nqcur": 4, "imxer": 5, "lenrw": 6, "leniw": 7,
          "nlu": 8, "nni": 9, "ncfn": 10, "netf": 11}

@@ -26,7 +26,9 @@ def _B():
 
 
 def gpu_schedule(problem, params, y0, t0, touts, rtol, atol, mf, itol, strict=False, iopt=0,
-                 rwork_opts=None, iwork_opts=None, per_call=False):
+                 rwork_opts=None, iwork_opts=None, per_call=False, itask=1, phase2=None):
+    """phase2 = dict(nsplit, rtol, atol, itol, itask, iopt, rwork_opts, iwork_opts): from output
+    nsplit on, the calls use these arguments, the first of them with istate = 3 (per_call only)."""
     """Run a batch on the GPU; returns dict like oracle_lib.batch_solve."""
     B = _B()
     params = np.asarray(params, dtype=np.float64)
@@ -52,8 +54,18 @@ def gpu_schedule(problem, params, y0, t0, touts, rtol, atol, mf, itol, strict=Fa
     ist = np.zeros((nsys, nout, 12), dtype=np.int32)
     if per_call:
         for k in range(nout):
+            if phase2 is not None and k == phase2["nsplit"]:
+                itol, rtol, atol = phase2["itol"], phase2["rtol"], phase2["atol"]
+                itask, iopt = phase2["itask"], phase2["iopt"]
+                rwork[0, :20] = 0.0
+                iwork[0, :10] = 0
+                if phase2.get("rwork_opts") is not None:
+                    rwork[0, :] = phase2["rwork_opts"]
+                if phase2.get("iwork_opts") is not None:
+                    iwork[0, :] = phase2["iwork_opts"]
+                istate[istate == 2] = 3
             if (istate > 0).all():
-                s.solve(neq, y, t, touts[k], itol, rtol, atol, 1, istate, iopt, rwork, lrw, iwork,
+                s.solve(neq, y, t, touts[k], itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork,
                         liw, mf)
             yo[k] = y
             to[:, k] = t
@@ -61,7 +73,7 @@ def gpu_schedule(problem, params, y0, t0, touts, rtol, atol, mf, itol, strict=Fa
             rst[:, k] = rwork[:, 10:14]
             ist[:, k] = iwork[:, 10:22]
     else:
-        s.solve_schedule(neq, y, t, touts, itol, rtol, atol, 1, istate, iopt, rwork, lrw, iwork,
+        s.solve_schedule(neq, y, t, touts, itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork,
                          liw, mf, yo)
         to[:, -1] = t
         isto[:, -1] = istate
@@ -371,6 +383,191 @@ def test_error_paths_match_reference_semantics():
     y[:] = [1.0, 0.0, 0.0]
     s.solve(3, y, t, 0.4, 2, [0.0], [0.0, 0.0, 0.0], 1, istate, 0, rwork, 20, iwork, 30, 21)
     assert (istate == -3).all()
+
+
+# ------------------------------------------------- full driver: itask 2-5, istate = 3 ------
+def _ropts(tcrit=0.0, h0=0.0, hmax=0.0, hmin=0.0):
+    r = np.zeros(20)
+    r[0], r[4], r[5], r[6] = tcrit, h0, hmax, hmin
+    return r
+
+
+def _iopts(ml=0, mu=0, maxord=0, mxstep=0):
+    iw = np.zeros(30, dtype=np.int32)
+    iw[0], iw[1], iw[4], iw[5] = ml, mu, maxord, mxstep
+    return iw
+
+
+def _same(a, b, keys=("y", "t", "istate", "istats", "rstats")):
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("itask", [2, 3, 4, 5])
+def test_robertson_itask_strict_bit_exact(itask):
+    """itask 2 (one step per call), 3 (stop at the first mesh point past tout), 4 (as 1, never
+    past tcrit), 5 (one step, never past tcrit), M:811-831 / 1399-1483 / 1586-1623: the
+    reference's call loop replayed call by call on the GPU, strict build bit for bit against
+    the oracle (y, t, istate and the optional outputs after every call)."""
+    B = _B()
+    nsys = 128
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    tcrit = 0.0
+    if itask == 2:
+        touts = np.full(40, 4.0e3)           # 40 single steps towards tout
+    elif itask == 5:
+        touts = np.full(40, 1.0e-3)          # single steps up to tcrit (reached after ~25 steps:
+        tcrit = 1.0e-3                       # the remaining calls return t = tcrit at once)
+    else:
+        touts = rob_touts()[:6]
+        if itask == 4:
+            tcrit = float(touts[-1])         # the last output sits exactly on tcrit
+    ref = O.batch_solve("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21,
+                        itol=2, itask=itask, tcrit=tcrit, pow_mode=1)
+    got = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21, 2,
+                       strict=True, per_call=True, itask=itask, rwork_opts=_ropts(tcrit=tcrit))
+    assert (got["istate"] == 2).all()
+    _same(got, ref)
+    if itask == 5:
+        assert (got["t"][:, -1] == tcrit).all()
+
+
+def test_itask4_schedule_equals_per_call_and_fast_build_agrees():
+    B = _B()
+    nsys = 128
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    touts = rob_touts()[:6]
+    tcrit = float(touts[-1])
+    a = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21, 2,
+                     strict=True, per_call=True, itask=4, rwork_opts=_ropts(tcrit=tcrit))
+    b = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21, 2,
+                     strict=True, per_call=False, itask=4, rwork_opts=_ropts(tcrit=tcrit))
+    assert np.array_equal(a["y"], b["y"])
+    assert np.array_equal(a["istats"][:, -1], b["istats"][:, -1])
+    f = gpu_schedule("robertson", par, ROB["y0"], 0.0, touts, tol["rtol"], tol["atol"], 21, 2,
+                     strict=False, per_call=False, itask=4, rwork_opts=_ropts(tcrit=tcrit))
+    assert (f["istate"][:, -1] == 2).all()
+    # never stepped past tcrit (beyond the round-off the reference's own `ihit` test allows)
+    tcur = f["rstats"][:, -1, O.RSTAT["tcur"]]
+    assert (tcur <= tcrit * (1.0 + 100 * 2.3e-16)).all(), float((tcur / tcrit - 1.0).max())
+    w = weighted_err(f["y"][:, :3], a["y"][:, :3], tol["rtol"][0], tol["atol"])
+    assert w.max() <= 10.0
+    na, nf = a["istats"][:, -1, 0].astype(np.int64).sum(), f["istats"][:, -1, 0].astype(np.int64).sum()
+    assert abs(na - nf) <= 0.02 * na
+
+
+def test_itask_schedule_restrictions_and_illegal_entries():
+    """itask 2, 3, 5 return at mesh points: a multi-tout schedule is refused.  Illegal inputs at
+    a call entry (messages 23, 24, 25) give istate = -3 and leave y and t alone."""
+    B = _B()
+    nsys = 32
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    with pytest.raises(B.BvodeError):
+        gpu_schedule("robertson", par, ROB["y0"], 0.0, rob_touts()[:3], tol["rtol"], tol["atol"], 21,
+                     2, itask=2)
+    g = gpu_schedule("robertson", par, ROB["y0"], 0.0, [0.4, 4.0], tol["rtol"], tol["atol"], 21, 2,
+                     strict=True, per_call=True)
+    s, y, t = g["solver"], g["y"][:, -1].copy(), g["t"][:, -1].copy()
+    rw, iw = np.zeros((nsys, 20)), np.zeros((nsys, 30), dtype=np.int32)
+    for itask, tout, tcrit in ((3, 0.01, 0.0),      # 23: tout behind tcur - hu
+                               (4, 40.0, 1.0),      # 24: tcrit behind tcur
+                               (4, 40.0, 20.0),     # 25: tcrit behind tout
+                               (5, 40.0, 1.0)):     # 24
+        yy, tt, ist = y.copy(), t.copy(), np.full(nsys, 2, dtype=np.int32)
+        rw[0, 0] = tcrit
+        s.solve(3, yy, tt, tout, 2, tol["rtol"], tol["atol"], itask, ist, 0, rw, 20, iw, 30, 21)
+        assert (ist == -3).all(), (itask, ist)
+        assert np.array_equal(yy, y) and np.array_equal(tt, t)
+    # the handle is still usable after the refused calls
+    ist = np.full(nsys, 2, dtype=np.int32)
+    s.solve(3, y, t, 40.0, 2, tol["rtol"], tol["atol"], 1, ist, 0, rw, 20, iw, 30, 21)
+    assert (ist == 2).all() and (t == 40.0).all()
+
+
+@pytest.mark.parametrize("problem,mf,lower", [("robertson", -21, True), ("robertson", 21, False),
+                                              ("vdp", 10, True), ("advection", -24, True),
+                                              ("advection", 24, False)])
+def test_istate3_parameter_change_strict_bit_exact(problem, mf, lower):
+    """istate = 3 (M:1382-1390, dvstep M:2031-2079): after some outputs the caller tightens the
+    tolerances, sets hmax and (lower = True) lowers maxord below the current order -- the order
+    is reduced (dvjust / truncation), h rescaled, the Jacobian refreshed -- bit for bit like the
+    oracle.  (With a SAVED Jacobian, mf > 0, a changed maxord moves the reference's work-array
+    segments, M:1246-1268, and its next dvjac reads the old LU factors as the saved Jacobian; that
+    aliasing is not reproduced -- see test_istate3_maxord_change_with_saved_jacobian.)"""
+    B = _B()
+    nsys = 96
+    if problem == "robertson":
+        par, y0 = B.batches.robertson_batch(nsys), ROB["y0"]
+        touts = rob_touts()[:7]
+        itol, rtol, atol = 2, [1e-4], [1e-8, 1e-14, 1e-6]
+        rtol2, atol2 = [1e-5], [1e-9, 1e-15, 1e-7]
+        kw, iw1 = {}, _iopts(mxstep=5000)
+        maxord2, hmax2 = 2, 3.0e3
+    elif problem == "vdp":
+        par, y0 = B.batches.perturbed((3.0,), nsys, 0.1, B.batches.SEED, 0), [2.0, 0.0]
+        touts = [1.39283880203 + k * 2.214773875 for k in range(4)]
+        itol, rtol, atol = 1, [0.0], [1e-6]
+        rtol2, atol2 = [0.0], [1e-7]
+        kw, iw1 = {}, _iopts(mxstep=5000)
+        maxord2, hmax2 = 2, 0.05                 # Adams at order 5-6 cut down to 2
+    else:
+        par, y0 = B.batches.advection_batch(nsys), B.batches.advection_y0()
+        touts = B.batches.advection_touts()
+        itol, rtol, atol = 1, [0.0], [1e-6]
+        rtol2, atol2 = [0.0], [1e-7]
+        kw, iw1 = dict(ml=5, mu=0), _iopts(5, 0, mxstep=5000)
+        maxord2, hmax2 = 2, 5.0
+    nsplit = 2 if problem == "vdp" else 3
+    if not lower:
+        maxord2 = 0
+    ref = O.batch_solve2(problem, par, y0, 0.0, touts, nsplit, rtol, atol, mf, rtol2, atol2,
+                         itol=itol, iopt=1, mxstep=5000, mxstep2=5000, maxord2=maxord2, hmax2=hmax2,
+                         pow_mode=1, **kw)
+    iw2 = iw1.copy()
+    iw2[4] = maxord2
+    got = gpu_schedule(problem, par, y0, 0.0, touts, rtol, atol, mf, itol, strict=True, iopt=1,
+                       iwork_opts=iw1, per_call=True,
+                       phase2=dict(nsplit=nsplit, rtol=rtol2, atol=atol2, itol=itol, itask=1, iopt=1,
+                                   rwork_opts=_ropts(hmax=hmax2), iwork_opts=iw2))
+    assert (ref["istate"] == 2).all()
+    if lower:  # the restart really lowered the order somewhere in the batch
+        assert (ref["istats"][:, nsplit - 1, O.ISTAT["nqu"]] > maxord2).any()
+        assert (ref["istats"][:, nsplit:, O.ISTAT["nqu"]] <= maxord2).all()
+    _same(got, ref)
+
+
+def test_istate3_maxord_change_with_saved_jacobian():
+    """mf = 21 (saved Jacobian) and a lowered maxord at istate = 3: the reference's next dvjac
+    would read its saved copy from work-array memory that now holds other data (the segment
+    pointers of M:1246-1268 moved); here the Jacobian is re-evaluated instead.  Checked against
+    the oracle's mf = -21 run of the same scenario (no saved copy, so no aliasing): same orders,
+    solution within tolerance, counters within 2 %."""
+    B = _B()
+    nsys = 96
+    par, y0 = B.batches.robertson_batch(nsys), ROB["y0"]
+    touts = rob_touts()[:7]
+    rtol, atol, rtol2, atol2 = [1e-4], [1e-8, 1e-14, 1e-6], [1e-5], [1e-9, 1e-15, 1e-7]
+    iw1 = _iopts(mxstep=5000)
+    iw2 = iw1.copy()
+    iw2[4] = 2
+    ref = O.batch_solve2("robertson", par, y0, 0.0, touts, 3, rtol, atol, -21, rtol2, atol2, itol=2,
+                         iopt=1, mxstep=5000, mxstep2=5000, maxord2=2, hmax2=3.0e3, pow_mode=1)
+    got = gpu_schedule("robertson", par, y0, 0.0, touts, rtol, atol, 21, 2, strict=True, iopt=1,
+                       iwork_opts=iw1, per_call=True,
+                       phase2=dict(nsplit=3, rtol=rtol2, atol=atol2, itol=2, itask=1, iopt=1,
+                                   rwork_opts=_ropts(hmax=3.0e3), iwork_opts=iw2))
+    assert (got["istate"] == 2).all()
+    assert (got["istats"][:, 3:, O.ISTAT["nqu"]] <= 2).all()
+    w = weighted_err(got["y"][:, 3:], ref["y"][:, 3:], 1e-5, atol2)
+    assert np.percentile(w, 99) <= 10.0, float(np.percentile(w, 99))
+    # (nfe / nni / nje are not comparable between mf = 21 and mf = -21: without a saved copy
+    # every matrix update re-evaluates J at the current y)
+    a = got["istats"][:, -1, O.ISTAT["nst"]].astype(np.int64).sum()
+    b = ref["istats"][:, -1, O.ISTAT["nst"]].astype(np.int64).sum()
+    assert abs(a - b) <= 0.03 * b, (a, b)
 
 
 # ------------------------------------------------------------------ warp-per-system ------
