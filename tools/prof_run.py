@@ -17,10 +17,23 @@ ap.add_argument("--nsys", type=int, default=1 << 17)
 ap.add_argument("--tol", default="headline")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--mf", type=int, default=21)
+ap.add_argument("--sort", default="none", help="none | lex | morton: order the systems by their parameters")
 a = ap.parse_args()
 tol = batches.ROBERTSON_TOL_HEADLINE if a.tol == "headline" else batches.ROBERTSON_TOL_REF
 touts = batches.robertson_touts()
 par = batches.robertson_batch(a.nsys)
+if a.sort != "none":
+    q = (par - par.min(axis=0)) / (par.max(axis=0) - par.min(axis=0) + 1e-300)
+    if a.sort == "lex":
+        order = np.lexsort((q[:, 2], q[:, 1], q[:, 0]))
+    else:
+        b = np.minimum((q * 1024).astype(np.uint64), 1023)
+        key = np.zeros(a.nsys, dtype=np.uint64)
+        for bit in range(10):
+            for d in range(3):
+                key |= ((b[:, d] >> np.uint64(bit)) & np.uint64(1)) << np.uint64(3 * bit + d)
+        order = np.argsort(key, kind="stable")
+    par = np.ascontiguousarray(par[order])
 s = B.dvode_t().initialize("robertson", a.nsys, par)
 for r in range(a.reps):
     y = np.tile(np.array(batches.ROBERTSON_Y0), (a.nsys, 1))
