@@ -59,6 +59,8 @@ def _load():
     lib.bvode_state_bytes.restype = C.c_longlong
     lib.bvode_dvsrco.argtypes = [vp, vp, C.c_int]
     lib.bvode_last_launch_count.argtypes = [vp]
+    lib.bvode_istate_summary.argtypes = [vp, vp]
+    lib.bvode_format_message.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     lib.bvode_measure_fp64_peak.argtypes = [C.c_int, dp]
     return lib
 
@@ -218,6 +220,24 @@ class dvode_t:
 
     def last_launch_count(self):
         return _lib.bvode_last_launch_count(self._h)
+
+    # -- xerrwd (M:3351-3394) as a host-side message stream --------------------------------
+    def istate_summary(self):
+        """{istate: number of systems} of the last host-buffer solve (0 = no error)."""
+        c = np.zeros(8, dtype=np.int32)
+        _check(_lib.bvode_istate_summary(self._h, _ptr(c)))
+        out = {0: int(c[0])}
+        out.update({-k: int(c[k]) for k in range(1, 7)})
+        out["other"] = int(c[7])
+        return out
+
+    def message(self, sys):
+        """The reference's xerrwd text for system `sys` ('' when it ended without error)."""
+        buf = C.create_string_buffer(1024)
+        n = _lib.bvode_format_message(self._h, int(sys), buf, 1024)
+        if n < 0:
+            _check(n)
+        return buf.value.decode()
 
     def _chk_arrays(self, y, t, istate, rwork, iwork, lrw, liw):
         if self._h is None:

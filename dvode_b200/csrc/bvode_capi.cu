@@ -5,6 +5,7 @@
 #include "bvode_internal.h"
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,6 +67,7 @@ struct bvode_solver {
     // state (allocated at the first istate = 1 call, when mf / ml / mu are known)
     int mf = 0, ml = 0, mu = 0;
     int maxord = 0;  // of the last call (istate = 3 may change it)
+    int mxstep = 500;
     size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
     double *d_state = nullptr;
     int *i_state = nullptr;
@@ -442,6 +444,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
                     itask != 1 || n3 != 0);
     if (rc != BVODE_OK) return rc;
     s->maxord = c.o.maxord;
+    s->mxstep = c.o.mxstep;
     // device -> host
     k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_y, s->d_aos, nsys, neq);
     s->last_launches++;
@@ -611,6 +614,94 @@ int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
         p += q.n;
     }
     return BVODE_OK;
+}
+
+// ---- xerrwd (M:3351-3394) as a host-side message stream --------------------------------
+// The kernels never print.  The reference's messages for the per-system outcomes are rebuilt
+// here from istate and the optional outputs (tcur, hcur, tolsf, imxer) of the last solve.
+int bvode_istate_summary(bvode_solver *s, int counts[8]) {
+    if (!s || !counts) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<int> ist((size_t)s->nsys);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(ist.data(), s->d_istate, sizeof(int) * ist.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; k++) counts[k] = 0;
+    for (int v : ist) {
+        if (v >= 1 && v <= 3) counts[0]++;        // 1, 2 (3 never comes back): no error
+        else if (v <= -1 && v >= -6) counts[-v]++;
+        else counts[7]++;
+    }
+    return BVODE_OK;
+}
+
+// Fortran D21.13 edit descriptor: 0.dddddddddddddD+ee
+static std::string fmt_d21_13(double x) {
+    char buf[64];
+    if (x == 0.0) return "   0.0000000000000D+00";
+    snprintf(buf, sizeof buf, "%.12E", fabs(x));
+    std::string m(buf);
+    const size_t e = m.find('E');
+    int ex = atoi(m.c_str() + e + 1) + 1;
+    std::string digits = m.substr(0, 1) + m.substr(2, e - 2);
+    snprintf(buf, sizeof buf, "%s0.%sD%c%02d", x < 0 ? "-" : "", digits.c_str(), ex < 0 ? '-' : '+', abs(ex));
+    std::string out(buf);
+    while (out.size() < 21) out = " " + out;
+    return out;
+}
+
+int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen) {
+    if (!s || !buf || buflen < 1 || sys < 0 || sys >= s->nsys) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const size_t ns = (size_t)s->nsys;
+    int ist = 0, imxer = 0;
+    double r[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(&ist, s->d_istate + sys, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; k++)
+        CUDA_TRY(cudaMemcpy(&r[k], s->d_rout + k * ns + sys, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&imxer, s->d_iout + 5 * ns + sys, sizeof(int), cudaMemcpyDeviceToHost));
+    const double hcur = r[1], tcur = r[2], tolsf = r[3];
+    auto i1 = [](int v) { char b[64]; snprintf(b, sizeof b, "      in above message,  i1 =%10d\n", v); return std::string(b); };
+    auto r1 = [](double a) { return "      in above message,  r1 =" + fmt_d21_13(a) + "\n"; };
+    auto r12 = [](double a, double b) { return "      in above message,  r1 =" + fmt_d21_13(a) + "   r2 =" + fmt_d21_13(b) + "\n"; };
+    std::string m;
+    switch (ist) {
+    case -1:  // M:1506-1509
+        m = "dvode--  at current t (=r1), mxstep (=i1) steps\n      taken on this call before reaching tout\n" +
+            i1(s->mxstep) + r1(tcur);
+        break;
+    case -2:  // M:1637-1640
+        m = "dvode--  at t (=r1), too much accuracy requested\n      for precision of machine:   see tolsf (=r2)\n" +
+            r12(tcur, tolsf);
+        break;
+    case -3:  // M:1081-1461: the device only sees messages 21, 22, 23-25, 26, 27
+        if (tolsf != 0.0)
+            m = "dvode--  at start of problem, too much accuracy\n      requested for precision of machine:   see tolsf (=r1)\n" + r1(tolsf);
+        else
+            m = "dvode--  illegal input detected on the device (ewt <= 0, tout too close to t to start,\n"
+                "      or itask / tout / tcrit inconsistent with the current t: messages 21-25, 27)\n";
+        break;
+    case -4:  // M:1560-1563
+        m = "dvode--  at t(=r1) and step size h(=r2), the error\n      test failed repeatedly or with abs(h) = hmin\n" +
+            r12(tcur, hcur);
+        break;
+    case -5:  // M:1570-1575
+        m = "dvode--  at t (=r1) and step size h (=r2), the\n      corrector convergence failed repeatedly\n"
+            "      or with abs(h) = hmin\n" + r12(tcur, hcur);
+        break;
+    case -6:  // M:1689-1690 (the index and value of the offending weight are not kept)
+        m = "dvode--  at t (=r1), ewt(i1) has become r2 <= 0.\n" + r1(tcur);
+        break;
+    default:
+        m = "";
+    }
+    if ((ist == -4 || ist == -5) && imxer > 0) {
+        char b[96];
+        snprintf(b, sizeof b, "      largest weighted local error: component imxer =%6d\n", imxer);
+        m += b;
+    }
+    snprintf(buf, (size_t)buflen, "%s", m.c_str());
+    return (int)m.size();
 }
 
 int bvode_measure_fp64_peak(int device, double *tflops) {

@@ -105,11 +105,26 @@ module bvode_module
          integer(c_int), value :: job
          integer(c_int) :: rc
       end function
+      !> xerrwd (dvode_module.F90:3351) as a host-side message stream
+      function bvode_istate_summary(handle, counts) bind(C, name='bvode_istate_summary') result(rc)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), intent(out) :: counts(8)     !! (ok, istate=-1, ..., istate=-6, other)
+         integer(c_int) :: rc
+      end function
+      function bvode_format_message(handle, sys, buf, buflen) bind(C, name='bvode_format_message') result(n)
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: handle
+         integer(c_int), value :: sys, buflen         !! sys is 0-based
+         character(kind=c_char), intent(out) :: buf(*)
+         integer(c_int) :: n
+      end function
    end interface
 
    public :: bvode_problem_lookup, bvode_problem_info, bvode_create, bvode_destroy, &
              bvode_last_error, bvode_set_params, bvode_solve, bvode_solve_schedule, &
-             bvode_dvindy, bvode_get_stats, bvode_state_bytes, bvode_dvsrco
+             bvode_dvindy, bvode_get_stats, bvode_state_bytes, bvode_dvsrco, &
+             bvode_istate_summary, bvode_format_message
 
    !> Batched counterpart of `type(dvode_t)` (dvode_module.F90:251-314).
    type, public :: bvode_t

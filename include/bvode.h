@@ -2,7 +2,7 @@
  * bvode.h -- C ABI of the B200-native batched VODE integrator.
  *
  * Drop-in boundary for ONE path of jacobwilliams/dvode: "integrate a batch of
- * independent stiff ODE systems with VODE's variable-order, variable-step BDF".
+ * independent ODE systems with VODE's variable-order, variable-step BDF / Adams methods".
  * Every entry point names the reference interface it replaces (file:line into
  * /root/reference; M = src/dvode_module.F90).  Plain C types only; all pointers
  * are HOST pointers unless the name says `_device`.
@@ -45,7 +45,7 @@ typedef struct bvode_solver bvode_solver;
 enum {
     BVODE_OK = 0,
     BVODE_EINVAL = -1,    /* illegal argument (the reference's istate = -3 input checks, M:1120-1303) */
-    BVODE_ENOTIMPL = -2,  /* legal in the reference but not built yet (see DESIGN.md scope table) */
+    BVODE_ENOTIMPL = -2,  /* legal in the reference but not built (e.g. istate = 3 with another mf) */
     BVODE_ECUDA = -3,     /* CUDA runtime error; bvode_last_error() has the text */
     BVODE_ENOMEM = -4,
     BVODE_EISTATE = -5    /* negative istate on input: M:1083-1089 aborts the run here */
@@ -73,15 +73,22 @@ BVODE_API int bvode_set_params(bvode_solver *s, const double *params);
 
 /* ---- solve == dvode (M:604-605), for the whole batch.  Same argument meaning as the
  * reference.  tout: one value for the batch (tout_per_system = 0) or tout[nsys] (= 1).
- * Built so far: itask = 1; istate in {1, 2}; mf in {21, 22, -21, -22} (thread-per-system
- * problems) and {22, 24, 25, ...} for the warp-per-system problems (see bvode_problem_info). */
+ *   itask  1-5 (M:811-831); 4 and 5 read tcrit = rwork(1) of row 0.
+ *   istate 1 (first call), 2 (continue), 3 (continue with changed itol / rtol / atol / itask /
+ *          optional inputs incl. a lower maxord; must then be 3 for every system; mf, ml, mu
+ *          and neq cannot change -- they select the kernel and the state layout).
+ *   mf     jsv*(10*meth + miter), M:999-1046: meth 1 (Adams) or 2 (BDF); miter 0 (functional
+ *          iteration), 1 / 2 (dense analytic / finite-difference J; thread-per-system problems,
+ *          miter 2 also for the dense warp problem), 3 (diagonal approximation), 4 / 5 (banded
+ *          analytic / FD J, band problems); mf < 0 = no saved Jacobian copy. */
 BVODE_API int bvode_solve(bvode_solver *s, int neq, double *y, double *t, const double *tout,
                 int tout_per_system, int itol, const double *rtol, const double *atol,
                 int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw,
                 int mf);
 
 /* The reference's usage loop (test/example.f90:56-66: nout calls with increasing tout) as ONE
- * call and one kernel launch: equivalent to
+ * call and one kernel launch (itask 1 or 4; itask 2, 3, 5 return at mesh points and are used one
+ * call at a time through bvode_solve): equivalent to
  *     for k in 0..nout-1: bvode_solve(..., tout = touts[k], ...); y_out[k] = y
  * including the per-call mxstep budget.  y holds y0 on entry (istate = 1) and the last output
  * on return; y_out[nout][nsys][neq] receives every output point (may be NULL). */
@@ -104,6 +111,15 @@ BVODE_API int bvode_get_stats(bvode_solver *s, double *rout, int *iout);
  * host buffer of bvode_state_bytes() bytes: checkpoint / resume. */
 BVODE_API long long bvode_state_bytes(const bvode_solver *s);
 BVODE_API int bvode_dvsrco(bvode_solver *s, void *sav, int job);
+
+/* ---- xerrwd (M:3351-3394) as a host-side message stream.  The kernels never print and never
+ * stop; the per-system outcome is istate.  bvode_istate_summary compacts the batch: counts[0] =
+ * systems without error (istate 1 / 2), counts[k] = systems with istate = -k (k = 1..6),
+ * counts[7] = anything else.  bvode_format_message writes the reference's message text for
+ * system `sys` (its "in above message, r1 = ..." lines filled from tcur / hcur / tolsf) into buf
+ * and returns its length (0 when that system ended without error). */
+BVODE_API int bvode_istate_summary(bvode_solver *s, int counts[8]);
+BVODE_API int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen);
 
 /* ---- device-resident variants (inputs already in HBM; used for the kernel-only metric).
  * Layout on the device is structure-of-arrays: y_device[neq][nsys], params_device[npar][nsys],

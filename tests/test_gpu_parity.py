@@ -358,6 +358,16 @@ def test_error_paths_match_reference_semantics():
     assert np.array_equal(iwork[:, 10:22], ref["istats"][:, 0])
     assert np.array_equal(rwork[:, 10:14], ref["rstats"][:, 0])
     assert (iwork[istate == -1, 10] == 500).all()
+    # the xerrwd text of the reference (M:1506-1509), rebuilt on the host from istate / tcur
+    summ = s.istate_summary()
+    assert summ[-1] == int((istate == -1).sum()) and summ[0] == int((istate == 2).sum())
+    k = int(np.flatnonzero(istate == -1)[0])
+    msg = s.message(k)
+    assert msg.startswith("dvode--  at current t (=r1), mxstep (=i1) steps\n      taken on this call before reaching tout")
+    assert "in above message,  i1 =       500" in msg
+    mant, ex = ("%.12E" % rwork[k, 12]).split("E")
+    d21 = "0.%s%sD%+03d" % (mant[0], mant[2:], int(ex) + 1)
+    assert ("in above message,  r1 =  " + d21) in msg, (msg, d21)
     # with iopt = 1, mxstep = 100000 it gets there
     y[:] = [1.0, 0.0, 0.0]
     t[:] = 0.0
