@@ -13,16 +13,18 @@
 #include <vector>
 
 // one entry per (build, problem), each from its own translation unit (bvode_registry.cu)
-#define BVODE_NPROBLEMS 4
+#define BVODE_NPROBLEMS 5
 extern "C" {
 const ProblemEntry *bvode_entry_fast_0(void);
 const ProblemEntry *bvode_entry_fast_1(void);
 const ProblemEntry *bvode_entry_fast_2(void);
 const ProblemEntry *bvode_entry_fast_3(void);
+const ProblemEntry *bvode_entry_fast_4(void);
 const ProblemEntry *bvode_entry_strict_0(void);
 const ProblemEntry *bvode_entry_strict_1(void);
 const ProblemEntry *bvode_entry_strict_2(void);
 const ProblemEntry *bvode_entry_strict_3(void);
+const ProblemEntry *bvode_entry_strict_4(void);
 }
 static const ProblemEntry *bvode_registry_fast(int *n) {
     static ProblemEntry tab[BVODE_NPROBLEMS];
@@ -30,6 +32,7 @@ static const ProblemEntry *bvode_registry_fast(int *n) {
     if (!init) {
         tab[0] = *bvode_entry_fast_0(); tab[1] = *bvode_entry_fast_1();
         tab[2] = *bvode_entry_fast_2(); tab[3] = *bvode_entry_fast_3();
+        tab[4] = *bvode_entry_fast_4();
         init = true;
     }
     *n = BVODE_NPROBLEMS;
@@ -41,6 +44,7 @@ static const ProblemEntry *bvode_registry_strict(int *n) {
     if (!init) {
         tab[0] = *bvode_entry_strict_0(); tab[1] = *bvode_entry_strict_1();
         tab[2] = *bvode_entry_strict_2(); tab[3] = *bvode_entry_strict_3();
+        tab[4] = *bvode_entry_strict_4();
         init = true;
     }
     *n = BVODE_NPROBLEMS;

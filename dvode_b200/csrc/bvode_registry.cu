@@ -1,6 +1,6 @@
 // bvode_registry.cu -- instantiates every kernel of ONE problem for one build and exports its
 // table entry.  Compiled once per (build, problem): -DBVODE_STRICT=0 (fast, the product) or
-// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..3.
+// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..4.
 #include "bvode_kernels.cuh"
 
 #ifndef BVODE_UNIT
@@ -16,6 +16,8 @@ static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp", VanDerPol);
 static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection", Advection25);
 #elif BVODE_UNIT == 3
 static const ProblemEntry kEntry = BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32);
+#elif BVODE_UNIT == 4
+static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp_maxnorm", VanDerPolMaxNorm);
 #endif
 }  // namespace BVODE_NS
 

@@ -133,8 +133,15 @@ struct ThreadPolicy {
         for (int i = 0; i < N; i++) v.i(e.hot.ipvt(i));
     }
 
-    // dvnorm_default, M:3295-3311: sequential sum in index order, like the reference.
+    // dewset (M:3238-3273) for one component, or the problem's own (M:431-467)
+    BV_DEV static double ewt_of(int i, double yi, double rtol, double atol) {
+        if constexpr (HasUserEwt<PROB>::value) return PROB::ewt(i, yi, rtol, atol);
+        else return rtol * fabs(yi) + atol;
+    }
+    // dvnorm_default, M:3295-3311: sequential sum in index order, like the reference
+    // (or the problem's own norm, M:468-503).
     BV_DEV static double norm(const double (&v)[N], const double (&w)[N]) {
+        if constexpr (HasUserNorm<PROB>::value) return PROB::norm(v, w);
         double sum = 0.0;
 #pragma unroll
         for (int i = 0; i < N; i++) {
@@ -150,6 +157,10 @@ struct ThreadPolicy {
 #if !BVODE_STRICT
     // mean square (norm^2) -- the fast build tests squares and keeps sqrt off the main path
     BV_DEV static double msq(const double (&v)[N], const double (&w)[N]) {
+        if constexpr (HasUserNorm<PROB>::value) {  // a user norm is only known as a norm
+            const double nv = PROB::norm(v, w);
+            return nv * nv;
+        }
         double sum = 0.0;
 #pragma unroll
         for (int i = 0; i < N; i++) {

@@ -65,6 +65,9 @@ struct WarpCommon {
         BV_DEV double atol(int) const { return a; }
     };
 
+    // dewset_default for this lane's component, M:3238-3273 (user-supplied weights / norms
+    // are a thread-per-system feature so far)
+    BV_DEV static double ewt_of(int, double yi, double rtol, double atol) { return rtol * fabs(yi) + atol; }
     // dvnorm_default, M:3295-3311.  Lanes >= N carry v = 0.
     BV_DEV static double norm(const double (&v)[1], const double (&w)[1]) {
         const double p = v[0] * w[0];

@@ -47,6 +47,28 @@ struct VanDerPol {
     }
 };
 
+// Van der Pol with USER-SUPPLIED error weights and norm: the optional `dewset` / `dvnorm`
+// procedure arguments of initialize (M:431-503) as two more members of the functor.
+//   ewt (i, y_i, rtol_i, atol_i)  replaces dewset_default (M:3238-3273), one component
+//   norm(v, w)                    replaces dvnorm_default (M:3295-3311)
+// Here: ewt_i = rtol_i*max(|y_i|, 1) + atol_i and the max norm.
+struct VanDerPolMaxNorm : VanDerPol {
+    BV_DEV static double ewt(int, double yi, double rtol, double atol) {
+        double ay = fabs(yi);
+        if (ay < 1.0) ay = 1.0;
+        return rtol * ay + atol;
+    }
+    BV_DEV static double norm(const double (&v)[2], const double (&w)[2]) {
+        double vm = 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double p = fabs(v[i] * w[i]);
+            if (p > vm) vm = p;
+        }
+        return vm;
+    }
+};
+
 }  // namespace BVODE_NS
 
 // ----------------------------------------------------------------------------------------

@@ -325,6 +325,17 @@ static __device__ __noinline__ int choose_ratio_f64(double xq, double xm, double
 }
 #endif
 
+// Detection of a problem's optional members `ewt` / `norm`: the user-replaceable dewset /
+// dvnorm of initialize (M:431-503).
+template <class P, class = void>
+struct HasUserEwt { static constexpr bool value = false; };
+template <class P>
+struct HasUserEwt<P, decltype((void)&P::ewt)> { static constexpr bool value = true; };
+template <class P, class = void>
+struct HasUserNorm { static constexpr bool value = false; };
+template <class P>
+struct HasUserNorm<P, decltype((void)&P::norm)> { static constexpr bool value = true; };
+
 // =================================================================== Engine =====
 // POL provides:
 //   Prob, N (equations), NLOC (vector elements held by this thread), MITER
@@ -370,7 +381,7 @@ struct Engine {
     BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
         double e[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) e[i] = tol.rtol(i) * fabs(hot.yh(0, i)) + tol.atol(i);
+        for (int i = 0; i < NLOC; i++) e[i] = POL::ewt_of(i, hot.yh(0, i), tol.rtol(i), tol.atol(i));
         bad = POL::any_le_zero(e);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) ewt[i] = qrcp(e[i]);

@@ -292,8 +292,8 @@ void dvo_dgbsl(const double *abd, int lda, int n, int ml, int mu, const int *ipv
 
 /* ------------------------------------------------ dewset / dvnorm -------- */
 /* M:3238-3273 */
-static void dewset(int n, int itol, const double *rtol, const double *atol,
-                   const double *ycur, double *ewt)
+static void dewset_default(int n, int itol, const double *rtol, const double *atol,
+                           const double *ycur, double *ewt)
 {
     int i;
     switch (itol) {
@@ -306,7 +306,7 @@ static void dewset(int n, int itol, const double *rtol, const double *atol,
 }
 
 /* M:3295-3311 */
-static double dvnorm(int n, const double *v, const double *w)
+static double dvnorm_default(int n, const double *v, const double *w)
 {
     double sum = ZERO;
     for (int i = 0; i < n; i++) {
@@ -316,6 +316,14 @@ static double dvnorm(int n, const double *v, const double *w)
     return sqrt(sum / (double)n);
 }
 
+/* the procedure pointers of dvode_t (M:305-306): user routine or default */
+#define dewset(n, itol, rtol, atol, ycur, ewt)                                        \
+    do {                                                                              \
+        if (me->dewset) me->dewset(me->ctx, (n), (itol), (rtol), (atol), (ycur), (ewt)); \
+        else dewset_default((n), (itol), (rtol), (atol), (ycur), (ewt));              \
+    } while (0)
+#define dvnorm(n, v, w) (me->dvnorm ? me->dvnorm(me->ctx, (n), (v), (w)) : dvnorm_default((n), (v), (w)))
+
 /* ------------------------------------------------------------- init ------ */
 void dvo_initialize(dvo_solver *s, dvo_f_fn f, dvo_jac_fn jac, void *ctx)
 {
@@ -323,6 +331,12 @@ void dvo_initialize(dvo_solver *s, dvo_f_fn f, dvo_jac_fn jac, void *ctx)
     s->f = f;
     s->jac = jac;
     s->ctx = ctx;
+}
+
+void dvo_set_user_norms(dvo_solver *s, dvo_ewt_fn ew, dvo_norm_fn nm)
+{
+    s->dewset = ew;
+    s->dvnorm = nm;
 }
 
 void dvo_dvsrco(dvo_solver *s, dvo_solver *sav, int job)

@@ -26,6 +26,10 @@ extern "C" {
 typedef void (*dvo_f_fn)(void *ctx, int neq, double t, const double *y, double *ydot);
 typedef void (*dvo_jac_fn)(void *ctx, int neq, double t, double *y, int ml, int mu,
                            double *pd, int nrowpd);
+/* user-replaceable error-weight and norm routines (M:431-503) */
+typedef void (*dvo_ewt_fn)(void *ctx, int n, int itol, const double *rtol, const double *atol,
+                           const double *ycur, double *ewt);
+typedef double (*dvo_norm_fn)(void *ctx, int n, const double *v, const double *w);
 
 /* dvode_data_t (M:40-153) + dvode_t (M:251-270) */
 typedef struct dvo_solver {
@@ -42,13 +46,17 @@ typedef struct dvo_solver {
     double etaq, etaqm1;
     dvo_f_fn f;
     dvo_jac_fn jac;
+    dvo_ewt_fn dewset;   /* NULL = dewset_default, M:3238 */
+    dvo_norm_fn dvnorm;  /* NULL = dvnorm_default, M:3295 */
     void *ctx;
     int last_msg;     /* number of the last xerrwd message (M:3351), 0 if none */
     int pow_mode;     /* 0 = libm pow (reference semantics); 1 = portable pow (dvo_ppow) */
 } dvo_solver;
 
-/* initialize, M:377-505 (dewset/dvnorm overrides are not part of the oracle) */
+/* initialize, M:377-505; the optional dewset / dvnorm procedure arguments (M:431-503) are set
+ * with dvo_set_user_norms (NULL keeps the default) */
 void dvo_initialize(dvo_solver *s, dvo_f_fn f, dvo_jac_fn jac, void *ctx);
+void dvo_set_user_norms(dvo_solver *s, dvo_ewt_fn dewset, dvo_norm_fn dvnorm);
 
 /* dvode / solve, M:604-1725.  rwork and iwork are 1-based in the reference;
  * here the caller passes plain C arrays of length lrw / liw and slot k of the

@@ -66,6 +66,31 @@ static void vdp_jac(void *ctx, int neq, double t, double *y, int ml, int mu, dou
     PD(2, 2) = p[0] * (1.0 - y[0] * y[0]);
 }
 
+/* Van der Pol with USER error weights and norm (initialize's optional dewset / dvnorm,
+ * M:431-503): ewt_i = rtol_i*max(|y_i|, 1) + atol_i, max norm. */
+static void vdpm_dewset(void *ctx, int n, int itol, const double *rtol, const double *atol,
+                        const double *ycur, double *ewt)
+{
+    (void)ctx;
+    for (int i = 0; i < n; i++) {
+        double r = (itol >= 3) ? rtol[i] : rtol[0];
+        double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        double ay = fabs(ycur[i]);
+        if (ay < 1.0) ay = 1.0;
+        ewt[i] = r * ay + a;
+    }
+}
+static double vdpm_dvnorm(void *ctx, int n, const double *v, const double *w)
+{
+    double vm = 0.0;
+    (void)ctx;
+    for (int i = 0; i < n; i++) {
+        double p = fabs(v[i] * w[i]);
+        if (p > vm) vm = p;
+    }
+    return vm;
+}
+
 /* ---------------------------------------------------- banded advection --- */
 /* par = (alph1, alph2), reference 1, 1; ng = 5 (dvdemo.f90:236-238) */
 #define NG 5
@@ -128,6 +153,7 @@ int dvo_problem_info(int problem, int *neq, int *npar)
     case 1: *neq = 2; *npar = 1; return 0;
     case 2: *neq = NG * NG; *npar = 2; return 0;
     case 3: *neq = BVODE_MECH_NS; *npar = BVODE_MECH_NR; return 0;
+    case 4: *neq = 2; *npar = 1; return 0;
     default: return -1;
     }
 }
@@ -139,6 +165,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     case 1: *f = vdp_f; *jac = vdp_jac; return 0;
     case 2: *f = adv_f; *jac = adv_jac; return 0;
     case 3: *f = mech_f; *jac = NULL; return 0;
+    case 4: *f = vdp_f; *jac = vdp_jac; return 0;
     default: return -1;
     }
 }
@@ -199,6 +226,7 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
             dvo_solver sol;
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
+            if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -267,6 +295,7 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
             dvo_solver sol;
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
+            if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -325,6 +354,7 @@ int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const doubl
     memcpy(y, y0, sizeof(double) * (size_t)neq);
     dvo_solver sol;
     dvo_initialize(&sol, f, jac, par);
+    if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
     sol.pow_mode = cfg->pow_mode;
     iwork[0] = cfg->ml; iwork[1] = cfg->mu;
     if (cfg->iopt) {

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 def test_registry_and_python_mirror_import():
     import dvode_b200 as B
     names = B.problem_names()
-    assert "robertson" in names and "vdp" in names
+    assert "robertson" in names and "vdp" in names and "vdp_maxnorm" in names
     assert B.problem_info("robertson")[1:] == (3, 3)
     assert B.problem_info("vdp")[1:] == (2, 1)
 

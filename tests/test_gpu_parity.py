@@ -90,6 +90,11 @@ def weighted_err(y, yref, rtol, atol):
     return np.abs(y - yref) / (rtol * np.abs(yref) + atol)
 
 
+def _same(a, b, keys=("y", "t", "istate", "istats", "rstats")):
+    for k in keys:
+        assert np.array_equal(a[k], b[k]), k
+
+
 ROB = dict(y0=[1.0, 0.0, 0.0], t0=0.0)
 
 
@@ -277,6 +282,32 @@ def test_all_method_flags_fast_batch_counters(problem, mfs):
             (problem, mf, float(np.median(w)), float(np.median(w0)))
 
 
+@pytest.mark.parametrize("mf", [10, 21, 22, 23])
+def test_user_supplied_dewset_and_dvnorm(mf):
+    """initialize's optional dewset / dvnorm procedure arguments (M:431-503): problem
+    `vdp_maxnorm` supplies ewt_i = rtol*max(|y_i|, 1) + atol and the max norm as members of its
+    functor.  Strict build bit for bit against the oracle running the same user routines; the
+    result differs from the default-norm run (so the user routines really are in use); fast build
+    within 2 % on the batch counters."""
+    B = _B()
+    nsys = 128
+    par = B.batches.perturbed((3.0,), nsys, 0.1, B.batches.SEED, 0)
+    touts = [1.39283880203 + k * 2.214773875 for k in range(4)]
+    ref = O.batch_solve("vdp_maxnorm", par, [2.0, 0.0], 0.0, touts, 1e-5, 1e-6, mf, itol=1, pow_mode=1)
+    dflt = O.batch_solve("vdp", par, [2.0, 0.0], 0.0, touts, 1e-5, 1e-6, mf, itol=1, pow_mode=1)
+    assert not np.array_equal(ref["istats"][:, -1], dflt["istats"][:, -1])
+    g = gpu_schedule("vdp_maxnorm", par, [2.0, 0.0], 0.0, touts, [1e-5], [1e-6], mf, 1, strict=True,
+                     per_call=True)
+    _same(g, ref)
+    f = gpu_schedule("vdp_maxnorm", par, [2.0, 0.0], 0.0, touts, [1e-5], [1e-6], mf, 1)
+    ref0 = O.batch_solve("vdp_maxnorm", par, [2.0, 0.0], 0.0, touts, 1e-5, 1e-6, mf, itol=1)
+    assert (f["istate"][:, -1] == 2).all()
+    for k in ("nst", "nfe"):
+        a = int(f["istats"][:, -1, O.ISTAT[k]].astype(np.int64).sum())
+        b = int(ref0["istats"][:, -1, O.ISTAT[k]].astype(np.int64).sum())
+        assert abs(a - b) <= 0.02 * b, (mf, k, a, b)
+
+
 def test_dvindy_matches_oracle():
     B = _B()
     nsys = 64
@@ -406,11 +437,6 @@ def _iopts(ml=0, mu=0, maxord=0, mxstep=0):
     iw = np.zeros(30, dtype=np.int32)
     iw[0], iw[1], iw[4], iw[5] = ml, mu, maxord, mxstep
     return iw
-
-
-def _same(a, b, keys=("y", "t", "istate", "istats", "rstats")):
-    for k in keys:
-        assert np.array_equal(a[k], b[k]), k
 
 
 @pytest.mark.parametrize("itask", [2, 3, 4, 5])
