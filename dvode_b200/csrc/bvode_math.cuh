@@ -41,6 +41,25 @@ BV_DEV double powi(double x, int m) {
     return m < 0 ? 1.0 / y : y;
 }
 
+// x**m for 2 <= m <= MAXP.  Strict build: powi (the reference's operation order).  Fast build,
+// small MAXP (BDF): straight-line products and a select -- no divergent loop in the step loop.
+template <int MAXP>
+BV_DEV double powi_small(double x, int m) {
+#if !BVODE_STRICT
+    if constexpr (MAXP <= 7) {
+        const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+        double r = x2;
+        r = (m == 3) ? x3 : r;
+        r = (m == 4) ? x4 : r;
+        r = (m == 5) ? x4 * x : r;
+        r = (m == 6) ? x3 * x3 : r;
+        r = (m == 7) ? x4 * x3 : r;
+        return r;
+    }
+#endif
+    return powi(x, m);
+}
+
 // Portable x**y, x > 0: same operation sequence as dvo_ppow in oracle/dvode_oracle.c.
 // Only meaningful bit for bit when compiled with -fmad=false.
 static __device__ __noinline__ double ppow(double x, double y) {

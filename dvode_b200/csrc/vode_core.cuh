@@ -130,22 +130,40 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const double t2 = 1.0 + (double)nq * t1;
     const double elL = pick<2, kLmaxBdf>(el, L);
     tq[2] = fabs(qdiv(alph0 * t2, t1));
-    tq[5] = fabs(qdiv(t2, qdiv(elL * rxi, rxis)));
     tq[1] = 0.0;
     tq[3] = 0.0;
+#if BVODE_STRICT
+    tq[5] = fabs(t2 / (elL * rxi / rxis));
     if (c.nqwait == 1) {
-        const double cnqm1 = qdiv(rxis, elL);
+        const double cnqm1 = rxis / elL;
         const double t3 = alph0 + recip_int(nq);
         const double t4 = ahatn0 + rxi;
-        double elp = qdiv(t3, 1.0 - t4 + t3);
-        tq[1] = fabs(qdiv(elp, cnqm1));
+        double elp = t3 / (1.0 - t4 + t3);
+        tq[1] = fabs(elp / cnqm1);
+        hsum = hsum + pick<1, kLmaxBdf>(tauv, nq);
+        rxi = h / hsum;
+        const double t5 = alph0 - recip_int(nq + 1);
+        const double t6 = ahatn0 - rxi;
+        elp = t2 / (1.0 - t6 + t5);
+        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
+    }
+#else
+    // fast build: the nested quotients of M:2478-2489 as single quotients
+    //   t2 / (elL*rxi/rxis)             = t2*rxis / (elL*rxi)
+    //   (t3/(1-t4+t3)) / (rxis/elL)     = t3*elL / ((1-t4+t3)*rxis)
+    //   (t2/(1-t6+t5)) * rxi*(L+1)*t5   = t2*rxi*(L+1)*t5 / (1-t6+t5)
+    tq[5] = fabs(qdiv(t2 * rxis, elL * rxi));
+    if (c.nqwait == 1) {
+        const double t3 = alph0 + recip_int(nq);
+        const double t4 = ahatn0 + rxi;
+        tq[1] = fabs(qdiv(t3 * elL, (1.0 - t4 + t3) * rxis));
         hsum = hsum + pick<1, kLmaxBdf>(tauv, nq);
         rxi = qdiv(h, hsum);
         const double t5 = alph0 - recip_int(nq + 1);
         const double t6 = ahatn0 - rxi;
-        elp = qdiv(t2, 1.0 - t6 + t5);
-        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
+        tq[3] = fabs(qdiv(t2 * rxi * ((double)L + 1.0) * t5, 1.0 - t6 + t5));
     }
+#endif
     tq[4] = 0.1 * tq[2];
 #pragma unroll
     for (int i = 1; i <= kLmaxBdf; i++) hot.el(i) = el[i];
@@ -175,6 +193,9 @@ BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf
     double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
     double hsum = up ? c.hscal : 0.0;
     const int jmax = up ? nq - 1 : nq - 2;
+#if !BVODE_STRICT
+    const double rhscal = qrcp(c.hscal);
+#endif
     double tauv[kLmaxBdf + 1];
 #pragma unroll
     for (int i = 1; i <= kLmaxBdf; i++) tauv[i] = hot.tau(i);
@@ -182,11 +203,17 @@ BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf
     for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
         if (j <= jmax) {
             hsum = hsum + (up ? tauv[j + 1] : tauv[j]);
-            const double xi = qdiv(hsum, c.hscal);
+#if BVODE_STRICT
+            const double xi = hsum / c.hscal;
+            const double rxi = up ? 1.0 / xi : 0.0;
+#else
+            const double xi = hsum * rhscal;  // one reciprocal of hscal, and 1/xi = hscal/hsum
+            const double rxi = up ? c.hscal * qrcp(hsum) : 0.0;
+#endif
             if (up) {
                 prod = prod * xi;
                 alph0 = alph0 - 1.0 / (double)(j + 1);
-                alph1 = alph1 + qrcp(xi);
+                alph1 = alph1 + rxi;
             }
             const double x = up ? xiold : xi;
 #pragma unroll
@@ -1254,7 +1281,7 @@ struct Engine {
                             }
                             if (c.L != lmax) {
                                 const double cnquot =
-                                    qdiv(hot.tq(5), hot.sd(SD_CONP)) * powi(qdiv(c.h, hot.tau(2)), c.L);
+                                    qdiv(hot.tq(5), hot.sd(SD_CONP)) * powi_small<kLmax>(qdiv(c.h, hot.tau(2)), c.L);
 #pragma unroll
                                 for (int i = 0; i < NLOC; i++)
                                     savf[i] = acor[i] - cnquot * acsav.get(i);

@@ -469,6 +469,31 @@ def test_robertson_itask_strict_bit_exact(itask):
         assert (got["t"][:, -1] == tcrit).all()
 
 
+@pytest.mark.parametrize("itask", [2, 3, 4, 5])
+def test_advection_itask_strict_bit_exact(itask):
+    """The same four task modes on a one-system-per-warp kernel (banded advection, mf = 24)."""
+    B = _B()
+    nsys = 64
+    par, y0 = B.batches.advection_batch(nsys), B.batches.advection_y0()
+    tcrit = 0.0
+    if itask == 2:
+        touts = np.full(30, 100.0)
+    elif itask == 5:
+        touts = np.full(30, 0.05)
+        tcrit = 0.05
+    else:
+        touts = B.batches.advection_touts()[:4]
+        if itask == 4:
+            tcrit = float(touts[-1])
+    ref = O.batch_solve("advection", par, y0, 0.0, touts, 0.0, 1e-6, 24, itol=1, itask=itask,
+                        tcrit=tcrit, ml=5, mu=0, pow_mode=1)
+    iw = _iopts(5, 0)
+    got = gpu_schedule("advection", par, y0, 0.0, touts, [0.0], [1e-6], 24, 1, strict=True,
+                       per_call=True, itask=itask, rwork_opts=_ropts(tcrit=tcrit), iwork_opts=iw)
+    assert (got["istate"] == 2).all()
+    _same(got, ref)
+
+
 def test_itask4_schedule_equals_per_call_and_fast_build_agrees():
     B = _B()
     nsys = 128
