@@ -22,7 +22,7 @@ BV_DEV void visit_state(ENG &e, V &v) {
     for (int j = 0; j < ENG::kLmax; j++)
 #pragma unroll
         for (int i = 0; i < ENG::NLOC; i++) v.dv(e.hot.yh(j, i));
-    ENG::POLICY::visit_acsav(e.acsav, v);
+    ENG::POLICY::visit_acsav(e, v);
 #pragma unroll
     for (int i = 0; i < ENG::NLOC; i++) v.dv(e.acor[i]);
     ENG::POLICY::visit_lin(e, v);
@@ -79,10 +79,6 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     e.o = a.o;
     e.tol.r = a.rtolv;
     e.tol.a = a.atolv;
-    e.acsav.p = a.dstate + (size_t)POL::kSlotAcsav * a.nsys + sys;
-    e.acsav.stride = (size_t)a.nsys;
-    e.lin.wjs.p = a.dstate + (size_t)POL::kSlotWjs * a.nsys + sys;
-    e.lin.wjs.stride = (size_t)a.nsys;
 #pragma unroll
     for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * a.nsys + sys];
 
@@ -175,8 +171,6 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
     constexpr int N = POL::N;
     Engine<POL> e;
     e.hot.bind(smem_thread, threadIdx.x);
-    e.acsav.p = nullptr;
-    e.lin.wjs.p = nullptr;
     Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
     visit_state(e, ld);
     e.c.L = e.c.nq + 1;

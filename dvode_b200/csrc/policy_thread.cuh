@@ -29,16 +29,8 @@ struct ThreadPolicy {
     static_assert(MITER >= 0 && MITER <= 3, "thread-per-system policy: miter 0..3");
     static_assert(N >= 2, "miter = 3 keeps wm(2) and the diagonal in the N x N matrix slots");
 
-    // Cold per-system data stays in its HBM state slot instead of registers: it is touched
-    // once per Jacobian / LU (every ~5-50 steps), and a warp's access is one coalesced line.
     typedef double Par[PROB::NPAR > 0 ? PROB::NPAR : 1];
-    struct GlobalVec {
-        double *p;       // slot 0 of this system
-        size_t stride;   // distance between slots (= nsys)
-        BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
-        BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
-    };
-    using AcSav = GlobalVec;  // the reference's yh(:,lmax) parking place (M:2259, 2298)
+    struct AcSav {};  // the acor copy the reference parks in yh(:,lmax) (M:2259, 2298) is hot.acs(i)
     struct Tol {              // rtol / atol expanded to N entries, in the kernel parameter bank
         const double *r, *a;
         BV_DEV double rtol(int i) const { return r[i]; }
@@ -58,10 +50,12 @@ struct ThreadPolicy {
 #define BVODE_THREAD_SMEM 1
 #endif
     static constexpr int kTPB = 128;
-    // doubles: tau[6], p[N][N], el[6], tq[5], sd[SD_COUNT]; ints: si[SI_COUNT], ipvt[N]
+    // doubles: tau[lmax], p[N][N], el[lmax], tq[5], sd[SD_COUNT], acs[N] (the acor copy of
+    // M:2259), wj[N][N] (saved Jacobian wm(locjs), mf > 0); ints: si[SI_COUNT], ipvt[N]
     static constexpr int kOffTau = 0, kOffP = kOffTau + kLmax, kOffEl = kOffP + N * N,
-                         kOffTq = kOffEl + kLmax, kOffSd = kOffTq + 5,
-                         kHotDoubles = kOffSd + SD_COUNT, kHotInts = SI_COUNT + N;
+                         kOffTq = kOffEl + kLmax, kOffSd = kOffTq + 5, kOffAcs = kOffSd + SD_COUNT,
+                         kOffWj = kOffAcs + N, kHotDoubles = kOffWj + (SAVEJ ? N * N : 0),
+                         kHotInts = SI_COUNT + N;
 #if BVODE_THREAD_SMEM
     struct Hot {
         double yhv[kLmax][N];
@@ -73,6 +67,8 @@ struct ThreadPolicy {
         BV_DEV volatile double &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
         BV_DEV volatile double &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
         BV_DEV volatile double &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
+        BV_DEV volatile double &acs(int i) const { return b[(kOffAcs + i) * kTPB]; }
+        BV_DEV volatile double &wj(int k) const { return b[(kOffWj + k) * kTPB]; }
         BV_DEV volatile int &si(int k) const { return bi[k * kTPB]; }
         BV_DEV volatile int &ipvt(int i) const { return bi[(SI_COUNT + i) * kTPB]; }
         BV_DEV void bind(double *smem, int tid) {
@@ -88,7 +84,10 @@ struct ThreadPolicy {
 #else
     struct Hot {
         double yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
+        double acsv[N], wjv[N * N];
         int siv[SI_COUNT], ipv[N];
+        BV_DEV double &acs(int i) { return acsv[i]; }
+        BV_DEV double &wj(int k) { return wjv[k]; }
         BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
         BV_DEV double &tau(int i) { return tauv[i]; }
         BV_DEV double &p(int i, int j) { return pv[i][j]; }
@@ -103,11 +102,14 @@ struct ThreadPolicy {
     static constexpr int kMinBlocks = 2;
 #endif
 
-    struct Lin {
-        // P = I - h*rl1*J and then its LU factors are hot.p(i, j) (row i, col j), the pivot rows
-        // hot.ipvt(k) (0-based); fast build: the diagonal holds 1/u_kk after dgefa.
-        GlobalVec wjs;    // saved Jacobian wm(locjs), element (i,j) at slot i*N+j (mf > 0)
-    };
+    struct Lin {};  // P = I - h*rl1*J / its LU factors: hot.p(i, j) (row i, col j), pivot rows
+                    // hot.ipvt(k) (0-based), saved Jacobian hot.wj(i*N + j); fast build: the
+                    // diagonal holds 1/u_kk after dgefa
+
+    template <class ENG>
+    BV_DEV static double acsav_get(ENG &e, int i) { return e.hot.acs(i); }
+    template <class ENG>
+    BV_DEV static void acsav_set(ENG &e, int i, double x) { e.hot.acs(i) = x; }
 
     template <class ENG>
     BV_DEV static void lin_init(ENG &e) {
@@ -115,20 +117,22 @@ struct ThreadPolicy {
         for (int i = 0; i < N; i++) e.hot.ipvt(i) = i;
     }
 
-    // state slots of one system, in visit order: yh, acsav*, acor, p, wjs*, tau, scalars
-    // (* = accessed in place through GlobalVec, skipped by the load / store visitors)
-    static constexpr int kSlotAcsav = kLmax * N;
-    static constexpr int kSlotWjs = kLmax * N + 2 * N + N * N;
-
-    template <class V>
-    BV_DEV static void visit_acsav(AcSav &, V &v) { v.skip_d(N); }
+    // state slots of one system, in visit order: yh, acsav, acor, p, wjs, ipvt, tau, scalars
+    template <class ENG, class V>
+    BV_DEV static void visit_acsav(ENG &e, V &v) {
+#pragma unroll
+        for (int i = 0; i < N; i++) v.d(e.hot.acs(i));
+    }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
             for (int j = 0; j < N; j++) v.d(e.hot.p(i, j));
-        if (SAVEJ) v.skip_d(N * N);
+        if (SAVEJ) {
+#pragma unroll
+            for (int k = 0; k < N * N; k++) v.d(e.hot.wj(k));
+        }
 #pragma unroll
         for (int i = 0; i < N; i++) v.i(e.hot.ipvt(i));
     }
@@ -373,7 +377,6 @@ struct ThreadPolicy {
     template <class ENG>
     BV_DEV static void jac_setup_dense(ENG &e, int &ierpj) {
         Ctl &c = e.c;
-        Lin &l = e.lin;
         ierpj = 0;
         const double hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
@@ -416,7 +419,7 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) l.wjs.set(i * N + j, P[i][j]);
+                    for (int j = 0; j < N; j++) e.hot.wj(i * N + j) = P[i][j];
             }
         } else {
             c.jcur = 0;
@@ -424,7 +427,7 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) P[i][j] = l.wjs.get(i * N + j);
+                    for (int j = 0; j < N; j++) P[i][j] = e.hot.wj(i * N + j);
             }
         }
         const double con = -hrl1;

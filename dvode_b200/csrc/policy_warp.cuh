@@ -59,6 +59,10 @@ struct WarpCommon {
         BV_DEV double get(int) const { return v; }
         BV_DEV void set(int, double x) { v = x; }
     };
+    template <class ENG>
+    BV_DEV static double acsav_get(ENG &e, int) { return e.acsav.v; }
+    template <class ENG>
+    BV_DEV static void acsav_set(ENG &e, int, double x) { e.acsav.v = x; }
     struct Tol {  // this lane's rtol / atol (0 for lanes >= N)
         double r, a;
         BV_DEV double rtol(int) const { return r; }
@@ -184,8 +188,8 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr int kLaneSlotWjs = kLmax + 2;
     static constexpr int kLaneSlots = kLmax + 2 + (SAVEJ ? N : 0);
     static constexpr int kLaneIntSlots = 1;
-    template <class V>
-    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class ENG, class V>
+    BV_DEV static void visit_acsav(ENG &e, V &v) { v.dv(e.acsav.v); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
         Lin &l = e.lin;
@@ -371,8 +375,8 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
     static int smem_doubles(int, int, bool) { return 0; }
     static constexpr int kLaneSlots = kLmax + 2 + 2;  // yh, acsav, acor, diag, phrl1
     static constexpr int kLaneIntSlots = 1;
-    template <class V>
-    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class ENG, class V>
+    BV_DEV static void visit_acsav(ENG &e, V &v) { v.dv(e.acsav.v); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
         v.dv(e.lin.diag);
@@ -464,8 +468,8 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     }
     static constexpr int kLaneSlots = kLmax + 2;  // yh[6], acsav, acor; the band arrays follow
     static constexpr int kLaneIntSlots = 1;
-    template <class V>
-    BV_DEV static void visit_acsav(typename Base::AcSav &a, V &v) { v.dv(a.v); }
+    template <class ENG, class V>
+    BV_DEV static void visit_acsav(ENG &e, V &v) { v.dv(e.acsav.v); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
         Lin &l = e.lin;

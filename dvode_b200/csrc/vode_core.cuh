@@ -522,7 +522,7 @@ struct Engine {
         double col[NLOC];
         if (up) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * acsav.get(i) : 0.0;
+            for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * POL::acsav_get(*this, i) : 0.0;
         } else {
             get_col(c.L, col);
 #pragma unroll
@@ -680,7 +680,7 @@ struct Engine {
             for (int i = 0; i < NLOC; i++) hot.yh(j, i) = 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) { acsav.set(i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
+        for (int i = 0; i < NLOC; i++) { POL::acsav_set(*this, i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
         POL::lin_init(*this);
         POL::f(t, y, savf, par);
 #pragma unroll
@@ -1250,7 +1250,7 @@ struct Engine {
                     c.nqwait = c.nqwait - 1;
                     if ((c.L != lmax) && (c.nqwait == 1)) {
 #pragma unroll
-                        for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
+                        for (int i = 0; i < NLOC; i++) POL::acsav_set(*this, i, acor[i]);
                         hot.sd(SD_CONP) = hot.tq(5);
                     }
                     if (hot.sd(SD_ETAMAX) != 1.0) {
@@ -1284,7 +1284,7 @@ struct Engine {
                                     qdiv(hot.tq(5), hot.sd(SD_CONP)) * powi_small<kLmax>(qdiv(c.h, hot.tau(2)), c.L);
 #pragma unroll
                                 for (int i = 0; i < NLOC; i++)
-                                    savf[i] = acor[i] - cnquot * acsav.get(i);
+                                    savf[i] = acor[i] - cnquot * POL::acsav_get(*this, i);
 #if BVODE_STRICT
                                 dup = qdiv(POL::norm(savf, ewt), hot.tq(3));
 #else
@@ -1336,7 +1336,7 @@ struct Engine {
                         }
                         if (save_acor) {
 #pragma unroll
-                            for (int i = 0; i < NLOC; i++) acsav.set(i, acor[i]);
+                            for (int i = 0; i < NLOC; i++) POL::acsav_set(*this, i, acor[i]);
                         }
 #if BVODE_STRICT
                         // label 450, M:2320-2330 (etamax != 1 here)
