@@ -199,10 +199,10 @@ struct WarpLoader {
     size_t nsys, sys;
     int ln, nblock;
     int kd = 0, kl = 0, ki = 0, kil = 0;
-    BV_DEV void d(double &x) { x = ds[(size_t)kd * nsys + sys]; kd++; }
-    BV_DEV void i(int &x) { x = is[(size_t)ki * nsys + sys]; ki++; }
-    BV_DEV void dv(double &x) { x = dl[((size_t)kl * nsys + sys) * 32 + ln]; kl++; }
-    BV_DEV void iv(int &x) { x = il[((size_t)kil * nsys + sys) * 32 + ln]; kil++; }
+    template <class T> BV_DEV void d(T &x) { x = ds[(size_t)kd * nsys + sys]; kd++; }
+    template <class T> BV_DEV void i(T &x) { x = is[(size_t)ki * nsys + sys]; ki++; }
+    template <class T> BV_DEV void dv(T &x) { x = dl[((size_t)kl * nsys + sys) * 32 + ln]; kl++; }
+    template <class T> BV_DEV void iv(T &x) { x = il[((size_t)kil * nsys + sys) * 32 + ln]; kil++; }
     BV_DEV void skip_dv(int n) { kl += n; }
     BV_DEV void block(double *sm, int n) {
         for (int k = ln; k < n; k += 32) sm[k] = db[sys * (size_t)nblock + k];
@@ -215,10 +215,10 @@ struct WarpStorer {
     size_t nsys, sys;
     int ln, nblock;
     int kd = 0, kl = 0, ki = 0, kil = 0;
-    BV_DEV void d(double &x) { if (ln == 0) ds[(size_t)kd * nsys + sys] = x; kd++; }
-    BV_DEV void i(int &x) { if (ln == 0) is[(size_t)ki * nsys + sys] = x; ki++; }
-    BV_DEV void dv(double &x) { dl[((size_t)kl * nsys + sys) * 32 + ln] = x; kl++; }
-    BV_DEV void iv(int &x) { il[((size_t)kil * nsys + sys) * 32 + ln] = x; kil++; }
+    template <class T> BV_DEV void d(T &x) { const double v = x; if (ln == 0) ds[(size_t)kd * nsys + sys] = v; kd++; }
+    template <class T> BV_DEV void i(T &x) { const int v = x; if (ln == 0) is[(size_t)ki * nsys + sys] = v; ki++; }
+    template <class T> BV_DEV void dv(T &x) { dl[((size_t)kl * nsys + sys) * 32 + ln] = x; kl++; }
+    template <class T> BV_DEV void iv(T &x) { il[((size_t)kil * nsys + sys) * 32 + ln] = x; kil++; }
     BV_DEV void skip_dv(int n) { kl += n; }
     BV_DEV void block(double *sm, int n) {
         __syncwarp();
@@ -244,6 +244,13 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
     db = dl + (size_t)POL::kLaneSlots * nsys * 32;
     il = istore + (size_t)kScalarI * nsys;
     nblock = 0;
+    {   // per-warp control state: after the kWarpTPB/32 matrix images of the CTA
+        int nb;
+        if constexpr (POL::kBand) nb = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
+        else if constexpr (POL::kPlain) nb = 0;
+        else nb = POL::N * POL::LDP;
+        e.hot.bind(smem + (size_t)(kWarpTPB / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
+    }
     if constexpr (POL::kBand) {
         nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
         e.lin.ml = ml;
@@ -262,15 +269,15 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
 }
 
 // One-system-per-warp kernels are latency-bound (dependent shuffle / FP64 chains, scalar
-// control replicated on 32 lanes): measured on B200, 65536 systems, mech32 / advection mf=24
-// systems/s at minBlocksPerSM = 2: 41.9k / 0.85M (206 / 168 registers, no spills); 4: 68.8k /
-// 0.91M; 6: 76.8k / 1.06M (85 registers, spills to L1); 8: 72.8k / 1.15M.  Resident warps
-// beat spills here.
-#ifndef BVODE_WARP_MINBLOCKS
-#define BVODE_WARP_MINBLOCKS 6
-#endif
+// control replicated on 32 lanes): resident warps beat registers.  Measured on B200, 65536
+// systems, systems/s by CTAs per SM (POL::kMinBlocks; 4 warps each):
+//                      4        5        6        8
+//   mech32 mf=22      73.2k    83.1k    91.6k    87.0k
+//   advection mf=24   1.37M    1.41M    1.60M    1.75M
+// (the replicated control state lives once per warp in shared memory, see WarpCommon::Hot;
+// before that: 6 CTAs 88.8k / 1.53M).
 template <class POL, bool GENERAL>
-__global__ void __launch_bounds__(kWarpTPB, BVODE_WARP_MINBLOCKS)
+__global__ void __launch_bounds__(kWarpTPB, POL::kMinBlocks)
 vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
@@ -419,7 +426,7 @@ template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = kWarpTPB / 32;
     const int grid = (a.nsys + spb - 1) / spb;
-    const size_t smem = sizeof(double) * spb * (size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu);
+    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles);
     if (a.general) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_warp_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -435,7 +442,7 @@ template <class POL>
 static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
     const int spb = kWarpTPB / 32;
     const int grid = (a.nsys + spb - 1) / spb;
-    const size_t smem = sizeof(double) * spb * (size_t)WarpLayout<POL>::nblock(a.ml, a.mu);
+    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.ml, a.mu) + POL::kWarpHotDoubles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(dvindy_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dvindy_warp_kernel<POL><<<grid, kWarpTPB, smem, st>>>(a);

@@ -43,16 +43,31 @@ struct WarpCommon {
         BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
         BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
     };
-    struct Hot {  // NLOC = 1: registers
-        double yhv[kLmax][1], tauv[kLmax + 1], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
-        int siv[SI_COUNT];
+    // Hot data.  The Nordsieck column entries of this lane's component live in registers.  The
+    // control state that is REPLICATED on the 32 lanes (tau, el, tq, conp / hu / hnew / crate /
+    // etamax, counters) is kept once per system in shared memory instead: every lane writes the
+    // same value to the same address and reads it back as a broadcast, so no synchronisation is
+    // needed, and ~55 registers per lane are free for the LU / solve loops (with the 80-register
+    // budget of 24 warps / SM the compiler had been re-deriving the lane id and the shared-memory
+    // row address inside every inner loop iteration).  Volatile, so the values are not promoted
+    // back into registers across the step loop.
+    static constexpr int kOffTau = 0, kOffEl = kOffTau + kLmax, kOffTq = kOffEl + kLmax,
+                         kOffSd = kOffTq + 5, kHotD = kOffSd + SD_COUNT,
+                         kWarpHotDoubles = kHotD + (SI_COUNT + 1) / 2;
+    struct Hot {
+        double yhv[kLmax][1];
+        volatile double *b;
+        volatile int *bi;
         BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
-        BV_DEV double &tau(int i) { return tauv[i]; }
-        BV_DEV double &el(int i) { return elv[i]; }
-        BV_DEV double &tq(int i) { return tqv[i]; }
-        BV_DEV double &sd(int k) { return sdv[k]; }
-        BV_DEV int &si(int k) { return siv[k]; }
-        BV_DEV void bind(double *, int) {}
+        BV_DEV volatile double &tau(int i) const { return b[kOffTau + (i - 1)]; }
+        BV_DEV volatile double &el(int i) const { return b[kOffEl + (i - 1)]; }
+        BV_DEV volatile double &tq(int i) const { return b[kOffTq + (i - 1)]; }
+        BV_DEV volatile double &sd(int k) const { return b[kOffSd + k]; }
+        BV_DEV volatile int &si(int k) const { return bi[k]; }
+        BV_DEV void bind(double *base, int) {
+            b = base;
+            bi = reinterpret_cast<int *>(base + kHotD);
+        }
     };
     struct AcSav {  // NLOC = 1: a register
         double v;
@@ -172,6 +187,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
     static constexpr bool kPlain = false;
+    static constexpr int kMinBlocks = 6;  // CTAs per SM (see bvode_kernels.cuh)
     static constexpr int LDP = N | 1;
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
@@ -364,6 +380,7 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
     static constexpr bool SAVEJ = false;
     static constexpr bool kBand = false;
     static constexpr bool kPlain = true;
+    static constexpr int kMinBlocks = 8;
     static_assert(MITER == 0 || MITER == 3, "plain policy");
 
     struct Lin {
@@ -449,6 +466,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = true;
     static constexpr bool kPlain = false;
+    static constexpr int kMinBlocks = 8;
     static_assert(MITER == 4 || MITER == 5, "band policy");
 
     struct Lin {
