@@ -62,7 +62,10 @@ struct Storer {
 };
 
 // ------------------------------------------------------- thread-per-system ------
-constexpr int kThreadTPB = 128;
+#ifndef BVODE_THREAD_TPB
+#define BVODE_THREAD_TPB 128
+#endif
+constexpr int kThreadTPB = BVODE_THREAD_TPB;
 
 template <class POL, bool GENERAL>
 __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
@@ -248,7 +251,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
         int nb;
         if constexpr (POL::kBand) nb = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
         else if constexpr (POL::kPlain) nb = 0;
-        else nb = POL::N * POL::LDP;
+        else nb = POL::kBlockDoubles;
         e.hot.bind(smem + (size_t)(kWarpTPB / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
     }
     if constexpr (POL::kBand) {
@@ -261,8 +264,9 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
     } else if constexpr (POL::kPlain) {
         (void)ml; (void)mu; (void)smem; (void)warp; (void)sys; (void)ln;
     } else {
-        nblock = POL::N * POL::LDP;
+        nblock = POL::kBlockDoubles;
         e.lin.p = smem + (size_t)warp * nblock;
+        e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::N * POL::LDP);
         e.lin.wjs.p = const_cast<double *>(dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
         e.lin.wjs.stride = nsys * 32;
     }

@@ -49,7 +49,10 @@ struct ThreadPolicy {
 #ifndef BVODE_THREAD_SMEM
 #define BVODE_THREAD_SMEM 1
 #endif
-    static constexpr int kTPB = 128;
+#ifndef BVODE_THREAD_TPB
+#define BVODE_THREAD_TPB 128
+#endif
+    static constexpr int kTPB = BVODE_THREAD_TPB;  // threads (= systems) per CTA
     // doubles: tau[lmax], p[N][N], el[lmax], tq[5], sd[SD_COUNT], acs[N] (the acor copy of
     // M:2259), wj[N][N] (saved Jacobian wm(locjs), mf > 0); ints: si[SI_COUNT], ipvt[N]
     static constexpr int kOffTau = 0, kOffP = kOffTau + kLmax, kOffEl = kOffP + N * N,

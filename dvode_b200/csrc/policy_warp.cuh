@@ -166,12 +166,25 @@ struct WarpCommon {
 };
 
 // =========================================================================== dense ====
-// Row i of the Newton matrix belongs to lane i; the matrix itself is in shared memory,
-// element (i, j) at p[i*LDP + j] with LDP odd, so "every lane reads its own row's column j"
-// and "every lane reads element (k, j)" (a broadcast) are both conflict-free.  All loops over
-// columns are run-time loops: the first version kept each row in registers with fully
-// unrolled loops (~20k instructions) and was bound by instruction fetch (ncu: 33 cycles of
-// no-instruction stall per issued instruction, profiles/r01_ncu_warp_dense_mech32_v1.txt).
+// Row i of the Newton matrix belongs to lane i for the whole factorisation; the matrix is in
+// shared memory, element (i, j) at p[i*LDP + j] with LDP odd, so "every lane reads its own
+// row's column j" and "every lane reads element (l, j)" (a broadcast) are both conflict-free.
+//
+// Pivoting is IMPLICIT: LINPACK's row interchanges (LP:96-110) move the active parts of two rows
+// and leave the multipliers where they are; dgesl repeats the same interchanges on b.  Here no
+// row ever moves.  Each lane keeps its row and a position `pos` (the index LINPACK's storage
+// would give that row); step k picks the pivot lane l = perm[k] and exchanges the POSITIONS of
+// the two rows.  A row pivoted at step k has pos = k for good, so "rows below the pivot" is
+// pos > k, a row's multipliers stay in its own storage, and b_i travels with row i in dgesl.
+// Every product and sum is the one LINPACK forms, on the same operands, in the same order per
+// element -- the factors, the solution and the tie rule (first maximum in LINPACK's row order,
+// BL:334) are bit-identical; only where a number is stored differs.  This removes the swap
+// traffic and the two lane-exchanges per solve step of the first version.
+//
+// All loops over columns are run-time loops: the very first version kept each row in registers
+// with fully unrolled loops (~20k instructions) and was bound by instruction fetch (ncu: 33
+// cycles of no-instruction stall per issued instruction,
+// profiles/r01_ncu_warp_dense_mech32_v1.txt).
 template <class PROB, int MITER_, bool SAVEJ_, int METH_ = 2>
 struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     using Base = WarpCommon<PROB, METH_>;
@@ -189,79 +202,112 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr bool kPlain = false;
     static constexpr int kMinBlocks = 6;  // CTAs per SM (see bvode_kernels.cuh)
     static constexpr int LDP = N | 1;
+    static constexpr int kBlockDoubles = N * LDP + 16;  // the matrix, then perm[32] (ints)
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
     struct Lin {
         double *p;      // shared memory, N rows x LDP: P = I - h*rl1*J, then its LU factors.
-                        // Fast build: the diagonal holds 1/u_kk after dgefa.
+                        // Fast build: the pivot entry of each row holds 1/u_kk after dgefa.
+        int *perm;      // shared memory: perm[k] = lane (row) that is the pivot of step k
         GlobalVec wjs;  // row `lane` of the saved Jacobian, element j at slot j (mf > 0)
-        int ipv;        // lane k holds ipvt(k) (0-based row)
+        int ipv;        // lane k holds perm[k]
+        int pos;        // position of this lane's row in LINPACK's storage order
     };
+    BV_DEV static bool real_lane() { return (N == 32) || (lane() < N); }
     template <class ENG>
-    BV_DEV static void lin_init(ENG &e) { e.lin.ipv = lane(); }
-    static int smem_doubles(int, int, bool) { return N * LDP; }
+    BV_DEV static void lin_init(ENG &e) {
+        e.lin.ipv = lane();
+        e.lin.pos = real_lane() ? lane() : 64;
+        e.lin.perm[lane()] = lane();
+        __syncwarp();
+    }
+    static int smem_doubles(int, int, bool) { return kBlockDoubles; }
     // per-lane double slots of one system, in visit order: yh[6], acsav, acor, wjs[N]*
     static constexpr int kLaneSlotWjs = kLmax + 2;
     static constexpr int kLaneSlots = kLmax + 2 + (SAVEJ ? N : 0);
-    static constexpr int kLaneIntSlots = 1;
+    static constexpr int kLaneIntSlots = 2;
     template <class ENG, class V>
     BV_DEV static void visit_acsav(ENG &e, V &v) { v.dv(e.acsav.v); }
     template <class ENG, class V>
     BV_DEV static void visit_lin(ENG &e, V &v) {
         Lin &l = e.lin;
         if (SAVEJ) v.skip_dv(N);
-        v.block(l.p, N * LDP);
+        v.block(l.p, kBlockDoubles);
         v.iv(l.ipv);
+        v.iv(l.pos);
+    }
+
+    // idamax (BL:311-359) over the rows that are still below the diagonal (`act`), magnitudes
+    // compared as integers (|v| of a finite double orders like its bit pattern): two warp
+    // reductions instead of a five-round shuffle tournament.  Several rows of the same largest
+    // magnitude: the first in LINPACK's row order wins.
+    BV_DEV static int pivot_lane(double v, bool act, int pos) {
+        const unsigned hi = act ? ((unsigned)__double2hiint(v) & 0x7fffffffu) : 0u;
+        const unsigned lo = (unsigned)__double2loint(v);
+        const unsigned mhi = __reduce_max_sync(kFull, hi);
+        const bool c1 = act && (hi == mhi);
+        const unsigned mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
+        const bool c2 = c1 && (lo == mlo);
+        unsigned b = __ballot_sync(kFull, c2);
+        if (b & (b - 1)) {  // warp-uniform
+            const unsigned mp = __reduce_min_sync(kFull, c2 ? (unsigned)pos : 0xffffu);
+            b = __ballot_sync(kFull, c2 && ((unsigned)pos == mp));
+        }
+        return __ffs((int)b) - 1;
     }
 
     // ---- dgefa, LP:46-120, rows across lanes ----------------------------------------
     BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();
-        double *row = lin.p + ln * LDP;  // lanes >= N never touch memory
+        const bool real = real_lane();
+        double *row = lin.p + (real ? ln : 0) * LDP;  // lanes >= N never write
+        int pos = real ? ln : 64;
         int info = 0;
         __syncwarp();
 #pragma unroll 1
         for (int k = 0; k < N - 1; k++) {
-            const double v = (ln < N) ? row[k] : 0.0;
-            const int l = Base::argmax_abs(v, k, N - 1);
-            if (ln == k) lin.ipv = l;
+            const bool act = real && (pos >= k);
+            const double v = row[k];
+            const int l = pivot_lane(v, act, pos);
             const double alk = shfl_d(v, l);
+            const int pl = __shfl_sync(kFull, pos, l);
+            if (ln == k) lin.ipv = l;
+            lin.perm[k] = l;  // the same value from every lane
+            // the interchange of LP:96-110: the two rows exchange positions
+            if (pos == k) pos = pl;
+            if (ln == l) pos = k;
             if (alk == 0.0) {
                 info = k + 1;
             } else {
-                const bool swap = (l != k);  // warp-uniform
-                // interchange a(l,k) <-> a(k,k), then scale the multipliers (LP:96-104)
-                double m = v;
-                if (swap) {
-                    const double akk = shfl_d(v, k);
-                    if (ln == l) m = akk;
-                    if (ln == k) m = alk;
-                }
-                const double t = -qrcp(alk);
-                if (ln > k && ln < N) m = t * m;
-                if (ln >= k && ln < N) row[k] = m;
-                __syncwarp();
-#pragma unroll 1
-                for (int j = k + 1; j < N; j++) {
-                    const double tj = lin.p[l * LDP + j];    // a(l,j): broadcast
-                    if (swap) {
-                        const double akj = lin.p[k * LDP + j];
-                        __syncwarp();
-                        if (ln == l) row[j] = akj;
-                        if (ln == k) row[j] = tj;
-                        __syncwarp();
-                    }
-                    if (ln > k && ln < N) row[j] = row[j] + tj * m;
-                }
-                __syncwarp();
-            }
-        }
-        if (ln == N - 1) lin.ipv = N - 1;
-        if (lin.p[(N - 1) * LDP + (N - 1)] == 0.0) info = N;
-#if !BVODE_STRICT
-        __syncwarp();
-        if (ln < N) row[ln] = qrcp(row[ln]);
+                const bool below = real && (pos > k);
+#if BVODE_STRICT
+                const double t = -1.0 / alk;
+#else
+                const double rp = qrcp(alk);
+                const double t = -rp;
+                if (ln == l) row[k] = rp;  // 1/u_kk: dgesl multiplies
 #endif
+                const double m = t * v;  // the multipliers (LP:102-104)
+                if (below) row[k] = m;
+                const double *prow = lin.p + l * LDP;  // the pivot row: broadcasts
+                if (below) {
+#pragma unroll 4
+                    for (int j = k + 1; j < N; j++) row[j] = row[j] + prow[j] * m;
+                }
+            }
+            __syncwarp();
+        }
+        {   // the row that is left is the last pivot
+            const int l = __ffs((int)__ballot_sync(kFull, real && (pos == N - 1))) - 1;
+            if (ln == N - 1) lin.ipv = l;
+            lin.perm[N - 1] = l;
+            const double v = row[N - 1];
+            if (shfl_d(v, l) == 0.0) info = N;
+#if !BVODE_STRICT
+            if (ln == l) row[N - 1] = qrcp(v);
+#endif
+        }
+        lin.pos = pos;
         __syncwarp();
         return info;
     }
@@ -270,31 +316,31 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     template <class ENG>
     BV_DEV static int solve(ENG &e, double (&x)[1]) {
         const Lin &lin = e.lin;
-        const int ln = lane();
-        const double *row = lin.p + ln * LDP;
+        const bool real = real_lane();
+        const double *row = lin.p + (real ? lane() : 0) * LDP;
+        const int pos = lin.pos;
+        const int *perm = lin.perm;
         double b = x[0];
-#pragma unroll 1
+        // forward elimination: b of the pivot row times this row's multiplier
+#pragma unroll 4
         for (int k = 0; k < N - 1; k++) {
-            const int l = __shfl_sync(kFull, lin.ipv, k);
-            const double t = shfl_d(b, l);
-            if (l != k) {
-                const double bk = shfl_d(b, k);
-                if (ln == l) b = bk;
-                if (ln == k) b = t;
-            }
-            if (ln > k && ln < N) b = b + t * row[k];
+            const double t = shfl_d(b, perm[k]);
+            const double m = row[k];
+            if (real && pos > k) b = b + t * m;
         }
-#pragma unroll 1
+        // back substitution
+#pragma unroll 4
         for (int k = N - 1; k >= 0; k--) {
+            const double m = row[k];
 #if BVODE_STRICT
-            if (ln == k) b = b / row[k];
+            if (pos == k) b = b / m;
 #else
-            if (ln == k) b = b * row[k];
+            if (pos == k) b = b * m;
 #endif
-            const double t = -shfl_d(b, k);
-            if (ln < k) b = b + t * row[k];
+            const double t = -shfl_d(b, perm[k]);
+            if (real && pos < k) b = b + t * m;
         }
-        x[0] = b;
+        x[0] = shfl_d(b, lin.ipv);  // component k is on the lane that was pivot k
         return 0;
     }
 
