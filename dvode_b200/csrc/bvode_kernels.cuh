@@ -266,7 +266,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
     } else {
         nblock = POL::kBlockDoubles;
         e.lin.p = smem + (size_t)warp * nblock;
-        e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::N * POL::LDP);
+        e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::N * POL::LDP + ((POL::N * POL::LDP) & 1));
         e.lin.wjs.p = const_cast<double *>(dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
         e.lin.wjs.stride = nsys * 32;
     }

@@ -24,6 +24,36 @@ constexpr unsigned kFull = 0xffffffffu;
 BV_DEV double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 BV_DEV double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
+// Shared-memory access through a 32-bit shared address held in ONE register, with compile-time
+// byte offsets.  The address is made opaque to the compiler once: under the register cap of the
+// warp kernels nvcc otherwise re-derives "lane id * row stride + base" from the special
+// registers inside every inner-loop iteration (6 of 16 instructions per solve step, ncu r1l).
+BV_DEV unsigned sm_addr(const void *p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+template <int OFF = 0>
+BV_DEV double lds_d(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF = 0>
+BV_DEV void sts_d(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF = 0>
+BV_DEV int lds_i(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+BV_DEV void lds_i4(unsigned a, int &v0, int &v1, int &v2, int &v3) {  // 16-byte aligned
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a));
+}
+BV_DEV void sts_i(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // Common pieces of the two warp policies.
 template <class PROB, int METH_>
 struct WarpCommon {
@@ -202,7 +232,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr bool kPlain = false;
     static constexpr int kMinBlocks = 6;  // CTAs per SM (see bvode_kernels.cuh)
     static constexpr int LDP = N | 1;
-    static constexpr int kBlockDoubles = N * LDP + 16;  // the matrix, then perm[32] (ints)
+    static constexpr int kBlockDoubles = N * LDP + 16 + ((N * LDP) & 1);  // the matrix, then perm[32] (ints), 16-byte aligned
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
     struct Lin {
@@ -260,19 +290,22 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();
         const bool real = real_lane();
-        double *row = lin.p + (real ? ln : 0) * LDP;  // lanes >= N never write
+        const unsigned pa = sm_addr(lin.p);                 // the matrix
+        const unsigned rowa = pa + (real ? ln : 0) * (LDP * 8);  // this lane's row (lanes >= N never write)
+        const unsigned perma = pa + (N * LDP + ((N * LDP) & 1)) * 8;
         int pos = real ? ln : 64;
         int info = 0;
         __syncwarp();
 #pragma unroll 1
         for (int k = 0; k < N - 1; k++) {
             const bool act = real && (pos >= k);
-            const double v = row[k];
+            const unsigned rk = rowa + k * 8;
+            const double v = lds_d(rk);
             const int l = pivot_lane(v, act, pos);
             const double alk = shfl_d(v, l);
             const int pl = __shfl_sync(kFull, pos, l);
             if (ln == k) lin.ipv = l;
-            lin.perm[k] = l;  // the same value from every lane
+            sts_i(perma + k * 4, l);  // the same value from every lane
             // the interchange of LP:96-110: the two rows exchange positions
             if (pos == k) pos = pl;
             if (ln == l) pos = k;
@@ -282,17 +315,33 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 const bool below = real && (pos > k);
 #if BVODE_STRICT
                 const double t = -1.0 / alk;
+                const double m = t * v;  // the multipliers (LP:102-104)
+                if (below) sts_d(rk, m);
 #else
+                // fast build: the pivot row keeps 1/u_kk (dgesl multiplies); the rows ALREADY
+                // pivoted scale their entry of column k by -1/u_kk as well, so that back
+                // substitution is b_i += b_k * (-u_ik/u_kk) with the un-normalised b_k -- one
+                // shuffle and one fma per step on the dependent chain, x_k = b_k/u_kk at the end
                 const double rp = qrcp(alk);
                 const double t = -rp;
-                if (ln == l) row[k] = rp;  // 1/u_kk: dgesl multiplies
+                const double m = t * v;
+                if (real) sts_d(rk, (ln == l) ? rp : m);
 #endif
-                const double m = t * v;  // the multipliers (LP:102-104)
-                if (below) row[k] = m;
-                const double *prow = lin.p + l * LDP;  // the pivot row: broadcasts
                 if (below) {
-#pragma unroll 4
-                    for (int j = k + 1; j < N; j++) row[j] = row[j] + prow[j] * m;
+                    // row(j) += pivot_row(j) * m, j > k (LP:105-118); loads first, then stores
+                    unsigned ar = rk + 8, ap = pa + l * (LDP * 8) + (k + 1) * 8;
+                    int cnt = N - 1 - k;
+#pragma unroll 1
+                    for (; cnt >= 4; cnt -= 4, ar += 32, ap += 32) {
+                        const double p0 = lds_d<0>(ap), p1 = lds_d<8>(ap), p2 = lds_d<16>(ap), p3 = lds_d<24>(ap);
+                        const double r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
+                        sts_d<0>(ar, r0 + p0 * m);
+                        sts_d<8>(ar, r1 + p1 * m);
+                        sts_d<16>(ar, r2 + p2 * m);
+                        sts_d<24>(ar, r3 + p3 * m);
+                    }
+#pragma unroll 1
+                    for (; cnt > 0; cnt--, ar += 8, ap += 8) sts_d(ar, lds_d(ar) + lds_d(ap) * m);
                 }
             }
             __syncwarp();
@@ -300,11 +349,13 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         {   // the row that is left is the last pivot
             const int l = __ffs((int)__ballot_sync(kFull, real && (pos == N - 1))) - 1;
             if (ln == N - 1) lin.ipv = l;
-            lin.perm[N - 1] = l;
-            const double v = row[N - 1];
-            if (shfl_d(v, l) == 0.0) info = N;
+            sts_i(perma + (N - 1) * 4, l);
+            const double v = lds_d<(N - 1) * 8>(rowa);
+            const double alk = shfl_d(v, l);
+            if (alk == 0.0) info = N;
 #if !BVODE_STRICT
-            if (ln == l) row[N - 1] = qrcp(v);
+            const double rp = qrcp(alk);
+            if (real) sts_d<(N - 1) * 8>(rowa, (ln == l) ? rp : -rp * v);  // column N-1 of U, scaled like the others
 #endif
         }
         lin.pos = pos;
@@ -313,33 +364,62 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     }
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------------
+    // One step: t = b of the pivot row of column k; rows taking part add t * (their entry of
+    // column k).  FWD: rows below the pivot (multipliers); !FWD: rows above it.
+    template <bool FWD, int OFF>
+    BV_DEV static void solve_step(double &b, unsigned rk, int l, int pos, int k, bool real) {
+        const double m = lds_d<OFF * 8>(rk);
+        const bool part = real && (FWD ? (pos > k + OFF) : (pos < k + OFF));
+#if BVODE_STRICT
+        if (!FWD && pos == k + OFF) b = b / m;
+        const double t = FWD ? shfl_d(b, l) : -shfl_d(b, l);
+        if (part) b = b + t * m;
+#else
+        const double t = shfl_d(b, l);
+        b = b + t * (part ? m : 0.0);  // the select is off the dependent chain
+#endif
+    }
     template <class ENG>
     BV_DEV static int solve(ENG &e, double (&x)[1]) {
         const Lin &lin = e.lin;
         const bool real = real_lane();
-        const double *row = lin.p + (real ? lane() : 0) * LDP;
+        const unsigned pa = sm_addr(lin.p);
+        const unsigned rowa = pa + (real ? lane() : 0) * (LDP * 8);
+        const unsigned perma = pa + (N * LDP + ((N * LDP) & 1)) * 8;
         const int pos = lin.pos;
-        const int *perm = lin.perm;
         double b = x[0];
-        // forward elimination: b of the pivot row times this row's multiplier
-#pragma unroll 4
-        for (int k = 0; k < N - 1; k++) {
-            const double t = shfl_d(b, perm[k]);
-            const double m = row[k];
-            if (real && pos > k) b = b + t * m;
+        // forward elimination, k = 0 .. N-2
+        int k = 0;
+#pragma unroll 1
+        for (; k + 3 < N - 1; k += 4) {
+            const unsigned rk = rowa + k * 8;
+            int l0, l1, l2, l3;
+            lds_i4(perma + k * 4, l0, l1, l2, l3);
+            solve_step<true, 0>(b, rk, l0, pos, k, real);
+            solve_step<true, 1>(b, rk, l1, pos, k, real);
+            solve_step<true, 2>(b, rk, l2, pos, k, real);
+            solve_step<true, 3>(b, rk, l3, pos, k, real);
         }
-        // back substitution
-#pragma unroll 4
-        for (int k = N - 1; k >= 0; k--) {
-            const double m = row[k];
-#if BVODE_STRICT
-            if (pos == k) b = b / m;
-#else
-            if (pos == k) b = b * m;
+#pragma unroll 1
+        for (; k < N - 1; k++) solve_step<true, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
+        // back substitution, k = N-1 .. kend (fast build: column 0 has no row above it)
+        constexpr int kend = BVODE_STRICT ? 0 : 1;
+        k = N - 1;
+#pragma unroll 1
+        for (; k - 3 >= kend; k -= 4) {
+            const unsigned rk = rowa + k * 8;
+            int l0, l1, l2, l3;
+            lds_i4(perma + (k - 3) * 4, l3, l2, l1, l0);
+            solve_step<false, 0>(b, rk, l0, pos, k, real);
+            solve_step<false, -1>(b, rk, l1, pos, k, real);
+            solve_step<false, -2>(b, rk, l2, pos, k, real);
+            solve_step<false, -3>(b, rk, l3, pos, k, real);
+        }
+#pragma unroll 1
+        for (; k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
+#if !BVODE_STRICT
+        if (real) b = b * lds_d(rowa + pos * 8);  // x_k = b_k / u_kk
 #endif
-            const double t = -shfl_d(b, perm[k]);
-            if (real && pos < k) b = b + t * m;
-        }
         x[0] = shfl_d(b, lin.ipv);  // component k is on the lane that was pivot k
         return 0;
     }
