@@ -173,6 +173,17 @@ struct WarpCommon {
         }
         return (v > 0.0) ? idx + 1 : 1;
     }
+    // idamax (BL:311-359) over the lanes with `act`: the lowest such lane holding the largest |x|.
+    // |x| of finite doubles order like their bit patterns, so two 32-bit warp reductions and one
+    // ballot replace the five-round shuffle tournament of argmax_abs below.
+    BV_DEV static unsigned max_abs_ballot(double x, bool act) {
+        const unsigned hi = act ? ((unsigned)__double2hiint(x) & 0x7fffffffu) : 0u;
+        const unsigned lo = (unsigned)__double2loint(x);
+        const unsigned mhi = __reduce_max_sync(kFull, hi);
+        const bool c1 = act && (hi == mhi);
+        const unsigned mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
+        return __ballot_sync(kFull, c1 && (lo == mlo));
+    }
     // idamax over lanes [lo, hi]: returns the lane of the first maximum of |x|
     BV_DEV static int argmax_abs(double x, int lo, int hi) {
         const int ln = lane();
@@ -272,14 +283,9 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // reductions instead of a five-round shuffle tournament.  Several rows of the same largest
     // magnitude: the first in LINPACK's row order wins.
     BV_DEV static int pivot_lane(double v, bool act, int pos) {
-        const unsigned hi = act ? ((unsigned)__double2hiint(v) & 0x7fffffffu) : 0u;
-        const unsigned lo = (unsigned)__double2loint(v);
-        const unsigned mhi = __reduce_max_sync(kFull, hi);
-        const bool c1 = act && (hi == mhi);
-        const unsigned mlo = __reduce_max_sync(kFull, c1 ? lo : 0u);
-        const bool c2 = c1 && (lo == mlo);
-        unsigned b = __ballot_sync(kFull, c2);
+        unsigned b = Base::max_abs_ballot(v, act);
         if (b & (b - 1)) {  // warp-uniform
+            const bool c2 = (b >> lane()) & 1u;
             const unsigned mp = __reduce_min_sync(kFull, c2 ? (unsigned)pos : 0xffffu);
             b = __ballot_sync(kFull, c2 && ((unsigned)pos == mp));
         }
@@ -651,7 +657,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             const int lm = (ml < n - k) ? ml : n - k;
             // l = idamax(lm+1, abd(m,k)) + m - 1: lanes 0..lm look at rows m..m+lm of column k
             const double cand = (ln <= lm) ? ABD(m + ln, k) : 0.0;
-            const int lrow = m + Base::argmax_abs(cand, 0, lm);  // 1-based row in abd
+            const int lrow = m + (__ffs((int)Base::max_abs_ballot(cand, ln <= lm)) - 1);  // 1-based row in abd
             const int piv = lrow + k - m;                        // 1-based row of the matrix
             if (ln == k - 1) l.ipv = piv - 1;
             const double alk = shfl_d(cand, lrow - m);
@@ -690,47 +696,84 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         if (ABD(m, n) == 0.0) info = n;
         __syncwarp();
 #if !BVODE_STRICT
-        // fast build: the diagonal keeps 1/u_kk so that dgbsl multiplies
-        if (ln < n) ABD(m, ln + 1) = qrcp(ABD(m, ln + 1));
+        // fast build: the diagonal keeps 1/u_kk so that dgbsl multiplies, and the entries of U
+        // above it are scaled by -1/u_kk: back substitution is then b_i += b_k * (-u_ik/u_kk)
+        // with the un-normalised b_k (one shuffle and one fma per step on the dependent chain)
+        if (ln < n) {
+            const int j = ln + 1;
+            const double rp = qrcp(ABD(m, j));
+            ABD(m, j) = rp;
+            const int lmj = ((j < m) ? j : m) - 1;
+            for (int i = 1; i <= lmj; i++) ABD(m - i, j) = -rp * ABD(m - i, j);
+        }
         __syncwarp();
 #endif
         return info;
     }
 
     // ---- dgbsl job = 0, LP:494-519: b_i in lane i-1 ------------------------------------------
+    // Entry (row i = lane+1, column k) of the band array is abd[(k-1)*ld + (m - k + lane)]: one
+    // shared address per lane that advances by (ld-1) doubles per column, for the multipliers
+    // below the diagonal (forward elimination), the diagonal and U above it (back substitution).
     template <class ENG>
     BV_DEV static int solve(ENG &e, double (&x)[1]) {
         const Lin &l = e.lin;
         const int ln = lane();
         const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
+        const bool real = (N == 32) || (ln < n);
+        const int step = (l.ld - 1) * 8;
+        const unsigned a1 = sm_addr(l.abd) + (m - 1 + (real ? ln : 0)) * 8;  // column 1
         double b = x[0];
         if (ml != 0) {
-#pragma unroll 1
-            for (int k = 1; k <= n - 1; k++) {
-                const int lm = (ml < n - k) ? ml : n - k;
-                const int lp = __shfl_sync(kFull, l.ipv, k - 1);  // 0-based
-                const double t = shfl_d(b, lp);
-                if (lp != k - 1) {
-                    const double bk = shfl_d(b, k - 1);
-                    if (ln == lp) b = bk;
-                    if (ln == k - 1) b = t;
+            // any row interchange at all?  (warp-uniform; none for diagonally dominant P)
+            const bool swaps = __any_sync(kFull, real && (l.ipv != ln)) != 0;
+            unsigned a = a1;
+#pragma unroll 4
+            for (int k = 1; k <= n - 1; k++, a += step) {
+                double t;
+                if (swaps) {
+                    const int lp = __shfl_sync(kFull, l.ipv, k - 1);  // 0-based
+                    t = shfl_d(b, lp);
+                    if (lp != k - 1) {
+                        const double bk = shfl_d(b, k - 1);
+                        if (ln == lp) b = bk;
+                        if (ln == k - 1) b = t;
+                    }
+                } else {
+                    t = shfl_d(b, k - 1);
                 }
-                const int i = ln + 1 - k;  // row offset below the diagonal
-                if (i >= 1 && i <= lm) b = b + t * ABD(m + i, k);
+                // rows k+1 .. min(k+ml, n)
+                const bool part = real && ((unsigned)(ln - k) < (unsigned)ml);
+                const double mv = lds_d(a);
+#if BVODE_STRICT
+                if (part) b = b + t * mv;
+#else
+                b = b + t * (part ? mv : 0.0);
+#endif
             }
         }
-#pragma unroll 1
-        for (int k = n; k >= 1; k--) {
+        {
+            unsigned a = a1 + (n - 1) * step;
 #if BVODE_STRICT
-            if (ln == k - 1) b = b / ABD(m, k);
+#pragma unroll 4
+            for (int k = n; k >= 1; k--, a -= step) {
+                const double mv = lds_d(a);
+                if (ln == k - 1) b = b / mv;
+                const double t = -shfl_d(b, k - 1);
+                // rows max(k-m+1, 1) .. k-1
+                const bool part = real && ((unsigned)(k - 2 - ln) < (unsigned)(m - 1));
+                if (part) b = b + t * mv;
+            }
 #else
-            if (ln == k - 1) b = b * ABD(m, k);
+#pragma unroll 4
+            for (int k = n; k >= 2; k--, a -= step) {
+                const double mv = lds_d(a);
+                const double t = shfl_d(b, k - 1);
+                const bool part = real && ((unsigned)(k - 2 - ln) < (unsigned)(m - 1));
+                b = b + t * (part ? mv : 0.0);
+            }
+            if (real) b = b * lds_d(a1 + ln * step);  // x_k = b_k / u_kk
 #endif
-            const int lm = ((k < m) ? k : m) - 1;
-            const int la = m - lm, lb = k - lm;
-            const double t = -shfl_d(b, k - 1);
-            const int i = ln + 1 - lb;  // 0..lm-1 for the rows lb..k-1
-            if (i >= 0 && i < lm) b = b + t * ABD(la + i, k);
         }
         x[0] = b;
         return 0;
