@@ -127,3 +127,26 @@ def test_robertson_example():
     for k, v in g["stats"].items():
         assert abs(st[k] - v) <= max(5, 0.15 * v), (k, st[k], v)
     assert (int(r["istats"][0, -1, O.ISTAT["lenrw"]]), int(r["istats"][0, -1, O.ISTAT["leniw"]])) == (67, 33)
+
+
+def test_band_pivoting_happens_in_the_oracle_lu():
+    """Sanity of tests/test_gpu_properties.py::test_band_pivoting_*: LINPACK's dgbfa (LP:275-396)
+    interchanges rows for P = I - 10*J of dvdemo problem 2 at alph1 = alph2 = 4."""
+    n, ml, mu = 25, 5, 0
+    ld = 2 * ml + mu + 1
+    abd = np.zeros((n, ld))  # column-major band storage: abd[j][i] = abd(i+1, j+1)
+    hl = 10.0
+    m = ml + mu + 1
+    for j in range(n):
+        abd[j, m - 1] = 1.0 + 2.0 * hl
+        if (j + 1) % 5 != 0 and j + 1 < n:
+            abd[j, m] = -hl * 4.0
+        if j + 5 < n:
+            abd[j, m - 1 + 5] = -hl * 4.0
+    import ctypes as C
+    ipvt = np.zeros(n, dtype=np.int32)
+    info = C.c_int()
+    a = np.ascontiguousarray(abd.reshape(-1))
+    O.lib().dvo_dgbfa(O._dp(a), ld, n, ml, mu, O._ip(ipvt), C.byref(info))
+    assert info.value == 0
+    assert (ipvt != np.arange(1, n + 1)).any()
