@@ -68,6 +68,7 @@ def _load():
 _lib = _load()
 
 FLAG_STRICT = 1
+FLAG_COMPACT = 2  # hand finished threads the next system of the batch (bvode.h)
 ISTAT = {"nst": 0, "nfe": 1, "nje": 2, "nqu": 3, "nqcur": 4, "imxer": 5, "lenrw": 6, "leniw": 7,
          "nlu": 8, "nni": 9, "ncfn": 10, "netf": 11}
 RSTAT = {"hu": 0, "hcur": 1, "tcur": 2, "tolsf": 3}
@@ -121,12 +122,12 @@ class dvode_t:
         self.nsys = self.neq = self.npar = 0
 
     # -- initialize(f, jac) -> initialize(problem, nsys, params) ------------------------
-    def initialize(self, problem, nsys, params=None, device=0, strict=False):
+    def initialize(self, problem, nsys, params=None, device=0, strict=False, compact=False):
         self.close()
         pid, self.neq, self.npar = problem_info(problem)
         h = C.c_void_p()
         _check(_lib.bvode_create(C.byref(h), pid, int(nsys), int(device),
-                                 FLAG_STRICT if strict else 0))
+                                 (FLAG_STRICT if strict else 0) | (FLAG_COMPACT if compact else 0)))
         self._h = h
         self.nsys = int(nsys)
         self.device = device

@@ -79,6 +79,7 @@ struct bvode_solver {
     double *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
            *d_rout = nullptr, *d_aos = nullptr, *d_yout = nullptr, *d_tout_ps = nullptr;
     int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
+    int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels)
     size_t aos_cap = 0, yout_cap = 0;
     bool params_external = false;
     int last_launches = 0;
@@ -193,7 +194,7 @@ void bvode_destroy(bvode_solver *s) {
     if (!s->params_external) cudaFree(s->d_params);
     cudaFree(s->d_y); cudaFree(s->d_t); cudaFree(s->d_tol); cudaFree(s->d_rout);
     cudaFree(s->d_aos); cudaFree(s->d_yout); cudaFree(s->d_tout_ps); cudaFree(s->d_istate);
-    cudaFree(s->d_iout); cudaFree(s->d_iaos);
+    cudaFree(s->d_iout); cudaFree(s->d_iaos); cudaFree(s->d_next);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -371,6 +372,11 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
         a.lenrw = c.lenrw;
         a.leniw = c.leniw;
         a.general = general ? 1 : 0;
+        if (s->pe->mode == 0 && (s->flags & BVODE_FLAG_COMPACT)) {
+            if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, sizeof(int)));
+            CUDA_TRY(cudaMemsetAsync(s->d_next, 0, sizeof(int), st));
+            a.next_sys = s->d_next;
+        }
         const int e = s->pe->launch(mf, a, st);
         if (e == -1000) { g_err = "mf not built for this problem"; return BVODE_ENOTIMPL; }
         if (e != 0) { g_err = std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)e); return BVODE_ECUDA; }

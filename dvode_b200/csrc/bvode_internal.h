@@ -38,6 +38,8 @@ struct KArgs {
     int *iout;                     // [12][nsys] iwork(11:22)
     int lenrw, leniw;              // iwork(17:18), M:1268-1273
     int general;                   // 1: full-driver kernel (itask 2-5, istate = 3); 0: lean itask = 1
+    int *next_sys;                 // thread-per-system kernels: counter handing out the systems beyond the
+                                   // grid (zeroed before the launch), or nullptr: one system per thread
 };
 
 struct DkyArgs {

@@ -67,13 +67,19 @@ struct Storer {
 #endif
 constexpr int kThreadTPB = BVODE_THREAD_TPB;
 
-template <class POL, bool GENERAL>
+// Each thread starts with system blockIdx*TPB + tid.  When the grid is smaller than the batch
+// (a.next_sys != nullptr: the launcher sizes it to what is resident at once), a thread whose
+// system is finished takes the next unclaimed index from a global counter and goes on inside
+// the same step loop -- the finished systems of a warp are replaced instead of idling until the
+// slowest one is done (mean / max attempts in a warp is 0.91 on the headline batch; far less
+// on heavy-tailed batches).  Which thread integrates which system does not change any result.
+// REFILL = false is the default instantiation (the hand-over code outside the step loop); the
+// compacting one is chosen by BVODE_FLAG_COMPACT: it pays off when the systems of a batch differ
+// widely in cost (measured: see DESIGN.md), and loses ~15 % on the homogeneous headline batch,
+// where replacing lanes at different times de-correlates the rare paths of a warp's 32 systems.
+template <class POL, bool GENERAL, bool REFILL>
 __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem_thread[];
-    const int sys = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sys >= a.nsys) return;
-    int ist = a.istate[sys];
-    if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return;  // failed / illegal: left untouched
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -82,87 +88,118 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     e.o = a.o;
     e.tol.r = a.rtolv;
     e.tol.a = a.atolv;
-#pragma unroll
-    for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * a.nsys + sys];
 
-    double t = a.t[sys];
-    double tolsf = 0.0;
-    bool first = false;
-    const double tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
-    if (ist == 1) {
-        if (tout0 == t) return;  // M:1101
-#pragma unroll
-        for (int i = 0; i < N; i++) e.y[i] = a.y[(size_t)i * a.nsys + sys];
-        const int r = e.init_problem(t, tout0);
-        if (r < 0) {  // illegal input detected on the device (messages 21, 22): y, t untouched
-            a.istate[sys] = r;
-            return;
+    int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    int nemit = 0;
+    double tout0 = 0.0;
+    const size_t ns = (size_t)a.nsys;
+
+    // ---- the kernel epilogue for one system: y, t, istate, the persistent state, optional outputs
+    auto store = [&](int ist, double t) {
+        if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
+            a.istate[sys] = IST_ILLEGAL;
+            if (nemit == 0) return;      // nothing was done: y, t and the state stay as they were
+            ist = IST_ILLEGAL;
         }
-        first = true;
-    } else {
-        Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
+        if (a.y_out) {  // a system that failed keeps its last state in the remaining output slots
+            for (int k2 = nemit; k2 < a.nout; k2++) {
+#pragma unroll
+                for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * ns + sys] = e.y[i];
+            }
+        }
+        double tolsf = 0.0;
+        if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
+            tolsf = 2.0 * kUround * e.norm_y0();  // M:1626, 1632, 1641
+#pragma unroll
+        for (int i = 0; i < N; i++) a.y[(size_t)i * ns + sys] = e.y[i];
+        a.t[sys] = t;
+        a.istate[sys] = ist;
+        {
+            Storer st{a.dstate + sys, a.istate_store + sys, ns};
+            visit_state(e, st);
+        }
+        // optional outputs, M:1670-1684 (success) / M:1708-1723 (failure)
+        a.rout[0 * ns + sys] = e.hot.sd(SD_HU);
+        a.rout[1 * ns + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
+        a.rout[2 * ns + sys] = e.c.tn;
+        a.rout[3 * ns + sys] = tolsf;
+        a.iout[0 * ns + sys] = e.hot.si(SI_NST);
+        a.iout[1 * ns + sys] = e.hot.si(SI_NFE);
+        a.iout[2 * ns + sys] = e.hot.si(SI_NJE);
+        a.iout[3 * ns + sys] = e.hot.si(SI_NQU);
+        a.iout[4 * ns + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
+        a.iout[5 * ns + sys] =
+            (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
+        a.iout[6 * ns + sys] = a.lenrw;
+        a.iout[7 * ns + sys] = a.leniw;
+        a.iout[8 * ns + sys] = e.hot.si(SI_NLU);
+        a.iout[9 * ns + sys] = e.hot.si(SI_NNI);
+        a.iout[10 * ns + sys] = e.hot.si(SI_NCFN);
+        a.iout[11 * ns + sys] = e.hot.si(SI_NETF);
+    };
+    // ---- the kernel prologue for system `sys`: 0 = nothing to do for it, 1 = first call, 2 = continuation
+    auto load = [&]() -> int {
+        const int ist = a.istate[sys];
+        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return 0;  // failed / illegal: left untouched
+#pragma unroll
+        for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * ns + sys];
+        const double t = a.t[sys];
+        tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
+        nemit = 0;
+        if (ist == 1) {
+            if (tout0 == t) return 0;  // M:1101
+#pragma unroll
+            for (int i = 0; i < N; i++) e.y[i] = a.y[(size_t)i * ns + sys];
+            const int r = e.init_problem(t, tout0);
+            if (r < 0) {  // illegal input detected on the device (messages 21, 22): y, t untouched
+                a.istate[sys] = r;
+                return 0;
+            }
+            return 1;
+        }
+        Loader ld{a.dstate + sys, a.istate_store + sys, ns};
         visit_state(e, ld);
         e.c.L = e.c.nq + 1;
         e.c.kflag = 0;
         e.c.jcur = 0;
         if (e.hot.si(SI_INIT) != 1) {  // M:1102-1106
             a.istate[sys] = IST_ILLEGAL;
-            return;
+            return 0;
         }
         if (GENERAL && ist == 3) e.restart_istate3(true);  // M:1383-1390
-    }
+        return 2;
+    };
 
-    int nemit = 0;
-    ist = e.template run<GENERAL>(
-        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
+    e.template run<GENERAL, REFILL>(
+        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; },
         [&](int k, const double (&yk)[N]) {
             nemit = k + 1;
             if (a.y_out) {
 #pragma unroll
-                for (int i = 0; i < N; i++) a.y_out[((size_t)k * N + i) * a.nsys + sys] = yk[i];
+                for (int i = 0; i < N; i++) a.y_out[((size_t)k * N + i) * ns + sys] = yk[i];
+            }
+        },
+        [&](bool have, int ist, double t) -> int {
+            if constexpr (REFILL) {
+                if (have) {
+                    store(ist, t);
+                    sys = (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
+                }
+                int got = 0;
+#pragma unroll 1
+                while (got == 0 && sys < a.nsys) {
+                    got = load();
+                    if (got == 0) sys = (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
+                }
+                return got;
+            } else {  // one system per thread and launch
+                if (have) {
+                    store(ist, t);
+                    return 0;
+                }
+                return (sys < a.nsys) ? load() : 0;
             }
         });
-    if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
-        a.istate[sys] = IST_ILLEGAL;
-        if (nemit == 0) return;      // nothing was done: y, t and the state stay as they were
-        ist = IST_ILLEGAL;
-    }
-    if (a.y_out) {  // a system that failed keeps its last state in the remaining output slots
-        for (int k2 = nemit; k2 < a.nout; k2++) {
-#pragma unroll
-            for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * a.nsys + sys] = e.y[i];
-        }
-    }
-    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
-        tolsf = 2.0 * kUround * e.norm_y0();  // M:1626, 1632, 1641
-
-#pragma unroll
-    for (int i = 0; i < N; i++) a.y[(size_t)i * a.nsys + sys] = e.y[i];
-    a.t[sys] = t;
-    a.istate[sys] = ist;
-    {
-        Storer st{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
-        visit_state(e, st);
-    }
-    // optional outputs, M:1670-1684 (success) / M:1708-1723 (failure)
-    const size_t ns = (size_t)a.nsys;
-    a.rout[0 * ns + sys] = e.hot.sd(SD_HU);
-    a.rout[1 * ns + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
-    a.rout[2 * ns + sys] = e.c.tn;
-    a.rout[3 * ns + sys] = tolsf;
-    a.iout[0 * ns + sys] = e.hot.si(SI_NST);
-    a.iout[1 * ns + sys] = e.hot.si(SI_NFE);
-    a.iout[2 * ns + sys] = e.hot.si(SI_NJE);
-    a.iout[3 * ns + sys] = e.hot.si(SI_NQU);
-    a.iout[4 * ns + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
-    a.iout[5 * ns + sys] =
-        (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
-    a.iout[6 * ns + sys] = a.lenrw;
-    a.iout[7 * ns + sys] = a.leniw;
-    a.iout[8 * ns + sys] = e.hot.si(SI_NLU);
-    a.iout[9 * ns + sys] = e.hot.si(SI_NNI);
-    a.iout[10 * ns + sys] = e.hot.si(SI_NCFN);
-    a.iout[11 * ns + sys] = e.hot.si(SI_NETF);
 }
 
 // dvindy for any k (M:1878-1959) from the stored state; one thread per system.
@@ -288,8 +325,6 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
     const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
     if (sys >= nsys) return;  // whole warp
-    int ist = a.istate[sys];
-    if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return;
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -297,27 +332,31 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
     e.o = a.o;
     e.tol.r = (ln < N) ? a.rtol[ln] : 0.0;
     e.tol.a = (ln < N) ? a.atol[ln] : 1.0;  // padding lanes: finite weight, value always 0
-    Prob::load_par(e.par, a.params, nsys, sys, ln);
     const double *dl, *db;
     const int *il;
     int nblock;
     warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.o.ml, a.o.mu, smem, dl, db, il,
               nblock);
+    int nemit = 0;
+    double tout0 = 0.0;
 
-    double t = a.t[sys];
-    double tolsf = 0.0;
-    bool first = false;
-    const double tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
-    if (ist == 1) {
-        if (tout0 == t) return;  // M:1101
-        e.y[0] = (ln < N) ? a.y[(size_t)ln * nsys + sys] : 0.0;
-        const int r = e.init_problem(t, tout0);
-        if (r < 0) {
-            if (ln == 0) a.istate[sys] = r;
-            return;
+    // ---- the kernel prologue: 0 = nothing to do for this system, 1 = first call, 2 = continuation
+    auto load = [&]() -> int {
+        const int ist = a.istate[sys];
+        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return 0;
+        Prob::load_par(e.par, a.params, nsys, sys, ln);
+        const double t = a.t[sys];
+        tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
+        if (ist == 1) {
+            if (tout0 == t) return 0;  // M:1101
+            e.y[0] = (ln < N) ? a.y[(size_t)ln * nsys + sys] : 0.0;
+            const int r = e.init_problem(t, tout0);
+            if (r < 0) {
+                if (ln == 0) a.istate[sys] = r;
+                return 0;
+            }
+            return 1;
         }
-        first = true;
-    } else {
         WarpLoader ld{a.dstate, dl, db, a.istate_store, il, nsys, sys, ln, nblock};
         visit_state(e, ld);
         e.c.L = e.c.nq + 1;
@@ -325,56 +364,67 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
         e.c.jcur = 0;
         if (e.hot.si(SI_INIT) != 1) {
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
-            return;
+            return 0;
         }
         if (GENERAL && ist == 3) e.restart_istate3(ln == 0);
-    }
+        return 2;
+    };
+    // ---- the kernel epilogue
+    auto store = [&](int ist, double t) {
+        if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
+            if (ln == 0) a.istate[sys] = IST_ILLEGAL;
+            if (nemit == 0) return;
+            ist = IST_ILLEGAL;
+        }
+        if (a.y_out && ln < N) {
+            for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
+        }
+        double tolsf = 0.0;
+        if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
+            tolsf = 2.0 * kUround * e.norm_y0();
+        const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
 
-    int nemit = 0;
-    ist = e.template run<GENERAL>(
-        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; }, first, t,
+        if (ln < N) a.y[(size_t)ln * nsys + sys] = e.y[0];
+        {
+            WarpStorer st{a.dstate, const_cast<double *>(dl), const_cast<double *>(db),
+                          a.istate_store, const_cast<int *>(il), nsys, sys, ln, nblock};
+            visit_state(e, st);
+        }
+        if (ln == 0) {
+            a.t[sys] = t;
+            a.istate[sys] = ist;
+            a.rout[0 * nsys + sys] = e.hot.sd(SD_HU);
+            a.rout[1 * nsys + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
+            a.rout[2 * nsys + sys] = e.c.tn;
+            a.rout[3 * nsys + sys] = tolsf;
+            a.iout[0 * nsys + sys] = e.hot.si(SI_NST);
+            a.iout[1 * nsys + sys] = e.hot.si(SI_NFE);
+            a.iout[2 * nsys + sys] = e.hot.si(SI_NJE);
+            a.iout[3 * nsys + sys] = e.hot.si(SI_NQU);
+            a.iout[4 * nsys + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
+            a.iout[5 * nsys + sys] = imx;
+            a.iout[6 * nsys + sys] = a.lenrw;
+            a.iout[7 * nsys + sys] = a.leniw;
+            a.iout[8 * nsys + sys] = e.hot.si(SI_NLU);
+            a.iout[9 * nsys + sys] = e.hot.si(SI_NNI);
+            a.iout[10 * nsys + sys] = e.hot.si(SI_NCFN);
+            a.iout[11 * nsys + sys] = e.hot.si(SI_NETF);
+        }
+    };
+
+    e.template run<GENERAL, false>(
+        a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; },
         [&](int k, const double (&yk)[1]) {
             nemit = k + 1;
             if (a.y_out && ln < N) a.y_out[((size_t)k * N + ln) * nsys + sys] = yk[0];
+        },
+        [&](bool have, int ist, double t) -> int {  // one system per warp and launch
+            if (have) {
+                store(ist, t);
+                return 0;
+            }
+            return load();
         });
-    if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
-        if (ln == 0) a.istate[sys] = IST_ILLEGAL;
-        if (nemit == 0) return;
-        ist = IST_ILLEGAL;
-    }
-    if (a.y_out && ln < N) {
-        for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
-    }
-    if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
-        tolsf = 2.0 * kUround * e.norm_y0();
-    const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
-
-    if (ln < N) a.y[(size_t)ln * nsys + sys] = e.y[0];
-    {
-        WarpStorer st{a.dstate, const_cast<double *>(dl), const_cast<double *>(db),
-                      a.istate_store, const_cast<int *>(il), nsys, sys, ln, nblock};
-        visit_state(e, st);
-    }
-    if (ln == 0) {
-        a.t[sys] = t;
-        a.istate[sys] = ist;
-        a.rout[0 * nsys + sys] = e.hot.sd(SD_HU);
-        a.rout[1 * nsys + sys] = (ist == IST_OK) ? e.hot.sd(SD_HNEW) : e.c.h;
-        a.rout[2 * nsys + sys] = e.c.tn;
-        a.rout[3 * nsys + sys] = tolsf;
-        a.iout[0 * nsys + sys] = e.hot.si(SI_NST);
-        a.iout[1 * nsys + sys] = e.hot.si(SI_NFE);
-        a.iout[2 * nsys + sys] = e.hot.si(SI_NJE);
-        a.iout[3 * nsys + sys] = e.hot.si(SI_NQU);
-        a.iout[4 * nsys + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
-        a.iout[5 * nsys + sys] = imx;
-        a.iout[6 * nsys + sys] = a.lenrw;
-        a.iout[7 * nsys + sys] = a.leniw;
-        a.iout[8 * nsys + sys] = e.hot.si(SI_NLU);
-        a.iout[9 * nsys + sys] = e.hot.si(SI_NNI);
-        a.iout[10 * nsys + sys] = e.hot.si(SI_NCFN);
-        a.iout[11 * nsys + sys] = e.hot.si(SI_NETF);
-    }
 }
 
 template <class POL>
@@ -401,21 +451,44 @@ __global__ void __launch_bounds__(kWarpTPB) dvindy_warp_kernel(const __grid_cons
 }
 
 // --------------------------------------------------------------- launchers ------
+// Grid of the compacting thread-per-system kernel: exactly the resident capacity (SMs x CTAs per
+// SM); finished threads claim the remaining systems through a.next_sys.
+template <class K>
+static int resident_grid(K kernel, size_t smem) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreadTPB, smem);
+    return (sms > 0 && per_sm > 0) ? sms * per_sm : 0;
+}
 template <class POL>
-static int launch_thread(const KArgs &a, cudaStream_t st) {
-    const int grid = (a.nsys + kThreadTPB - 1) / kThreadTPB;
+static int launch_thread(const KArgs &a0, cudaStream_t st) {
+    KArgs a = a0;
     static_assert(POL::kTPB == kThreadTPB, "shared-memory stride");
     size_t smem = POL::kSmemBytes;
     if (const char *pad = getenv("BVODE_PAD_SMEM")) smem += (size_t)atol(pad);  // occupancy experiments
+    const int need = (a.nsys + kThreadTPB - 1) / kThreadTPB;
     if (a.general) {
+        a.next_sys = nullptr;
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute(vode_thread_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vode_thread_kernel<POL, true><<<grid, kThreadTPB, smem, st>>>(a);
-    } else {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(vode_thread_kernel<POL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vode_thread_kernel<POL, false><<<grid, kThreadTPB, smem, st>>>(a);
+            cudaFuncSetAttribute(vode_thread_kernel<POL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        vode_thread_kernel<POL, true, false><<<need, kThreadTPB, smem, st>>>(a);
+        return (int)cudaGetLastError();
     }
+    if (a.next_sys) {  // BVODE_FLAG_COMPACT
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(vode_thread_kernel<POL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static int capacity = -1;  // per instantiation
+        if (capacity < 0) capacity = resident_grid(vode_thread_kernel<POL, false, true>, smem);
+        if (capacity > 0 && need > capacity) {
+            vode_thread_kernel<POL, false, true><<<capacity, kThreadTPB, smem, st>>>(a);
+            return (int)cudaGetLastError();
+        }
+        a.next_sys = nullptr;  // the whole batch is resident at once: nothing to hand out
+    }
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(vode_thread_kernel<POL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vode_thread_kernel<POL, false, false><<<need, kThreadTPB, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 template <class POL>

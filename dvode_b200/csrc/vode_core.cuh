@@ -874,9 +874,25 @@ struct Engine {
     // GENERAL = false is the lean instantiation for itask = 1 (the hot path).  GENERAL = true
     // adds the rest of the driver: itask 2-5 with tcrit / kuth (blocks D and F, M:1399-1483,
     // 1586-1623; dvstep M:2100-2103) and the istate = 3 restart (jstart = -1, M:2031-2079).
-    template <bool GENERAL, class TOUT, class EMIT>
-    BV_DEV int run(int nout, TOUT tout_of, bool first, double &t_out, EMIT emit) {
+    //
+    // Systems come and go INSIDE the loop: `next(have, ist, t_out)` is called whenever this lane
+    // has no system to work on -- at the start (have = false), and when its system is finished
+    // (have = true; ist / t_out are its output istate and t, this->y its output solution).  It
+    // stores the finished system, loads another one (init_problem for istate = 1, the saved
+    // state otherwise) and returns 0 = no more work, 1 = a first call (init_problem ran in this
+    // launch: goto 200, M:1381), 2 = a continuation call.  A kernel that gives each lane exactly
+    // one system returns 0 the second time; the thread-per-system kernel hands finished lanes the
+    // next system of the batch, so that a warp is not held by its slowest system alone
+    // (compaction of finished systems).
+    // REFILL = false: `next` runs once before the loop and once after it (the lean shape: the
+    // hand-over code is outside the instruction-cache-sensitive step loop); REFILL = true: inside.
+    template <bool GENERAL, bool REFILL, class TOUT, class EMIT, class NEXT>
+    BV_DEV void run(int nout, TOUT tout_of, EMIT emit, NEXT next) {
         constexpr int kfc = -3, kfh = -7, mxncf = 10;
+#ifndef BVODE_REFILL_GROUP
+#define BVODE_REFILL_GROUP 4
+#endif
+        [[maybe_unused]] constexpr int kRefillGroup = BVODE_REFILL_GROUP;
         [[maybe_unused]] constexpr double addon = 1.0e-6;
         constexpr double bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
                          etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
@@ -888,21 +904,15 @@ struct Engine {
 #endif
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
-        int nslast = hot.si(SI_NST);  // M:1399 (and 1337 on the first call)
+        int nslast = 0;  // M:1399 (and 1337 on the first call)
         const int lmax = o.maxord + 1;
-        int istate = 0;  // 0 = keep stepping; every loop below has a single exit (see dvnlsd)
+        int istate = 1;  // 0 = keep stepping; every loop below has a single exit (see dvnlsd).
+                         // Non-zero with have == false: nothing loaded yet.
+        bool have = false, alive = true;
         int kout = 0;
-        double tout = tout_of(0);
+        double tout = 0.0;
         // "reached": tout lies inside the step just taken -> interpolate instead of stepping
-        bool reached = !GENERAL && !first && !((c.tn - tout) * c.h < 0.0);
-        if (reached) {
-            // block D on a continuation call checks dvindy's flag (message 27, M:1459-1464)
-            double dky[NLOC];
-            if (dvindy0(tout, dky) != 0) {
-                reached = false;
-                istate = IST_ILLEGAL_ENTRY;
-            }
-        }
+        bool reached = false;
         // ---- GENERAL: what the current call does next (blocks D and F for every itask)
         enum { ACT_STEP = 0, ACT_RET_INTERP = 1, ACT_RET_YH = 2, ACT_ILLEGAL = 3 };
         [[maybe_unused]] int act = ACT_STEP, kuth = 0;
@@ -967,20 +977,78 @@ struct Engine {
             }
             return ((c.tn - to) * c.h < 0.0) ? ACT_STEP : ACT_RET_INTERP;
         };
-        if constexpr (GENERAL) {
-            if (!first) act = block_d(tout);
-        }
-
         int entry = E_NEWSTEP;
-        bool skip_ewt = first;
-        double told = c.tn;
+        bool skip_ewt = false;
+        double told = 0.0;
         int ncf = 0, nflag = 0;
 
+        auto handover = [&]() {
+            // ---- this lane's system is finished (or none is loaded yet): hand it over, get the next
+            int ist_ret = 0;
+            double t_ret = 0.0;
+            if (have) {
+                if (istate == IST_OK) {
+                    t_ret = GENERAL ? t_emit : tout;  // y was set by the last emit
+                    ist_ret = IST_OK;
+                } else if (istate == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry: that call changes nothing
+                    t_ret = (GENERAL && kout > 0) ? t_emit : tout;
+                    ist_ret = istate;
+                } else {
+                    // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
+                    t_ret = c.tn;
+                    ist_ret = istate;
+                }
+            }
+            const int got = next(have, ist_ret, t_ret);
+            if (got == 0) {
+                alive = false;
+            } else {
+                // ---- entry of the first call for the new system (block D on a continuation call)
+                const bool first = (got == 1);
+                have = true;
+                istate = 0;
+                kout = 0;
+                tout = tout_of(0);
+                nslast = hot.si(SI_NST);
+                reached = !GENERAL && !first && !((c.tn - tout) * c.h < 0.0);
+                if (reached) {
+                    // block D on a continuation call checks dvindy's flag (message 27, M:1459-1464)
+                    double dky[NLOC];
+                    if (dvindy0(tout, dky) != 0) {
+                        reached = false;
+                        istate = IST_ILLEGAL_ENTRY;
+                    }
+                }
+                if constexpr (GENERAL) {
+                    act = ACT_STEP;
+                    kuth = 0;
+                    ihit = false;
+                    t_emit = tout;
+                    if (!first) act = block_d(tout);
+                }
+                entry = E_NEWSTEP;
+                skip_ewt = first;
+                told = c.tn;
+                ncf = 0;
+                nflag = 0;
+            }
+        };
+        if constexpr (!REFILL) handover();
 #pragma unroll 1
-        while (istate == 0) {
+        while (REFILL ? (__any_sync(0xffffffffu, alive) != 0) : (alive && istate == 0)) {
+            if constexpr (REFILL) {
+                // Finished lanes are replaced in groups: a lane waits until kRefillGroup lanes of
+                // its warp are idle (or nothing else runs), so that the hand-over code runs for
+                // several lanes at once and the systems that start together stay in step.
+                const unsigned idle = __ballot_sync(0xffffffffu, alive && istate != 0);
+                const unsigned busy = __ballot_sync(0xffffffffu, alive && istate == 0);
+                if (alive && istate != 0 && (__popc(idle) >= kRefillGroup || busy == 0u)) handover();
+            }
             // ---- block G / D: output points reached by the last step (M:1457-1467, 1618-1622)
 #pragma unroll 1
-            while (reached) {
+            while (REFILL ? (reached && istate == 0) : reached) {
                 dvindy0(tout, y);
                 emit(kout, y);
                 kout = kout + 1;
@@ -1416,19 +1484,9 @@ struct Engine {
                 }
             }  // if (istate == 0)
         }
-        if (istate == IST_OK) {
-            t_out = GENERAL ? t_emit : tout;  // y was set by the last emit
-            return IST_OK;
+        if constexpr (!REFILL) {
+            if (have) handover();
         }
-        if (istate == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry: that call changes nothing
-            if (GENERAL && kout > 0) t_out = t_emit;
-            return istate;
-        }
-        // ---- block H: unsuccessful return (M:1708-1723): y <- yh(:,1), t <- tn
-#pragma unroll
-        for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
-        t_out = c.tn;
-        return istate;
     }
 };
 

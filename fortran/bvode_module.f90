@@ -22,6 +22,7 @@ module bvode_module
    integer(c_int), parameter, public :: BVODE_OK = 0, BVODE_EINVAL = -1, BVODE_ENOTIMPL = -2, &
                                         BVODE_ECUDA = -3, BVODE_ENOMEM = -4, BVODE_EISTATE = -5
    integer(c_int), parameter, public :: BVODE_FLAG_STRICT = 1
+   integer(c_int), parameter, public :: BVODE_FLAG_COMPACT = 2
 
    interface
       function bvode_problem_lookup(name) bind(C, name='bvode_problem_lookup') result(id)

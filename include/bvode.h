@@ -53,7 +53,11 @@ enum {
 
 /* flags for bvode_create */
 enum {
-    BVODE_FLAG_STRICT = 1 /* run the -fmad=false / portable-pow build (bit-for-bit parity runs) */
+    BVODE_FLAG_STRICT = 1, /* run the -fmad=false / portable-pow build (bit-for-bit parity runs) */
+    BVODE_FLAG_COMPACT = 2 /* thread-per-system kernels, itask = 1: launch only as many threads as are
+                            * resident at once and give a thread whose system is finished the next
+                            * unclaimed system of the batch (compaction of finished systems).  Results
+                            * are identical; pays off when the systems differ widely in cost. */
 };
 
 /* ---- problem registry: stands in for the procedure arguments of initialize (M:377-505) ---- */

@@ -227,3 +227,43 @@ def test_empty_batch_is_refused_at_create():
     B = _B()
     with pytest.raises(Exception):
         B.dvode_t().initialize("robertson", 0, np.zeros((0, 3)))
+
+
+# ------------------------------------------------------- compaction of finished systems ------
+@pytest.mark.parametrize("strict", [False, True])
+def test_compaction_gives_identical_results(strict):
+    """BVODE_FLAG_COMPACT: the grid holds only the threads resident at once and a thread whose
+    system is finished takes the next unclaimed one.  Which thread integrates which system must
+    not change a single bit: same batch (larger than the resident capacity, ragged, with a
+    heavy tail through per-system tout) with and without the flag."""
+    B = _B()
+    nsys = (1 << 17) + 77
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_HEADLINE
+    tps = np.full(nsys, 40.0)
+    tps[::61] = 4.0e6
+    out = []
+    for compact in (False, True):
+        s = B.dvode_t().initialize("robertson", nsys, par, strict=strict, compact=compact)
+        y = np.tile(np.array(B.batches.ROBERTSON_Y0), (nsys, 1))
+        t = np.zeros(nsys)
+        ist = np.ones(nsys, dtype=np.int32)
+        rw = np.zeros((nsys, 20))
+        iw = np.zeros((nsys, 30), dtype=np.int32)
+        iw[0, 5] = 100000
+        s.solve(3, y, t, tps, tol["itol"], tol["rtol"], tol["atol"], 1, ist, 1, rw, 20, iw, 30, 21)
+        assert (ist == 2).all()
+        # a continuation call (istate = 2: the saved state is reloaded) one decade on
+        s.solve(3, y, t, tps * 10.0, tol["itol"], tol["rtol"], tol["atol"], 1, ist, 1, rw, 20, iw, 30, 21)
+        assert (ist == 2).all()
+        out.append((y.copy(), t.copy(), rw[:, 10:14].copy(), iw[:, 10:22].copy()))
+        s.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    # and against the oracle on a sample (strict build: bit for bit)
+    if strict:
+        idx = np.arange(0, nsys, 997)
+        ref = O.batch_solve("robertson", par[idx], B.batches.ROBERTSON_Y0, 0.0, [40.0, 400.0], tol["rtol"],
+                            tol["atol"], 21, itol=2, iopt=1, mxstep=100000, pow_mode=1)
+        short = tps[idx] == 40.0
+        assert np.array_equal(out[1][0][idx][short], ref["y"][short, 1])
