@@ -63,7 +63,7 @@ struct Storer {
 
 // ------------------------------------------------------- thread-per-system ------
 #ifndef BVODE_THREAD_TPB
-#define BVODE_THREAD_TPB 128
+#define BVODE_THREAD_TPB 32
 #endif
 constexpr int kThreadTPB = BVODE_THREAD_TPB;
 

@@ -247,7 +247,10 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
     static constexpr bool kPlain = false;
-    static constexpr int kMinBlocks = 6;  // CTAs per SM (see bvode_kernels.cuh)
+#ifndef BVODE_DENSE_MINBLOCKS
+#define BVODE_DENSE_MINBLOCKS 5
+#endif
+    static constexpr int kMinBlocks = BVODE_DENSE_MINBLOCKS;  // CTAs per SM (see bvode_kernels.cuh)
     static constexpr int LDP = N | 1;
     static constexpr int kBlockDoubles = N * LDP + 16 + ((N * LDP) & 1);  // the matrix, then perm[32] (ints), 16-byte aligned
     static_assert(MITER == 1 || MITER == 2, "dense policy");
@@ -605,7 +608,10 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = true;
     static constexpr bool kPlain = false;
-    static constexpr int kMinBlocks = 8;
+#ifndef BVODE_BAND_MINBLOCKS
+#define BVODE_BAND_MINBLOCKS 8
+#endif
+    static constexpr int kMinBlocks = BVODE_BAND_MINBLOCKS;
     static_assert(MITER == 4 || MITER == 5, "band policy");
 
     struct Lin {
