@@ -302,6 +302,14 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     }
 
     // ---- dgefa, LP:46-120, rows across lanes ----------------------------------------
+    // Two pivot steps per pass over the rows (a rank-2 update): the multipliers of step k are
+    // applied to column k+1 alone, the pivot of step k+1 is chosen from it, and every later
+    // column j then takes  row(j) += p1(j)*m  and  row(j) += p2'(j)*m1  in one load / store of the
+    // row element, where p2'(j) = p2(j) + p1(j)*m(l1) is the second pivot row AFTER step k --
+    // formed by every lane from two broadcast loads exactly as the lane that owns that row forms it.
+    // Each element sees the same two operations, on the same operands, in the same order as in
+    // LINPACK's column-by-column elimination; the shared-memory traffic per element update drops
+    // from 5 wavefronts (broadcast + row load + row store) to 3.
     BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();
         const bool real = real_lane();
@@ -310,20 +318,27 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         const unsigned perma = pa + (N * LDP + ((N * LDP) & 1)) * 8;
         int pos = real ? ln : 64;
         int info = 0;
-        __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < N - 1; k++) {
-            const bool act = real && (pos >= k);
-            const unsigned rk = rowa + k * 8;
-            const double v = lds_d(rk);
-            const int l = pivot_lane(v, act, pos);
-            const double alk = shfl_d(v, l);
+        // idamax + the interchange of LP:96-110 (the two rows exchange positions) for column k,
+        // v = this lane's entry of that column
+        auto pick = [&](int k, double v, int &l, double &alk) {
+            l = pivot_lane(v, real && (pos >= k), pos);
+            alk = shfl_d(v, l);
             const int pl = __shfl_sync(kFull, pos, l);
             if (ln == k) lin.ipv = l;
             sts_i(perma + k * 4, l);  // the same value from every lane
-            // the interchange of LP:96-110: the two rows exchange positions
             if (pos == k) pos = pl;
             if (ln == l) pos = k;
+        };
+        __syncwarp();
+        int k = 0;
+#pragma unroll 1
+        while (k < N - 1) {
+            const unsigned rk = rowa + k * 8;
+            const double v = lds_d(rk);
+            int l;
+            double alk;
+            pick(k, v, l, alk);
+            int adv = 1;
             if (alk == 0.0) {
                 info = k + 1;
             } else {
@@ -342,9 +357,70 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 const double m = t * v;
                 if (real) sts_d(rk, (ln == l) ? rp : m);
 #endif
-                if (below) {
-                    // row(j) += pivot_row(j) * m, j > k (LP:105-118); loads first, then stores
-                    unsigned ar = rk + 8, ap = pa + l * (LDP * 8) + (k + 1) * 8;
+                const unsigned pr0 = pa + l * (LDP * 8);  // the pivot row: broadcasts
+                bool pair = false;
+                if (k + 1 < N - 1) {
+                    // ---- column k+1 after step k, and its pivot
+                    adv = 2;
+                    double w = lds_d<8>(rk);
+                    const double p1k = lds_d<8>(pr0 + k * 8);
+                    if (below) w = w + p1k * m;
+                    int l1;
+                    double alk1;
+                    pick(k + 1, w, l1, alk1);
+                    if (alk1 == 0.0) {
+                        info = k + 2;  // LP:87-88: nothing is eliminated in column k+1; step k is completed below
+                    } else {
+                        pair = true;
+                        const bool below1 = real && (pos > k + 1);
+#if BVODE_STRICT
+                        const double t1 = -1.0 / alk1;
+                        const double m1 = t1 * w;
+                        if (below1) sts_d<8>(rk, m1);
+                        if (ln == l1) sts_d<8>(rk, w);
+#else
+                        const double rp1 = qrcp(alk1);
+                        const double t1 = -rp1;
+                        const double m1 = t1 * w;
+                        if (real) sts_d<8>(rk, (ln == l1) ? rp1 : m1);
+#endif
+                        const double ml1 = shfl_d(m, l1);  // multiplier of the second pivot row in step k
+                        const unsigned pr1 = pa + l1 * (LDP * 8);
+                        // every lane runs the loop (the __syncwarp between the loads and the stores
+                        // orders the other lanes' reads of row l1 before its owner's update of it)
+                        unsigned ar = rk + 16, a1 = pr0 + (k + 2) * 8, a2 = pr1 + (k + 2) * 8;
+                        int cnt = N - 2 - k;
+#pragma unroll 1
+                        for (; cnt >= 4; cnt -= 4, ar += 32, a1 += 32, a2 += 32) {
+                            const double p0 = lds_d<0>(a1), p1 = lds_d<8>(a1), p2 = lds_d<16>(a1), p3 = lds_d<24>(a1);
+                            const double q0 = lds_d<0>(a2), q1 = lds_d<8>(a2), q2 = lds_d<16>(a2), q3 = lds_d<24>(a2);
+                            double r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
+                            __syncwarp();
+                            r0 = r0 + p0 * m; r1 = r1 + p1 * m; r2 = r2 + p2 * m; r3 = r3 + p3 * m;
+                            if (below1) {
+                                r0 = r0 + (q0 + p0 * ml1) * m1;
+                                r1 = r1 + (q1 + p1 * ml1) * m1;
+                                r2 = r2 + (q2 + p2 * ml1) * m1;
+                                r3 = r3 + (q3 + p3 * ml1) * m1;
+                            }
+                            if (below) {
+                                sts_d<0>(ar, r0); sts_d<8>(ar, r1); sts_d<16>(ar, r2); sts_d<24>(ar, r3);
+                            }
+                        }
+#pragma unroll 1
+                        for (; cnt > 0; cnt--, ar += 8, a1 += 8, a2 += 8) {
+                            const double p0 = lds_d(a1), q0 = lds_d(a2);
+                            double r0 = lds_d(ar);
+                            __syncwarp();
+                            r0 = r0 + p0 * m;
+                            if (below1) r0 = r0 + (q0 + p0 * ml1) * m1;
+                            if (below) sts_d(ar, r0);
+                        }
+                    }
+                }
+                if (!pair && below) {
+                    // one step: row(j) += pivot_row(j) * m, j > k (LP:105-118); loads first, then stores
+                    unsigned ar = rk + 8, ap = pr0 + (k + 1) * 8;
                     int cnt = N - 1 - k;
 #pragma unroll 1
                     for (; cnt >= 4; cnt -= 4, ar += 32, ap += 32) {
@@ -360,6 +436,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 }
             }
             __syncwarp();
+            k += adv;
         }
         {   // the row that is left is the last pivot
             const int l = __ffs((int)__ballot_sync(kFull, real && (pos == N - 1))) - 1;
@@ -411,6 +488,10 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             const unsigned rk = rowa + k * 8;
             int l0, l1, l2, l3;
             lds_i4(perma + k * 4, l0, l1, l2, l3);
+            // (a four-step look-ahead -- the next pivot rows' b formed redundantly by every lane
+            // from broadcast entries, one shuffle latency per four steps -- was measured SLOWER,
+            // 149k vs 165k systems/s: the kernel is bound by instruction and shared-memory
+            // throughput, not by this chain)
             solve_step<true, 0>(b, rk, l0, pos, k, real);
             solve_step<true, 1>(b, rk, l1, pos, k, real);
             solve_step<true, 2>(b, rk, l2, pos, k, real);
