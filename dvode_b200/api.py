@@ -53,6 +53,8 @@ def _load():
                                          vp]
     lib.bvode_solve_schedule_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp,
                                                 C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp]
+    lib.bvode_solve_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int,
+                                       vp, vp, C.c_int, vp]
     lib.bvode_dvindy.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     lib.bvode_get_stats.argtypes = [vp, vp, vp]
     lib.bvode_state_bytes.argtypes = [vp]
@@ -194,6 +196,15 @@ class dvode_t:
             int(itol), _ptr(rtol), _ptr(atol), int(itask), C.c_void_p(istate_ptr), int(iopt),
             _ptr(rwork_opts), _ptr(iwork_opts), int(mf),
             C.c_void_p(y_out_ptr) if y_out_ptr else None, C.c_void_p(stream) if stream else None))
+
+    def solve_device(self, neq, y_ptr, t_ptr, tout_ptr, itol, rtol, atol, itask, istate_ptr, iopt,
+                     rwork_opts, iwork_opts, mf, stream=0):
+        """One call with device-resident SoA buffers and a tout per system (tout_ptr: double[nsys] in HBM)."""
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        _check(_lib.bvode_solve_device(
+            self._h, int(neq), C.c_void_p(y_ptr), C.c_void_p(t_ptr), C.c_void_p(tout_ptr), int(itol),
+            _ptr(rtol), _ptr(atol), int(itask), C.c_void_p(istate_ptr), int(iopt), _ptr(rwork_opts),
+            _ptr(iwork_opts), int(mf), C.c_void_p(stream) if stream else None))
 
     # -- dvindy(t, k, yh, ldyh, dky, iflag): yh/ldyh are the handle's device state -------
     def dvindy(self, t, k):

@@ -523,6 +523,26 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, doub
     return BVODE_OK;
 }
 
+int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_device,
+                       const double *tout_device, int itol, const double *rtol, const double *atol,
+                       int itask, int *istate_device, int iopt, const double *rwork_opts,
+                       const int *iwork_opts, int mf, void *stream) {
+    if (!s || !y_device || !t_device || !istate_device || !tout_device) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    Checked c;
+    int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, 20, 30,
+                        false, mf, &c);
+    if (rc != BVODE_OK) return rc;
+    const double tout1 = 0.0;  // unused: every system has its own tout
+    rc = run_device(s, c, mf, y_device, t_device, istate_device, 1, &tout1, tout_device, nullptr,
+                    (cudaStream_t)stream, itask != 1);
+    if (rc != BVODE_OK) return rc;
+    s->maxord = c.o.maxord;
+    CUDA_TRY(cudaGetLastError());
+    return BVODE_OK;
+}
+
 int bvode_last_launch_count(const bvode_solver *s) { return s ? s->last_launches : 0; }
 
 int bvode_get_stats(bvode_solver *s, double *rout, int *iout) {

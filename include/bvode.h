@@ -134,6 +134,12 @@ BVODE_API int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_de
                                 const double *atol, int itask, int *istate_device, int iopt,
                                 const double *rwork_opts, const int *iwork_opts, int mf,
                                 double *y_out_device, void *stream);
+/* One call (M:604-605) with inputs in HBM and a tout PER SYSTEM, tout_device[nsys] (the device-pointer form of
+ * bvode_solve with tout_per_system = 1); optional outputs through bvode_get_stats. */
+BVODE_API int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_device,
+                       const double *tout_device, int itol, const double *rtol, const double *atol,
+                       int itask, int *istate_device, int iopt, const double *rwork_opts,
+                       const int *iwork_opts, int mf, void *stream);
 /* number of kernels the last solve call launched (bench.py's gpu_launches) */
 BVODE_API int bvode_last_launch_count(const bvode_solver *s);
 

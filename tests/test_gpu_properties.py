@@ -267,3 +267,31 @@ def test_compaction_gives_identical_results(strict):
                             tol["atol"], 21, itol=2, iopt=1, mxstep=100000, pow_mode=1)
         short = tps[idx] == 40.0
         assert np.array_equal(out[1][0][idx][short], ref["y"][short, 1])
+
+
+def test_device_pointer_call_with_per_system_tout():
+    """bvode_solve_device (inputs in HBM, tout per system) = bvode_solve with tout_per_system = 1."""
+    import torch
+    B = _B()
+    nsys = 1000
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    tps = 0.4 * 10.0 ** (np.arange(nsys) % 5)
+    s = B.dvode_t().initialize("robertson", nsys, par)
+    y = np.tile(np.array(B.batches.ROBERTSON_Y0), (nsys, 1)); t = np.zeros(nsys); ist = np.ones(nsys, dtype=np.int32)
+    rw = np.zeros((nsys, 20)); iw = np.zeros((nsys, 30), dtype=np.int32)
+    s.solve(3, y, t, tps, 2, tol["rtol"], tol["atol"], 1, ist, 0, rw, 20, iw, 30, 21)
+    s.close()
+    dev = torch.device("cuda", 0)
+    s = B.dvode_t().initialize("robertson", nsys, par)
+    yd = torch.tensor(np.tile(np.array(B.batches.ROBERTSON_Y0)[:, None], (1, nsys)), dtype=torch.float64, device=dev)
+    td = torch.zeros(nsys, dtype=torch.float64, device=dev)
+    isd = torch.ones(nsys, dtype=torch.int32, device=dev)
+    tod = torch.tensor(tps, dtype=torch.float64, device=dev)
+    s.solve_device(3, yd.data_ptr(), td.data_ptr(), tod.data_ptr(), 2, tol["rtol"], tol["atol"], 1, isd.data_ptr(), 0,
+                   np.zeros(20), np.zeros(30, dtype=np.int32), 21)
+    torch.cuda.synchronize()
+    assert np.array_equal(yd.cpu().numpy().T, y)
+    assert np.array_equal(td.cpu().numpy(), t) and np.array_equal(t, tps)
+    assert np.array_equal(isd.cpu().numpy(), ist) and (ist == 2).all()
+    s.close()
