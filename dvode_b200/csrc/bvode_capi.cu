@@ -13,6 +13,7 @@
 #include <vector>
 
 // one entry per (build, problem), each from its own translation unit (bvode_registry.cu)
+#include <mutex>
 #define BVODE_NPROBLEMS 5
 extern "C" {
 const ProblemEntry *bvode_entry_fast_0(void);
@@ -26,29 +27,33 @@ const ProblemEntry *bvode_entry_strict_2(void);
 const ProblemEntry *bvode_entry_strict_3(void);
 const ProblemEntry *bvode_entry_strict_4(void);
 }
+// The problem table: the built-in problems, then whatever bvode_register_problem appended (user
+// f / jac functors compiled into a library of their own against csrc/bvode_user_problem.cuh).
+// Fixed capacity: handles keep pointers into it.
+constexpr int kMaxProblems = 64;
+static ProblemEntry g_tab_fast[kMaxProblems], g_tab_strict[kMaxProblems];
+static int g_nproblems = 0;
+static std::mutex g_tab_mutex;
+static void registry_init() {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    if (g_nproblems != 0) return;
+    g_tab_fast[0] = *bvode_entry_fast_0(); g_tab_fast[1] = *bvode_entry_fast_1();
+    g_tab_fast[2] = *bvode_entry_fast_2(); g_tab_fast[3] = *bvode_entry_fast_3();
+    g_tab_fast[4] = *bvode_entry_fast_4();
+    g_tab_strict[0] = *bvode_entry_strict_0(); g_tab_strict[1] = *bvode_entry_strict_1();
+    g_tab_strict[2] = *bvode_entry_strict_2(); g_tab_strict[3] = *bvode_entry_strict_3();
+    g_tab_strict[4] = *bvode_entry_strict_4();
+    g_nproblems = BVODE_NPROBLEMS;
+}
 static const ProblemEntry *bvode_registry_fast(int *n) {
-    static ProblemEntry tab[BVODE_NPROBLEMS];
-    static bool init = false;
-    if (!init) {
-        tab[0] = *bvode_entry_fast_0(); tab[1] = *bvode_entry_fast_1();
-        tab[2] = *bvode_entry_fast_2(); tab[3] = *bvode_entry_fast_3();
-        tab[4] = *bvode_entry_fast_4();
-        init = true;
-    }
-    *n = BVODE_NPROBLEMS;
-    return tab;
+    registry_init();
+    *n = g_nproblems;
+    return g_tab_fast;
 }
 static const ProblemEntry *bvode_registry_strict(int *n) {
-    static ProblemEntry tab[BVODE_NPROBLEMS];
-    static bool init = false;
-    if (!init) {
-        tab[0] = *bvode_entry_strict_0(); tab[1] = *bvode_entry_strict_1();
-        tab[2] = *bvode_entry_strict_2(); tab[3] = *bvode_entry_strict_3();
-        tab[4] = *bvode_entry_strict_4();
-        init = true;
-    }
-    *n = BVODE_NPROBLEMS;
-    return tab;
+    registry_init();
+    *n = g_nproblems;
+    return g_tab_strict;
 }
 
 static thread_local std::string g_err;
@@ -145,12 +150,44 @@ int bvode_problem_info(int problem, int *neq, int *npar, const char **name) {
     return BVODE_OK;
 }
 
+int bvode_plugin_abi(void) { return BVODE_PLUGIN_ABI; }
+int bvode_register_problem(const void *entry_fast, const void *entry_strict, int abi) {
+    if (!entry_fast) return BVODE_EINVAL;
+    if (abi != BVODE_PLUGIN_ABI) {
+        g_err = "bvode_register_problem: the problem library was compiled against other kernel headers (ABI tag differs)";
+        return BVODE_EINVAL;
+    }
+    registry_init();
+    const ProblemEntry *f = static_cast<const ProblemEntry *>(entry_fast);
+    const ProblemEntry *st = static_cast<const ProblemEntry *>(entry_strict);
+    if (!f->name || !f->launch || !f->state_size || !f->supports || f->neq < 1) return BVODE_EINVAL;
+    if (st && (st->neq != f->neq || st->npar != f->npar || st->mode != f->mode)) return BVODE_EINVAL;
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    for (int i = 0; i < g_nproblems; i++)
+        if (strcmp(g_tab_fast[i].name, f->name) == 0) {
+            g_err = "bvode_register_problem: a problem of this name is registered already";
+            return BVODE_EINVAL;
+        }
+    if (g_nproblems >= kMaxProblems) return BVODE_ENOMEM;
+    const int id = g_nproblems;
+    g_tab_fast[id] = *f;
+    if (st) {
+        g_tab_strict[id] = *st;
+    } else {  // no strict build supplied: a handle with BVODE_FLAG_STRICT is refused at create
+        g_tab_strict[id] = *f;
+        g_tab_strict[id].launch = nullptr;
+    }
+    g_nproblems = id + 1;
+    return id;
+}
+
 // -------------------------------------------------------------------- lifetime ----
 int bvode_create(bvode_solver **out, int problem, int nsys, int device, unsigned flags) {
     if (!out || nsys <= 0) return BVODE_EINVAL;
     int n;
     const ProblemEntry *e = registry(flags, &n);
     if (problem < 0 || problem >= n) return BVODE_EINVAL;
+    if (!e[problem].launch) { g_err = "this problem was registered without a strict build"; return BVODE_ENOTIMPL; }
     CUDA_TRY(cudaSetDevice(device));
     bvode_solver *s = new bvode_solver();
     s->problem = problem;

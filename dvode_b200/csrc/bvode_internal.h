@@ -62,3 +62,7 @@ struct ProblemEntry {
     int (*launch)(int mf, const KArgs &a, cudaStream_t st);
     int (*launch_dky)(int mf, const DkyArgs &a, cudaStream_t st);
 };
+
+// Tag a problem library passes to bvode_register_problem: it must have been compiled against
+// these very structs (bump the leading number when KArgs / DkyArgs / ProblemEntry change meaning).
+#define BVODE_PLUGIN_ABI ((int)(2 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))

@@ -25,6 +25,14 @@ module bvode_module
    integer(c_int), parameter, public :: BVODE_FLAG_COMPACT = 2
 
    interface
+      !> A user problem library (csrc/bvode_user_problem.cuh) loaded by the application: pass what its
+      !> bvode_user_entry_fast() / bvode_user_entry_strict() / bvode_user_abi_fast() return.
+      function bvode_register_problem(entry_fast, entry_strict, abi) bind(C, name='bvode_register_problem') result(id)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: entry_fast, entry_strict
+         integer(c_int), value :: abi
+         integer(c_int) :: id
+      end function
       function bvode_problem_lookup(name) bind(C, name='bvode_problem_lookup') result(id)
          import :: c_int, c_char
          character(kind=c_char), intent(in) :: name(*)
@@ -122,7 +130,7 @@ module bvode_module
       end function
    end interface
 
-   public :: bvode_problem_lookup, bvode_problem_info, bvode_create, bvode_destroy, &
+   public :: bvode_register_problem, bvode_problem_lookup, bvode_problem_info, bvode_create, bvode_destroy, &
              bvode_last_error, bvode_set_params, bvode_solve, bvode_solve_schedule, &
              bvode_dvindy, bvode_get_stats, bvode_state_bytes, bvode_dvsrco, &
              bvode_istate_summary, bvode_format_message

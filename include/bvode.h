@@ -65,6 +65,15 @@ BVODE_API int bvode_problem_count(void);
 BVODE_API int bvode_problem_lookup(const char *name);                        /* id >= 0, or -1 */
 BVODE_API int bvode_problem_info(int problem, int *neq, int *npar, const char **name);
 
+/* Register a user problem at run time: the f / jac (and optional dewset / dvnorm) procedure arguments of
+ * initialize (M:377-505) as a __device__ functor compiled into a library of its own with
+ * dvode_b200/csrc/bvode_user_problem.cuh (examples/decay_chain.cu).  entry_fast /
+ * entry_strict are what that library's bvode_user_entry_fast() / bvode_user_entry_strict() return
+ * (entry_strict may be NULL: BVODE_FLAG_STRICT handles are then refused), abi its bvode_user_abi_fast().
+ * Returns the new problem id (>= bvode_problem_count() before the call) or a negative BVODE_E* code. */
+BVODE_API int bvode_register_problem(const void *entry_fast, const void *entry_strict, int abi);
+BVODE_API int bvode_plugin_abi(void);
+
 /* ---- lifetime: replaces `type(dvode_t) :: solver` + `call solver%initialize(f, jac)` (M:377) ----
  * One handle owns the device-resident state of nsys systems on one GPU. */
 BVODE_API int bvode_create(bvode_solver **out, int problem, int nsys, int device, unsigned flags);
