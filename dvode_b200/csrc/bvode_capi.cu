@@ -84,7 +84,10 @@ struct bvode_solver {
     double *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
            *d_rout = nullptr, *d_aos = nullptr, *d_yout = nullptr, *d_tout_ps = nullptr;
     int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
-    int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels)
+    int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels); one per stream
+    cudaStream_t stream2 = nullptr;  // second stream of the pipelined host-buffer path
+    double *d_yout_aos = nullptr;    // [nout][nsys][neq] staging of the output points in host layout
+    size_t yout_aos_cap = 0;
     size_t aos_cap = 0, yout_cap = 0;
     bool params_external = false;
     int last_launches = 0;
@@ -103,6 +106,24 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsys) return;
     for (int i = 0; i < n; i++) aos[(size_t)s * n + i] = soa[(size_t)i * nsys + s];
+}
+// the same for the systems [s0, s0 + count) of a batch of nsys, nvec consecutive [n][nsys] arrays
+// (grid.y = which array): the chunks of the pipelined host-buffer path
+__global__ void k_aos_to_soa_range(const double *__restrict__ aos, double *__restrict__ soa, int nsys,
+                                   int n, int s0, int count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const size_t g = (size_t)s0 + s;
+    for (int i = 0; i < n; i++) soa[(size_t)i * nsys + g] = aos[g * n + i];
+}
+__global__ void k_soa_to_aos_range(const double *__restrict__ soa, double *__restrict__ aos, int nsys,
+                                   int n, int s0, int count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const size_t g = (size_t)s0 + s, v = blockIdx.y;
+    const double *src = soa + v * (size_t)n * nsys;
+    double *dst = aos + v * (size_t)n * nsys;
+    for (int i = 0; i < n; i++) dst[g * n + i] = src[(size_t)i * nsys + g];
 }
 __global__ void k_isoa_to_aos(const int *__restrict__ soa, int *__restrict__ aos, int nsys,
                               int n) {
@@ -231,7 +252,8 @@ void bvode_destroy(bvode_solver *s) {
     if (!s->params_external) cudaFree(s->d_params);
     cudaFree(s->d_y); cudaFree(s->d_t); cudaFree(s->d_tol); cudaFree(s->d_rout);
     cudaFree(s->d_aos); cudaFree(s->d_yout); cudaFree(s->d_tout_ps); cudaFree(s->d_istate);
-    cudaFree(s->d_iout); cudaFree(s->d_iaos); cudaFree(s->d_next);
+    cudaFree(s->d_iout); cudaFree(s->d_iaos); cudaFree(s->d_next); cudaFree(s->d_yout_aos);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -374,19 +396,24 @@ static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
 // Launch the integration for touts[0..nout) on device-resident SoA buffers.
 static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, double *d_t,
                       int *d_istate, int nout, const double *touts, const double *d_tout_ps,
-                      double *d_yout, cudaStream_t st, bool general) {
+                      double *d_yout, cudaStream_t st, bool general, int sys0 = 0, int count = -1,
+                      int lane = 0, bool upload_tol = true) {
+    if (count < 0) count = s->nsys;
     if (nout > 1 && !(c.o.itask == 1 || c.o.itask == 4)) {
         g_err = "a tout schedule (nout > 1) needs itask 1 or 4: itask 2, 3, 5 return at mesh points, one call at a time";
         return BVODE_EINVAL;
     }
     int rc = ensure_state(s, mf, c.o.ml, c.o.mu);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
-                             cudaMemcpyHostToDevice, st));
+    if (upload_tol)
+        CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
+                                 cudaMemcpyHostToDevice, st));
     for (int k0 = 0; k0 < nout; k0 += BVODE_MAX_NOUT) {
         KArgs a;
         memset(&a, 0, sizeof(a));
         a.nsys = s->nsys;
+        a.sys0 = sys0;
+        a.count = count;
         a.nout = (nout - k0 < BVODE_MAX_NOUT) ? nout - k0 : BVODE_MAX_NOUT;
         for (int k = 0; k < a.nout; k++) a.touts[k] = touts[k0 + k];
         a.tout_ps = d_tout_ps;
@@ -410,9 +437,9 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
         a.leniw = c.leniw;
         a.general = general ? 1 : 0;
         if (s->pe->mode == 0 && (s->flags & BVODE_FLAG_COMPACT)) {
-            if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, sizeof(int)));
-            CUDA_TRY(cudaMemsetAsync(s->d_next, 0, sizeof(int), st));
-            a.next_sys = s->d_next;
+            if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, 2 * sizeof(int)));
+            CUDA_TRY(cudaMemsetAsync(s->d_next + lane, 0, sizeof(int), st));
+            a.next_sys = s->d_next + lane;
         }
         const int e = s->pe->launch(mf, a, st);
         if (e == -1000) { g_err = "mf not built for this problem"; return BVODE_ENOTIMPL; }
@@ -461,19 +488,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     }
     cudaStream_t st = s->stream;
     const int TB = 256;
-    // host -> device.  On continuation calls y and t are outputs only (M:608-618).
-    CUDA_TRY(cudaMemcpyAsync(s->d_istate, istate, sizeof(int) * ns, cudaMemcpyHostToDevice, st));
-    if (any_first) {
-        CUDA_TRY(cudaMemcpyAsync(s->d_aos, y, sizeof(double) * ns * neq, cudaMemcpyHostToDevice, st));
-        k_aos_to_soa<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_aos, s->d_y, nsys, neq);
-        s->last_launches++;
-        CUDA_TRY(cudaMemcpyAsync(s->d_t, t, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
-    }
-    const double *d_tout_ps = nullptr;
-    if (tout_ps) {
-        CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, tout_ps, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
-        d_tout_ps = s->d_tout_ps;
-    }
+    const double *d_tout_ps = tout_ps ? s->d_tout_ps : nullptr;
     double *d_yout = nullptr;
     if (y_out) {
         const size_t need = ns * neq * nout;
@@ -484,28 +499,65 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
             CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(double) * need));
             s->yout_cap = need;
         }
+        if (need > s->yout_aos_cap) {
+            cudaFree(s->d_yout_aos);
+            s->d_yout_aos = nullptr;
+            s->yout_aos_cap = 0;
+            CUDA_TRY(cudaMalloc(&s->d_yout_aos, sizeof(double) * need));
+            s->yout_aos_cap = need;
+        }
         d_yout = s->d_yout;
     }
-    double tout1 = 0.0;
-    rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, st,
-                    itask != 1 || n3 != 0);
-    if (rc != BVODE_OK) return rc;
-    s->maxord = c.o.maxord;
-    s->mxstep = c.o.mxstep;
-    // device -> host
-    k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(s->d_y, s->d_aos, nsys, neq);
-    s->last_launches++;
-    CUDA_TRY(cudaMemcpyAsync(y, s->d_aos, sizeof(double) * ns * neq, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(t, s->d_t, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(istate, s->d_istate, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
-    if (y_out) {
-        for (int k = 0; k < nout; k++) {
-            CUDA_TRY(cudaStreamSynchronize(st));  // d_aos is reused per output point
-            k_soa_to_aos<<<cdiv(nsys, TB), TB, 0, st>>>(d_yout + (size_t)k * neq * ns, s->d_aos, nsys, neq);
+    rc = ensure_state(s, mf, c.o.ml, c.o.mu);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // The batch goes through in chunks on two streams: the copies of one chunk (inputs in, every
+    // output point out) run under the kernels of its neighbours, and a chunk's kernel fills the
+    // SMs the previous one's tail leaves idle.  One chunk for small batches.
+    const int kChunk = 1 << 17;
+    const int nchunks = (nsys >= 2 * kChunk && nout <= BVODE_MAX_NOUT) ? cdiv(nsys, kChunk) : 1;
+    if (nchunks > 1 && !s->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    const double tout1 = 0.0;
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int s0 = (int)((long long)nsys * ch / nchunks), s1 = (int)((long long)nsys * (ch + 1) / nchunks);
+        const int cnt = s1 - s0;
+        const int lane = ch & 1;
+        cudaStream_t cs = lane ? s->stream2 : s->stream;
+        // host -> device.  On continuation calls y and t are outputs only (M:608-618).
+        CUDA_TRY(cudaMemcpyAsync(s->d_istate + s0, istate + s0, sizeof(int) * cnt, cudaMemcpyHostToDevice, cs));
+        if (any_first) {
+            CUDA_TRY(cudaMemcpyAsync(s->d_aos + (size_t)s0 * neq, y + (size_t)s0 * neq, sizeof(double) * cnt * neq,
+                                     cudaMemcpyHostToDevice, cs));
+            k_aos_to_soa_range<<<cdiv(cnt, TB), TB, 0, cs>>>(s->d_aos, s->d_y, nsys, neq, s0, cnt);
             s->last_launches++;
-            CUDA_TRY(cudaMemcpyAsync(y_out + (size_t)k * neq * ns, s->d_aos, sizeof(double) * ns * neq, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(s->d_t + s0, t + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
+        }
+        if (tout_ps)
+            CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps + s0, tout_ps + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
+        rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, cs,
+                        itask != 1 || n3 != 0, s0, cnt, lane, false);
+        if (rc != BVODE_OK) return rc;
+        // device -> host
+        k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), 1), TB, 0, cs>>>(s->d_y, s->d_aos, nsys, neq, s0, cnt);
+        s->last_launches++;
+        CUDA_TRY(cudaMemcpyAsync(y + (size_t)s0 * neq, s->d_aos + (size_t)s0 * neq, sizeof(double) * cnt * neq,
+                                 cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(t + s0, s->d_t + s0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(istate + s0, s->d_istate + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (y_out) {
+            k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), nout), TB, 0, cs>>>(d_yout, s->d_yout_aos, nsys, neq, s0, cnt);
+            s->last_launches++;
+            for (int k = 0; k < nout; k++) {
+                const size_t off = ((size_t)k * ns + s0) * neq;
+                CUDA_TRY(cudaMemcpyAsync(y_out + off, s->d_yout_aos + off, sizeof(double) * cnt * neq,
+                                         cudaMemcpyDeviceToHost, cs));
+            }
         }
     }
+    s->maxord = c.o.maxord;
+    s->mxstep = c.o.mxstep;
+    if (s->stream2) CUDA_TRY(cudaStreamSynchronize(s->stream2));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (have_headers) {
         std::vector<double> ro(4 * ns);

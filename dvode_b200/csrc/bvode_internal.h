@@ -21,7 +21,8 @@ struct BvOpts {
 
 // Arguments of one solve launch.  All pointers are device pointers, SoA layout.
 struct KArgs {
-    int nsys, nout;
+    int nsys, nout;                // nsys: systems of the batch = stride of every SoA array
+    int sys0, count;               // this launch integrates systems [sys0, sys0 + count)
     double touts[BVODE_MAX_NOUT];  // output points of this launch (nout >= 1)
     const double *tout_ps;         // per-system tout[nsys] (only with nout == 1) or nullptr
     double *dstate;                // [nd][nsys] persistent real state  (the reference's rwork(21:))
@@ -65,4 +66,4 @@ struct ProblemEntry {
 
 // Tag a problem library passes to bvode_register_problem: it must have been compiled against
 // these very structs (bump the leading number when KArgs / DkyArgs / ProblemEntry change meaning).
-#define BVODE_PLUGIN_ABI ((int)(2 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))
+#define BVODE_PLUGIN_ABI ((int)(3 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     e.tol.r = a.rtolv;
     e.tol.a = a.atolv;
 
-    int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    int sys = a.sys0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int sys_end = a.sys0 + a.count;  // this launch integrates systems [sys0, sys0 + count)
     int nemit = 0;
     double tout0 = 0.0;
     const size_t ns = (size_t)a.nsys;
@@ -183,13 +184,13 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
             if constexpr (REFILL) {
                 if (have) {
                     store(ist, t);
-                    sys = (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
+                    sys = a.sys0 + (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
                 }
                 int got = 0;
 #pragma unroll 1
-                while (got == 0 && sys < a.nsys) {
+                while (got == 0 && sys < sys_end) {
                     got = load();
-                    if (got == 0) sys = (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
+                    if (got == 0) sys = a.sys0 + (int)(gridDim.x * blockDim.x) + atomicAdd(a.next_sys, 1);
                 }
                 return got;
             } else {  // one system per thread and launch
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
                     store(ist, t);
                     return 0;
                 }
-                return (sys < a.nsys) ? load() : 0;
+                return (sys < sys_end) ? load() : 0;
             }
         });
 }
@@ -322,9 +323,9 @@ __global__ void __launch_bounds__(kWarpTPB, POL::kMinBlocks)
 vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
+    const size_t sys = (size_t)a.sys0 + (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
-    if (sys >= nsys) return;  // whole warp
+    if (sys >= (size_t)(a.sys0 + a.count)) return;  // whole warp
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -467,7 +468,7 @@ static int launch_thread(const KArgs &a0, cudaStream_t st) {
     static_assert(POL::kTPB == kThreadTPB, "shared-memory stride");
     size_t smem = POL::kSmemBytes;
     if (const char *pad = getenv("BVODE_PAD_SMEM")) smem += (size_t)atol(pad);  // occupancy experiments
-    const int need = (a.nsys + kThreadTPB - 1) / kThreadTPB;
+    const int need = (a.count + kThreadTPB - 1) / kThreadTPB;
     if (a.general) {
         a.next_sys = nullptr;
         if (smem > 48 * 1024)
@@ -502,7 +503,7 @@ static int launch_dky_thread(const DkyArgs &a, cudaStream_t st) {
 template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = kWarpTPB / 32;
-    const int grid = (a.nsys + spb - 1) / spb;
+    const int grid = (a.count + spb - 1) / spb;
     const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles);
     if (a.general) {
         if (smem > 48 * 1024)
