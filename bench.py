@@ -32,7 +32,7 @@ METRIC = "stiff ODE systems solved/s (Robertson, rtol 1e-6)"
 UNIT = "systems/s"
 NSYS_PER_GPU = 1 << 20
 # measured DRAM traffic of the headline kernel (ncu, see roofline.traffic_source)
-NCU_DRAM_BYTES_PER_SYSTEM = 1134
+NCU_DRAM_BYTES_PER_SYSTEM = 1137
 
 
 def flops_per_system_robertson(nst, nfe, nje, nlu, nni, ncfn, netf):
@@ -354,9 +354,9 @@ def main():
                          "algorithmic_flops_per_system": flops_launch / nsys,
                          "traffic": NCU_DRAM_BYTES_PER_SYSTEM * nsys,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                           "capture (profiles/r01_ncu_thread_kernel_r1n.txt: 148.7 MB for 131072 "
-                                           "systems = 1134 B/system vs 1024 algorithmic), scaled to this launch",
-                         "fp64_pipe_active_ncu": 0.301, "issue_active_ncu": 0.482,
+                                           "capture (profiles/r01_ncu_thread_kernel_r1p.txt: 149.0 MB for 131072 "
+                                           "systems = 1137 B/system vs 1024 algorithmic), scaled to this launch",
+                         "fp64_pipe_active_ncu": 0.301, "issue_active_ncu": 0.483,
                          "hbm": {"achieved": bytes_launch / kern_s / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": bytes_launch / kern_s / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_system": bytes_per_system_robertson(nout)}},
