@@ -471,7 +471,12 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     // parameters applies to the whole batch; mf / ml / mu select the kernel and the state layout
     // and cannot change without a new handle
     if (n3 != 0 && n3 != nsys) { g_err = "istate = 3 must be given for every system of the batch"; return BVODE_EINVAL; }
-    if (n3 != 0 && (!s->d_state || s->mf != mf)) { g_err = "istate = 3 with a different mf is not built (the state layout is per method flag)"; return BVODE_ENOTIMPL; }
+    if (n3 != 0 && !s->d_state) { g_err = "istate = 3 before a successful first call"; return BVODE_EINVAL; }
+    const bool mf_changed = (n3 != 0 && s->mf != mf);
+    if (mf_changed && (abs(s->mf) / 10 != abs(mf) / 10)) {
+        g_err = "istate = 3 with another method family (meth) is not built: the Nordsieck array has another shape";
+        return BVODE_ENOTIMPL;
+    }
     Checked c;
     const bool have_headers = rwork && iwork;
     int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c);
@@ -479,8 +484,47 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         if (rc == BVODE_EINVAL) for (int j = 0; j < nsys; j++) istate[j] = -3;
         return rc;
     }
-    if (n3 != 0 && (c.o.ml != s->ml || c.o.mu != s->mu)) { g_err = "istate = 3 with different ml / mu is not built"; return BVODE_ENOTIMPL; }
+    {   // ml / mu only mean something for the banded method flags (miter 4, 5)
+        const int mo = abs(s->mf) % 10, mn = abs(mf) % 10;
+        const bool band_old = (mo == 4 || mo == 5), band_new = (mn == 4 || mn == 5);
+        if (n3 != 0 && band_old && band_new && (c.o.ml != s->ml || c.o.mu != s->mu)) {
+            g_err = "istate = 3 with different ml / mu is not built";
+            return BVODE_ENOTIMPL;
+        }
+    }
     if (n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
+    if (mf_changed) {
+        // M:999-1046 at istate = 3: a new miter / jsv.  The state moves into the layout of the new
+        // method flag; the Newton matrix and the saved Jacobian are rebuilt at the restart.
+        size_t nd = 0, ni = 0;
+        s->pe->state_size(mf, c.o.ml, c.o.mu, (size_t)nsys, &nd, &ni);
+        double *dn = nullptr;
+        int *in = nullptr;
+        CUDA_TRY(cudaMalloc(&dn, sizeof(double) * nd));
+        CUDA_TRY(cudaMalloc(&in, sizeof(int) * ni));
+        CUDA_TRY(cudaMemsetAsync(dn, 0, sizeof(double) * nd, s->stream));
+        CUDA_TRY(cudaMemsetAsync(in, 0, sizeof(int) * ni, s->stream));
+        const int e = s->pe->state_convert ? s->pe->state_convert(s->mf, mf, c.o.ml, c.o.mu, (size_t)nsys, s->d_state,
+                                                                  s->i_state, dn, in, s->stream)
+                                           : -1000;
+        if (e != 0) {
+            cudaFree(dn);
+            cudaFree(in);
+            g_err = "istate = 3: this change of mf is not built";
+            return BVODE_ENOTIMPL;
+        }
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_state);
+        cudaFree(s->i_state);
+        s->d_state = dn;
+        s->i_state = in;
+        s->nd = nd;
+        s->ni = ni;
+        s->mf = mf;
+        s->ml = c.o.ml;
+        s->mu = c.o.mu;
+        c.o.jreset = 1;
+    }
     if (!any_first && (s->mf != mf || !s->d_state)) {
         for (int j = 0; j < nsys; j++) istate[j] = -3;  // M:1102-1106
         g_err = "istate = 2 but the solver was not initialised with this mf";

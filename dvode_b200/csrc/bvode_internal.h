@@ -62,8 +62,14 @@ struct ProblemEntry {
     void (*state_size)(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni);
     int (*launch)(int mf, const KArgs &a, cudaStream_t st);
     int (*launch_dky)(int mf, const DkyArgs &a, cudaStream_t st);
+    // istate = 3 with another method flag of the SAME family (meth): carry the part of the state that
+    // does not depend on miter / jsv -- Nordsieck array, acor copy, tau, scalars, counters -- over into
+    // the layout of mf_new (zero-filled by the caller; the Newton matrix is rebuilt at the restart,
+    // M:2748).  Returns 0, or -1000 if the pair is not convertible.
+    int (*state_convert)(int mf_old, int mf_new, int ml, int mu, size_t nsys, const double *d_old,
+                         const int *i_old, double *d_new, int *i_new, cudaStream_t st);
 };
 
 // Tag a problem library passes to bvode_register_problem: it must have been compiled against
 // these very structs (bump the leading number when KArgs / DkyArgs / ProblemEntry change meaning).
-#define BVODE_PLUGIN_ABI ((int)(3 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))
+#define BVODE_PLUGIN_ABI ((int)(4 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))

@@ -583,6 +583,22 @@ static void thread_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, s
     *ni = nsys * (size_t)(N + 19);
 }
 template <class PROB>
+static int thread_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
+                                const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
+    constexpr int N = PROB::N;
+    const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
+    if (a.meth != b.meth) return -1000;
+    const int lm = kLmaxOf(a.meth);
+    // doubles: yh, acor copy, acor, P (head) | saved J if jsv > 0 | tau, scalars (tail); see thread_state_size
+    const size_t head = (size_t)(lm * N + 2 * N + N * N), tail = (size_t)(lm + 14);
+    const size_t wo = a.savej ? (size_t)N * N : 0, wn = b.savej ? (size_t)N * N : 0;
+    cudaMemcpyAsync(d_new, d_old, sizeof(double) * head * nsys, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(d_new + (head + wn) * nsys, d_old + (head + wo) * nsys, sizeof(double) * tail * nsys,
+                    cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(i_new, i_old, sizeof(int) * (size_t)(N + 19) * nsys, cudaMemcpyDeviceToDevice, st);
+    return (int)cudaGetLastError();
+}
+template <class PROB>
 static int thread_supports(int mf, int ml, int mu) {
     (void)ml; (void)mu;
     const MfParts m = mf_parts(mf);
@@ -591,7 +607,7 @@ static int thread_supports(int mf, int ml, int mu) {
 #define BVODE_THREAD_PROBLEM(NAME, PROB)                                                    \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 0, thread_supports<PROB>, thread_state_size<PROB>,       \
-            thread_dispatch<PROB>, thread_dky_dispatch<PROB>                                \
+            thread_dispatch<PROB>, thread_dky_dispatch<PROB>, thread_state_convert<PROB>    \
     }
 
 // ---- warp-per-system problems ---------------------------------------------------------------
@@ -662,6 +678,18 @@ static void warp_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, siz
     });
 }
 template <class PROB, int KIND>
+static int warp_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
+                              const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
+    const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
+    if (a.meth != b.meth) return -1000;
+    const int lm = kLmaxOf(a.meth);
+    // every warp policy starts with scalars[lm + 14][nsys], then the lane slots yh[lm], acor copy, acor
+    const size_t nd = ((size_t)(lm + 14) + (size_t)(lm + 2) * 32) * nsys;
+    cudaMemcpyAsync(d_new, d_old, sizeof(double) * nd, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(i_new, i_old, sizeof(int) * (size_t)kScalarI * nsys, cudaMemcpyDeviceToDevice, st);
+    return (int)cudaGetLastError();
+}
+template <class PROB, int KIND>
 static int warp_supports(int mf, int ml, int mu) {
     const MfParts m = mf_parts(mf);
     if (m.meth != 1 && m.meth != 2) return 0;
@@ -673,12 +701,12 @@ static int warp_supports(int mf, int ml, int mu) {
 #define BVODE_WARP_DENSE_FD_PROBLEM(NAME, PROB)                                             \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 1>, warp_state_size<PROB, 1>,     \
-            warp_dispatch<PROB, 1>, warp_dky_dispatch<PROB, 1>                              \
+            warp_dispatch<PROB, 1>, warp_dky_dispatch<PROB, 1>, warp_state_convert<PROB, 1> \
     }
 #define BVODE_WARP_BAND_PROBLEM(NAME, PROB)                                                 \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 2>, warp_state_size<PROB, 2>,     \
-            warp_dispatch<PROB, 2>, warp_dky_dispatch<PROB, 2>                              \
+            warp_dispatch<PROB, 2>, warp_dky_dispatch<PROB, 2>, warp_state_convert<PROB, 2> \
     }
 
 }  // namespace BVODE_NS

@@ -88,8 +88,9 @@ BVODE_API int bvode_set_params(bvode_solver *s, const double *params);
  * reference.  tout: one value for the batch (tout_per_system = 0) or tout[nsys] (= 1).
  *   itask  1-5 (M:811-831); 4 and 5 read tcrit = rwork(1) of row 0.
  *   istate 1 (first call), 2 (continue), 3 (continue with changed itol / rtol / atol / itask /
- *          optional inputs incl. a lower maxord; must then be 3 for every system; mf, ml, mu
- *          and neq cannot change -- they select the kernel and the state layout).
+ *          optional inputs incl. a lower maxord; must then be 3 for every system; mf may change
+ *          within a method family -- miter / jsv, the state moves into the new kernel's layout and
+ *          the Jacobian is re-evaluated -- but not meth, ml / mu of a banded flag, or neq).
  *   mf     jsv*(10*meth + miter), M:999-1046: meth 1 (Adams) or 2 (BDF); miter 0 (functional
  *          iteration), 1 / 2 (dense analytic / finite-difference J; thread-per-system problems,
  *          miter 2 also for the dense warp problem), 3 (diagonal approximation), 4 / 5 (banded

@@ -277,6 +277,12 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
         return -1;
     int lrw, liw;
     dvo_work_sizes(neq, cfg->mf, cfg->ml, cfg->mu, cfg->iopt ? cfg->maxord : 0, &lrw, &liw);
+    {   /* the istate = 3 call may carry another method flag (M:999-1046): the larger work arrays */
+        int lrw2, liw2;
+        dvo_work_sizes(neq, cfg2->mf, cfg2->ml, cfg2->mu, cfg->iopt ? cfg->maxord : 0, &lrw2, &liw2);
+        if (lrw2 > lrw) lrw = lrw2;
+        if (liw2 > liw) liw = liw2;
+    }
     if (liw < 30) liw = 30;
     int fail = 0;
 #ifdef _OPENMP

@@ -122,9 +122,10 @@ def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1,
 def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, atol2, itol=1,
                  itol2=None, itask=1, itask2=None, iopt=0, iopt2=None, ml=0, mu=0, maxord=0,
                  maxord2=0, mxstep=0, mxstep2=0, hmax=0.0, hmax2=0.0, hmin=0.0, hmin2=0.0,
-                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant=""):
+                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant="", mf2=None):
     """Outputs [0, nsplit) with the first parameter set, then an istate = 3 call with the second
-    set (same mf) and continuation calls: the reference's parameter-change restart."""
+    set (and method flag mf2, default the same) and continuation calls: the reference's
+    parameter-change restart."""
     neq, npar = problem_info(problem)
     params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(npar, 1)))
     nsys = params.shape[0]
@@ -136,7 +137,7 @@ def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, 
     pick = lambda a, b: b if b is not None else a
     cfg = BatchCfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, 0, 0.0, hmax,
                    hmin, tcrit, pow_mode)
-    cfg2 = BatchCfg(PROBLEMS[problem], mf, pick(itol, itol2), pick(itask, itask2), pick(iopt, iopt2),
+    cfg2 = BatchCfg(PROBLEMS[problem], mf if mf2 is None else mf2, pick(itol, itol2), pick(itask, itask2), pick(iopt, iopt2),
                     ml, mu, maxord2, mxstep2, 0, 0.0, hmax2, hmin2, tcrit2, pow_mode)
     y = np.zeros((nsys, nout, neq))
     t = np.zeros((nsys, nout))
