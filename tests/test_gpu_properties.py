@@ -295,3 +295,37 @@ def test_device_pointer_call_with_per_system_tout():
     assert np.array_equal(td.cpu().numpy(), t) and np.array_equal(t, tps)
     assert np.array_equal(isd.cpu().numpy(), ist) and (ist == 2).all()
     s.close()
+
+
+def test_pipelined_host_path_ragged_chunks():
+    """Batches of 2^18 systems and more go through the host-buffer entry points in chunks of 2^17 on
+    two streams (copies under kernels).  A batch that does not divide evenly: every system's rows are
+    those of a small batch run on its own, for the schedule call and for per-system tout."""
+    B = _B()
+    nsys = (1 << 18) + 333
+    par = B.batches.robertson_batch(nsys)
+    tol = B.batches.ROBERTSON_TOL_REF
+    touts = B.batches.robertson_touts()[:4]
+    yo, y, t, ist, iw = _schedule_device_resident("robertson", par, B.batches.ROBERTSON_Y0, touts, tol, 21)
+    assert (ist == 2).all() and np.array_equal(t, np.full(nsys, touts[-1]))
+    assert np.abs(yo.sum(axis=2) - 1.0).max() < 1e-5
+    for lo in (0, (1 << 17) - 7, nsys - 300):  # inside the first chunk, across a boundary, the ragged tail
+        sl = slice(lo, lo + 300)
+        yo_s, y_s, _, _, iw_s = _schedule_device_resident("robertson", np.ascontiguousarray(par[sl]),
+                                                          B.batches.ROBERTSON_Y0, touts, tol, 21)
+        assert np.array_equal(yo_s, yo[:, sl]) and np.array_equal(y_s, y[sl])
+        assert np.array_equal(iw_s[:, 10:22], iw[sl, 10:22])
+    # one call with a tout per system
+    s = B.dvode_t().initialize("robertson", nsys, par)
+    y2 = np.tile(np.array(B.batches.ROBERTSON_Y0), (nsys, 1)); t2 = np.zeros(nsys); ist2 = np.ones(nsys, dtype=np.int32)
+    tps = np.where(np.arange(nsys) % 3 == 0, touts[1], touts[3])
+    s.solve(3, y2, t2, tps, tol["itol"], tol["rtol"], tol["atol"], 1, ist2, 0, None, 0, None, 0, 21)
+    s.close()
+    assert (ist2 == 2).all() and np.array_equal(t2, tps)
+    for lo in ((1 << 17) - 7, nsys - 300):
+        sl = slice(lo, lo + 300)
+        s = B.dvode_t().initialize("robertson", 300, np.ascontiguousarray(par[sl]))
+        y3 = np.tile(np.array(B.batches.ROBERTSON_Y0), (300, 1)); t3 = np.zeros(300); ist3 = np.ones(300, dtype=np.int32)
+        s.solve(3, y3, t3, tps[sl], tol["itol"], tol["rtol"], tol["atol"], 1, ist3, 0, None, 0, None, 0, 21)
+        s.close()
+        assert np.array_equal(y3, y2[sl]) and np.array_equal(t3, t2[sl])
