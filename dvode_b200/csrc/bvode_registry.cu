@@ -1,6 +1,6 @@
 // bvode_registry.cu -- instantiates every kernel of ONE problem for one build and exports its
 // table entry.  Compiled once per (build, problem): -DBVODE_STRICT=0 (fast, the product) or
-// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..4.
+// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..5.
 #include "bvode_kernels.cuh"
 
 #ifndef BVODE_UNIT
@@ -18,6 +18,8 @@ static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection", Advectio
 static const ProblemEntry kEntry = BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32);
 #elif BVODE_UNIT == 4
 static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp_maxnorm", VanDerPolMaxNorm);
+#elif BVODE_UNIT == 5
+static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection_maxnorm", Advection25MaxNorm);
 #endif
 }  // namespace BVODE_NS
 

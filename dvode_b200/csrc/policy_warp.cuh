@@ -120,11 +120,28 @@ struct WarpCommon {
         BV_DEV double atol(int) const { return a; }
     };
 
-    // dewset_default for this lane's component, M:3238-3273 (user-supplied weights / norms
-    // are a thread-per-system feature so far)
-    BV_DEV static double ewt_of(int, double yi, double rtol, double atol) { return rtol * fabs(yi) + atol; }
+    // dewset_default for this lane's component, M:3238-3273, or the problem's own (M:431-467)
+    BV_DEV static double ewt_of(int, double yi, double rtol, double atol) {
+        if constexpr (HasUserEwt<PROB>::value) return PROB::ewt(lane(), yi, rtol, atol);
+        else return rtol * fabs(yi) + atol;
+    }
+    // a user-supplied norm (M:468-503) in its lane-wise form: a fold over the components
+    BV_DEV static double user_norm(double v, double w) {
+        const double p = PROB::norm_term(v, w);
+#if BVODE_STRICT
+        double acc = PROB::norm_init;
+#pragma unroll 1
+        for (int i = 0; i < N; i++) acc = PROB::norm_combine(acc, shfl_d(p, i));
+#else
+        double acc = (lane() < N) ? PROB::norm_combine(PROB::norm_init, p) : PROB::norm_init;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc = PROB::norm_combine(acc, shfl_xor_d(acc, m));
+#endif
+        return PROB::norm_final(acc);
+    }
     // dvnorm_default, M:3295-3311.  Lanes >= N carry v = 0.
     BV_DEV static double norm(const double (&v)[1], const double (&w)[1]) {
+        if constexpr (HasLaneNorm<PROB>::value) return user_norm(v[0], w[0]);
         const double p = v[0] * w[0];
         const double p2 = p * p;
 #if BVODE_STRICT
@@ -141,6 +158,10 @@ struct WarpCommon {
     }
 #if !BVODE_STRICT
     BV_DEV static double msq(const double (&v)[1], const double (&w)[1]) {
+        if constexpr (HasLaneNorm<PROB>::value) {  // a user norm is only known as a norm
+            const double nv = user_norm(v[0], w[0]);
+            return nv * nv;
+        }
         const double p = v[0] * w[0];
         double sum = (lane() < N) ? p * p : 0.0;
 #pragma unroll

@@ -106,6 +106,24 @@ struct Advection25 {
     }
 };
 
+// dvdemo problem 2 with USER-SUPPLIED error weights and norm (M:431-503) in the lane-wise form of
+// the warp kernels: `ewt` as for thread problems (one component), and the norm as a fold over the
+// components -- norm_term(v_i, w_i), norm_combine(acc, term) applied in index order (the strict build
+// folds sequentially like a Fortran loop; the fast build as a butterfly, so combine should be
+// associative up to rounding), norm_init its identity, norm_final(acc).  Here: the weights and the
+// max norm of VanDerPolMaxNorm.
+struct Advection25MaxNorm : Advection25 {
+    BV_DEV static double ewt(int, double yi, double rtol, double atol) {
+        double ay = fabs(yi);
+        if (ay < 1.0) ay = 1.0;
+        return rtol * ay + atol;
+    }
+    static constexpr double norm_init = 0.0;
+    BV_DEV static double norm_term(double v, double w) { return fabs(v * w); }
+    BV_DEV static double norm_combine(double acc, double p) { return (p > acc) ? p : acc; }
+    BV_DEV static double norm_final(double acc) { return acc; }
+};
+
 // Synthetic 32-species mass-action network (BASELINE.json config 4; builder-defined, NOT in
 // the reference).  64 reactions: r < 32 unimolecular A -> B, r >= 32 bimolecular
 // A + B -> C + D; tables in include/bvode_mech32.h.  par = 64 rate constants; lane r holds

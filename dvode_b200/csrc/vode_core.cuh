@@ -363,6 +363,11 @@ struct HasUserNorm { static constexpr bool value = false; };
 template <class P>
 struct HasUserNorm<P, decltype((void)&P::norm)> { static constexpr bool value = true; };
 
+template <class P, class = void>
+struct HasLaneNorm { static constexpr bool value = false; };  // the lane-wise form (norm_term / combine / final)
+template <class P>
+struct HasLaneNorm<P, decltype((void)&P::norm_term)> { static constexpr bool value = true; };
+
 // =================================================================== Engine =====
 // POL provides:
 //   Prob, N (equations), NLOC (vector elements held by this thread), MITER

@@ -154,6 +154,7 @@ int dvo_problem_info(int problem, int *neq, int *npar)
     case 2: *neq = NG * NG; *npar = 2; return 0;
     case 3: *neq = BVODE_MECH_NS; *npar = BVODE_MECH_NR; return 0;
     case 4: *neq = 2; *npar = 1; return 0;
+    case 5: *neq = NG * NG; *npar = 2; return 0;  /* advection with the user norms of problem 4 */
     default: return -1;
     }
 }
@@ -166,6 +167,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     case 2: *f = adv_f; *jac = adv_jac; return 0;
     case 3: *f = mech_f; *jac = NULL; return 0;
     case 4: *f = vdp_f; *jac = vdp_jac; return 0;
+    case 5: *f = adv_f; *jac = adv_jac; return 0;
     default: return -1;
     }
 }
@@ -226,7 +228,7 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
             dvo_solver sol;
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
-            if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+            if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -301,7 +303,7 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
             dvo_solver sol;
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
-            if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+            if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -360,7 +362,7 @@ int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const doubl
     memcpy(y, y0, sizeof(double) * (size_t)neq);
     dvo_solver sol;
     dvo_initialize(&sol, f, jac, par);
-    if (cfg->problem == 4) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+    if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
     sol.pow_mode = cfg->pow_mode;
     iwork[0] = cfg->ml; iwork[1] = cfg->mu;
     if (cfg->iopt) {

@@ -309,6 +309,31 @@ def test_user_supplied_dewset_and_dvnorm(mf):
         assert abs(a - b) <= 0.02 * b, (mf, k, a, b)
 
 
+@pytest.mark.parametrize("mf", [10, 23, 24, 25, -25])
+def test_user_supplied_dewset_and_dvnorm_warp_problem(mf):
+    """The same user routines for a one-system-per-warp problem (`advection_maxnorm`, n = 25), in their
+    lane-wise form: ewt per component, the norm as a fold (norm_term / norm_combine / norm_final)."""
+    B = _B()
+    nsys = 96
+    par = B.batches.advection_batch(nsys)
+    y0, touts = B.batches.advection_y0(), B.batches.advection_touts()[:4]
+    kw, iw = dict(ml=5, mu=0), _iw(5, 0)
+    ref = O.batch_solve("advection_maxnorm", par, y0, 0.0, touts, 1e-5, 1e-7, mf, itol=1, pow_mode=1, **kw)
+    dflt = O.batch_solve("advection", par, y0, 0.0, touts, 1e-5, 1e-7, mf, itol=1, pow_mode=1, **kw)
+    assert (ref["istate"] == 2).all()
+    assert not np.array_equal(ref["istats"][:, -1], dflt["istats"][:, -1])
+    g = gpu_schedule("advection_maxnorm", par, y0, 0.0, touts, [1e-5], [1e-7], mf, 1, strict=True, per_call=True,
+                     iwork_opts=iw)
+    _same(g, ref)
+    f = gpu_schedule("advection_maxnorm", par, y0, 0.0, touts, [1e-5], [1e-7], mf, 1, iwork_opts=iw)
+    ref0 = O.batch_solve("advection_maxnorm", par, y0, 0.0, touts, 1e-5, 1e-7, mf, itol=1, **kw)
+    assert (f["istate"][:, -1] == 2).all()
+    for k in ("nst", "nfe"):
+        a = int(f["istats"][:, -1, O.ISTAT[k]].astype(np.int64).sum())
+        b = int(ref0["istats"][:, -1, O.ISTAT[k]].astype(np.int64).sum())
+        assert abs(a - b) <= 0.02 * b, (mf, k, a, b)
+
+
 def test_dvindy_matches_oracle():
     B = _B()
     nsys = 64
