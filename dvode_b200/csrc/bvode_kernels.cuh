@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
 template <class POL>
 __host__ __device__ constexpr int scalar_d() { return POL::kLmax + 14; }  // tau(1:lmax) + the 14 scalars of visit_state
 constexpr int kScalarI = 19;
-constexpr int kWarpTPB = 128;         // 4 systems per block
+#ifndef BVODE_WARP_TPB
+#define BVODE_WARP_TPB 128
+#endif
+constexpr int kWarpTPB = BVODE_WARP_TPB;  // threads per CTA = 32 x systems per CTA
 
 struct WarpLoader {
     const double *ds, *dl, *db;
