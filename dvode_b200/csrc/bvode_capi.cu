@@ -583,7 +583,11 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
             CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps + s0, tout_ps + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
         rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, cs,
                         itask != 1 || n3 != 0, s0, cnt, lane, false);
-        if (rc != BVODE_OK) return rc;
+        if (rc != BVODE_OK) {  // nothing may still be writing into the caller's buffers when we return
+            cudaStreamSynchronize(s->stream);
+            if (s->stream2) cudaStreamSynchronize(s->stream2);
+            return rc;
+        }
         // device -> host
         k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), 1), TB, 0, cs>>>(s->d_y, s->d_aos, nsys, neq, s0, cnt);
         s->last_launches++;

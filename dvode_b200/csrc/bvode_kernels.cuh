@@ -482,8 +482,14 @@ static int launch_thread(const KArgs &a0, cudaStream_t st) {
     if (a.next_sys) {  // BVODE_FLAG_COMPACT
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_thread_kernel<POL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        static int capacity = -1;  // per instantiation
-        if (capacity < 0) capacity = resident_grid(vode_thread_kernel<POL, false, true>, smem);
+        static int cap_of[64];  // per instantiation and device (0 = not asked yet); benign if two threads race
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int capacity = (dev >= 0 && dev < 64) ? cap_of[dev] : 0;
+        if (capacity == 0) {
+            capacity = resident_grid(vode_thread_kernel<POL, false, true>, smem);
+            if (dev >= 0 && dev < 64) cap_of[dev] = capacity;
+        }
         if (capacity > 0 && need > capacity) {
             vode_thread_kernel<POL, false, true><<<capacity, kThreadTPB, smem, st>>>(a);
             return (int)cudaGetLastError();
