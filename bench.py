@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--nsys", type=int, default=NSYS_PER_GPU, help="systems per GPU")
     ap.add_argument("--tol", default="headline", choices=["headline", "ref"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the device-resident numbers of the banded and the 32-species configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -311,6 +313,41 @@ def main():
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
         gather_ms = float(gt.item())
 
+    # ---- the other single-GPU configurations of BASELINE.json, device-resident, for the record ----
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = []
+        for name, mf, lg, par_fn, y0c, toutc, tolc, iopt, ml, mxs in (
+                ("advection", 24, 18, batches.advection_batch, batches.advection_y0(), batches.advection_touts(),
+                 batches.ADVECTION_TOL, 0, 5, 0),
+                ("mech32", 22, 16, batches.mech32_batch, batches.mech32_y0(), batches.mech32_touts(),
+                 batches.MECH32_TOL, 1, 0, 100000)):
+            nc = 1 << lg
+            sc = B.dvode_t().initialize(name, nc, par_fn(nc))
+            y0d = torch.tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(y0c)[:, None], (sc.neq, nc))),
+                               dtype=torch.float64, device=dev)
+            ydc, tdc = torch.empty_like(y0d), torch.zeros(nc, dtype=torch.float64, device=dev)
+            isc = torch.ones(nc, dtype=torch.int32, device=dev)
+            iwc = np.zeros(30, dtype=np.int32)
+            iwc[0], iwc[5] = ml, mxs
+            best = None
+            for rep in range(3):
+                ydc.copy_(y0d); tdc.zero_(); isc.fill_(1)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                sc.solve_schedule_device(sc.neq, ydc.data_ptr(), tdc.data_ptr(), toutc, tolc["itol"], tolc["rtol"],
+                                         tolc["atol"], 1, isc.data_ptr(), iopt, np.zeros(20), iwc, mf, 0,
+                                         stream.cuda_stream)
+                c1.record(stream)
+                torch.cuda.synchronize()
+                if rep > 0:
+                    best = c0.elapsed_time(c1) if best is None else min(best, c0.elapsed_time(c1))
+            other.append({"workload": "%s, mf=%d, 2^%d systems, device-resident, best of 2 after a warm-up" % (name, mf, lg),
+                          "value": nc / best * 1e3, "unit": UNIT, "ms": best,
+                          "systems_ok": int((isc == 2).sum().item())})
+            sc.close()
+            del y0d, ydc, tdc, isc
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # ~10-30 s of CPU work: ~4000 systems/s/core -> 2^20 systems on a 16-core box
@@ -366,6 +403,8 @@ def main():
             line["final_gather_ms"] = gather_ms
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if other is not None:
+            line["other_configs"] = other
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
