@@ -107,3 +107,20 @@ def mech32_batch(nsys, amp=0.1, seed=SEED, first=0):
 
 
 MECH32_TOL = dict(itol=1, rtol=[1e-6], atol=[1e-12])
+
+
+# ---- reaction-diffusion chain, n = 48 (builder-defined; two components per lane) -----------
+DIFFUSION48_PAR = (50.0, 1.0)
+DIFFUSION48_TOL = dict(itol=1, rtol=[1e-6], atol=[1e-9])
+
+
+def diffusion48_batch(nsys, amp=0.1, seed=SEED, first=0):
+    return perturbed(DIFFUSION48_PAR, nsys, amp, seed, first)
+
+
+def diffusion48_y0():
+    return np.zeros(48)
+
+
+def diffusion48_touts():
+    return np.array([0.01, 0.1, 1.0, 10.0])

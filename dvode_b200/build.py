@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
     nv = _nvcc()
     fast_extra = os.environ.get("BVODE_EXTRA_NVCC", "").split()
     units = [("capi.o", "bvode_capi.cu", [])]
-    for u in range(6):  # one translation unit per problem and build, compiled in parallel
+    for u in range(7):  # one translation unit per problem and build, compiled in parallel
         units.append(("reg_fast_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=0", "-DBVODE_UNIT=%d" % u] + fast_extra))
         units.append(("reg_strict_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false", "-DBVODE_UNIT=%d" % u]))
     procs = []

@@ -14,7 +14,7 @@
 
 // one entry per (build, problem), each from its own translation unit (bvode_registry.cu)
 #include <mutex>
-#define BVODE_NPROBLEMS 6
+#define BVODE_NPROBLEMS 7
 extern "C" {
 const ProblemEntry *bvode_entry_fast_0(void);
 const ProblemEntry *bvode_entry_fast_1(void);
@@ -22,12 +22,14 @@ const ProblemEntry *bvode_entry_fast_2(void);
 const ProblemEntry *bvode_entry_fast_3(void);
 const ProblemEntry *bvode_entry_fast_4(void);
 const ProblemEntry *bvode_entry_fast_5(void);
+const ProblemEntry *bvode_entry_fast_6(void);
 const ProblemEntry *bvode_entry_strict_0(void);
 const ProblemEntry *bvode_entry_strict_1(void);
 const ProblemEntry *bvode_entry_strict_2(void);
 const ProblemEntry *bvode_entry_strict_3(void);
 const ProblemEntry *bvode_entry_strict_4(void);
 const ProblemEntry *bvode_entry_strict_5(void);
+const ProblemEntry *bvode_entry_strict_6(void);
 }
 // The problem table: the built-in problems, then whatever bvode_register_problem appended (user
 // f / jac functors compiled into a library of their own against csrc/bvode_user_problem.cuh).
@@ -42,9 +44,11 @@ static void registry_init() {
     g_tab_fast[0] = *bvode_entry_fast_0(); g_tab_fast[1] = *bvode_entry_fast_1();
     g_tab_fast[2] = *bvode_entry_fast_2(); g_tab_fast[3] = *bvode_entry_fast_3();
     g_tab_fast[4] = *bvode_entry_fast_4(); g_tab_fast[5] = *bvode_entry_fast_5();
+    g_tab_fast[6] = *bvode_entry_fast_6();
     g_tab_strict[0] = *bvode_entry_strict_0(); g_tab_strict[1] = *bvode_entry_strict_1();
     g_tab_strict[2] = *bvode_entry_strict_2(); g_tab_strict[3] = *bvode_entry_strict_3();
     g_tab_strict[4] = *bvode_entry_strict_4(); g_tab_strict[5] = *bvode_entry_strict_5();
+    g_tab_strict[6] = *bvode_entry_strict_6();
     g_nproblems = BVODE_NPROBLEMS;
 }
 static const ProblemEntry *bvode_registry_fast(int *n) {

@@ -5,6 +5,7 @@
 #include "bvode_internal.h"
 #include "policy_thread.cuh"
 #include "policy_warp.cuh"
+#include "policy_warp2.cuh"
 #include "problems.cuh"
 
 namespace BVODE_NS {
@@ -334,8 +335,17 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 
     Engine<POL> e;
     e.o = a.o;
-    e.tol.r = (ln < N) ? a.rtol[ln] : 0.0;
-    e.tol.a = (ln < N) ? a.atol[ln] : 1.0;  // padding lanes: finite weight, value always 0
+    constexpr int NL = POL::NLOC;  // components per lane: component ln + 32*i in slot i
+    if constexpr (NL == 1) {
+        e.tol.r = (ln < N) ? a.rtol[ln] : 0.0;
+        e.tol.a = (ln < N) ? a.atol[ln] : 1.0;  // padding lanes: finite weight, value always 0
+    } else {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            e.tol.r[i] = (ln + 32 * i < N) ? a.rtol[ln + 32 * i] : 0.0;
+            e.tol.a[i] = (ln + 32 * i < N) ? a.atol[ln + 32 * i] : 1.0;
+        }
+    }
     const double *dl, *db;
     const int *il;
     int nblock;
@@ -353,7 +363,8 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
         tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
         if (ist == 1) {
             if (tout0 == t) return 0;  // M:1101
-            e.y[0] = (ln < N) ? a.y[(size_t)ln * nsys + sys] : 0.0;
+#pragma unroll
+            for (int i = 0; i < NL; i++) e.y[i] = (ln + 32 * i < N) ? a.y[(size_t)(ln + 32 * i) * nsys + sys] : 0.0;
             const int r = e.init_problem(t, tout0);
             if (r < 0) {
                 if (ln == 0) a.istate[sys] = r;
@@ -380,15 +391,21 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             if (nemit == 0) return;
             ist = IST_ILLEGAL;
         }
-        if (a.y_out && ln < N) {
-            for (int k2 = nemit; k2 < a.nout; k2++) a.y_out[((size_t)k2 * N + ln) * nsys + sys] = e.y[0];
+        if (a.y_out) {
+            for (int k2 = nemit; k2 < a.nout; k2++) {
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                    if (ln + 32 * i < N) a.y_out[((size_t)k2 * N + ln + 32 * i) * nsys + sys] = e.y[i];
+            }
         }
         double tolsf = 0.0;
         if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
             tolsf = 2.0 * kUround * e.norm_y0();
         const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
 
-        if (ln < N) a.y[(size_t)ln * nsys + sys] = e.y[0];
+#pragma unroll
+        for (int i = 0; i < NL; i++)
+            if (ln + 32 * i < N) a.y[(size_t)(ln + 32 * i) * nsys + sys] = e.y[i];
         {
             WarpStorer st{a.dstate, const_cast<double *>(dl), const_cast<double *>(db),
                           a.istate_store, const_cast<int *>(il), nsys, sys, ln, nblock};
@@ -418,9 +435,13 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 
     e.template run<GENERAL, false>(
         a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; },
-        [&](int k, const double (&yk)[1]) {
+        [&](int k, const double (&yk)[NL]) {
             nemit = k + 1;
-            if (a.y_out && ln < N) a.y_out[((size_t)k * N + ln) * nsys + sys] = yk[0];
+            if (a.y_out) {
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                    if (ln + 32 * i < N) a.y_out[((size_t)k * N + ln + 32 * i) * nsys + sys] = yk[i];
+            }
         },
         [&](bool have, int ist, double t) -> int {  // one system per warp and launch
             if (have) {
@@ -448,9 +469,11 @@ __global__ void __launch_bounds__(kWarpTPB) dvindy_warp_kernel(const __grid_cons
     visit_state(e, ld);
     e.c.L = e.c.nq + 1;
     const double t = a.t_ps ? a.t_ps[sys] : a.t;
-    double dky[1];
+    double dky[POL::NLOC];
     const int iflag = e.dvindy_k(t, a.k, dky);
-    if (ln < N) a.dky[(size_t)ln * nsys + sys] = dky[0];
+#pragma unroll
+    for (int i = 0; i < POL::NLOC; i++)
+        if (ln + 32 * i < N) a.dky[(size_t)(ln + 32 * i) * nsys + sys] = dky[i];
     if (ln == 0) a.iflag[sys] = iflag;
 }
 
@@ -707,6 +730,50 @@ static int warp_supports(int mf, int ml, int mu) {
     return (m.miter == 4 || m.miter == 5) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 &&
            ml < PROB::N && mu < PROB::N;
 }
+// ---- one system per warp, two components per lane (32 < n <= 64): dense FD Jacobian only so far
+template <class PROB>
+static int warp2_dispatch(int mf, const KArgs &a, cudaStream_t st) {
+    const MfParts m = mf_parts(mf);
+    if (m.miter != 2) return -1000;
+    if (m.meth == 1)
+        return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 1>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 1>>(a, st);
+    if (m.meth == 2)
+        return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 2>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 2>>(a, st);
+    return -1000;
+}
+template <class PROB, class F>
+static int warp2_layout(int mf, F &&fn) {
+    const MfParts m = mf_parts(mf);
+    if (m.miter != 2) return -1000;
+    if (m.meth == 1) return m.savej ? fn(WarpDense2Policy<PROB, 2, true, 1>{}) : fn(WarpDense2Policy<PROB, 2, false, 1>{});
+    if (m.meth == 2) return m.savej ? fn(WarpDense2Policy<PROB, 2, true, 2>{}) : fn(WarpDense2Policy<PROB, 2, false, 2>{});
+    return -1000;
+}
+template <class PROB>
+static int warp2_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
+    return warp2_layout<PROB>(mf, [&](auto pol) { return launch_dky_warp<decltype(pol)>(a, st); });
+}
+template <class PROB>
+static void warp2_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
+    *nd = *ni = 0;
+    warp2_layout<PROB>(mf, [&](auto pol) {
+        WarpLayout<decltype(pol)>::sizes(ml, mu, nsys, nd, ni);
+        return 0;
+    });
+}
+template <class PROB>
+static int warp2_supports(int mf, int, int) {
+    const MfParts m = mf_parts(mf);
+    return (m.meth == 1 || m.meth == 2) && m.miter == 2;
+}
+static int no_state_convert(int, int, int, int, size_t, const double *, const int *, double *, int *, cudaStream_t) {
+    return -1000;
+}
+#define BVODE_WARP2_DENSE_FD_PROBLEM(NAME, PROB)                                            \
+    ProblemEntry {                                                                          \
+        NAME, PROB::N, PROB::NPAR, 1, warp2_supports<PROB>, warp2_state_size<PROB>,         \
+            warp2_dispatch<PROB>, warp2_dky_dispatch<PROB>, no_state_convert                \
+    }
 #define BVODE_WARP_DENSE_FD_PROBLEM(NAME, PROB)                                             \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 1>, warp_state_size<PROB, 1>,     \

@@ -1,6 +1,6 @@
 // bvode_registry.cu -- instantiates every kernel of ONE problem for one build and exports its
 // table entry.  Compiled once per (build, problem): -DBVODE_STRICT=0 (fast, the product) or
-// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..5.
+// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..6.
 #include "bvode_kernels.cuh"
 
 #ifndef BVODE_UNIT
@@ -20,6 +20,8 @@ static const ProblemEntry kEntry = BVODE_WARP_DENSE_FD_PROBLEM("mech32", Mech32)
 static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp_maxnorm", VanDerPolMaxNorm);
 #elif BVODE_UNIT == 5
 static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection_maxnorm", Advection25MaxNorm);
+#elif BVODE_UNIT == 6
+static const ProblemEntry kEntry = BVODE_WARP2_DENSE_FD_PROBLEM("diffusion48", Diffusion48);
 #endif
 }  // namespace BVODE_NS
 

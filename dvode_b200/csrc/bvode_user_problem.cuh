@@ -47,3 +47,5 @@
 // one system per warp (n <= 32), lane-wise f_lane: banded (miter 4 / 5) or dense FD (miter 2) Jacobian
 #define BVODE_REGISTER_WARP_BAND_PROBLEM(NAME, PROB) BVODE_USER_ENTRY_(BVODE_WARP_BAND_PROBLEM, NAME, PROB)
 #define BVODE_REGISTER_WARP_DENSE_FD_PROBLEM(NAME, PROB) BVODE_USER_ENTRY_(BVODE_WARP_DENSE_FD_PROBLEM, NAME, PROB)
+// one system per warp, two components per lane (32 < n <= 64), f_lane2: dense FD Jacobian (miter 2)
+#define BVODE_REGISTER_WARP2_DENSE_FD_PROBLEM(NAME, PROB) BVODE_USER_ENTRY_(BVODE_WARP2_DENSE_FD_PROBLEM, NAME, PROB)

@@ -162,4 +162,27 @@ struct Mech32 {
     }
 };
 
+// 1-D reaction-diffusion chain with n = 48 cells and walls at both ends (builder-defined, NOT in the
+// reference: it exercises the two-components-per-lane mapping for 32 < n <= 64):
+//     y_i' = D (y_{i-1} - 2 y_i + y_{i+1}) - k y_i^2 + s_i,   s_i = 1 in the first four cells.
+// par = (D, k).  f_lane2: this lane's components ln (slot 0) and ln + 32 (slot 1).
+struct Diffusion48 {
+    static constexpr int N = 48, NPAR = 2, NPAR_LANE = 2;
+    BV_DEV static void load_par(double (&par)[2], const double *params, size_t nsys, size_t sys, int) {
+        par[0] = params[sys];
+        par[1] = params[nsys + sys];
+    }
+    BV_DEV static void f_lane2(double, const double (&y)[2], double (&ydot)[2], const double (&p)[2], int ln) {
+        const unsigned full = 0xffffffffu;
+        const double up0 = __shfl_up_sync(full, y[0], 1), dn0 = __shfl_down_sync(full, y[0], 1);
+        const double up1 = __shfl_up_sync(full, y[1], 1), dn1 = __shfl_down_sync(full, y[1], 1);
+        const double y31 = __shfl_sync(full, y[0], 31), y32 = __shfl_sync(full, y[1], 0);
+        const double l0 = (ln > 0) ? up0 : 0.0, r0 = (ln < 31) ? dn0 : y32;
+        const double l1 = (ln > 0) ? up1 : y31, r1 = (ln + 33 < N) ? dn1 : 0.0;
+        const double s0 = (ln < 4) ? 1.0 : 0.0;
+        ydot[0] = p[0] * ((l0 - 2.0 * y[0]) + r0) - p[1] * y[0] * y[0] + s0;
+        ydot[1] = p[0] * ((l1 - 2.0 * y[1]) + r1) - p[1] * y[1] * y[1] + 0.0;
+    }
+};
+
 }  // namespace BVODE_NS

@@ -155,7 +155,21 @@ int dvo_problem_info(int problem, int *neq, int *npar)
     case 3: *neq = BVODE_MECH_NS; *npar = BVODE_MECH_NR; return 0;
     case 4: *neq = 2; *npar = 1; return 0;
     case 5: *neq = NG * NG; *npar = 2; return 0;  /* advection with the user norms of problem 4 */
+    case 6: *neq = 48; *npar = 2; return 0;
     default: return -1;
+    }
+}
+
+/* ------------------------------------------- reaction-diffusion chain, n = 48 --- */
+/* builder-defined (dvode_b200/csrc/problems.cuh, Diffusion48): par = (D, k) */
+static void dif_f(void *ctx, int neq, double t, const double *y, double *ydot)
+{
+    const double *p = (const double *)ctx;
+    (void)neq; (void)t;
+    for (int i = 0; i < 48; i++) {
+        double l = (i > 0) ? y[i - 1] : 0.0, r = (i + 1 < 48) ? y[i + 1] : 0.0;
+        double s = (i < 4) ? 1.0 : 0.0;
+        ydot[i] = p[0] * ((l - 2.0 * y[i]) + r) - p[1] * y[i] * y[i] + s;
     }
 }
 
@@ -168,6 +182,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     case 3: *f = mech_f; *jac = NULL; return 0;
     case 4: *f = vdp_f; *jac = vdp_jac; return 0;
     case 5: *f = adv_f; *jac = adv_jac; return 0;
+    case 6: *f = dif_f; *jac = NULL; return 0;
     default: return -1;
     }
 }

@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
 
 PROBLEMS = {"robertson": 0, "vdp": 1, "advection": 2, "mech32": 3, "vdp_maxnorm": 4,
-            "advection_maxnorm": 5}
+            "advection_maxnorm": 5, "diffusion48": 6}
 
 
 class BatchCfg(C.Structure):

@@ -890,3 +890,83 @@ def test_warp_dvindy_and_checkpoint():
                       iwork, 30, 24, yo)
     assert (istate == 2).all()
     assert np.array_equal(yo.transpose(1, 0, 2), full["y"][:, 3:])
+
+
+# ------------------------------------------- two components per lane (32 < n <= 64) ------
+@pytest.mark.parametrize("mf", [22, -22, 12])
+def test_diffusion48_strict_bit_exact(mf):
+    """n = 48 on the one-system-per-warp kernel with TWO components per lane (WarpDense2Policy): dense
+    finite-difference Jacobian, implicit pivoting over two rows per lane; bit for bit like the oracle."""
+    B = _B()
+    nsys = 37
+    par = B.batches.diffusion48_batch(nsys)
+    tol = B.batches.DIFFUSION48_TOL
+    touts = B.batches.diffusion48_touts()
+    ref = O.batch_solve("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], mf,
+                        itol=1, iopt=1, mxstep=20000, pow_mode=1)
+    got = gpu_schedule("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], mf, 1,
+                       strict=True, iopt=1, iwork_opts=_iw(0, 0, 20000))
+    assert (ref["istate"] == 2).all() and (got["istate"][:, -1] == 2).all()
+    assert np.array_equal(got["y"], ref["y"])
+    assert np.array_equal(got["istats"][:, -1], ref["istats"][:, -1])
+    assert np.array_equal(got["rstats"][:, -1], ref["rstats"][:, -1])
+    # per call = schedule, and dvindy / checkpoint go through the same state layout
+    got2 = gpu_schedule("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], mf, 1,
+                        strict=True, iopt=1, iwork_opts=_iw(0, 0, 20000), per_call=True)
+    _same(got2, ref)
+
+
+def test_diffusion48_fast_parity():
+    B = _B()
+    nsys = 1024
+    par = B.batches.diffusion48_batch(nsys)
+    tol = B.batches.DIFFUSION48_TOL
+    touts = B.batches.diffusion48_touts()
+    ref = O.batch_solve("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], 22,
+                        itol=1, iopt=1, mxstep=20000)
+    got = gpu_schedule("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], 22, 1,
+                       iopt=1, iwork_opts=_iw(0, 0, 20000))
+    assert (got["istate"][:, -1] == 2).all()
+    w = weighted_err(got["y"], ref["y"], tol["rtol"], tol["atol"])
+    assert w.max() <= 10.0, w.max()  # a smooth parabolic problem: pointwise agreement holds
+    for name in ("nst", "nfe", "nje", "nlu", "nni"):
+        a = got["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        b = ref["istats"][:, -1, O.ISTAT[name]].astype(np.int64).sum()
+        assert abs(a - b) <= 0.02 * b, (name, a, b)
+
+
+def test_diffusion48_dvindy_and_checkpoint():
+    """dvindy and dvsrco through the two-components-per-lane state layout: k = 0 at tcur reproduces
+    yh(:,1) = the current solution, k = 1 the derivative f(y); a restored handle continues bit for bit."""
+    B = _B()
+    nsys = 33
+    par = B.batches.diffusion48_batch(nsys)
+    tol = B.batches.DIFFUSION48_TOL
+    touts = B.batches.diffusion48_touts()
+    args = ("diffusion48", par, B.batches.diffusion48_y0(), 0.0)
+    full = gpu_schedule(*args, touts, tol["rtol"], tol["atol"], 22, 1, iopt=1, iwork_opts=_iw(0, 0, 20000))
+    half = gpu_schedule(*args, touts[:2], tol["rtol"], tol["atol"], 22, 1, iopt=1, iwork_opts=_iw(0, 0, 20000))
+    s = half["solver"]
+    r, _ = s.stats()
+    y_tcur, iflag = s.dvindy(r[:, 2], 0)
+    assert (iflag == 0).all()
+    d1, iflag = s.dvindy(r[:, 2], 1)
+    assert (iflag == 0).all()
+    yp = np.pad(y_tcur, ((0, 0), (1, 1)))
+    src = np.where(np.arange(48) < 4, 1.0, 0.0)
+    f = par[:, :1] * (yp[:, :-2] - 2.0 * y_tcur + yp[:, 2:]) - par[:, 1:] * y_tcur ** 2 + src
+    assert np.abs(d1 - f).max() < 1e-3 * np.abs(f).max()
+    _, iflag = s.dvindy(r[:, 2], 7)
+    assert (iflag == -1).all()
+    sav = s.dvsrco(None, 1)
+    s2 = B.dvode_t().initialize("diffusion48", nsys, par)
+    s2.dvsrco(sav, 2)
+    y, t = half["y"][:, -1].copy(), half["t"][:, -1].copy()
+    istate = np.full(nsys, 2, dtype=np.int32)
+    iwork = np.zeros((nsys, 30), dtype=np.int32)
+    iwork[0, 5] = 20000
+    rwork = np.zeros((nsys, 20))
+    yo = np.zeros((2, nsys, 48))
+    s2.solve_schedule(48, y, t, touts[2:], 1, tol["rtol"], tol["atol"], 1, istate, 1, rwork, 20, iwork, 30, 22, yo)
+    assert (istate == 2).all()
+    assert np.array_equal(yo.transpose(1, 0, 2), full["y"][:, 2:])
