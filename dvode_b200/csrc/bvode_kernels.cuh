@@ -236,7 +236,11 @@ constexpr int kScalarI = 19;
 #ifndef BVODE_WARP_TPB
 #define BVODE_WARP_TPB 128
 #endif
-constexpr int kWarpTPB = BVODE_WARP_TPB;  // threads per CTA = 32 x systems per CTA
+constexpr int kWarpTPB = BVODE_WARP_TPB;  // threads per CTA = 32 x systems per CTA (a policy may choose its own)
+template <class POL, class = void>
+struct WarpTpb { static constexpr int value = kWarpTPB; };
+template <class POL>
+struct WarpTpb<POL, decltype((void)POL::kTPB)> { static constexpr int value = POL::kTPB; };
 
 struct WarpLoader {
     const double *ds, *dl, *db;
@@ -294,7 +298,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
         if constexpr (POL::kBand) nb = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
         else if constexpr (POL::kPlain) nb = 0;
         else nb = POL::kBlockDoubles;
-        e.hot.bind(smem + (size_t)(kWarpTPB / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
+        e.hot.bind(smem + (size_t)(WarpTpb<POL>::value / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
     }
     if constexpr (POL::kBand) {
         nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
@@ -323,11 +327,11 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
 // (the replicated control state lives once per warp in shared memory, see WarpCommon::Hot;
 // before that: 6 CTAs 88.8k / 1.53M).
 template <class POL, bool GENERAL>
-__global__ void __launch_bounds__(kWarpTPB, POL::kMinBlocks)
+__global__ void __launch_bounds__(WarpTpb<POL>::value, POL::kMinBlocks)
 vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    const size_t sys = (size_t)a.sys0 + (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
+    const size_t sys = (size_t)a.sys0 + (size_t)blockIdx.x * (WarpTpb<POL>::value / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
     if (sys >= (size_t)(a.sys0 + a.count)) return;  // whole warp
     constexpr int N = POL::N;
@@ -453,10 +457,10 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 }
 
 template <class POL>
-__global__ void __launch_bounds__(kWarpTPB) dvindy_warp_kernel(const __grid_constant__ DkyArgs a) {
+__global__ void __launch_bounds__(WarpTpb<POL>::value) dvindy_warp_kernel(const __grid_constant__ DkyArgs a) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-    const size_t sys = (size_t)blockIdx.x * (kWarpTPB / 32) + warp;
+    const size_t sys = (size_t)blockIdx.x * (WarpTpb<POL>::value / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
     if (sys >= nsys) return;
     constexpr int N = POL::N;
@@ -534,28 +538,28 @@ static int launch_dky_thread(const DkyArgs &a, cudaStream_t st) {
 }
 template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
-    const int spb = kWarpTPB / 32;
+    const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.count + spb - 1) / spb;
     const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles);
     if (a.general) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_warp_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vode_warp_kernel<POL, true><<<grid, kWarpTPB, smem, st>>>(a);
+        vode_warp_kernel<POL, true><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     } else {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_warp_kernel<POL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vode_warp_kernel<POL, false><<<grid, kWarpTPB, smem, st>>>(a);
+        vode_warp_kernel<POL, false><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
 template <class POL>
 static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
-    const int spb = kWarpTPB / 32;
+    const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.nsys + spb - 1) / spb;
     const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.ml, a.mu) + POL::kWarpHotDoubles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(dvindy_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dvindy_warp_kernel<POL><<<grid, kWarpTPB, smem, st>>>(a);
+    dvindy_warp_kernel<POL><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -734,20 +738,29 @@ static int warp_supports(int mf, int ml, int mu) {
 template <class PROB>
 static int warp2_dispatch(int mf, const KArgs &a, cudaStream_t st) {
     const MfParts m = mf_parts(mf);
-    if (m.miter != 2) return -1000;
-    if (m.meth == 1)
-        return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 1>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 1>>(a, st);
-    if (m.meth == 2)
-        return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 2>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 2>>(a, st);
+    if (m.meth == 1) {
+        if (m.miter == 0) return launch_warp<WarpPlain2Policy<PROB, 0, 1>>(a, st);
+        if (m.miter == 3) return launch_warp<WarpPlain2Policy<PROB, 3, 1>>(a, st);
+        if (m.miter == 2)
+            return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 1>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 1>>(a, st);
+    }
+    if (m.meth == 2) {
+        if (m.miter == 0) return launch_warp<WarpPlain2Policy<PROB, 0, 2>>(a, st);
+        if (m.miter == 3) return launch_warp<WarpPlain2Policy<PROB, 3, 2>>(a, st);
+        if (m.miter == 2)
+            return m.savej ? launch_warp<WarpDense2Policy<PROB, 2, true, 2>>(a, st) : launch_warp<WarpDense2Policy<PROB, 2, false, 2>>(a, st);
+    }
     return -1000;
 }
 template <class PROB, class F>
 static int warp2_layout(int mf, F &&fn) {
     const MfParts m = mf_parts(mf);
+    if (m.meth != 1 && m.meth != 2) return -1000;
+    if (m.miter == 0 || m.miter == 3)  // one state layout for both
+        return (m.meth == 1) ? fn(WarpPlain2Policy<PROB, 0, 1>{}) : fn(WarpPlain2Policy<PROB, 0, 2>{});
     if (m.miter != 2) return -1000;
     if (m.meth == 1) return m.savej ? fn(WarpDense2Policy<PROB, 2, true, 1>{}) : fn(WarpDense2Policy<PROB, 2, false, 1>{});
-    if (m.meth == 2) return m.savej ? fn(WarpDense2Policy<PROB, 2, true, 2>{}) : fn(WarpDense2Policy<PROB, 2, false, 2>{});
-    return -1000;
+    return m.savej ? fn(WarpDense2Policy<PROB, 2, true, 2>{}) : fn(WarpDense2Policy<PROB, 2, false, 2>{});
 }
 template <class PROB>
 static int warp2_dky_dispatch(int mf, const DkyArgs &a, cudaStream_t st) {
@@ -764,7 +777,7 @@ static void warp2_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, si
 template <class PROB>
 static int warp2_supports(int mf, int, int) {
     const MfParts m = mf_parts(mf);
-    return (m.meth == 1 || m.meth == 2) && m.miter == 2;
+    return (m.meth == 1 || m.meth == 2) && (m.miter == 0 || m.miter == 2 || m.miter == 3);
 }
 static int no_state_convert(int, int, int, int, size_t, const double *, const int *, double *, int *, cudaStream_t) {
     return -1000;

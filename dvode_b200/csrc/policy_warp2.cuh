@@ -8,8 +8,9 @@
 //
 //   WarpDense2Policy : dense finite-difference Jacobian, mf = +-12 / +-22
 //                      dvjac miter 2  M:2941-3001, dgefa LP:46-120, dgesl LP:206-225
-// This is the first, untuned form of the mapping (one step of elimination per pass, one CTA of four
-// systems per SM because of the 64 x 65 matrix per warp): it is here for coverage of n up to 64.
+//   WarpPlain2Policy : functional iteration / diagonal approximation, mf = 10, 13, 20, 23
+// This is the first form of the mapping (one step of elimination per pass; two systems per CTA and
+// three CTAs per SM because of the 64 x 65 matrix per warp): it is here for coverage of n up to 64.
 #pragma once
 #include "policy_warp.cuh"
 
@@ -162,7 +163,14 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
     static constexpr bool kPlain = false;
-    static constexpr int kMinBlocks = 1;  // 4 x (64 x 65 doubles) of shared memory per CTA
+#ifndef BVODE_DENSE2_TPB
+#define BVODE_DENSE2_TPB 64
+#endif
+#ifndef BVODE_DENSE2_MINBLOCKS
+#define BVODE_DENSE2_MINBLOCKS 3
+#endif
+    static constexpr int kTPB = BVODE_DENSE2_TPB;  // 2 systems per CTA: 2 x (64 x 65 doubles) of shared memory
+    static constexpr int kMinBlocks = BVODE_DENSE2_MINBLOCKS;
     static constexpr int LDP = N | 1;
     static constexpr int kBlockDoubles = N * LDP + 32 + ((N * LDP) & 1);  // the matrix, then perm[64] (ints)
     static_assert(MITER == 2, "dense finite-difference Jacobian");
@@ -436,6 +444,103 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
         const int ier = dgefa(l);
         if (ier != 0) ierpj = 1;
+    }
+};
+
+// No Newton matrix: functional iteration (miter = 0, M:2822-2837) or the diagonal Jacobian
+// approximation (miter = 3: dvjac M:3004-3028, dvsol M:3164-3181), two diagonal entries per lane.
+template <class PROB, int MITER_, int METH_ = 2>
+struct WarpPlain2Policy : WarpCommon2<PROB, METH_> {
+    using Base = WarpCommon2<PROB, METH_>;
+    using Prob = PROB;
+    using Base::lane;
+    using Base::valid;
+    static constexpr int N = PROB::N;
+    static constexpr int NLOC = 2;
+    static constexpr int MITER = MITER_;
+    static constexpr int METH = METH_;
+    static constexpr int kLmax = Base::kLmax;
+    static constexpr bool SAVEJ = false;
+    static constexpr bool kBand = false;
+    static constexpr bool kPlain = true;
+    static constexpr int kMinBlocks = 4;
+    static_assert(MITER == 0 || MITER == 3, "plain policy");
+
+    struct Lin {
+        double diag[2];  // wm(2 + c): inverted diagonal of P (miter = 3)
+        double phrl1;    // wm(2): h*rl1 at the last update (replicated on all lanes)
+    };
+    template <class ENG>
+    BV_DEV static void lin_init(ENG &e) { e.lin.diag[0] = e.lin.diag[1] = 1.0; e.lin.phrl1 = 0.0; }
+    static int smem_doubles(int, int, bool) { return 0; }
+    static constexpr int kLaneSlots = 2 * kLmax + 4 + 3;  // yh, acsav, acor, diag[2], phrl1
+    static constexpr int kLaneIntSlots = 1;
+    template <class ENG, class V>
+    BV_DEV static void visit_acsav(ENG &e, V &v) {
+        v.dv(e.acsav.v[0]);
+        v.dv(e.acsav.v[1]);
+    }
+    template <class ENG, class V>
+    BV_DEV static void visit_lin(ENG &e, V &v) {
+        v.dv(e.lin.diag[0]);
+        v.dv(e.lin.diag[1]);
+        v.dv(e.lin.phrl1);
+        int dummy = 0;
+        v.iv(dummy);
+    }
+    // index of the first component with `z`, 64 if none (the reference stops at the first zero:
+    // entries before it are already updated)
+    BV_DEV static int first_of(bool z0, bool z1) {
+        const unsigned m0 = __ballot_sync(kFull, z0), m1 = __ballot_sync(kFull, z1);
+        return m0 ? (__ffs((int)m0) - 1) : (m1 ? (__ffs((int)m1) - 1 + 32) : 64);
+    }
+
+    template <class ENG>
+    BV_DEV static int solve(ENG &e, double (&x)[2]) {
+        Lin &l = e.lin;
+        const double hrl1 = e.c.h * e.c.rl1;
+        const double phrl1 = l.phrl1;
+        l.phrl1 = hrl1;
+        if (hrl1 != phrl1) {
+            const double r = hrl1 / phrl1;
+            const double di[2] = {1.0 - r * (1.0 - 1.0 / l.diag[0]), 1.0 - r * (1.0 - 1.0 / l.diag[1])};
+            const int first = first_of(fabs(di[0]) == 0.0, valid(1) && fabs(di[1]) == 0.0);
+            if (lane() < first) l.diag[0] = 1.0 / di[0];
+            if (valid(1) && lane() + 32 < first) l.diag[1] = 1.0 / di[1];
+            if (first < 64) return 1;
+        }
+        x[0] = l.diag[0] * x[0];
+        x[1] = valid(1) ? l.diag[1] * x[1] : 0.0;
+        return 0;
+    }
+
+    template <class ENG>
+    BV_DEV static void jac_setup(ENG &e, int &ierpj) {
+        Ctl &c = e.c;
+        Lin &l = e.lin;
+        ierpj = 0;
+        const double hrl1 = c.h * c.rl1;
+        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        c.jcur = 1;
+        l.phrl1 = hrl1;
+        const double r = c.rl1 * 0.1;
+#pragma unroll
+        for (int i = 0; i < 2; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
+        double w[2];
+        Base::f(c.tn, e.y, w, e.par);
+        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
+        double r0[2], di[2];
+        bool big[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            r0[i] = c.h * e.savf[i] - e.hot.yh(1, i);
+            di[i] = 0.1 * r0[i] - c.h * (w[i] - e.savf[i]);
+            big[i] = valid(i) && (fabs(r0[i]) >= kUround / e.ewt[i]);
+        }
+        const int first = first_of(big[0] && fabs(di[0]) == 0.0, big[1] && fabs(di[1]) == 0.0);
+        if (lane() < first) l.diag[0] = big[0] ? 0.1 * r0[0] / di[0] : 1.0;
+        if (valid(1) && lane() + 32 < first) l.diag[1] = big[1] ? 0.1 * r0[1] / di[1] : 1.0;
+        if (first < 64) ierpj = 1;
     }
 };
 

@@ -916,6 +916,23 @@ def test_diffusion48_strict_bit_exact(mf):
     _same(got2, ref)
 
 
+@pytest.mark.parametrize("mf", [10, 13, 20, 23])
+def test_diffusion48_functional_and_diagonal_strict_bit_exact(mf):
+    """The matrix-free method flags on the two-components-per-lane mapping (WarpPlain2Policy):
+    functional iteration and the diagonal Jacobian approximation, Adams and BDF."""
+    B = _B()
+    nsys = 35
+    par = B.batches.diffusion48_batch(nsys)
+    tol = B.batches.DIFFUSION48_TOL
+    touts = B.batches.diffusion48_touts()[:3]
+    ref = O.batch_solve("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], mf,
+                        itol=1, iopt=1, mxstep=20000, pow_mode=1)
+    got = gpu_schedule("diffusion48", par, B.batches.diffusion48_y0(), 0.0, touts, tol["rtol"], tol["atol"], mf, 1,
+                       strict=True, iopt=1, iwork_opts=_iw(0, 0, 20000), per_call=True)
+    assert (ref["istate"] == 2).all()
+    _same(got, ref)
+
+
 def test_diffusion48_fast_parity():
     B = _B()
     nsys = 1024
