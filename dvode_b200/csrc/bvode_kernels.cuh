@@ -646,6 +646,11 @@ static int thread_supports(int mf, int ml, int mu) {
             thread_dispatch<PROB>, thread_dky_dispatch<PROB>, thread_state_convert<PROB>    \
     }
 
+template <class P, class = void>
+struct HasJacRow { static constexpr bool value = false; };
+template <class P>
+struct HasJacRow<P, decltype((void)&P::jac_row)> { static constexpr bool value = true; };
+
 // ---- warp-per-system problems ---------------------------------------------------------------
 // KIND 1: dense finite-difference Jacobian available (miter 2); KIND 2: banded (miter 4, 5).
 // Both kinds also run miter 0 (functional iteration) and 3 (diagonal approximation).
@@ -654,6 +659,11 @@ static int warp_dispatch_m(const MfParts &m, const KArgs &a, cudaStream_t st) {
     switch (m.miter) {
     case 0: return launch_warp<WarpPlainPolicy<PROB, 0, METH>>(a, st);
     case 3: return launch_warp<WarpPlainPolicy<PROB, 3, METH>>(a, st);
+    case 1:  // dense analytic Jacobian: problems with a jac_row member
+        if constexpr (KIND == 1 && HasJacRow<PROB>::value)
+            return m.savej ? launch_warp<WarpDensePolicy<PROB, 1, true, METH>>(a, st)
+                           : launch_warp<WarpDensePolicy<PROB, 1, false, METH>>(a, st);
+        return -1000;
     case 2:
         if constexpr (KIND == 1)
             return m.savej ? launch_warp<WarpDensePolicy<PROB, 2, true, METH>>(a, st)
@@ -684,7 +694,7 @@ template <class PROB, int KIND, int METH, class F>
 static int warp_layout_m(const MfParts &m, F &&fn) {
     if (m.miter == 0 || m.miter == 3) return fn(WarpPlainPolicy<PROB, 0, METH>{});
     if constexpr (KIND == 1) {
-        if (m.miter == 2)
+        if (m.miter == 2 || (m.miter == 1 && HasJacRow<PROB>::value))  // one state layout for both
             return m.savej ? fn(WarpDensePolicy<PROB, 2, true, METH>{})
                            : fn(WarpDensePolicy<PROB, 2, false, METH>{});
     } else {
@@ -730,7 +740,7 @@ static int warp_supports(int mf, int ml, int mu) {
     const MfParts m = mf_parts(mf);
     if (m.meth != 1 && m.meth != 2) return 0;
     if (m.miter == 0 || m.miter == 3) return 1;
-    if (KIND == 1) return m.miter == 2;
+    if (KIND == 1) return m.miter == 2 || (m.miter == 1 && HasJacRow<PROB>::value);
     return (m.miter == 4 || m.miter == 5) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 &&
            ml < PROB::N && mu < PROB::N;
 }

@@ -566,8 +566,8 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 if (ln < N) {
 #pragma unroll 1
                     for (int j = 0; j < N; j++) row[j] = 0.0;
-                    PROB::jac_row(c.tn, e.y[0], row, e.par, ln);
                 }
+                PROB::jac_row(c.tn, e.y[0], row, e.par, ln);  // every lane calls (it may shuffle); lanes >= N must not write
             } else {
                 // finite differences, M:2959-2976: column j for all rows at once
                 const double r0 = Base::fd_r0(c, e.savf, e.ewt);

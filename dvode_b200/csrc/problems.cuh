@@ -160,6 +160,30 @@ struct Mech32 {
         }
         return d;
     }
+    // Row `ln` of the Jacobian, accumulated entry by entry in the order of f (all 32 lanes call: the
+    // rate constants and the partner concentrations come by shuffle).  d(k y_a y_b)/dy_a = k y_b,
+    // d/dy_b = k y_a; unimolecular: k.  `row` is pre-zeroed by the solver (M:2947-2949).
+    BV_DEV static void jac_row(double, double y, double *row, const double (&k)[2], int ln) {
+        const unsigned full = 0xffffffffu;
+#pragma unroll 1
+        for (int e = 0; e < BVODE_MECH_MAXE; e++) {
+            const int r = g_mech_ent_r[ln][e];  // -1: unused slot (still takes part in the shuffles)
+            const double s = g_mech_ent_s[ln][e];
+            const int rr = (r < 0) ? 0 : r;
+            const int a = g_mech_ra[rr], b = g_mech_rb[rr];  // b = -1: unimolecular
+            const double k0 = __shfl_sync(full, k[0], rr & 31), k1 = __shfl_sync(full, k[1], rr & 31);
+            const double kr = (rr >= 32) ? k1 : k0;
+            const double ya = __shfl_sync(full, y, a), yb = __shfl_sync(full, y, (b < 0) ? 0 : b);
+            if (r >= 0) {
+                if (b < 0) {
+                    row[a] = row[a] + s * kr;
+                } else {
+                    row[a] = row[a] + s * (kr * yb);
+                    row[b] = row[b] + s * (kr * ya);
+                }
+            }
+        }
+    }
 };
 
 // 1-D reaction-diffusion chain with n = 48 cells and walls at both ends (builder-defined, NOT in the

@@ -160,6 +160,27 @@ int dvo_problem_info(int problem, int *neq, int *npar)
     }
 }
 
+/* analytic Jacobian of the mechanism, entry by entry in the order of mech_f (pd pre-zeroed, M:2947) */
+static void mech_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd, int nrowpd)
+{
+    const double *k = (const double *)ctx;
+    (void)neq; (void)t; (void)ml; (void)mu;
+    for (int i = 0; i < BVODE_MECH_NS; i++) {
+        for (int e = 0; e < BVODE_MECH_MAXE; e++) {
+            int r = bvode_mech_ent_r[i][e];
+            if (r < 0) break;
+            double s = bvode_mech_ent_s[i][e];
+            int a = bvode_mech_ra[r], b = bvode_mech_rb[r];
+            if (b < 0) {
+                pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * k[r];
+            } else {
+                pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * (k[r] * y[b]);
+                pd[i + b * nrowpd] = pd[i + b * nrowpd] + s * (k[r] * y[a]);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------- reaction-diffusion chain, n = 48 --- */
 /* builder-defined (dvode_b200/csrc/problems.cuh, Diffusion48): par = (D, k) */
 static void dif_f(void *ctx, int neq, double t, const double *y, double *ydot)
@@ -179,7 +200,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     case 0: *f = rob_f; *jac = rob_jac; return 0;
     case 1: *f = vdp_f; *jac = vdp_jac; return 0;
     case 2: *f = adv_f; *jac = adv_jac; return 0;
-    case 3: *f = mech_f; *jac = NULL; return 0;
+    case 3: *f = mech_f; *jac = mech_jac; return 0;
     case 4: *f = vdp_f; *jac = vdp_jac; return 0;
     case 5: *f = adv_f; *jac = adv_jac; return 0;
     case 6: *f = dif_f; *jac = NULL; return 0;

@@ -808,7 +808,7 @@ def test_advection_fast_parity():
             assert abs(a - b) <= 0.02 * b, (mf, name, a, b)
 
 
-@pytest.mark.parametrize("mf", [22, -22])
+@pytest.mark.parametrize("mf", [22, -22, 21, -21])
 def test_mech32_strict_bit_exact(mf):
     B = _B()
     nsys = 64

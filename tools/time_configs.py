@@ -19,8 +19,8 @@ if a.which in ("both", "advection"):
     for mf in (24, 25):
         cfgs.append(("advection", mf, batches.advection_batch(a.nsys), batches.advection_y0(),
                      batches.advection_touts(), batches.ADVECTION_TOL, 0, (5, 0, 0)))
-if a.which in ("both", "mech32"):
-    cfgs.append(("mech32", 22, batches.mech32_batch(a.nsys), batches.mech32_y0(),
+if a.which in ("both", "mech32", "mech32_21"):
+    cfgs.append(("mech32", 21 if a.which == "mech32_21" else 22, batches.mech32_batch(a.nsys), batches.mech32_y0(),
                  batches.mech32_touts(), batches.MECH32_TOL, 1, (0, 0, 100000)))
 for name, mf, par, y0, touts, tol, iopt, (ml, mu, mxstep) in cfgs:
     s = B.dvode_t().initialize(name, a.nsys, par)
