@@ -9,8 +9,8 @@ fails loudly if the library is missing.  Only `dvode_b200.build` (the nvcc recip
 """
 import importlib
 
-_API_NAMES = ("BvodeError", "dvode_t", "fp64_peak_tflops", "library_path", "problem_info",
-              "problem_names")
+_API_NAMES = ("BvodeError", "Comm", "dvode_multi_t", "dvode_t", "fp64_peak_tflops", "library_path",
+              "nccl_version", "problem_info", "problem_names")
 __all__ = list(_API_NAMES) + ["api", "batches", "build", "plugins", "sharding"]
 
 

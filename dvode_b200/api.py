@@ -60,10 +60,36 @@ def _load():
     lib.bvode_state_bytes.argtypes = [vp]
     lib.bvode_state_bytes.restype = C.c_longlong
     lib.bvode_dvsrco.argtypes = [vp, vp, C.c_int]
+    lib.bvode_dvsrco_n.argtypes = [vp, vp, C.c_longlong, C.c_int]
+    lib.bvode_reset.argtypes = [vp]
+    # multi-GPU
+    ll, llp = C.c_longlong, C.POINTER(C.c_longlong)
+    lib.bvode_shard_range.argtypes = [ll, C.c_int, C.c_int, llp, llp]
+    lib.bvode_shard_range.restype = None
+    lib.bvode_comm_unique_id.argtypes = [C.c_char_p]
+    lib.bvode_comm_create.argtypes = [C.POINTER(vp), C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.bvode_comm_adopt.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]
+    lib.bvode_comm_destroy.argtypes = [vp]
+    lib.bvode_comm_destroy.restype = None
+    lib.bvode_gather_device.argtypes = [vp, vp, C.c_int, ll, vp, vp, vp, vp, vp, vp]
+    lib.bvode_gather.argtypes = [vp, vp, C.c_int, ll, vp, vp, vp, vp, vp]
+    lib.bvode_multi_create.argtypes = [C.POINTER(vp), C.c_int, ll, C.c_int, ip, C.c_uint]
+    lib.bvode_multi_destroy.argtypes = [vp]
+    lib.bvode_multi_destroy.restype = None
+    lib.bvode_multi_device_count.argtypes = [vp]
+    lib.bvode_multi_handle.argtypes = [vp, C.c_int]
+    lib.bvode_multi_handle.restype = vp
+    lib.bvode_multi_set_params.argtypes = [vp, vp]
+    lib.bvode_multi_solve.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp,
+                                      C.c_int, vp, C.c_int, vp, C.c_int, C.c_int]
+    lib.bvode_multi_solve_schedule.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp,
+                                               C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp]
+    lib.bvode_multi_gather_device.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     lib.bvode_last_launch_count.argtypes = [vp]
     lib.bvode_istate_summary.argtypes = [vp, vp]
     lib.bvode_format_message.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     lib.bvode_measure_fp64_peak.argtypes = [C.c_int, dp]
+    lib.bvode_lu_test.argtypes = [C.c_int] * 5 + [vp] * 6 + [C.c_int, C.c_uint]
     return lib
 
 
@@ -71,6 +97,7 @@ _lib = _load()
 
 FLAG_STRICT = 1
 FLAG_COMPACT = 2  # hand finished threads the next system of the batch (bvode.h)
+FLAG_PER_SYSTEM = 4  # rtol / atol / optional inputs per system, as the reference has them per instance
 ISTAT = {"nst": 0, "nfe": 1, "nje": 2, "nqu": 3, "nqcur": 4, "imxer": 5, "lenrw": 6, "leniw": 7,
          "nlu": 8, "nni": 9, "ncfn": 10, "netf": 11}
 RSTAT = {"hu": 0, "hcur": 1, "tcur": 2, "tolsf": 3}
@@ -124,12 +151,16 @@ class dvode_t:
         self.nsys = self.neq = self.npar = 0
 
     # -- initialize(f, jac) -> initialize(problem, nsys, params) ------------------------
-    def initialize(self, problem, nsys, params=None, device=0, strict=False, compact=False):
+    def initialize(self, problem, nsys, params=None, device=0, strict=False, compact=False,
+                   per_system=False):
+        """per_system=True: rtol / atol are [nsys, 1 or neq] and the optional inputs are read from
+        every row of rwork / iwork (each system its own solver instance, M:729-751)."""
         self.close()
         pid, self.neq, self.npar = problem_info(problem)
         h = C.c_void_p()
         _check(_lib.bvode_create(C.byref(h), pid, int(nsys), int(device),
-                                 (FLAG_STRICT if strict else 0) | (FLAG_COMPACT if compact else 0)))
+                                 (FLAG_STRICT if strict else 0) | (FLAG_COMPACT if compact else 0) |
+                                 (FLAG_PER_SYSTEM if per_system else 0)))
         self._h = h
         self.nsys = int(nsys)
         self.device = device
@@ -220,8 +251,39 @@ class dvode_t:
         if job == 1:
             n = _lib.bvode_state_bytes(self._h)
             sav = np.zeros(n, dtype=np.uint8)
-        _check(_lib.bvode_dvsrco(self._h, _ptr(sav), int(job)))
+        _check(_lib.bvode_dvsrco_n(self._h, _ptr(sav), int(sav.nbytes), int(job)))
         return sav
+
+    def reset(self):
+        """Drop the integration state (the next call must have istate = 1)."""
+        _check(_lib.bvode_reset(self._h))
+
+    # -- multi-GPU: the final gather of solutions and statistics (bvode.h) -------------------
+    def gather_device(self, comm, root, nsys_total, y_all=0, t_all=0, istate_all=0, rout_all=0,
+                      iout_all=0, stream=0):
+        """Device pointers (ints) on the root; on other ranks any non-zero value = wanted."""
+        vp = lambda x: C.c_void_p(x) if x else None
+        _check(_lib.bvode_gather_device(self._h, comm._c, int(root), int(nsys_total), vp(y_all),
+                                        vp(t_all), vp(istate_all), vp(rout_all), vp(iout_all),
+                                        vp(stream)))
+
+    def gather(self, comm, root, nsys_total, want=("y", "t", "istate", "rout", "iout")):
+        """Host arrays on the root (dict of numpy arrays); None on the other ranks."""
+        is_root = comm.rank == root
+        out = {}
+        shapes = {"y": ((nsys_total, self.neq), np.float64), "t": ((nsys_total,), np.float64),
+                  "istate": ((nsys_total,), np.int32), "rout": ((nsys_total, 4), np.float64),
+                  "iout": ((nsys_total, 12), np.int32)}
+        args = []
+        for k in ("y", "t", "istate", "rout", "iout"):
+            if k in want:
+                a = np.zeros(*shapes[k]) if is_root else np.zeros(1, dtype=shapes[k][1])
+                out[k] = a
+                args.append(_ptr(a))
+            else:
+                args.append(None)
+        _check(_lib.bvode_gather(self._h, comm._c, int(root), int(nsys_total), *args))
+        return out if is_root else None
 
     def stats(self):
         """Optional outputs: (rwork(11:14)[nsys,4], iwork(11:22)[nsys,12])."""
@@ -267,3 +329,126 @@ class dvode_t:
         if not ok:
             raise BvodeError(-1, "y/t/istate/rwork/iwork must be contiguous numpy arrays of "
                                  "float64/float64/int32/float64/int32 with nsys rows")
+
+
+def lu_test(kind, a, b, ml=0, mu=0, strict=False, device=0):
+    """The device LINPACK routines in isolation (bvode_lu_test): a[nmat, n, n] with a[m, i, j] = A(i, j)
+    (kind 0-2) or a[nmat, n, lda] LINPACK band columns (kind 3), b[nmat, n].  Returns
+    (afac, ipvt, x, info) as described in include/bvode.h; afac for kind 0 comes back as [m, i, j]."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    nmat, n = b.shape
+    if kind == 3:
+        ain = np.ascontiguousarray(a)
+    else:
+        ain = np.ascontiguousarray(a.transpose(0, 2, 1))  # column-major per matrix
+    afac = np.zeros_like(ain)
+    ipvt = np.zeros((nmat, n), dtype=np.int32)
+    x = np.zeros((nmat, n))
+    info = np.zeros(nmat, dtype=np.int32)
+    _check(_lib.bvode_lu_test(int(kind), int(n), int(ml), int(mu), int(nmat), _ptr(ain), _ptr(b), _ptr(afac),
+                              _ptr(ipvt), _ptr(x), _ptr(info), int(device), FLAG_STRICT if strict else 0))
+    if kind == 0:
+        afac = afac.transpose(0, 2, 1)
+    return afac, ipvt, x, info
+
+
+def shard_range(nsys_total, rank, world):
+    """[first, last) of the contiguous block of systems owned by `rank` (bvode_shard_range)."""
+    f, l = C.c_longlong(), C.c_longlong()
+    _lib.bvode_shard_range(int(nsys_total), int(rank), int(world), C.byref(f), C.byref(l))
+    return f.value, l.value
+
+
+def nccl_version():
+    return _lib.bvode_nccl_version()
+
+
+class Comm:
+    """An NCCL communicator behind the C ABI (bvode_comm_*): one process per GPU."""
+
+    def __init__(self, world, rank, device, unique_id=None):
+        self.world, self.rank, self.device = int(world), int(rank), int(device)
+        c = C.c_void_p()
+        _check(_lib.bvode_comm_create(C.byref(c), unique_id, self.world, self.rank, self.device))
+        self._c = c
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        _check(_lib.bvode_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if self._c is not None:
+            _lib.bvode_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class dvode_multi_t:
+    """One process, several GPUs (bvode_multi_*): the batch is sharded by system index over the
+    devices; solve / solve_schedule take arrays of nsys_total rows with the arguments of dvode_t."""
+
+    def __init__(self):
+        self._m = None
+
+    def initialize(self, problem, nsys_total, params=None, devices=None, ndev=None, strict=False,
+                   per_system=False):
+        self.close()
+        pid, self.neq, self.npar = problem_info(problem)
+        if devices is None:
+            devices = list(range(int(ndev or 1)))
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        m = C.c_void_p()
+        _check(_lib.bvode_multi_create(C.byref(m), pid, int(nsys_total), dv.size,
+                                       dv.ctypes.data_as(C.POINTER(C.c_int)),
+                                       (FLAG_STRICT if strict else 0) | (FLAG_PER_SYSTEM if per_system else 0)))
+        self._m = m
+        self.nsys = int(nsys_total)
+        self.ndev = dv.size
+        if params is not None:
+            p = _f64(params, (self.nsys, max(self.npar, 1)))
+            _check(_lib.bvode_multi_set_params(self._m, _ptr(p)))
+        return self
+
+    def solve(self, neq, y, t, tout, itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork, liw, mf):
+        tout = _f64(tout).reshape(-1)
+        per = 1 if tout.size > 1 else 0
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        _check(_lib.bvode_multi_solve(self._m, int(neq), _ptr(y), _ptr(t), _ptr(tout), per, int(itol),
+                                      _ptr(rtol), _ptr(atol), int(itask), _ptr(istate), int(iopt),
+                                      _ptr(rwork), int(lrw), _ptr(iwork), int(liw), int(mf)))
+
+    def solve_schedule(self, neq, y, t, touts, itol, rtol, atol, itask, istate, iopt, rwork, lrw,
+                       iwork, liw, mf, y_out=None):
+        touts = _f64(touts).reshape(-1)
+        rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
+        if y_out is not None:
+            assert y_out.dtype == np.float64 and y_out.flags.c_contiguous
+            assert y_out.shape == (touts.size, self.nsys, self.neq)
+        _check(_lib.bvode_multi_solve_schedule(self._m, int(neq), _ptr(y), _ptr(t), touts.size, _ptr(touts),
+                                               int(itol), _ptr(rtol), _ptr(atol), int(itask), _ptr(istate),
+                                               int(iopt), _ptr(rwork), int(lrw), _ptr(iwork), int(liw),
+                                               int(mf), _ptr(y_out)))
+
+    def gather_device(self, root_slot, y_all=0, t_all=0, istate_all=0, rout_all=0, iout_all=0):
+        vp = lambda x: C.c_void_p(x) if x else None
+        _check(_lib.bvode_multi_gather_device(self._m, int(root_slot), vp(y_all), vp(t_all),
+                                              vp(istate_all), vp(rout_all), vp(iout_all)))
+
+    def close(self):
+        if self._m is not None:
+            _lib.bvode_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

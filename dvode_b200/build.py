@@ -45,8 +45,10 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nv = _nvcc()
     fast_extra = os.environ.get("BVODE_EXTRA_NVCC", "").split()
-    units = [("capi.o", "bvode_capi.cu", [])]
-    for u in range(7):  # one translation unit per problem and build, compiled in parallel
+    units = [("capi.o", "bvode_capi.cu", []), ("multi.o", "bvode_multi.cu", [])]
+    units.append(("lutest_fast.o", "bvode_lutest.cu", ["-DBVODE_STRICT=0"] + fast_extra))
+    units.append(("lutest_strict.o", "bvode_lutest.cu", ["-DBVODE_STRICT=1", "-fmad=false"]))
+    for u in range(8):  # one translation unit per problem and build, compiled in parallel
         units.append(("reg_fast_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=0", "-DBVODE_UNIT=%d" % u] + fast_extra))
         units.append(("reg_strict_%d.o" % u, "bvode_registry.cu", ["-DBVODE_STRICT=1", "-fmad=false", "-DBVODE_UNIT=%d" % u]))
     procs = []
@@ -60,7 +62,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nv] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units]
+    cmd = [nv] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units] + ["-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

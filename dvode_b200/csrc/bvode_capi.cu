@@ -14,7 +14,7 @@
 
 // one entry per (build, problem), each from its own translation unit (bvode_registry.cu)
 #include <mutex>
-#define BVODE_NPROBLEMS 7
+#define BVODE_NPROBLEMS 8
 extern "C" {
 const ProblemEntry *bvode_entry_fast_0(void);
 const ProblemEntry *bvode_entry_fast_1(void);
@@ -23,6 +23,7 @@ const ProblemEntry *bvode_entry_fast_3(void);
 const ProblemEntry *bvode_entry_fast_4(void);
 const ProblemEntry *bvode_entry_fast_5(void);
 const ProblemEntry *bvode_entry_fast_6(void);
+const ProblemEntry *bvode_entry_fast_7(void);
 const ProblemEntry *bvode_entry_strict_0(void);
 const ProblemEntry *bvode_entry_strict_1(void);
 const ProblemEntry *bvode_entry_strict_2(void);
@@ -30,6 +31,7 @@ const ProblemEntry *bvode_entry_strict_3(void);
 const ProblemEntry *bvode_entry_strict_4(void);
 const ProblemEntry *bvode_entry_strict_5(void);
 const ProblemEntry *bvode_entry_strict_6(void);
+const ProblemEntry *bvode_entry_strict_7(void);
 }
 // The problem table: the built-in problems, then whatever bvode_register_problem appended (user
 // f / jac functors compiled into a library of their own against csrc/bvode_user_problem.cuh).
@@ -44,11 +46,11 @@ static void registry_init() {
     g_tab_fast[0] = *bvode_entry_fast_0(); g_tab_fast[1] = *bvode_entry_fast_1();
     g_tab_fast[2] = *bvode_entry_fast_2(); g_tab_fast[3] = *bvode_entry_fast_3();
     g_tab_fast[4] = *bvode_entry_fast_4(); g_tab_fast[5] = *bvode_entry_fast_5();
-    g_tab_fast[6] = *bvode_entry_fast_6();
+    g_tab_fast[6] = *bvode_entry_fast_6(); g_tab_fast[7] = *bvode_entry_fast_7();
     g_tab_strict[0] = *bvode_entry_strict_0(); g_tab_strict[1] = *bvode_entry_strict_1();
     g_tab_strict[2] = *bvode_entry_strict_2(); g_tab_strict[3] = *bvode_entry_strict_3();
     g_tab_strict[4] = *bvode_entry_strict_4(); g_tab_strict[5] = *bvode_entry_strict_5();
-    g_tab_strict[6] = *bvode_entry_strict_6();
+    g_tab_strict[6] = *bvode_entry_strict_6(); g_tab_strict[7] = *bvode_entry_strict_7();
     g_nproblems = BVODE_NPROBLEMS;
 }
 static const ProblemEntry *bvode_registry_fast(int *n) {
@@ -64,6 +66,7 @@ static const ProblemEntry *bvode_registry_strict(int *n) {
 
 static thread_local std::string g_err;
 const char *bvode_last_error(void) { return g_err.c_str(); }
+void bvode_set_error(const std::string &msg) { g_err = msg; }  // for bvode_multi.cu
 
 #define CUDA_TRY(expr)                                                                     \
     do {                                                                                   \
@@ -74,30 +77,7 @@ const char *bvode_last_error(void) { return g_err.c_str(); }
         }                                                                                  \
     } while (0)
 
-struct bvode_solver {
-    int problem = 0, nsys = 0, device = 0, neq = 0, npar = 0;
-    unsigned flags = 0;
-    const ProblemEntry *pe = nullptr;
-    cudaStream_t stream = nullptr;
-    // state (allocated at the first istate = 1 call, when mf / ml / mu are known)
-    int mf = 0, ml = 0, mu = 0;
-    int maxord = 0;  // of the last call (istate = 3 may change it)
-    int mxstep = 500;
-    size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
-    double *d_state = nullptr;
-    int *i_state = nullptr;
-    // batch buffers, SoA on the device
-    double *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
-           *d_rout = nullptr, *d_aos = nullptr, *d_yout = nullptr, *d_tout_ps = nullptr;
-    int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
-    int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels); one per stream
-    cudaStream_t stream2 = nullptr;  // second stream of the pipelined host-buffer path
-    double *d_yout_aos = nullptr;    // [nout][nsys][neq] staging of the output points in host layout
-    size_t yout_aos_cap = 0;
-    size_t aos_cap = 0, yout_cap = 0;
-    bool params_external = false;
-    int last_launches = 0;
-};
+#include "bvode_handle.h"
 
 // ---------------------------------------------------------------- small kernels ----
 // host layout [nsys][n]  <->  device layout [n][nsys]
@@ -130,6 +110,13 @@ __global__ void k_soa_to_aos_range(const double *__restrict__ soa, double *__res
     const double *src = soa + v * (size_t)n * nsys;
     double *dst = aos + v * (size_t)n * nsys;
     for (int i = 0; i < n; i++) dst[g * n + i] = src[(size_t)i * nsys + g];
+}
+__global__ void k_isoa_to_aos_range(const int *__restrict__ soa, int *__restrict__ aos, int nsys,
+                                    int n, int s0, int count) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const size_t g = (size_t)s0 + s;
+    for (int i = 0; i < n; i++) aos[g * n + i] = soa[(size_t)i * nsys + g];
 }
 __global__ void k_isoa_to_aos(const int *__restrict__ soa, int *__restrict__ aos, int nsys,
                               int n) {
@@ -241,6 +228,10 @@ int bvode_create(bvode_solver **out, int problem, int nsys, int device, unsigned
     if (err == cudaSuccess) err = cudaMemsetAsync(s->d_rout, 0, sizeof(double) * 4 * ns, s->stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(s->d_iout, 0, sizeof(int) * 12 * ns, s->stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(s->d_params, 0, sizeof(double) * ns * (s->npar > 0 ? s->npar : 1), s->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_istate, 0, sizeof(int) * ns, s->stream);
+    // the handle's stream does not synchronise with the caller's streams (cudaStreamNonBlocking):
+    // the buffers must be ready before a first launch on any of them
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
     if (err != cudaSuccess) {
         g_err = std::string("bvode_create: ") + cudaGetErrorString(err);
         bvode_destroy(s);
@@ -259,6 +250,11 @@ void bvode_destroy(bvode_solver *s) {
     cudaFree(s->d_y); cudaFree(s->d_t); cudaFree(s->d_tol); cudaFree(s->d_rout);
     cudaFree(s->d_aos); cudaFree(s->d_yout); cudaFree(s->d_tout_ps); cudaFree(s->d_istate);
     cudaFree(s->d_iout); cudaFree(s->d_iaos); cudaFree(s->d_next); cudaFree(s->d_yout_aos);
+    cudaFree(s->d_tol_ps); cudaFree(s->d_optd_ps); cudaFree(s->d_opti_ps); cudaFree(s->d_rout_aos);
+    cudaFree(s->d_pack);
+    if (s->h_rout) cudaFreeHost(s->h_rout);
+    if (s->h_iout) cudaFreeHost(s->h_iout);
+    for (cudaEvent_t ev : s->chunk_done) cudaEventDestroy(ev);
     if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -308,6 +304,39 @@ static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, 
     *leniw = (miter == 0 || miter == 3) ? 30 : 30 + neq;
 }
 
+// The optional inputs of one solver instance (M:729-751), defaulted as in M:1174-1238: rw / iw are that
+// instance's rwork(1:20) / iwork(1:30) header.  Returns nullptr, or the text of the input error.
+static const char *read_optional_inputs(int meth, int itask, int iopt, const double *rw, const int *iw, BvOpts *o) {
+    const int mord = (meth == 1) ? 12 : 5;
+    o->tcrit = ((itask == 4 || itask == 5) && rw) ? rw[0] : 0.0;
+    if (iopt == 1) {
+        o->maxord = iw[4];
+        if (o->maxord < 0) return "maxord < 0";
+        if (o->maxord == 0) o->maxord = 100;
+        if (o->maxord > mord) o->maxord = mord;
+        o->mxstep = iw[5];
+        if (o->mxstep < 0) return "mxstep < 0";
+        if (o->mxstep == 0) o->mxstep = 500;
+        o->mxhnil = iw[6];
+        if (o->mxhnil < 0) return "mxhnil < 0";
+        if (o->mxhnil == 0) o->mxhnil = 10;
+        o->h0 = rw[4];
+        const double hmax = rw[5];
+        if (hmax < 0.0) return "hmax < 0";
+        o->hmax_inv = hmax > 0.0 ? 1.0 / hmax : 0.0;
+        o->hmin = rw[6];
+        if (o->hmin < 0.0) return "hmin < 0";
+    } else {
+        o->maxord = mord;
+        o->mxstep = 500;
+        o->mxhnil = 10;
+        o->h0 = 0.0;
+        o->hmax_inv = 0.0;
+        o->hmin = 0.0;
+    }
+    return nullptr;
+}
+
 // Returns BVODE_OK, or the error class; mirrors M:1092-1303 for the batch-uniform inputs.
 static int check_args(const bvode_solver *s, int neq, int itol, const double *rtol,
                       const double *atol, int itask, int iopt, const double *rwork0,
@@ -339,35 +368,9 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
     o.ml = ml;
     o.mu = mu;
     o.itask = itask;
-    o.tcrit = (itask == 4 || itask == 5) ? rwork0[0] : 0.0;
     o.jreset = 0;
-    const int mord = (meth == 1) ? 12 : 5;
-    if (iopt == 1) {
-        if (!rwork0 || !iwork0) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
-        o.maxord = iwork0[4];
-        if (o.maxord < 0) { g_err = "maxord < 0"; return BVODE_EINVAL; }
-        if (o.maxord == 0) o.maxord = 100;
-        if (o.maxord > mord) o.maxord = mord;
-        o.mxstep = iwork0[5];
-        if (o.mxstep < 0) { g_err = "mxstep < 0"; return BVODE_EINVAL; }
-        if (o.mxstep == 0) o.mxstep = 500;
-        o.mxhnil = iwork0[6];
-        if (o.mxhnil < 0) { g_err = "mxhnil < 0"; return BVODE_EINVAL; }
-        if (o.mxhnil == 0) o.mxhnil = 10;
-        o.h0 = rwork0[4];
-        const double hmax = rwork0[5];
-        if (hmax < 0.0) { g_err = "hmax < 0"; return BVODE_EINVAL; }
-        o.hmax_inv = hmax > 0.0 ? 1.0 / hmax : 0.0;
-        o.hmin = rwork0[6];
-        if (o.hmin < 0.0) { g_err = "hmin < 0"; return BVODE_EINVAL; }
-    } else {
-        o.maxord = mord;
-        o.mxstep = 500;
-        o.mxhnil = 10;
-        o.h0 = 0.0;
-        o.hmax_inv = 0.0;
-        o.hmin = 0.0;
-    }
+    if (iopt == 1 && (!rwork0 || !iwork0)) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
+    if (const char *msg = read_optional_inputs(meth, itask, iopt, rwork0, iwork0, &o)) { g_err = msg; return BVODE_EINVAL; }
     c->tol.resize(2 * (size_t)neq);
     for (int i = 0; i < neq; i++) {
         const double r = (itol >= 3) ? rtol[i] : rtol[0];
@@ -378,6 +381,59 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
         c->tol[neq + i] = a;
     }
     work_sizes(neq, mf, ml, mu, o.maxord, &c->lenrw, &c->leniw);
+    return BVODE_OK;
+}
+
+// BVODE_FLAG_PER_SYSTEM: every system is its own solver instance as far as rtol / atol and the optional
+// inputs go, as in the reference (M:729-751, 928-965): rtol[nsys][nr], atol[nsys][na] with nr, na = 1 or
+// neq according to itol, and the optional inputs of system i in row i of rwork / iwork.  A system whose
+// row is illegal gets istate = -3 and is skipped (M:1120-1303 does that per instance); with a
+// device-resident istate the call is refused instead.  mf, ml / mu, itol, itask, iopt stay batch-uniform.
+static int prepare_per_system(bvode_solver *s, const Checked &c, int neq, int itol, const double *rtol,
+                              const double *atol, int itask, int iopt, const double *rwork, int lrw,
+                              const int *iwork, int liw, int *istate_host, bool restart3, int mf,
+                              cudaStream_t st) {
+    const size_t ns = (size_t)s->nsys;
+    if (iopt == 1 && (!rwork || !iwork || lrw < 20 || liw < 30)) { g_err = "iopt = 1 needs rwork[nsys][lrw >= 20] and iwork[nsys][liw >= 30]"; return BVODE_EINVAL; }
+    if ((itask == 4 || itask == 5) && (!rwork || lrw < 1)) { g_err = "itask 4/5 needs rwork(1) = tcrit in every row"; return BVODE_EINVAL; }
+    if (!s->d_tol_ps) {
+        CUDA_TRY(cudaMalloc(&s->d_tol_ps, sizeof(double) * 2 * neq * ns));
+        CUDA_TRY(cudaMalloc(&s->d_optd_ps, sizeof(double) * 4 * ns));
+        CUDA_TRY(cudaMalloc(&s->d_opti_ps, sizeof(int) * 3 * ns));
+    }
+    const int nr = (itol >= 3) ? neq : 1, na = (itol == 2 || itol == 4) ? neq : 1;
+    const int meth = abs(mf) / 10;
+    std::vector<double> tol(2 * (size_t)neq * ns), od(4 * ns);
+    std::vector<int> oi(3 * ns);
+    const bool have_prev = s->maxord_ps.size() == ns;
+    std::vector<int> maxord_new(ns);
+    for (size_t i = 0; i < ns; i++) {
+        bool bad = false;
+        for (int k = 0; k < neq; k++) {
+            const double r = rtol[i * nr + (nr > 1 ? k : 0)], a = atol[i * na + (na > 1 ? k : 0)];
+            if (!(r >= 0.0) || !(a >= 0.0)) bad = true;
+            tol[(size_t)k * ns + i] = r;
+            tol[(size_t)(neq + k) * ns + i] = a;
+        }
+        BvOpts o = c.o;
+        if (read_optional_inputs(meth, itask, iopt, rwork ? rwork + i * (size_t)lrw : nullptr,
+                                 iwork ? iwork + i * (size_t)liw : nullptr, &o))
+            bad = true;
+        if (bad) {
+            if (!istate_host) { g_err = "per-system rtol / atol / optional inputs: an illegal row (and istate is on the device)"; return BVODE_EINVAL; }
+            istate_host[i] = -3;
+        }
+        od[i] = o.h0; od[ns + i] = o.hmax_inv; od[2 * ns + i] = o.hmin; od[3 * ns + i] = o.tcrit;
+        const int prev = have_prev ? s->maxord_ps[i] : s->maxord;
+        oi[i] = o.maxord; oi[ns + i] = o.mxstep;
+        oi[2 * ns + i] = (c.o.jreset || (restart3 && mf > 0 && o.maxord != prev)) ? 1 : 0;
+        maxord_new[i] = o.maxord;
+    }
+    s->maxord_ps.swap(maxord_new);
+    CUDA_TRY(cudaMemcpyAsync(s->d_tol_ps, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_optd_ps, od.data(), sizeof(double) * od.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_opti_ps, oi.data(), sizeof(int) * oi.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // the vectors go out of scope
     return BVODE_OK;
 }
 
@@ -411,6 +467,9 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
     }
     int rc = ensure_state(s, mf, c.o.ml, c.o.mu);
     if (rc) return rc;
+    s->last_y = d_y;
+    s->last_t = d_t;
+    s->last_istate = d_istate;
     if (upload_tol)
         CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
                                  cudaMemcpyHostToDevice, st));
@@ -442,7 +501,13 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
         a.lenrw = c.lenrw;
         a.leniw = c.leniw;
         a.general = general ? 1 : 0;
-        if (s->pe->mode == 0 && (s->flags & BVODE_FLAG_COMPACT)) {
+        if (s->flags & BVODE_FLAG_PER_SYSTEM) {  // read by the full-driver kernels
+            a.tol_ps = s->d_tol_ps;
+            a.optd_ps = s->d_optd_ps;
+            a.opti_ps = s->d_opti_ps;
+            a.general = 1;
+        }
+        if (s->pe->mode == 0 && (s->flags & BVODE_FLAG_COMPACT) && !a.general) {
             if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, 2 * sizeof(int)));
             CUDA_TRY(cudaMemsetAsync(s->d_next + lane, 0, sizeof(int), st));
             a.next_sys = s->d_next + lane;
@@ -458,7 +523,7 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
 static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
                       const double *touts, const double *tout_ps, int itol, const double *rtol,
                       const double *atol, int itask, int *istate, int iopt, double *rwork,
-                      int lrw, int *iwork, int liw, int mf, double *y_out) {
+                      int lrw, int *iwork, int liw, int mf, double *y_out, long long yout_sys_stride = 0) {
     if (!s || !y || !t || !istate || nout < 1 || (!touts && !tout_ps)) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const int nsys = s->nsys;
@@ -498,7 +563,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
             return BVODE_ENOTIMPL;
         }
     }
-    if (n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
+    if (!(s->flags & BVODE_FLAG_PER_SYSTEM) && n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
     if (mf_changed) {
         // M:999-1046 at istate = 3: a new miter / jsv.  The state moves into the layout of the new
         // method flag; the Newton matrix and the saved Jacobian are rebuilt at the restart.
@@ -561,7 +626,19 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     rc = ensure_state(s, mf, c.o.ml, c.o.mu);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(), cudaMemcpyHostToDevice, st));
+    if (s->flags & BVODE_FLAG_PER_SYSTEM) {
+        rc = prepare_per_system(s, c, neq, itol, rtol, atol, itask, iopt, rwork, lrw, iwork, liw, istate, n3 != 0, mf, st);
+        if (rc) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
+    // optional outputs (M:1670-1723) travel with their chunk: SoA -> [nsys][4] / [nsys][12] on the device,
+    // one copy into pinned staging, and the host scatters a chunk's rows into the caller's rwork / iwork
+    // headers while the GPU works on the next chunks
+    if (have_headers) {
+        if (!s->d_rout_aos) CUDA_TRY(cudaMalloc(&s->d_rout_aos, sizeof(double) * 4 * ns));
+        if (!s->h_rout) CUDA_TRY(cudaMallocHost(&s->h_rout, sizeof(double) * 4 * ns));
+        if (!s->h_iout) CUDA_TRY(cudaMallocHost(&s->h_iout, sizeof(int) * 12 * ns));
+    }
     // The batch goes through in chunks on two streams: the copies of one chunk (inputs in, every
     // output point out) run under the kernels of its neighbours, and a chunk's kernel fills the
     // SMs the previous one's tail leaves idle.  One chunk for small batches.
@@ -599,30 +676,48 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
                                  cudaMemcpyDeviceToHost, cs));
         CUDA_TRY(cudaMemcpyAsync(t + s0, s->d_t + s0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, cs));
         CUDA_TRY(cudaMemcpyAsync(istate + s0, s->d_istate + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, cs));
+        if (have_headers) {
+            k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), 1), TB, 0, cs>>>(s->d_rout, s->d_rout_aos, nsys, 4, s0, cnt);
+            k_isoa_to_aos_range<<<cdiv(cnt, TB), TB, 0, cs>>>(s->d_iout, s->d_iaos, nsys, 12, s0, cnt);
+            s->last_launches += 2;
+            CUDA_TRY(cudaMemcpyAsync(s->h_rout + (size_t)s0 * 4, s->d_rout_aos + (size_t)s0 * 4, sizeof(double) * 4 * cnt,
+                                     cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaMemcpyAsync(s->h_iout + (size_t)s0 * 12, s->d_iaos + (size_t)s0 * 12, sizeof(int) * 12 * cnt,
+                                     cudaMemcpyDeviceToHost, cs));
+        }
         if (y_out) {
             k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), nout), TB, 0, cs>>>(d_yout, s->d_yout_aos, nsys, neq, s0, cnt);
             s->last_launches++;
+            const size_t hs = yout_sys_stride > 0 ? (size_t)yout_sys_stride : ns;  // systems per output slab of y_out
             for (int k = 0; k < nout; k++) {
-                const size_t off = ((size_t)k * ns + s0) * neq;
-                CUDA_TRY(cudaMemcpyAsync(y_out + off, s->d_yout_aos + off, sizeof(double) * cnt * neq,
+                const size_t off = ((size_t)k * ns + s0) * neq, hoff = ((size_t)k * hs + s0) * neq;
+                CUDA_TRY(cudaMemcpyAsync(y_out + hoff, s->d_yout_aos + off, sizeof(double) * cnt * neq,
                                          cudaMemcpyDeviceToHost, cs));
             }
+        }
+        if (have_headers) {
+            while ((int)s->chunk_done.size() <= ch) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                s->chunk_done.push_back(ev);
+            }
+            CUDA_TRY(cudaEventRecord(s->chunk_done[ch], cs));
         }
     }
     s->maxord = c.o.maxord;
     s->mxstep = c.o.mxstep;
-    if (s->stream2) CUDA_TRY(cudaStreamSynchronize(s->stream2));
-    CUDA_TRY(cudaStreamSynchronize(st));
     if (have_headers) {
-        std::vector<double> ro(4 * ns);
-        std::vector<int> io(12 * ns);
-        CUDA_TRY(cudaMemcpy(ro.data(), s->d_rout, sizeof(double) * 4 * ns, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(io.data(), s->d_iout, sizeof(int) * 12 * ns, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < ns; i++) {
-            for (int k = 0; k < 4; k++) rwork[i * lrw + 10 + k] = ro[(size_t)k * ns + i];
-            for (int k = 0; k < 12; k++) iwork[i * liw + 10 + k] = io[(size_t)k * ns + i];
+        for (int ch = 0; ch < nchunks; ch++) {
+            const size_t s0 = (size_t)((long long)nsys * ch / nchunks), s1 = (size_t)((long long)nsys * (ch + 1) / nchunks);
+            CUDA_TRY(cudaEventSynchronize(s->chunk_done[ch]));
+            for (size_t i = s0; i < s1; i++) {
+                memcpy(rwork + i * lrw + 10, s->h_rout + i * 4, sizeof(double) * 4);
+                memcpy(iwork + i * liw + 10, s->h_iout + i * 12, sizeof(int) * 12);
+            }
         }
     }
+    if (s->stream2) CUDA_TRY(cudaStreamSynchronize(s->stream2));
+    CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     return BVODE_OK;
 }
@@ -644,6 +739,46 @@ int bvode_solve_schedule(bvode_solver *s, int neq, double *y, double *t, int nou
                       rwork, lrw, iwork, liw, mf, y_out);
 }
 
+// Device-resident entry points: istate lives in HBM, so the continuation checks of M:1102-1106 cannot be
+// made per system here.  A handle whose state exists is therefore bound to its mf / ml / mu: a call
+// with other values would silently re-initialise systems that continue with istate = 2, and is refused
+// (bvode_reset drops the state when a new problem is meant).
+static int device_path_prepare(bvode_solver *s, const Checked &c, int neq, int itol, const double *rtol,
+                               const double *atol, int itask, int iopt, const double *rwork_opts,
+                               const int *iwork_opts, int mf, cudaStream_t st) {
+    if (s->d_state && (s->mf != mf || s->ml != c.o.ml || s->mu != c.o.mu)) {
+        g_err = "device-resident solve with another mf / ml / mu than the handle's state was built for "
+                "(call bvode_reset first, or use the host-buffer entry points for an istate = 3 change)";
+        return BVODE_EINVAL;
+    }
+    if (s->flags & BVODE_FLAG_PER_SYSTEM)
+        return prepare_per_system(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, 20, iwork_opts, 30,
+                                  nullptr, false, mf, st ? st : s->stream);
+    return BVODE_OK;
+}
+
+int bvode_reset(bvode_solver *s) {
+    if (!s) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(s->d_state);
+    cudaFree(s->i_state);
+    s->d_state = nullptr;
+    s->i_state = nullptr;
+    s->nd = s->ni = 0;
+    s->mf = s->ml = s->mu = s->maxord = 0;
+    s->maxord_ps.clear();
+    return BVODE_OK;
+}
+
+int bvode_solve_schedule_strided(bvode_solver *s, int neq, double *y, double *t, int nout, const double *touts,
+                                 const double *tout_ps, int itol, const double *rtol, const double *atol, int itask,
+                                 int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw, int mf,
+                                 double *y_out, long long yout_sys_stride) {
+    return solve_host(s, neq, y, t, nout, touts, tout_ps, itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork,
+                      liw, mf, y_out, yout_sys_stride);
+}
+
 int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, double *t_device,
                                 int nout, const double *touts, int itol, const double *rtol,
                                 const double *atol, int itask, int *istate_device, int iopt,
@@ -658,10 +793,13 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, doub
     if (rc != BVODE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;  // 0 = the legacy default stream, as documented
     // (device-resident istate: istate = 3 is only accepted through the host-buffer entry points)
+    rc = device_path_prepare(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, mf, st);
+    if (rc != BVODE_OK) return rc;
     rc = run_device(s, c, mf, y_device, t_device, istate_device, nout, touts, nullptr,
                     y_out_device, st, itask != 1);
     if (rc != BVODE_OK) return rc;
     s->maxord = c.o.maxord;
+    s->mxstep = c.o.mxstep;
     CUDA_TRY(cudaGetLastError());
     return BVODE_OK;
 }
@@ -678,10 +816,13 @@ int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_dev
                         false, mf, &c);
     if (rc != BVODE_OK) return rc;
     const double tout1 = 0.0;  // unused: every system has its own tout
+    rc = device_path_prepare(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, mf, (cudaStream_t)stream);
+    if (rc != BVODE_OK) return rc;
     rc = run_device(s, c, mf, y_device, t_device, istate_device, 1, &tout1, tout_device, nullptr,
                     (cudaStream_t)stream, itask != 1);
     if (rc != BVODE_OK) return rc;
     s->maxord = c.o.maxord;
+    s->mxstep = c.o.mxstep;
     CUDA_TRY(cudaGetLastError());
     return BVODE_OK;
 }
@@ -749,45 +890,67 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
 }
 
 // ---- dvsrco (M:3198-3216): the whole batch state as one host blob ------------------
+// header, then: real state, integer state, optional outputs (rwork(11:14), iwork(11:22)), and the
+// handle's own copy of istate / t / y of the last host-buffer call -- everything a fresh handle needs
+// to continue with istate = 2 (or 3) and to answer bvode_istate_summary / bvode_format_message.
 struct SavHeader {
-    int magic, problem, nsys, mf, ml, mu;
+    int magic, problem, nsys, mf, ml, mu, maxord, mxstep, neq, reserved;
     unsigned long long nd, ni;
 };
+static const int kSavMagic = 0x62766f65;  // "bvoe": layout 2 (layout 1 had no istate / t / y / maxord / mxstep)
+static size_t sav_bytes(const bvode_solver *s, size_t nd, size_t ni) {
+    const size_t ns = (size_t)s->nsys;
+    return sizeof(SavHeader) + sizeof(double) * nd + sizeof(int) * ni + sizeof(double) * 4 * ns +
+           sizeof(int) * 12 * ns + sizeof(int) * ns + sizeof(double) * ns + sizeof(double) * ns * s->neq;
+}
 long long bvode_state_bytes(const bvode_solver *s) {
     if (!s || !s->d_state) return 0;
-    return (long long)(sizeof(SavHeader) + sizeof(double) * s->nd + sizeof(int) * s->ni +
-                       sizeof(double) * 4 * s->nsys + sizeof(int) * 12 * s->nsys);
+    return (long long)sav_bytes(s, s->nd, s->ni);
 }
-int bvode_dvsrco(bvode_solver *s, void *sav, int job) {
+int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job) {
     if (!s || !sav || (job != 1 && job != 2)) return BVODE_EINVAL;  // M:3212-3213 `error stop`
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->stream2) CUDA_TRY(cudaStreamSynchronize(s->stream2));
     char *p = (char *)sav;
     if (job == 1) {
-        if (!s->d_state) return BVODE_EINVAL;
-        SavHeader h{0x62766f64, s->problem, s->nsys, s->mf, s->ml, s->mu,
+        if (!s->d_state) { g_err = "dvsrco(job = 1) before any successful solve"; return BVODE_EINVAL; }
+        if (nbytes >= 0 && (size_t)nbytes < sav_bytes(s, s->nd, s->ni)) { g_err = "dvsrco: buffer shorter than bvode_state_bytes()"; return BVODE_EINVAL; }
+        SavHeader h{kSavMagic, s->problem, s->nsys, s->mf, s->ml, s->mu, s->maxord, s->mxstep, s->neq, 0,
                     (unsigned long long)s->nd, (unsigned long long)s->ni};
         memcpy(p, &h, sizeof(h));
     } else {
+        if (nbytes >= 0 && (size_t)nbytes < sizeof(SavHeader)) { g_err = "dvsrco: buffer shorter than its header"; return BVODE_EINVAL; }
         SavHeader h;
         memcpy(&h, p, sizeof(h));
-        if (h.magic != 0x62766f64 || h.problem != s->problem || h.nsys != s->nsys) return BVODE_EINVAL;
+        if (h.magic != kSavMagic || h.problem != s->problem || h.nsys != s->nsys || h.neq != s->neq) {
+            g_err = "dvsrco(job = 2): the buffer was not saved from a handle of this problem and batch size";
+            return BVODE_EINVAL;
+        }
+        size_t nd = 0, ni = 0;
+        if (!s->pe->supports(h.mf, h.ml, h.mu)) return BVODE_EINVAL;
+        s->pe->state_size(h.mf, h.ml, h.mu, (size_t)s->nsys, &nd, &ni);
+        if (h.nd != nd || h.ni != ni) { g_err = "dvsrco(job = 2): state sizes in the buffer do not match this build"; return BVODE_EINVAL; }
+        if (nbytes >= 0 && (size_t)nbytes < sav_bytes(s, nd, ni)) { g_err = "dvsrco(job = 2): buffer shorter than the state it describes"; return BVODE_EINVAL; }
         int rc = ensure_state(s, h.mf, h.ml, h.mu);
         if (rc) return rc;
-        if (h.nd != s->nd || h.ni != s->ni) return BVODE_EINVAL;
+        s->maxord = h.maxord;
+        s->mxstep = h.mxstep;
     }
     p += sizeof(SavHeader);
-    const cudaMemcpyKind kind = (job == 1) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
-    struct { void *d; size_t n; } parts[4] = {
+    const size_t ns = (size_t)s->nsys;
+    struct { void *d; size_t n; } parts[7] = {
         {s->d_state, sizeof(double) * s->nd}, {s->i_state, sizeof(int) * s->ni},
-        {s->d_rout, sizeof(double) * 4 * s->nsys}, {s->d_iout, sizeof(int) * 12 * s->nsys}};
+        {s->d_rout, sizeof(double) * 4 * ns}, {s->d_iout, sizeof(int) * 12 * ns},
+        {s->d_istate, sizeof(int) * ns}, {s->d_t, sizeof(double) * ns}, {s->d_y, sizeof(double) * ns * s->neq}};
     for (auto &q : parts) {
-        if (job == 1) CUDA_TRY(cudaMemcpy(p, q.d, q.n, kind));
-        else CUDA_TRY(cudaMemcpy(q.d, p, q.n, kind));
+        if (job == 1) CUDA_TRY(cudaMemcpy(p, q.d, q.n, cudaMemcpyDeviceToHost));
+        else CUDA_TRY(cudaMemcpy(q.d, p, q.n, cudaMemcpyHostToDevice));
         p += q.n;
     }
     return BVODE_OK;
 }
+int bvode_dvsrco(bvode_solver *s, void *sav, int job) { return bvode_dvsrco_n(s, sav, -1, job); }
 
 // ---- xerrwd (M:3351-3394) as a host-side message stream --------------------------------
 // The kernels never print.  The reference's messages for the per-system outcomes are rebuilt
@@ -875,6 +1038,43 @@ int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen) {
     }
     snprintf(buf, (size_t)buflen, "%s", m.c_str());
     return (int)m.size();
+}
+
+// ---- the device LINPACK routines in isolation (csrc/bvode_lutest.cu) ----------------------------
+extern "C" int bvode_lutest_fast(int, int, int, int, int, const double *, const double *, double *, int *, double *, int *);
+extern "C" int bvode_lutest_strict(int, int, int, int, int, const double *, const double *, double *, int *, double *, int *);
+int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const double *a, const double *b, double *afac,
+                  int *ipvt, double *x, int *info, int device, unsigned flags) {
+    if (!a || !b || !afac || !ipvt || !x || !info || nmat < 1 || n < 1) return BVODE_EINVAL;
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t na = (size_t)nmat * (kind == 3 ? (size_t)(2 * ml + mu + 1) * n : (size_t)n * n), nb = (size_t)nmat * n;
+    double *da = nullptr, *db = nullptr, *df = nullptr, *dx = nullptr;
+    int *dp = nullptr, *di = nullptr;
+    cudaError_t e = cudaMalloc(&da, sizeof(double) * na);
+    if (e == cudaSuccess) e = cudaMalloc(&df, sizeof(double) * na);
+    if (e == cudaSuccess) e = cudaMalloc(&db, sizeof(double) * nb);
+    if (e == cudaSuccess) e = cudaMalloc(&dx, sizeof(double) * nb);
+    if (e == cudaSuccess) e = cudaMalloc(&dp, sizeof(int) * nb);
+    if (e == cudaSuccess) e = cudaMalloc(&di, sizeof(int) * nmat);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, sizeof(double) * na, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, sizeof(double) * nb, cudaMemcpyHostToDevice);
+    int rc = BVODE_OK;
+    if (e == cudaSuccess) {
+        const int r = (flags & BVODE_FLAG_STRICT) ? bvode_lutest_strict(kind, n, ml, mu, nmat, da, db, df, dp, dx, di)
+                                                  : bvode_lutest_fast(kind, n, ml, mu, nmat, da, db, df, dp, dx, di);
+        if (r == -1000) { g_err = "bvode_lu_test: this kind / n is not instantiated"; rc = BVODE_ENOTIMPL; }
+        else if (r != 0) e = (cudaError_t)r;
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && rc == BVODE_OK) {
+        e = cudaMemcpy(afac, df, sizeof(double) * na, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(x, dx, sizeof(double) * nb, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(ipvt, dp, sizeof(int) * nb, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(info, di, sizeof(int) * nmat, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(da); cudaFree(db); cudaFree(df); cudaFree(dx); cudaFree(dp); cudaFree(di);
+    if (e != cudaSuccess) { g_err = std::string("bvode_lu_test: ") + cudaGetErrorString(e); return BVODE_ECUDA; }
+    return rc;
 }
 
 int bvode_measure_fp64_peak(int device, double *tflops) {

@@ -32,7 +32,14 @@ struct KArgs {
     double *t;                     // [nsys] in/out
     int *istate;                   // [nsys] in/out
     const double *rtol, *atol;     // [neq] each, already expanded according to itol
-    double rtolv[8], atolv[8];     // the same, by value, for thread-per-system kernels (neq <= 8)
+    double rtolv[8], atolv[8];     // the same, by value, for thread-per-system kernels with neq <= 8
+                                   // (larger thread problems read rtol / atol above)
+    // Per-system tolerances and optional inputs (BVODE_FLAG_PER_SYSTEM; the reference takes them per
+    // solver instance, M:729-751, 928-965).  nullptr = batch-uniform (rtol / atol / o above).  Read by
+    // the full-driver kernels only (general = 1).
+    const double *tol_ps;          // [2*neq][nsys]: rtol then atol, expanded according to itol
+    const double *optd_ps;         // [4][nsys]: h0, 1/hmax (0 = none), hmin, tcrit
+    const int *opti_ps;            // [3][nsys]: maxord, mxstep, jreset
     BvOpts o;
     double *y_out;                 // [nout][neq][nsys] or nullptr
     double *rout;                  // [4][nsys]  rwork(11:14)
@@ -72,4 +79,4 @@ struct ProblemEntry {
 
 // Tag a problem library passes to bvode_register_problem: it must have been compiled against
 // these very structs (bump the leading number when KArgs / DkyArgs / ProblemEntry change meaning).
-#define BVODE_PLUGIN_ABI ((int)(4 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))
+#define BVODE_PLUGIN_ABI ((int)(5 * 1000000 + (sizeof(KArgs) % 1000) * 1000 + sizeof(ProblemEntry) % 1000))

@@ -62,6 +62,18 @@ struct Storer {
     template <class T> BV_DEV void iv(T &x) { i(x); }
 };
 
+// Per-system optional inputs (BVODE_FLAG_PER_SYSTEM): what the reference reads from each solver
+// instance's rwork(1), rwork(5:7), iwork(5:6) (M:729-751, 1174-1238), defaulted on the host.
+BV_DEV void load_opts_ps(BvOpts &o, const KArgs &a, size_t ns, size_t sys) {
+    o.h0 = a.optd_ps[sys];
+    o.hmax_inv = a.optd_ps[ns + sys];
+    o.hmin = a.optd_ps[2 * ns + sys];
+    o.tcrit = a.optd_ps[3 * ns + sys];
+    o.maxord = a.opti_ps[sys];
+    o.mxstep = a.opti_ps[ns + sys];
+    o.jreset = a.opti_ps[2 * ns + sys];
+}
+
 // ------------------------------------------------------- thread-per-system ------
 #ifndef BVODE_THREAD_TPB
 #define BVODE_THREAD_TPB 32
@@ -87,8 +99,11 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     Engine<POL> e;
     e.hot.bind(smem_thread, threadIdx.x);
     e.o = a.o;
-    e.tol.r = a.rtolv;
-    e.tol.a = a.atolv;
+#pragma unroll
+    for (int i = 0; i < N; i++) {  // N <= 8: by-value kernel parameters; larger: the [neq] arrays in HBM
+        e.tol.rv[i] = (N <= 8) ? a.rtolv[i < 8 ? i : 0] : a.rtol[i];
+        e.tol.av[i] = (N <= 8) ? a.atolv[i < 8 ? i : 0] : a.atol[i];
+    }
 
     int sys = a.sys0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int sys_end = a.sys0 + a.count;  // this launch integrates systems [sys0, sys0 + count)
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
         a.iout[4 * ns + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
         a.iout[5 * ns + sys] =
             (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
-        a.iout[6 * ns + sys] = a.lenrw;
+        a.iout[6 * ns + sys] = a.lenrw + (GENERAL ? N * (e.o.maxord - a.o.maxord) : 0);  // M:1246: 20 + nyh*(maxord+1) + ...
         a.iout[7 * ns + sys] = a.leniw;
         a.iout[8 * ns + sys] = e.hot.si(SI_NLU);
         a.iout[9 * ns + sys] = e.hot.si(SI_NNI);
@@ -142,12 +157,32 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     // ---- the kernel prologue for system `sys`: 0 = nothing to do for it, 1 = first call, 2 = continuation
     auto load = [&]() -> int {
         const int ist = a.istate[sys];
-        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return 0;  // failed / illegal: left untouched
+        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) {  // failed / illegal: left untouched
+            // a schedule split over several launches (nout > BVODE_MAX_NOUT): a system that failed in an
+            // earlier launch keeps its last state in the output slots of this one as well
+            if (ist < 0 && a.y_out) {
+                for (int k2 = 0; k2 < a.nout; k2++) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * ns + sys] = a.y[(size_t)i * ns + sys];
+                }
+            }
+            return 0;
+        }
 #pragma unroll
         for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * ns + sys];
         const double t = a.t[sys];
         tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
         nemit = 0;
+        if constexpr (GENERAL) {  // per-system tolerances / optional inputs (M:729-751, 928-965)
+            if (a.tol_ps) {
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    e.tol.rv[i] = a.tol_ps[(size_t)i * ns + sys];
+                    e.tol.av[i] = a.tol_ps[(size_t)(N + i) * ns + sys];
+                }
+            }
+            if (a.optd_ps) load_opts_ps(e.o, a, ns, (size_t)sys);
+        }
         if (ist == 1) {
             if (tout0 == t) return 0;  // M:1101
 #pragma unroll
@@ -361,7 +396,36 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
     // ---- the kernel prologue: 0 = nothing to do for this system, 1 = first call, 2 = continuation
     auto load = [&]() -> int {
         const int ist = a.istate[sys];
-        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) return 0;
+        if (ist != 1 && ist != 2 && !(GENERAL && ist == 3)) {
+            if (ist < 0 && a.y_out) {  // failed in an earlier launch of a split schedule: see the thread kernel
+                for (int k2 = 0; k2 < a.nout; k2++) {
+#pragma unroll
+                    for (int i = 0; i < NL; i++)
+                        if (ln + 32 * i < N)
+                            a.y_out[((size_t)k2 * N + ln + 32 * i) * nsys + sys] = a.y[(size_t)(ln + 32 * i) * nsys + sys];
+                }
+            }
+            return 0;
+        }
+        if constexpr (GENERAL) {  // per-system tolerances / optional inputs (M:729-751, 928-965)
+            if (a.tol_ps) {
+                if constexpr (NL == 1) {
+                    if (ln < N) {
+                        e.tol.r = a.tol_ps[(size_t)ln * nsys + sys];
+                        e.tol.a = a.tol_ps[(size_t)(N + ln) * nsys + sys];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NL; i++) {
+                        if (ln + 32 * i < N) {
+                            e.tol.r[i] = a.tol_ps[(size_t)(ln + 32 * i) * nsys + sys];
+                            e.tol.a[i] = a.tol_ps[(size_t)(N + ln + 32 * i) * nsys + sys];
+                        }
+                    }
+                }
+            }
+            if (a.optd_ps) load_opts_ps(e.o, a, nsys, sys);
+        }
         Prob::load_par(e.par, a.params, nsys, sys, ln);
         const double t = a.t[sys];
         tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
@@ -428,7 +492,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             a.iout[3 * nsys + sys] = e.hot.si(SI_NQU);
             a.iout[4 * nsys + sys] = (ist == IST_OK) ? e.c.newq : e.c.nq;
             a.iout[5 * nsys + sys] = imx;
-            a.iout[6 * nsys + sys] = a.lenrw;
+            a.iout[6 * nsys + sys] = a.lenrw + (GENERAL ? N * (e.o.maxord - a.o.maxord) : 0);
             a.iout[7 * nsys + sys] = a.leniw;
             a.iout[8 * nsys + sys] = e.hot.si(SI_NLU);
             a.iout[9 * nsys + sys] = e.hot.si(SI_NNI);

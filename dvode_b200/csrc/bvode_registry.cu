@@ -1,6 +1,6 @@
 // bvode_registry.cu -- instantiates every kernel of ONE problem for one build and exports its
 // table entry.  Compiled once per (build, problem): -DBVODE_STRICT=0 (fast, the product) or
-// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..6.
+// -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..7.
 #include "bvode_kernels.cuh"
 
 #ifndef BVODE_UNIT
@@ -22,6 +22,8 @@ static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp_maxnorm", VanDerPol
 static const ProblemEntry kEntry = BVODE_WARP_BAND_PROBLEM("advection_maxnorm", Advection25MaxNorm);
 #elif BVODE_UNIT == 6
 static const ProblemEntry kEntry = BVODE_WARP2_DENSE_FD_PROBLEM("diffusion48", Diffusion48);
+#elif BVODE_UNIT == 7
+static const ProblemEntry kEntry = BVODE_THREAD_PROBLEM("vdp_ewtdrop", VanDerPolEwtDrop);
 #endif
 }  // namespace BVODE_NS
 

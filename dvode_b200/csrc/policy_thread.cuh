@@ -31,10 +31,13 @@ struct ThreadPolicy {
 
     typedef double Par[PROB::NPAR > 0 ? PROB::NPAR : 1];
     struct AcSav {};  // the acor copy the reference parks in yh(:,lmax) (M:2259, 2298) is hot.acs(i)
-    struct Tol {              // rtol / atol expanded to N entries, in the kernel parameter bank
-        const double *r, *a;
-        BV_DEV double rtol(int i) const { return r[i]; }
-        BV_DEV double atol(int i) const { return a[i]; }
+    // rtol / atol expanded to N entries.  Batch-uniform tolerances are copies of kernel parameters
+    // (the compiler reads them straight from the constant bank); per-system ones (KArgs::tol_ps,
+    // full-driver kernel only) are loaded with the system.
+    struct Tol {
+        double rv[N], av[N];
+        BV_DEV double rtol(int i) const { return rv[i]; }
+        BV_DEV double atol(int i) const { return av[i]; }
     };
 
     // Hot per-system data.  The Nordsieck array always lives in registers.  Everything that is

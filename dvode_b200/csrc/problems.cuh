@@ -69,6 +69,17 @@ struct VanDerPolMaxNorm : VanDerPol {
     }
 };
 
+// Van der Pol with a user dewset (M:431-467) whose first weight turns non-positive once |y_1| < 1/2
+// (builder-defined test problem, the oracle's problem 7): it drives the `ewt(i) <= 0` exit of the step
+// loop, istate = -6 (M:1516-1521), which the default weights reach only for a component that is exactly 0.
+struct VanDerPolEwtDrop : VanDerPol {
+    BV_DEV static double ewt(int i, double yi, double rtol, double atol) {
+        double e = rtol * fabs(yi) + atol;
+        if (i == 0 && fabs(yi) < 0.5) e = e - 1.0;
+        return e;
+    }
+};
+
 }  // namespace BVODE_NS
 
 // ----------------------------------------------------------------------------------------

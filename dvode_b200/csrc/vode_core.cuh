@@ -910,7 +910,7 @@ struct Engine {
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
         int nslast = 0;  // M:1399 (and 1337 on the first call)
-        const int lmax = o.maxord + 1;
+        int lmax = o.maxord + 1;  // per system when the optional inputs are (set again at hand-over)
         int istate = 1;  // 0 = keep stepping; every loop below has a single exit (see dvnlsd).
                          // Non-zero with have == false: nothing loaded yet.
         bool have = false, alive = true;
@@ -1012,6 +1012,7 @@ struct Engine {
             } else {
                 // ---- entry of the first call for the new system (block D on a continuation call)
                 const bool first = (got == 1);
+                if constexpr (GENERAL) lmax = o.maxord + 1;
                 have = true;
                 istate = 0;
                 kout = 0;

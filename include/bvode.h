@@ -13,13 +13,15 @@
  *   istate [nsys]        per-system state flag, same integer codes as M:832-908
  *   rwork  [nsys][lrw]   lrw >= 20: per-system copy of the reference's rwork(1:20) header.
  *                        Optional INPUTS rwork(1,5,6,7) are batch-uniform and are read from
- *                        system 0's row; optional OUTPUTS rwork(11:14) are written per system.
+ *                        system 0's row (from every row with BVODE_FLAG_PER_SYSTEM); optional
+ *                        OUTPUTS rwork(11:14) are written per system.
  *                        The reference's rwork(21:) (Nordsieck array, Newton matrix, ...) is
  *                        the device-resident state owned by the handle.
  *   iwork  [nsys][liw]   liw >= 30: same for iwork(1:30): inputs iwork(1,2,5,6,7) from row 0,
  *                        outputs iwork(11:22) per system.
  *   rtol, atol           scalars or arrays of length neq according to itol (M:663-668),
- *                        shared by all systems of the batch.
+ *                        shared by all systems of the batch; with BVODE_FLAG_PER_SYSTEM one such
+ *                        scalar / array PER SYSTEM: rtol[nsys][1 or neq], atol[nsys][1 or neq].
  * The user callbacks f / jac (M:316-334) cannot be host function pointers: they are
  * __device__ functors compiled into the library and selected by `problem` id.
  *
@@ -54,10 +56,17 @@ enum {
 /* flags for bvode_create */
 enum {
     BVODE_FLAG_STRICT = 1, /* run the -fmad=false / portable-pow build (bit-for-bit parity runs) */
-    BVODE_FLAG_COMPACT = 2 /* thread-per-system kernels, itask = 1: launch only as many threads as are
+    BVODE_FLAG_COMPACT = 2,/* thread-per-system kernels, itask = 1: launch only as many threads as are
                             * resident at once and give a thread whose system is finished the next
                             * unclaimed system of the batch (compaction of finished systems).  Results
                             * are identical; pays off when the systems differ widely in cost. */
+    BVODE_FLAG_PER_SYSTEM = 4
+                           /* every system is its own solver instance as far as tolerances and optional
+                            * inputs go, as in the reference (M:729-751, 928-965): rtol[nsys][1 or neq],
+                            * atol[nsys][1 or neq] (by itol), and the optional inputs rwork(1,5,6,7) /
+                            * iwork(5,6,7) are read from EVERY system's row.  A system whose row is illegal
+                            * gets istate = -3 and is left alone (M:1120-1303).  mf, ml / mu, itol, itask,
+                            * iopt stay batch-uniform.  Runs the full-driver kernels. */
 };
 
 /* ---- problem registry: stands in for the procedure arguments of initialize (M:377-505) ---- */
@@ -122,9 +131,17 @@ BVODE_API int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, i
 BVODE_API int bvode_get_stats(bvode_solver *s, double *rout, int *iout);
 
 /* dvsrco (M:3198-3216): save (job = 1) / restore (job = 2) the whole batch state to / from a
- * host buffer of bvode_state_bytes() bytes: checkpoint / resume. */
+ * host buffer of bvode_state_bytes() bytes: checkpoint / resume.  The blob carries the persistent
+ * state, the optional outputs, the handle's istate / t / y of the last host-buffer call and the
+ * optional inputs that persist between calls (maxord, mxstep).  bvode_dvsrco_n checks the buffer
+ * length `nbytes` against what it reads or writes; bvode_dvsrco trusts the caller (the reference's
+ * argument list has no length). */
 BVODE_API long long bvode_state_bytes(const bvode_solver *s);
+BVODE_API int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job);
 BVODE_API int bvode_dvsrco(bvode_solver *s, void *sav, int job);
+/* Drop the integration state of the handle (the next call must be a first call, istate = 1): needed
+ * before a device-resident solve with another mf / ml / mu on the same handle. */
+BVODE_API int bvode_reset(bvode_solver *s);
 
 /* ---- xerrwd (M:3351-3394) as a host-side message stream.  The kernels never print and never
  * stop; the per-system outcome is istate.  bvode_istate_summary compacts the batch: counts[0] =
@@ -152,6 +169,76 @@ BVODE_API int bvode_solve_device(bvode_solver *s, int neq, double *y_device, dou
                        const int *iwork_opts, int mf, void *stream);
 /* number of kernels the last solve call launched (bench.py's gpu_launches) */
 BVODE_API int bvode_last_launch_count(const bvode_solver *s);
+
+/* ---- multi-GPU: the batch shards by system index, each GPU integrates its block on its
+ * own, and the only exchange is a final gather of solutions and statistics to one GPU over NVLink (NCCL,
+ * loaded at run time).  No reference analogue: dvode is a serial code, one solver instance per thread.
+ *
+ * bvode_shard_range: rank r of `world` owns systems [first, last); block sizes differ by at most one.
+ *
+ * One process per GPU: rank 0 calls bvode_comm_unique_id, the 128 bytes travel to the other ranks by
+ * whatever the application has (MPI_Bcast, a file, torch.distributed), every rank calls
+ * bvode_comm_create; or bvode_comm_adopt wraps an ncclComm_t the application made itself.
+ *
+ * bvode_gather_device: after a solve, gather the final y / t / istate and the optional outputs of every
+ * rank's handle into arrays on the root's GPU, in system order and host layout: y_all[nsys_total][neq],
+ * t_all[nsys_total], istate_all[nsys_total], rout_all[nsys_total][4], iout_all[nsys_total][12] (device
+ * pointers on the root; on the other ranks any non-NULL value means "this array is wanted"; every rank must
+ * pass the same set).  Enqueued on `stream` (a cudaStream_t as void*, NULL = the handle's own); returns
+ * without waiting.  bvode_gather: the same with HOST arrays on the root, and it waits. */
+typedef struct bvode_comm bvode_comm;
+BVODE_API void bvode_shard_range(long long nsys_total, int rank, int world, long long *first, long long *last);
+BVODE_API int bvode_nccl_version(void);                       /* 0: NCCL could not be loaded */
+BVODE_API int bvode_comm_unique_id(char id[128]);
+BVODE_API int bvode_comm_create(bvode_comm **out, const char id[128], int world, int rank, int device);
+BVODE_API int bvode_comm_adopt(bvode_comm **out, void *nccl_comm, int world, int rank, int device);
+BVODE_API void bvode_comm_destroy(bvode_comm *c);
+BVODE_API int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys_total,
+                                  double *y_all_device, double *t_all_device, int *istate_all_device,
+                                  double *rout_all_device, int *iout_all_device, void *stream);
+BVODE_API int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, double *y_all,
+                           double *t_all, int *istate_all, double *rout_all, int *iout_all);
+
+/* One process, several GPUs -- what a Fortran / C program without MPI calls to use the whole box.  The
+ * batch of nsys_total systems is sharded over `ndev` devices (devices[ndev], NULL = 0..ndev-1); the solve
+ * calls take arrays of nsys_total rows with exactly the arguments of bvode_solve / bvode_solve_schedule
+ * and run every block on its own GPU at the same time (each GPU copies its rows over its own PCIe link).
+ * bvode_multi_gather_device puts the final results of all blocks into one GPU's memory (NCCL over NVLink)
+ * for callers that go on working on the device.  bvode_multi_handle gives the per-device handle
+ * (bvode_dvindy, bvode_get_stats, ... on one block). */
+typedef struct bvode_multi bvode_multi;
+BVODE_API int bvode_multi_create(bvode_multi **out, int problem, long long nsys_total, int ndev,
+                                 const int *devices, unsigned flags);
+BVODE_API void bvode_multi_destroy(bvode_multi *m);
+BVODE_API int bvode_multi_device_count(const bvode_multi *m);
+BVODE_API bvode_solver *bvode_multi_handle(bvode_multi *m, int slot);
+BVODE_API int bvode_multi_set_params(bvode_multi *m, const double *params);
+BVODE_API int bvode_multi_solve(bvode_multi *m, int neq, double *y, double *t, const double *tout,
+                                int tout_per_system, int itol, const double *rtol, const double *atol,
+                                int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork,
+                                int liw, int mf);
+BVODE_API int bvode_multi_solve_schedule(bvode_multi *m, int neq, double *y, double *t, int nout,
+                                         const double *touts, int itol, const double *rtol,
+                                         const double *atol, int itask, int *istate, int iopt,
+                                         double *rwork, int lrw, int *iwork, int liw, int mf, double *y_out);
+BVODE_API int bvode_multi_gather_device(bvode_multi *m, int root_slot, double *y_all_device,
+                                        double *t_all_device, int *istate_all_device,
+                                        double *rout_all_device, int *iout_all_device);
+
+/* ---- the device LINPACK routines in isolation: known-answer entry for tests and diagnostics.  The reference
+ * has no test of dgefa / dgesl / dgbfa / dgbsl (LP:46-522) on their own; this runs exactly the factor / solve code
+ * of one kernel family on nmat matrices and one right-hand side each (all HOST pointers).
+ *   kind 0  one matrix per thread, registers (n = 2, 3, 4): a[nmat][n*n] column-major; afac / ipvt come back in
+ *           LINPACK's layout (ipvt 1-based)
+ *   kind 1  one matrix per warp, row i on lane i, implicit pivoting (n = 5, 25, 32); kind 2: two rows per lane
+ *           (n = 48, 64): afac[nmat][n][n] is the row image (row r never moves), ipvt[k] = the row that is the
+ *           pivot of step k (0-based)
+ *   kind 3  LINPACK band storage (n = 25): a[nmat][n][2*ml+mu+1] (abd(i, j) at a[j*lda + i]); afac / ipvt in
+ *           LINPACK's layout
+ * x[nmat][n] = the solution (zeros where info != 0); info[nmat] as dgefa / dgbfa (LP:87-88, 119).
+ * flags: BVODE_FLAG_STRICT selects the bit-exact build. */
+BVODE_API int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const double *a, const double *b,
+                            double *afac, int *ipvt, double *x, int *info, int device, unsigned flags);
 
 /* ---- DFMA peak microbenchmark (roofline denominator, FP64 vector pipe).  Runs `iters`
  * dependent-chain FMAs x 8 chains per thread on every SM and returns TFLOP/s. */

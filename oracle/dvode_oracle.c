@@ -154,6 +154,23 @@ static int idamax(int n, const double *dx) /* returns 1-based index */
 #define A(i, j) a[((i)-1) + (size_t)((j)-1) * lda]
 
 /* LP:46-120 */
+/* Test instrumentation (not part of the restated algorithm): how many times dvjac reported a singular
+ * matrix since the last reset, so that a test can show it really drove the integrator down that path. */
+static int g_singular_events = 0;
+void dvo_singular_events_add(void)
+{
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    g_singular_events++;
+}
+int dvo_singular_events(int reset)
+{
+    int v = g_singular_events;
+    if (reset) g_singular_events = 0;
+    return v;
+}
+
 void dvo_dgefa(double *a, int lda, int n, int *ipvt, int *info)
 {
     double t;
@@ -915,7 +932,10 @@ static void dvnlsd(dvo_solver *me, double *y, double *yh, int ldyh, double *vsav
             me->drc = ZERO;
             me->crate = one;
             me->nslp = me->nst;
-            if (ierpj != 0) break;
+            if (ierpj != 0) {
+                dvo_singular_events_add();  /* test instrumentation: a singular Newton matrix (M:2999) */
+                break;
+            }
         }
         for (i = 0; i < n; i++) acor[i] = ZERO;
 

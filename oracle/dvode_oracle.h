@@ -53,6 +53,10 @@ typedef struct dvo_solver {
     int pow_mode;     /* 0 = libm pow (reference semantics); 1 = portable pow (dvo_ppow) */
 } dvo_solver;
 
+/* test instrumentation: singular Newton matrices seen (dvjac's ierpj != 0) since the last reset */
+void dvo_singular_events_add(void);
+int dvo_singular_events(int reset);
+
 /* initialize, M:377-505; the optional dewset / dvnorm procedure arguments (M:431-503) are set
  * with dvo_set_user_norms (NULL keeps the default) */
 void dvo_initialize(dvo_solver *s, dvo_f_fn f, dvo_jac_fn jac, void *ctx);

@@ -36,6 +36,9 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
                      const double *rtol2, const double *atol2, double *y_out, double *t_out,
                      int *istate_out, double *rstats, int *istats, int nthreads);
 
+/* threads the last dvo_batch_solve / dvo_batch_solve2 call actually ran on */
+int dvo_last_threads(void);
+
 int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par, const double *y0, double t0,
                      double tout, const double *rtol, const double *atol, int k, int nq,
                      const double *tqs, double *dky_out, int *iflag_out, double *tcur,

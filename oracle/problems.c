@@ -10,6 +10,9 @@
  *   problem 3  synthetic 32-species mass-action network (builder-defined, not in
  *              the reference; tables shared with the device build through
  *              include/bvode_mech32.h)
+ *   problem 7  Van der Pol with a user dewset whose first weight turns non-positive once
+ *              |y_1| < 1/2 (builder-defined): drives the `ewt(i) <= 0` exit, istate = -6
+ *              (M:1516-1521), which the default weights only reach when a component is exactly 0
  */
 #include "dvode_oracle.h"
 #include "oracle_batch.h"
@@ -78,6 +81,18 @@ static void vdpm_dewset(void *ctx, int n, int itol, const double *rtol, const do
         double ay = fabs(ycur[i]);
         if (ay < 1.0) ay = 1.0;
         ewt[i] = r * ay + a;
+    }
+}
+/* problem 7: the default weights, except that ewt_1 drops by one once |y_1| < 1/2 */
+static void vdpd_dewset(void *ctx, int n, int itol, const double *rtol, const double *atol,
+                        const double *ycur, double *ewt)
+{
+    (void)ctx;
+    for (int i = 0; i < n; i++) {
+        double r = (itol >= 3) ? rtol[i] : rtol[0];
+        double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        ewt[i] = r * fabs(ycur[i]) + a;
+        if (i == 0 && fabs(ycur[i]) < 0.5) ewt[i] = ewt[i] - 1.0;
     }
 }
 static double vdpm_dvnorm(void *ctx, int n, const double *v, const double *w)
@@ -156,6 +171,7 @@ int dvo_problem_info(int problem, int *neq, int *npar)
     case 4: *neq = 2; *npar = 1; return 0;
     case 5: *neq = NG * NG; *npar = 2; return 0;  /* advection with the user norms of problem 4 */
     case 6: *neq = 48; *npar = 2; return 0;
+    case 7: *neq = 2; *npar = 1; return 0;
     default: return -1;
     }
 }
@@ -204,6 +220,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     case 4: *f = vdp_f; *jac = vdp_jac; return 0;
     case 5: *f = adv_f; *jac = adv_jac; return 0;
     case 6: *f = dif_f; *jac = NULL; return 0;
+    case 7: *f = vdp_f; *jac = vdp_jac; return 0;
     default: return -1;
     }
 }
@@ -233,6 +250,10 @@ void dvo_work_sizes(int neq, int mf, int ml, int mu, int maxord_in, int *lrw, in
     *liw = (miter == 0 || miter == 3) ? 30 : 30 + neq;
 }
 
+/* threads the last batch call actually ran on (bench.py reports it as `cores`) */
+static int g_last_threads = 1;
+int dvo_last_threads(void) { return g_last_threads; }
+
 /* One independent solver instance per system, replaying the reference's call
  * sequence (example.f90:56-66): for each tout, one dvode call with itask as
  * configured; istate carried between calls; stop at the first negative istate. */
@@ -253,6 +274,10 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
 #pragma omp parallel num_threads(nthreads)
 #endif
     {
+#ifdef _OPENMP
+#pragma omp single nowait
+        g_last_threads = omp_get_num_threads();
+#endif
         double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
         int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
         double *y = (double *)malloc(sizeof(double) * (size_t)neq);
@@ -265,6 +290,7 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
             if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+            if (cfg->problem == 7) dvo_set_user_norms(&sol, vdpd_dewset, NULL);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -328,6 +354,10 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
 #pragma omp parallel num_threads(nthreads)
 #endif
     {
+#ifdef _OPENMP
+#pragma omp single nowait
+        g_last_threads = omp_get_num_threads();
+#endif
         double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
         int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
         double *y = (double *)malloc(sizeof(double) * (size_t)neq);
@@ -340,6 +370,7 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
             memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
             if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+            if (cfg->problem == 7) dvo_set_user_norms(&sol, vdpd_dewset, NULL);
             sol.pow_mode = cfg->pow_mode;
             memset(rwork, 0, sizeof(double) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
@@ -399,6 +430,7 @@ int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const doubl
     dvo_solver sol;
     dvo_initialize(&sol, f, jac, par);
     if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
+            if (cfg->problem == 7) dvo_set_user_norms(&sol, vdpd_dewset, NULL);
     sol.pow_mode = cfg->pow_mode;
     iwork[0] = cfg->ml; iwork[1] = cfg->mu;
     if (cfg->iopt) {

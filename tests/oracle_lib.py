@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
 
 PROBLEMS = {"robertson": 0, "vdp": 1, "advection": 2, "mech32": 3, "vdp_maxnorm": 4,
-            "advection_maxnorm": 5, "diffusion48": 6}
+            "advection_maxnorm": 5, "diffusion48": 6, "vdp_ewtdrop": 7}
 
 
 class BatchCfg(C.Structure):
@@ -72,6 +72,21 @@ def lib(variant=""):
         _lib.dvo_dgbsl.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, dp]
         _libs[variant] = _lib
     return _libs[variant]
+
+
+def singular_events(reset=True, variant=""):
+    """Singular Newton matrices (dvjac's ierpj != 0, M:2999) seen since the last reset."""
+    L = lib(variant)
+    L.dvo_singular_events.restype = C.c_int
+    L.dvo_singular_events.argtypes = [C.c_int]
+    return int(L.dvo_singular_events(1 if reset else 0))
+
+
+def threads_used(variant=""):
+    """Threads the last batch_solve call of this library actually ran on (omp_get_num_threads)."""
+    L = lib(variant)
+    L.dvo_last_threads.restype = C.c_int
+    return int(L.dvo_last_threads())
 
 
 def _dp(a):

@@ -27,8 +27,8 @@ def _worker(rank, world, port, nsys, out_path):
     touts = batches.robertson_touts()[:3]
     r = O.batch_solve("robertson", par, batches.ROBERTSON_Y0, 0.0, touts, tol["rtol"], tol["atol"],
                       21, itol=2, nthreads=1)
-    y = sharding.gather_to_rank0(torch.from_numpy(r["y"][:, -1].copy()), dist, rank, world)
-    st = sharding.gather_to_rank0(torch.from_numpy(r["istats"][:, -1].copy()), dist, rank, world)
+    y = sharding.gather_to_rank0(torch.from_numpy(r["y"][:, -1].copy()), dist, rank, world, nsys)
+    st = sharding.gather_to_rank0(torch.from_numpy(r["istats"][:, -1].copy()), dist, rank, world, nsys)
     if rank == 0:
         np.savez(out_path, y=y.numpy(), st=st.numpy())
     dist.barrier()
