@@ -470,6 +470,7 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
     s->last_y = d_y;
     s->last_t = d_t;
     s->last_istate = d_istate;
+    s->last_stream = st;
     if (upload_tol)
         CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
                                  cudaMemcpyHostToDevice, st));

@@ -39,6 +39,7 @@ struct bvode_solver {
     // ---- what the last solve call left where (bvode_gather reads these)
     double *last_y = nullptr, *last_t = nullptr;  // SoA [neq][nsys], [nsys] on the device
     int *last_istate = nullptr;
+    cudaStream_t last_stream = nullptr;  // the stream the last solve was enqueued on
     double *d_pack = nullptr;        // bvode_gather: this rank's packed final results
     size_t pack_cap = 0;
 };

@@ -212,7 +212,7 @@ int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys
     }
     if (!s->last_y || !s->last_t || !s->last_istate) { bvode_set_error("bvode_gather before any solve"); return BVODE_EINVAL; }
     CUDA_TRY(cudaSetDevice(s->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // as in bvode_solve_*_device: 0 = the legacy default stream
     const int n = s->nsys, neq = s->neq;
     const bool is_root = (c->rank == root);
     const int TB = 256, grid = (n + TB - 1) / TB;
@@ -289,6 +289,8 @@ int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total,
     double *wy = y_all ? (is_root ? dy : (double *)1) : nullptr, *wt = t_all ? (is_root ? dt : (double *)1) : nullptr;
     double *wr = rout_all ? (is_root ? dr : (double *)1) : nullptr;
     int *wi = iout_all ? (is_root ? di : (int *)1) : nullptr, *wist = istate_all ? (is_root ? dist : (int *)1) : nullptr;
+    // the results may still be in flight on the stream of a device-resident solve
+    if (s->last_stream != s->stream) CUDA_TRY(cudaStreamSynchronize(s->last_stream));
     int rc = bvode_gather_device(s, c, root, nsys_total, wy, wt, wist, wr, wi, s->stream);
     if (rc == BVODE_OK && is_root) {
         const size_t nt = (size_t)nsys_total;
@@ -444,14 +446,14 @@ int bvode_multi_gather_device(bvode_multi *m, int root_slot, double *y_all, doub
     }
     if (m->ndev == 1) {
         bvode_comm c1;
-        return bvode_gather_device(m->h[0], &c1, 0, m->nsys_total, y_all, t_all, istate_all, rout_all, iout_all, nullptr);
+        return bvode_gather_device(m->h[0], &c1, 0, m->nsys_total, y_all, t_all, istate_all, rout_all, iout_all, m->h[0]->stream);
     }
     // one thread drives all devices: the sends / receives of every rank inside one group
     NCCL_TRY(nccl().GroupStart());
     int rc = BVODE_OK;
     for (int d = 0; d < m->ndev && rc == BVODE_OK; d++)
         rc = bvode_gather_device(m->h[d], m->comms[d], root_slot, m->nsys_total, y_all, t_all, istate_all, rout_all,
-                                 iout_all, nullptr);
+                                 iout_all, m->h[d]->stream);
     NCCL_TRY(nccl().GroupEnd());
     if (rc != BVODE_OK) return rc;
     for (int d = 0; d < m->ndev; d++) {

@@ -184,8 +184,8 @@ BVODE_API int bvode_last_launch_count(const bvode_solver *s);
  * rank's handle into arrays on the root's GPU, in system order and host layout: y_all[nsys_total][neq],
  * t_all[nsys_total], istate_all[nsys_total], rout_all[nsys_total][4], iout_all[nsys_total][12] (device
  * pointers on the root; on the other ranks any non-NULL value means "this array is wanted"; every rank must
- * pass the same set).  Enqueued on `stream` (a cudaStream_t as void*, NULL = the handle's own); returns
- * without waiting.  bvode_gather: the same with HOST arrays on the root, and it waits. */
+ * pass the same set).  Enqueued on `stream` (a cudaStream_t as void*, 0 = the default stream, as in
+ * bvode_solve_schedule_device: pass the stream the solve was enqueued on); returns without waiting.  bvode_gather: the same with HOST arrays on the root, and it waits. */
 typedef struct bvode_comm bvode_comm;
 BVODE_API void bvode_shard_range(long long nsys_total, int rank, int world, long long *first, long long *last);
 BVODE_API int bvode_nccl_version(void);                       /* 0: NCCL could not be loaded */
