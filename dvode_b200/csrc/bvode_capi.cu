@@ -369,6 +369,7 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
     o.mu = mu;
     o.itask = itask;
     o.jreset = 0;
+    o.stash = 0;
     if (iopt == 1 && (!rwork0 || !iwork0)) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
     if (const char *msg = read_optional_inputs(meth, itask, iopt, rwork0, iwork0, &o)) { g_err = msg; return BVODE_EINVAL; }
     c->tol.resize(2 * (size_t)neq);
@@ -545,10 +546,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     if (n3 != 0 && n3 != nsys) { g_err = "istate = 3 must be given for every system of the batch"; return BVODE_EINVAL; }
     if (n3 != 0 && !s->d_state) { g_err = "istate = 3 before a successful first call"; return BVODE_EINVAL; }
     const bool mf_changed = (n3 != 0 && s->mf != mf);
-    if (mf_changed && (abs(s->mf) / 10 != abs(mf) / 10)) {
-        g_err = "istate = 3 with another method family (meth) is not built: the Nordsieck array has another shape";
-        return BVODE_ENOTIMPL;
-    }
+    const bool array_shrinks = mf_changed && (abs(s->mf) / 10 == 1) && (abs(mf) / 10 == 2);  // Adams -> BDF: lmax 13 -> 6
     Checked c;
     const bool have_headers = rwork && iwork;
     int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c);
@@ -596,6 +594,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         s->ml = c.o.ml;
         s->mu = c.o.mu;
         c.o.jreset = 1;
+        c.o.stash = array_shrinks ? 1 : 0;
     }
     if (!any_first && (s->mf != mf || !s->d_state)) {
         for (int j = 0; j < nsys; j++) istate[j] = -3;  // M:1102-1106

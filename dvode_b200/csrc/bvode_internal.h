@@ -17,6 +17,9 @@ struct BvOpts {
                                  // copy is not trusted (the reference's work-array segments move,
                                  // M:1246-1268, and its copy is lost) -> re-evaluate at the next dvjac
     double tcrit;                // rwork(1), itask 4 / 5
+    int stash;                   // istate = 3 from Adams to BDF: the Nordsieck array shrinks from 13 to 6 columns; the
+                                 // old column maxord + 2, which the order reduction of M:1385, 2044-2079 reads, travels
+                                 // in the acor slot of the converted state
 };
 
 // Arguments of one solve launch.  All pointers are device pointers, SoA layout.

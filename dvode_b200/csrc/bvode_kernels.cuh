@@ -320,35 +320,42 @@ struct WarpLayout {
     }
 };
 
+// The three state regions of a warp kernel (see the layout above), recomputed from the kernel arguments where a
+// system is loaded or stored instead of being kept in registers across the step loop.
+template <class POL>
+struct WarpRegions {
+    const double *dl, *db;
+    const int *il;
+    int nblock;
+    BV_DEV WarpRegions(const double *dstate, const int *istore, size_t nsys, int ml, int mu) {
+        dl = dstate + (size_t)scalar_d<POL>() * nsys;
+        db = dl + (size_t)POL::kLaneSlots * nsys * 32;
+        il = istore + (size_t)kScalarI * nsys;
+        if constexpr (POL::kBand) nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
+        else if constexpr (POL::kPlain) nblock = 0;
+        else nblock = POL::kBlockDoubles;
+    }
+};
+
 template <class POL>
 BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, size_t nsys,
-                      size_t sys, int ln, int warp, int ml, int mu, double *smem,
-                      const double *&dl, const double *&db, const int *&il, int &nblock) {
-    dl = dstate + (size_t)scalar_d<POL>() * nsys;
-    db = dl + (size_t)POL::kLaneSlots * nsys * 32;
-    il = istore + (size_t)kScalarI * nsys;
-    nblock = 0;
-    {   // per-warp control state: after the kWarpTPB/32 matrix images of the CTA
-        int nb;
-        if constexpr (POL::kBand) nb = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
-        else if constexpr (POL::kPlain) nb = 0;
-        else nb = POL::kBlockDoubles;
-        e.hot.bind(smem + (size_t)(WarpTpb<POL>::value / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
-    }
+                      size_t sys, int ln, int warp, int ml, int mu, double *smem) {
+    const WarpRegions<POL> rg(dstate, istore, nsys, ml, mu);
+    const int nb = rg.nblock;
+    // per-warp control state: after the kWarpTPB/32 matrix images of the CTA
+    e.hot.bind(smem + (size_t)(WarpTpb<POL>::value / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
     if constexpr (POL::kBand) {
-        nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
         e.lin.ml = ml;
         e.lin.mu = mu;
         e.lin.ld = POL::band_ld(ml, mu);
-        e.lin.abd = smem + (size_t)warp * nblock;
+        e.lin.abd = smem + (size_t)warp * nb;
         e.lin.wjs = e.lin.abd + e.lin.ld * POL::N;
     } else if constexpr (POL::kPlain) {
         (void)ml; (void)mu; (void)smem; (void)warp; (void)sys; (void)ln;
     } else {
-        nblock = POL::kBlockDoubles;
-        e.lin.p = smem + (size_t)warp * nblock;
-        e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::N * POL::LDP + ((POL::N * POL::LDP) & 1));
-        e.lin.wjs.p = const_cast<double *>(dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
+        e.lin.p = smem + (size_t)warp * nb;
+        e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::kPermOff);
+        e.lin.wjs.p = const_cast<double *>(rg.dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
         e.lin.wjs.stride = nsys * 32;
     }
 }
@@ -385,11 +392,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             e.tol.a[i] = (ln + 32 * i < N) ? a.atol[ln + 32 * i] : 1.0;
         }
     }
-    const double *dl, *db;
-    const int *il;
-    int nblock;
-    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.o.ml, a.o.mu, smem, dl, db, il,
-              nblock);
+    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.o.ml, a.o.mu, smem);
     int nemit = 0;
     double tout0 = 0.0;
 
@@ -440,7 +443,8 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             }
             return 1;
         }
-        WarpLoader ld{a.dstate, dl, db, a.istate_store, il, nsys, sys, ln, nblock};
+        const WarpRegions<POL> rg(a.dstate, a.istate_store, nsys, a.o.ml, a.o.mu);
+        WarpLoader ld{a.dstate, rg.dl, rg.db, a.istate_store, rg.il, nsys, sys, ln, rg.nblock};
         visit_state(e, ld);
         e.c.L = e.c.nq + 1;
         e.c.kflag = 0;
@@ -475,8 +479,9 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
         for (int i = 0; i < NL; i++)
             if (ln + 32 * i < N) a.y[(size_t)(ln + 32 * i) * nsys + sys] = e.y[i];
         {
-            WarpStorer st{a.dstate, const_cast<double *>(dl), const_cast<double *>(db),
-                          a.istate_store, const_cast<int *>(il), nsys, sys, ln, nblock};
+            const WarpRegions<POL> rg(a.dstate, a.istate_store, nsys, a.o.ml, a.o.mu);
+            WarpStorer st{a.dstate, const_cast<double *>(rg.dl), const_cast<double *>(rg.db),
+                          a.istate_store, const_cast<int *>(rg.il), nsys, sys, ln, rg.nblock};
             visit_state(e, st);
         }
         if (ln == 0) {
@@ -529,11 +534,9 @@ __global__ void __launch_bounds__(WarpTpb<POL>::value) dvindy_warp_kernel(const 
     if (sys >= nsys) return;
     constexpr int N = POL::N;
     Engine<POL> e;
-    const double *dl, *db;
-    const int *il;
-    int nblock;
-    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.ml, a.mu, smem, dl, db, il, nblock);
-    WarpLoader ld{a.dstate, dl, db, a.istate_store, il, nsys, sys, ln, nblock};
+    warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.ml, a.mu, smem);
+    const WarpRegions<POL> rg(a.dstate, a.istate_store, nsys, a.ml, a.mu);
+    WarpLoader ld{a.dstate, rg.dl, rg.db, a.istate_store, rg.il, nsys, sys, ln, rg.nblock};
     visit_state(e, ld);
     e.c.L = e.c.nq + 1;
     const double t = a.t_ps ? a.t_ps[sys] : a.t;
@@ -604,14 +607,23 @@ template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.count + spb - 1) / spb;
-    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles);
+    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles +
+                                               ScratchDoublesOf<typename POL::Prob>::value);
+    // Shared memory / L1 split: ask for just what POL::kMinBlocks resident CTAs need (+1 KB each that the
+    // system reserves), so that the rest of the 256 KB stays L1 -- the kernels' register spills and the
+    // problems' coefficient tables live there (ncu r2d: with the maximum carve-out spills went to L2).
+    int carve = (int)((POL::kMinBlocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (const char *cv = getenv("BVODE_CARVEOUT")) carve = atoi(cv);  // experiments
+    if (carve > 100) carve = 100;
     if (a.general) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_warp_kernel<POL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (carve >= 0) cudaFuncSetAttribute(vode_warp_kernel<POL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         vode_warp_kernel<POL, true><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     } else {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(vode_warp_kernel<POL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (carve >= 0) cudaFuncSetAttribute(vode_warp_kernel<POL, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         vode_warp_kernel<POL, false><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
@@ -682,20 +694,33 @@ static void thread_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, s
     *nd = nsys * (size_t)(lm * N + 2 * N + N * N + (m.savej ? N * N : 0) + lm + 14);
     *ni = nsys * (size_t)(N + 19);
 }
+// Copy `rows` SoA rows of `width` entries each (D2D, async).
+template <class T>
+static void copy_rows(T *dst, const T *src, size_t rows, size_t width, cudaStream_t st) {
+    if (rows) cudaMemcpyAsync(dst, src, sizeof(T) * rows * width, cudaMemcpyDeviceToDevice, st);
+}
+// istate = 3 with another method flag: carry the method-independent part of the state over into the layout of
+// mf_new (zero-filled by the caller).  Within a family only miter / jsv change; across families (Adams <-> BDF)
+// the Nordsieck array and the tau history have another number of columns (lmax = 13 / 6): the common columns are
+// copied (a Nordsieck array means the same under both methods, M:2031-2079 goes on from it), and when the array
+// shrinks its old column maxord_new + 2 -- which the order reduction of M:1385 / 2044-2079 reads -- goes into the
+// acor slot (free at a restart: dvnlsd zeroes acor before its next use).
 template <class PROB>
 static int thread_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
                                 const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
-    constexpr int N = PROB::N;
+    constexpr size_t N = PROB::N;
     const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
-    if (a.meth != b.meth) return -1000;
-    const int lm = kLmaxOf(a.meth);
-    // doubles: yh, acor copy, acor, P (head) | saved J if jsv > 0 | tau, scalars (tail); see thread_state_size
-    const size_t head = (size_t)(lm * N + 2 * N + N * N), tail = (size_t)(lm + 14);
-    const size_t wo = a.savej ? (size_t)N * N : 0, wn = b.savej ? (size_t)N * N : 0;
-    cudaMemcpyAsync(d_new, d_old, sizeof(double) * head * nsys, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(d_new + (head + wn) * nsys, d_old + (head + wo) * nsys, sizeof(double) * tail * nsys,
-                    cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(i_new, i_old, sizeof(int) * (size_t)(N + 19) * nsys, cudaMemcpyDeviceToDevice, st);
+    const size_t la = kLmaxOf(a.meth), lb = kLmaxOf(b.meth), lmin = la < lb ? la : lb;
+    // doubles: yh[lm][N], acor copy[N], acor[N], P[N][N] | saved J if jsv > 0 | tau[lm], 14 scalars; see thread_state_size
+    const size_t acs_a = la * N, acs_b = lb * N;
+    const size_t tau_a = acs_a + 2 * N + N * N + (a.savej ? N * N : 0), tau_b = acs_b + 2 * N + N * N + (b.savej ? N * N : 0);
+    copy_rows(d_new, d_old, lmin * N, nsys, st);                                              // yh
+    copy_rows(d_new + acs_b * nsys, d_old + acs_a * nsys, N, nsys, st);                       // acor copy
+    if (la > lb) copy_rows(d_new + (acs_b + N) * nsys, d_old + lb * N * nsys, N, nsys, st);    // acor slot <- old yh(:, lmax_new + 1)
+    else copy_rows(d_new + (acs_b + N) * nsys, d_old + (acs_a + N) * nsys, N, nsys, st);       // acor
+    copy_rows(d_new + tau_b * nsys, d_old + tau_a * nsys, lmin, nsys, st);                    // tau
+    copy_rows(d_new + (tau_b + lb) * nsys, d_old + (tau_a + la) * nsys, 14, nsys, st);         // scalars
+    copy_rows(i_new, i_old, N + 19, nsys, st);
     return (int)cudaGetLastError();
 }
 template <class PROB>
@@ -711,9 +736,13 @@ static int thread_supports(int mf, int ml, int mu) {
     }
 
 template <class P, class = void>
-struct HasJacRow { static constexpr bool value = false; };
+struct HasJacRowMember { static constexpr bool value = false; };
 template <class P>
-struct HasJacRow<P, decltype((void)&P::jac_row)> { static constexpr bool value = true; };
+struct HasJacRowMember<P, decltype((void)&P::jac_row)> { static constexpr bool value = true; };
+template <class P>
+struct HasJacRow { static constexpr bool value = HasJacRowMember<P>::value || HasJacDenseFull<P>::value; };
+template <class P>
+constexpr bool kHasBandJac = HasJacBandCol<P>::value || HasJacBandFull<P>::value;
 
 // ---- warp-per-system problems ---------------------------------------------------------------
 // KIND 1: dense finite-difference Jacobian available (miter 2); KIND 2: banded (miter 4, 5).
@@ -723,7 +752,7 @@ static int warp_dispatch_m(const MfParts &m, const KArgs &a, cudaStream_t st) {
     switch (m.miter) {
     case 0: return launch_warp<WarpPlainPolicy<PROB, 0, METH>>(a, st);
     case 3: return launch_warp<WarpPlainPolicy<PROB, 3, METH>>(a, st);
-    case 1:  // dense analytic Jacobian: problems with a jac_row member
+    case 1:  // dense analytic Jacobian: problems with a jac_row (or whole-matrix jac_dense_full) member
         if constexpr (KIND == 1 && HasJacRow<PROB>::value)
             return m.savej ? launch_warp<WarpDensePolicy<PROB, 1, true, METH>>(a, st)
                            : launch_warp<WarpDensePolicy<PROB, 1, false, METH>>(a, st);
@@ -733,8 +762,8 @@ static int warp_dispatch_m(const MfParts &m, const KArgs &a, cudaStream_t st) {
             return m.savej ? launch_warp<WarpDensePolicy<PROB, 2, true, METH>>(a, st)
                            : launch_warp<WarpDensePolicy<PROB, 2, false, METH>>(a, st);
         return -1000;
-    case 4:
-        if constexpr (KIND == 2)
+    case 4:  // banded analytic Jacobian: problems with jac_band_col (or whole-matrix jac_band_full)
+        if constexpr (KIND == 2 && kHasBandJac<PROB>)
             return m.savej ? launch_warp<WarpBandPolicy<PROB, 4, true, METH>>(a, st)
                            : launch_warp<WarpBandPolicy<PROB, 4, false, METH>>(a, st);
         return -1000;
@@ -787,17 +816,29 @@ static void warp_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, siz
         return 0;
     });
 }
+// The same for the one-system-per-warp layouts: scalars[lm + 14][nsys], then the lane slots yh[lm][NLOC], acor
+// copy[NLOC], acor[NLOC] (rows of nsys * 32); everything else (matrix images, pivots) is rebuilt at the restart.
+template <int NLOC>
+static int warp_convert_generic(int mf_old, int mf_new, size_t nsys, const double *d_old, const int *i_old,
+                                double *d_new, int *i_new, cudaStream_t st) {
+    const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
+    const size_t la = kLmaxOf(a.meth), lb = kLmaxOf(b.meth), lmin = la < lb ? la : lb;
+    copy_rows(d_new, d_old, lmin, nsys, st);                                     // tau
+    copy_rows(d_new + lb * nsys, d_old + la * nsys, 14, nsys, st);               // scalars
+    const double *lo = d_old + (la + 14) * nsys;
+    double *ln = d_new + (lb + 14) * nsys;
+    const size_t w = nsys * 32;
+    copy_rows(ln, lo, lmin * NLOC, w, st);                                       // yh
+    copy_rows(ln + lb * NLOC * w, lo + la * NLOC * w, NLOC, w, st);              // acor copy
+    if (la > lb) copy_rows(ln + (lb + 1) * NLOC * w, lo + lb * NLOC * w, NLOC, w, st);  // acor slot <- old yh(:, lmax_new + 1)
+    else copy_rows(ln + (lb + 1) * NLOC * w, lo + (la + 1) * NLOC * w, NLOC, w, st);    // acor
+    copy_rows(i_new, i_old, (size_t)kScalarI, nsys, st);
+    return (int)cudaGetLastError();
+}
 template <class PROB, int KIND>
 static int warp_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
                               const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
-    const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
-    if (a.meth != b.meth) return -1000;
-    const int lm = kLmaxOf(a.meth);
-    // every warp policy starts with scalars[lm + 14][nsys], then the lane slots yh[lm], acor copy, acor
-    const size_t nd = ((size_t)(lm + 14) + (size_t)(lm + 2) * 32) * nsys;
-    cudaMemcpyAsync(d_new, d_old, sizeof(double) * nd, cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(i_new, i_old, sizeof(int) * (size_t)kScalarI * nsys, cudaMemcpyDeviceToDevice, st);
-    return (int)cudaGetLastError();
+    return warp_convert_generic<1>(mf_old, mf_new, nsys, d_old, i_old, d_new, i_new, st);
 }
 template <class PROB, int KIND>
 static int warp_supports(int mf, int ml, int mu) {
@@ -805,6 +846,7 @@ static int warp_supports(int mf, int ml, int mu) {
     if (m.meth != 1 && m.meth != 2) return 0;
     if (m.miter == 0 || m.miter == 3) return 1;
     if (KIND == 1) return m.miter == 2 || (m.miter == 1 && HasJacRow<PROB>::value);
+    if (m.miter == 4 && !kHasBandJac<PROB>) return 0;
     return (m.miter == 4 || m.miter == 5) && ml >= 0 && mu >= 0 && ml + mu + 1 <= 32 &&
            ml < PROB::N && mu < PROB::N;
 }
@@ -853,13 +895,14 @@ static int warp2_supports(int mf, int, int) {
     const MfParts m = mf_parts(mf);
     return (m.meth == 1 || m.meth == 2) && (m.miter == 0 || m.miter == 2 || m.miter == 3);
 }
-static int no_state_convert(int, int, int, int, size_t, const double *, const int *, double *, int *, cudaStream_t) {
-    return -1000;
+static int warp2_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old, const int *i_old,
+                               double *d_new, int *i_new, cudaStream_t st) {
+    return warp_convert_generic<2>(mf_old, mf_new, nsys, d_old, i_old, d_new, i_new, st);
 }
 #define BVODE_WARP2_DENSE_FD_PROBLEM(NAME, PROB)                                            \
     ProblemEntry {                                                                          \
         NAME, PROB::N, PROB::NPAR, 1, warp2_supports<PROB>, warp2_state_size<PROB>,         \
-            warp2_dispatch<PROB>, warp2_dky_dispatch<PROB>, no_state_convert                \
+            warp2_dispatch<PROB>, warp2_dky_dispatch<PROB>, warp2_state_convert             \
     }
 #define BVODE_WARP_DENSE_FD_PROBLEM(NAME, PROB)                                             \
     ProblemEntry {                                                                          \

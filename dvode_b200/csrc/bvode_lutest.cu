@@ -55,11 +55,11 @@ __global__ void k_lu_dense(int nmat, const double *a, const double *b, double *a
     if (m >= nmat) return;
     LuEng<typename POL::Lin> e;
     e.lin.p = smem;
-    e.lin.perm = reinterpret_cast<int *>(smem + N * POL::LDP + ((N * POL::LDP) & 1));
+    e.lin.perm = reinterpret_cast<int *>(smem + POL::kPermOff);
     if (ln < N)
         for (int j = 0; j < N; j++) e.lin.p[ln * POL::LDP + j] = a[(size_t)m * N * N + j * N + ln];
     POL::lin_init(e);
-    const int inf = POL::dgefa(e.lin);
+    const int inf = POL::factor(e.lin);
     double xv[1] = {(ln < N) ? b[(size_t)m * N + ln] : 0.0};
     if (inf == 0) POL::solve(e, xv);
     __syncwarp();
@@ -80,14 +80,14 @@ __global__ void k_lu_dense2(int nmat, const double *a, const double *b, double *
     if (m >= nmat) return;
     LuEng<typename POL::Lin> e;
     e.lin.p = smem;
-    e.lin.perm = reinterpret_cast<int *>(smem + N * POL::LDP + ((N * POL::LDP) & 1));
+    e.lin.perm = reinterpret_cast<int *>(smem + POL::kPermOff);
     for (int s = 0; s < 2; s++) {
         const int r = ln + 32 * s;
         if (r < N)
             for (int j = 0; j < N; j++) e.lin.p[r * POL::LDP + j] = a[(size_t)m * N * N + j * N + r];
     }
     POL::lin_init(e);
-    const int inf = POL::dgefa(e.lin);
+    const int inf = POL::factor(e.lin);
     double xv[2] = {b[(size_t)m * N + ln], (ln + 32 < N) ? b[(size_t)m * N + ln + 32] : 0.0};
     if (inf == 0) POL::solve(e, xv);
     __syncwarp();

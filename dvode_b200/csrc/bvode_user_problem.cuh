@@ -22,6 +22,7 @@
 // (dvode_b200.plugins.build_problem / register_problem do both steps from Python).
 #pragma once
 #include "bvode_kernels.cuh"
+#include "bvode_ref_problem.cuh"
 
 #define BV_UCAT2(a, b) a##b
 #define BV_UCAT(a, b) BV_UCAT2(a, b)
@@ -49,3 +50,9 @@
 #define BVODE_REGISTER_WARP_DENSE_FD_PROBLEM(NAME, PROB) BVODE_USER_ENTRY_(BVODE_WARP_DENSE_FD_PROBLEM, NAME, PROB)
 // one system per warp, two components per lane (32 < n <= 64), f_lane2: dense FD Jacobian (miter 2)
 #define BVODE_REGISTER_WARP2_DENSE_FD_PROBLEM(NAME, PROB) BVODE_USER_ENTRY_(BVODE_WARP2_DENSE_FD_PROBLEM, NAME, PROB)
+
+// the same three mappings for callbacks in the REFERENCE's whole-vector form f(neq, t, y, ydot, par) /
+// jac(neq, t, y, ml, mu, pd, nrowpd, par) (M:316-334; csrc/bvode_ref_problem.cuh): no lane-wise rewrite
+#define BVODE_REGISTER_WARP_REF_BAND_PROBLEM(NAME, REF) BVODE_USER_ENTRY_(BVODE_WARP_BAND_PROBLEM, NAME, RefWarp<REF>)
+#define BVODE_REGISTER_WARP_REF_DENSE_PROBLEM(NAME, REF) BVODE_USER_ENTRY_(BVODE_WARP_DENSE_FD_PROBLEM, NAME, RefWarp<REF>)
+#define BVODE_REGISTER_WARP_REF2_DENSE_PROBLEM(NAME, REF) BVODE_USER_ENTRY_(BVODE_WARP2_DENSE_FD_PROBLEM, NAME, RefWarp2<REF>)

