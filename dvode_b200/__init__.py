@@ -11,12 +11,12 @@ import importlib
 
 _API_NAMES = ("BvodeError", "Comm", "dvode_multi_t", "dvode_t", "fp64_peak_tflops", "library_path",
               "nccl_version", "problem_info", "problem_names")
-__all__ = list(_API_NAMES) + ["api", "batches", "build", "plugins", "sharding"]
+__all__ = list(_API_NAMES) + ["api", "api32", "batches", "build", "plugins", "sharding"]
 
 
 def __getattr__(name):
     if name in _API_NAMES:
         return getattr(importlib.import_module(".api", __name__), name)
-    if name in ("api", "batches", "build", "plugins", "sharding"):
+    if name in ("api", "api32", "batches", "build", "plugins", "sharding"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -17,8 +17,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# The working precision of this module: REAL64 over libbvode.so, or -- when this file is loaded as
+# dvode_b200.api32 -- REAL32 over libbvode32.so (the reference's kind switch, dvode_kinds_module.F90:29-31).
+_REAL32 = __name__.endswith("api32")
+REAL = np.float32 if _REAL32 else np.float64
 # BVODE_LIB lets experiments point at another build of the same library (never a fallback)
-_LIB_PATH = os.environ.get("BVODE_LIB") or os.path.join(_HERE, "libbvode.so")
+_LIB_PATH = (os.path.join(_HERE, "libbvode32.so") if _REAL32 else
+             (os.environ.get("BVODE_LIB") or os.path.join(_HERE, "libbvode.so")))
 
 
 class BvodeError(RuntimeError):
@@ -113,7 +118,7 @@ def _ptr(a):
 
 
 def _f64(a, shape=None):
-    a = np.ascontiguousarray(a, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=REAL)
     if shape is not None:
         a = a.reshape(shape)
     return a
@@ -210,7 +215,7 @@ class dvode_t:
         touts = _f64(touts).reshape(-1)
         rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
         if y_out is not None:
-            assert y_out.dtype == np.float64 and y_out.flags.c_contiguous
+            assert y_out.dtype == REAL and y_out.flags.c_contiguous
             assert y_out.shape == (touts.size, self.nsys, self.neq)
         _check(_lib.bvode_solve_schedule(self._h, int(neq), _ptr(y), _ptr(t), touts.size,
                                          _ptr(touts), int(itol), _ptr(rtol), _ptr(atol),
@@ -241,7 +246,7 @@ class dvode_t:
     def dvindy(self, t, k):
         t = _f64(t).reshape(-1)
         per = 1 if t.size > 1 else 0
-        dky = np.zeros((self.nsys, self.neq))
+        dky = np.zeros((self.nsys, self.neq), dtype=REAL)
         iflag = np.zeros(self.nsys, dtype=np.int32)
         _check(_lib.bvode_dvindy(self._h, _ptr(t), per, int(k), _ptr(dky), _ptr(iflag)))
         return dky, iflag
@@ -271,8 +276,8 @@ class dvode_t:
         """Host arrays on the root (dict of numpy arrays); None on the other ranks."""
         is_root = comm.rank == root
         out = {}
-        shapes = {"y": ((nsys_total, self.neq), np.float64), "t": ((nsys_total,), np.float64),
-                  "istate": ((nsys_total,), np.int32), "rout": ((nsys_total, 4), np.float64),
+        shapes = {"y": ((nsys_total, self.neq), REAL), "t": ((nsys_total,), REAL),
+                  "istate": ((nsys_total,), np.int32), "rout": ((nsys_total, 4), REAL),
                   "iout": ((nsys_total, 12), np.int32)}
         args = []
         for k in ("y", "t", "istate", "rout", "iout"):
@@ -287,7 +292,7 @@ class dvode_t:
 
     def stats(self):
         """Optional outputs: (rwork(11:14)[nsys,4], iwork(11:22)[nsys,12])."""
-        r = np.zeros((self.nsys, 4))
+        r = np.zeros((self.nsys, 4), dtype=REAL)
         i = np.zeros((self.nsys, 12), dtype=np.int32)
         _check(_lib.bvode_get_stats(self._h, _ptr(r), _ptr(i)))
         return r, i
@@ -316,19 +321,19 @@ class dvode_t:
     def _chk_arrays(self, y, t, istate, rwork, iwork, lrw, liw):
         if self._h is None:
             raise BvodeError(-1, "initialize() has not been called")
-        ok = (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous and
+        ok = (isinstance(y, np.ndarray) and y.dtype == REAL and y.flags.c_contiguous and
               y.size == self.nsys * self.neq and isinstance(t, np.ndarray) and
-              t.dtype == np.float64 and t.size == self.nsys and isinstance(istate, np.ndarray) and
+              t.dtype == REAL and t.size == self.nsys and isinstance(istate, np.ndarray) and
               istate.dtype == np.int32 and istate.size == self.nsys)
         if rwork is not None:
-            ok = ok and rwork.dtype == np.float64 and rwork.flags.c_contiguous and \
+            ok = ok and rwork.dtype == REAL and rwork.flags.c_contiguous and \
                 rwork.size == self.nsys * lrw
         if iwork is not None:
             ok = ok and iwork.dtype == np.int32 and iwork.flags.c_contiguous and \
                 iwork.size == self.nsys * liw
         if not ok:
             raise BvodeError(-1, "y/t/istate/rwork/iwork must be contiguous numpy arrays of "
-                                 "float64/float64/int32/float64/int32 with nsys rows")
+                                 "real/real/int32/real/int32 (real = %s) with nsys rows" % REAL.__name__)
 
 
 def lu_test(kind, a, b, ml=0, mu=0, strict=False, device=0):
@@ -430,7 +435,7 @@ class dvode_multi_t:
         touts = _f64(touts).reshape(-1)
         rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
         if y_out is not None:
-            assert y_out.dtype == np.float64 and y_out.flags.c_contiguous
+            assert y_out.dtype == REAL and y_out.flags.c_contiguous
             assert y_out.shape == (touts.size, self.nsys, self.neq)
         _check(_lib.bvode_multi_solve_schedule(self._m, int(neq), _ptr(y), _ptr(t), touts.size, _ptr(touts),
                                                int(itol), _ptr(rtol), _ptr(atol), int(itask), _ptr(istate),

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbvode.so")
+LIB32 = os.path.join(HERE, "libbvode32.so")  # the REAL32 build (-DBVODE_REAL32): strict arithmetic, thread problems
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
@@ -32,10 +33,10 @@ def _sources():
     return [p for p in out if os.path.exists(p)]
 
 
-def is_stale():
-    if not os.path.exists(LIB):
+def is_stale(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(p) > t for p in _sources())
 
 
@@ -67,5 +68,37 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _compile_and_link(nv, units, lib, verbose):
+    procs = []
+    for obj, src, extra in units:
+        cmd = [nv] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out.decode())
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call([nv] + ARCH + ["-shared", "-o", lib] + [os.path.join(OBJ, u[0]) for u in units] + ["-ldl"])
+    return lib
+
+
+def build32(force=False, verbose=False):
+    """libbvode32.so: the same sources with -DBVODE_REAL32 (the reference's REAL32 kind, K:29-31): every
+    `bvode_real` of the C ABI is a float.  Strict arithmetic only (each operation individually rounded, so
+    that the float oracle reproduces it bit for bit) and the thread-per-system problems (units 0, 1, 4, 7)."""
+    if not force and not is_stale(LIB32):
+        return LIB32
+    os.makedirs(OBJ, exist_ok=True)
+    r32 = ["-DBVODE_REAL32"]
+    units = [("capi32.o", "bvode_capi.cu", r32), ("multi32.o", "bvode_multi.cu", r32)]
+    for u in (0, 1, 4, 7):
+        units.append(("reg32_strict_%d.o" % u, "bvode_registry.cu",
+                      r32 + ["-DBVODE_STRICT=1", "-fmad=false", "-DBVODE_UNIT=%d" % u]))
+    return _compile_and_link(_nvcc(), units, LIB32, verbose)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build32(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -43,6 +43,12 @@ static std::mutex g_tab_mutex;
 static void registry_init() {
     std::lock_guard<std::mutex> lock(g_tab_mutex);
     if (g_nproblems != 0) return;
+#if BVODE_REAL_IS_FLOAT
+    // REAL32 (libbvode32.so): strict arithmetic, thread-per-system problems; one table serves both flags
+    const ProblemEntry *ent[4] = {bvode_entry_strict_0(), bvode_entry_strict_1(), bvode_entry_strict_4(), bvode_entry_strict_7()};
+    for (int i = 0; i < 4; i++) g_tab_fast[i] = g_tab_strict[i] = *ent[i];
+    g_nproblems = 4;
+#else
     g_tab_fast[0] = *bvode_entry_fast_0(); g_tab_fast[1] = *bvode_entry_fast_1();
     g_tab_fast[2] = *bvode_entry_fast_2(); g_tab_fast[3] = *bvode_entry_fast_3();
     g_tab_fast[4] = *bvode_entry_fast_4(); g_tab_fast[5] = *bvode_entry_fast_5();
@@ -52,6 +58,7 @@ static void registry_init() {
     g_tab_strict[4] = *bvode_entry_strict_4(); g_tab_strict[5] = *bvode_entry_strict_5();
     g_tab_strict[6] = *bvode_entry_strict_6(); g_tab_strict[7] = *bvode_entry_strict_7();
     g_nproblems = BVODE_NPROBLEMS;
+#endif
 }
 static const ProblemEntry *bvode_registry_fast(int *n) {
     registry_init();
@@ -81,13 +88,13 @@ void bvode_set_error(const std::string &msg) { g_err = msg; }  // for bvode_mult
 
 // ---------------------------------------------------------------- small kernels ----
 // host layout [nsys][n]  <->  device layout [n][nsys]
-__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int nsys,
+__global__ void k_aos_to_soa(const real *__restrict__ aos, real *__restrict__ soa, int nsys,
                              int n) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsys) return;
     for (int i = 0; i < n; i++) soa[(size_t)i * nsys + s] = aos[(size_t)s * n + i];
 }
-__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, int nsys,
+__global__ void k_soa_to_aos(const real *__restrict__ soa, real *__restrict__ aos, int nsys,
                              int n) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsys) return;
@@ -95,20 +102,20 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
 }
 // the same for the systems [s0, s0 + count) of a batch of nsys, nvec consecutive [n][nsys] arrays
 // (grid.y = which array): the chunks of the pipelined host-buffer path
-__global__ void k_aos_to_soa_range(const double *__restrict__ aos, double *__restrict__ soa, int nsys,
+__global__ void k_aos_to_soa_range(const real *__restrict__ aos, real *__restrict__ soa, int nsys,
                                    int n, int s0, int count) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= count) return;
     const size_t g = (size_t)s0 + s;
     for (int i = 0; i < n; i++) soa[(size_t)i * nsys + g] = aos[g * n + i];
 }
-__global__ void k_soa_to_aos_range(const double *__restrict__ soa, double *__restrict__ aos, int nsys,
+__global__ void k_soa_to_aos_range(const real *__restrict__ soa, real *__restrict__ aos, int nsys,
                                    int n, int s0, int count) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= count) return;
     const size_t g = (size_t)s0 + s, v = blockIdx.y;
-    const double *src = soa + v * (size_t)n * nsys;
-    double *dst = aos + v * (size_t)n * nsys;
+    const real *src = soa + v * (size_t)n * nsys;
+    real *dst = aos + v * (size_t)n * nsys;
     for (int i = 0; i < n; i++) dst[g * n + i] = src[(size_t)i * nsys + g];
 }
 __global__ void k_isoa_to_aos_range(const int *__restrict__ soa, int *__restrict__ aos, int nsys,
@@ -124,6 +131,7 @@ __global__ void k_isoa_to_aos(const int *__restrict__ soa, int *__restrict__ aos
     if (s >= nsys) return;
     for (int i = 0; i < n; i++) aos[(size_t)s * n + i] = soa[(size_t)i * nsys + s];
 }
+// REALIFY-OFF
 // DFMA peak: 8 independent chains per thread, 1024 threads per block, 4 blocks per SM
 __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// REALIFY-ON
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // -------------------------------------------------------------------- registry ----
@@ -213,21 +222,21 @@ int bvode_create(bvode_solver **out, int problem, int nsys, int device, unsigned
     s->npar = s->pe->npar;
     const size_t ns = (size_t)nsys;
     cudaError_t err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_params, sizeof(double) * ns * (s->npar > 0 ? s->npar : 1));
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_y, sizeof(double) * ns * s->neq);
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_t, sizeof(double) * ns);
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_tout_ps, sizeof(double) * ns);
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_tol, sizeof(double) * 2 * s->neq);
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_rout, sizeof(double) * 4 * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_params, sizeof(real) * ns * (s->npar > 0 ? s->npar : 1));
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_y, sizeof(real) * ns * s->neq);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_t, sizeof(real) * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_tout_ps, sizeof(real) * ns);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_tol, sizeof(real) * 2 * s->neq);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_rout, sizeof(real) * 4 * ns);
     if (err == cudaSuccess) err = cudaMalloc(&s->d_istate, sizeof(int) * ns);
     if (err == cudaSuccess) err = cudaMalloc(&s->d_iout, sizeof(int) * 12 * ns);
     if (err == cudaSuccess) err = cudaMalloc(&s->d_iaos, sizeof(int) * 12 * ns);
     s->aos_cap = ns * (size_t)(s->neq > s->npar ? s->neq : s->npar);
     if (s->aos_cap < 4 * ns) s->aos_cap = 4 * ns;
-    if (err == cudaSuccess) err = cudaMalloc(&s->d_aos, sizeof(double) * s->aos_cap);
-    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_rout, 0, sizeof(double) * 4 * ns, s->stream);
+    if (err == cudaSuccess) err = cudaMalloc(&s->d_aos, sizeof(real) * s->aos_cap);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_rout, 0, sizeof(real) * 4 * ns, s->stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(s->d_iout, 0, sizeof(int) * 12 * ns, s->stream);
-    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_params, 0, sizeof(double) * ns * (s->npar > 0 ? s->npar : 1), s->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(s->d_params, 0, sizeof(real) * ns * (s->npar > 0 ? s->npar : 1), s->stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(s->d_istate, 0, sizeof(int) * ns, s->stream);
     // the handle's stream does not synchronise with the caller's streams (cudaStreamNonBlocking):
     // the buffers must be ready before a first launch on any of them
@@ -260,23 +269,23 @@ void bvode_destroy(bvode_solver *s) {
     delete s;
 }
 
-int bvode_set_params(bvode_solver *s, const double *params) {
+int bvode_set_params(bvode_solver *s, const real *params) {
     if (!s || (!params && s->npar > 0)) return BVODE_EINVAL;
     if (s->npar == 0) return BVODE_OK;
     if (s->params_external) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t ns = (size_t)s->nsys;
-    CUDA_TRY(cudaMemcpyAsync(s->d_aos, params, sizeof(double) * ns * s->npar, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_aos, params, sizeof(real) * ns * s->npar, cudaMemcpyHostToDevice, s->stream));
     k_aos_to_soa<<<cdiv(s->nsys, 256), 256, 0, s->stream>>>(s->d_aos, s->d_params, s->nsys, s->npar);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return BVODE_OK;
 }
 
-int bvode_set_params_device(bvode_solver *s, const double *params_device) {
+int bvode_set_params_device(bvode_solver *s, const real *params_device) {
     if (!s || !params_device) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
-    CUDA_TRY(cudaMemcpyAsync(s->d_params, params_device, sizeof(double) * (size_t)s->nsys * s->npar,
+    CUDA_TRY(cudaMemcpyAsync(s->d_params, params_device, sizeof(real) * (size_t)s->nsys * s->npar,
                              cudaMemcpyDeviceToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return BVODE_OK;
@@ -286,7 +295,7 @@ int bvode_set_params_device(bvode_solver *s, const double *params_device) {
 struct Checked {
     BvOpts o;
     int lenrw, leniw;
-    std::vector<double> tol;  // rtol[neq] then atol[neq], expanded according to itol
+    std::vector<real> tol;  // rtol[neq] then atol[neq], expanded according to itol
 };
 
 // Work-array lengths the reference would need, M:1246-1273 (reported in iwork(17:18)).
@@ -306,9 +315,9 @@ static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, 
 
 // The optional inputs of one solver instance (M:729-751), defaulted as in M:1174-1238: rw / iw are that
 // instance's rwork(1:20) / iwork(1:30) header.  Returns nullptr, or the text of the input error.
-static const char *read_optional_inputs(int meth, int itask, int iopt, const double *rw, const int *iw, BvOpts *o) {
+static const char *read_optional_inputs(int meth, int itask, int iopt, const real *rw, const int *iw, BvOpts *o) {
     const int mord = (meth == 1) ? 12 : 5;
-    o->tcrit = ((itask == 4 || itask == 5) && rw) ? rw[0] : 0.0;
+    o->tcrit = ((itask == 4 || itask == 5) && rw) ? rw[0] : BV_R(0.0);
     if (iopt == 1) {
         o->maxord = iw[4];
         if (o->maxord < 0) return "maxord < 0";
@@ -321,25 +330,25 @@ static const char *read_optional_inputs(int meth, int itask, int iopt, const dou
         if (o->mxhnil < 0) return "mxhnil < 0";
         if (o->mxhnil == 0) o->mxhnil = 10;
         o->h0 = rw[4];
-        const double hmax = rw[5];
-        if (hmax < 0.0) return "hmax < 0";
-        o->hmax_inv = hmax > 0.0 ? 1.0 / hmax : 0.0;
+        const real hmax = rw[5];
+        if (hmax < BV_R(0.0)) return "hmax < 0";
+        o->hmax_inv = hmax > BV_R(0.0) ? BV_R(1.0) / hmax : BV_R(0.0);
         o->hmin = rw[6];
-        if (o->hmin < 0.0) return "hmin < 0";
+        if (o->hmin < BV_R(0.0)) return "hmin < 0";
     } else {
         o->maxord = mord;
         o->mxstep = 500;
         o->mxhnil = 10;
-        o->h0 = 0.0;
-        o->hmax_inv = 0.0;
-        o->hmin = 0.0;
+        o->h0 = BV_R(0.0);
+        o->hmax_inv = BV_R(0.0);
+        o->hmin = BV_R(0.0);
     }
     return nullptr;
 }
 
 // Returns BVODE_OK, or the error class; mirrors M:1092-1303 for the batch-uniform inputs.
-static int check_args(const bvode_solver *s, int neq, int itol, const double *rtol,
-                      const double *atol, int itask, int iopt, const double *rwork0,
+static int check_args(const bvode_solver *s, int neq, int itol, const real *rtol,
+                      const real *atol, int itask, int iopt, const real *rwork0,
                       const int *iwork0, int lrw, int liw, bool have_headers, int mf,
                       Checked *c) {
     if (neq != s->neq) { g_err = "neq does not match the problem"; return BVODE_EINVAL; }
@@ -370,14 +379,15 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
     o.itask = itask;
     o.jreset = 0;
     o.stash = 0;
+    o.lmaxchg = 0;
     if (iopt == 1 && (!rwork0 || !iwork0)) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
     if (const char *msg = read_optional_inputs(meth, itask, iopt, rwork0, iwork0, &o)) { g_err = msg; return BVODE_EINVAL; }
     c->tol.resize(2 * (size_t)neq);
     for (int i = 0; i < neq; i++) {
-        const double r = (itol >= 3) ? rtol[i] : rtol[0];
-        const double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
-        if (r < 0.0) { g_err = "rtol < 0"; return BVODE_EINVAL; }
-        if (a < 0.0) { g_err = "atol < 0"; return BVODE_EINVAL; }
+        const real r = (itol >= 3) ? rtol[i] : rtol[0];
+        const real a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        if (r < BV_R(0.0)) { g_err = "rtol < 0"; return BVODE_EINVAL; }
+        if (a < BV_R(0.0)) { g_err = "atol < 0"; return BVODE_EINVAL; }
         c->tol[i] = r;
         c->tol[neq + i] = a;
     }
@@ -390,29 +400,29 @@ static int check_args(const bvode_solver *s, int neq, int itol, const double *rt
 // neq according to itol, and the optional inputs of system i in row i of rwork / iwork.  A system whose
 // row is illegal gets istate = -3 and is skipped (M:1120-1303 does that per instance); with a
 // device-resident istate the call is refused instead.  mf, ml / mu, itol, itask, iopt stay batch-uniform.
-static int prepare_per_system(bvode_solver *s, const Checked &c, int neq, int itol, const double *rtol,
-                              const double *atol, int itask, int iopt, const double *rwork, int lrw,
+static int prepare_per_system(bvode_solver *s, const Checked &c, int neq, int itol, const real *rtol,
+                              const real *atol, int itask, int iopt, const real *rwork, int lrw,
                               const int *iwork, int liw, int *istate_host, bool restart3, int mf,
                               cudaStream_t st) {
     const size_t ns = (size_t)s->nsys;
     if (iopt == 1 && (!rwork || !iwork || lrw < 20 || liw < 30)) { g_err = "iopt = 1 needs rwork[nsys][lrw >= 20] and iwork[nsys][liw >= 30]"; return BVODE_EINVAL; }
     if ((itask == 4 || itask == 5) && (!rwork || lrw < 1)) { g_err = "itask 4/5 needs rwork(1) = tcrit in every row"; return BVODE_EINVAL; }
     if (!s->d_tol_ps) {
-        CUDA_TRY(cudaMalloc(&s->d_tol_ps, sizeof(double) * 2 * neq * ns));
-        CUDA_TRY(cudaMalloc(&s->d_optd_ps, sizeof(double) * 4 * ns));
+        CUDA_TRY(cudaMalloc(&s->d_tol_ps, sizeof(real) * 2 * neq * ns));
+        CUDA_TRY(cudaMalloc(&s->d_optd_ps, sizeof(real) * 4 * ns));
         CUDA_TRY(cudaMalloc(&s->d_opti_ps, sizeof(int) * 3 * ns));
     }
     const int nr = (itol >= 3) ? neq : 1, na = (itol == 2 || itol == 4) ? neq : 1;
     const int meth = abs(mf) / 10;
-    std::vector<double> tol(2 * (size_t)neq * ns), od(4 * ns);
+    std::vector<real> tol(2 * (size_t)neq * ns), od(4 * ns);
     std::vector<int> oi(3 * ns);
     const bool have_prev = s->maxord_ps.size() == ns;
     std::vector<int> maxord_new(ns);
     for (size_t i = 0; i < ns; i++) {
         bool bad = false;
         for (int k = 0; k < neq; k++) {
-            const double r = rtol[i * nr + (nr > 1 ? k : 0)], a = atol[i * na + (na > 1 ? k : 0)];
-            if (!(r >= 0.0) || !(a >= 0.0)) bad = true;
+            const real r = rtol[i * nr + (nr > 1 ? k : 0)], a = atol[i * na + (na > 1 ? k : 0)];
+            if (!(r >= BV_R(0.0)) || !(a >= BV_R(0.0))) bad = true;
             tol[(size_t)k * ns + i] = r;
             tol[(size_t)(neq + k) * ns + i] = a;
         }
@@ -427,12 +437,13 @@ static int prepare_per_system(bvode_solver *s, const Checked &c, int neq, int it
         od[i] = o.h0; od[ns + i] = o.hmax_inv; od[2 * ns + i] = o.hmin; od[3 * ns + i] = o.tcrit;
         const int prev = have_prev ? s->maxord_ps[i] : s->maxord;
         oi[i] = o.maxord; oi[ns + i] = o.mxstep;
-        oi[2 * ns + i] = (c.o.jreset || (restart3 && mf > 0 && o.maxord != prev)) ? 1 : 0;
+        oi[2 * ns + i] = ((c.o.jreset || (restart3 && mf > 0 && o.maxord != prev)) ? 1 : 0) |
+                         ((restart3 && (c.o.lmaxchg || o.maxord != prev)) ? 2 : 0);
         maxord_new[i] = o.maxord;
     }
     s->maxord_ps.swap(maxord_new);
-    CUDA_TRY(cudaMemcpyAsync(s->d_tol_ps, tol.data(), sizeof(double) * tol.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s->d_optd_ps, od.data(), sizeof(double) * od.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_tol_ps, tol.data(), sizeof(real) * tol.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_optd_ps, od.data(), sizeof(real) * od.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->d_opti_ps, oi.data(), sizeof(int) * oi.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // the vectors go out of scope
     return BVODE_OK;
@@ -445,9 +456,9 @@ static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
     s->d_state = nullptr;
     s->i_state = nullptr;
     s->pe->state_size(mf, ml, mu, (size_t)s->nsys, &s->nd, &s->ni);
-    CUDA_TRY(cudaMalloc(&s->d_state, sizeof(double) * s->nd));
+    CUDA_TRY(cudaMalloc(&s->d_state, sizeof(real) * s->nd));
     CUDA_TRY(cudaMalloc(&s->i_state, sizeof(int) * s->ni));
-    CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(double) * s->nd, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(real) * s->nd, s->stream));
     CUDA_TRY(cudaMemsetAsync(s->i_state, 0, sizeof(int) * s->ni, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->mf = mf;
@@ -457,9 +468,9 @@ static int ensure_state(bvode_solver *s, int mf, int ml, int mu) {
 }
 
 // Launch the integration for touts[0..nout) on device-resident SoA buffers.
-static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, double *d_t,
-                      int *d_istate, int nout, const double *touts, const double *d_tout_ps,
-                      double *d_yout, cudaStream_t st, bool general, int sys0 = 0, int count = -1,
+static int run_device(bvode_solver *s, const Checked &c, int mf, real *d_y, real *d_t,
+                      int *d_istate, int nout, const real *touts, const real *d_tout_ps,
+                      real *d_yout, cudaStream_t st, bool general, int sys0 = 0, int count = -1,
                       int lane = 0, bool upload_tol = true) {
     if (count < 0) count = s->nsys;
     if (nout > 1 && !(c.o.itask == 1 || c.o.itask == 4)) {
@@ -473,7 +484,7 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
     s->last_istate = d_istate;
     s->last_stream = st;
     if (upload_tol)
-        CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(),
+        CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(real) * c.tol.size(),
                                  cudaMemcpyHostToDevice, st));
     for (int k0 = 0; k0 < nout; k0 += BVODE_MAX_NOUT) {
         KArgs a;
@@ -522,10 +533,10 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, double *d_y, do
     return BVODE_OK;
 }
 
-static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
-                      const double *touts, const double *tout_ps, int itol, const double *rtol,
-                      const double *atol, int itask, int *istate, int iopt, double *rwork,
-                      int lrw, int *iwork, int liw, int mf, double *y_out, long long yout_sys_stride = 0) {
+static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
+                      const real *touts, const real *tout_ps, int itol, const real *rtol,
+                      const real *atol, int itask, int *istate, int iopt, real *rwork,
+                      int lrw, int *iwork, int liw, int mf, real *y_out, long long yout_sys_stride = 0) {
     if (!s || !y || !t || !istate || nout < 1 || (!touts && !tout_ps)) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const int nsys = s->nsys;
@@ -563,16 +574,17 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         }
     }
     if (!(s->flags & BVODE_FLAG_PER_SYSTEM) && n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
+    if (n3 != 0 && (c.o.maxord != s->maxord || abs(s->mf) / 10 != abs(mf) / 10)) c.o.lmaxchg = 1;
     if (mf_changed) {
         // M:999-1046 at istate = 3: a new miter / jsv.  The state moves into the layout of the new
         // method flag; the Newton matrix and the saved Jacobian are rebuilt at the restart.
         size_t nd = 0, ni = 0;
         s->pe->state_size(mf, c.o.ml, c.o.mu, (size_t)nsys, &nd, &ni);
-        double *dn = nullptr;
+        real *dn = nullptr;
         int *in = nullptr;
-        CUDA_TRY(cudaMalloc(&dn, sizeof(double) * nd));
+        CUDA_TRY(cudaMalloc(&dn, sizeof(real) * nd));
         CUDA_TRY(cudaMalloc(&in, sizeof(int) * ni));
-        CUDA_TRY(cudaMemsetAsync(dn, 0, sizeof(double) * nd, s->stream));
+        CUDA_TRY(cudaMemsetAsync(dn, 0, sizeof(real) * nd, s->stream));
         CUDA_TRY(cudaMemsetAsync(in, 0, sizeof(int) * ni, s->stream));
         const int e = s->pe->state_convert ? s->pe->state_convert(s->mf, mf, c.o.ml, c.o.mu, (size_t)nsys, s->d_state,
                                                                   s->i_state, dn, in, s->stream)
@@ -603,29 +615,29 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     }
     cudaStream_t st = s->stream;
     const int TB = 256;
-    const double *d_tout_ps = tout_ps ? s->d_tout_ps : nullptr;
-    double *d_yout = nullptr;
+    const real *d_tout_ps = tout_ps ? s->d_tout_ps : nullptr;
+    real *d_yout = nullptr;
     if (y_out) {
         const size_t need = ns * neq * nout;
         if (need > s->yout_cap) {
             cudaFree(s->d_yout);
             s->d_yout = nullptr;
             s->yout_cap = 0;
-            CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(double) * need));
+            CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(real) * need));
             s->yout_cap = need;
         }
         if (need > s->yout_aos_cap) {
             cudaFree(s->d_yout_aos);
             s->d_yout_aos = nullptr;
             s->yout_aos_cap = 0;
-            CUDA_TRY(cudaMalloc(&s->d_yout_aos, sizeof(double) * need));
+            CUDA_TRY(cudaMalloc(&s->d_yout_aos, sizeof(real) * need));
             s->yout_aos_cap = need;
         }
         d_yout = s->d_yout;
     }
     rc = ensure_state(s, mf, c.o.ml, c.o.mu);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(double) * c.tol.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_tol, c.tol.data(), sizeof(real) * c.tol.size(), cudaMemcpyHostToDevice, st));
     if (s->flags & BVODE_FLAG_PER_SYSTEM) {
         rc = prepare_per_system(s, c, neq, itol, rtol, atol, itask, iopt, rwork, lrw, iwork, liw, istate, n3 != 0, mf, st);
         if (rc) return rc;
@@ -635,8 +647,8 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     // one copy into pinned staging, and the host scatters a chunk's rows into the caller's rwork / iwork
     // headers while the GPU works on the next chunks
     if (have_headers) {
-        if (!s->d_rout_aos) CUDA_TRY(cudaMalloc(&s->d_rout_aos, sizeof(double) * 4 * ns));
-        if (!s->h_rout) CUDA_TRY(cudaMallocHost(&s->h_rout, sizeof(double) * 4 * ns));
+        if (!s->d_rout_aos) CUDA_TRY(cudaMalloc(&s->d_rout_aos, sizeof(real) * 4 * ns));
+        if (!s->h_rout) CUDA_TRY(cudaMallocHost(&s->h_rout, sizeof(real) * 4 * ns));
         if (!s->h_iout) CUDA_TRY(cudaMallocHost(&s->h_iout, sizeof(int) * 12 * ns));
     }
     // The batch goes through in chunks on two streams: the copies of one chunk (inputs in, every
@@ -645,7 +657,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     const int kChunk = 1 << 17;
     const int nchunks = (nsys >= 2 * kChunk && nout <= BVODE_MAX_NOUT) ? cdiv(nsys, kChunk) : 1;
     if (nchunks > 1 && !s->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    const double tout1 = 0.0;
+    const real tout1 = BV_R(0.0);
     for (int ch = 0; ch < nchunks; ch++) {
         const int s0 = (int)((long long)nsys * ch / nchunks), s1 = (int)((long long)nsys * (ch + 1) / nchunks);
         const int cnt = s1 - s0;
@@ -654,14 +666,14 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         // host -> device.  On continuation calls y and t are outputs only (M:608-618).
         CUDA_TRY(cudaMemcpyAsync(s->d_istate + s0, istate + s0, sizeof(int) * cnt, cudaMemcpyHostToDevice, cs));
         if (any_first) {
-            CUDA_TRY(cudaMemcpyAsync(s->d_aos + (size_t)s0 * neq, y + (size_t)s0 * neq, sizeof(double) * cnt * neq,
+            CUDA_TRY(cudaMemcpyAsync(s->d_aos + (size_t)s0 * neq, y + (size_t)s0 * neq, sizeof(real) * cnt * neq,
                                      cudaMemcpyHostToDevice, cs));
             k_aos_to_soa_range<<<cdiv(cnt, TB), TB, 0, cs>>>(s->d_aos, s->d_y, nsys, neq, s0, cnt);
             s->last_launches++;
-            CUDA_TRY(cudaMemcpyAsync(s->d_t + s0, t + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(s->d_t + s0, t + s0, sizeof(real) * cnt, cudaMemcpyHostToDevice, cs));
         }
         if (tout_ps)
-            CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps + s0, tout_ps + s0, sizeof(double) * cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps + s0, tout_ps + s0, sizeof(real) * cnt, cudaMemcpyHostToDevice, cs));
         rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, cs,
                         itask != 1 || n3 != 0, s0, cnt, lane, false);
         if (rc != BVODE_OK) {  // nothing may still be writing into the caller's buffers when we return
@@ -672,15 +684,15 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
         // device -> host
         k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), 1), TB, 0, cs>>>(s->d_y, s->d_aos, nsys, neq, s0, cnt);
         s->last_launches++;
-        CUDA_TRY(cudaMemcpyAsync(y + (size_t)s0 * neq, s->d_aos + (size_t)s0 * neq, sizeof(double) * cnt * neq,
+        CUDA_TRY(cudaMemcpyAsync(y + (size_t)s0 * neq, s->d_aos + (size_t)s0 * neq, sizeof(real) * cnt * neq,
                                  cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaMemcpyAsync(t + s0, s->d_t + s0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(t + s0, s->d_t + s0, sizeof(real) * cnt, cudaMemcpyDeviceToHost, cs));
         CUDA_TRY(cudaMemcpyAsync(istate + s0, s->d_istate + s0, sizeof(int) * cnt, cudaMemcpyDeviceToHost, cs));
         if (have_headers) {
             k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), 1), TB, 0, cs>>>(s->d_rout, s->d_rout_aos, nsys, 4, s0, cnt);
             k_isoa_to_aos_range<<<cdiv(cnt, TB), TB, 0, cs>>>(s->d_iout, s->d_iaos, nsys, 12, s0, cnt);
             s->last_launches += 2;
-            CUDA_TRY(cudaMemcpyAsync(s->h_rout + (size_t)s0 * 4, s->d_rout_aos + (size_t)s0 * 4, sizeof(double) * 4 * cnt,
+            CUDA_TRY(cudaMemcpyAsync(s->h_rout + (size_t)s0 * 4, s->d_rout_aos + (size_t)s0 * 4, sizeof(real) * 4 * cnt,
                                      cudaMemcpyDeviceToHost, cs));
             CUDA_TRY(cudaMemcpyAsync(s->h_iout + (size_t)s0 * 12, s->d_iaos + (size_t)s0 * 12, sizeof(int) * 12 * cnt,
                                      cudaMemcpyDeviceToHost, cs));
@@ -691,7 +703,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
             const size_t hs = yout_sys_stride > 0 ? (size_t)yout_sys_stride : ns;  // systems per output slab of y_out
             for (int k = 0; k < nout; k++) {
                 const size_t off = ((size_t)k * ns + s0) * neq, hoff = ((size_t)k * hs + s0) * neq;
-                CUDA_TRY(cudaMemcpyAsync(y_out + hoff, s->d_yout_aos + off, sizeof(double) * cnt * neq,
+                CUDA_TRY(cudaMemcpyAsync(y_out + hoff, s->d_yout_aos + off, sizeof(real) * cnt * neq,
                                          cudaMemcpyDeviceToHost, cs));
             }
         }
@@ -711,7 +723,7 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
             const size_t s0 = (size_t)((long long)nsys * ch / nchunks), s1 = (size_t)((long long)nsys * (ch + 1) / nchunks);
             CUDA_TRY(cudaEventSynchronize(s->chunk_done[ch]));
             for (size_t i = s0; i < s1; i++) {
-                memcpy(rwork + i * lrw + 10, s->h_rout + i * 4, sizeof(double) * 4);
+                memcpy(rwork + i * lrw + 10, s->h_rout + i * 4, sizeof(real) * 4);
                 memcpy(iwork + i * liw + 10, s->h_iout + i * 12, sizeof(int) * 12);
             }
         }
@@ -722,19 +734,19 @@ static int solve_host(bvode_solver *s, int neq, double *y, double *t, int nout,
     return BVODE_OK;
 }
 
-int bvode_solve(bvode_solver *s, int neq, double *y, double *t, const double *tout,
-                int tout_per_system, int itol, const double *rtol, const double *atol, int itask,
-                int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw, int mf) {
+int bvode_solve(bvode_solver *s, int neq, real *y, real *t, const real *tout,
+                int tout_per_system, int itol, const real *rtol, const real *atol, int itask,
+                int *istate, int iopt, real *rwork, int lrw, int *iwork, int liw, int mf) {
     if (!tout) return BVODE_EINVAL;
     return solve_host(s, neq, y, t, 1, tout_per_system ? nullptr : tout,
                       tout_per_system ? tout : nullptr, itol, rtol, atol, itask, istate, iopt,
                       rwork, lrw, iwork, liw, mf, nullptr);
 }
 
-int bvode_solve_schedule(bvode_solver *s, int neq, double *y, double *t, int nout,
-                         const double *touts, int itol, const double *rtol, const double *atol,
-                         int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork,
-                         int liw, int mf, double *y_out) {
+int bvode_solve_schedule(bvode_solver *s, int neq, real *y, real *t, int nout,
+                         const real *touts, int itol, const real *rtol, const real *atol,
+                         int itask, int *istate, int iopt, real *rwork, int lrw, int *iwork,
+                         int liw, int mf, real *y_out) {
     return solve_host(s, neq, y, t, nout, touts, nullptr, itol, rtol, atol, itask, istate, iopt,
                       rwork, lrw, iwork, liw, mf, y_out);
 }
@@ -743,8 +755,8 @@ int bvode_solve_schedule(bvode_solver *s, int neq, double *y, double *t, int nou
 // made per system here.  A handle whose state exists is therefore bound to its mf / ml / mu: a call
 // with other values would silently re-initialise systems that continue with istate = 2, and is refused
 // (bvode_reset drops the state when a new problem is meant).
-static int device_path_prepare(bvode_solver *s, const Checked &c, int neq, int itol, const double *rtol,
-                               const double *atol, int itask, int iopt, const double *rwork_opts,
+static int device_path_prepare(bvode_solver *s, const Checked &c, int neq, int itol, const real *rtol,
+                               const real *atol, int itask, int iopt, const real *rwork_opts,
                                const int *iwork_opts, int mf, cudaStream_t st) {
     if (s->d_state && (s->mf != mf || s->ml != c.o.ml || s->mu != c.o.mu)) {
         g_err = "device-resident solve with another mf / ml / mu than the handle's state was built for "
@@ -771,19 +783,19 @@ int bvode_reset(bvode_solver *s) {
     return BVODE_OK;
 }
 
-int bvode_solve_schedule_strided(bvode_solver *s, int neq, double *y, double *t, int nout, const double *touts,
-                                 const double *tout_ps, int itol, const double *rtol, const double *atol, int itask,
-                                 int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw, int mf,
-                                 double *y_out, long long yout_sys_stride) {
+int bvode_solve_schedule_strided(bvode_solver *s, int neq, real *y, real *t, int nout, const real *touts,
+                                 const real *tout_ps, int itol, const real *rtol, const real *atol, int itask,
+                                 int *istate, int iopt, real *rwork, int lrw, int *iwork, int liw, int mf,
+                                 real *y_out, long long yout_sys_stride) {
     return solve_host(s, neq, y, t, nout, touts, tout_ps, itol, rtol, atol, itask, istate, iopt, rwork, lrw, iwork,
                       liw, mf, y_out, yout_sys_stride);
 }
 
-int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, double *t_device,
-                                int nout, const double *touts, int itol, const double *rtol,
-                                const double *atol, int itask, int *istate_device, int iopt,
-                                const double *rwork_opts, const int *iwork_opts, int mf,
-                                double *y_out_device, void *stream) {
+int bvode_solve_schedule_device(bvode_solver *s, int neq, real *y_device, real *t_device,
+                                int nout, const real *touts, int itol, const real *rtol,
+                                const real *atol, int itask, int *istate_device, int iopt,
+                                const real *rwork_opts, const int *iwork_opts, int mf,
+                                real *y_out_device, void *stream) {
     if (!s || !y_device || !t_device || !istate_device || !touts || nout < 1) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     s->last_launches = 0;
@@ -804,9 +816,9 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, doub
     return BVODE_OK;
 }
 
-int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_device,
-                       const double *tout_device, int itol, const double *rtol, const double *atol,
-                       int itask, int *istate_device, int iopt, const double *rwork_opts,
+int bvode_solve_device(bvode_solver *s, int neq, real *y_device, real *t_device,
+                       const real *tout_device, int itol, const real *rtol, const real *atol,
+                       int itask, int *istate_device, int iopt, const real *rwork_opts,
                        const int *iwork_opts, int mf, void *stream) {
     if (!s || !y_device || !t_device || !istate_device || !tout_device) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
@@ -815,7 +827,7 @@ int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_dev
     int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, 20, 30,
                         false, mf, &c);
     if (rc != BVODE_OK) return rc;
-    const double tout1 = 0.0;  // unused: every system has its own tout
+    const real tout1 = BV_R(0.0);  // unused: every system has its own tout
     rc = device_path_prepare(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, mf, (cudaStream_t)stream);
     if (rc != BVODE_OK) return rc;
     rc = run_device(s, c, mf, y_device, t_device, istate_device, 1, &tout1, tout_device, nullptr,
@@ -829,14 +841,14 @@ int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_dev
 
 int bvode_last_launch_count(const bvode_solver *s) { return s ? s->last_launches : 0; }
 
-int bvode_get_stats(bvode_solver *s, double *rout, int *iout) {
+int bvode_get_stats(bvode_solver *s, real *rout, int *iout) {
     if (!s) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t ns = (size_t)s->nsys;
     const int TB = 256;
     if (rout) {
         k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, s->stream>>>(s->d_rout, s->d_aos, s->nsys, 4);
-        CUDA_TRY(cudaMemcpyAsync(rout, s->d_aos, sizeof(double) * 4 * ns, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(rout, s->d_aos, sizeof(real) * 4 * ns, cudaMemcpyDeviceToHost, s->stream));
     }
     if (iout) {
         k_isoa_to_aos<<<cdiv(s->nsys, TB), TB, 0, s->stream>>>(s->d_iout, s->d_iaos, s->nsys, 12);
@@ -846,7 +858,7 @@ int bvode_get_stats(bvode_solver *s, double *rout, int *iout) {
     return BVODE_OK;
 }
 
-int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, double *dky,
+int bvode_dvindy(bvode_solver *s, const real *t, int t_per_system, int k, real *dky,
                  int *iflag) {
     if (!s || !t || !dky || !iflag) return BVODE_EINVAL;
     if (!s->d_state) { g_err = "dvindy before any successful solve"; return BVODE_EINVAL; }
@@ -861,7 +873,7 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
     a.ml = s->ml;
     a.mu = s->mu;
     if (t_per_system) {
-        CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, t, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps, t, sizeof(real) * ns, cudaMemcpyHostToDevice, st));
         a.t_ps = s->d_tout_ps;
     } else {
         a.t = t[0];
@@ -874,7 +886,7 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
         cudaFree(s->d_yout);
         s->d_yout = nullptr;
         s->yout_cap = 0;
-        CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(double) * need));
+        CUDA_TRY(cudaMalloc(&s->d_yout, sizeof(real) * need));
         s->yout_cap = need;
     }
     a.dky = s->d_yout;
@@ -882,7 +894,7 @@ int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, doub
     const int e = s->pe->launch_dky(s->mf, a, st);
     if (e != 0) { g_err = "dvindy kernel launch failed"; return e == -1000 ? BVODE_ENOTIMPL : BVODE_ECUDA; }
     k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, st>>>(s->d_yout, s->d_aos, s->nsys, s->neq);
-    CUDA_TRY(cudaMemcpyAsync(dky, s->d_aos, sizeof(double) * ns * s->neq, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dky, s->d_aos, sizeof(real) * ns * s->neq, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(iflag, s->d_iaos, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -900,8 +912,8 @@ struct SavHeader {
 static const int kSavMagic = 0x62766f65;  // "bvoe": layout 2 (layout 1 had no istate / t / y / maxord / mxstep)
 static size_t sav_bytes(const bvode_solver *s, size_t nd, size_t ni) {
     const size_t ns = (size_t)s->nsys;
-    return sizeof(SavHeader) + sizeof(double) * nd + sizeof(int) * ni + sizeof(double) * 4 * ns +
-           sizeof(int) * 12 * ns + sizeof(int) * ns + sizeof(double) * ns + sizeof(double) * ns * s->neq;
+    return sizeof(SavHeader) + sizeof(real) * nd + sizeof(int) * ni + sizeof(real) * 4 * ns +
+           sizeof(int) * 12 * ns + sizeof(int) * ns + sizeof(real) * ns + sizeof(real) * ns * s->neq;
 }
 long long bvode_state_bytes(const bvode_solver *s) {
     if (!s || !s->d_state) return 0;
@@ -940,9 +952,9 @@ int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job) {
     p += sizeof(SavHeader);
     const size_t ns = (size_t)s->nsys;
     struct { void *d; size_t n; } parts[7] = {
-        {s->d_state, sizeof(double) * s->nd}, {s->i_state, sizeof(int) * s->ni},
-        {s->d_rout, sizeof(double) * 4 * ns}, {s->d_iout, sizeof(int) * 12 * ns},
-        {s->d_istate, sizeof(int) * ns}, {s->d_t, sizeof(double) * ns}, {s->d_y, sizeof(double) * ns * s->neq}};
+        {s->d_state, sizeof(real) * s->nd}, {s->i_state, sizeof(int) * s->ni},
+        {s->d_rout, sizeof(real) * 4 * ns}, {s->d_iout, sizeof(int) * 12 * ns},
+        {s->d_istate, sizeof(int) * ns}, {s->d_t, sizeof(real) * ns}, {s->d_y, sizeof(real) * ns * s->neq}};
     for (auto &q : parts) {
         if (job == 1) CUDA_TRY(cudaMemcpy(p, q.d, q.n, cudaMemcpyDeviceToHost));
         else CUDA_TRY(cudaMemcpy(q.d, p, q.n, cudaMemcpyHostToDevice));
@@ -970,6 +982,7 @@ int bvode_istate_summary(bvode_solver *s, int counts[8]) {
     return BVODE_OK;
 }
 
+// REALIFY-OFF
 // Fortran D21.13 edit descriptor: 0.dddddddddddddD+ee
 static std::string fmt_d21_13(double x) {
     char buf[64];
@@ -985,21 +998,22 @@ static std::string fmt_d21_13(double x) {
     return out;
 }
 
+// REALIFY-ON
 int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen) {
     if (!s || !buf || buflen < 1 || sys < 0 || sys >= s->nsys) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     const size_t ns = (size_t)s->nsys;
     int ist = 0, imxer = 0;
-    double r[4] = {0, 0, 0, 0};
+    real r[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpy(&ist, s->d_istate + sys, sizeof(int), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 4; k++)
-        CUDA_TRY(cudaMemcpy(&r[k], s->d_rout + k * ns + sys, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&r[k], s->d_rout + k * ns + sys, sizeof(real), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&imxer, s->d_iout + 5 * ns + sys, sizeof(int), cudaMemcpyDeviceToHost));
-    const double hcur = r[1], tcur = r[2], tolsf = r[3];
+    const real hcur = r[1], tcur = r[2], tolsf = r[3];
     auto i1 = [](int v) { char b[64]; snprintf(b, sizeof b, "      in above message,  i1 =%10d\n", v); return std::string(b); };
-    auto r1 = [](double a) { return "      in above message,  r1 =" + fmt_d21_13(a) + "\n"; };
-    auto r12 = [](double a, double b) { return "      in above message,  r1 =" + fmt_d21_13(a) + "   r2 =" + fmt_d21_13(b) + "\n"; };
+    auto r1 = [](real a) { return "      in above message,  r1 =" + fmt_d21_13(a) + "\n"; };
+    auto r12 = [](real a, real b) { return "      in above message,  r1 =" + fmt_d21_13(a) + "   r2 =" + fmt_d21_13(b) + "\n"; };
     std::string m;
     switch (ist) {
     case -1:  // M:1506-1509
@@ -1011,7 +1025,7 @@ int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen) {
             r12(tcur, tolsf);
         break;
     case -3:  // M:1081-1461: the device only sees messages 21, 22, 23-25, 26, 27
-        if (tolsf != 0.0)
+        if (tolsf != BV_R(0.0))
             m = "dvode--  at start of problem, too much accuracy\n      requested for precision of machine:   see tolsf (=r1)\n" + r1(tolsf);
         else
             m = "dvode--  illegal input detected on the device (ewt <= 0, tout too close to t to start,\n"
@@ -1041,23 +1055,29 @@ int bvode_format_message(bvode_solver *s, int sys, char *buf, int buflen) {
 }
 
 // ---- the device LINPACK routines in isolation (csrc/bvode_lutest.cu) ----------------------------
-extern "C" int bvode_lutest_fast(int, int, int, int, int, const double *, const double *, double *, int *, double *, int *);
-extern "C" int bvode_lutest_strict(int, int, int, int, int, const double *, const double *, double *, int *, double *, int *);
-int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const double *a, const double *b, double *afac,
-                  int *ipvt, double *x, int *info, int device, unsigned flags) {
+#if !BVODE_REAL_IS_FLOAT
+extern "C" int bvode_lutest_fast(int, int, int, int, int, const real *, const real *, real *, int *, real *, int *);
+extern "C" int bvode_lutest_strict(int, int, int, int, int, const real *, const real *, real *, int *, real *, int *);
+#endif
+int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const real *a, const real *b, real *afac,
+                  int *ipvt, real *x, int *info, int device, unsigned flags) {
     if (!a || !b || !afac || !ipvt || !x || !info || nmat < 1 || n < 1) return BVODE_EINVAL;
+#if BVODE_REAL_IS_FLOAT
+    g_err = "bvode_lu_test: not part of the REAL32 build";
+    return BVODE_ENOTIMPL;
+#else
     CUDA_TRY(cudaSetDevice(device));
     const size_t na = (size_t)nmat * (kind == 3 ? (size_t)(2 * ml + mu + 1) * n : (size_t)n * n), nb = (size_t)nmat * n;
-    double *da = nullptr, *db = nullptr, *df = nullptr, *dx = nullptr;
+    real *da = nullptr, *db = nullptr, *df = nullptr, *dx = nullptr;
     int *dp = nullptr, *di = nullptr;
-    cudaError_t e = cudaMalloc(&da, sizeof(double) * na);
-    if (e == cudaSuccess) e = cudaMalloc(&df, sizeof(double) * na);
-    if (e == cudaSuccess) e = cudaMalloc(&db, sizeof(double) * nb);
-    if (e == cudaSuccess) e = cudaMalloc(&dx, sizeof(double) * nb);
+    cudaError_t e = cudaMalloc(&da, sizeof(real) * na);
+    if (e == cudaSuccess) e = cudaMalloc(&df, sizeof(real) * na);
+    if (e == cudaSuccess) e = cudaMalloc(&db, sizeof(real) * nb);
+    if (e == cudaSuccess) e = cudaMalloc(&dx, sizeof(real) * nb);
     if (e == cudaSuccess) e = cudaMalloc(&dp, sizeof(int) * nb);
     if (e == cudaSuccess) e = cudaMalloc(&di, sizeof(int) * nmat);
-    if (e == cudaSuccess) e = cudaMemcpy(da, a, sizeof(double) * na, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(db, b, sizeof(double) * nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, sizeof(real) * na, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, sizeof(real) * nb, cudaMemcpyHostToDevice);
     int rc = BVODE_OK;
     if (e == cudaSuccess) {
         const int r = (flags & BVODE_FLAG_STRICT) ? bvode_lutest_strict(kind, n, ml, mu, nmat, da, db, df, dp, dx, di)
@@ -1067,16 +1087,18 @@ int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const double *a, co
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && rc == BVODE_OK) {
-        e = cudaMemcpy(afac, df, sizeof(double) * na, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(x, dx, sizeof(double) * nb, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(afac, df, sizeof(real) * na, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(x, dx, sizeof(real) * nb, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(ipvt, dp, sizeof(int) * nb, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(info, di, sizeof(int) * nmat, cudaMemcpyDeviceToHost);
     }
     cudaFree(da); cudaFree(db); cudaFree(df); cudaFree(dx); cudaFree(dp); cudaFree(di);
     if (e != cudaSuccess) { g_err = std::string("bvode_lu_test: ") + cudaGetErrorString(e); return BVODE_ECUDA; }
     return rc;
+#endif
 }
 
+// REALIFY-OFF
 int bvode_measure_fp64_peak(int device, double *tflops) {
     if (!tflops) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(device));

@@ -15,31 +15,31 @@ struct bvode_solver {
     int maxord = 0;  // of the last call (istate = 3 may change it)
     int mxstep = 500;
     size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
-    double *d_state = nullptr;
+    real *d_state = nullptr;
     int *i_state = nullptr;
     // batch buffers, SoA on the device
-    double *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
+    real *d_params = nullptr, *d_y = nullptr, *d_t = nullptr, *d_tol = nullptr,
            *d_rout = nullptr, *d_aos = nullptr, *d_yout = nullptr, *d_tout_ps = nullptr;
     int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
     int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels); one per stream
     cudaStream_t stream2 = nullptr;  // second stream of the pipelined host-buffer path
-    double *d_yout_aos = nullptr;    // [nout][nsys][neq] staging of the output points in host layout
+    real *d_yout_aos = nullptr;    // [nout][nsys][neq] staging of the output points in host layout
     size_t yout_aos_cap = 0;
     size_t aos_cap = 0, yout_cap = 0;
     bool params_external = false;
     int last_launches = 0;
     // ---- per-system tolerances / optional inputs (BVODE_FLAG_PER_SYSTEM)
-    double *d_tol_ps = nullptr, *d_optd_ps = nullptr;
+    real *d_tol_ps = nullptr, *d_optd_ps = nullptr;
     int *d_opti_ps = nullptr;
     std::vector<int> maxord_ps;      // per-system maxord of the last call (istate = 3 compares with it)
     // ---- optional outputs of the host-buffer path: [nsys][4] / [nsys][12] on the device, then pinned
-    double *d_rout_aos = nullptr, *h_rout = nullptr;
+    real *d_rout_aos = nullptr, *h_rout = nullptr;
     int *h_iout = nullptr;
     std::vector<cudaEvent_t> chunk_done;
     // ---- what the last solve call left where (bvode_gather reads these)
-    double *last_y = nullptr, *last_t = nullptr;  // SoA [neq][nsys], [nsys] on the device
+    real *last_y = nullptr, *last_t = nullptr;  // SoA [neq][nsys], [nsys] on the device
     int *last_istate = nullptr;
     cudaStream_t last_stream = nullptr;  // the stream the last solve was enqueued on
-    double *d_pack = nullptr;        // bvode_gather: this rank's packed final results
+    real *d_pack = nullptr;        // bvode_gather: this rank's packed final results
     size_t pack_cap = 0;
 };

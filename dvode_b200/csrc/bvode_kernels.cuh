@@ -4,8 +4,10 @@
 #include <stdlib.h>
 #include "bvode_internal.h"
 #include "policy_thread.cuh"
+#if !BVODE_REAL_IS_FLOAT  // the REAL32 build (libbvode32.so) carries the thread-per-system kernels only
 #include "policy_warp.cuh"
 #include "policy_warp2.cuh"
+#endif
 #include "problems.cuh"
 
 namespace BVODE_NS {
@@ -40,7 +42,7 @@ BV_DEV void visit_state(ENG &e, V &v) {
 
 // (T is double / int, or their volatile forms for fields a policy parks in shared memory)
 struct Loader {
-    const double *dp;
+    const real *dp;
     const int *ip;
     size_t stride;
     int kd = 0, ki = 0;
@@ -51,7 +53,7 @@ struct Loader {
     template <class T> BV_DEV void iv(T &x) { i(x); }
 };
 struct Storer {
-    double *dp;
+    real *dp;
     int *ip;
     size_t stride;
     int kd = 0, ki = 0;
@@ -71,7 +73,8 @@ BV_DEV void load_opts_ps(BvOpts &o, const KArgs &a, size_t ns, size_t sys) {
     o.tcrit = a.optd_ps[3 * ns + sys];
     o.maxord = a.opti_ps[sys];
     o.mxstep = a.opti_ps[ns + sys];
-    o.jreset = a.opti_ps[2 * ns + sys];
+    o.jreset = a.opti_ps[2 * ns + sys] & 1;
+    o.lmaxchg = (a.opti_ps[2 * ns + sys] >> 1) & 1;
 }
 
 // ------------------------------------------------------- thread-per-system ------
@@ -92,7 +95,7 @@ constexpr int kThreadTPB = BVODE_THREAD_TPB;
 // where replacing lanes at different times de-correlates the rare paths of a warp's 32 systems.
 template <class POL, bool GENERAL, bool REFILL>
 __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
-    extern __shared__ double smem_thread[];
+    extern __shared__ real smem_thread[];
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;
 
@@ -108,11 +111,11 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     int sys = a.sys0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int sys_end = a.sys0 + a.count;  // this launch integrates systems [sys0, sys0 + count)
     int nemit = 0;
-    double tout0 = 0.0;
+    real tout0 = BV_R(0.0);
     const size_t ns = (size_t)a.nsys;
 
     // ---- the kernel epilogue for one system: y, t, istate, the persistent state, optional outputs
-    auto store = [&](int ist, double t) {
+    auto store = [&](int ist, real t) {
         if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
             a.istate[sys] = IST_ILLEGAL;
             if (nemit == 0) return;      // nothing was done: y, t and the state stay as they were
@@ -124,9 +127,9 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
                 for (int i = 0; i < N; i++) a.y_out[((size_t)k2 * N + i) * ns + sys] = e.y[i];
             }
         }
-        double tolsf = 0.0;
+        real tolsf = BV_R(0.0);
         if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
-            tolsf = 2.0 * kUround * e.norm_y0();  // M:1626, 1632, 1641
+            tolsf = BV_R(2.0) * kUround * e.norm_y0();  // M:1626, 1632, 1641
 #pragma unroll
         for (int i = 0; i < N; i++) a.y[(size_t)i * ns + sys] = e.y[i];
         a.t[sys] = t;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
         }
 #pragma unroll
         for (int k = 0; k < Prob::NPAR; k++) e.par[k] = a.params[(size_t)k * ns + sys];
-        const double t = a.t[sys];
+        const real t = a.t[sys];
         tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
         nemit = 0;
         if constexpr (GENERAL) {  // per-system tolerances / optional inputs (M:729-751, 928-965)
@@ -209,14 +212,14 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
 
     e.template run<GENERAL, REFILL>(
         a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; },
-        [&](int k, const double (&yk)[N]) {
+        [&](int k, const real (&yk)[N]) {
             nemit = k + 1;
             if (a.y_out) {
 #pragma unroll
                 for (int i = 0; i < N; i++) a.y_out[((size_t)k * N + i) * ns + sys] = yk[i];
             }
         },
-        [&](bool have, int ist, double t) -> int {
+        [&](bool have, int ist, real t) -> int {
             if constexpr (REFILL) {
                 if (have) {
                     store(ist, t);
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
 // dvindy for any k (M:1878-1959) from the stored state; one thread per system.
 template <class POL>
 __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_constant__ DkyArgs a) {
-    extern __shared__ double smem_thread[];
+    extern __shared__ real smem_thread[];
     const int sys = blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= a.nsys) return;
     constexpr int N = POL::N;
@@ -251,14 +254,15 @@ __global__ void __launch_bounds__(kThreadTPB) dvindy_thread_kernel(const __grid_
     Loader ld{a.dstate + sys, a.istate_store + sys, (size_t)a.nsys};
     visit_state(e, ld);
     e.c.L = e.c.nq + 1;
-    const double t = a.t_ps ? a.t_ps[sys] : a.t;
-    double dky[N];
+    const real t = a.t_ps ? a.t_ps[sys] : a.t;
+    real dky[N];
     const int iflag = e.dvindy_k(t, a.k, dky);
 #pragma unroll
     for (int i = 0; i < N; i++) a.dky[(size_t)i * a.nsys + sys] = dky[i];
     a.iflag[sys] = iflag;
 }
 
+#if !BVODE_REAL_IS_FLOAT
 // ---------------------------------------------------------- warp-per-system ------
 // State layout in HBM for one-system-per-warp kernels (all in the same dstate / istate_store
 // allocations, regions in this order):
@@ -278,7 +282,7 @@ template <class POL>
 struct WarpTpb<POL, decltype((void)POL::kTPB)> { static constexpr int value = POL::kTPB; };
 
 struct WarpLoader {
-    const double *ds, *dl, *db;
+    const real *ds, *dl, *db;
     const int *is, *il;
     size_t nsys, sys;
     int ln, nblock;
@@ -288,23 +292,23 @@ struct WarpLoader {
     template <class T> BV_DEV void dv(T &x) { x = dl[((size_t)kl * nsys + sys) * 32 + ln]; kl++; }
     template <class T> BV_DEV void iv(T &x) { x = il[((size_t)kil * nsys + sys) * 32 + ln]; kil++; }
     BV_DEV void skip_dv(int n) { kl += n; }
-    BV_DEV void block(double *sm, int n) {
+    BV_DEV void block(real *sm, int n) {
         for (int k = ln; k < n; k += 32) sm[k] = db[sys * (size_t)nblock + k];
         __syncwarp();
     }
 };
 struct WarpStorer {
-    double *ds, *dl, *db;
+    real *ds, *dl, *db;
     int *is, *il;
     size_t nsys, sys;
     int ln, nblock;
     int kd = 0, kl = 0, ki = 0, kil = 0;
-    template <class T> BV_DEV void d(T &x) { const double v = x; if (ln == 0) ds[(size_t)kd * nsys + sys] = v; kd++; }
+    template <class T> BV_DEV void d(T &x) { const real v = x; if (ln == 0) ds[(size_t)kd * nsys + sys] = v; kd++; }
     template <class T> BV_DEV void i(T &x) { const int v = x; if (ln == 0) is[(size_t)ki * nsys + sys] = v; ki++; }
     template <class T> BV_DEV void dv(T &x) { dl[((size_t)kl * nsys + sys) * 32 + ln] = x; kl++; }
     template <class T> BV_DEV void iv(T &x) { il[((size_t)kil * nsys + sys) * 32 + ln] = x; kil++; }
     BV_DEV void skip_dv(int n) { kl += n; }
-    BV_DEV void block(double *sm, int n) {
+    BV_DEV void block(real *sm, int n) {
         __syncwarp();
         for (int k = ln; k < n; k += 32) db[sys * (size_t)nblock + k] = sm[k];
     }
@@ -324,10 +328,10 @@ struct WarpLayout {
 // system is loaded or stored instead of being kept in registers across the step loop.
 template <class POL>
 struct WarpRegions {
-    const double *dl, *db;
+    const real *dl, *db;
     const int *il;
     int nblock;
-    BV_DEV WarpRegions(const double *dstate, const int *istore, size_t nsys, int ml, int mu) {
+    BV_DEV WarpRegions(const real *dstate, const int *istore, size_t nsys, int ml, int mu) {
         dl = dstate + (size_t)scalar_d<POL>() * nsys;
         db = dl + (size_t)POL::kLaneSlots * nsys * 32;
         il = istore + (size_t)kScalarI * nsys;
@@ -338,8 +342,8 @@ struct WarpRegions {
 };
 
 template <class POL>
-BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, size_t nsys,
-                      size_t sys, int ln, int warp, int ml, int mu, double *smem) {
+BV_DEV void warp_bind(Engine<POL> &e, const real *dstate, const int *istore, size_t nsys,
+                      size_t sys, int ln, int warp, int ml, int mu, real *smem) {
     const WarpRegions<POL> rg(dstate, istore, nsys, ml, mu);
     const int nb = rg.nblock;
     // per-warp control state: after the kWarpTPB/32 matrix images of the CTA
@@ -355,7 +359,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
     } else {
         e.lin.p = smem + (size_t)warp * nb;
         e.lin.perm = reinterpret_cast<int *>(e.lin.p + POL::kPermOff);
-        e.lin.wjs.p = const_cast<double *>(rg.dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
+        e.lin.wjs.p = const_cast<real *>(rg.dl) + ((size_t)POL::kLaneSlotWjs * nsys + sys) * 32 + ln;
         e.lin.wjs.stride = nsys * 32;
     }
 }
@@ -371,7 +375,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const double *dstate, const int *istore, s
 template <class POL, bool GENERAL>
 __global__ void __launch_bounds__(WarpTpb<POL>::value, POL::kMinBlocks)
 vode_warp_kernel(const __grid_constant__ KArgs a) {
-    extern __shared__ double smem[];
+    extern __shared__ real smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const size_t sys = (size_t)a.sys0 + (size_t)blockIdx.x * (WarpTpb<POL>::value / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
@@ -383,18 +387,18 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
     e.o = a.o;
     constexpr int NL = POL::NLOC;  // components per lane: component ln + 32*i in slot i
     if constexpr (NL == 1) {
-        e.tol.r = (ln < N) ? a.rtol[ln] : 0.0;
-        e.tol.a = (ln < N) ? a.atol[ln] : 1.0;  // padding lanes: finite weight, value always 0
+        e.tol.r = (ln < N) ? a.rtol[ln] : BV_R(0.0);
+        e.tol.a = (ln < N) ? a.atol[ln] : BV_R(1.0);  // padding lanes: finite weight, value always 0
     } else {
 #pragma unroll
         for (int i = 0; i < NL; i++) {
-            e.tol.r[i] = (ln + 32 * i < N) ? a.rtol[ln + 32 * i] : 0.0;
-            e.tol.a[i] = (ln + 32 * i < N) ? a.atol[ln + 32 * i] : 1.0;
+            e.tol.r[i] = (ln + 32 * i < N) ? a.rtol[ln + 32 * i] : BV_R(0.0);
+            e.tol.a[i] = (ln + 32 * i < N) ? a.atol[ln + 32 * i] : BV_R(1.0);
         }
     }
     warp_bind(e, a.dstate, a.istate_store, nsys, sys, ln, warp, a.o.ml, a.o.mu, smem);
     int nemit = 0;
-    double tout0 = 0.0;
+    real tout0 = BV_R(0.0);
 
     // ---- the kernel prologue: 0 = nothing to do for this system, 1 = first call, 2 = continuation
     auto load = [&]() -> int {
@@ -430,12 +434,12 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             if (a.optd_ps) load_opts_ps(e.o, a, nsys, sys);
         }
         Prob::load_par(e.par, a.params, nsys, sys, ln);
-        const double t = a.t[sys];
+        const real t = a.t[sys];
         tout0 = a.tout_ps ? a.tout_ps[sys] : a.touts[0];
         if (ist == 1) {
             if (tout0 == t) return 0;  // M:1101
 #pragma unroll
-            for (int i = 0; i < NL; i++) e.y[i] = (ln + 32 * i < N) ? a.y[(size_t)(ln + 32 * i) * nsys + sys] : 0.0;
+            for (int i = 0; i < NL; i++) e.y[i] = (ln + 32 * i < N) ? a.y[(size_t)(ln + 32 * i) * nsys + sys] : BV_R(0.0);
             const int r = e.init_problem(t, tout0);
             if (r < 0) {
                 if (ln == 0) a.istate[sys] = r;
@@ -457,7 +461,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
         return 2;
     };
     // ---- the kernel epilogue
-    auto store = [&](int ist, double t) {
+    auto store = [&](int ist, real t) {
         if (ist == IST_ILLEGAL_ENTRY) {  // illegal input at a call entry (messages 23-25, 27)
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
             if (nemit == 0) return;
@@ -470,9 +474,9 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
                     if (ln + 32 * i < N) a.y_out[((size_t)k2 * N + ln + 32 * i) * nsys + sys] = e.y[i];
             }
         }
-        double tolsf = 0.0;
+        real tolsf = BV_R(0.0);
         if (ist == IST_TOLSF || (ist == IST_ILLEGAL && e.hot.si(SI_NST) == 0))
-            tolsf = 2.0 * kUround * e.norm_y0();
+            tolsf = BV_R(2.0) * kUround * e.norm_y0();
         const int imx = (ist == IST_ERRTEST || ist == IST_CONVFAIL) ? POL::imxer(e.acor, e.ewt) : 0;
 
 #pragma unroll
@@ -480,7 +484,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             if (ln + 32 * i < N) a.y[(size_t)(ln + 32 * i) * nsys + sys] = e.y[i];
         {
             const WarpRegions<POL> rg(a.dstate, a.istate_store, nsys, a.o.ml, a.o.mu);
-            WarpStorer st{a.dstate, const_cast<double *>(rg.dl), const_cast<double *>(rg.db),
+            WarpStorer st{a.dstate, const_cast<real *>(rg.dl), const_cast<real *>(rg.db),
                           a.istate_store, const_cast<int *>(rg.il), nsys, sys, ln, rg.nblock};
             visit_state(e, st);
         }
@@ -508,7 +512,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 
     e.template run<GENERAL, false>(
         a.nout, [&](int k) { return (k == 0) ? tout0 : a.touts[k]; },
-        [&](int k, const double (&yk)[NL]) {
+        [&](int k, const real (&yk)[NL]) {
             nemit = k + 1;
             if (a.y_out) {
 #pragma unroll
@@ -516,7 +520,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
                     if (ln + 32 * i < N) a.y_out[((size_t)k * N + ln + 32 * i) * nsys + sys] = yk[i];
             }
         },
-        [&](bool have, int ist, double t) -> int {  // one system per warp and launch
+        [&](bool have, int ist, real t) -> int {  // one system per warp and launch
             if (have) {
                 store(ist, t);
                 return 0;
@@ -527,7 +531,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 
 template <class POL>
 __global__ void __launch_bounds__(WarpTpb<POL>::value) dvindy_warp_kernel(const __grid_constant__ DkyArgs a) {
-    extern __shared__ double smem[];
+    extern __shared__ real smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
     const size_t sys = (size_t)blockIdx.x * (WarpTpb<POL>::value / 32) + warp;
     const size_t nsys = (size_t)a.nsys;
@@ -539,8 +543,8 @@ __global__ void __launch_bounds__(WarpTpb<POL>::value) dvindy_warp_kernel(const 
     WarpLoader ld{a.dstate, rg.dl, rg.db, a.istate_store, rg.il, nsys, sys, ln, rg.nblock};
     visit_state(e, ld);
     e.c.L = e.c.nq + 1;
-    const double t = a.t_ps ? a.t_ps[sys] : a.t;
-    double dky[POL::NLOC];
+    const real t = a.t_ps ? a.t_ps[sys] : a.t;
+    real dky[POL::NLOC];
     const int iflag = e.dvindy_k(t, a.k, dky);
 #pragma unroll
     for (int i = 0; i < POL::NLOC; i++)
@@ -548,6 +552,7 @@ __global__ void __launch_bounds__(WarpTpb<POL>::value) dvindy_warp_kernel(const 
     if (ln == 0) a.iflag[sys] = iflag;
 }
 
+#endif  // !BVODE_REAL_IS_FLOAT
 // --------------------------------------------------------------- launchers ------
 // Grid of the compacting thread-per-system kernel: exactly the resident capacity (SMs x CTAs per
 // SM); finished threads claim the remaining systems through a.next_sys.
@@ -603,11 +608,12 @@ static int launch_dky_thread(const DkyArgs &a, cudaStream_t st) {
     dvindy_thread_kernel<POL><<<grid, kThreadTPB, POL::kSmemBytes, st>>>(a);
     return (int)cudaGetLastError();
 }
+#if !BVODE_REAL_IS_FLOAT
 template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.count + spb - 1) / spb;
-    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles +
+    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles +
                                                ScratchDoublesOf<typename POL::Prob>::value);
     // Shared memory / L1 split: ask for just what POL::kMinBlocks resident CTAs need (+1 KB each that the
     // system reserves), so that the rest of the 256 KB stays L1 -- the kernels' register spills and the
@@ -632,13 +638,14 @@ template <class POL>
 static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
     const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.nsys + spb - 1) / spb;
-    const size_t smem = sizeof(double) * spb * ((size_t)WarpLayout<POL>::nblock(a.ml, a.mu) + POL::kWarpHotDoubles);
+    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nblock(a.ml, a.mu) + POL::kWarpHotDoubles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(dvindy_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dvindy_warp_kernel<POL><<<grid, WarpTpb<POL>::value, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
+#endif  // !BVODE_REAL_IS_FLOAT
 // ------------------------------------------------------------------ dispatch ------
 // mf = jsv * (10*meth + miter), M:999-1046.  jsv only matters where a Jacobian is stored
 // (miter 1, 2, 4, 5).
@@ -706,8 +713,8 @@ static void copy_rows(T *dst, const T *src, size_t rows, size_t width, cudaStrea
 // shrinks its old column maxord_new + 2 -- which the order reduction of M:1385 / 2044-2079 reads -- goes into the
 // acor slot (free at a restart: dvnlsd zeroes acor before its next use).
 template <class PROB>
-static int thread_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
-                                const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
+static int thread_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const real *d_old,
+                                const int *i_old, real *d_new, int *i_new, cudaStream_t st) {
     constexpr size_t N = PROB::N;
     const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
     const size_t la = kLmaxOf(a.meth), lb = kLmaxOf(b.meth), lmin = la < lb ? la : lb;
@@ -735,6 +742,7 @@ static int thread_supports(int mf, int ml, int mu) {
             thread_dispatch<PROB>, thread_dky_dispatch<PROB>, thread_state_convert<PROB>    \
     }
 
+#if !BVODE_REAL_IS_FLOAT
 template <class P, class = void>
 struct HasJacRowMember { static constexpr bool value = false; };
 template <class P>
@@ -819,14 +827,14 @@ static void warp_state_size(int mf, int ml, int mu, size_t nsys, size_t *nd, siz
 // The same for the one-system-per-warp layouts: scalars[lm + 14][nsys], then the lane slots yh[lm][NLOC], acor
 // copy[NLOC], acor[NLOC] (rows of nsys * 32); everything else (matrix images, pivots) is rebuilt at the restart.
 template <int NLOC>
-static int warp_convert_generic(int mf_old, int mf_new, size_t nsys, const double *d_old, const int *i_old,
-                                double *d_new, int *i_new, cudaStream_t st) {
+static int warp_convert_generic(int mf_old, int mf_new, size_t nsys, const real *d_old, const int *i_old,
+                                real *d_new, int *i_new, cudaStream_t st) {
     const MfParts a = mf_parts(mf_old), b = mf_parts(mf_new);
     const size_t la = kLmaxOf(a.meth), lb = kLmaxOf(b.meth), lmin = la < lb ? la : lb;
     copy_rows(d_new, d_old, lmin, nsys, st);                                     // tau
     copy_rows(d_new + lb * nsys, d_old + la * nsys, 14, nsys, st);               // scalars
-    const double *lo = d_old + (la + 14) * nsys;
-    double *ln = d_new + (lb + 14) * nsys;
+    const real *lo = d_old + (la + 14) * nsys;
+    real *ln = d_new + (lb + 14) * nsys;
     const size_t w = nsys * 32;
     copy_rows(ln, lo, lmin * NLOC, w, st);                                       // yh
     copy_rows(ln + lb * NLOC * w, lo + la * NLOC * w, NLOC, w, st);              // acor copy
@@ -836,8 +844,8 @@ static int warp_convert_generic(int mf_old, int mf_new, size_t nsys, const doubl
     return (int)cudaGetLastError();
 }
 template <class PROB, int KIND>
-static int warp_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old,
-                              const int *i_old, double *d_new, int *i_new, cudaStream_t st) {
+static int warp_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const real *d_old,
+                              const int *i_old, real *d_new, int *i_new, cudaStream_t st) {
     return warp_convert_generic<1>(mf_old, mf_new, nsys, d_old, i_old, d_new, i_new, st);
 }
 template <class PROB, int KIND>
@@ -895,8 +903,8 @@ static int warp2_supports(int mf, int, int) {
     const MfParts m = mf_parts(mf);
     return (m.meth == 1 || m.meth == 2) && (m.miter == 0 || m.miter == 2 || m.miter == 3);
 }
-static int warp2_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const double *d_old, const int *i_old,
-                               double *d_new, int *i_new, cudaStream_t st) {
+static int warp2_state_convert(int mf_old, int mf_new, int, int, size_t nsys, const real *d_old, const int *i_old,
+                               real *d_new, int *i_new, cudaStream_t st) {
     return warp_convert_generic<2>(mf_old, mf_new, nsys, d_old, i_old, d_new, i_new, st);
 }
 #define BVODE_WARP2_DENSE_FD_PROBLEM(NAME, PROB)                                            \
@@ -914,5 +922,7 @@ static int warp2_state_convert(int mf_old, int mf_new, int, int, size_t nsys, co
         NAME, PROB::N, PROB::NPAR, 1, warp_supports<PROB, 2>, warp_state_size<PROB, 2>,     \
             warp_dispatch<PROB, 2>, warp_dky_dispatch<PROB, 2>, warp_state_convert<PROB, 2> \
     }
+
+#endif  // !BVODE_REAL_IS_FLOAT
 
 }  // namespace BVODE_NS

@@ -21,34 +21,41 @@
 #endif
 
 #define BV_DEV __device__ __forceinline__
+#include "bvode_real.h"
 
 namespace BVODE_NS {
 
-constexpr double kUround = 2.220446049250313e-16;  // epsilon(1.0_real64), M:36
+// REALIFY-OFF
+#if BVODE_REAL_IS_FLOAT
+constexpr real kUround = 1.1920929e-07f;  // epsilon(1.0_real32), M:36 with wp = real32 (K:29-31)
+#else
+constexpr real kUround = 2.220446049250313e-16;  // epsilon(1.0_real64), M:36
+#endif
+// REALIFY-ON
 
-BV_DEV double dmax2(double a, double b) { return a > b ? a : b; }
-BV_DEV double dmin2(double a, double b) { return a < b ? a : b; }
-BV_DEV double dsign(double a, double b) { return copysign(fabs(a), b); }
+BV_DEV real dmax2(real a, real b) { return a > b ? a : b; }
+BV_DEV real dmin2(real a, real b) { return a < b ? a : b; }
+BV_DEV real dsign(real a, real b) { return copysign(fabs(a), b); }
 
 // x**n for integer n the way gfortran lowers it (libgcc __powidf2), M:1956, M:2287.
-BV_DEV double powi(double x, int m) {
+BV_DEV real powi(real x, int m) {
     unsigned int n = m < 0 ? (unsigned int)(-m) : (unsigned int)m;
-    double y = (n & 1u) ? x : 1.0;
+    real y = (n & 1u) ? x : BV_R(1.0);
     while (n >>= 1) {
         x = x * x;
         if (n & 1u) y *= x;
     }
-    return m < 0 ? 1.0 / y : y;
+    return m < 0 ? BV_R(1.0) / y : y;
 }
 
 // x**m for 2 <= m <= MAXP.  Strict build: powi (the reference's operation order).  Fast build,
 // small MAXP (BDF): straight-line products and a select -- no divergent loop in the step loop.
 template <int MAXP>
-BV_DEV double powi_small(double x, int m) {
+BV_DEV real powi_small(real x, int m) {
 #if !BVODE_STRICT
     if constexpr (MAXP <= 7) {
-        const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
-        double r = x2;
+        const real x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+        real r = x2;
         r = (m == 3) ? x3 : r;
         r = (m == 4) ? x4 : r;
         r = (m == 5) ? x4 * x : r;
@@ -60,6 +67,7 @@ BV_DEV double powi_small(double x, int m) {
     return powi(x, m);
 }
 
+// REALIFY-OFF (double inside whatever `real` is)
 // Portable x**y, x > 0: same operation sequence as dvo_ppow in oracle/dvode_oracle.c.
 // Only meaningful bit for bit when compiled with -fmad=false.
 static __device__ __noinline__ double ppow(double x, double y) {
@@ -125,10 +133,12 @@ static __device__ __noinline__ double ppow(double x, double y) {
     return (er * t1) * t2;
 }
 
+// REALIFY-ON
 // x**y with real y: the reference calls libm pow through gfortran (M:2201, 2275, 2282, 2292).
-BV_DEV double rpow(double x, double y) {
+// (REAL32: the portable pow works in double and its result is rounded to real -- on both sides.)
+BV_DEV real rpow(real x, real y) {
 #if BVODE_STRICT
-    return ppow(x, y);
+    return (real)ppow((real)x, (real)y);
 #else
     return pow(x, y);
 #endif
@@ -143,20 +153,20 @@ BV_DEV double rpow(double x, double y) {
 // cache).  Valid for normal, finite divisors with |b| in [2^-1000, 2^1000]: step sizes, error
 // weights and the order coefficients of a running integration are all far inside that.
 #if BVODE_STRICT
-BV_DEV double qrcp(double b) { return 1.0 / b; }
-BV_DEV double qdiv(double a, double b) { return a / b; }
+BV_DEV real qrcp(real b) { return BV_R(1.0) / b; }
+BV_DEV real qdiv(real a, real b) { return a / b; }
 #else
-BV_DEV double qrcp(double b) {
-    double r;
+BV_DEV real qrcp(real b) {
+    real r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    const double e = fma(-b, r, 1.0);
-    const double t = fma(e, e, e);
+    const real e = fma(-b, r, BV_R(1.0));
+    const real t = fma(e, e, e);
     return fma(r, t, r);
 }
-BV_DEV double qdiv(double a, double b) {
-    const double r = qrcp(b);
-    const double q = a * r;
-    const double rem = fma(-b, q, a);
+BV_DEV real qdiv(real a, real b) {
+    const real r = qrcp(b);
+    const real q = a * r;
+    const real rem = fma(-b, q, a);
     return fma(rem, r, q);
 }
 #endif
@@ -164,68 +174,68 @@ BV_DEV double qdiv(double a, double b) {
 // 1/(double)k for the small integers of the order logic (k = 0..15): the same bits as the
 // reference's `one/real(k)` divide, from a constant-bank table (one indexed LDC; lanes at
 // different orders cost one replay per distinct k) -- no divide, no divergent switch.
-__constant__ double kRecipTab[16] = {0.0,        1.0,        1.0 / 2.0,  1.0 / 3.0,  1.0 / 4.0,  1.0 / 5.0,
-                                     1.0 / 6.0,  1.0 / 7.0,  1.0 / 8.0,  1.0 / 9.0,  1.0 / 10.0, 1.0 / 11.0,
-                                     1.0 / 12.0, 1.0 / 13.0, 1.0 / 14.0, 1.0 / 15.0};
-BV_DEV double recip_int(int k) { return kRecipTab[k & 15]; }
+__constant__ real kRecipTab[16] = {BV_R(0.0),        BV_R(1.0),        BV_R(1.0) / BV_R(2.0),  BV_R(1.0) / BV_R(3.0),  BV_R(1.0) / BV_R(4.0),  BV_R(1.0) / BV_R(5.0),
+                                     BV_R(1.0) / BV_R(6.0),  BV_R(1.0) / BV_R(7.0),  BV_R(1.0) / BV_R(8.0),  BV_R(1.0) / BV_R(9.0),  BV_R(1.0) / BV_R(10.0), BV_R(1.0) / BV_R(11.0),
+                                     BV_R(1.0) / BV_R(12.0), BV_R(1.0) / BV_R(13.0), BV_R(1.0) / BV_R(14.0), BV_R(1.0) / BV_R(15.0)};
+BV_DEV real recip_int(int k) { return kRecipTab[k & 15]; }
 
 #if !BVODE_STRICT
 // Fast build: the step-size ratio eta = 1/(x**(1/k) + addon) (M:2201, 2275, 2282, 2292) is
 // evaluated as 1/(exp2(log2(x)/k) + addon) with the double-precision log2 / exp2 below
 // (rounding-level difference from pow).
-typedef double lg_t;
+typedef real lg_t;
 // log2 / exp2 in double precision, ~2 ulp (checked against libm over 2e6 random arguments:
 // max relative error 4.3e-16 / 2.2e-16), about a third of the instructions of CUDA's
 // correctly-rounded-ish log2() / exp2(): atanh series on the mantissa reduced to
 // [sqrt(1/2), sqrt(2)], degree-13 Taylor polynomial of 2^f on [-1/2, 1/2].
-BV_DEV lg_t log2_fast(double x) {
+BV_DEV lg_t log2_fast(real x) {
     unsigned long long u = (unsigned long long)__double_as_longlong(x);
     int e = (int)(u >> 52) - 1023;
     u = (u & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
-    double m = __longlong_as_double((long long)u);
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    const double s = qdiv(m - 1.0, m + 1.0), z = s * s;
-    double p = 1.0 / 21.0;
-    p = fma(p, z, 1.0 / 19.0);
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, 1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, 1.0 / 3.0);
-    const double t = s * 2.8853900817779268;  // 2/ln 2
-    return fma(t * z, p, t) + (double)e;
+    real m = __longlong_as_double((long long)u);
+    if (m > BV_R(1.4142135623730951)) { m *= BV_R(0.5); e += 1; }
+    const real s = qdiv(m - BV_R(1.0), m + BV_R(1.0)), z = s * s;
+    real p = BV_R(1.0) / BV_R(21.0);
+    p = fma(p, z, BV_R(1.0) / BV_R(19.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(17.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(15.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(13.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(11.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(9.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(7.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(5.0));
+    p = fma(p, z, BV_R(1.0) / BV_R(3.0));
+    const real t = s * BV_R(2.8853900817779268);  // 2/ln 2
+    return fma(t * z, p, t) + (real)e;
 }
 // log2 of a positive normal double in single precision: exponent exactly, mantissa through the
 // hardware lg2 (absolute error < 3e-7 + 6e-8 |log2 x|).  Only used to ORDER step-ratio
 // candidates that are far apart; near_f32 says when two such values are too close to call.
-BV_DEV float log2_f32(double x) {
+BV_DEV float log2_f32(real x) {
     const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
     const int e = (int)(hi >> 20) - 1023;
     const float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
     return (float)e + __log2f(m);
 }
 BV_DEV bool near_f32(float a, float b) { return fabsf(a - b) <= 1.0e-5f * (1.0f + fabsf(a) + fabsf(b)); }
-BV_DEV double exp2_fast(lg_t l) {
-    const double n = rint(l), f = l - n;
-    double p = 1.369148885390412888e-12;
-    p = fma(p, f, 2.567843599348820514e-11);
-    p = fma(p, f, 4.445538271870811498e-10);
-    p = fma(p, f, 7.054911620801123329e-9);
-    p = fma(p, f, 1.017808600923969973e-7);
-    p = fma(p, f, 1.321548679014430949e-6);
-    p = fma(p, f, 1.525273380405984028e-5);
-    p = fma(p, f, 1.540353039338160995e-4);
-    p = fma(p, f, 1.333355814642844342e-3);
-    p = fma(p, f, 9.618129107628477232e-3);
-    p = fma(p, f, 5.550410866482157995e-2);
-    p = fma(p, f, 2.402265069591007123e-1);
-    p = fma(p, f, 6.931471805599453094e-1);
-    p = fma(p, f, 1.0);
+BV_DEV real exp2_fast(lg_t l) {
+    const real n = rint(l), f = l - n;
+    real p = BV_R(1.369148885390412888e-12);
+    p = fma(p, f, BV_R(2.567843599348820514e-11));
+    p = fma(p, f, BV_R(4.445538271870811498e-10));
+    p = fma(p, f, BV_R(7.054911620801123329e-9));
+    p = fma(p, f, BV_R(1.017808600923969973e-7));
+    p = fma(p, f, BV_R(1.321548679014430949e-6));
+    p = fma(p, f, BV_R(1.525273380405984028e-5));
+    p = fma(p, f, BV_R(1.540353039338160995e-4));
+    p = fma(p, f, BV_R(1.333355814642844342e-3));
+    p = fma(p, f, BV_R(9.618129107628477232e-3));
+    p = fma(p, f, BV_R(5.550410866482157995e-2));
+    p = fma(p, f, BV_R(2.402265069591007123e-1));
+    p = fma(p, f, BV_R(6.931471805599453094e-1));
+    p = fma(p, f, BV_R(1.0));
     const int ni = (int)n;
-    if (ni < -1020) return 0.0;
+    if (ni < -1020) return BV_R(0.0);
     if (ni > 1020) return __longlong_as_double(0x7ff0000000000000LL);
     return p * __longlong_as_double((long long)(ni + 1023) << 52);
 }

@@ -179,18 +179,18 @@ struct PackLayout {
 static PackLayout pack_layout(size_t n, int neq) {
     PackLayout L;
     L.off_y = 0;
-    L.off_t = L.off_y + sizeof(double) * n * neq;
-    L.off_rout = L.off_t + sizeof(double) * n;
-    L.off_iout = L.off_rout + sizeof(double) * 4 * n;
+    L.off_t = L.off_y + sizeof(real) * n * neq;
+    L.off_rout = L.off_t + sizeof(real) * n;
+    L.off_iout = L.off_rout + sizeof(real) * 4 * n;
     L.off_ist = L.off_iout + sizeof(int) * 12 * n;
     L.total = L.off_ist + sizeof(int) * n;
     return L;
 }
 // SoA (the kernels' layout) -> the five host-layout sections; any destination may be null
-__global__ void k_pack_results(int n, int neq, const double *__restrict__ y, const double *__restrict__ t,
-                               const int *__restrict__ ist, const double *__restrict__ rout,
-                               const int *__restrict__ iout, double *__restrict__ py, double *__restrict__ pt,
-                               double *__restrict__ prout, int *__restrict__ piout, int *__restrict__ pist) {
+__global__ void k_pack_results(int n, int neq, const real *__restrict__ y, const real *__restrict__ t,
+                               const int *__restrict__ ist, const real *__restrict__ rout,
+                               const int *__restrict__ iout, real *__restrict__ py, real *__restrict__ pt,
+                               real *__restrict__ prout, int *__restrict__ piout, int *__restrict__ pist) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const size_t ns = (size_t)n;
@@ -201,8 +201,8 @@ __global__ void k_pack_results(int n, int neq, const double *__restrict__ y, con
     if (pist) pist[s] = ist[s];
 }
 
-int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, double *y_all,
-                        double *t_all, int *istate_all, double *rout_all, int *iout_all, void *stream) {
+int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, real *y_all,
+                        real *t_all, int *istate_all, real *rout_all, int *iout_all, void *stream) {
     if (!s || !c || root < 0 || root >= c->world) return BVODE_EINVAL;
     long long first, last;
     bvode_shard_range(nsys_total, c->rank, c->world, &first, &last);
@@ -232,9 +232,9 @@ int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys
             bvode_shard_range(nsys_total, r, c->world, &f, &l);
             const size_t m = (size_t)(l - f);
             if (m == 0) continue;
-            if (y_all) NCCL_TRY(nccl().Recv(y_all + (size_t)f * neq, sizeof(double) * m * neq, ncclInt8, r, c->comm, st));
-            if (t_all) NCCL_TRY(nccl().Recv(t_all + f, sizeof(double) * m, ncclInt8, r, c->comm, st));
-            if (rout_all) NCCL_TRY(nccl().Recv(rout_all + (size_t)f * 4, sizeof(double) * 4 * m, ncclInt8, r, c->comm, st));
+            if (y_all) NCCL_TRY(nccl().Recv(y_all + (size_t)f * neq, sizeof(real) * m * neq, ncclInt8, r, c->comm, st));
+            if (t_all) NCCL_TRY(nccl().Recv(t_all + f, sizeof(real) * m, ncclInt8, r, c->comm, st));
+            if (rout_all) NCCL_TRY(nccl().Recv(rout_all + (size_t)f * 4, sizeof(real) * 4 * m, ncclInt8, r, c->comm, st));
             if (iout_all) NCCL_TRY(nccl().Recv(iout_all + (size_t)f * 12, sizeof(int) * 12 * m, ncclInt8, r, c->comm, st));
             if (istate_all) NCCL_TRY(nccl().Recv(istate_all + f, sizeof(int) * m, ncclInt8, r, c->comm, st));
         }
@@ -254,15 +254,15 @@ int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys
     }
     char *pk = (char *)s->d_pack;
     k_pack_results<<<grid, TB, 0, st>>>(n, neq, s->last_y, s->last_t, s->last_istate, s->d_rout, s->d_iout,
-                                        y_all ? (double *)(pk + L.off_y) : nullptr, t_all ? (double *)(pk + L.off_t) : nullptr,
-                                        rout_all ? (double *)(pk + L.off_rout) : nullptr,
+                                        y_all ? (real *)(pk + L.off_y) : nullptr, t_all ? (real *)(pk + L.off_t) : nullptr,
+                                        rout_all ? (real *)(pk + L.off_rout) : nullptr,
                                         iout_all ? (int *)(pk + L.off_iout) : nullptr,
                                         istate_all ? (int *)(pk + L.off_ist) : nullptr);
     CUDA_TRY(cudaGetLastError());
     NCCL_TRY(nccl().GroupStart());
-    if (y_all) NCCL_TRY(nccl().Send(pk + L.off_y, sizeof(double) * (size_t)n * neq, ncclInt8, root, c->comm, st));
-    if (t_all) NCCL_TRY(nccl().Send(pk + L.off_t, sizeof(double) * (size_t)n, ncclInt8, root, c->comm, st));
-    if (rout_all) NCCL_TRY(nccl().Send(pk + L.off_rout, sizeof(double) * 4 * (size_t)n, ncclInt8, root, c->comm, st));
+    if (y_all) NCCL_TRY(nccl().Send(pk + L.off_y, sizeof(real) * (size_t)n * neq, ncclInt8, root, c->comm, st));
+    if (t_all) NCCL_TRY(nccl().Send(pk + L.off_t, sizeof(real) * (size_t)n, ncclInt8, root, c->comm, st));
+    if (rout_all) NCCL_TRY(nccl().Send(pk + L.off_rout, sizeof(real) * 4 * (size_t)n, ncclInt8, root, c->comm, st));
     if (iout_all) NCCL_TRY(nccl().Send(pk + L.off_iout, sizeof(int) * 12 * (size_t)n, ncclInt8, root, c->comm, st));
     if (istate_all) NCCL_TRY(nccl().Send(pk + L.off_ist, sizeof(int) * (size_t)n, ncclInt8, root, c->comm, st));
     NCCL_TRY(nccl().GroupEnd());
@@ -270,24 +270,24 @@ int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys
 }
 
 // Host destinations on the root: the device gather into scratch on the root's GPU, then one copy per array.
-int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, double *y_all, double *t_all,
-                 int *istate_all, double *rout_all, int *iout_all) {
+int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, real *y_all, real *t_all,
+                 int *istate_all, real *rout_all, int *iout_all) {
     if (!s || !c || root < 0 || root >= c->world) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const bool is_root = (c->rank == root);
     const int neq = s->neq;
     char *scratch = nullptr;
     const PackLayout L = pack_layout((size_t)nsys_total, neq);
-    double *dy = nullptr, *dt = nullptr, *dr = nullptr;
+    real *dy = nullptr, *dt = nullptr, *dr = nullptr;
     int *di = nullptr, *dist = nullptr;
     if (is_root) {
         CUDA_TRY(cudaMalloc(&scratch, L.total));
-        dy = (double *)(scratch + L.off_y); dt = (double *)(scratch + L.off_t); dr = (double *)(scratch + L.off_rout);
+        dy = (real *)(scratch + L.off_y); dt = (real *)(scratch + L.off_t); dr = (real *)(scratch + L.off_rout);
         di = (int *)(scratch + L.off_iout); dist = (int *)(scratch + L.off_ist);
     }
     // non-root ranks pass "wanted" markers (any non-null pointer)
-    double *wy = y_all ? (is_root ? dy : (double *)1) : nullptr, *wt = t_all ? (is_root ? dt : (double *)1) : nullptr;
-    double *wr = rout_all ? (is_root ? dr : (double *)1) : nullptr;
+    real *wy = y_all ? (is_root ? dy : (real *)1) : nullptr, *wt = t_all ? (is_root ? dt : (real *)1) : nullptr;
+    real *wr = rout_all ? (is_root ? dr : (real *)1) : nullptr;
     int *wi = iout_all ? (is_root ? di : (int *)1) : nullptr, *wist = istate_all ? (is_root ? dist : (int *)1) : nullptr;
     // the results may still be in flight on the stream of a device-resident solve
     if (s->last_stream != s->stream) CUDA_TRY(cudaStreamSynchronize(s->last_stream));
@@ -295,9 +295,9 @@ int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total,
     if (rc == BVODE_OK && is_root) {
         const size_t nt = (size_t)nsys_total;
         cudaError_t e = cudaSuccess;
-        if (y_all && e == cudaSuccess) e = cudaMemcpyAsync(y_all, dy, sizeof(double) * nt * neq, cudaMemcpyDeviceToHost, s->stream);
-        if (t_all && e == cudaSuccess) e = cudaMemcpyAsync(t_all, dt, sizeof(double) * nt, cudaMemcpyDeviceToHost, s->stream);
-        if (rout_all && e == cudaSuccess) e = cudaMemcpyAsync(rout_all, dr, sizeof(double) * 4 * nt, cudaMemcpyDeviceToHost, s->stream);
+        if (y_all && e == cudaSuccess) e = cudaMemcpyAsync(y_all, dy, sizeof(real) * nt * neq, cudaMemcpyDeviceToHost, s->stream);
+        if (t_all && e == cudaSuccess) e = cudaMemcpyAsync(t_all, dt, sizeof(real) * nt, cudaMemcpyDeviceToHost, s->stream);
+        if (rout_all && e == cudaSuccess) e = cudaMemcpyAsync(rout_all, dr, sizeof(real) * 4 * nt, cudaMemcpyDeviceToHost, s->stream);
         if (iout_all && e == cudaSuccess) e = cudaMemcpyAsync(iout_all, di, sizeof(int) * 12 * nt, cudaMemcpyDeviceToHost, s->stream);
         if (istate_all && e == cudaSuccess) e = cudaMemcpyAsync(istate_all, dist, sizeof(int) * nt, cudaMemcpyDeviceToHost, s->stream);
         if (e != cudaSuccess) { bvode_set_error(cudaGetErrorString(e)); rc = BVODE_ECUDA; }
@@ -374,30 +374,30 @@ static int for_each_device(bvode_multi *m, F fn) {
     return BVODE_OK;
 }
 
-int bvode_multi_set_params(bvode_multi *m, const double *params) {
+int bvode_multi_set_params(bvode_multi *m, const real *params) {
     if (!m || (!params && m->npar > 0)) return BVODE_EINVAL;
     return for_each_device(m, [&](int d) { return bvode_set_params(m->h[d], params + (size_t)m->first[d] * m->npar); });
 }
 
 // internal (bvode_capi.cu): bvode_solve_schedule with the caller's y_out being a slab of a larger
 // array -- output point k of this handle's systems starts at y_out + k * yout_sys_stride * neq
-extern int bvode_solve_schedule_strided(bvode_solver *s, int neq, double *y, double *t, int nout, const double *touts,
-                                        const double *tout_ps, int itol, const double *rtol, const double *atol, int itask,
-                                        int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw, int mf,
-                                        double *y_out, long long yout_sys_stride);
+extern int bvode_solve_schedule_strided(bvode_solver *s, int neq, real *y, real *t, int nout, const real *touts,
+                                        const real *tout_ps, int itol, const real *rtol, const real *atol, int itask,
+                                        int *istate, int iopt, real *rwork, int lrw, int *iwork, int liw, int mf,
+                                        real *y_out, long long yout_sys_stride);
 
 // solve == dvode (M:604-605) for the whole batch over all devices of the handle; arguments as bvode_solve_schedule
 // (tout schedule) with arrays of nsys_total rows.  rtol / atol: batch-uniform, or per system with BVODE_FLAG_PER_SYSTEM.
-int bvode_multi_solve_schedule(bvode_multi *m, int neq, double *y, double *t, int nout, const double *touts, int itol,
-                               const double *rtol, const double *atol, int itask, int *istate, int iopt, double *rwork,
-                               int lrw, int *iwork, int liw, int mf, double *y_out) {
+int bvode_multi_solve_schedule(bvode_multi *m, int neq, real *y, real *t, int nout, const real *touts, int itol,
+                               const real *rtol, const real *atol, int itask, int *istate, int iopt, real *rwork,
+                               int lrw, int *iwork, int liw, int mf, real *y_out) {
     if (!m || !y || !t || !istate || !touts || nout < 1 || !rtol || !atol) return BVODE_EINVAL;
     const bool ps = (m->h[0]->flags & BVODE_FLAG_PER_SYSTEM) != 0;
     const int nr = ps ? ((itol >= 3) ? neq : 1) : 0, na = ps ? ((itol == 2 || itol == 4) ? neq : 1) : 0;
     return for_each_device(m, [&](int d) {
         const size_t f = (size_t)m->first[d];
         // batch-uniform optional inputs are read from row 0 of each slice: give every slice the batch's row 0
-        double *rw = rwork ? rwork + f * lrw : nullptr;
+        real *rw = rwork ? rwork + f * lrw : nullptr;
         int *iw = iwork ? iwork + f * liw : nullptr;
         if (!ps && d > 0) {
             if (rw) for (int k = 0; k < 10 && k < lrw; k++) rw[k] = rwork[k];
@@ -409,15 +409,15 @@ int bvode_multi_solve_schedule(bvode_multi *m, int neq, double *y, double *t, in
     });
 }
 
-int bvode_multi_solve(bvode_multi *m, int neq, double *y, double *t, const double *tout, int tout_per_system, int itol,
-                      const double *rtol, const double *atol, int itask, int *istate, int iopt, double *rwork, int lrw,
+int bvode_multi_solve(bvode_multi *m, int neq, real *y, real *t, const real *tout, int tout_per_system, int itol,
+                      const real *rtol, const real *atol, int itask, int *istate, int iopt, real *rwork, int lrw,
                       int *iwork, int liw, int mf) {
     if (!m || !y || !t || !istate || !tout || !rtol || !atol) return BVODE_EINVAL;
     const bool ps = (m->h[0]->flags & BVODE_FLAG_PER_SYSTEM) != 0;
     const int nr = ps ? ((itol >= 3) ? neq : 1) : 0, na = ps ? ((itol == 2 || itol == 4) ? neq : 1) : 0;
     return for_each_device(m, [&](int d) {
         const size_t f = (size_t)m->first[d];
-        double *rw = rwork ? rwork + f * lrw : nullptr;
+        real *rw = rwork ? rwork + f * lrw : nullptr;
         int *iw = iwork ? iwork + f * liw : nullptr;
         if (!ps && d > 0) {
             if (rw) for (int k = 0; k < 10 && k < lrw; k++) rw[k] = rwork[k];
@@ -431,8 +431,8 @@ int bvode_multi_solve(bvode_multi *m, int neq, double *y, double *t, const doubl
 
 // The final gather into ONE GPU's memory (device slot `root_slot`): y_all[nsys_total][neq] etc. are device
 // pointers on that GPU.  One NCCL group over the communicators of ncclCommInitAll.
-int bvode_multi_gather_device(bvode_multi *m, int root_slot, double *y_all, double *t_all, int *istate_all,
-                              double *rout_all, int *iout_all) {
+int bvode_multi_gather_device(bvode_multi *m, int root_slot, real *y_all, real *t_all, int *istate_all,
+                              real *rout_all, int *iout_all) {
     if (!m || root_slot < 0 || root_slot >= m->ndev) return BVODE_EINVAL;
     if (m->ndev > 1 && m->comms.empty()) {
         if (!nccl().ok) { bvode_set_error(nccl().why); return BVODE_ENOTIMPL; }

@@ -44,16 +44,16 @@ struct RefWarpCommon {
     static constexpr int kScratchDoubles = 2 * NP + ((NPAR + 1) & ~1) + 2;   // y, ydot, par per warp
     // this warp's scratch: at the END of the CTA's dynamic shared memory (the kernels lay out their own data
     // from the start; launch_warp adds kScratchDoubles per warp for problems that declare it)
-    BV_DEV static double *scratch() {
-        extern __shared__ double bv_dyn_smem[];
+    BV_DEV static real *scratch() {
+        extern __shared__ real bv_dyn_smem[];
         unsigned total;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(total));
         const int nw = blockDim.x >> 5, w = threadIdx.x >> 5;
         return bv_dyn_smem + (total >> 3) - (nw - w) * kScratchDoubles;
     }
-    BV_DEV static double *par_of(double *sc) { return sc + 2 * NP; }
-    BV_DEV static void load_par(double (&)[1], const double *params, size_t nsys, size_t sys, int ln) {
-        double *ps = par_of(scratch());
+    BV_DEV static real *par_of(real *sc) { return sc + 2 * NP; }
+    BV_DEV static void load_par(real (&)[1], const real *params, size_t nsys, size_t sys, int ln) {
+        real *ps = par_of(scratch());
         for (int k = ln; k < NPAR; k += 32) ps[k] = params[(size_t)k * nsys + sys];
         __syncwarp();
     }
@@ -65,18 +65,18 @@ struct RefWarp : RefWarpCommon<REF> {
     using C = RefWarpCommon<REF>;
     static constexpr int N = REF::N;
     static_assert(N <= 32, "one component per lane: n <= 32 (RefWarp2 for 32 < n <= 64)");
-    BV_DEV static void stage(double y, int ln) {
-        double *sc = C::scratch();
+    BV_DEV static void stage(real y, int ln) {
+        real *sc = C::scratch();
         __syncwarp();
         if (ln < N) sc[ln] = y;
         __syncwarp();
     }
-    BV_DEV static double f_lane(double t, double y, const double (&)[1], int ln) {
-        double *sc = C::scratch();
+    BV_DEV static real f_lane(real t, real y, const real (&)[1], int ln) {
+        real *sc = C::scratch();
         stage(y, ln);
         if (ln == 0) REF::f(N, t, sc, sc + C::NP, C::par_of(sc));
         __syncwarp();
-        return (ln < N) ? sc[C::NP + ln] : 0.0;
+        return (ln < N) ? sc[C::NP + ln] : BV_R(0.0);
     }
 };
 template <class REF>
@@ -85,22 +85,22 @@ struct RefWarp<REF, true> : RefWarp<REF, false> {
     using C = RefWarpCommon<REF>;
     static constexpr int N = REF::N;
     // banded analytic Jacobian (miter 4): pd = &abd(ml + 1, 1), nrowpd = the array's leading dimension (M:3047)
-    BV_DEV static void jac_band_full(double t, double y, double *pd, int nrowpd, int ml, int mu, const double (&)[1], int ln) {
-        double *sc = C::scratch();
+    BV_DEV static void jac_band_full(real t, real y, real *pd, int nrowpd, int ml, int mu, const real (&)[1], int ln) {
+        real *sc = C::scratch();
         B::stage(y, ln);
         if (ln == 0) REF::jac(N, t, sc, ml, mu, pd, nrowpd, C::par_of(sc));
         __syncwarp();
     }
     // dense analytic Jacobian (miter 1): the kernel's matrix is p[i*ldp + j]; the callback sees it as the
     // column-major pd(nrowpd = ldp, neq), i.e. transposed, and the warp transposes it in place afterwards
-    BV_DEV static void jac_dense_full(double t, double y, double *p, int ldp, const double (&)[1], int ln) {
-        double *sc = C::scratch();
+    BV_DEV static void jac_dense_full(real t, real y, real *p, int ldp, const real (&)[1], int ln) {
+        real *sc = C::scratch();
         B::stage(y, ln);
         if (ln == 0) REF::jac(N, t, sc, 0, 0, p, ldp, C::par_of(sc));
         __syncwarp();
         for (int i = 0; i < N; i++) {  // lane j > i swaps (i, j) with (j, i)
             if (ln > i && ln < N) {
-                const double a = p[i * ldp + ln], b = p[ln * ldp + i];
+                const real a = p[i * ldp + ln], b = p[ln * ldp + i];
                 p[i * ldp + ln] = b;
                 p[ln * ldp + i] = a;
             }
@@ -115,8 +115,8 @@ struct RefWarp2 : RefWarpCommon<REF> {
     using C = RefWarpCommon<REF>;
     static constexpr int N = REF::N;
     static_assert(N > 32 && N <= 64, "two components per lane: 32 < n <= 64");
-    BV_DEV static void f_lane2(double t, const double (&y)[2], double (&ydot)[2], const double (&)[1], int ln) {
-        double *sc = C::scratch();
+    BV_DEV static void f_lane2(real t, const real (&y)[2], real (&ydot)[2], const real (&)[1], int ln) {
+        real *sc = C::scratch();
         __syncwarp();
         sc[ln] = y[0];
         if (ln + 32 < N) sc[ln + 32] = y[1];
@@ -124,7 +124,7 @@ struct RefWarp2 : RefWarpCommon<REF> {
         if (ln == 0) REF::f(N, t, sc, sc + C::NP, C::par_of(sc));
         __syncwarp();
         ydot[0] = sc[C::NP + ln];
-        ydot[1] = (ln + 32 < N) ? sc[C::NP + ln + 32] : 0.0;
+        ydot[1] = (ln + 32 < N) ? sc[C::NP + ln + 32] : BV_R(0.0);
     }
 };
 

@@ -3,6 +3,9 @@
 // -DBVODE_STRICT=1 -fmad=false, and -DBVODE_UNIT=0..7.
 #include "bvode_kernels.cuh"
 
+#if BVODE_REAL_IS_FLOAT && (BVODE_UNIT == 2 || BVODE_UNIT == 3 || BVODE_UNIT == 5 || BVODE_UNIT == 6)
+#error "the REAL32 build carries the thread-per-system problems only (units 0, 1, 4, 7)"
+#endif
 #ifndef BVODE_UNIT
 #error "compile with -DBVODE_UNIT=<problem index>"
 #endif

@@ -29,15 +29,15 @@ struct ThreadPolicy {
     static_assert(MITER >= 0 && MITER <= 3, "thread-per-system policy: miter 0..3");
     static_assert(N >= 2, "miter = 3 keeps wm(2) and the diagonal in the N x N matrix slots");
 
-    typedef double Par[PROB::NPAR > 0 ? PROB::NPAR : 1];
+    typedef real Par[PROB::NPAR > 0 ? PROB::NPAR : 1];
     struct AcSav {};  // the acor copy the reference parks in yh(:,lmax) (M:2259, 2298) is hot.acs(i)
     // rtol / atol expanded to N entries.  Batch-uniform tolerances are copies of kernel parameters
     // (the compiler reads them straight from the constant bank); per-system ones (KArgs::tol_ps,
     // full-driver kernel only) are loaded with the system.
     struct Tol {
-        double rv[N], av[N];
-        BV_DEV double rtol(int i) const { return rv[i]; }
-        BV_DEV double atol(int i) const { return av[i]; }
+        real rv[N], av[N];
+        BV_DEV real rtol(int i) const { return rv[i]; }
+        BV_DEV real atol(int i) const { return av[i]; }
     };
 
     // Hot per-system data.  The Nordsieck array always lives in registers.  Everything that is
@@ -66,45 +66,45 @@ struct ThreadPolicy {
                          kHotInts = SI_COUNT + N;
 #if BVODE_THREAD_SMEM
     struct Hot {
-        double yhv[kLmax][N];
-        volatile double *b;  // this thread's element 0 of the double region
+        real yhv[kLmax][N];
+        volatile real *b;  // this thread's element 0 of the double region
         volatile int *bi;    // ... of the int region
-        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
-        BV_DEV volatile double &tau(int i) const { return b[(kOffTau + (i - 1)) * kTPB]; }
-        BV_DEV volatile double &p(int i, int j) const { return b[(kOffP + i * N + j) * kTPB]; }
-        BV_DEV volatile double &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
-        BV_DEV volatile double &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
-        BV_DEV volatile double &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
-        BV_DEV volatile double &acs(int i) const { return b[(kOffAcs + i) * kTPB]; }
-        BV_DEV volatile double &wj(int k) const { return b[(kOffWj + k) * kTPB]; }
+        BV_DEV real &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV volatile real &tau(int i) const { return b[(kOffTau + (i - 1)) * kTPB]; }
+        BV_DEV volatile real &p(int i, int j) const { return b[(kOffP + i * N + j) * kTPB]; }
+        BV_DEV volatile real &el(int i) const { return b[(kOffEl + (i - 1)) * kTPB]; }
+        BV_DEV volatile real &tq(int i) const { return b[(kOffTq + (i - 1)) * kTPB]; }
+        BV_DEV volatile real &sd(int k) const { return b[(kOffSd + k) * kTPB]; }
+        BV_DEV volatile real &acs(int i) const { return b[(kOffAcs + i) * kTPB]; }
+        BV_DEV volatile real &wj(int k) const { return b[(kOffWj + k) * kTPB]; }
         BV_DEV volatile int &si(int k) const { return bi[k * kTPB]; }
         BV_DEV volatile int &ipvt(int i) const { return bi[(SI_COUNT + i) * kTPB]; }
-        BV_DEV void bind(double *smem, int tid) {
+        BV_DEV void bind(real *smem, int tid) {
             b = smem + tid;
             bi = reinterpret_cast<int *>(smem + (size_t)kHotDoubles * kTPB) + tid;
         }
     };
-    static constexpr size_t kSmemBytes = (sizeof(double) * kHotDoubles + sizeof(int) * kHotInts) * kTPB;
+    static constexpr size_t kSmemBytes = (sizeof(real) * kHotDoubles + sizeof(int) * kHotInts) * kTPB;
 #ifndef BVODE_THREAD_MINBLOCKS
 #define BVODE_THREAD_MINBLOCKS (384 / BVODE_THREAD_TPB)  // 12 warps per SM
 #endif
     static constexpr int kMinBlocks = BVODE_THREAD_MINBLOCKS;
 #else
     struct Hot {
-        double yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
-        double acsv[N], wjv[N * N];
+        real yhv[kLmax][N], tauv[kLmax + 1], pv[N][N], elv[kLmax + 1], tqv[6], sdv[SD_COUNT];
+        real acsv[N], wjv[N * N];
         int siv[SI_COUNT], ipv[N];
-        BV_DEV double &acs(int i) { return acsv[i]; }
-        BV_DEV double &wj(int k) { return wjv[k]; }
-        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
-        BV_DEV double &tau(int i) { return tauv[i]; }
-        BV_DEV double &p(int i, int j) { return pv[i][j]; }
-        BV_DEV double &el(int i) { return elv[i]; }
-        BV_DEV double &tq(int i) { return tqv[i]; }
-        BV_DEV double &sd(int k) { return sdv[k]; }
+        BV_DEV real &acs(int i) { return acsv[i]; }
+        BV_DEV real &wj(int k) { return wjv[k]; }
+        BV_DEV real &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV real &tau(int i) { return tauv[i]; }
+        BV_DEV real &p(int i, int j) { return pv[i][j]; }
+        BV_DEV real &el(int i) { return elv[i]; }
+        BV_DEV real &tq(int i) { return tqv[i]; }
+        BV_DEV real &sd(int k) { return sdv[k]; }
         BV_DEV int &si(int k) { return siv[k]; }
         BV_DEV int &ipvt(int i) { return ipv[i]; }
-        BV_DEV void bind(double *, int) {}
+        BV_DEV void bind(real *, int) {}
     };
     static constexpr size_t kSmemBytes = 0;
     static constexpr int kMinBlocks = 2;
@@ -115,9 +115,9 @@ struct ThreadPolicy {
                     // diagonal holds 1/u_kk after dgefa
 
     template <class ENG>
-    BV_DEV static double acsav_get(ENG &e, int i) { return e.hot.acs(i); }
+    BV_DEV static real acsav_get(ENG &e, int i) { return e.hot.acs(i); }
     template <class ENG>
-    BV_DEV static void acsav_set(ENG &e, int i, double x) { e.hot.acs(i) = x; }
+    BV_DEV static void acsav_set(ENG &e, int i, real x) { e.hot.acs(i) = x; }
 
     template <class ENG>
     BV_DEV static void lin_init(ENG &e) {
@@ -146,117 +146,117 @@ struct ThreadPolicy {
     }
 
     // dewset (M:3238-3273) for one component, or the problem's own (M:431-467)
-    BV_DEV static double ewt_of(int i, double yi, double rtol, double atol) {
+    BV_DEV static real ewt_of(int i, real yi, real rtol, real atol) {
         if constexpr (HasUserEwt<PROB>::value) return PROB::ewt(i, yi, rtol, atol);
         else return rtol * fabs(yi) + atol;
     }
     // dvnorm_default, M:3295-3311: sequential sum in index order, like the reference
     // (or the problem's own norm, M:468-503).
-    BV_DEV static double norm(const double (&v)[N], const double (&w)[N]) {
+    BV_DEV static real norm(const real (&v)[N], const real (&w)[N]) {
         if constexpr (HasUserNorm<PROB>::value) return PROB::norm(v, w);
-        double sum = 0.0;
+        real sum = BV_R(0.0);
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double p = v[i] * w[i];
+            const real p = v[i] * w[i];
             sum = sum + p * p;
         }
 #if BVODE_STRICT
-        return sqrt(sum / (double)N);
+        return sqrt(sum / (real)N);
 #else
-        return sqrt(sum * (1.0 / (double)N));
+        return sqrt(sum * (BV_R(1.0) / (real)N));
 #endif
     }
 #if !BVODE_STRICT
     // mean square (norm^2) -- the fast build tests squares and keeps sqrt off the main path
-    BV_DEV static double msq(const double (&v)[N], const double (&w)[N]) {
+    BV_DEV static real msq(const real (&v)[N], const real (&w)[N]) {
         if constexpr (HasUserNorm<PROB>::value) {  // a user norm is only known as a norm
-            const double nv = PROB::norm(v, w);
+            const real nv = PROB::norm(v, w);
             return nv * nv;
         }
-        double sum = 0.0;
+        real sum = BV_R(0.0);
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double p = v[i] * w[i];
+            const real p = v[i] * w[i];
             sum = sum + p * p;
         }
-        return sum * (1.0 / (double)N);
+        return sum * (BV_R(1.0) / (real)N);
     }
 #endif
-    BV_DEV static bool any_le_zero(const double (&v)[N]) {
+    BV_DEV static bool any_le_zero(const real (&v)[N]) {
         bool bad = false;
 #pragma unroll
-        for (int i = 0; i < N; i++) bad = bad || (v[i] <= 0.0);
+        for (int i = 0; i < N; i++) bad = bad || (v[i] <= BV_R(0.0));
         return bad;
     }
     // dvhin's upper bound loop, M:1784-1790
-    BV_DEV static double hin_upper_bound(double hub, const double (&y0)[N], const double (&ydot)[N],
+    BV_DEV static real hin_upper_bound(real hub, const real (&y0)[N], const real (&ydot)[N],
                                          const Tol &tol) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double delyi = 0.1 * fabs(y0[i]) + tol.atol(i);
-            const double afi = fabs(ydot[i]);
+            const real delyi = BV_R(0.1) * fabs(y0[i]) + tol.atol(i);
+            const real afi = fabs(ydot[i]);
             if (afi * hub > delyi) hub = delyi / afi;
         }
         return hub;
     }
-    BV_DEV static void f(double t, const double (&y)[N], double (&ydot)[N], const Par &par) {
+    BV_DEV static void f(real t, const real (&y)[N], real (&ydot)[N], const Par &par) {
         PROB::f(t, y, ydot, par);
     }
     // compute_imxer, M:1694-1706 (1-based index)
-    BV_DEV static int imxer(const double (&acor)[N], const double (&ewt)[N]) {
-        double big = 0.0;
+    BV_DEV static int imxer(const real (&acor)[N], const real (&ewt)[N]) {
+        real big = BV_R(0.0);
         int im = 1;
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const double size = fabs(acor[i] * ewt[i]);
+            const real size = fabs(acor[i] * ewt[i]);
             if (big < size) { big = size; im = i + 1; }
         }
         return im;
     }
 
     // ---- dgefa, LP:46-120 ----------------------------------------------------------
-    BV_DEV static int dgefa(double (&a)[N][N], int (&ipvt)[N]) {
+    BV_DEV static int dgefa(real (&a)[N][N], int (&ipvt)[N]) {
 #define a_(i, j) a[i][j]
         int info = 0;
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
             // idamax over rows k..N-1 of column k
             int l = k;
-            double dmax = fabs(a_(k, k));
+            real dmax = fabs(a_(k, k));
 #pragma unroll
             for (int i = k + 1; i < N; i++) {
-                const double xmag = fabs(a_(i, k));
+                const real xmag = fabs(a_(i, k));
                 if (xmag > dmax) { l = i; dmax = xmag; }
             }
             ipvt[k] = l;
-            double alk = a_(k, k);
+            real alk = a_(k, k);
 #pragma unroll
             for (int i = k + 1; i < N; i++) alk = (l == i) ? a_(i, k) : alk;
-            if (alk == 0.0) {
+            if (alk == BV_R(0.0)) {
                 info = k + 1;
             } else {
                 // interchange a(l,k) <-> a(k,k)
-                const double akk = a_(k, k);
+                const real akk = a_(k, k);
 #pragma unroll
                 for (int i = k + 1; i < N; i++) a_(i, k) = (l == i) ? akk : a_(i, k);
 #if BVODE_STRICT
                 a_(k, k) = alk;
-                const double t = -1.0 / alk;
+                const real t = -BV_R(1.0) / alk;
 #else
                 // fast build: the diagonal keeps 1/u_kk so that dgesl multiplies; one reciprocal
                 // serves both the multipliers and the back substitution
-                const double rp = qrcp(alk);
+                const real rp = qrcp(alk);
                 a_(k, k) = rp;
-                const double t = -rp;
+                const real t = -rp;
 #endif
 #pragma unroll
                 for (int i = k + 1; i < N; i++) a_(i, k) = t * a_(i, k);
 #pragma unroll
                 for (int j = k + 1; j < N; j++) {
-                    double tj = a_(k, j);
+                    real tj = a_(k, j);
 #pragma unroll
                     for (int i = k + 1; i < N; i++) tj = (l == i) ? a_(i, j) : tj;
-                    const double akj = a_(k, j);
+                    const real akj = a_(k, j);
 #pragma unroll
                     for (int i = k + 1; i < N; i++) a_(i, j) = (l == i) ? akj : a_(i, j);
                     a_(k, j) = tj;
@@ -266,7 +266,7 @@ struct ThreadPolicy {
             }
         }
         ipvt[N - 1] = N - 1;
-        if (a_(N - 1, N - 1) == 0.0) info = N;
+        if (a_(N - 1, N - 1) == BV_R(0.0)) info = N;
 #if !BVODE_STRICT
         a_(N - 1, N - 1) = qrcp(a_(N - 1, N - 1));
 #endif
@@ -275,15 +275,15 @@ struct ThreadPolicy {
     }
 
     // ---- dgesl job = 0, LP:206-225 -------------------------------------------------
-    BV_DEV static void dgesl(const double (&a)[N][N], const int (&ipvt)[N], double (&b)[N]) {
+    BV_DEV static void dgesl(const real (&a)[N][N], const int (&ipvt)[N], real (&b)[N]) {
 #define a_(i, j) a[i][j]
 #pragma unroll
         for (int k = 0; k < N - 1; k++) {
             const int l = ipvt[k];
-            double t = b[k];
+            real t = b[k];
 #pragma unroll
             for (int i = k + 1; i < N; i++) t = (l == i) ? b[i] : t;
-            const double bk = b[k];
+            const real bk = b[k];
 #pragma unroll
             for (int i = k + 1; i < N; i++) b[i] = (l == i) ? bk : b[i];
             b[k] = t;
@@ -297,7 +297,7 @@ struct ThreadPolicy {
 #else
             b[k] = b[k] * a_(k, k);
 #endif
-            const double t = -b[k];
+            const real t = -b[k];
 #pragma unroll
             for (int i = 0; i < k; i++) b[i] = b[i] + t * a_(i, k);
         }
@@ -306,22 +306,22 @@ struct ThreadPolicy {
 
     // dvsol, M:3139-3191 (returns iersl)
     template <class ENG>
-    BV_DEV static int solve(ENG &e, double (&x)[N]) {
+    BV_DEV static int solve(ENG &e, real (&x)[N]) {
         if constexpr (MITER == 3) {
             // diagonal approximation, M:3164-3181: wm(2) = hrl1 of the last update is
             // hot.p(1, 0), the inverted diagonal wm(3:) is hot.p(0, i)
-            const double phrl1 = e.hot.p(1, 0);
-            const double hrl1 = e.c.h * e.c.rl1;
+            const real phrl1 = e.hot.p(1, 0);
+            const real hrl1 = e.c.h * e.c.rl1;
             e.hot.p(1, 0) = hrl1;
             int iersl = 0;
             if (hrl1 != phrl1) {
-                const double r = hrl1 / phrl1;
+                const real r = hrl1 / phrl1;
 #pragma unroll
                 for (int i = 0; i < N; i++) {
                     if (iersl == 0) {
-                        const double di = 1.0 - r * (1.0 - 1.0 / e.hot.p(0, i));
-                        if (fabs(di) == 0.0) iersl = 1;
-                        else e.hot.p(0, i) = 1.0 / di;
+                        const real di = BV_R(1.0) - r * (BV_R(1.0) - BV_R(1.0) / e.hot.p(0, i));
+                        if (fabs(di) == BV_R(0.0)) iersl = 1;
+                        else e.hot.p(0, i) = BV_R(1.0) / di;
                     }
                 }
             }
@@ -331,7 +331,7 @@ struct ThreadPolicy {
             }
             return iersl;
         } else {
-            double a[N][N];
+            real a[N][N];
             int ipvt[N];
 #pragma unroll
             for (int i = 0; i < N; i++) {
@@ -349,26 +349,26 @@ struct ThreadPolicy {
     BV_DEV static void jac_setup_diag(ENG &e, int &ierpj) {
         Ctl &c = e.c;
         ierpj = 0;
-        const double hrl1 = c.h * c.rl1;
+        const real hrl1 = c.h * c.rl1;
         // M:3004-3028: diagonal Jacobian approximation from one extra f evaluation
         e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
         c.jcur = 1;
         e.hot.p(1, 0) = hrl1;  // wm(2)
-        const double r = c.rl1 * 0.1;
+        const real r = c.rl1 * BV_R(0.1);
 #pragma unroll
         for (int i = 0; i < N; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
-        double w[N];
+        real w[N];
         f(c.tn, e.y, w, e.par);
         e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
 #pragma unroll
         for (int i = 0; i < N; i++) {
             if (ierpj == 0) {
-                const double r0 = c.h * e.savf[i] - e.hot.yh(1, i);
-                const double di = 0.1 * r0 - c.h * (w[i] - e.savf[i]);
-                double wi = 1.0;
+                const real r0 = c.h * e.savf[i] - e.hot.yh(1, i);
+                const real di = BV_R(0.1) * r0 - c.h * (w[i] - e.savf[i]);
+                real wi = BV_R(1.0);
                 if (fabs(r0) >= kUround / e.ewt[i]) {
-                    if (fabs(di) == 0.0) ierpj = 1;
-                    else wi = 0.1 * r0 / di;
+                    if (fabs(di) == BV_R(0.0)) ierpj = 1;
+                    else wi = BV_R(0.1) * r0 / di;
                 }
                 if (ierpj == 0) e.hot.p(0, i) = wi;
             }
@@ -386,14 +386,14 @@ struct ThreadPolicy {
     BV_DEV static void jac_setup_dense(ENG &e, int &ierpj) {
         Ctl &c = e.c;
         ierpj = 0;
-        const double hrl1 = c.h * c.rl1;
+        const real hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
             if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;      // msbj = 50, M:1328
-            if (c.icf == 1 && c.drc < 0.2) jok = -1;              // ccmxj = 0.2, M:1327
+            if (c.icf == 1 && c.drc < BV_R(0.2)) jok = -1;              // ccmxj = 0.2, M:1327
             if (c.icf == 2) jok = -1;
         }
-        double P[N][N];
+        real P[N][N];
         if (jok == -1) {
             e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
@@ -402,18 +402,18 @@ struct ThreadPolicy {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int j = 0; j < N; j++) P[i][j] = 0.0;  // M:2947-2949
+                    for (int j = 0; j < N; j++) P[i][j] = BV_R(0.0);  // M:2947-2949
                 PROB::jac(c.tn, e.y, P, e.par);
             } else {
                 // finite differences, M:2959-2976 (ftem = acor)
-                double fac = norm(e.savf, e.ewt);
-                double r0 = 1000.0 * fabs(c.h) * kUround * (double)N * fac;
-                if (r0 == 0.0) r0 = 1.0;
-                const double srur = sqrt(kUround);  // wm(1), M:1326
+                real fac = norm(e.savf, e.ewt);
+                real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)N * fac;
+                if (r0 == BV_R(0.0)) r0 = BV_R(1.0);
+                const real srur = sqrt(kUround);  // wm(1), M:1326
 #pragma unroll
                 for (int j = 0; j < N; j++) {
-                    const double yj = e.y[j];
-                    const double r = dmax2(srur * fabs(yj), qdiv(r0, e.ewt[j]));
+                    const real yj = e.y[j];
+                    const real r = dmax2(srur * fabs(yj), qdiv(r0, e.ewt[j]));
                     e.y[j] = e.y[j] + r;
                     fac = qrcp(r);
                     f(c.tn, e.y, e.acor, e.par);
@@ -438,13 +438,13 @@ struct ThreadPolicy {
                     for (int j = 0; j < N; j++) P[i][j] = e.hot.wj(i * N + j);
             }
         }
-        const double con = -hrl1;
+        const real con = -hrl1;
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
             for (int j = 0; j < N; j++) P[i][j] = con * P[i][j];
 #pragma unroll
-        for (int i = 0; i < N; i++) P[i][i] = P[i][i] + 1.0;
+        for (int i = 0; i < N; i++) P[i][i] = P[i][i] + BV_R(1.0);
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
         int ipvt[N];
         const int ier = dgefa(P, ipvt);

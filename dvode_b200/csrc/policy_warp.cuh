@@ -39,8 +39,8 @@ struct ScratchDoublesOf { static constexpr int value = 0; };  // per-warp shared
 template <class P>
 struct ScratchDoublesOf<P, decltype((void)P::kScratchDoubles)> { static constexpr int value = P::kScratchDoubles; };
 
-BV_DEV double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
-BV_DEV double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+BV_DEV real shfl_d(real v, int src) { return __shfl_sync(kFull, v, src); }
+BV_DEV real shfl_xor_d(real v, int m) { return __shfl_xor_sync(kFull, v, m); }
 
 // Shared-memory access through a 32-bit shared address held in ONE register, with compile-time
 // byte offsets.  The address is made opaque to the compiler once: under the register cap of the
@@ -52,13 +52,13 @@ BV_DEV unsigned sm_addr(const void *p) {
     return a;
 }
 template <int OFF = 0>
-BV_DEV double lds_d(unsigned a) {
-    double v;
+BV_DEV real lds_d(unsigned a) {
+    real v;
     asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
     return v;
 }
 template <int OFF = 0>
-BV_DEV void sts_d(unsigned a, double v) {
+BV_DEV void sts_d(unsigned a, real v) {
     asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
 }
 template <int OFF = 0>
@@ -72,17 +72,17 @@ BV_DEV void lds_i4(unsigned a, int &v0, int &v1, int &v2, int &v3) {  // 16-byte
 }
 // b += t*m on the lanes where (unsigned)x < (unsigned)lim: one compare and one predicated fma (the
 // compiler's own choice is an unconditional fma plus two selects on the dependent chain).
-BV_DEV void fma_if_ltu(double &b, double t, double m, int x, int lim) {
+BV_DEV void fma_if_ltu(real &b, real t, real m, int x, int lim) {
     asm("{\n .reg .pred p;\n setp.lt.u32 p, %3, %4;\n @p fma.rn.f64 %0, %1, %2, %0;\n}"
         : "+d"(b) : "d"(t), "d"(m), "r"(x), "r"(lim));
 }
 // 16-byte shared accesses (two doubles); the address must be 16-byte aligned
 template <int OFF = 0>
-BV_DEV void lds_d2(unsigned a, double &v0, double &v1) {
+BV_DEV void lds_d2(unsigned a, real &v0, real &v1) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(v0), "=d"(v1) : "r"(a), "n"(OFF));
 }
 template <int OFF = 0>
-BV_DEV void sts_d2(unsigned a, double v0, double v1) {
+BV_DEV void sts_d2(unsigned a, real v0, real v1) {
     asm volatile("st.shared.v2.f64 [%0+%1], {%2,%3};" ::"r"(a), "n"(OFF), "d"(v0), "d"(v1) : "memory");
 }
 BV_DEV void sts_i(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -95,16 +95,16 @@ struct WarpCommon {
     static constexpr int kLmax = kLmaxOf(METH);
     static_assert(N <= 32, "warp-per-system policy holds one component per lane");
     static constexpr int NLOC = 1;
-    typedef double Par[PROB::NPAR_LANE > 0 ? PROB::NPAR_LANE : 1];
+    typedef real Par[PROB::NPAR_LANE > 0 ? PROB::NPAR_LANE : 1];
 
     BV_DEV static int lane() { return threadIdx.x & 31; }
 
     // Per-lane vector element kept in its HBM state slot (cold data).
     struct GlobalVec {
-        double *p;      // this lane's element of slot 0
+        real *p;      // this lane's element of slot 0
         size_t stride;  // distance between slots (= nsys * 32)
-        BV_DEV double get(int k) const { return p[(size_t)k * stride]; }
-        BV_DEV void set(int k, double v) const { p[(size_t)k * stride] = v; }
+        BV_DEV real get(int k) const { return p[(size_t)k * stride]; }
+        BV_DEV void set(int k, real v) const { p[(size_t)k * stride] = v; }
     };
     // Hot data.  The Nordsieck column entries of this lane's component live in registers.  The
     // control state that is REPLICATED on the 32 lanes (tau, el, tq, conp / hu / hnew / crate /
@@ -118,117 +118,117 @@ struct WarpCommon {
                          kOffSd = kOffTq + 5, kHotD = kOffSd + SD_COUNT,
                          kWarpHotDoubles = kHotD + (SI_COUNT + 1) / 2;
     struct Hot {
-        double yhv[kLmax][1];
-        volatile double *b;  // the counters follow the doubles: si(k) is addressed from b as well (one pointer live)
-        BV_DEV double &yh(int j, int i) { return yhv[j][i]; }
-        BV_DEV volatile double &tau(int i) const { return b[kOffTau + (i - 1)]; }
-        BV_DEV volatile double &el(int i) const { return b[kOffEl + (i - 1)]; }
-        BV_DEV volatile double &tq(int i) const { return b[kOffTq + (i - 1)]; }
-        BV_DEV volatile double &sd(int k) const { return b[kOffSd + k]; }
+        real yhv[kLmax][1];
+        volatile real *b;  // the counters follow the doubles: si(k) is addressed from b as well (one pointer live)
+        BV_DEV real &yh(int j, int i) { return yhv[j][i]; }
+        BV_DEV volatile real &tau(int i) const { return b[kOffTau + (i - 1)]; }
+        BV_DEV volatile real &el(int i) const { return b[kOffEl + (i - 1)]; }
+        BV_DEV volatile real &tq(int i) const { return b[kOffTq + (i - 1)]; }
+        BV_DEV volatile real &sd(int k) const { return b[kOffSd + k]; }
         BV_DEV volatile int &si(int k) const { return reinterpret_cast<volatile int *>(b + kHotD)[k]; }
-        BV_DEV void bind(double *base, int) {
+        BV_DEV void bind(real *base, int) {
             b = base;
         }
     };
     struct AcSav {  // NLOC = 1: a register
-        double v;
-        BV_DEV double get(int) const { return v; }
-        BV_DEV void set(int, double x) { v = x; }
+        real v;
+        BV_DEV real get(int) const { return v; }
+        BV_DEV void set(int, real x) { v = x; }
     };
     template <class ENG>
-    BV_DEV static double acsav_get(ENG &e, int) { return e.acsav.v; }
+    BV_DEV static real acsav_get(ENG &e, int) { return e.acsav.v; }
     template <class ENG>
-    BV_DEV static void acsav_set(ENG &e, int, double x) { e.acsav.v = x; }
+    BV_DEV static void acsav_set(ENG &e, int, real x) { e.acsav.v = x; }
     struct Tol {  // this lane's rtol / atol (0 for lanes >= N)
-        double r, a;
-        BV_DEV double rtol(int) const { return r; }
-        BV_DEV double atol(int) const { return a; }
+        real r, a;
+        BV_DEV real rtol(int) const { return r; }
+        BV_DEV real atol(int) const { return a; }
     };
 
     // dewset_default for this lane's component, M:3238-3273, or the problem's own (M:431-467)
-    BV_DEV static double ewt_of(int, double yi, double rtol, double atol) {
+    BV_DEV static real ewt_of(int, real yi, real rtol, real atol) {
         if constexpr (HasUserEwt<PROB>::value) return PROB::ewt(lane(), yi, rtol, atol);
         else return rtol * fabs(yi) + atol;
     }
     // a user-supplied norm (M:468-503) in its lane-wise form: a fold over the components
-    BV_DEV static double user_norm(double v, double w) {
-        const double p = PROB::norm_term(v, w);
+    BV_DEV static real user_norm(real v, real w) {
+        const real p = PROB::norm_term(v, w);
 #if BVODE_STRICT
-        double acc = PROB::norm_init;
+        real acc = PROB::norm_init;
 #pragma unroll 1
         for (int i = 0; i < N; i++) acc = PROB::norm_combine(acc, shfl_d(p, i));
 #else
-        double acc = (lane() < N) ? PROB::norm_combine(PROB::norm_init, p) : PROB::norm_init;
+        real acc = (lane() < N) ? PROB::norm_combine(PROB::norm_init, p) : PROB::norm_init;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) acc = PROB::norm_combine(acc, shfl_xor_d(acc, m));
 #endif
         return PROB::norm_final(acc);
     }
     // dvnorm_default, M:3295-3311.  Lanes >= N carry v = 0.
-    BV_DEV static double norm(const double (&v)[1], const double (&w)[1]) {
+    BV_DEV static real norm(const real (&v)[1], const real (&w)[1]) {
         if constexpr (HasLaneNorm<PROB>::value) return user_norm(v[0], w[0]);
-        const double p = v[0] * w[0];
-        const double p2 = p * p;
+        const real p = v[0] * w[0];
+        const real p2 = p * p;
 #if BVODE_STRICT
-        double sum = 0.0;
+        real sum = BV_R(0.0);
 #pragma unroll
         for (int i = 0; i < N; i++) sum = sum + shfl_d(p2, i);
-        return sqrt(sum / (double)N);
+        return sqrt(sum / (real)N);
 #else
-        double sum = (lane() < N) ? p2 : 0.0;
+        real sum = (lane() < N) ? p2 : BV_R(0.0);
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
-        return sqrt(sum * (1.0 / (double)N));
+        return sqrt(sum * (BV_R(1.0) / (real)N));
 #endif
     }
 #if !BVODE_STRICT
-    BV_DEV static double msq(const double (&v)[1], const double (&w)[1]) {
+    BV_DEV static real msq(const real (&v)[1], const real (&w)[1]) {
         if constexpr (HasLaneNorm<PROB>::value) {  // a user norm is only known as a norm
-            const double nv = user_norm(v[0], w[0]);
+            const real nv = user_norm(v[0], w[0]);
             return nv * nv;
         }
-        const double p = v[0] * w[0];
-        double sum = (lane() < N) ? p * p : 0.0;
+        const real p = v[0] * w[0];
+        real sum = (lane() < N) ? p * p : BV_R(0.0);
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
-        return sum * (1.0 / (double)N);
+        return sum * (BV_R(1.0) / (real)N);
     }
 #endif
-    BV_DEV static bool any_le_zero(const double (&v)[1]) {
-        return __any_sync(kFull, (lane() < N) && (v[0] <= 0.0)) != 0;
+    BV_DEV static bool any_le_zero(const real (&v)[1]) {
+        return __any_sync(kFull, (lane() < N) && (v[0] <= BV_R(0.0))) != 0;
     }
     // dvhin's upper bound loop, M:1784-1790: sequential in i because hub feeds the test
-    BV_DEV static double hin_upper_bound(double hub, const double (&y0)[1], const double (&ydot)[1],
+    BV_DEV static real hin_upper_bound(real hub, const real (&y0)[1], const real (&ydot)[1],
                                          const Tol &tol) {
-        const double delyi = 0.1 * fabs(y0[0]) + tol.a;
-        const double afi = fabs(ydot[0]);
+        const real delyi = BV_R(0.1) * fabs(y0[0]) + tol.a;
+        const real afi = fabs(ydot[0]);
 #pragma unroll 1
         for (int i = 0; i < N; i++) {
-            const double d = shfl_d(delyi, i), a = shfl_d(afi, i);
+            const real d = shfl_d(delyi, i), a = shfl_d(afi, i);
             if (a * hub > d) hub = d / a;
         }
         return hub;
     }
-    BV_DEV static void f(double t, const double (&y)[1], double (&ydot)[1], const Par &par) {
+    BV_DEV static void f(real t, const real (&y)[1], real (&ydot)[1], const Par &par) {
         ydot[0] = PROB::f_lane(t, y[0], par, lane());
-        if (lane() >= N) ydot[0] = 0.0;
+        if (lane() >= N) ydot[0] = BV_R(0.0);
     }
     // compute_imxer, M:1694-1706: first index of the largest |acor*ewt| (strict '<')
-    BV_DEV static int imxer(const double (&acor)[1], const double (&ewt)[1]) {
-        double v = (lane() < N) ? fabs(acor[0] * ewt[0]) : -1.0;
+    BV_DEV static int imxer(const real (&acor)[1], const real (&ewt)[1]) {
+        real v = (lane() < N) ? fabs(acor[0] * ewt[0]) : -BV_R(1.0);
         int idx = lane();
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
-            const double ov = shfl_xor_d(v, m);
+            const real ov = shfl_xor_d(v, m);
             const int oi = __shfl_xor_sync(kFull, idx, m);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        return (v > 0.0) ? idx + 1 : 1;
+        return (v > BV_R(0.0)) ? idx + 1 : 1;
     }
     // idamax (BL:311-359) over the lanes with `act`: the lowest such lane holding the largest |x|.
     // |x| of finite doubles order like their bit patterns, so two 32-bit warp reductions and one
     // ballot replace the five-round shuffle tournament of argmax_abs below.
-    BV_DEV static unsigned max_abs_ballot(double x, bool act) {
+    BV_DEV static unsigned max_abs_ballot(real x, bool act) {
         const unsigned hi = act ? ((unsigned)__double2hiint(x) & 0x7fffffffu) : 0u;
         const unsigned lo = (unsigned)__double2loint(x);
         const unsigned mhi = __reduce_max_sync(kFull, hi);
@@ -237,23 +237,23 @@ struct WarpCommon {
         return __ballot_sync(kFull, c1 && (lo == mlo));
     }
     // idamax over lanes [lo, hi]: returns the lane of the first maximum of |x|
-    BV_DEV static int argmax_abs(double x, int lo, int hi) {
+    BV_DEV static int argmax_abs(real x, int lo, int hi) {
         const int ln = lane();
-        double v = (ln >= lo && ln <= hi) ? fabs(x) : -1.0;
+        real v = (ln >= lo && ln <= hi) ? fabs(x) : -BV_R(1.0);
         int idx = ln;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
-            const double ov = shfl_xor_d(v, m);
+            const real ov = shfl_xor_d(v, m);
             const int oi = __shfl_xor_sync(kFull, idx, m);
             if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
         return idx;
     }
     // FD increment of component `lane`, M:2966 / M:3065: r = max(srur*|y|, r0/ewt)
-    BV_DEV static double fd_r0(const Ctl &c, const double (&savf)[1], const double (&ewt)[1]) {
-        const double fac = norm(savf, ewt);
-        double r0 = 1000.0 * fabs(c.h) * kUround * (double)N * fac;
-        if (r0 == 0.0) r0 = 1.0;
+    BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[1], const real (&ewt)[1]) {
+        const real fac = norm(savf, ewt);
+        real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)N * fac;
+        if (r0 == BV_R(0.0)) r0 = BV_R(1.0);
         return r0;
     }
 };
@@ -314,7 +314,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     static_assert(MITER == 1 || MITER == 2, "dense policy");
 
     struct Lin {
-        double *p;      // shared memory, N rows x LDP: P = I - h*rl1*J, then its LU factors.
+        real *p;      // shared memory, N rows x LDP: P = I - h*rl1*J, then its LU factors.
                         // Fast build: the pivot entry of each row holds 1/u_kk after dgefa.
         int *perm;      // shared memory: perm[k] = lane (row) that is the pivot of step k
         GlobalVec wjs;  // row `lane` of the saved Jacobian, element j at slot j (mf > 0)
@@ -349,7 +349,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // compared as integers (|v| of a finite double orders like its bit pattern): two warp
     // reductions instead of a five-round shuffle tournament.  Several rows of the same largest
     // magnitude: the first in LINPACK's row order wins.
-    BV_DEV static int pivot_lane(double v, bool act, int pos) {
+    BV_DEV static int pivot_lane(real v, bool act, int pos) {
         unsigned b = Base::max_abs_ballot(v, act);
         if (b & (b - 1)) {  // warp-uniform
             const bool c2 = (b >> lane()) & 1u;
@@ -370,16 +370,16 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // from 5 wavefronts (broadcast + row load + row store) to 3.
     BV_DEV static int dgefa(Lin &lin) {
         const int ln = lane();
-        const bool real = real_lane();
+        const bool live = real_lane();
         const unsigned pa = sm_addr(lin.p);                 // the matrix
-        const unsigned rowa = pa + (real ? ln : 0) * (LDP * 8);  // this lane's row (lanes >= N never write)
+        const unsigned rowa = pa + (live ? ln : 0) * (LDP * 8);  // this lane's row (lanes >= N never write)
         const unsigned perma = pa + kPermOff * 8;
-        int pos = real ? ln : 64;
+        int pos = live ? ln : 64;
         int info = 0;
         // idamax + the interchange of LP:96-110 (the two rows exchange positions) for column k,
         // v = this lane's entry of that column
-        auto pick = [&](int k, double v, int &l, double &alk) {
-            l = pivot_lane(v, real && (pos >= k), pos);
+        auto pick = [&](int k, real v, int &l, real &alk) {
+            l = pivot_lane(v, live && (pos >= k), pos);
             alk = shfl_d(v, l);
             const int pl = __shfl_sync(kFull, pos, l);
             if (ln == k) lin.ipv = l;
@@ -392,57 +392,57 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
 #pragma unroll 1
         while (k < N - 1) {
             const unsigned rk = rowa + k * 8;
-            const double v = lds_d(rk);
+            const real v = lds_d(rk);
             int l;
-            double alk;
+            real alk;
             pick(k, v, l, alk);
             int adv = 1;
-            if (alk == 0.0) {
+            if (alk == BV_R(0.0)) {
                 info = k + 1;
             } else {
-                const bool below = real && (pos > k);
+                const bool below = live && (pos > k);
 #if BVODE_STRICT
-                const double t = -1.0 / alk;
-                const double m = t * v;  // the multipliers (LP:102-104)
+                const real t = -BV_R(1.0) / alk;
+                const real m = t * v;  // the multipliers (LP:102-104)
                 if (below) sts_d(rk, m);
 #else
                 // fast build: the pivot row keeps 1/u_kk (dgesl multiplies); the rows ALREADY
                 // pivoted scale their entry of column k by -1/u_kk as well, so that back
                 // substitution is b_i += b_k * (-u_ik/u_kk) with the un-normalised b_k -- one
                 // shuffle and one fma per step on the dependent chain, x_k = b_k/u_kk at the end
-                const double rp = qrcp(alk);
-                const double t = -rp;
-                const double m = t * v;
-                if (real) sts_d(rk, (ln == l) ? rp : m);
+                const real rp = qrcp(alk);
+                const real t = -rp;
+                const real m = t * v;
+                if (live) sts_d(rk, (ln == l) ? rp : m);
 #endif
                 const unsigned pr0 = pa + l * (LDP * 8);  // the pivot row: broadcasts
                 bool pair = false;
                 if (k + 1 < N - 1) {
                     // ---- column k+1 after step k, and its pivot
                     adv = 2;
-                    double w = lds_d<8>(rk);
-                    const double p1k = lds_d<8>(pr0 + k * 8);
+                    real w = lds_d<8>(rk);
+                    const real p1k = lds_d<8>(pr0 + k * 8);
                     if (below) w = w + p1k * m;
                     int l1;
-                    double alk1;
+                    real alk1;
                     pick(k + 1, w, l1, alk1);
-                    if (alk1 == 0.0) {
+                    if (alk1 == BV_R(0.0)) {
                         info = k + 2;  // LP:87-88: nothing is eliminated in column k+1; step k is completed below
                     } else {
                         pair = true;
-                        const bool below1 = real && (pos > k + 1);
+                        const bool below1 = live && (pos > k + 1);
 #if BVODE_STRICT
-                        const double t1 = -1.0 / alk1;
-                        const double m1 = t1 * w;
+                        const real t1 = -BV_R(1.0) / alk1;
+                        const real m1 = t1 * w;
                         if (below1) sts_d<8>(rk, m1);
                         if (ln == l1) sts_d<8>(rk, w);
 #else
-                        const double rp1 = qrcp(alk1);
-                        const double t1 = -rp1;
-                        const double m1 = t1 * w;
-                        if (real) sts_d<8>(rk, (ln == l1) ? rp1 : m1);
+                        const real rp1 = qrcp(alk1);
+                        const real t1 = -rp1;
+                        const real m1 = t1 * w;
+                        if (live) sts_d<8>(rk, (ln == l1) ? rp1 : m1);
 #endif
-                        const double ml1 = shfl_d(m, l1);  // multiplier of the second pivot row in step k
+                        const real ml1 = shfl_d(m, l1);  // multiplier of the second pivot row in step k
                         const unsigned pr1 = pa + l1 * (LDP * 8);
                         // every lane runs the loop (the __syncwarp between the loads and the stores
                         // orders the other lanes' reads of row l1 before its owner's update of it)
@@ -450,9 +450,9 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                         int cnt = N - 2 - k;
 #pragma unroll 1
                         for (; cnt >= 4; cnt -= 4, ar += 32, a1 += 32, a2 += 32) {
-                            const double p0 = lds_d<0>(a1), p1 = lds_d<8>(a1), p2 = lds_d<16>(a1), p3 = lds_d<24>(a1);
-                            const double q0 = lds_d<0>(a2), q1 = lds_d<8>(a2), q2 = lds_d<16>(a2), q3 = lds_d<24>(a2);
-                            double r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
+                            const real p0 = lds_d<0>(a1), p1 = lds_d<8>(a1), p2 = lds_d<16>(a1), p3 = lds_d<24>(a1);
+                            const real q0 = lds_d<0>(a2), q1 = lds_d<8>(a2), q2 = lds_d<16>(a2), q3 = lds_d<24>(a2);
+                            real r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
                             __syncwarp();
                             r0 = r0 + p0 * m; r1 = r1 + p1 * m; r2 = r2 + p2 * m; r3 = r3 + p3 * m;
                             if (below1) {
@@ -467,8 +467,8 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                         }
 #pragma unroll 1
                         for (; cnt > 0; cnt--, ar += 8, a1 += 8, a2 += 8) {
-                            const double p0 = lds_d(a1), q0 = lds_d(a2);
-                            double r0 = lds_d(ar);
+                            const real p0 = lds_d(a1), q0 = lds_d(a2);
+                            real r0 = lds_d(ar);
                             __syncwarp();
                             r0 = r0 + p0 * m;
                             if (below1) r0 = r0 + (q0 + p0 * ml1) * m1;
@@ -482,8 +482,8 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     int cnt = N - 1 - k;
 #pragma unroll 1
                     for (; cnt >= 4; cnt -= 4, ar += 32, ap += 32) {
-                        const double p0 = lds_d<0>(ap), p1 = lds_d<8>(ap), p2 = lds_d<16>(ap), p3 = lds_d<24>(ap);
-                        const double r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
+                        const real p0 = lds_d<0>(ap), p1 = lds_d<8>(ap), p2 = lds_d<16>(ap), p3 = lds_d<24>(ap);
+                        const real r0 = lds_d<0>(ar), r1 = lds_d<8>(ar), r2 = lds_d<16>(ar), r3 = lds_d<24>(ar);
                         sts_d<0>(ar, r0 + p0 * m);
                         sts_d<8>(ar, r1 + p1 * m);
                         sts_d<16>(ar, r2 + p2 * m);
@@ -497,15 +497,15 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             k += adv;
         }
         {   // the row that is left is the last pivot
-            const int l = __ffs((int)__ballot_sync(kFull, real && (pos == N - 1))) - 1;
+            const int l = __ffs((int)__ballot_sync(kFull, live && (pos == N - 1))) - 1;
             if (ln == N - 1) lin.ipv = l;
             sts_i(perma + (N - 1) * 4, l);
-            const double v = lds_d<(N - 1) * 8>(rowa);
-            const double alk = shfl_d(v, l);
-            if (alk == 0.0) info = N;
+            const real v = lds_d<(N - 1) * 8>(rowa);
+            const real alk = shfl_d(v, l);
+            if (alk == BV_R(0.0)) info = N;
 #if !BVODE_STRICT
-            const double rp = qrcp(alk);
-            if (real) sts_d<(N - 1) * 8>(rowa, (ln == l) ? rp : -rp * v);  // column N-1 of U, scaled like the others
+            const real rp = qrcp(alk);
+            if (live) sts_d<(N - 1) * 8>(rowa, (ln == l) ? rp : -rp * v);  // column N-1 of U, scaled like the others
 #endif
         }
         lin.pos = pos;
@@ -537,30 +537,30 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         // single-lane store and one broadcast load of the pivot row, instead of a load and a store of every
         // lane's own row (the shared-memory data pipe is what bounds this kernel, ncu r1o).
         const int ln = lane();
-        const bool real = real_lane();
+        const bool live = real_lane();
         const unsigned pa = sm_addr(lin.p);
-        const unsigned rowa = pa + (real ? ln : 0) * (LDP * 8);
+        const unsigned rowa = pa + (live ? ln : 0) * (LDP * 8);
         const unsigned perma = pa + kPermOff * 8;
         const unsigned bufa = pa + kVecOff * 8;
         constexpr int NE = (N + 1) & ~1;  // entries moved in pairs; r[N] (N odd) is a dummy
-        double r[NE];
+        real r[NE];
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < NE; j += 2) lds_d2(rowa + j * 8, r[j], r[j + 1]);
-        bool unused = real;  // this lane's row has not been a pivot row yet
+        bool unused = live;  // this lane's row has not been a pivot row yet
         int info = 0;
 #pragma unroll 1
         for (int k = 0; k < N && info == 0; k++) {
-            const double v = r[0];
+            const real v = r[0];
             const unsigned b = Base::max_abs_ballot(v, unused);
             const int l = __ffs((int)b) - 1;  // ties: the lowest row
-            const double piv = shfl_d(v, l);
+            const real piv = shfl_d(v, l);
             if (ln == k) lin.ipv = l;
             sts_i(perma + k * 4, l);
-            if (piv == 0.0) {
+            if (piv == BV_R(0.0)) {
                 info = k + 1;
             } else {
-                const double rp = qrcp(piv);
+                const real rp = qrcp(piv);
                 const bool mine = (ln == l);
                 if (mine) {
                     // the pivot row publishes its entries of the other columns UNSCALED, rotated, with a 1 in the
@@ -569,27 +569,27 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     // so the new pivot row is P/pivot, the others lose their column-k entry, and the last place
                     // (column k of the inverse) receives t itself.  The single-lane section is the stores only.
 #pragma unroll
-                    for (int j = 0; j + 1 < N; j += 2) sts_d2(bufa + j * 8, r[j + 1], (j + 2 < N) ? r[j + 2] : 1.0);
-                    if (N & 1) sts_d(bufa + (N - 1) * 8, 1.0);
+                    for (int j = 0; j + 1 < N; j += 2) sts_d2(bufa + j * 8, r[j + 1], (j + 2 < N) ? r[j + 2] : BV_R(1.0));
+                    if (N & 1) sts_d(bufa + (N - 1) * 8, BV_R(1.0));
 #pragma unroll
-                    for (int j = 1; j < N; j++) r[j] = 0.0;
+                    for (int j = 1; j < N; j++) r[j] = BV_R(0.0);
                     unused = false;
                 }
                 __syncwarp();
-                const double t = mine ? rp : -v * rp;
+                const real t = mine ? rp : -v * rp;
 #pragma unroll
                 for (int j = 0; j < NE; j += 2) {
-                    double p0, p1;
+                    real p0, p1;
                     lds_d2(bufa + j * 8, p0, p1);
-                    const double a0 = (j + 1 < N) ? r[j + 1] : 0.0;
-                    const double a1 = (j + 2 < N) ? r[j + 2] : 0.0;
+                    const real a0 = (j + 1 < N) ? r[j + 1] : BV_R(0.0);
+                    const real a1 = (j + 2 < N) ? r[j + 2] : BV_R(0.0);
                     r[j] = fma(t, p0, a0);
                     if (j + 1 < N) r[j + 1] = fma(t, p1, a1);
                 }
                 __syncwarp();
             }
         }
-        if (real) {
+        if (live) {
 #pragma unroll
             for (int j = 0; j < NE; j += 2) sts_d2(rowa + j * 8, r[j], r[j + 1]);
         }
@@ -598,29 +598,29 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         return info;
     }
     template <class ENG>
-    BV_DEV static int solve_inverse(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve_inverse(ENG &e, real (&x)[1]) {
         const Lin &lin = e.lin;
-        const bool real = real_lane();
+        const bool live = real_lane();
         const unsigned pa = sm_addr(lin.p);
-        const unsigned rowa = pa + (real ? lane() : 0) * (LDP * 8);
+        const unsigned rowa = pa + (live ? lane() : 0) * (LDP * 8);
         const unsigned veca = pa + kVecOff * 8;
         // b[perm[j]] to lane j, then to shared memory: every lane needs all of them
-        const double bp = shfl_d(x[0], lin.ipv);
+        const real bp = shfl_d(x[0], lin.ipv);
         __syncwarp();
-        sts_d(veca + lane() * 8, real ? bp : 0.0);
+        sts_d(veca + lane() * 8, live ? bp : BV_R(0.0));
         __syncwarp();
-        double s0 = 0.0, s1 = 0.0;
+        real s0 = BV_R(0.0), s1 = BV_R(0.0);
         constexpr int NP = N & ~1;
 #pragma unroll 8
         for (int j = 0; j < NP; j += 2) {
-            double a0, a1, b0, b1;
+            real a0, a1, b0, b1;
             lds_d2(rowa + j * 8, a0, a1);
             lds_d2(veca + j * 8, b0, b1);
             s0 = fma(a0, b0, s0);
             s1 = fma(a1, b1, s1);
         }
         if (N & 1) s0 = fma(lds_d(rowa + (N - 1) * 8), lds_d(veca + (N - 1) * 8), s0);
-        const double s = real ? s0 + s1 : 0.0;
+        const real s = live ? s0 + s1 : BV_R(0.0);
         x[0] = shfl_d(s, lin.ipv);  // x_k is the sum of row perm[k]
         return 0;
     }
@@ -629,29 +629,29 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // One step: t = b of the pivot row of column k; rows taking part add t * (their entry of
     // column k).  FWD: rows below the pivot (multipliers); !FWD: rows above it.
     template <bool FWD, int OFF>
-    BV_DEV static void solve_step(double &b, unsigned rk, int l, int pos, int k, bool real) {
-        const double m = lds_d<OFF * 8>(rk);
-        const bool part = real && (FWD ? (pos > k + OFF) : (pos < k + OFF));
+    BV_DEV static void solve_step(real &b, unsigned rk, int l, int pos, int k, bool live) {
+        const real m = lds_d<OFF * 8>(rk);
+        const bool part = live && (FWD ? (pos > k + OFF) : (pos < k + OFF));
 #if BVODE_STRICT
         if (!FWD && pos == k + OFF) b = b / m;
-        const double t = FWD ? shfl_d(b, l) : -shfl_d(b, l);
+        const real t = FWD ? shfl_d(b, l) : -shfl_d(b, l);
         if (part) b = b + t * m;
 #else
-        const double t = shfl_d(b, l);
-        b = b + t * (part ? m : 0.0);  // the select is off the dependent chain (measured faster
+        const real t = shfl_d(b, l);
+        b = b + t * (part ? m : BV_R(0.0));  // the select is off the dependent chain (measured faster
                                        // here than one predicated fma: 162k vs 157k systems/s)
 #endif
     }
     template <class ENG>
-    BV_DEV static int solve(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve(ENG &e, real (&x)[1]) {
         if constexpr (kInverse) return solve_inverse(e, x);
         const Lin &lin = e.lin;
-        const bool real = real_lane();
+        const bool live = real_lane();
         const unsigned pa = sm_addr(lin.p);
-        const unsigned rowa = pa + (real ? lane() : 0) * (LDP * 8);
+        const unsigned rowa = pa + (live ? lane() : 0) * (LDP * 8);
         const unsigned perma = pa + kPermOff * 8;
         const int pos = lin.pos;
-        double b = x[0];
+        real b = x[0];
         // forward elimination, k = 0 .. N-2
         int k = 0;
 #pragma unroll 1
@@ -663,33 +663,33 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             // from broadcast entries, one shuffle latency per four steps -- was measured SLOWER,
             // 149k vs 165k systems/s: the kernel is bound by instruction and shared-memory
             // throughput, not by this chain)
-            solve_step<true, 0>(b, rk, l0, pos, k, real);
-            solve_step<true, 1>(b, rk, l1, pos, k, real);
-            solve_step<true, 2>(b, rk, l2, pos, k, real);
-            solve_step<true, 3>(b, rk, l3, pos, k, real);
+            solve_step<true, 0>(b, rk, l0, pos, k, live);
+            solve_step<true, 1>(b, rk, l1, pos, k, live);
+            solve_step<true, 2>(b, rk, l2, pos, k, live);
+            solve_step<true, 3>(b, rk, l3, pos, k, live);
         }
 #pragma unroll 1
-        for (; k < N - 1; k++) solve_step<true, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
+        for (; k < N - 1; k++) solve_step<true, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, live);
         // back substitution, k = N-1 .. kend (fast build: column 0 has no row above it)
         constexpr int kend = BVODE_STRICT ? 0 : 1;
         k = N - 1;
         // (perm[] is read four entries at a time from 16-byte aligned addresses: single steps down to k = 3 mod 4)
 #pragma unroll 1
-        for (; (k & 3) != 3 && k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
+        for (; (k & 3) != 3 && k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, live);
 #pragma unroll 1
         for (; k - 3 >= kend; k -= 4) {
             const unsigned rk = rowa + k * 8;
             int l0, l1, l2, l3;
             lds_i4(perma + (k - 3) * 4, l3, l2, l1, l0);
-            solve_step<false, 0>(b, rk, l0, pos, k, real);
-            solve_step<false, -1>(b, rk, l1, pos, k, real);
-            solve_step<false, -2>(b, rk, l2, pos, k, real);
-            solve_step<false, -3>(b, rk, l3, pos, k, real);
+            solve_step<false, 0>(b, rk, l0, pos, k, live);
+            solve_step<false, -1>(b, rk, l1, pos, k, live);
+            solve_step<false, -2>(b, rk, l2, pos, k, live);
+            solve_step<false, -3>(b, rk, l3, pos, k, live);
         }
 #pragma unroll 1
-        for (; k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, real);
+        for (; k >= kend; k--) solve_step<false, 0>(b, rowa + k * 8, lds_i(perma + k * 4), pos, k, live);
 #if !BVODE_STRICT
-        if (real) b = b * lds_d(rowa + pos * 8);  // x_k = b_k / u_kk
+        if (live) b = b * lds_d(rowa + pos * 8);  // x_k = b_k / u_kk
 #endif
         x[0] = shfl_d(b, lin.ipv);  // component k is on the lane that was pivot k
         return 0;
@@ -701,13 +701,13 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         Ctl &c = e.c;
         Lin &l = e.lin;
         const int ln = lane();
-        double *row = l.p + ln * LDP;
+        real *row = l.p + ln * LDP;
         ierpj = 0;
-        const double hrl1 = c.h * c.rl1;
+        const real hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
             if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;
-            if (c.icf == 1 && c.drc < 0.2) jok = -1;
+            if (c.icf == 1 && c.drc < BV_R(0.2)) jok = -1;
             if (c.icf == 2) jok = -1;
         }
         __syncwarp();
@@ -718,7 +718,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             if constexpr (MITER == 1) {
                 if (ln < N) {
 #pragma unroll 1
-                    for (int j = 0; j < N; j++) row[j] = 0.0;
+                    for (int j = 0; j < N; j++) row[j] = BV_R(0.0);
                 }
                 if constexpr (HasJacDenseFull<PROB>::value)  // the reference's jac(neq, t, y, ml, mu, pd, nrowpd)
                     PROB::jac_dense_full(c.tn, e.y[0], l.p, LDP, e.par, ln);
@@ -726,15 +726,15 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     PROB::jac_row(c.tn, e.y[0], row, e.par, ln);  // every lane calls (it may shuffle); lanes >= N must not write
             } else {
                 // finite differences, M:2959-2976: column j for all rows at once
-                const double r0 = Base::fd_r0(c, e.savf, e.ewt);
-                const double srur = sqrt(kUround);
-                const double rmine = dmax2(srur * fabs(e.y[0]), qdiv(r0, e.ewt[0]));
-                const double ysave = e.y[0];
+                const real r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const real srur = sqrt(kUround);
+                const real rmine = dmax2(srur * fabs(e.y[0]), qdiv(r0, e.ewt[0]));
+                const real ysave = e.y[0];
 #pragma unroll 1
                 for (int j = 0; j < N; j++) {
-                    const double r = shfl_d(rmine, j);
+                    const real r = shfl_d(rmine, j);
                     if (ln == j) e.y[0] = ysave + r;
-                    const double fac = qrcp(r);
+                    const real fac = qrcp(r);
                     Base::f(c.tn, e.y, e.acor, e.par);
                     if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
                     e.y[0] = ysave;
@@ -753,11 +753,11 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 for (int j = 0; j < N; j++) row[j] = l.wjs.get(j);
             }
         }
-        const double con = -hrl1;
+        const real con = -hrl1;
         if (ln < N) {
 #pragma unroll 1
             for (int j = 0; j < N; j++) row[j] = con * row[j];
-            row[ln] = row[ln] + 1.0;
+            row[ln] = row[ln] + BV_R(1.0);
         }
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
         const int ier = factor(l);
@@ -790,11 +790,11 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
     static_assert(MITER == 0 || MITER == 3, "plain policy");
 
     struct Lin {
-        double diag;   // wm(2 + lane): inverted diagonal of P (miter = 3)
-        double phrl1;  // wm(2): h*rl1 at the last update (replicated on all lanes)
+        real diag;   // wm(2 + lane): inverted diagonal of P (miter = 3)
+        real phrl1;  // wm(2): h*rl1 at the last update (replicated on all lanes)
     };
     template <class ENG>
-    BV_DEV static void lin_init(ENG &e) { e.lin.diag = 1.0; e.lin.phrl1 = 0.0; }
+    BV_DEV static void lin_init(ENG &e) { e.lin.diag = BV_R(1.0); e.lin.phrl1 = BV_R(0.0); }
     static int smem_doubles(int, int, bool) { return 0; }
     static constexpr int kLaneSlots = kLmax + 2 + 2;  // yh, acsav, acor, diag, phrl1
     static constexpr int kLaneIntSlots = 1;
@@ -809,19 +809,19 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
     }
 
     template <class ENG>
-    BV_DEV static int solve(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve(ENG &e, real (&x)[1]) {
         Lin &l = e.lin;
-        const double hrl1 = e.c.h * e.c.rl1;
-        const double phrl1 = l.phrl1;
+        const real hrl1 = e.c.h * e.c.rl1;
+        const real phrl1 = l.phrl1;
         l.phrl1 = hrl1;
         if (hrl1 != phrl1) {
-            const double r = hrl1 / phrl1;
-            const double di = 1.0 - r * (1.0 - 1.0 / l.diag);
-            const bool zero = (lane() < N) && (fabs(di) == 0.0);
+            const real r = hrl1 / phrl1;
+            const real di = BV_R(1.0) - r * (BV_R(1.0) - BV_R(1.0) / l.diag);
+            const bool zero = (lane() < N) && (fabs(di) == BV_R(0.0));
             // the reference stops at the first zero: entries before it are already updated
             const unsigned zmask = __ballot_sync(kFull, zero);
             const int first = zmask ? (__ffs((int)zmask) - 1) : 32;
-            if (lane() < first) l.diag = 1.0 / di;
+            if (lane() < first) l.diag = BV_R(1.0) / di;
             if (zmask) return 1;
         }
         x[0] = l.diag * x[0];
@@ -833,22 +833,22 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
         Ctl &c = e.c;
         Lin &l = e.lin;
         ierpj = 0;
-        const double hrl1 = c.h * c.rl1;
+        const real hrl1 = c.h * c.rl1;
         e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
         c.jcur = 1;
         l.phrl1 = hrl1;
-        const double r = c.rl1 * 0.1;
+        const real r = c.rl1 * BV_R(0.1);
         e.y[0] = e.y[0] + r * (c.h * e.savf[0] - e.hot.yh(1, 0));
-        double w[1];
+        real w[1];
         Base::f(c.tn, e.y, w, e.par);
         e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
-        const double r0 = c.h * e.savf[0] - e.hot.yh(1, 0);
-        const double di = 0.1 * r0 - c.h * (w[0] - e.savf[0]);
+        const real r0 = c.h * e.savf[0] - e.hot.yh(1, 0);
+        const real di = BV_R(0.1) * r0 - c.h * (w[0] - e.savf[0]);
         const bool big = (lane() < N) && (fabs(r0) >= kUround / e.ewt[0]);
-        const bool zero = big && (fabs(di) == 0.0);
+        const bool zero = big && (fabs(di) == BV_R(0.0));
         const unsigned zmask = __ballot_sync(kFull, zero);
         const int first = zmask ? (__ffs((int)zmask) - 1) : 32;
-        if (lane() < first) l.diag = big ? 0.1 * r0 / di : 1.0;
+        if (lane() < first) l.diag = big ? BV_R(0.1) * r0 / di : BV_R(1.0);
         if (zmask) ierpj = 1;
     }
 };
@@ -879,8 +879,8 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     static_assert(MITER == 4 || MITER == 5, "band policy");
 
     struct Lin {
-        double *abd;   // shared memory, ld x N
-        double *wjs;   // shared memory, mband x N (mf > 0)
+        real *abd;   // shared memory, ld x N
+        real *wjs;   // shared memory, mband x N (mf > 0)
         int ml, mu, ld;
         int ipv;       // lane k holds ipvt(k+1) as a 0-based row of the full matrix
     };
@@ -918,7 +918,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         {
             const int jz = ln + 1;
             if (jz >= j0 && jz <= j1) {
-                for (int i = m + 1 - jz; i <= ml; i++) ABD(i, jz) = 0.0;
+                for (int i = m + 1 - jz; i <= ml; i++) ABD(i, jz) = BV_R(0.0);
             }
         }
         __syncwarp();
@@ -930,27 +930,27 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
 #pragma unroll 1
         for (int k = 1; k <= n - 1; k++, ck += ld8) {
             jz = jz + 1;
-            if (jz <= n && ln < ml) sts_d(base + (jz - 1) * ld8 + ln * 8, 0.0);  // LP:318-323
+            if (jz <= n && ln < ml) sts_d(base + (jz - 1) * ld8 + ln * 8, BV_R(0.0));  // LP:318-323
             __syncwarp();
             const int lm = (ml < n - k) ? ml : n - k;
             // l = idamax(lm+1, abd(m,k)) + m - 1: lanes 0..lm look at rows m..m+lm of column k
             const bool cact = (ln <= lm);
-            double v = 0.0;
+            real v = BV_R(0.0);
             if (cact) v = lds_d(ck);
             const int lofs = __ffs((int)Base::max_abs_ballot(v, cact)) - 1;  // pivot row - diagonal row
             const int piv = lofs + k;                                        // 1-based row of the matrix
             if (ln == k - 1) l.ipv = piv - 1;
-            const double alk = shfl_d(v, lofs);
-            if (alk == 0.0) {
+            const real alk = shfl_d(v, lofs);
+            if (alk == BV_R(0.0)) {
                 info = k;
             } else {
                 const bool swap = (lofs != 0);  // warp-uniform
                 if (swap) {  // interchange, LP:335-339, in registers
-                    const double akk = shfl_d(v, 0);
+                    const real akk = shfl_d(v, 0);
                     if (ln == lofs) v = akk;
                     if (ln == 0) v = alk;
                 }
-                const double t = -qrcp(alk);
+                const real t = -qrcp(alk);
                 if (ln >= 1 && cact) v = t * v;  // dscal, LP:343
                 if (cact && (swap || ln >= 1)) sts_d(ck, v);
                 const int jun = mu + piv;
@@ -961,9 +961,9 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                 // mm = m - (lane+1) is the row of abd that holds matrix row k in column j
                 if (ln < ju - k) {
                     const unsigned amm = base + (k + ln) * ld8 + (m - ln - 2) * 8;
-                    const double tj = lds_d(amm + lofs * 8);
+                    const real tj = lds_d(amm + lofs * 8);
                     if (swap) {
-                        const double tmm = lds_d(amm);
+                        const real tmm = lds_d(amm);
                         sts_d(amm + lofs * 8, tmm);
                         sts_d(amm, tj);
                     }
@@ -972,8 +972,8 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                     int cnt = lm;
 #pragma unroll 1
                     for (; cnt >= 4; cnt -= 4, aj += 32, ak += 32) {
-                        const double p0 = lds_d<0>(ak), p1 = lds_d<8>(ak), p2 = lds_d<16>(ak), p3 = lds_d<24>(ak);
-                        const double r0 = lds_d<0>(aj), r1 = lds_d<8>(aj), r2 = lds_d<16>(aj), r3 = lds_d<24>(aj);
+                        const real p0 = lds_d<0>(ak), p1 = lds_d<8>(ak), p2 = lds_d<16>(ak), p3 = lds_d<24>(ak);
+                        const real r0 = lds_d<0>(aj), r1 = lds_d<8>(aj), r2 = lds_d<16>(aj), r3 = lds_d<24>(aj);
                         sts_d<0>(aj, r0 + tj * p0);
                         sts_d<8>(aj, r1 + tj * p1);
                         sts_d<16>(aj, r2 + tj * p2);
@@ -986,7 +986,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             }
         }
         if (ln == n - 1) l.ipv = n - 1;
-        if (ABD(m, n) == 0.0) info = n;
+        if (ABD(m, n) == BV_R(0.0)) info = n;
         __syncwarp();
 #if !BVODE_STRICT
         // fast build: the diagonal keeps 1/u_kk so that dgbsl multiplies, and the entries of U
@@ -994,7 +994,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         // with the un-normalised b_k (one shuffle and one fma per step on the dependent chain)
         if (ln < n) {
             const int j = ln + 1;
-            const double rp = qrcp(ABD(m, j));
+            const real rp = qrcp(ABD(m, j));
             ABD(m, j) = rp;
             const int lmj = ((j < m) ? j : m) - 1;
             for (int i = 1; i <= lmj; i++) ABD(m - i, j) = -rp * ABD(m - i, j);
@@ -1009,26 +1009,26 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     // shared address per lane that advances by (ld-1) doubles per column, for the multipliers
     // below the diagonal (forward elimination), the diagonal and U above it (back substitution).
     template <class ENG>
-    BV_DEV static int solve(ENG &e, double (&x)[1]) {
+    BV_DEV static int solve(ENG &e, real (&x)[1]) {
         const Lin &l = e.lin;
         const int ln = lane();
         const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
-        const bool real = (N == 32) || (ln < n);
+        const bool live = (N == 32) || (ln < n);
         const int step = (l.ld - 1) * 8;
-        const unsigned a1 = sm_addr(l.abd) + (m - 1 + (real ? ln : 0)) * 8;  // column 1
-        double b = x[0];
+        const unsigned a1 = sm_addr(l.abd) + (m - 1 + (live ? ln : 0)) * 8;  // column 1
+        real b = x[0];
         if (ml != 0) {
             // any row interchange at all?  (warp-uniform; none for diagonally dominant P)
-            const bool swaps = __any_sync(kFull, real && (l.ipv != ln)) != 0;
+            const bool swaps = __any_sync(kFull, live && (l.ipv != ln)) != 0;
             unsigned a = a1;
 #pragma unroll 4
             for (int k = 1; k <= n - 1; k++, a += step) {
-                double t;
+                real t;
                 if (swaps) {
                     const int lp = __shfl_sync(kFull, l.ipv, k - 1);  // 0-based
                     t = shfl_d(b, lp);
                     if (lp != k - 1) {
-                        const double bk = shfl_d(b, k - 1);
+                        const real bk = shfl_d(b, k - 1);
                         if (ln == lp) b = bk;
                         if (ln == k - 1) b = t;
                     }
@@ -1036,13 +1036,13 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                     t = shfl_d(b, k - 1);
                 }
                 // rows k+1 .. min(k+ml, n)
-                const bool part = real && ((unsigned)(ln - k) < (unsigned)ml);
-                const double mv = lds_d(a);
+                const bool part = live && ((unsigned)(ln - k) < (unsigned)ml);
+                const real mv = lds_d(a);
 #if BVODE_STRICT
                 if (part) b = b + t * mv;
 #else
                 (void)part;
-                fma_if_ltu(b, t, mv, ln - k, real ? ml : 0);
+                fma_if_ltu(b, t, mv, ln - k, live ? ml : 0);
 #endif
             }
         }
@@ -1051,21 +1051,21 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
 #if BVODE_STRICT
 #pragma unroll 4
             for (int k = n; k >= 1; k--, a -= step) {
-                const double mv = lds_d(a);
+                const real mv = lds_d(a);
                 if (ln == k - 1) b = b / mv;
-                const double t = -shfl_d(b, k - 1);
+                const real t = -shfl_d(b, k - 1);
                 // rows max(k-m+1, 1) .. k-1
-                const bool part = real && ((unsigned)(k - 2 - ln) < (unsigned)(m - 1));
+                const bool part = live && ((unsigned)(k - 2 - ln) < (unsigned)(m - 1));
                 if (part) b = b + t * mv;
             }
 #else
 #pragma unroll 4
             for (int k = n; k >= 2; k--, a -= step) {
-                const double mv = lds_d(a);
-                const double t = shfl_d(b, k - 1);
-                fma_if_ltu(b, t, mv, k - 2 - ln, real ? m - 1 : 0);
+                const real mv = lds_d(a);
+                const real t = shfl_d(b, k - 1);
+                fma_if_ltu(b, t, mv, k - 2 - ln, live ? m - 1 : 0);
             }
-            if (real) b = b * lds_d(a1 + ln * step);  // x_k = b_k / u_kk
+            if (live) b = b * lds_d(a1 + ln * step);  // x_k = b_k / u_kk
 #endif
         }
         x[0] = b;
@@ -1081,11 +1081,11 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         const int n = N, ml = l.ml, mu = l.mu;
         const int mband = ml + mu + 1, meband = mband + ml;
         ierpj = 0;
-        const double hrl1 = c.h * c.rl1;
+        const real hrl1 = c.h * c.rl1;
         int jok = SAVEJ ? 1 : -1;
         if (SAVEJ) {
             if (e.hot.si(SI_NST) == 0 || e.hot.si(SI_NST) > e.hot.si(SI_NSLJ) + 50) jok = -1;
-            if (c.icf == 1 && c.drc < 0.2) jok = -1;
+            if (c.icf == 1 && c.drc < BV_R(0.2)) jok = -1;
             if (c.icf == 2) jok = -1;
         }
         __syncwarp();
@@ -1096,7 +1096,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             if constexpr (MITER == 4) {
                 // zero wm(3:), then jac fills rows ml+1..meband of each column (M:3044-3047)
                 if (ln < n)
-                    for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = 0.0;
+                    for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = BV_R(0.0);
                 __syncwarp();
                 // pd(i - j + mu + 1, j) = df_i/dy_j with pd = abd rows ml+1.. (nrowpd = meband)
                 if constexpr (HasJacBandFull<PROB>::value)  // the reference's jac: pd = &abd(ml+1, 1), nrowpd = ld (M:3047)
@@ -1106,11 +1106,11 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             } else {
                 // banded finite differences, M:3056-3081
                 const int mba = (mband < n) ? mband : n;
-                const double r0 = Base::fd_r0(c, e.savf, e.ewt);
-                const double srur = sqrt(kUround);
-                const double ysave = e.y[0];
+                const real r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const real srur = sqrt(kUround);
+                const real ysave = e.y[0];
                 // yh(:,1) is what the reference restores y from (M:3070); identical to ysave
-                const double rmine = dmax2(srur * fabs(ysave), qdiv(r0, e.ewt[0]));
+                const real rmine = dmax2(srur * fabs(ysave), qdiv(r0, e.ewt[0]));
 #pragma unroll 1
                 for (int j = 1; j <= mba; j++) {
                     const bool mine = (ln < n) && (((ln + 1 - j) % mband) == 0) && (ln + 1 >= j);
@@ -1118,13 +1118,13 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                     Base::f(c.tn, e.y, e.acor, e.par);
                     e.y[0] = ysave;
                     // column jj = j, j+mband, ...: rows i1..i2, stored at abd(i - jj + mband, jj)
-                    const double diff = e.acor[0] - e.savf[0];  // row ln+1
+                    const real diff = e.acor[0] - e.savf[0];  // row ln+1
                     const int i = ln + 1;
                     // the perturbed column that covers row i in this group (bands do not overlap)
 #pragma unroll 1
                     for (int jj = j; jj <= n; jj += mband) {
-                        const double r = shfl_d(rmine, jj - 1);
-                        const double fac = qrcp(r);
+                        const real r = shfl_d(rmine, jj - 1);
+                        const real fac = qrcp(r);
                         const int i1 = (jj - mu > 1) ? jj - mu : 1;
                         const int i2 = (jj + ml < n) ? jj + ml : n;
                         if (i >= i1 && i <= i2) ABD(i - jj + mband, jj) = diff * fac;
@@ -1146,10 +1146,10 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         }
         __syncwarp();
         // multiply by -h*rl1 (all meband rows, M:3093) and add the identity (M:3094-3098)
-        const double con = -hrl1;
+        const real con = -hrl1;
         if (ln < n) {
             for (int i = 1; i <= meband; i++) ABD(i, ln + 1) = con * ABD(i, ln + 1);
-            ABD(mband, ln + 1) = ABD(mband, ln + 1) + 1.0;
+            ABD(mband, ln + 1) = ABD(mband, ln + 1) + BV_R(1.0);
         }
         __syncwarp();
         e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;

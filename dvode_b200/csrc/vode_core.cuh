@@ -55,7 +55,7 @@ enum : int {
 // the counters -- is reached through the policy's `Hot` storage (shared memory for the
 // thread-per-system policy, registers for the warp policies) by the slot ids below.
 struct Ctl {
-    double h, hscal, eta, tn, rc, prl1, rl1, drc, acnrm;
+    real h, hscal, eta, tn, rc, prl1, rl1, drc, acnrm;
     int nq, L, nqwait, newq, newh, jstart, icf, ipup, jcur, kflag;
 };
 // SD_ETAQ / SD_ETAQM1: the reference's etaq / etaqm1 (M:258-259), which only an istate = 3 call
@@ -69,16 +69,16 @@ enum : int { SI_NST = 0, SI_NFE, SI_NJE, SI_NLU, SI_NNI, SI_NCFN, SI_NETF, SI_NQ
 using Opts = ::BvOpts;  // batch-uniform optional inputs (M:729-751)
 
 template <int LO, int HI>
-BV_DEV double pick(const double *a, int idx) {
-    double r = a[LO];
+BV_DEV real pick(const real *a, int idx) {
+    real r = a[LO];
 #pragma unroll
     for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? a[i] : r;
     return r;
 }
 
 template <int LO, int HI, class HOT>
-BV_DEV double pick_tau(HOT &hot, int idx) {
-    double r = hot.tau(LO);
+BV_DEV real pick_tau(HOT &hot, int idx) {
+    real r = hot.tau(LO);
 #pragma unroll
     for (int i = LO + 1; i <= HI; i++) r = (idx == i) ? hot.tau(i) : r;
     return r;
@@ -92,23 +92,23 @@ BV_DEV double pick_tau(HOT &hot, int idx) {
 template <class HOT>
 BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     const int nq = c.nq, L = c.L;
-    const double h = c.h;
-    double el[kLmaxBdf + 1], tq[6];
+    const real h = c.h;
+    real el[kLmaxBdf + 1], tq[6];
 #pragma unroll
-    for (int i = 3; i <= kLmaxBdf; i++) el[i] = 0.0;
-    el[1] = 1.0;
-    el[2] = 1.0;
-    double tauv[kLmaxBdf + 1];
+    for (int i = 3; i <= kLmaxBdf; i++) el[i] = BV_R(0.0);
+    el[1] = BV_R(1.0);
+    el[2] = BV_R(1.0);
+    real tauv[kLmaxBdf + 1];
 #pragma unroll
     for (int i = 1; i <= kLmaxBdf; i++) tauv[i] = hot.tau(i);
-    double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
+    real alph0 = -BV_R(1.0), ahatn0 = -BV_R(1.0), hsum = h, rxi = BV_R(1.0), rxis = BV_R(1.0);
     if (nq != 1) {
 #pragma unroll
         for (int j = 1; j <= kMaxOrdBdf - 2; j++) {
             if (j <= nq - 2) {
                 hsum = hsum + tauv[j];
                 rxi = qdiv(h, hsum);
-                alph0 = alph0 - 1.0 / (double)(j + 1);
+                alph0 = alph0 - BV_R(1.0) / (real)(j + 1);
 #pragma unroll
                 for (int iback = 1; iback <= j + 1; iback++) {
                     const int i = (j + 3) - iback;
@@ -126,26 +126,26 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
             if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
         }
     }
-    const double t1 = 1.0 - ahatn0 + alph0;
-    const double t2 = 1.0 + (double)nq * t1;
-    const double elL = pick<2, kLmaxBdf>(el, L);
+    const real t1 = BV_R(1.0) - ahatn0 + alph0;
+    const real t2 = BV_R(1.0) + (real)nq * t1;
+    const real elL = pick<2, kLmaxBdf>(el, L);
     tq[2] = fabs(qdiv(alph0 * t2, t1));
-    tq[1] = 0.0;
-    tq[3] = 0.0;
+    tq[1] = BV_R(0.0);
+    tq[3] = BV_R(0.0);
 #if BVODE_STRICT
     tq[5] = fabs(t2 / (elL * rxi / rxis));
     if (c.nqwait == 1) {
-        const double cnqm1 = rxis / elL;
-        const double t3 = alph0 + recip_int(nq);
-        const double t4 = ahatn0 + rxi;
-        double elp = t3 / (1.0 - t4 + t3);
+        const real cnqm1 = rxis / elL;
+        const real t3 = alph0 + recip_int(nq);
+        const real t4 = ahatn0 + rxi;
+        real elp = t3 / (BV_R(1.0) - t4 + t3);
         tq[1] = fabs(elp / cnqm1);
         hsum = hsum + pick<1, kLmaxBdf>(tauv, nq);
         rxi = h / hsum;
-        const double t5 = alph0 - recip_int(nq + 1);
-        const double t6 = ahatn0 - rxi;
-        elp = t2 / (1.0 - t6 + t5);
-        tq[3] = fabs(elp * rxi * ((double)L + 1.0) * t5);
+        const real t5 = alph0 - recip_int(nq + 1);
+        const real t6 = ahatn0 - rxi;
+        elp = t2 / (BV_R(1.0) - t6 + t5);
+        tq[3] = fabs(elp * rxi * ((real)L + BV_R(1.0)) * t5);
     }
 #else
     // fast build: the nested quotients of M:2478-2489 as single quotients
@@ -154,17 +154,17 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
     //   (t2/(1-t6+t5)) * rxi*(L+1)*t5   = t2*rxi*(L+1)*t5 / (1-t6+t5)
     tq[5] = fabs(qdiv(t2 * rxis, elL * rxi));
     if (c.nqwait == 1) {
-        const double t3 = alph0 + recip_int(nq);
-        const double t4 = ahatn0 + rxi;
-        tq[1] = fabs(qdiv(t3 * elL, (1.0 - t4 + t3) * rxis));
+        const real t3 = alph0 + recip_int(nq);
+        const real t4 = ahatn0 + rxi;
+        tq[1] = fabs(qdiv(t3 * elL, (BV_R(1.0) - t4 + t3) * rxis));
         hsum = hsum + pick<1, kLmaxBdf>(tauv, nq);
         rxi = qdiv(h, hsum);
-        const double t5 = alph0 - recip_int(nq + 1);
-        const double t6 = ahatn0 - rxi;
-        tq[3] = fabs(qdiv(t2 * rxi * ((double)L + 1.0) * t5, 1.0 - t6 + t5));
+        const real t5 = alph0 - recip_int(nq + 1);
+        const real t6 = ahatn0 - rxi;
+        tq[3] = fabs(qdiv(t2 * rxi * ((real)L + BV_R(1.0)) * t5, BV_R(1.0) - t6 + t5));
     }
 #endif
-    tq[4] = 0.1 * tq[2];
+    tq[4] = BV_R(0.1) * tq[2];
 #pragma unroll
     for (int i = 1; i <= kLmaxBdf; i++) hot.el(i) = el[i];
     // tq(1), tq(3) are only read by the order selection of the step whose dvset ran with
@@ -185,18 +185,18 @@ BV_DEV void dvset_bdf(Ctl &c, HOT &hot) {
 // el is returned in a local array (the reference leaves it in el(:), which dvset overwrites
 // before its next use).  Returns t1 = (-alph0 - alph1)/prod for the order increase.
 template <class HOT>
-BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf + 1]) {
+BV_DEV real dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, real (&el)[kLmaxBdf + 1]) {
     const int nq = c.nq;
 #pragma unroll
-    for (int j = 0; j <= kLmaxBdf; j++) el[j] = 0.0;
-    el[3] = 1.0;
-    double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0;
-    double hsum = up ? c.hscal : 0.0;
+    for (int j = 0; j <= kLmaxBdf; j++) el[j] = BV_R(0.0);
+    el[3] = BV_R(1.0);
+    real alph0 = -BV_R(1.0), alph1 = BV_R(1.0), prod = BV_R(1.0), xiold = BV_R(1.0);
+    real hsum = up ? c.hscal : BV_R(0.0);
     const int jmax = up ? nq - 1 : nq - 2;
 #if !BVODE_STRICT
-    const double rhscal = qrcp(c.hscal);
+    const real rhscal = qrcp(c.hscal);
 #endif
-    double tauv[kLmaxBdf + 1];
+    real tauv[kLmaxBdf + 1];
 #pragma unroll
     for (int i = 1; i <= kLmaxBdf; i++) tauv[i] = hot.tau(i);
 #pragma unroll
@@ -204,18 +204,18 @@ BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf
         if (j <= jmax) {
             hsum = hsum + (up ? tauv[j + 1] : tauv[j]);
 #if BVODE_STRICT
-            const double xi = hsum / c.hscal;
-            const double rxi = up ? 1.0 / xi : 0.0;
+            const real xi = hsum / c.hscal;
+            const real rxi = up ? BV_R(1.0) / xi : BV_R(0.0);
 #else
-            const double xi = hsum * rhscal;  // one reciprocal of hscal, and 1/xi = hscal/hsum
-            const double rxi = up ? c.hscal * qrcp(hsum) : 0.0;
+            const real xi = hsum * rhscal;  // one reciprocal of hscal, and 1/xi = hscal/hsum
+            const real rxi = up ? c.hscal * qrcp(hsum) : BV_R(0.0);
 #endif
             if (up) {
                 prod = prod * xi;
-                alph0 = alph0 - 1.0 / (double)(j + 1);
+                alph0 = alph0 - BV_R(1.0) / (real)(j + 1);
                 alph1 = alph1 + rxi;
             }
-            const double x = up ? xiold : xi;
+            const real x = up ? xiold : xi;
 #pragma unroll
             for (int iback = 1; iback <= j + 1; iback++) {
                 const int i = (j + 4) - iback;
@@ -231,15 +231,15 @@ BV_DEV double dvjust_coeffs_bdf(Ctl &c, HOT &hot, bool up, double (&el)[kLmaxBdf
 // call switches an Adams history at order 6 to BDF (maxord = nq - 1, M:2059-2068).  Run-time loops, out of
 // line.  el(3:nq) such that yh(:,j) -= yh(:,L)*el(j).
 template <class HOT>
-static __device__ __noinline__ void dvjust_coeffs_bdf_down_wide(Ctl &c, HOT &hot, double (&el)[kLmaxBdf + 1]) {
+static __device__ __noinline__ void dvjust_coeffs_bdf_down_wide(Ctl &c, HOT &hot, real (&el)[kLmaxBdf + 1]) {
     const int nq = c.nq;  // == kMaxOrdBdf + 1
-    double w[kLmaxOf(1) + 2];
-    for (int j = 0; j < kLmaxOf(1) + 2; j++) w[j] = 0.0;
-    w[3] = 1.0;
-    double hsum = 0.0;
+    real w[kLmaxOf(1) + 2];
+    for (int j = 0; j < kLmaxOf(1) + 2; j++) w[j] = BV_R(0.0);
+    w[3] = BV_R(1.0);
+    real hsum = BV_R(0.0);
     for (int j = 1; j <= nq - 2; j++) {
         hsum = hsum + hot.tau(j);
-        const double xi = hsum / c.hscal;
+        const real xi = hsum / c.hscal;
         const int jp1 = j + 1;
         for (int iback = 1; iback <= jp1; iback++) {
             const int i = (j + 4) - iback;
@@ -256,68 +256,68 @@ template <class HOT>
 BV_DEV void dvset_adams(Ctl &c, HOT &hot) {
     constexpr int LM = kLmaxOf(1);
     const int nq = c.nq, L = c.L, nqm1 = nq - 1;
-    const double h = c.h;
-    double el[LM + 1], em[LM + 2], tq[6], tauv[LM + 1];
-    for (int i = 1; i <= LM; i++) { tauv[i] = hot.tau(i); el[i] = 0.0; }  // el above L: zero (see accept update)
-    tq[1] = 0.0; tq[2] = 0.0; tq[3] = 0.0; tq[5] = 0.0;
-    const double flotl = (double)L;
+    const real h = c.h;
+    real el[LM + 1], em[LM + 2], tq[6], tauv[LM + 1];
+    for (int i = 1; i <= LM; i++) { tauv[i] = hot.tau(i); el[i] = BV_R(0.0); }  // el above L: zero (see accept update)
+    tq[1] = BV_R(0.0); tq[2] = BV_R(0.0); tq[3] = BV_R(0.0); tq[5] = BV_R(0.0);
+    const real flotl = (real)L;
     if (nq != 1) {
-        double hsum = h;
-        em[1] = 1.0;
-        const double flotnq = flotl - 1.0;
-        for (int i = 2; i <= L; i++) em[i] = 0.0;
+        real hsum = h;
+        em[1] = BV_R(1.0);
+        const real flotnq = flotl - BV_R(1.0);
+        for (int i = 2; i <= L; i++) em[i] = BV_R(0.0);
         for (int j = 1; j <= nqm1; j++) {
             if ((j == nqm1) && (c.nqwait == 1)) {
-                double s = 1.0, csum = 0.0;
+                real s = BV_R(1.0), csum = BV_R(0.0);
                 for (int i = 1; i <= nqm1; i++) {
-                    csum = csum + s * em[i] / (double)(i + 1);
+                    csum = csum + s * em[i] / (real)(i + 1);
                     s = -s;
                 }
                 tq[1] = em[nqm1] / (flotnq * csum);
             }
-            const double rxi = h / hsum;
+            const real rxi = h / hsum;
             for (int iback = 1; iback <= j; iback++) {
                 const int i = (j + 2) - iback;
                 em[i] = em[i] + em[i - 1] * rxi;
             }
             hsum = hsum + tauv[j];
         }
-        double s = 1.0, em0 = 0.0, csum = 0.0;
+        real s = BV_R(1.0), em0 = BV_R(0.0), csum = BV_R(0.0);
         for (int i = 1; i <= nq; i++) {
-            const double floti = (double)i;
+            const real floti = (real)i;
             em0 = em0 + s * em[i] / floti;
-            csum = csum + s * em[i] / (floti + 1.0);
+            csum = csum + s * em[i] / (floti + BV_R(1.0));
             s = -s;
         }
-        s = 1.0 / em0;
-        el[1] = 1.0;
-        for (int i = 1; i <= nq; i++) el[i + 1] = s * em[i] / (double)i;
-        const double xi = hsum / h;
+        s = BV_R(1.0) / em0;
+        el[1] = BV_R(1.0);
+        for (int i = 1; i <= nq; i++) el[i + 1] = s * em[i] / (real)i;
+        const real xi = hsum / h;
         tq[2] = xi * em0 / csum;
         tq[5] = xi / el[L];
         if (c.nqwait == 1) {
-            const double rxi = 1.0 / xi;
+            const real rxi = BV_R(1.0) / xi;
             for (int iback = 1; iback <= nq; iback++) {
                 const int i = (L + 1) - iback;
                 em[i] = em[i] + em[i - 1] * rxi;
             }
-            s = 1.0;
-            csum = 0.0;
+            s = BV_R(1.0);
+            csum = BV_R(0.0);
             for (int i = 1; i <= L; i++) {
-                csum = csum + s * em[i] / (double)(i + 1);
+                csum = csum + s * em[i] / (real)(i + 1);
                 s = -s;
             }
             tq[3] = flotl * em0 / csum;
         }
     } else {
-        el[1] = 1.0;
-        el[2] = 1.0;
-        tq[1] = 1.0;
-        tq[2] = 2.0;
-        tq[3] = 6.0 * tq[2];
-        tq[5] = 1.0;
+        el[1] = BV_R(1.0);
+        el[2] = BV_R(1.0);
+        tq[1] = BV_R(1.0);
+        tq[2] = BV_R(2.0);
+        tq[3] = BV_R(6.0) * tq[2];
+        tq[5] = BV_R(1.0);
     }
-    tq[4] = 0.1 * tq[2];
+    tq[4] = BV_R(0.1) * tq[2];
     for (int i = 1; i <= LM; i++) hot.el(i) = el[i];
     hot.tq(2) = tq[2];
     hot.tq(4) = tq[4];
@@ -331,21 +331,21 @@ BV_DEV void dvset_adams(Ctl &c, HOT &hot) {
 // dvjust, Adams order decrease (M:2669-2692): el(3:nq) such that yh(:,j) -= yh(:,L)*el(j).
 // (The Adams order increase only zeroes the new column, M:2661-2666.)
 template <class HOT>
-BV_DEV void dvjust_coeffs_adams_down(Ctl &c, HOT &hot, double (&el)[kLmaxOf(1) + 1]) {
+BV_DEV void dvjust_coeffs_adams_down(Ctl &c, HOT &hot, real (&el)[kLmaxOf(1) + 1]) {
     constexpr int LM = kLmaxOf(1);
     const int nq = c.nq;
-    for (int j = 0; j <= LM; j++) el[j] = 0.0;
-    el[2] = 1.0;
-    double hsum = 0.0;
+    for (int j = 0; j <= LM; j++) el[j] = BV_R(0.0);
+    el[2] = BV_R(1.0);
+    real hsum = BV_R(0.0);
     for (int j = 1; j <= nq - 2; j++) {
         hsum = hsum + hot.tau(j);
-        const double xi = hsum / c.hscal;
+        const real xi = hsum / c.hscal;
         for (int iback = 1; iback <= j + 1; iback++) {
             const int i = (j + 3) - iback;
             el[i] = el[i] * xi + el[i - 1];
         }
     }
-    for (int j = 2; j <= nq - 1; j++) el[j + 1] = (double)nq * el[j] / (double)j;
+    for (int j = 2; j <= nq - 1; j++) el[j + 1] = (real)nq * el[j] / (real)j;
 }
 
 template <int METH, class HOT>
@@ -364,12 +364,12 @@ BV_DEV int choose_ratio(T lq, T lm, T lp) {
 }
 // The same decision from double-precision logs: the rare case where the single-precision
 // screen is too close to call.  Out of line to keep the step loop small.
-static __device__ __noinline__ int choose_ratio_f64(double xq, double xm, double xp, double scq, double scm,
-                                             double scp, bool has_m, bool has_p) {
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double lq = log2_fast(xq) * scq;
-    const double lm = has_m ? log2_fast(xm) * scm : inf;
-    const double lp = has_p ? log2_fast(xp) * scp : inf;
+static __device__ __noinline__ int choose_ratio_f64(real xq, real xm, real xp, real scq, real scm,
+                                             real scp, bool has_m, bool has_p) {
+    const real inf = __longlong_as_double(0x7ff0000000000000LL);
+    const real lq = log2_fast(xq) * scq;
+    const real lm = has_m ? log2_fast(xm) * scm : inf;
+    const real lp = has_p ? log2_fast(xp) * scp : inf;
     return choose_ratio(lq, lm, lp);
 }
 #endif
@@ -423,8 +423,8 @@ struct Engine {
     Ctl c;
     typename POL::Hot hot;   // yh(j,i): Nordsieck history, column j = h^j y^(j)/j!; tau(1:6);
                              // (thread policy) the Newton matrix -- registers or shared memory
-    double ewt[NLOC];        // stored inverted (M:1359, 1522)
-    double savf[NLOC], acor[NLOC], y[NLOC];
+    real ewt[NLOC];        // stored inverted (M:1359, 1522)
+    real savf[NLOC], acor[NLOC], y[NLOC];
     typename POL::Par par;   // per-system parameters of f / jac, as this thread holds them
     typename POL::AcSav acsav;  // the reference's yh(:,lmax) scratch use (M:2259, 2298)
     typename POL::Tol tol;
@@ -433,7 +433,7 @@ struct Engine {
 
     // ---- small vector helpers --------------------------------------------------
     BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
-        double e[NLOC];
+        real e[NLOC];
 #pragma unroll
         for (int i = 0; i < NLOC; i++) e[i] = POL::ewt_of(i, hot.yh(0, i), tol.rtol(i), tol.atol(i));
         bad = POL::any_le_zero(e);
@@ -442,15 +442,15 @@ struct Engine {
     }
 
 #if !BVODE_STRICT
-    BV_DEV double msq_y0() {
-        double y0v[NLOC];
+    BV_DEV real msq_y0() {
+        real y0v[NLOC];
 #pragma unroll
         for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
         return POL::msq(y0v, ewt);
     }
 #endif
-    BV_DEV double norm_y0() {  // dvnorm(yh(:,1), ewt), M:1525
-        double y0v[NLOC];
+    BV_DEV real norm_y0() {  // dvnorm(yh(:,1), ewt), M:1525
+        real y0v[NLOC];
 #pragma unroll
         for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
         return POL::norm(y0v, ewt);
@@ -479,8 +479,8 @@ struct Engine {
     // label 300, M:2131-2139.  Runs on every attempt: lanes that enter at label 400 pass
     // eta = 1, which changes nothing (x * 1.0 == x and h == hscal there), so the warp does
     // not split on "was h changed?".
-    BV_DEV void rescale(double eta) {
-        double r = 1.0;
+    BV_DEV void rescale(real eta) {
+        real r = BV_R(1.0);
 #pragma unroll
         for (int j = 2; j <= kLmax; j++) {
             r = r * eta;
@@ -492,7 +492,7 @@ struct Engine {
         c.rc = c.rc * eta;
     }
     // column `col` (1-based) of yh selected at run time
-    BV_DEV void get_col(int col, double (&out)[NLOC]) {
+    BV_DEV void get_col(int col, real (&out)[NLOC]) {
 #pragma unroll
         for (int i = 0; i < NLOC; i++) out[i] = hot.yh(0, i);
 #pragma unroll
@@ -515,14 +515,18 @@ struct Engine {
     //    by re-evaluating it (o.jreset, set by the host when maxord changed).
     BV_DEV void restart_istate3(bool first_comp) {
         c.jstart = -1;
-        xcol_quirk = false;
+        xcol_mode = 0;
         if (c.nq > o.maxord) {
+            // What dvjust(-1) will find in yh(:, maxord + 2) (case maxord = nq - 1, M:2060-2068) is decided by the
+            // reference's work-array layout: the segments after yh start at lwm = lyh + (maxord+1)*nyh, i.e. ON that
+            // column.  miter > 0: wm(1) = sqrt(uround) lands on its first component (M:1386); miter = 0: lenwm = 0,
+            // so ewt itself (refreshed before the step, M:1516-1523) overlays the whole column.
             if (GENERAL_STASH && o.stash && o.maxord + 2 > kLmax) {
                 // the method family changed (Adams -> BDF): yh(:, maxord + 2) of the old, wider array came along
-                // in the acor slot (state_convert); dvjust(-1) below reads it from savf
+                // in the acor slot (state_convert); dvjust(-1) reads it from savf
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) savf[i] = acor[i];
-                xcol_quirk = (MITER > 0) && first_comp;
+                if (MITER > 0 && first_comp) xcol_mode = 1;
             } else {
                 get_col(o.maxord + 2, savf);
                 if (MITER > 0 && first_comp) {
@@ -532,19 +536,32 @@ struct Engine {
                     }
                 }
             }
+            if (MITER == 0) xcol_mode = 2;
         }
         if (o.jreset) hot.si(SI_NSLJ) = hot.si(SI_NST) - 51;  // forces jok = -1 (msbj = 50)
+        // The acor copy of a pending order increase is parked in yh(:, lmax) (M:2259, 2298); with another lmax the
+        // reference's dvjust(+1) / order test read yh(:, lmax_new) -- a Nordsieck column (zero above the order)
+        // -- until the copy is saved again.  Mirrored for a column that exists in this array.
+        if (o.lmaxchg && o.maxord + 1 <= kLmax) {
+#pragma unroll
+            for (int j = 1; j <= kLmax; j++) {
+                if (j == o.maxord + 1) {
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) POL::acsav_set(*this, i, hot.yh(j - 1, i));
+                }
+            }
+        }
     }
     static constexpr bool GENERAL_STASH = (METH == 2);  // only a BDF kernel can be entered from a wider array
-    bool xcol_quirk = false;  // M:1386 wrote sqrt(uround) onto component 1 of that column (see above)
+    int xcol_mode = 0;  // until the restart's dvjust(-1) has run: 1 = component 1 of that column is sqrt(uround), 2 = the column is ewt
 
     // dvjust, M:2568-2694 (BDF), both directions in one pass over yh.
     //   down: yh(:,j) -= yh(:,L)*el(j), j = 3..nq   (nothing if nq == 2, M:2581); the freed
     //         column L is zeroed to keep the zero-column invariant.
     //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
     BV_DEV void order_change(bool up) {
-        double el[kLmax + 1];
-        double t1 = 0.0;
+        real el[kLmax + 1];
+        real t1 = BV_R(0.0);
         if constexpr (METH == 2) {
             if (!up && c.nq > kMaxOrdBdf) dvjust_coeffs_bdf_down_wide(c, hot, el);  // order 6, from an Adams history
             else t1 = dvjust_coeffs_bdf(c, hot, up, el);
@@ -553,22 +570,26 @@ struct Engine {
             // zero-column invariant already guarantees; lowering it needs el(3:nq)
             if (up) {
 #pragma unroll
-                for (int j = 0; j <= kLmax; j++) el[j] = 0.0;
+                for (int j = 0; j <= kLmax; j++) el[j] = BV_R(0.0);
             } else {
                 dvjust_coeffs_adams_down(c, hot, el);
             }
         }
-        double col[NLOC];
+        real col[NLOC];
         if (up) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * POL::acsav_get(*this, i) : 0.0;
+            for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * POL::acsav_get(*this, i) : BV_R(0.0);
         } else {
             if (GENERAL_STASH && c.L > kLmax) {  // right after an Adams -> BDF restart at order 6 (see restart_istate3)
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) col[i] = savf[i];
-                if (xcol_quirk) col[0] = sqrt(kUround);
+                if (xcol_mode == 1) col[0] = sqrt(kUround);
             } else {
                 get_col(c.L, col);
+            }
+            if (xcol_mode == 2) {  // miter = 0 at an istate = 3 restart: the column is overlaid by ewt
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) col[i] = ewt[i];
             }
 #pragma unroll
             for (int i = 0; i < NLOC; i++) col[i] = -col[i];
@@ -583,18 +604,18 @@ struct Engine {
             }
             if (j == jnew) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = up ? col[i] : 0.0;
+                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = up ? col[i] : BV_R(0.0);
             }
         }
     }
 
     // ---- dvindy, k = 0 (M:1905-1952).  iflag as in the reference. ----------------
-    BV_DEV int dvindy0(double t, double (&dky)[NLOC]) {
-        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
-        const double tp = c.tn - hot.sd(SD_HU) - tfuzz;
-        const double tn1 = c.tn + tfuzz;
-        if ((t - tp) * (t - tn1) > 0.0) return -2;
-        const double s = qdiv(t - c.tn, c.h);
+    BV_DEV int dvindy0(real t, real (&dky)[NLOC]) {
+        const real tfuzz = BV_R(100.0) * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
+        const real tp = c.tn - hot.sd(SD_HU) - tfuzz;
+        const real tn1 = c.tn + tfuzz;
+        if ((t - tp) * (t - tn1) > BV_R(0.0)) return -2;
+        const real s = qdiv(t - c.tn, c.h);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) dky[i] = hot.yh(kLmax - 1, i);
 #pragma unroll
@@ -606,21 +627,21 @@ struct Engine {
     }
 
     // ---- dvindy for any k (M:1905-1957), from the current state --------------------------
-    BV_DEV int dvindy_k(double t, int k, double (&dky)[NLOC]) {
+    BV_DEV int dvindy_k(real t, int k, real (&dky)[NLOC]) {
         const int nq = c.nq, L = nq + 1;
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) dky[i] = 0.0;
+        for (int i = 0; i < NLOC; i++) dky[i] = BV_R(0.0);
         if (k < 0 || k > nq) return -1;
-        const double tfuzz = 100.0 * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
-        const double tp = c.tn - hot.sd(SD_HU) - tfuzz;
-        const double tn1 = c.tn + tfuzz;
-        if ((t - tp) * (t - tn1) > 0.0) return -2;
-        const double s = (t - c.tn) / c.h;
+        const real tfuzz = BV_R(100.0) * kUround * dsign(fabs(c.tn) + fabs(hot.sd(SD_HU)), hot.sd(SD_HU));
+        const real tp = c.tn - hot.sd(SD_HU) - tfuzz;
+        const real tn1 = c.tn + tfuzz;
+        if ((t - tp) * (t - tn1) > BV_R(0.0)) return -2;
+        const real s = (t - c.tn) / c.h;
         int ic = 1;
         if (k != 0)
             for (int jj = L - k; jj <= nq; jj++) ic = ic * jj;
-        double cc = (double)ic;
-        double col[NLOC];
+        real cc = (real)ic;
+        real col[NLOC];
         get_col(L, col);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) dky[i] = cc * col[i];
@@ -631,14 +652,14 @@ struct Engine {
                 ic = 1;
                 if (k != 0)
                     for (int jj = jp1 - k; jj <= j; jj++) ic = ic * jj;
-                cc = (double)ic;
+                cc = (real)ic;
                 get_col(jp1, col);
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) dky[i] = cc * col[i] + s * dky[i];
             }
         }
         if (k != 0) {
-            const double r = powi(c.h, -k);
+            const real r = powi(c.h, -k);
 #pragma unroll
             for (int i = 0; i < NLOC; i++) dky[i] = r * dky[i];
         }
@@ -646,44 +667,44 @@ struct Engine {
     }
 
     // ---- dvhin (M:1738-1851).  y0 = yh[0], ydot = yh[1]; scratch y, acor. ---------
-    BV_DEV int dvhin(double t0, double tout, double &h0, int &niter) {
+    BV_DEV int dvhin(real t0, real tout, real &h0, int &niter) {
         niter = 0;
-        const double tdist = fabs(tout - t0);
-        const double tround = kUround * dmax2(fabs(t0), fabs(tout));
-        if (tdist < 2.0 * tround) return -1;
-        const double hlb = 100.0 * tround;
-        double hub = 0.1 * tdist;
+        const real tdist = fabs(tout - t0);
+        const real tround = kUround * dmax2(fabs(t0), fabs(tout));
+        if (tdist < BV_R(2.0) * tround) return -1;
+        const real hlb = BV_R(100.0) * tround;
+        real hub = BV_R(0.1) * tdist;
         {
-            double y0v[NLOC], ydv[NLOC];
+            real y0v[NLOC], ydv[NLOC];
 #pragma unroll
             for (int i = 0; i < NLOC; i++) { y0v[i] = hot.yh(0, i); ydv[i] = hot.yh(1, i); }
             hub = POL::hin_upper_bound(hub, y0v, ydv, tol);
         }
         int iter = 0;
-        double hg = sqrt(hlb * hub);
+        real hg = sqrt(hlb * hub);
         if (hub < hlb) {
             h0 = hg;
         } else {
-            double hnew = hg;
+            real hnew = hg;
             bool more = true;
 #pragma unroll 1
             while (more) {
-                const double h = dsign(hg, tout - t0);
-                const double t1 = t0 + h;
+                const real h = dsign(hg, tout - t0);
+                const real t1 = t0 + h;
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + h * hot.yh(1, i);
                 POL::f(t1, y, acor, par);
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) acor[i] = (acor[i] - hot.yh(1, i)) / h;
-                const double yddnrm = POL::norm(acor, ewt);
-                if (yddnrm * hub * hub > 2.0) hnew = sqrt(2.0 / yddnrm);
+                const real yddnrm = POL::norm(acor, ewt);
+                if (yddnrm * hub * hub > BV_R(2.0)) hnew = sqrt(BV_R(2.0) / yddnrm);
                 else hnew = sqrt(hg * hub);
                 iter = iter + 1;
                 more = false;
                 if (iter < 4) {
-                    const double hrat = hnew / hg;
-                    if ((hrat <= 0.5) || (hrat >= 2.0)) {
-                        if ((iter >= 2) && (hnew > 2.0 * hg)) {
+                    const real hrat = hnew / hg;
+                    if ((hrat <= BV_R(0.5)) || (hrat >= BV_R(2.0))) {
+                        if ((iter >= 2) && (hnew > BV_R(2.0) * hg)) {
                             hnew = hg;
                         } else {
                             hg = hnew;
@@ -692,7 +713,7 @@ struct Engine {
                     }
                 }
             }
-            h0 = hnew * 0.5;
+            h0 = hnew * BV_R(0.5);
             if (h0 < hlb) h0 = hlb;
             if (h0 > hub) h0 = hub;
         }
@@ -703,29 +724,29 @@ struct Engine {
 
     // ---- block C: first call for the problem (M:1312-1381) -----------------------
     // y[] holds the initial values on entry.  Returns 0 or a negative istate.
-    BV_DEV int init_problem(double t, double tout) {
+    BV_DEV int init_problem(real t, real tout) {
         c.tn = t;
         c.jstart = 0;
         hot.si(SI_NHNIL) = 0;
         hot.si(SI_NST) = hot.si(SI_NJE) = hot.si(SI_NNI) = hot.si(SI_NCFN) = hot.si(SI_NETF) = hot.si(SI_NLU) = 0;
         hot.si(SI_NSLJ) = 0;
-        hot.sd(SD_HU) = 0.0;
+        hot.sd(SD_HU) = BV_R(0.0);
         hot.si(SI_NQU) = 0;
         hot.si(SI_INIT) = 0;
         c.icf = 0; c.ipup = 0; c.jcur = 0; c.kflag = 0; hot.si(SI_NSLP) = 0; c.newh = 0; c.newq = 0;
-        c.eta = 0.0; hot.sd(SD_HNEW) = 0.0; hot.sd(SD_CONP) = 0.0; hot.sd(SD_CRATE) = 0.0; c.drc = 0.0; c.acnrm = 0.0;
-        c.rl1 = 0.0; hot.sd(SD_ETAMAX) = 0.0; c.hscal = 0.0; c.rc = 0.0; c.prl1 = 0.0;
+        c.eta = BV_R(0.0); hot.sd(SD_HNEW) = BV_R(0.0); hot.sd(SD_CONP) = BV_R(0.0); hot.sd(SD_CRATE) = BV_R(0.0); c.drc = BV_R(0.0); c.acnrm = BV_R(0.0);
+        c.rl1 = BV_R(0.0); hot.sd(SD_ETAMAX) = BV_R(0.0); c.hscal = BV_R(0.0); c.rc = BV_R(0.0); c.prl1 = BV_R(0.0);
 #pragma unroll
-        for (int j = 1; j <= kLmax; j++) { hot.tau(j) = 0.0; hot.el(j) = 0.0; }
+        for (int j = 1; j <= kLmax; j++) { hot.tau(j) = BV_R(0.0); hot.el(j) = BV_R(0.0); }
 #pragma unroll
-        for (int j = 1; j <= 5; j++) hot.tq(j) = 0.0;
+        for (int j = 1; j <= 5; j++) hot.tq(j) = BV_R(0.0);
 #pragma unroll
         for (int j = 0; j < kLmax; j++) {
 #pragma unroll
-            for (int i = 0; i < NLOC; i++) hot.yh(j, i) = 0.0;
+            for (int i = 0; i < NLOC; i++) hot.yh(j, i) = BV_R(0.0);
         }
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) { POL::acsav_set(*this, i, 0.0); acor[i] = 0.0; savf[i] = 0.0; }
+        for (int i = 0; i < NLOC; i++) { POL::acsav_set(*this, i, BV_R(0.0)); acor[i] = BV_R(0.0); savf[i] = BV_R(0.0); }
         POL::lin_init(*this);
         POL::f(t, y, savf, par);
 #pragma unroll
@@ -735,24 +756,24 @@ struct Engine {
         for (int i = 0; i < NLOC; i++) hot.yh(0, i) = y[i];
         c.nq = 1;
         c.L = 2;
-        c.h = 1.0;
+        c.h = BV_R(1.0);
         bool bad;
         dewset_invert(bad);
         if (bad) return IST_ILLEGAL;  // message 21
-        double h0 = o.h0;
-        if ((tout - t) * h0 < 0.0) return IST_ILLEGAL;  // message 14, M:1214
+        real h0 = o.h0;
+        if ((tout - t) * h0 < BV_R(0.0)) return IST_ILLEGAL;  // message 14, M:1214
         if (o.itask == 4 || o.itask == 5) {  // M:1314-1323
-            if ((o.tcrit - tout) * (tout - t) < 0.0) return IST_ILLEGAL;  // message 25
-            if (h0 != 0.0 && (t + h0 - o.tcrit) * h0 > 0.0) h0 = o.tcrit - t;
+            if ((o.tcrit - tout) * (tout - t) < BV_R(0.0)) return IST_ILLEGAL;  // message 25
+            if (h0 != BV_R(0.0) && (t + h0 - o.tcrit) * h0 > BV_R(0.0)) h0 = o.tcrit - t;
         }
-        if (h0 == 0.0) {
+        if (h0 == BV_R(0.0)) {
             int niter;
             const int ier = dvhin(t, tout, h0, niter);
             hot.si(SI_NFE) = hot.si(SI_NFE) + niter;
             if (ier != 0) return IST_ILLEGAL;  // message 22
         }
-        const double rh = fabs(h0) * o.hmax_inv;
-        if (rh > 1.0) h0 = h0 / rh;
+        const real rh = fabs(h0) * o.hmax_inv;
+        if (rh > BV_R(1.0)) h0 = h0 / rh;
         c.h = h0;
 #pragma unroll
         for (int i = 0; i < NLOC; i++) hot.yh(1, i) = h0 * hot.yh(1, i);
@@ -763,17 +784,17 @@ struct Engine {
     // Single-exit loops only: a `return` or `break` out of a divergent region moves the
     // warp's reconvergence point to the end of the function, and the 32 systems of a warp
     // would then run one after the other for the rest of the integration.
-    BV_DEV int dvnlsd(int nflag, double rtq4) {
+    BV_DEV int dvnlsd(int nflag, real rtq4) {
         constexpr int maxcor = 3, msbp = 20;
-        constexpr double ccmax = 0.3, crdown = 0.3, rdiv = 2.0;
+        constexpr real ccmax = BV_R(0.3), crdown = BV_R(0.3), rdiv = BV_R(2.0);
         if (c.jstart == 0) hot.si(SI_NSLP) = 0;
         if (nflag == 0) c.icf = 0;
         if (nflag == -2) c.ipup = MITER;
         if (c.jstart == 0 || c.jstart == -1) c.ipup = MITER;  // M:2748
         if constexpr (MITER == 0) {
-            hot.sd(SD_CRATE) = 1.0;  // M:2751
+            hot.sd(SD_CRATE) = BV_R(1.0);  // M:2751
         } else {
-            c.drc = fabs(c.rc - 1.0);
+            c.drc = fabs(c.rc - BV_R(1.0));
             if (c.drc > ccmax || hot.si(SI_NST) >= hot.si(SI_NSLP) + msbp) c.ipup = MITER;
         }
         (void)rtq4;
@@ -782,7 +803,7 @@ struct Engine {
 #pragma unroll 1
         while (result == 1) {
             int m = 0;
-            double delp = 0.0, del = 0.0;
+            real delp = BV_R(0.0), del = BV_R(0.0);
             bool converged = false, singular = false;
 #pragma unroll
             for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
@@ -793,21 +814,21 @@ struct Engine {
                     int ierpj;
                     POL::jac_setup(*this, ierpj);
                     c.ipup = 0;
-                    c.rc = 1.0;
-                    c.drc = 0.0;
-                    hot.sd(SD_CRATE) = 1.0;
+                    c.rc = BV_R(1.0);
+                    c.drc = BV_R(0.0);
+                    hot.sd(SD_CRATE) = BV_R(1.0);
                     hot.si(SI_NSLP) = hot.si(SI_NST);
                     singular = (ierpj != 0);
                 }
             }
             if (!singular) {
 #pragma unroll
-                for (int i = 0; i < NLOC; i++) acor[i] = 0.0;
+                for (int i = 0; i < NLOC; i++) acor[i] = BV_R(0.0);
                 // 2/(1+rc), M:2813: rc is fixed during the iterations of one pass
                 // 2/(1+rc), BDF only (M:2813): rc is fixed during the iterations of one pass
-                const bool do_scale = (METH == 2) && (c.rc != 1.0);
-                const double cscale = (METH == 2) ? qdiv(2.0, 1.0 + c.rc) : 1.0;
-                const double rl1h = c.rl1 * c.h;
+                const bool do_scale = (METH == 2) && (c.rc != BV_R(1.0));
+                const real cscale = (METH == 2) ? qdiv(BV_R(2.0), BV_R(1.0) + c.rc) : BV_R(1.0);
+                const real rl1h = c.rl1 * c.h;
                 bool iterate = true;
 #pragma unroll 1
                 while (iterate) {
@@ -858,15 +879,15 @@ struct Engine {
                     }
 #if BVODE_STRICT
                     if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), qdiv(del, delp));
-                    const double dcon = qdiv(del * dmin2(1.0, hot.sd(SD_CRATE)), hot.tq(4));
+                    const real dcon = qdiv(del * dmin2(BV_R(1.0), hot.sd(SD_CRATE)), hot.tq(4));
                     const bool diverging = !(m + 1 < 2 || del <= rdiv * delp);
 #else
                     if (m != 0) hot.sd(SD_CRATE) = dmax2(crdown * hot.sd(SD_CRATE), sqrt(qdiv(del, delp)));
-                    const double cfac = dmin2(1.0, hot.sd(SD_CRATE)) * rtq4;
-                    const double dcon = del * (cfac * cfac);
+                    const real cfac = dmin2(BV_R(1.0), hot.sd(SD_CRATE)) * rtq4;
+                    const real dcon = del * (cfac * cfac);
                     const bool diverging = !(m + 1 < 2 || del <= (rdiv * rdiv) * delp);
 #endif
-                    if (dcon <= 1.0) {
+                    if (dcon <= BV_R(1.0)) {
                         converged = true;
                         iterate = false;
                     } else {
@@ -903,8 +924,8 @@ struct Engine {
     }
 
     // eta = 1 / (x**(1/k) + addon), M:2201, 2275, 2282, 2292
-    BV_DEV static double eta_of(double x, int k) {
-        return qrcp(rpow(x, recip_int(k)) + 1.0e-6);
+    BV_DEV static real eta_of(real x, int k) {
+        return qrcp(rpow(x, recip_int(k)) + BV_R(1.0e-6));
     }
 
     // ---- the step loop: driver blocks D/E/F around dvstep (M:1399-1623, 1975-2377) --
@@ -938,14 +959,14 @@ struct Engine {
 #define BVODE_REFILL_GROUP 4
 #endif
         [[maybe_unused]] constexpr int kRefillGroup = BVODE_REFILL_GROUP;
-        [[maybe_unused]] constexpr double addon = 1.0e-6;
-        constexpr double bias1 = 6.0, bias2 = 6.0, bias3 = 10.0, etacf = 0.25,
-                         etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
-                         etamx3 = 10.0, onepsm = 1.00001;
+        [[maybe_unused]] constexpr real addon = BV_R(1.0e-6);
+        constexpr real bias1 = BV_R(6.0), bias2 = BV_R(6.0), bias3 = BV_R(10.0), etacf = BV_R(0.25),
+                         etamin = BV_R(0.1), etamxf = BV_R(0.2), etamx1 = BV_R(1.0e4), etamx2 = BV_R(10.0),
+                         etamx3 = BV_R(10.0), onepsm = BV_R(1.00001);
 #if BVODE_STRICT
-        constexpr double thresh = 1.5;
+        constexpr real thresh = BV_R(1.5);
 #else
-        const lg_t l2thr = (lg_t)-0.5849646647653407;  // log2(1/thresh - addon), thresh = 1.5
+        const lg_t l2thr = (lg_t)-BV_R(0.5849646647653407);  // log2(1/thresh - addon), thresh = 1.5
 #endif
         enum { E_NEWSTEP = 0, E_RESCALE = 1, E_PREDICT = 2, E_DOWN_RESCALE = 3 };
 
@@ -955,82 +976,82 @@ struct Engine {
                          // Non-zero with have == false: nothing loaded yet.
         bool have = false, alive = true;
         int kout = 0;
-        double tout = 0.0;
+        real tout = BV_R(0.0);
         // "reached": tout lies inside the step just taken -> interpolate instead of stepping
         bool reached = false;
         // ---- GENERAL: what the current call does next (blocks D and F for every itask)
         enum { ACT_STEP = 0, ACT_RET_INTERP = 1, ACT_RET_YH = 2, ACT_ILLEGAL = 3 };
         [[maybe_unused]] int act = ACT_STEP, kuth = 0;
         [[maybe_unused]] bool ihit = false;
-        [[maybe_unused]] double t_emit = tout;
+        [[maybe_unused]] real t_emit = tout;
         const int itask = GENERAL ? o.itask : 1;
         // tcrit handling shared by blocks D and F (M:1469-1483, 1600-1612): true = return now
         auto tcrit_logic = [&]() -> bool {
-            const double hmx = fabs(c.tn) + fabs(c.h);
-            ihit = fabs(c.tn - o.tcrit) <= 100.0 * kUround * hmx;
+            const real hmx = fabs(c.tn) + fabs(c.h);
+            ihit = fabs(c.tn - o.tcrit) <= BV_R(100.0) * kUround * hmx;
             if (ihit) return true;
-            const double tnext = c.tn + hot.sd(SD_HNEW) * (1.0 + 4.0 * kUround);
-            if ((tnext - o.tcrit) * c.h > 0.0) {
-                c.h = (o.tcrit - c.tn) * (1.0 - 4.0 * kUround);
+            const real tnext = c.tn + hot.sd(SD_HNEW) * (BV_R(1.0) + BV_R(4.0) * kUround);
+            if ((tnext - o.tcrit) * c.h > BV_R(0.0)) {
+                c.h = (o.tcrit - c.tn) * (BV_R(1.0) - BV_R(4.0) * kUround);
                 kuth = 1;
             }
             return false;
         };
         // block D, M:1399-1483: entry of a continuation call
-        auto block_d = [&](double to) -> int {
+        auto block_d = [&](real to) -> int {
             nslast = hot.si(SI_NST);
             kuth = 0;
             ihit = false;
             if (itask == 2) return ACT_STEP;
             if (itask == 3) {
-                const double tp = c.tn - hot.sd(SD_HU) * (1.0 + 100.0 * kUround);
-                if ((tp - to) * c.h > 0.0) return ACT_ILLEGAL;  // message 23
-                if ((c.tn - to) * c.h >= 0.0) return ACT_RET_YH;
+                const real tp = c.tn - hot.sd(SD_HU) * (BV_R(1.0) + BV_R(100.0) * kUround);
+                if ((tp - to) * c.h > BV_R(0.0)) return ACT_ILLEGAL;  // message 23
+                if ((c.tn - to) * c.h >= BV_R(0.0)) return ACT_RET_YH;
                 return ACT_STEP;
             }
             if (itask == 4 || itask == 5) {
-                if ((c.tn - o.tcrit) * c.h > 0.0) return ACT_ILLEGAL;  // message 24
+                if ((c.tn - o.tcrit) * c.h > BV_R(0.0)) return ACT_ILLEGAL;  // message 24
                 if (itask == 4) {
-                    if ((o.tcrit - to) * c.h < 0.0) return ACT_ILLEGAL;  // message 25
-                    if ((c.tn - to) * c.h >= 0.0) {
-                        double dky[NLOC];
+                    if ((o.tcrit - to) * c.h < BV_R(0.0)) return ACT_ILLEGAL;  // message 25
+                    if ((c.tn - to) * c.h >= BV_R(0.0)) {
+                        real dky[NLOC];
                         if (dvindy0(to, dky) != 0) return ACT_ILLEGAL;  // message 27
                         return ACT_RET_INTERP;
                     }
                 }
                 return tcrit_logic() ? ACT_RET_YH : ACT_STEP;
             }
-            if ((c.tn - to) * c.h < 0.0) return ACT_STEP;
-            double dky[NLOC];
+            if ((c.tn - to) * c.h < BV_R(0.0)) return ACT_STEP;
+            real dky[NLOC];
             if (dvindy0(to, dky) != 0) return ACT_ILLEGAL;  // message 27
             return ACT_RET_INTERP;
         };
         // block F, M:1586-1623: after a successful step
-        auto block_f = [&](double to) -> int {
+        auto block_f = [&](real to) -> int {
             kuth = 0;
             ihit = false;
             if (itask == 2) return ACT_RET_YH;
-            if (itask == 3) return ((c.tn - to) * c.h < 0.0) ? ACT_STEP : ACT_RET_YH;
+            if (itask == 3) return ((c.tn - to) * c.h < BV_R(0.0)) ? ACT_STEP : ACT_RET_YH;
             if (itask == 4) {
-                if ((c.tn - to) * c.h < 0.0) return tcrit_logic() ? ACT_RET_YH : ACT_STEP;
+                if ((c.tn - to) * c.h < BV_R(0.0)) return tcrit_logic() ? ACT_RET_YH : ACT_STEP;
                 return ACT_RET_INTERP;
             }
             if (itask == 5) {
-                const double hmx = fabs(c.tn) + fabs(c.h);
-                ihit = fabs(c.tn - o.tcrit) <= 100.0 * kUround * hmx;
+                const real hmx = fabs(c.tn) + fabs(c.h);
+                ihit = fabs(c.tn - o.tcrit) <= BV_R(100.0) * kUround * hmx;
                 return ACT_RET_YH;
             }
-            return ((c.tn - to) * c.h < 0.0) ? ACT_STEP : ACT_RET_INTERP;
+            return ((c.tn - to) * c.h < BV_R(0.0)) ? ACT_STEP : ACT_RET_INTERP;
         };
         int entry = E_NEWSTEP;
         bool skip_ewt = false;
-        double told = 0.0;
+        real told = BV_R(0.0);
         int ncf = 0, nflag = 0;
 
         auto handover = [&]() {
             // ---- this lane's system is finished (or none is loaded yet): hand it over, get the next
             int ist_ret = 0;
-            double t_ret = 0.0;
+            real t_ret = BV_R(0.0);
             if (have) {
                 if (istate == IST_OK) {
                     t_ret = GENERAL ? t_emit : tout;  // y was set by the last emit
@@ -1058,10 +1079,10 @@ struct Engine {
                 kout = 0;
                 tout = tout_of(0);
                 nslast = hot.si(SI_NST);
-                reached = !GENERAL && !first && !((c.tn - tout) * c.h < 0.0);
+                reached = !GENERAL && !first && !((c.tn - tout) * c.h < BV_R(0.0));
                 if (reached) {
                     // block D on a continuation call checks dvindy's flag (message 27, M:1459-1464)
-                    double dky[NLOC];
+                    real dky[NLOC];
                     if (dvindy0(tout, dky) != 0) {
                         reached = false;
                         istate = IST_ILLEGAL_ENTRY;
@@ -1101,7 +1122,7 @@ struct Engine {
                 if (kout < nout) {
                     tout = tout_of(kout);
                     nslast = hot.si(SI_NST);
-                    reached = !((c.tn - tout) * c.h < 0.0);
+                    reached = !((c.tn - tout) * c.h < BV_R(0.0));
                 } else {
                     reached = false;
                     istate = IST_OK;
@@ -1149,11 +1170,11 @@ struct Engine {
                     skip_ewt = false;
                     if (istate == 0) {
 #if BVODE_STRICT
-                        const double tolsf = kUround * norm_y0();
-                        const bool too_much = (tolsf > 1.0);
+                        const real tolsf = kUround * norm_y0();
+                        const bool too_much = (tolsf > BV_R(1.0));
 #else
                         // tolsf > 1  <=>  uround^2 * mean-square > 1 (no sqrt on the main path)
-                        const bool too_much = ((kUround * kUround) * msq_y0() > 1.0);
+                        const bool too_much = ((kUround * kUround) * msq_y0() > BV_R(1.0));
 #endif
                         if (too_much) istate = (hot.si(SI_NST) == 0) ? IST_ILLEGAL : IST_TOLSF;
                     }
@@ -1169,8 +1190,8 @@ struct Engine {
                             c.nq = 1;
                             c.L = 2;
                             hot.tau(1) = c.h;
-                            c.prl1 = 1.0;
-                            c.rc = 0.0;
+                            c.prl1 = BV_R(1.0);
+                            c.rc = BV_R(0.0);
                             hot.sd(SD_ETAMAX) = etamx1;
                             c.nqwait = 2;
                             c.hscal = c.h;
@@ -1182,22 +1203,22 @@ struct Engine {
                                     // yh(:, maxord + 2) when nq > maxord, M:1385)
                                     const int maxord = o.maxord;
                                     if (c.newq > maxord) {
-                                        const double flotl = (double)lmax;
+                                        const real flotl = (real)lmax;
                                         if (maxord < c.nq - 1 || (maxord == c.nq - 1 && c.newq == c.nq)) {
-                                            const double ddn = POL::norm(savf, ewt) / hot.tq(1);
-                                            c.eta = 1.0 / (rpow(bias1 * ddn, 1.0 / flotl) + addon);
+                                            const real ddn = POL::norm(savf, ewt) / hot.tq(1);
+                                            c.eta = BV_R(1.0) / (rpow(bias1 * ddn, BV_R(1.0) / flotl) + addon);
                                         }
 #if BVODE_STRICT
                                         if (maxord == c.nq && c.newq == c.nq + 1) c.eta = hot.sd(SD_ETAQ);
                                         if (maxord == c.nq - 1 && c.newq == c.nq + 1) c.eta = hot.sd(SD_ETAQM1);
 #else
                                         if (maxord == c.nq && c.newq == c.nq + 1)
-                                            c.eta = 1.0 / (rpow(hot.sd(SD_ETAQ), 0.5 * recip_int(c.L)) + addon);
+                                            c.eta = BV_R(1.0) / (rpow(hot.sd(SD_ETAQ), BV_R(0.5) * recip_int(c.L)) + addon);
                                         if (maxord == c.nq - 1 && c.newq == c.nq + 1)
-                                            c.eta = 1.0 / (rpow(hot.sd(SD_ETAQM1), 0.5 * recip_int(c.L - 1)) + addon);
+                                            c.eta = BV_R(1.0) / (rpow(hot.sd(SD_ETAQM1), BV_R(0.5) * recip_int(c.L - 1)) + addon);
 #endif
                                         if (maxord == c.nq - 1) order_change(false);  // dvjust(-1)
-                                        c.eta = dmin2(c.eta, 1.0);
+                                        c.eta = dmin2(c.eta, BV_R(1.0));
                                         c.nq = maxord;
                                         c.L = lmax;
                                         // columns above the new order: zero-column invariant
@@ -1205,14 +1226,15 @@ struct Engine {
                                         for (int j = 2; j <= kLmax; j++) {
                                             if (j > lmax) {
 #pragma unroll
-                                                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = 0.0;
+                                                for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = BV_R(0.0);
                                             }
                                         }
                                         c.newq = c.nq;  // (the reference jumps to label 300 here)
                                     }
+                                    xcol_mode = 0;
                                     if (kuth == 1) c.eta = dmin2(c.eta, fabs(c.h / c.hscal));
                                     if (kuth == 0) c.eta = dmax2(c.eta, o.hmin / fabs(c.hscal));
-                                    c.eta = c.eta / dmax2(1.0, fabs(c.hscal) * o.hmax_inv * c.eta);
+                                    c.eta = c.eta / dmax2(BV_R(1.0), fabs(c.hscal) * o.hmax_inv * c.eta);
                                     c.newh = 1;
                                     c.nqwait = c.L;
                                 } else if (kuth == 1) {  // h was cut to land on tcrit, M:2100-2103
@@ -1242,7 +1264,7 @@ struct Engine {
                     c.L = c.nq + 1;
                     c.nqwait = c.L;
                 }
-                rescale(entry == E_RESCALE ? c.eta : 1.0);
+                rescale(entry == E_RESCALE ? c.eta : BV_R(1.0));
 
                 // ---- label 400: predict, coefficients (M:2147-2158)
                 c.tn = c.tn + c.h;
@@ -1252,21 +1274,21 @@ struct Engine {
                 c.rc = c.rc * qdiv(c.rl1, c.prl1);
                 c.prl1 = c.rl1;
 #if BVODE_STRICT
-                const double rtq2 = 0.0, rtq4 = 0.0;
+                const real rtq2 = BV_R(0.0), rtq4 = BV_R(0.0);
                 (void)rtq2;
 #else
-                const double rtq2 = qrcp(hot.tq(2));
-                const double rtq4 = 10.0 * rtq2;  // tq(4) = 0.1 * tq(2), M:2559
+                const real rtq2 = qrcp(hot.tq(2));
+                const real rtq4 = BV_R(10.0) * rtq2;  // tq(4) = 0.1 * tq(2), M:2559
 #endif
                 nflag = dvnlsd(nflag, rtq4);
 
                 const bool conv = (nflag == 0);
 #if BVODE_STRICT
-                const double dsm = conv ? qdiv(c.acnrm, hot.tq(2)) : 0.0;
+                const real dsm = conv ? qdiv(c.acnrm, hot.tq(2)) : BV_R(0.0);
 #else
-                const double dsm = conv ? c.acnrm * (rtq2 * rtq2) : 0.0;  // dsm^2
+                const real dsm = conv ? c.acnrm * (rtq2 * rtq2) : BV_R(0.0);  // dsm^2
 #endif
-                const bool accept = conv && !(dsm > 1.0);
+                const bool accept = conv && !(dsm > BV_R(1.0));
                 if (!accept) {  // both kinds of failure undo the prediction (M:2180-2187, 2341-2348)
                     c.tn = told;
                     retract();
@@ -1280,16 +1302,16 @@ struct Engine {
                 // per attempt serves whichever lane needs a ratio: the failed error test, or
                 // the accepted step whose ratio reaches `thresh` (phase B below).
 #if BVODE_STRICT
-                const double etaq = conv ? eta_of(bias2 * dsm, c.L) : 0.0;
+                const real etaq = conv ? eta_of(bias2 * dsm, c.L) : BV_R(0.0);
 #else
-                const double xq = (bias2 * bias2) * dsm;  // dsm holds dsm^2: log2(x)/(2L)
+                const real xq = (bias2 * bias2) * dsm;  // dsm holds dsm^2: log2(x)/(2L)
                 int pend = 0;  // 1: ratio for a failed error test, 2: ratio after an accepted step
                 int wsel = 0;  // winning candidate: 0 current order, 1 order - 1, 2 order + 1
-                double xsel = xq, scsel = 0.5 * recip_int(c.L);
+                real xsel = xq, scsel = BV_R(0.5) * recip_int(c.L);
                 float lwf = 0.0f;
 #endif
                 // hmin/|h| of the failure paths (M:2202, 2221, 2360), one evaluation for all
-                const double hmr = accept ? 0.0 : qdiv(o.hmin, fabs(c.h));
+                const real hmr = accept ? BV_R(0.0) : qdiv(o.hmin, fabs(c.h));
                 if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
                     c.kflag = c.kflag - 1;
@@ -1300,7 +1322,7 @@ struct Engine {
                         c.jstart = 1;
                         istate = IST_ERRTEST;
                     } else {
-                        hot.sd(SD_ETAMAX) = 1.0;
+                        hot.sd(SD_ETAMAX) = BV_R(1.0);
                         if (c.kflag > kfc) {
 #if BVODE_STRICT
                             c.eta = etaq;
@@ -1334,7 +1356,7 @@ struct Engine {
                     // ---- corrector failed to converge (M:2338-2367)
                     ncf = ncf + 1;
                     hot.si(SI_NCFN) = hot.si(SI_NCFN) + 1;
-                    hot.sd(SD_ETAMAX) = 1.0;
+                    hot.sd(SD_ETAMAX) = BV_R(1.0);
                     if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
                         c.kflag = -2;
                         c.jstart = 1;
@@ -1357,7 +1379,7 @@ struct Engine {
                     hot.tau(1) = c.h;
 #pragma unroll
                     for (int j = 1; j <= kLmax; j++) {
-                        const double elj = hot.el(j);
+                        const real elj = hot.el(j);
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = hot.yh(j - 1, i) + elj * acor[i];
                     }
@@ -1367,11 +1389,11 @@ struct Engine {
                         for (int i = 0; i < NLOC; i++) POL::acsav_set(*this, i, acor[i]);
                         hot.sd(SD_CONP) = hot.tq(5);
                     }
-                    if (hot.sd(SD_ETAMAX) != 1.0) {
+                    if (hot.sd(SD_ETAMAX) != BV_R(1.0)) {
                         int newq = c.nq;
                         bool save_acor = false;
 #if BVODE_STRICT
-                        double eta = etaq;
+                        real eta = etaq;
                         hot.sd(SD_ETAQ) = etaq;
 #else
                         pend = 2;
@@ -1380,21 +1402,21 @@ struct Engine {
 #endif
                         if (c.nqwait == 0) {
                             c.nqwait = 2;
-                            double ddn = 0.0, dup = 0.0;
+                            real ddn = BV_R(0.0), dup = BV_R(0.0);
                             if (c.nq != 1) {
-                                double top[NLOC];
+                                real top[NLOC];
                                 get_col(c.L, top);
 #if BVODE_STRICT
                                 ddn = qdiv(POL::norm(top, ewt), hot.tq(1));
 #else
                                 {
-                                    const double r1 = qrcp(hot.tq(1));
+                                    const real r1 = qrcp(hot.tq(1));
                                     ddn = POL::msq(top, ewt) * (r1 * r1);  // ddn^2
                                 }
 #endif
                             }
                             if (c.L != lmax) {
-                                const double cnquot =
+                                const real cnquot =
                                     qdiv(hot.tq(5), hot.sd(SD_CONP)) * powi_small<kLmax>(qdiv(c.h, hot.tau(2)), c.L);
 #pragma unroll
                                 for (int i = 0; i < NLOC; i++)
@@ -1403,14 +1425,14 @@ struct Engine {
                                 dup = qdiv(POL::norm(savf, ewt), hot.tq(3));
 #else
                                 {
-                                    const double r3 = qrcp(hot.tq(3));
+                                    const real r3 = qrcp(hot.tq(3));
                                     dup = POL::msq(savf, ewt) * (r3 * r3);  // dup^2
                                 }
 #endif
                             }
 #if BVODE_STRICT
-                            const double etaqm1 = (c.nq != 1) ? eta_of(bias1 * ddn, c.L - 1) : 0.0;
-                            const double etaqp1 = (c.L != lmax) ? eta_of(bias3 * dup, c.L + 1) : 0.0;
+                            const real etaqm1 = (c.nq != 1) ? eta_of(bias1 * ddn, c.L - 1) : BV_R(0.0);
+                            const real etaqp1 = (c.L != lmax) ? eta_of(bias3 * dup, c.L + 1) : BV_R(0.0);
                             hot.sd(SD_ETAQM1) = etaqm1;
                             if (etaq < etaqp1) {
                                 if (etaqp1 <= etaqm1) {
@@ -1429,8 +1451,8 @@ struct Engine {
                             // eta_a < eta_b  <=>  log2(x_a)/k_a > log2(x_b)/k_b ; an order that is
                             // not available (ratio 0) has log-ratio +infinity
                             const bool has_m = (c.nq != 1), has_p = (c.L != lmax);
-                            const double xm = (bias1 * bias1) * ddn, xp = (bias3 * bias3) * dup;
-                            const double scm = 0.5 * recip_int(c.L - 1), scp = 0.5 * recip_int(c.L + 1);
+                            const real xm = (bias1 * bias1) * ddn, xp = (bias3 * bias3) * dup;
+                            const real scm = BV_R(0.5) * recip_int(c.L - 1), scp = BV_R(0.5) * recip_int(c.L + 1);
                             auto choose = [](float lq_, float lm_, float lp_) -> int {
                                 return choose_ratio(lq_, lm_, lp_);
                             };
@@ -1457,12 +1479,12 @@ struct Engine {
                         if (eta < thresh) {
                             c.newq = c.nq;
                             c.newh = 0;
-                            c.eta = 1.0;
+                            c.eta = BV_R(1.0);
                             hot.sd(SD_HNEW) = c.h;
                         } else {
                             c.newq = newq;
                             c.eta = dmin2(eta, hot.sd(SD_ETAMAX));
-                            c.eta = qdiv(c.eta, dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta));
+                            c.eta = qdiv(c.eta, dmax2(BV_R(1.0), fabs(c.h) * o.hmax_inv * c.eta));
                             c.newh = 1;
                             hot.sd(SD_HNEW) = c.h * c.eta;
                         }
@@ -1474,7 +1496,7 @@ struct Engine {
                         if (c.nqwait < 2) c.nqwait = 2;
                         c.newq = c.nq;
                         c.newh = 0;
-                        c.eta = 1.0;
+                        c.eta = BV_R(1.0);
                         hot.sd(SD_HNEW) = c.h;
                     }
                     // label 500
@@ -1482,9 +1504,9 @@ struct Engine {
                     if (hot.si(SI_NST) <= 10) hot.sd(SD_ETAMAX) = etamx2;
                     {
 #if BVODE_STRICT
-                        const double r = qrcp(hot.tq(2));
+                        const real r = qrcp(hot.tq(2));
 #else
-                        const double r = rtq2;
+                        const real r = rtq2;
 #endif
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) acor[i] = r * acor[i];
@@ -1493,7 +1515,7 @@ struct Engine {
                     // ---- block F, itask = 1 (M:1586-1622)
                     hot.si(SI_INIT) = 1;
                     entry = E_NEWSTEP;
-                    if constexpr (!GENERAL) reached = !((c.tn - tout) * c.h < 0.0);
+                    if constexpr (!GENERAL) reached = !((c.tn - tout) * c.h < BV_R(0.0));
                 }
 #if !BVODE_STRICT
                 // ---- phase B: the one ratio evaluation of this attempt
@@ -1501,23 +1523,23 @@ struct Engine {
                     const float l2thr_f = -0.58496466f;
                     const bool keepf = (lwf > l2thr_f);
                     const bool unsure = (pend == 2) && near_f32(lwf, l2thr_f);
-                    double lsel = 0.0;
+                    real lsel = BV_R(0.0);
                     if (pend == 1 || !keepf || unsure) lsel = log2_fast(xsel) * scsel;
                     const bool keep = (pend == 2) && (unsure ? (lsel > l2thr) : keepf);
                     if (keep) {  // label 450, M:2320-2324
                         c.newq = c.nq;
                         c.newh = 0;
-                        c.eta = 1.0;
+                        c.eta = BV_R(1.0);
                         hot.sd(SD_HNEW) = c.h;
                     } else {
-                        const double eta = qrcp(exp2_fast(lsel) + addon);
+                        const real eta = qrcp(exp2_fast(lsel) + addon);
                         if (pend == 1) {  // M:2201-2204
                             c.eta = dmax2(dmax2(eta, hmr), etamin);
                             if ((c.kflag <= -2) && (c.eta > etamxf)) c.eta = etamxf;
                         } else {  // M:2325-2330; c.eta holds this step's etamax
                             c.eta = dmin2(eta, c.eta);
-                            const double d = dmax2(1.0, fabs(c.h) * o.hmax_inv * c.eta);
-                            if (d != 1.0) c.eta = qdiv(c.eta, d);
+                            const real d = dmax2(BV_R(1.0), fabs(c.h) * o.hmax_inv * c.eta);
+                            if (d != BV_R(1.0)) c.eta = qdiv(c.eta, d);
                             c.newh = 1;
                             hot.sd(SD_HNEW) = c.h * c.eta;
                         }

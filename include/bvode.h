@@ -42,6 +42,16 @@ extern "C" {
 #define BVODE_API
 #endif
 
+/* The working precision of the library: the reference's `wp` (src/dvode_kinds_module.F90:29-31).  libbvode.so
+ * is the REAL64 build; libbvode32.so (compiled with -DBVODE_REAL32) is the REAL32 build of the same sources and
+ * exports the same entry points with every `bvode_real` a float (strict arithmetic, thread-per-system problems).
+ * An application selects one at compile time, like the reference's -DREAL32. */
+#ifdef BVODE_REAL32
+typedef float bvode_real;
+#else
+typedef double bvode_real;
+#endif
+
 typedef struct bvode_solver bvode_solver;
 
 enum {
@@ -91,7 +101,7 @@ BVODE_API const char *bvode_last_error(void);
 
 /* Per-system parameters read by f / jac: params[nsys][npar] (what the Fortran callbacks
  * would reach by host association, e.g. Robertson's three rate constants). */
-BVODE_API int bvode_set_params(bvode_solver *s, const double *params);
+BVODE_API int bvode_set_params(bvode_solver *s, const bvode_real *params);
 
 /* ---- solve == dvode (M:604-605), for the whole batch.  Same argument meaning as the
  * reference.  tout: one value for the batch (tout_per_system = 0) or tout[nsys] (= 1).
@@ -104,9 +114,9 @@ BVODE_API int bvode_set_params(bvode_solver *s, const double *params);
  *          iteration), 1 / 2 (dense analytic / finite-difference J; thread-per-system problems,
  *          miter 2 also for the dense warp problem), 3 (diagonal approximation), 4 / 5 (banded
  *          analytic / FD J, band problems); mf < 0 = no saved Jacobian copy. */
-BVODE_API int bvode_solve(bvode_solver *s, int neq, double *y, double *t, const double *tout,
-                int tout_per_system, int itol, const double *rtol, const double *atol,
-                int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork, int liw,
+BVODE_API int bvode_solve(bvode_solver *s, int neq, bvode_real *y, bvode_real *t, const bvode_real *tout,
+                int tout_per_system, int itol, const bvode_real *rtol, const bvode_real *atol,
+                int itask, int *istate, int iopt, bvode_real *rwork, int lrw, int *iwork, int liw,
                 int mf);
 
 /* The reference's usage loop (test/example.f90:56-66: nout calls with increasing tout) as ONE
@@ -115,20 +125,20 @@ BVODE_API int bvode_solve(bvode_solver *s, int neq, double *y, double *t, const 
  *     for k in 0..nout-1: bvode_solve(..., tout = touts[k], ...); y_out[k] = y
  * including the per-call mxstep budget.  y holds y0 on entry (istate = 1) and the last output
  * on return; y_out[nout][nsys][neq] receives every output point (may be NULL). */
-BVODE_API int bvode_solve_schedule(bvode_solver *s, int neq, double *y, double *t, int nout,
-                         const double *touts, int itol, const double *rtol, const double *atol,
-                         int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork,
-                         int liw, int mf, double *y_out);
+BVODE_API int bvode_solve_schedule(bvode_solver *s, int neq, bvode_real *y, bvode_real *t, int nout,
+                         const bvode_real *touts, int itol, const bvode_real *rtol, const bvode_real *atol,
+                         int itask, int *istate, int iopt, bvode_real *rwork, int lrw, int *iwork,
+                         int liw, int mf, bvode_real *y_out);
 
 /* ---- dvindy (M:1878-1959): k-th derivative of the interpolating polynomial at t.
  * t: one value (t_per_system = 0) or t[nsys]; dky[nsys][neq]; iflag[nsys] = 0 / -1 / -2. */
-BVODE_API int bvode_dvindy(bvode_solver *s, const double *t, int t_per_system, int k, double *dky,
+BVODE_API int bvode_dvindy(bvode_solver *s, const bvode_real *t, int t_per_system, int k, bvode_real *dky,
                  int *iflag);
 
 /* Optional outputs without a solve call: rout[nsys][4] = rwork(11:14) = hu, hcur, tcur, tolsf;
  * iout[nsys][12] = iwork(11:22) = nst, nfe, nje, nqu, nqcur, imxer, lenrw, leniw, nlu, nni,
  * ncfn, netf (M:764-783, 978-997).  Either pointer may be NULL. */
-BVODE_API int bvode_get_stats(bvode_solver *s, double *rout, int *iout);
+BVODE_API int bvode_get_stats(bvode_solver *s, bvode_real *rout, int *iout);
 
 /* dvsrco (M:3198-3216): save (job = 1) / restore (job = 2) the whole batch state to / from a
  * host buffer of bvode_state_bytes() bytes: checkpoint / resume.  The blob carries the persistent
@@ -155,17 +165,17 @@ BVODE_API int bvode_format_message(bvode_solver *s, int sys, char *buf, int bufl
 /* ---- device-resident variants (inputs already in HBM; used for the kernel-only metric).
  * Layout on the device is structure-of-arrays: y_device[neq][nsys], params_device[npar][nsys],
  * y_out_device[nout][neq][nsys].  stream is a cudaStream_t passed as void* (0 = default). */
-BVODE_API int bvode_set_params_device(bvode_solver *s, const double *params_device);
-BVODE_API int bvode_solve_schedule_device(bvode_solver *s, int neq, double *y_device, double *t_device,
-                                int nout, const double *touts, int itol, const double *rtol,
-                                const double *atol, int itask, int *istate_device, int iopt,
-                                const double *rwork_opts, const int *iwork_opts, int mf,
-                                double *y_out_device, void *stream);
+BVODE_API int bvode_set_params_device(bvode_solver *s, const bvode_real *params_device);
+BVODE_API int bvode_solve_schedule_device(bvode_solver *s, int neq, bvode_real *y_device, bvode_real *t_device,
+                                int nout, const bvode_real *touts, int itol, const bvode_real *rtol,
+                                const bvode_real *atol, int itask, int *istate_device, int iopt,
+                                const bvode_real *rwork_opts, const int *iwork_opts, int mf,
+                                bvode_real *y_out_device, void *stream);
 /* One call (M:604-605) with inputs in HBM and a tout PER SYSTEM, tout_device[nsys] (the device-pointer form of
  * bvode_solve with tout_per_system = 1); optional outputs through bvode_get_stats. */
-BVODE_API int bvode_solve_device(bvode_solver *s, int neq, double *y_device, double *t_device,
-                       const double *tout_device, int itol, const double *rtol, const double *atol,
-                       int itask, int *istate_device, int iopt, const double *rwork_opts,
+BVODE_API int bvode_solve_device(bvode_solver *s, int neq, bvode_real *y_device, bvode_real *t_device,
+                       const bvode_real *tout_device, int itol, const bvode_real *rtol, const bvode_real *atol,
+                       int itask, int *istate_device, int iopt, const bvode_real *rwork_opts,
                        const int *iwork_opts, int mf, void *stream);
 /* number of kernels the last solve call launched (bench.py's gpu_launches) */
 BVODE_API int bvode_last_launch_count(const bvode_solver *s);
@@ -194,10 +204,10 @@ BVODE_API int bvode_comm_create(bvode_comm **out, const char id[128], int world,
 BVODE_API int bvode_comm_adopt(bvode_comm **out, void *nccl_comm, int world, int rank, int device);
 BVODE_API void bvode_comm_destroy(bvode_comm *c);
 BVODE_API int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys_total,
-                                  double *y_all_device, double *t_all_device, int *istate_all_device,
-                                  double *rout_all_device, int *iout_all_device, void *stream);
-BVODE_API int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, double *y_all,
-                           double *t_all, int *istate_all, double *rout_all, int *iout_all);
+                                  bvode_real *y_all_device, bvode_real *t_all_device, int *istate_all_device,
+                                  bvode_real *rout_all_device, int *iout_all_device, void *stream);
+BVODE_API int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total, bvode_real *y_all,
+                           bvode_real *t_all, int *istate_all, bvode_real *rout_all, int *iout_all);
 
 /* One process, several GPUs -- what a Fortran / C program without MPI calls to use the whole box.  The
  * batch of nsys_total systems is sharded over `ndev` devices (devices[ndev], NULL = 0..ndev-1); the solve
@@ -212,18 +222,18 @@ BVODE_API int bvode_multi_create(bvode_multi **out, int problem, long long nsys_
 BVODE_API void bvode_multi_destroy(bvode_multi *m);
 BVODE_API int bvode_multi_device_count(const bvode_multi *m);
 BVODE_API bvode_solver *bvode_multi_handle(bvode_multi *m, int slot);
-BVODE_API int bvode_multi_set_params(bvode_multi *m, const double *params);
-BVODE_API int bvode_multi_solve(bvode_multi *m, int neq, double *y, double *t, const double *tout,
-                                int tout_per_system, int itol, const double *rtol, const double *atol,
-                                int itask, int *istate, int iopt, double *rwork, int lrw, int *iwork,
+BVODE_API int bvode_multi_set_params(bvode_multi *m, const bvode_real *params);
+BVODE_API int bvode_multi_solve(bvode_multi *m, int neq, bvode_real *y, bvode_real *t, const bvode_real *tout,
+                                int tout_per_system, int itol, const bvode_real *rtol, const bvode_real *atol,
+                                int itask, int *istate, int iopt, bvode_real *rwork, int lrw, int *iwork,
                                 int liw, int mf);
-BVODE_API int bvode_multi_solve_schedule(bvode_multi *m, int neq, double *y, double *t, int nout,
-                                         const double *touts, int itol, const double *rtol,
-                                         const double *atol, int itask, int *istate, int iopt,
-                                         double *rwork, int lrw, int *iwork, int liw, int mf, double *y_out);
-BVODE_API int bvode_multi_gather_device(bvode_multi *m, int root_slot, double *y_all_device,
-                                        double *t_all_device, int *istate_all_device,
-                                        double *rout_all_device, int *iout_all_device);
+BVODE_API int bvode_multi_solve_schedule(bvode_multi *m, int neq, bvode_real *y, bvode_real *t, int nout,
+                                         const bvode_real *touts, int itol, const bvode_real *rtol,
+                                         const bvode_real *atol, int itask, int *istate, int iopt,
+                                         bvode_real *rwork, int lrw, int *iwork, int liw, int mf, bvode_real *y_out);
+BVODE_API int bvode_multi_gather_device(bvode_multi *m, int root_slot, bvode_real *y_all_device,
+                                        bvode_real *t_all_device, int *istate_all_device,
+                                        bvode_real *rout_all_device, int *iout_all_device);
 
 /* ---- the device LINPACK routines in isolation: known-answer entry for tests and diagnostics.  The reference
  * has no test of dgefa / dgesl / dgbfa / dgbsl (LP:46-522) on their own; this runs exactly the factor / solve code
@@ -237,8 +247,8 @@ BVODE_API int bvode_multi_gather_device(bvode_multi *m, int root_slot, double *y
  *           LINPACK's layout
  * x[nmat][n] = the solution (zeros where info != 0); info[nmat] as dgefa / dgbfa (LP:87-88, 119).
  * flags: BVODE_FLAG_STRICT selects the bit-exact build. */
-BVODE_API int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const double *a, const double *b,
-                            double *afac, int *ipvt, double *x, int *info, int device, unsigned flags);
+BVODE_API int bvode_lu_test(int kind, int n, int ml, int mu, int nmat, const bvode_real *a, const bvode_real *b,
+                            bvode_real *afac, int *ipvt, bvode_real *x, int *info, int device, unsigned flags);
 
 /* ---- DFMA peak microbenchmark (roofline denominator, FP64 vector pipe).  Runs `iters`
  * dependent-chain FMAs x 8 chains per thread on every SM and returns TFLOP/s. */

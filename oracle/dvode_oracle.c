@@ -12,34 +12,35 @@
  * control flow can be compared side by side with the reference.
  */
 #include "dvode_oracle.h"
-#include <math.h>
+#include <tgmath.h> /* type-generic fabs / sqrt / copysign: float functions in the REAL32 build, as in C++ */
 #include <string.h>
 #include <stdint.h>
 
-#define ZERO 0.0
-#define ONE 1.0
+#define ZERO ((real)0.0)
+#define ONE ((real)1.0)
 static const int mord[3] = {0, 12, 5}; /* M:38 */
 
-static inline double dmax2(double a, double b) { return a > b ? a : b; }
-static inline double dmin2(double a, double b) { return a < b ? a : b; }
+static inline real dmax2(real a, real b) { return a > b ? a : b; }
+static inline real dmin2(real a, real b) { return a < b ? a : b; }
 static inline int imax2(int a, int b) { return a > b ? a : b; }
 static inline int imin2(int a, int b) { return a < b ? a : b; }
-static inline double dsign(double a, double b) { return copysign(fabs(a), b); }
+static inline real dsign(real a, real b) { return copysign(fabs(a), b); }
 
 /* ---------------------------------------------------------------- pow ---- */
 
 /* gfortran lowers real**integer to __builtin_powi -> libgcc __powidf2 */
-double dvo_powi(double x, int m)
+real dvo_powi(real x, int m)
 {
     unsigned int n = m < 0 ? -(unsigned int)m : (unsigned int)m;
-    double y = (n % 2) ? x : 1.0;
+    real y = (n % 2) ? x : DVO_R(1.0);
     while (n >>= 1) {
         x = x * x;
         if (n % 2) y *= x;
     }
-    return m < 0 ? 1.0 / y : y;
+    return m < 0 ? DVO_R(1.0) / y : y;
 }
 
+/* REALIFY-OFF (double inside whatever `real` is) */
 /* Portable x**y for x > 0: exp(y*log(x)) from + - * / and bit moves only, with
  * every operation individually rounded (no FMA), so that the device strict
  * build reproduces it bit for bit.  Accuracy: a few ulp; it is NOT the
@@ -114,37 +115,38 @@ double dvo_ppow(double x, double y)
     return (er * t1.d) * t2.d;
 }
 
-static inline double rpow(const dvo_solver *me, double x, double y)
+/* REALIFY-ON */
+static inline real rpow(const dvo_solver *me, real x, real y)
 {
-    return me->pow_mode ? dvo_ppow(x, y) : pow(x, y);
+    return me->pow_mode ? (real)dvo_ppow((real)x, (real)y) : (real)pow((real)x, (real)y);
 }
 
 /* ------------------------------------------------------------- BLAS-1 ---- */
 /* BL:37 daxpy (da == 0 early-out, BL:50), BL:100 dcopy, BL:233 dscal,
  * BL:311 idamax (first index of max |x|, strict '>', BL:334).  Unit stride
  * only -- every call site on the path uses incx = incy = 1. */
-static void daxpy(int n, double da, const double *dx, double *dy)
+static void daxpy(int n, real da, const real *dx, real *dy)
 {
     if (n <= 0) return;
     if (da == ZERO) return;
     for (int i = 0; i < n; i++) dy[i] = dy[i] + da * dx[i];
 }
-static void dcopy(int n, const double *dx, double *dy)
+static void dcopy(int n, const real *dx, real *dy)
 {
     for (int i = 0; i < n; i++) dy[i] = dx[i];
 }
-static void dscal(int n, double da, double *dx)
+static void dscal(int n, real da, real *dx)
 {
     for (int i = 0; i < n; i++) dx[i] = da * dx[i];
 }
-static int idamax(int n, const double *dx) /* returns 1-based index */
+static int idamax(int n, const real *dx) /* returns 1-based index */
 {
     if (n <= 0) return 0;
     int imax = 1;
     if (n == 1) return imax;
-    double dmax = fabs(dx[0]);
+    real dmax = fabs(dx[0]);
     for (int i = 2; i <= n; i++) {
-        double xmag = fabs(dx[i - 1]);
+        real xmag = fabs(dx[i - 1]);
         if (xmag > dmax) { imax = i; dmax = xmag; }
     }
     return imax;
@@ -171,9 +173,9 @@ int dvo_singular_events(int reset)
     return v;
 }
 
-void dvo_dgefa(double *a, int lda, int n, int *ipvt, int *info)
+void dvo_dgefa(real *a, int lda, int n, int *ipvt, int *info)
 {
-    double t;
+    real t;
     int j, k, kp1, l, nm1;
     *info = 0;
     nm1 = n - 1;
@@ -182,11 +184,11 @@ void dvo_dgefa(double *a, int lda, int n, int *ipvt, int *info)
             kp1 = k + 1;
             l = idamax(n - k + 1, &A(k, k)) + k - 1;
             ipvt[k - 1] = l;
-            if (A(l, k) == 0.0) {
+            if (A(l, k) == DVO_R(0.0)) {
                 *info = k;
             } else {
                 if (l != k) { t = A(l, k); A(l, k) = A(k, k); A(k, k) = t; }
-                t = -1.0 / A(k, k);
+                t = -DVO_R(1.0) / A(k, k);
                 dscal(n - k, t, &A(k + 1, k));
                 for (j = kp1; j <= n; j++) {
                     t = A(l, j);
@@ -197,13 +199,13 @@ void dvo_dgefa(double *a, int lda, int n, int *ipvt, int *info)
         }
     }
     ipvt[n - 1] = n;
-    if (A(n, n) == 0.0) *info = n;
+    if (A(n, n) == DVO_R(0.0)) *info = n;
 }
 
 /* LP:157-228, job = 0 branch (LP:206-225) */
-void dvo_dgesl(const double *a, int lda, int n, const int *ipvt, double *b)
+void dvo_dgesl(const real *a, int lda, int n, const int *ipvt, real *b)
 {
-    double t;
+    real t;
     int k, kb, l, nm1;
     nm1 = n - 1;
     if (nm1 >= 1) {
@@ -225,9 +227,9 @@ void dvo_dgesl(const double *a, int lda, int n, const int *ipvt, double *b)
 
 #define ABD(i, j) abd[((i)-1) + (size_t)((j)-1) * lda]
 /* LP:275-396 */
-void dvo_dgbfa(double *abd, int lda, int n, int ml, int mu, int *ipvt, int *info)
+void dvo_dgbfa(real *abd, int lda, int n, int ml, int mu, int *ipvt, int *info)
 {
-    double t;
+    real t;
     int i, i0, j, ju, jz, j0, j1, k, kp1, l, lm, m, mm, nm1;
     m = ml + mu + 1;
     *info = 0;
@@ -236,7 +238,7 @@ void dvo_dgbfa(double *abd, int lda, int n, int ml, int mu, int *ipvt, int *info
     if (j1 >= j0) {
         for (jz = j0; jz <= j1; jz++) {
             i0 = m + 1 - jz;
-            for (i = i0; i <= ml; i++) ABD(i, jz) = 0.0;
+            for (i = i0; i <= ml; i++) ABD(i, jz) = DVO_R(0.0);
         }
     }
     jz = j1;
@@ -248,16 +250,16 @@ void dvo_dgbfa(double *abd, int lda, int n, int ml, int mu, int *ipvt, int *info
             jz = jz + 1;
             if (jz <= n) {
                 if (ml >= 1)
-                    for (i = 1; i <= ml; i++) ABD(i, jz) = 0.0;
+                    for (i = 1; i <= ml; i++) ABD(i, jz) = DVO_R(0.0);
             }
             lm = imin2(ml, n - k);
             l = idamax(lm + 1, &ABD(m, k)) + m - 1;
             ipvt[k - 1] = l + k - m;
-            if (ABD(l, k) == 0.0) {
+            if (ABD(l, k) == DVO_R(0.0)) {
                 *info = k;
             } else {
                 if (l != m) { t = ABD(l, k); ABD(l, k) = ABD(m, k); ABD(m, k) = t; }
-                t = -1.0 / ABD(m, k);
+                t = -DVO_R(1.0) / ABD(m, k);
                 dscal(lm, t, &ABD(m + 1, k));
                 ju = imin2(imax2(ju, mu + ipvt[k - 1]), n);
                 mm = m;
@@ -274,13 +276,13 @@ void dvo_dgbfa(double *abd, int lda, int n, int ml, int mu, int *ipvt, int *info
         }
     }
     ipvt[n - 1] = n;
-    if (ABD(m, n) == 0.0) *info = n;
+    if (ABD(m, n) == DVO_R(0.0)) *info = n;
 }
 
 /* LP:435-522, job = 0 branch (LP:494-519) */
-void dvo_dgbsl(const double *abd, int lda, int n, int ml, int mu, const int *ipvt, double *b)
+void dvo_dgbsl(const real *abd, int lda, int n, int ml, int mu, const int *ipvt, real *b)
 {
-    double t;
+    real t;
     int k, kb, l, la, lb, lm, m, nm1;
     m = mu + ml + 1;
     nm1 = n - 1;
@@ -309,8 +311,8 @@ void dvo_dgbsl(const double *abd, int lda, int n, int ml, int mu, const int *ipv
 
 /* ------------------------------------------------ dewset / dvnorm -------- */
 /* M:3238-3273 */
-static void dewset_default(int n, int itol, const double *rtol, const double *atol,
-                           const double *ycur, double *ewt)
+static void dewset_default(int n, int itol, const real *rtol, const real *atol,
+                           const real *ycur, real *ewt)
 {
     int i;
     switch (itol) {
@@ -323,14 +325,14 @@ static void dewset_default(int n, int itol, const double *rtol, const double *at
 }
 
 /* M:3295-3311 */
-static double dvnorm_default(int n, const double *v, const double *w)
+static real dvnorm_default(int n, const real *v, const real *w)
 {
-    double sum = ZERO;
+    real sum = ZERO;
     for (int i = 0; i < n; i++) {
-        double p = v[i] * w[i];
+        real p = v[i] * w[i];
         sum = sum + p * p;
     }
-    return sqrt(sum / (double)n);
+    return sqrt(sum / (real)n);
 }
 
 /* the procedure pointers of dvode_t (M:305-306): user routine or default */
@@ -368,13 +370,13 @@ void dvo_dvsrco(dvo_solver *s, dvo_solver *sav, int job)
 
 /* ------------------------------------------------------------- dvhin ----- */
 /* M:1738-1851.  All arrays 0-based here. */
-static void dvhin(dvo_solver *me, int n, double t0, const double *y0, const double *ydot,
-                  double tout, double uround, const double *ewt, int itol,
-                  const double *atol, double *y, double *temp, double *h0, int *niter,
+static void dvhin(dvo_solver *me, int n, real t0, const real *y0, const real *ydot,
+                  real tout, real uround, const real *ewt, int itol,
+                  const real *atol, real *y, real *temp, real *h0, int *niter,
                   int *ier)
 {
-    const double half = 0.5, hun = 100.0, pt1 = 0.1, two = 2.0;
-    double afi, atoli, delyi, h, hg, hlb, hnew = 0.0, hrat, hub, t1, tdist, tround, yddnrm;
+    const real half = DVO_R(0.5), hun = DVO_R(100.0), pt1 = DVO_R(0.1), two = DVO_R(2.0);
+    real afi, atoli, delyi, h, hg, hlb, hnew = DVO_R(0.0), hrat, hub, t1, tdist, tround, yddnrm;
     int i, iter;
 
     *niter = 0;
@@ -426,12 +428,12 @@ static void dvhin(dvo_solver *me, int n, double t0, const double *y0, const doub
 
 /* ------------------------------------------------------------ dvindy ----- */
 /* M:1878-1959 */
-void dvo_dvindy(dvo_solver *me, double t, int k, const double *yh, int ldyh, double *dky,
+void dvo_dvindy(dvo_solver *me, real t, int k, const real *yh, int ldyh, real *dky,
                 int *iflag)
 {
 #define YH(i, j) yh[((i)-1) + (size_t)((j)-1) * ldyh]
-    const double hun = 100.0;
-    double c, r, s, tfuzz, tn1, tp;
+    const real hun = DVO_R(100.0);
+    real c, r, s, tfuzz, tn1, tp;
     int i, ic, j, jb, jb2, jj, jj1, jp1;
 
     *iflag = 0;
@@ -446,7 +448,7 @@ void dvo_dvindy(dvo_solver *me, double t, int k, const double *yh, int ldyh, dou
         jj1 = me->l - k;
         for (jj = jj1; jj <= me->nq; jj++) ic = ic * jj;
     }
-    c = (double)ic;
+    c = (real)ic;
     for (i = 1; i <= me->n; i++) dky[i - 1] = c * YH(i, me->l);
     if (k != me->nq) {
         jb2 = me->nq - k;
@@ -458,7 +460,7 @@ void dvo_dvindy(dvo_solver *me, double t, int k, const double *yh, int ldyh, dou
                 jj1 = jp1 - k;
                 for (jj = jj1; jj <= j; jj++) ic = ic * jj;
             }
-            c = (double)ic;
+            c = (real)ic;
             for (i = 1; i <= me->n; i++) dky[i - 1] = c * YH(i, jp1) + s * dky[i - 1];
         }
         if (k == 0) return;
@@ -472,13 +474,13 @@ void dvo_dvindy(dvo_solver *me, double t, int k, const double *yh, int ldyh, dou
 /* M:2422-2561.  el, tau, tq are used 1-based (element 0 unused). */
 static void dvset(dvo_solver *me)
 {
-    const double cortes = 0.1, one = 1.0, six = 6.0, two = 2.0;
-    double ahatn0, alph0, cnqm1, csum, elp, em[14], em0, floti, flotl, flotnq, hsum, rxi,
+    const real cortes = DVO_R(0.1), one = DVO_R(1.0), six = DVO_R(6.0), two = DVO_R(2.0);
+    real ahatn0, alph0, cnqm1, csum, elp, em[14], em0, floti, flotl, flotnq, hsum, rxi,
         rxis, s, t1, t2, t3, t4, t5, t6, xi;
     int i, iback, j, jp1, nqm1, nqm2;
-    double *el = me->el, *tau = me->tau, *tq = me->tq;
+    real *el = me->el, *tau = me->tau, *tq = me->tq;
 
-    flotl = (double)me->l;
+    flotl = (real)me->l;
     nqm1 = me->nq - 1;
     nqm2 = me->nq - 2;
     if (me->meth == 2) {
@@ -495,13 +497,13 @@ static void dvset(dvo_solver *me)
                 hsum = hsum + tau[j];
                 rxi = me->h / hsum;
                 jp1 = j + 1;
-                alph0 = alph0 - one / (double)jp1;
+                alph0 = alph0 - one / (real)jp1;
                 for (iback = 1; iback <= jp1; iback++) {
                     i = (j + 3) - iback;
                     el[i] = el[i] + el[i - 1] * rxi;
                 }
             }
-            alph0 = alph0 - one / (double)me->nq;
+            alph0 = alph0 - one / (real)me->nq;
             rxis = -el[2] - alph0;
             hsum = hsum + tau[nqm1];
             rxi = me->h / hsum;
@@ -512,18 +514,18 @@ static void dvset(dvo_solver *me)
             }
         }
         t1 = one - ahatn0 + alph0;
-        t2 = one + (double)me->nq * t1;
+        t2 = one + (real)me->nq * t1;
         tq[2] = fabs(alph0 * t2 / t1);
         tq[5] = fabs(t2 / (el[me->l] * rxi / rxis));
         if (me->nqwait == 1) {
             cnqm1 = rxis / el[me->l];
-            t3 = alph0 + one / (double)me->nq;
+            t3 = alph0 + one / (real)me->nq;
             t4 = ahatn0 + rxi;
             elp = t3 / (one - t4 + t3);
             tq[1] = fabs(elp / cnqm1);
             hsum = hsum + tau[me->nq];
             rxi = me->h / hsum;
-            t5 = alph0 - one / (double)(me->nq + 1);
+            t5 = alph0 - one / (real)(me->nq + 1);
             t6 = ahatn0 - rxi;
             elp = t2 / (one - t6 + t5);
             tq[3] = fabs(elp * rxi * (flotl + one) * t5);
@@ -539,7 +541,7 @@ static void dvset(dvo_solver *me)
                 s = one;
                 csum = ZERO;
                 for (i = 1; i <= nqm1; i++) {
-                    csum = csum + s * em[i] / (double)(i + 1);
+                    csum = csum + s * em[i] / (real)(i + 1);
                     s = -s;
                 }
                 tq[1] = em[nqm1] / (flotnq * csum);
@@ -555,14 +557,14 @@ static void dvset(dvo_solver *me)
         em0 = ZERO;
         csum = ZERO;
         for (i = 1; i <= me->nq; i++) {
-            floti = (double)i;
+            floti = (real)i;
             em0 = em0 + s * em[i] / floti;
             csum = csum + s * em[i] / (floti + one);
             s = -s;
         }
         s = one / em0;
         el[1] = one;
-        for (i = 1; i <= me->nq; i++) el[i + 1] = s * em[i] / (double)i;
+        for (i = 1; i <= me->nq; i++) el[i + 1] = s * em[i] / (real)i;
         xi = hsum / me->h;
         tq[2] = xi * em0 / csum;
         tq[5] = xi / el[me->l];
@@ -575,7 +577,7 @@ static void dvset(dvo_solver *me)
             s = one;
             csum = ZERO;
             for (i = 1; i <= me->l; i++) {
-                csum = csum + s * em[i] / (double)(i + 1);
+                csum = csum + s * em[i] / (real)(i + 1);
                 s = -s;
             }
             tq[3] = flotl * em0 / csum;
@@ -593,13 +595,13 @@ static void dvset(dvo_solver *me)
 
 /* ------------------------------------------------------------ dvjust ----- */
 /* M:2568-2694 */
-static void dvjust(dvo_solver *me, double *yh, int ldyh, int iord)
+static void dvjust(dvo_solver *me, real *yh, int ldyh, int iord)
 {
 #define YH(i, j) yh[((i)-1) + (size_t)((j)-1) * ldyh]
-    const double one = 1.0;
-    double alph0, alph1, hsum, prod, t1, xi, xiold;
+    const real one = DVO_R(1.0);
+    real alph0, alph1, hsum, prod, t1, xi, xiold;
     int i, iback, j, jp1, lp1, nqm1, nqm2, nqp1;
-    double *el = me->el, *tau = me->tau;
+    real *el = me->el, *tau = me->tau;
 
     if ((me->nq == 2) && (iord != 1)) return;
     nqm1 = me->nq - 1;
@@ -619,7 +621,7 @@ static void dvjust(dvo_solver *me, double *yh, int ldyh, int iord)
                     hsum = hsum + tau[jp1];
                     xi = hsum / me->hscal;
                     prod = prod * xi;
-                    alph0 = alph0 - one / (double)jp1;
+                    alph0 = alph0 - one / (real)jp1;
                     alph1 = alph1 + one / xi;
                     for (iback = 1; iback <= jp1; iback++) {
                         i = (j + 4) - iback;
@@ -667,7 +669,7 @@ static void dvjust(dvo_solver *me, double *yh, int ldyh, int iord)
                 el[i] = el[i] * xi + el[i - 1];
             }
         }
-        for (j = 2; j <= nqm1; j++) el[j + 1] = (double)me->nq * el[j] / (double)j;
+        for (j = 2; j <= nqm1; j++) el[j + 1] = (real)me->nq * el[j] / (real)j;
         for (j = 3; j <= me->nq; j++)
             for (i = 1; i <= me->n; i++) YH(i, j) = YH(i, j) - YH(i, me->l) * el[j];
         return;
@@ -677,7 +679,7 @@ static void dvjust(dvo_solver *me, double *yh, int ldyh, int iord)
 
 /* ------------------------------------------------------------- dacopy ---- */
 /* M:3112-3127 */
-static void dacopy(int nrow, int ncol, const double *a, int nrowa, double *b, int nrowb)
+static void dacopy(int nrow, int ncol, const real *a, int nrowa, real *b, int nrowb)
 {
     for (int ic = 0; ic < ncol; ic++)
         dcopy(nrow, a + (size_t)ic * nrowa, b + (size_t)ic * nrowb);
@@ -685,8 +687,8 @@ static void dacopy(int nrow, int ncol, const double *a, int nrowa, double *b, in
 
 /* -------------------------------------------------------------- dvjac ---- */
 /* M:2897-3104.  wm and iwm 1-based via macros; y, ewt, ftem, savf 1-based too. */
-static void dvjac(dvo_solver *me, double *y0, const double *yh, int ldyh, const double *ewt0,
-                  double *ftem0, const double *savf0, double *wm0, int *iwm0, int *ierpj)
+static void dvjac(dvo_solver *me, real *y0, const real *yh, int ldyh, const real *ewt0,
+                  real *ftem0, const real *savf0, real *wm0, int *iwm0, int *ierpj)
 {
 #define YH(i, j) yh[((i)-1) + (size_t)((j)-1) * ldyh]
 #define WM(i) wm0[(i)-1]
@@ -695,8 +697,8 @@ static void dvjac(dvo_solver *me, double *y0, const double *yh, int ldyh, const 
 #define EWT(i) ewt0[(i)-1]
 #define FTEM(i) ftem0[(i)-1]
 #define SAVF(i) savf0[(i)-1]
-    const double one = 1.0, thou = 1000.0, pt1 = 0.1;
-    double con, di, fac, hrl1, r, r0, srur, yi, yj, yjj;
+    const real one = DVO_R(1.0), thou = DVO_R(1000.0), pt1 = DVO_R(0.1);
+    real con, di, fac, hrl1, r, r0, srur, yi, yj, yjj;
     int i, i1, i2, ier, ii, j, j1, jj, jok, lenp = 0, mba, mband, meb1, meband, ml, ml3, mu,
         np1;
     const int n = me->n;
@@ -725,7 +727,7 @@ static void dvjac(dvo_solver *me, double *y0, const double *yh, int ldyh, const 
         me->nslj = me->nst;
         me->jcur = 1;
         fac = dvnorm(n, savf0, ewt0);
-        r0 = thou * fabs(me->h) * me->uround * (double)n * fac;
+        r0 = thou * fabs(me->h) * me->uround * (real)n * fac;
         if (r0 == ZERO) r0 = one;
         srur = WM(1);
         j1 = 2;
@@ -809,7 +811,7 @@ static void dvjac(dvo_solver *me, double *y0, const double *yh, int ldyh, const 
         meb1 = meband - 1;
         srur = WM(1);
         fac = dvnorm(n, savf0, ewt0);
-        r0 = thou * fabs(me->h) * me->uround * (double)n * fac;
+        r0 = thou * fabs(me->h) * me->uround * (real)n * fac;
         if (r0 == ZERO) r0 = one;
         for (j = 1; j <= mba; j++) {
             for (i = j; i <= n; i += mband) {
@@ -857,11 +859,11 @@ static void dvjac(dvo_solver *me, double *y0, const double *yh, int ldyh, const 
 
 /* -------------------------------------------------------------- dvsol ---- */
 /* M:3139-3191 */
-static void dvsol(dvo_solver *me, double *wm0, int *iwm0, double *x, int *iersl)
+static void dvsol(dvo_solver *me, real *wm0, int *iwm0, real *x, int *iersl)
 {
-    const double one = 1.0;
+    const real one = DVO_R(1.0);
     int i, meband, ml, mu;
-    double di, hrl1, phrl1, r;
+    real di, hrl1, phrl1, r;
     const int n = me->n;
 
     *iersl = 0;
@@ -897,13 +899,13 @@ static void dvsol(dvo_solver *me, double *wm0, int *iwm0, double *x, int *iersl)
 
 /* ------------------------------------------------------------- dvnlsd ---- */
 /* M:2703-2879.  y, savf, ewt, acor 0-based; yh 1-based via macro. */
-static void dvnlsd(dvo_solver *me, double *y, double *yh, int ldyh, double *vsav, double *savf,
-                   const double *ewt, double *acor, int *iwm, double *wm, int *nflag)
+static void dvnlsd(dvo_solver *me, real *y, real *yh, int ldyh, real *vsav, real *savf,
+                   const real *ewt, real *acor, int *iwm, real *wm, int *nflag)
 {
 #define YH(i, j) yh[((i)-1) + (size_t)((j)-1) * ldyh]
     const int maxcor = 3, msbp = 20;
-    const double ccmax = 0.3, crdown = 0.3, rdiv = 2.0, one = 1.0, two = 2.0;
-    double cscale, dcon, del = 0.0, delp;
+    const real ccmax = DVO_R(0.3), crdown = DVO_R(0.3), rdiv = DVO_R(2.0), one = DVO_R(1.0), two = DVO_R(2.0);
+    real cscale, dcon, del = DVO_R(0.0), delp;
     int i, ierpj, iersl, m;
     const int n = me->n;
     (void)vsav;
@@ -1000,16 +1002,16 @@ static void dvnlsd(dvo_solver *me, double *y, double *yh, int ldyh, double *vsav
 
 /* ------------------------------------------------------------- dvstep ---- */
 /* M:1975-2377 */
-static void dvstep(dvo_solver *me, double *y, double *yh, int ldyh, double *yh1, double *ewt,
-                   double *savf, double *vsav, double *acor, double *wm, int *iwm)
+static void dvstep(dvo_solver *me, real *y, real *yh, int ldyh, real *yh1, real *ewt,
+                   real *savf, real *vsav, real *acor, real *wm, int *iwm)
 {
 #define YH(i, j) yh[((i)-1) + (size_t)((j)-1) * ldyh]
 #define YH1(i) yh1[(i)-1]
     const int kfc = -3, kfh = -7, mxncf = 10;
-    const double one = 1.0, addon = 1.0e-6, bias1 = 6.0, bias2 = 6.0, bias3 = 10.0,
-                 etacf = 0.25, etamin = 0.1, etamxf = 0.2, etamx1 = 1.0e4, etamx2 = 10.0,
-                 etamx3 = 10.0, onepsm = 1.00001, thresh = 1.5;
-    double cnquot, ddn, dsm, dup, etaqp1, flotl, r, told;
+    const real one = DVO_R(1.0), addon = DVO_R(1.0e-6), bias1 = DVO_R(6.0), bias2 = DVO_R(6.0), bias3 = DVO_R(10.0),
+                 etacf = DVO_R(0.25), etamin = DVO_R(0.1), etamxf = DVO_R(0.2), etamx1 = DVO_R(1.0e4), etamx2 = DVO_R(10.0),
+                 etamx3 = DVO_R(10.0), onepsm = DVO_R(1.00001), thresh = DVO_R(1.5);
+    real cnquot, ddn, dsm, dup, etaqp1, flotl, r, told;
     int i, i1, i2, iback, j, jb, ncf, nflag;
     const int n = me->n;
 
@@ -1030,7 +1032,7 @@ static void dvstep(dvo_solver *me, double *y, double *yh, int ldyh, double *yh1,
                     for (i = i1; i <= i2; i++) YH1(i) = ZERO;
             }
             if (me->newq > me->maxord) {
-                flotl = (double)me->lmax;
+                flotl = (real)me->lmax;
                 if (me->maxord < me->nq - 1) {
                     ddn = dvnorm(n, savf, ewt) / me->tq[1];
                     me->eta = one / (rpow(me, bias1 * ddn, one / flotl) + addon);
@@ -1133,7 +1135,7 @@ L400: /* predict, M:2147-2158 */
             } else {
                 me->etamax = one;
                 if (me->kflag > kfc) {
-                    flotl = (double)me->l;
+                    flotl = (real)me->l;
                     me->eta = one / (rpow(me, bias2 * dsm, one / flotl) + addon);
                     me->eta = dmax2(dmax2(me->eta, me->hmin / fabs(me->h)), etamin);
                     if ((me->kflag <= -2) && (me->eta > etamxf)) me->eta = etamxf;
@@ -1179,7 +1181,7 @@ L400: /* predict, M:2147-2158 */
                 me->conp = me->tq[5];
             }
             if (me->etamax != one) {
-                flotl = (double)me->l;
+                flotl = (real)me->l;
                 me->etaq = one / (rpow(me, bias2 * dsm, one / flotl) + addon);
                 if (me->nqwait == 0) {
                     me->nqwait = 2;
@@ -1278,16 +1280,16 @@ L500: /* M:2370-2375 */
 
 /* -------------------------------------------------------------- dvode ---- */
 /* M:604-1725 */
-void dvo_solve(dvo_solver *me, int neq, double *y, double *t, double tout, int itol,
-               const double *rtol, const double *atol, int itask, int *istate, int iopt,
-               double *rwork, int lrw, int *iwork, int liw, int mf)
+void dvo_solve(dvo_solver *me, int neq, real *y, real *t, real tout, int itol,
+               const real *rtol, const real *atol, int itask, int *istate, int iopt,
+               real *rwork, int lrw, int *iwork, int liw, int mf)
 {
 #define RW(i) rwork[(i)-1]
 #define IW(i) iwork[(i)-1]
     const int mxhnl0 = 10, mxstp0 = 500;
-    const double one = 1.0, two = 2.0, four = 4.0, pt2 = 0.2, hun = 100.0;
+    const real one = DVO_R(1.0), two = DVO_R(2.0), four = DVO_R(4.0), pt2 = DVO_R(0.2), hun = DVO_R(100.0);
     int ihit = 0;
-    double atoli, big, h0 = 0.0, hmax, hmx, rh, rtoli, size, tcrit = 0.0, tnext, tolsf, tp;
+    real atoli, big, h0 = DVO_R(0.0), hmax, hmx, rh, rtoli, size, tcrit = DVO_R(0.0), tnext, tolsf, tp;
     int i, ier, iflag, imxer, jco, leniw, lenj, lenp, lenrw, lenwm = 0, lf0, mband, mfa,
         ml = 0, mu = 0, niter, nslast = 0;
 
@@ -1457,7 +1459,11 @@ void dvo_solve(dvo_solver *me, int neq, double *y, double *t, double tout, int i
     }
     if (*istate == 1) {
         /* block c, M:1312-1381 */
-        me->uround = 2.220446049250313e-16; /* epsilon(1.0_real64), M:36 */
+#ifdef DVO_REAL32
+        me->uround = 1.1920929e-07f; /* epsilon(1.0_real32), M:36 with wp = real32 */
+#else
+        me->uround = DVO_R(2.220446049250313e-16); /* epsilon(1.0_real64), M:36 */
+#endif
         me->tn = *t;
         if (itask == 4 || itask == 5) {
             tcrit = RW(1);

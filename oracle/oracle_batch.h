@@ -14,35 +14,35 @@ typedef struct dvo_batch_cfg {
     int mf, itol, itask, iopt; /* as in dvode, M:604 */
     int ml, mu;                /* iwork(1:2) */
     int maxord, mxstep, mxhnil;/* iwork(5:7), used when iopt = 1 */
-    double h0, hmax, hmin;     /* rwork(5:7), used when iopt = 1 */
-    double tcrit;              /* rwork(1) */
+    real h0, hmax, hmin;     /* rwork(5:7), used when iopt = 1 */
+    real tcrit;              /* rwork(1) */
     int pow_mode;              /* 0 libm pow, 1 portable pow (strict GPU comparison) */
 } dvo_batch_cfg;
 
 int dvo_problem_info(int problem, int *neq, int *npar);
-void dvo_problem_f(int problem, const double *par, double t, const double *y, double *ydot);
+void dvo_problem_f(int problem, const real *par, real t, const real *y, real *ydot);
 void dvo_work_sizes(int neq, int mf, int ml, int mu, int maxord_in, int *lrw, int *liw);
 
 /* returns the number of systems that ended with istate < 0 (or -1 on bad problem).
  * rstats[.][.][4] = rwork(11:14); istats[.][.][12] = iwork(11:22). */
-int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, const double *y0,
-                    double t0, int nout, const double *touts, const double *rtol,
-                    const double *atol, double *y_out, double *t_out, int *istate_out,
-                    double *rstats, int *istats, int nthreads);
+int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const real *params, const real *y0,
+                    real t0, int nout, const real *touts, const real *rtol,
+                    const real *atol, real *y_out, real *t_out, int *istate_out,
+                    real *rstats, int *istats, int nthreads);
 
 int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int nsplit, int nsys,
-                     const double *params, const double *y0, double t0, int nout,
-                     const double *touts, const double *rtol, const double *atol,
-                     const double *rtol2, const double *atol2, double *y_out, double *t_out,
-                     int *istate_out, double *rstats, int *istats, int nthreads);
+                     const real *params, const real *y0, real t0, int nout,
+                     const real *touts, const real *rtol, const real *atol,
+                     const real *rtol2, const real *atol2, real *y_out, real *t_out,
+                     int *istate_out, real *rstats, int *istats, int nthreads);
 
 /* threads the last dvo_batch_solve / dvo_batch_solve2 call actually ran on */
 int dvo_last_threads(void);
 
-int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par, const double *y0, double t0,
-                     double tout, const double *rtol, const double *atol, int k, int nq,
-                     const double *tqs, double *dky_out, int *iflag_out, double *tcur,
-                     double *hu);
+int dvo_single_dense(const dvo_batch_cfg *cfg, const real *par, const real *y0, real t0,
+                     real tout, const real *rtol, const real *atol, int k, int nq,
+                     const real *tqs, real *dky_out, int *iflag_out, real *tcur,
+                     real *hu);
 #ifdef __cplusplus
 }
 #endif

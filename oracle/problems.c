@@ -17,7 +17,7 @@
 #include "dvode_oracle.h"
 #include "oracle_batch.h"
 #include "../include/bvode_mech32.h"
-#include <math.h>
+#include <tgmath.h> /* type-generic fabs / sqrt / copysign: float functions in the REAL32 build, as in C++ */
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -26,18 +26,18 @@
 
 /* ---------------------------------------------------------- Robertson ---- */
 /* par = (k1, k2, k3); reference values 0.04, 1e4, 3e7 (example.f90:87-89) */
-static void rob_f(void *ctx, int neq, double t, const double *y, double *ydot)
+static void rob_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
-    const double *k = (const double *)ctx;
+    const real *k = (const real *)ctx;
     (void)neq; (void)t;
     ydot[0] = -k[0] * y[0] + k[1] * y[1] * y[2];
     ydot[2] = k[2] * y[1] * y[1];
     ydot[1] = -ydot[0] - ydot[2];
 }
-static void rob_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+static void rob_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *pd,
                     int nrowpd)
 {
-    const double *k = (const double *)ctx;
+    const real *k = (const real *)ctx;
     (void)neq; (void)t; (void)ml; (void)mu;
 #define PD(i, j) pd[((i)-1) + ((j)-1) * nrowpd]
     PD(1, 1) = -k[0];
@@ -45,62 +45,62 @@ static void rob_jac(void *ctx, int neq, double t, double *y, int ml, int mu, dou
     PD(1, 3) = k[1] * y[1];
     PD(2, 1) = k[0];
     PD(2, 3) = -PD(1, 3);
-    PD(3, 2) = (2.0 * k[2]) * y[1];
+    PD(3, 2) = (DVO_R(2.0) * k[2]) * y[1];
     PD(2, 2) = -PD(1, 2) - PD(3, 2);
 }
 
 /* -------------------------------------------------------- Van der Pol ---- */
 /* par = (eta), reference value 3 (dvdemo.f90:214,227) */
-static void vdp_f(void *ctx, int neq, double t, const double *y, double *ydot)
+static void vdp_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
-    const double *p = (const double *)ctx;
+    const real *p = (const real *)ctx;
     (void)neq; (void)t;
     ydot[0] = y[1];
-    ydot[1] = p[0] * (1.0 - y[0] * y[0]) * y[1] - y[0];
+    ydot[1] = p[0] * (DVO_R(1.0) - y[0] * y[0]) * y[1] - y[0];
 }
-static void vdp_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+static void vdp_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *pd,
                     int nrowpd)
 {
-    const double *p = (const double *)ctx;
+    const real *p = (const real *)ctx;
     (void)neq; (void)t; (void)ml; (void)mu;
-    PD(1, 1) = 0.0;
-    PD(1, 2) = 1.0;
-    PD(2, 1) = -(2.0 * p[0]) * y[0] * y[1] - 1.0;
-    PD(2, 2) = p[0] * (1.0 - y[0] * y[0]);
+    PD(1, 1) = DVO_R(0.0);
+    PD(1, 2) = DVO_R(1.0);
+    PD(2, 1) = -(DVO_R(2.0) * p[0]) * y[0] * y[1] - DVO_R(1.0);
+    PD(2, 2) = p[0] * (DVO_R(1.0) - y[0] * y[0]);
 }
 
 /* Van der Pol with USER error weights and norm (initialize's optional dewset / dvnorm,
  * M:431-503): ewt_i = rtol_i*max(|y_i|, 1) + atol_i, max norm. */
-static void vdpm_dewset(void *ctx, int n, int itol, const double *rtol, const double *atol,
-                        const double *ycur, double *ewt)
+static void vdpm_dewset(void *ctx, int n, int itol, const real *rtol, const real *atol,
+                        const real *ycur, real *ewt)
 {
     (void)ctx;
     for (int i = 0; i < n; i++) {
-        double r = (itol >= 3) ? rtol[i] : rtol[0];
-        double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
-        double ay = fabs(ycur[i]);
-        if (ay < 1.0) ay = 1.0;
+        real r = (itol >= 3) ? rtol[i] : rtol[0];
+        real a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        real ay = fabs(ycur[i]);
+        if (ay < DVO_R(1.0)) ay = DVO_R(1.0);
         ewt[i] = r * ay + a;
     }
 }
 /* problem 7: the default weights, except that ewt_1 drops by one once |y_1| < 1/2 */
-static void vdpd_dewset(void *ctx, int n, int itol, const double *rtol, const double *atol,
-                        const double *ycur, double *ewt)
+static void vdpd_dewset(void *ctx, int n, int itol, const real *rtol, const real *atol,
+                        const real *ycur, real *ewt)
 {
     (void)ctx;
     for (int i = 0; i < n; i++) {
-        double r = (itol >= 3) ? rtol[i] : rtol[0];
-        double a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
+        real r = (itol >= 3) ? rtol[i] : rtol[0];
+        real a = (itol == 2 || itol == 4) ? atol[i] : atol[0];
         ewt[i] = r * fabs(ycur[i]) + a;
-        if (i == 0 && fabs(ycur[i]) < 0.5) ewt[i] = ewt[i] - 1.0;
+        if (i == 0 && fabs(ycur[i]) < DVO_R(0.5)) ewt[i] = ewt[i] - DVO_R(1.0);
     }
 }
-static double vdpm_dvnorm(void *ctx, int n, const double *v, const double *w)
+static real vdpm_dvnorm(void *ctx, int n, const real *v, const real *w)
 {
-    double vm = 0.0;
+    real vm = DVO_R(0.0);
     (void)ctx;
     for (int i = 0; i < n; i++) {
-        double p = fabs(v[i] * w[i]);
+        real p = fabs(v[i] * w[i]);
         if (p > vm) vm = p;
     }
     return vm;
@@ -109,48 +109,48 @@ static double vdpm_dvnorm(void *ctx, int n, const double *v, const double *w)
 /* ---------------------------------------------------- banded advection --- */
 /* par = (alph1, alph2), reference 1, 1; ng = 5 (dvdemo.f90:236-238) */
 #define NG 5
-static void adv_f(void *ctx, int neq, double t, const double *y, double *ydot)
+static void adv_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
-    const double *p = (const double *)ctx;
+    const real *p = (const real *)ctx;
     (void)neq; (void)t;
     for (int j = 1; j <= NG; j++)
         for (int i = 1; i <= NG; i++) {
             int k = i + (j - 1) * NG;
-            double d = -2.0 * y[k - 1];
+            real d = -DVO_R(2.0) * y[k - 1];
             if (i != 1) d = d + y[k - 2] * p[0];
             if (j != 1) d = d + y[k - NG - 1] * p[1];
             ydot[k - 1] = d;
         }
 }
-static void adv_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd,
+static void adv_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *pd,
                     int nrowpd)
 {
-    const double *p = (const double *)ctx;
+    const real *p = (const real *)ctx;
     (void)t; (void)y;
     int mband = ml + mu + 1, mu1 = mu + 1, mu2 = mu + 2;
     for (int j = 1; j <= neq; j++) {
-        PD(mu1, j) = -2.0;
+        PD(mu1, j) = -DVO_R(2.0);
         PD(mu2, j) = p[0];
         PD(mband, j) = p[1];
     }
-    for (int j = NG; j <= neq; j += NG) PD(mu2, j) = 0.0;
+    for (int j = NG; j <= neq; j += NG) PD(mu2, j) = DVO_R(0.0);
 }
 
 /* ------------------------------------------- synthetic 32-species network - */
 /* par = 64 rate constants.  ydot_i = sum over the species' entry list, in
  * reaction order, of sign * rate_r (same order as the device functor). */
-static void mech_f(void *ctx, int neq, double t, const double *y, double *ydot)
+static void mech_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
-    const double *k = (const double *)ctx;
-    double rate[BVODE_MECH_NR];
+    const real *k = (const real *)ctx;
+    real rate[BVODE_MECH_NR];
     (void)neq; (void)t;
     for (int r = 0; r < BVODE_MECH_NR; r++) {
-        double q = k[r] * y[bvode_mech_ra[r]];
+        real q = k[r] * y[bvode_mech_ra[r]];
         if (bvode_mech_rb[r] >= 0) q = q * y[bvode_mech_rb[r]];
         rate[r] = q;
     }
     for (int i = 0; i < BVODE_MECH_NS; i++) {
-        double d = 0.0;
+        real d = DVO_R(0.0);
         for (int e = 0; e < BVODE_MECH_MAXE; e++) {
             int r = bvode_mech_ent_r[i][e];
             if (r < 0) break;
@@ -177,15 +177,15 @@ int dvo_problem_info(int problem, int *neq, int *npar)
 }
 
 /* analytic Jacobian of the mechanism, entry by entry in the order of mech_f (pd pre-zeroed, M:2947) */
-static void mech_jac(void *ctx, int neq, double t, double *y, int ml, int mu, double *pd, int nrowpd)
+static void mech_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *pd, int nrowpd)
 {
-    const double *k = (const double *)ctx;
+    const real *k = (const real *)ctx;
     (void)neq; (void)t; (void)ml; (void)mu;
     for (int i = 0; i < BVODE_MECH_NS; i++) {
         for (int e = 0; e < BVODE_MECH_MAXE; e++) {
             int r = bvode_mech_ent_r[i][e];
             if (r < 0) break;
-            double s = bvode_mech_ent_s[i][e];
+            real s = bvode_mech_ent_s[i][e];
             int a = bvode_mech_ra[r], b = bvode_mech_rb[r];
             if (b < 0) {
                 pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * k[r];
@@ -199,14 +199,14 @@ static void mech_jac(void *ctx, int neq, double t, double *y, int ml, int mu, do
 
 /* ------------------------------------------- reaction-diffusion chain, n = 48 --- */
 /* builder-defined (dvode_b200/csrc/problems.cuh, Diffusion48): par = (D, k) */
-static void dif_f(void *ctx, int neq, double t, const double *y, double *ydot)
+static void dif_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
-    const double *p = (const double *)ctx;
+    const real *p = (const real *)ctx;
     (void)neq; (void)t;
     for (int i = 0; i < 48; i++) {
-        double l = (i > 0) ? y[i - 1] : 0.0, r = (i + 1 < 48) ? y[i + 1] : 0.0;
-        double s = (i < 4) ? 1.0 : 0.0;
-        ydot[i] = p[0] * ((l - 2.0 * y[i]) + r) - p[1] * y[i] * y[i] + s;
+        real l = (i > 0) ? y[i - 1] : DVO_R(0.0), r = (i + 1 < 48) ? y[i + 1] : DVO_R(0.0);
+        real s = (i < 4) ? DVO_R(1.0) : DVO_R(0.0);
+        ydot[i] = p[0] * ((l - DVO_R(2.0) * y[i]) + r) - p[1] * y[i] * y[i] + s;
     }
 }
 
@@ -225,7 +225,7 @@ static int problem_fns(int problem, dvo_f_fn *f, dvo_jac_fn *jac)
     }
 }
 
-void dvo_problem_f(int problem, const double *par, double t, const double *y, double *ydot)
+void dvo_problem_f(int problem, const real *par, real t, const real *y, real *ydot)
 {
     dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
     if (problem_fns(problem, &f, &jac) || dvo_problem_info(problem, &neq, &npar)) return;
@@ -257,10 +257,10 @@ int dvo_last_threads(void) { return g_last_threads; }
 /* One independent solver instance per system, replaying the reference's call
  * sequence (example.f90:56-66): for each tout, one dvode call with itask as
  * configured; istate carried between calls; stop at the first negative istate. */
-int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, const double *y0,
-                    double t0, int nout, const double *touts, const double *rtol,
-                    const double *atol, double *y_out, double *t_out, int *istate_out,
-                    double *rstats, int *istats, int nthreads)
+int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const real *params, const real *y0,
+                    real t0, int nout, const real *touts, const real *rtol,
+                    const real *atol, real *y_out, real *t_out, int *istate_out,
+                    real *rstats, int *istats, int nthreads)
 {
     dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
     if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
@@ -278,23 +278,23 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
 #pragma omp single nowait
         g_last_threads = omp_get_num_threads();
 #endif
-        double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
+        real *rwork = (real *)malloc(sizeof(real) * (size_t)lrw);
         int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
-        double *y = (double *)malloc(sizeof(double) * (size_t)neq);
-        double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
+        real *y = (real *)malloc(sizeof(real) * (size_t)neq);
+        real *par = (real *)malloc(sizeof(real) * (size_t)(npar > 0 ? npar : 1));
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 16)
 #endif
         for (int s = 0; s < nsys; s++) {
             dvo_solver sol;
-            memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
+            memcpy(par, params + (size_t)s * npar, sizeof(real) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
             if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             if (cfg->problem == 7) dvo_set_user_norms(&sol, vdpd_dewset, NULL);
             sol.pow_mode = cfg->pow_mode;
-            memset(rwork, 0, sizeof(double) * (size_t)lrw);
+            memset(rwork, 0, sizeof(real) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
-            memcpy(y, y0 + (size_t)s * neq, sizeof(double) * (size_t)neq);
+            memcpy(y, y0 + (size_t)s * neq, sizeof(real) * (size_t)neq);
             iwork[0] = cfg->ml;
             iwork[1] = cfg->mu;
             if (cfg->iopt) {
@@ -302,17 +302,17 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
                 iwork[4] = cfg->maxord; iwork[5] = cfg->mxstep; iwork[6] = cfg->mxhnil;
             }
             rwork[0] = cfg->tcrit;
-            double t = t0;
+            real t = t0;
             int istate = 1;
             for (int io = 0; io < nout; io++) {
                 if (istate >= 0)
                     dvo_solve(&sol, neq, y, &t, touts[io], cfg->itol, rtol, atol, cfg->itask,
                               &istate, cfg->iopt, rwork, lrw, iwork, liw, cfg->mf);
                 size_t o = (size_t)s * nout + io;
-                memcpy(y_out + o * neq, y, sizeof(double) * (size_t)neq);
+                memcpy(y_out + o * neq, y, sizeof(real) * (size_t)neq);
                 if (t_out) t_out[o] = t;
                 if (istate_out) istate_out[o] = istate;
-                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(double) * 4);
+                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(real) * 4);
                 if (istats) memcpy(istats + o * 12, iwork + 10, sizeof(int) * 12);
             }
             if (istate < 0) {
@@ -331,10 +331,10 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const double *params, co
  * cfg2 / rtol2 / atol2 (same mf; the reference's "parameter change" restart, M:1382-1390) and
  * ordinary continuation calls for the remaining outputs. */
 int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int nsplit, int nsys,
-                     const double *params, const double *y0, double t0, int nout,
-                     const double *touts, const double *rtol, const double *atol,
-                     const double *rtol2, const double *atol2, double *y_out, double *t_out,
-                     int *istate_out, double *rstats, int *istats, int nthreads)
+                     const real *params, const real *y0, real t0, int nout,
+                     const real *touts, const real *rtol, const real *atol,
+                     const real *rtol2, const real *atol2, real *y_out, real *t_out,
+                     int *istate_out, real *rstats, int *istats, int nthreads)
 {
     dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
     if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
@@ -358,28 +358,28 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
 #pragma omp single nowait
         g_last_threads = omp_get_num_threads();
 #endif
-        double *rwork = (double *)malloc(sizeof(double) * (size_t)lrw);
+        real *rwork = (real *)malloc(sizeof(real) * (size_t)lrw);
         int *iwork = (int *)malloc(sizeof(int) * (size_t)liw);
-        double *y = (double *)malloc(sizeof(double) * (size_t)neq);
-        double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
+        real *y = (real *)malloc(sizeof(real) * (size_t)neq);
+        real *par = (real *)malloc(sizeof(real) * (size_t)(npar > 0 ? npar : 1));
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 16)
 #endif
         for (int s = 0; s < nsys; s++) {
             dvo_solver sol;
-            memcpy(par, params + (size_t)s * npar, sizeof(double) * (size_t)npar);
+            memcpy(par, params + (size_t)s * npar, sizeof(real) * (size_t)npar);
             dvo_initialize(&sol, f, jac, par);
             if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
             if (cfg->problem == 7) dvo_set_user_norms(&sol, vdpd_dewset, NULL);
             sol.pow_mode = cfg->pow_mode;
-            memset(rwork, 0, sizeof(double) * (size_t)lrw);
+            memset(rwork, 0, sizeof(real) * (size_t)lrw);
             memset(iwork, 0, sizeof(int) * (size_t)liw);
-            memcpy(y, y0 + (size_t)s * neq, sizeof(double) * (size_t)neq);
-            double t = t0;
+            memcpy(y, y0 + (size_t)s * neq, sizeof(real) * (size_t)neq);
+            real t = t0;
             int istate = 1;
             for (int io = 0; io < nout; io++) {
                 const dvo_batch_cfg *c = (io < nsplit) ? cfg : cfg2;
-                const double *rt = (io < nsplit) ? rtol : rtol2, *at = (io < nsplit) ? atol : atol2;
+                const real *rt = (io < nsplit) ? rtol : rtol2, *at = (io < nsplit) ? atol : atol2;
                 if (io == nsplit && istate == 2) istate = 3;
                 iwork[0] = c->ml;
                 iwork[1] = c->mu;
@@ -390,10 +390,10 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
                     dvo_solve(&sol, neq, y, &t, touts[io], c->itol, rt, at, c->itask, &istate,
                               c->iopt, rwork, lrw, iwork, liw, c->mf);
                 size_t o = (size_t)s * nout + io;
-                memcpy(y_out + o * neq, y, sizeof(double) * (size_t)neq);
+                memcpy(y_out + o * neq, y, sizeof(real) * (size_t)neq);
                 if (t_out) t_out[o] = t;
                 if (istate_out) istate_out[o] = istate;
-                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(double) * 4);
+                if (rstats) memcpy(rstats + o * 4, rwork + 10, sizeof(real) * 4);
                 if (istats) memcpy(istats + o * 12, iwork + 10, sizeof(int) * 12);
             }
             if (istate < 0) {
@@ -411,22 +411,22 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
 /* dvindy at user points after the last solve of a single system: convenience
  * used by the dense-output parity tests.  Integrates system 0 of the batch to
  * tout with one call, then evaluates derivative order k at each tq. */
-int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const double *y0, double t0,
-                     double tout, const double *rtol, const double *atol, int k, int nq,
-                     const double *tqs, double *dky_out, int *iflag_out, double *tcur,
-                     double *hu)
+int dvo_single_dense(const dvo_batch_cfg *cfg, const real *par_in, const real *y0, real t0,
+                     real tout, const real *rtol, const real *atol, int k, int nq,
+                     const real *tqs, real *dky_out, int *iflag_out, real *tcur,
+                     real *hu)
 {
     dvo_f_fn f; dvo_jac_fn jac; int neq, npar;
     if (problem_fns(cfg->problem, &f, &jac) || dvo_problem_info(cfg->problem, &neq, &npar))
         return -1;
     int lrw, liw;
     dvo_work_sizes(neq, cfg->mf, cfg->ml, cfg->mu, cfg->iopt ? cfg->maxord : 0, &lrw, &liw);
-    double *rwork = (double *)calloc((size_t)lrw, sizeof(double));
+    real *rwork = (real *)calloc((size_t)lrw, sizeof(real));
     int *iwork = (int *)calloc((size_t)liw, sizeof(int));
-    double *y = (double *)malloc(sizeof(double) * (size_t)neq);
-    double *par = (double *)malloc(sizeof(double) * (size_t)(npar > 0 ? npar : 1));
-    memcpy(par, par_in, sizeof(double) * (size_t)npar);
-    memcpy(y, y0, sizeof(double) * (size_t)neq);
+    real *y = (real *)malloc(sizeof(real) * (size_t)neq);
+    real *par = (real *)malloc(sizeof(real) * (size_t)(npar > 0 ? npar : 1));
+    memcpy(par, par_in, sizeof(real) * (size_t)npar);
+    memcpy(y, y0, sizeof(real) * (size_t)neq);
     dvo_solver sol;
     dvo_initialize(&sol, f, jac, par);
     if (cfg->problem == 4 || cfg->problem == 5) dvo_set_user_norms(&sol, vdpm_dewset, vdpm_dvnorm);
@@ -437,7 +437,7 @@ int dvo_single_dense(const dvo_batch_cfg *cfg, const double *par_in, const doubl
         rwork[4] = cfg->h0; rwork[5] = cfg->hmax; rwork[6] = cfg->hmin;
         iwork[4] = cfg->maxord; iwork[5] = cfg->mxstep; iwork[6] = cfg->mxhnil;
     }
-    double t = t0;
+    real t = t0;
     int istate = 1;
     dvo_solve(&sol, neq, y, &t, tout, cfg->itol, rtol, atol, cfg->itask, &istate, cfg->iopt,
               rwork, lrw, iwork, liw, cfg->mf);

@@ -25,13 +25,22 @@ class BatchCfg(C.Structure):
                 ("pow_mode", C.c_int)]
 
 
+class BatchCfg32(C.Structure):  # liboracle32.so: every `real` a float
+    _fields_ = [("problem", C.c_int), ("mf", C.c_int), ("itol", C.c_int), ("itask", C.c_int),
+                ("iopt", C.c_int), ("ml", C.c_int), ("mu", C.c_int), ("maxord", C.c_int),
+                ("mxstep", C.c_int), ("mxhnil", C.c_int), ("h0", C.c_float),
+                ("hmax", C.c_float), ("hmin", C.c_float), ("tcrit", C.c_float),
+                ("pow_mode", C.c_int)]
+
+
 def build(force=False):
     srcs = [os.path.join(_ROOT, "oracle", f) for f in
             ("dvode_oracle.c", "problems.c", "dvode_oracle.h", "oracle_batch.h", "Makefile")]
     srcs.append(os.path.join(_ROOT, "include", "bvode_mech32.h"))
     fma = _SO.replace("liboracle.so", "liboracle_fma.so")
-    stale = force or not os.path.exists(_SO) or not os.path.exists(fma) or any(
-        os.path.getmtime(s) > min(os.path.getmtime(_SO), os.path.getmtime(fma))
+    r32 = _SO.replace("liboracle.so", "liboracle32.so")
+    stale = force or not all(os.path.exists(x) for x in (_SO, fma, r32)) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(_SO), os.path.getmtime(fma), os.path.getmtime(r32))
         for s in srcs if os.path.exists(s))
     if stale:
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle")],
@@ -47,8 +56,17 @@ def lib(variant=""):
     if variant not in _libs:
         path = build()
         if variant:
-            path = path.replace("liboracle.so", "liboracle_%s.so" % variant)
+            path = path.replace("liboracle.so", "liboracle32.so" if variant == "32" else "liboracle_%s.so" % variant)
         _lib = C.CDLL(path)
+        if variant == "32":  # only the batch driver is used on the REAL32 twin
+            fp = C.POINTER(C.c_float)
+            ip = C.POINTER(C.c_int)
+            _lib.dvo_batch_solve.restype = C.c_int
+            _lib.dvo_batch_solve.argtypes = [C.POINTER(BatchCfg32), C.c_int, fp, fp, C.c_float,
+                                             C.c_int, fp, fp, fp, fp, fp, ip, fp, ip, C.c_int]
+            _lib.dvo_problem_info.argtypes = [C.c_int, ip, ip]
+            _libs[variant] = _lib
+            return _lib
         dp = C.POINTER(C.c_double)
         ip = C.POINTER(C.c_int)
         _lib.dvo_batch_solve.restype = C.c_int
@@ -112,25 +130,29 @@ def work_sizes(neq, mf, ml=0, mu=0, maxord=0):
 def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1, iopt=0,
                 ml=0, mu=0, maxord=0, mxstep=0, mxhnil=0, h0=0.0, hmax=0.0, hmin=0.0,
                 tcrit=0.0, pow_mode=0, nthreads=0, variant=""):
-    """Run the oracle on a batch.  Returns dict(y[nsys,nout,neq], t, istate, rstats, istats)."""
+    """Run the oracle on a batch.  Returns dict(y[nsys,nout,neq], t, istate, rstats, istats).
+    variant "32": the REAL32 twin (float arrays in and out)."""
+    ft = np.float32 if variant == "32" else np.float64
+    fptr = (lambda a: a.ctypes.data_as(C.POINTER(C.c_float))) if variant == "32" else _dp
     neq, npar = problem_info(problem)
-    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(npar, 1)))
+    params = np.ascontiguousarray(np.asarray(params, dtype=ft).reshape(-1, max(npar, 1)))
     nsys = params.shape[0]
-    y0 = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=np.float64), (nsys, neq)))
-    touts = np.ascontiguousarray(np.asarray(touts, dtype=np.float64).reshape(-1))
+    y0 = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=ft), (nsys, neq)))
+    touts = np.ascontiguousarray(np.asarray(touts, dtype=ft).reshape(-1))
     nout = touts.size
-    rtol = np.ascontiguousarray(np.atleast_1d(np.asarray(rtol, dtype=np.float64)))
-    atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=np.float64)))
-    cfg = BatchCfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, mxhnil,
-                   h0, hmax, hmin, tcrit, pow_mode)
-    y = np.zeros((nsys, nout, neq))
-    t = np.zeros((nsys, nout))
+    rtol = np.ascontiguousarray(np.atleast_1d(np.asarray(rtol, dtype=ft)))
+    atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=ft)))
+    Cfg = BatchCfg32 if variant == "32" else BatchCfg
+    cfg = Cfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, mxhnil,
+              h0, hmax, hmin, tcrit, pow_mode)
+    y = np.zeros((nsys, nout, neq), dtype=ft)
+    t = np.zeros((nsys, nout), dtype=ft)
     ist = np.zeros((nsys, nout), dtype=np.int32)
-    rst = np.zeros((nsys, nout, 4))
+    rst = np.zeros((nsys, nout, 4), dtype=ft)
     ista = np.zeros((nsys, nout, 12), dtype=np.int32)
-    nfail = lib(variant).dvo_batch_solve(C.byref(cfg), nsys, _dp(params), _dp(y0), float(t0), nout,
-                                  _dp(touts), _dp(rtol), _dp(atol), _dp(y), _dp(t), _ip(ist),
-                                  _dp(rst), _ip(ista), nthreads)
+    nfail = lib(variant).dvo_batch_solve(C.byref(cfg), nsys, fptr(params), fptr(y0), float(t0), nout,
+                                         fptr(touts), fptr(rtol), fptr(atol), fptr(y), fptr(t), _ip(ist),
+                                         fptr(rst), _ip(ista), nthreads)
     assert nfail >= 0
     return {"y": y, "t": t, "istate": ist, "rstats": rst, "istats": ista, "nfail": nfail}
 

@@ -553,15 +553,18 @@ def test_dvsrco_restores_everything_a_fresh_handle_needs():
 
 
 # ------------------------------------------------------------------ istate = 3 across method families ----
-@pytest.mark.parametrize("problem,mf,mf2", [("vdp", 10, 21), ("vdp", 21, 10), ("vdp", 12, 22), ("vdp", 22, 12),
-                                            ("vdp", 10, 20), ("vdp", 23, 13), ("advection", 14, 24),
-                                            ("advection", 25, 10), ("mech32", 12, 22), ("mech32", 22, 12),
-                                            ("diffusion48", 12, 22)])
+@pytest.mark.parametrize("problem,mf,mf2", [("vdp", 10, 21), ("vdp", 21, 10), ("vdp", 12, -22), ("vdp", 22, -12),
+                                            ("vdp", 10, 20), ("vdp", 23, 13), ("advection", 14, -24),
+                                            ("advection", 25, 10), ("mech32", 12, -22), ("mech32", 22, -12),
+                                            ("diffusion48", 12, -22)])
 def test_istate3_changes_the_method_family(problem, mf, mf2):
     """meth is re-read from mf on every call (M:1149-1153): an istate = 3 call may switch Adams <-> BDF.  The
     Nordsieck array carries over (13 <-> 6 columns); from Adams at order > 5 the order is cut to the BDF maximum
     through M:1385 / 2044-2079 -- orders 4..8 occur at the switch of the Van der Pol batch, so both the
-    `dvjust(-1)` case (order 6) and the plain truncation (order >= 7) are on the path.  Strict build, bit for bit."""
+    `dvjust(-1)` case (order 6) and the plain truncation (order >= 7) are on the path.  Strict build, bit for bit.
+    (Where the old flag kept a Jacobian copy the new one is taken with jsv = -1: with jsv = +1 the reference's dvjac
+    may reuse a "saved copy" from work-array words that hold the old Nordsieck columns after lwm moved, M:1246-1268 --
+    not mirrored here, the Jacobian is re-evaluated at the restart instead; DESIGN.md.)"""
     B = _B()
     nsys = 48
     kw, iw = {}, None
