@@ -79,6 +79,8 @@ struct ThreadPolicy {
         BV_DEV volatile real &wj(int k) const { return b[(kOffWj + k) * kTPB]; }
         BV_DEV volatile int &si(int k) const { return bi[k * kTPB]; }
         BV_DEV volatile int &ipvt(int i) const { return bi[(SI_COUNT + i) * kTPB]; }
+        BV_DEV void si_add(int k, int d) const { bi[k * kTPB] = bi[k * kTPB] + d; }  // this thread's own slot
+        BV_DEV void sync() const {}
         BV_DEV void bind(real *smem, int tid) {
             b = smem + tid;
             bi = reinterpret_cast<int *>(smem + (size_t)kHotDoubles * kTPB) + tid;
@@ -104,6 +106,8 @@ struct ThreadPolicy {
         BV_DEV real &sd(int k) { return sdv[k]; }
         BV_DEV int &si(int k) { return siv[k]; }
         BV_DEV int &ipvt(int i) { return ipv[i]; }
+        BV_DEV void si_add(int k, int d) { siv[k] = siv[k] + d; }
+        BV_DEV void sync() const {}
         BV_DEV void bind(real *, int) {}
     };
     static constexpr size_t kSmemBytes = 0;
@@ -351,7 +355,7 @@ struct ThreadPolicy {
         ierpj = 0;
         const real hrl1 = c.h * c.rl1;
         // M:3004-3028: diagonal Jacobian approximation from one extra f evaluation
-        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        e.hot.si_add(SI_NJE, 1);
         c.jcur = 1;
         e.hot.p(1, 0) = hrl1;  // wm(2)
         const real r = c.rl1 * BV_R(0.1);
@@ -359,7 +363,7 @@ struct ThreadPolicy {
         for (int i = 0; i < N; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
         real w[N];
         f(c.tn, e.y, w, e.par);
-        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
+        e.hot.si_add(SI_NFE, 1);
 #pragma unroll
         for (int i = 0; i < N; i++) {
             if (ierpj == 0) {
@@ -395,7 +399,7 @@ struct ThreadPolicy {
         }
         real P[N][N];
         if (jok == -1) {
-            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si_add(SI_NJE, 1);
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if (MITER == 1) {
@@ -421,7 +425,7 @@ struct ThreadPolicy {
                     for (int i = 0; i < N; i++) P[i][j] = (e.acor[i] - e.savf[i]) * fac;
                     e.y[j] = yj;
                 }
-                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
+                e.hot.si_add(SI_NFE, N);
             }
             if (SAVEJ) {
 #pragma unroll
@@ -445,7 +449,7 @@ struct ThreadPolicy {
             for (int j = 0; j < N; j++) P[i][j] = con * P[i][j];
 #pragma unroll
         for (int i = 0; i < N; i++) P[i][i] = P[i][i] + BV_R(1.0);
-        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
+        e.hot.si_add(SI_NLU, 1);
         int ipvt[N];
         const int ier = dgefa(P, ipvt);
         if (ier != 0) ierpj = 1;

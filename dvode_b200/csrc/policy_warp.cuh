@@ -21,6 +21,17 @@ namespace BVODE_NS {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// dginv (the dense inversion) keeps a 64-register row: out of line it gets its own register allocation and the
+// step loop around it is not squeezed by it (experiments: -DBVODE_DGINV_NOINLINE=0/1)
+#ifndef BVODE_DGINV_NOINLINE
+#define BVODE_DGINV_NOINLINE 0
+#endif
+#if BVODE_DGINV_NOINLINE
+#define BVODE_DGINV_INLINE __device__ __noinline__
+#else
+#define BVODE_DGINV_INLINE BV_DEV
+#endif
+
 // optional members of a warp problem (bvode_ref_problem.cuh: callbacks in the reference's whole-vector form)
 template <class P, class = void>
 struct HasJacDenseFull { static constexpr bool value = false; };
@@ -126,6 +137,19 @@ struct WarpCommon {
         BV_DEV volatile real &tq(int i) const { return b[kOffTq + (i - 1)]; }
         BV_DEV volatile real &sd(int k) const { return b[kOffSd + k]; }
         BV_DEV volatile int &si(int k) const { return reinterpret_cast<volatile int *>(b + kHotD)[k]; }
+        // The control state is ONE copy per warp that all 32 lanes read and write with the same values.  That is
+        // only sound while no lane can read a slot after another lane has already written its next value: a
+        // read-modify-write separates its read from its write by a warp barrier, and the engine calls sync()
+        // where one phase's reads meet the next phase's writes (independent thread scheduling gives no lockstep
+        // guarantee after a lane-dependent branch).
+        BV_DEV void si_add(int k, int d) const {
+            volatile int *p = reinterpret_cast<volatile int *>(b + kHotD) + k;
+            const int v = *p;
+            __syncwarp();
+            *p = v + d;
+            __syncwarp();
+        }
+        BV_DEV void sync() const { __syncwarp(); }
         BV_DEV void bind(real *base, int) {
             b = base;
         }
@@ -527,7 +551,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // cond(P)*uround; the batch statistics stay inside the reference's +-2 % (tests).  Every lane works in
     // every elimination step, so the inversion costs about the instructions of the factorisation it
     // replaces (N^3 lane-fmas at full occupancy against N^3/3 at a third of it).
-    BV_DEV static int dginv(Lin &lin) {
+    BVODE_DGINV_INLINE static int dginv(Lin &lin) {
         // The lane's row lives in REGISTERS for the whole inversion, rotated by one entry per step so that
         // "column k" is always r[0] and every register index is static inside a run-time loop over k:
         // step k reads r[0] (the pivot candidate), lane l (the pivot row) scales its row and publishes it to
@@ -712,7 +736,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         }
         __syncwarp();
         if (jok == -1) {
-            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si_add(SI_NJE, 1);
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if constexpr (MITER == 1) {
@@ -739,7 +763,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
                     e.y[0] = ysave;
                 }
-                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
+                e.hot.si_add(SI_NFE, N);
             }
             if (SAVEJ && ln < N) {
 #pragma unroll 4
@@ -759,7 +783,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             for (int j = 0; j < N; j++) row[j] = con * row[j];
             row[ln] = row[ln] + BV_R(1.0);
         }
-        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
+        e.hot.si_add(SI_NLU, 1);
         const int ier = factor(l);
         if (ier != 0) ierpj = 1;
     }
@@ -834,14 +858,14 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
         Lin &l = e.lin;
         ierpj = 0;
         const real hrl1 = c.h * c.rl1;
-        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        e.hot.si_add(SI_NJE, 1);
         c.jcur = 1;
         l.phrl1 = hrl1;
         const real r = c.rl1 * BV_R(0.1);
         e.y[0] = e.y[0] + r * (c.h * e.savf[0] - e.hot.yh(1, 0));
         real w[1];
         Base::f(c.tn, e.y, w, e.par);
-        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
+        e.hot.si_add(SI_NFE, 1);
         const real r0 = c.h * e.savf[0] - e.hot.yh(1, 0);
         const real di = BV_R(0.1) * r0 - c.h * (w[0] - e.savf[0]);
         const bool big = (lane() < N) && (fabs(r0) >= kUround / e.ewt[0]);
@@ -1090,7 +1114,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         }
         __syncwarp();
         if (jok == -1) {
-            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si_add(SI_NJE, 1);
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             if constexpr (MITER == 4) {
@@ -1130,7 +1154,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                         if (i >= i1 && i <= i2) ABD(i - jj + mband, jj) = diff * fac;
                     }
                 }
-                e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + mba;
+                e.hot.si_add(SI_NFE, mba);
             }
             __syncwarp();
             if (SAVEJ) {  // dacopy(mband, n, wm(ml3), meband, wm(locjs), mband)
@@ -1152,7 +1176,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             ABD(mband, ln + 1) = ABD(mband, ln + 1) + BV_R(1.0);
         }
         __syncwarp();
-        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
+        e.hot.si_add(SI_NLU, 1);
         const int ier = dgbfa(l);
         if (ier != 0) ierpj = 1;
     }

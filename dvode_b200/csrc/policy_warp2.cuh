@@ -46,6 +46,19 @@ struct WarpCommon2 {
         BV_DEV volatile real &tq(int i) const { return b[kOffTq + (i - 1)]; }
         BV_DEV volatile real &sd(int k) const { return b[kOffSd + k]; }
         BV_DEV volatile int &si(int k) const { return reinterpret_cast<volatile int *>(b + kHotD)[k]; }
+        // The control state is ONE copy per warp that all 32 lanes read and write with the same values.  That is
+        // only sound while no lane can read a slot after another lane has already written its next value: a
+        // read-modify-write separates its read from its write by a warp barrier, and the engine calls sync()
+        // where one phase's reads meet the next phase's writes (independent thread scheduling gives no lockstep
+        // guarantee after a lane-dependent branch).
+        BV_DEV void si_add(int k, int d) const {
+            volatile int *p = reinterpret_cast<volatile int *>(b + kHotD) + k;
+            const int v = *p;
+            __syncwarp();
+            *p = v + d;
+            __syncwarp();
+        }
+        BV_DEV void sync() const { __syncwarp(); }
         BV_DEV void bind(real *base, int) {
             b = base;
         }
@@ -401,7 +414,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
         __syncwarp();
         const real con = -hrl1;
         if (jok == -1) {
-            e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+            e.hot.si_add(SI_NJE, 1);
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             // finite differences, M:2959-2976: column j for all rows at once
@@ -427,7 +440,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
                 e.y[0] = ysave[0];
                 e.y[1] = ysave[1];
             }
-            e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + N;
+            e.hot.si_add(SI_NFE, N);
         } else {
             c.jcur = 0;
             if (SAVEJ) {
@@ -441,7 +454,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
         // P = I - h*rl1*J (M:2984-2992)
         sts_d(rowa[0] + ln * 8, lds_d(rowa[0] + ln * 8) + BV_R(1.0));
         if (ok[1]) sts_d(rowa[1] + (ln + 32) * 8, lds_d(rowa[1] + (ln + 32) * 8) + BV_R(1.0));
-        e.hot.si(SI_NLU) = e.hot.si(SI_NLU) + 1;
+        e.hot.si_add(SI_NLU, 1);
         const int ier = dgefa(l);
         if (ier != 0) ierpj = 1;
     }
@@ -520,7 +533,7 @@ struct WarpPlain2Policy : WarpCommon2<PROB, METH_> {
         Lin &l = e.lin;
         ierpj = 0;
         const real hrl1 = c.h * c.rl1;
-        e.hot.si(SI_NJE) = e.hot.si(SI_NJE) + 1;
+        e.hot.si_add(SI_NJE, 1);
         c.jcur = 1;
         l.phrl1 = hrl1;
         const real r = c.rl1 * BV_R(0.1);
@@ -528,7 +541,7 @@ struct WarpPlain2Policy : WarpCommon2<PROB, METH_> {
         for (int i = 0; i < 2; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
         real w[2];
         Base::f(c.tn, e.y, w, e.par);
-        e.hot.si(SI_NFE) = e.hot.si(SI_NFE) + 1;
+        e.hot.si_add(SI_NFE, 1);
         real r0[2], di[2];
         bool big[2];
 #pragma unroll

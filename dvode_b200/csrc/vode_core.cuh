@@ -559,11 +559,14 @@ struct Engine {
     //   down: yh(:,j) -= yh(:,L)*el(j), j = 3..nq   (nothing if nq == 2, M:2581); the freed
     //         column L is zeroed to keep the zero-column invariant.
     //   up:   yh(:,L+1) = t1*acsav ; yh(:,j) += el(j)*yh(:,L+1), j = 3..nq+1
+    // WIDE (the istate = 3 restart only): an order above this family's maximum and the column overlays of the
+    // reference's work array are possible; the step loop's own order changes never need them.
+    template <bool WIDE = false>
     BV_DEV void order_change(bool up) {
         real el[kLmax + 1];
         real t1 = BV_R(0.0);
         if constexpr (METH == 2) {
-            if (!up && c.nq > kMaxOrdBdf) dvjust_coeffs_bdf_down_wide(c, hot, el);  // order 6, from an Adams history
+            if (WIDE && !up && c.nq > kMaxOrdBdf) dvjust_coeffs_bdf_down_wide(c, hot, el);  // order 6, from an Adams history
             else t1 = dvjust_coeffs_bdf(c, hot, up, el);
         } else {
             // Adams (M:2656-2692): raising the order only zeroes the new column, which the
@@ -580,14 +583,14 @@ struct Engine {
 #pragma unroll
             for (int i = 0; i < NLOC; i++) col[i] = (METH == 2) ? t1 * POL::acsav_get(*this, i) : BV_R(0.0);
         } else {
-            if (GENERAL_STASH && c.L > kLmax) {  // right after an Adams -> BDF restart at order 6 (see restart_istate3)
+            if (WIDE && GENERAL_STASH && c.L > kLmax) {  // right after an Adams -> BDF restart at order 6 (see restart_istate3)
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) col[i] = savf[i];
                 if (xcol_mode == 1) col[0] = sqrt(kUround);
             } else {
                 get_col(c.L, col);
             }
-            if (xcol_mode == 2) {  // miter = 0 at an istate = 3 restart: the column is overlaid by ewt
+            if (WIDE && xcol_mode == 2) {  // miter = 0 at an istate = 3 restart: the column is overlaid by ewt
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) col[i] = ewt[i];
             }
@@ -769,7 +772,7 @@ struct Engine {
         if (h0 == BV_R(0.0)) {
             int niter;
             const int ier = dvhin(t, tout, h0, niter);
-            hot.si(SI_NFE) = hot.si(SI_NFE) + niter;
+            hot.si_add(SI_NFE, niter);
             if (ier != 0) return IST_ILLEGAL;  // message 22
         }
         const real rh = fabs(h0) * o.hmax_inv;
@@ -808,7 +811,7 @@ struct Engine {
 #pragma unroll
             for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
             POL::f(c.tn, y, savf, par);
-            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
+            hot.si_add(SI_NFE, 1);
             if constexpr (MITER != 0) {
                 if (c.ipup > 0) {
                     int ierpj;
@@ -839,7 +842,7 @@ struct Engine {
                         for (int i = 0; i < NLOC; i++)
                             y[i] = rl1h * savf[i] - (c.rl1 * hot.yh(1, i) + acor[i]);
                         iersl = POL::solve(*this, y);
-                        hot.si(SI_NNI) = hot.si(SI_NNI) + 1;
+                        hot.si_add(SI_NNI, 1);
                     }
                     if (iersl > 0) {  // dvsol failed (diagonal approximation, M:2806)
                         iterate = false;
@@ -897,7 +900,7 @@ struct Engine {
                         } else {
                             delp = del;
                             POL::f(c.tn, y, savf, par);
-                            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
+                            hot.si_add(SI_NFE, 1);
                         }
                     }
                 }
@@ -1105,6 +1108,7 @@ struct Engine {
         if constexpr (!REFILL) handover();
 #pragma unroll 1
         while (REFILL ? (__any_sync(0xffffffffu, alive) != 0) : (alive && istate == 0)) {
+            hot.sync();  // (warp policies) last attempt's reads of the shared control state before this one's writes
             if constexpr (REFILL) {
                 // Finished lanes are replaced in groups: a lane waits until kRefillGroup lanes of
                 // its warp are idle (or nothing else runs), so that the hand-over code runs for
@@ -1179,7 +1183,7 @@ struct Engine {
                         if (too_much) istate = (hot.si(SI_NST) == 0) ? IST_ILLEGAL : IST_TOLSF;
                     }
                     if (istate == 0) {
-                        if ((c.tn + c.h) == c.tn) hot.si(SI_NHNIL) = hot.si(SI_NHNIL) + 1;
+                        if ((c.tn + c.h) == c.tn) hot.si_add(SI_NHNIL, 1);
                         // ---- dvstep prologue, M:2024-2128
                         c.kflag = 0;
                         told = c.tn;
@@ -1217,7 +1221,7 @@ struct Engine {
                                         if (maxord == c.nq - 1 && c.newq == c.nq + 1)
                                             c.eta = BV_R(1.0) / (rpow(hot.sd(SD_ETAQM1), BV_R(0.5) * recip_int(c.L - 1)) + addon);
 #endif
-                                        if (maxord == c.nq - 1) order_change(false);  // dvjust(-1)
+                                        if (maxord == c.nq - 1) order_change<true>(false);  // dvjust(-1)
                                         c.eta = dmin2(c.eta, BV_R(1.0));
                                         c.nq = maxord;
                                         c.L = lmax;
@@ -1270,6 +1274,7 @@ struct Engine {
                 c.tn = c.tn + c.h;
                 predict();
                 dvset<METH>(c, hot);
+                hot.sync();
                 c.rl1 = qrcp(hot.el(2));
                 c.rc = c.rc * qdiv(c.rl1, c.prl1);
                 c.prl1 = c.rl1;
@@ -1315,7 +1320,7 @@ struct Engine {
                 if (conv && !accept) {
                     // ---- error test failed (M:2177-2237)
                     c.kflag = c.kflag - 1;
-                    hot.si(SI_NETF) = hot.si(SI_NETF) + 1;
+                    hot.si_add(SI_NETF, 1);
                     nflag = -2;
                     if (fabs(c.h) <= o.hmin * onepsm) {
                         c.kflag = -1;
@@ -1342,7 +1347,7 @@ struct Engine {
                             c.hscal = c.h;
                             hot.tau(1) = c.h;
                             POL::f(c.tn, y, savf, par);
-                            hot.si(SI_NFE) = hot.si(SI_NFE) + 1;
+                            hot.si_add(SI_NFE, 1);
 #pragma unroll
                             for (int i = 0; i < NLOC; i++) hot.yh(1, i) = c.h * savf[i];
                             c.nqwait = 10;
@@ -1355,7 +1360,7 @@ struct Engine {
                 } else if (!conv) {
                     // ---- corrector failed to converge (M:2338-2367)
                     ncf = ncf + 1;
-                    hot.si(SI_NCFN) = hot.si(SI_NCFN) + 1;
+                    hot.si_add(SI_NCFN, 1);
                     hot.sd(SD_ETAMAX) = BV_R(1.0);
                     if (fabs(c.h) <= o.hmin * onepsm || ncf == mxncf) {
                         c.kflag = -2;
@@ -1369,14 +1374,21 @@ struct Engine {
                 } else {
                     // ---- successful step (M:2245-2330, 2370-2375)
                     c.kflag = 0;
-                    hot.si(SI_NST) = hot.si(SI_NST) + 1;
+                    hot.si_add(SI_NST, 1);
                     hot.sd(SD_HU) = c.h;
                     hot.si(SI_NQU) = c.nq;
+                    {   // tau(i) = tau(i-1), i = L..2 (M:2249-2253): all reads, then all writes
+                        real tv[kLmax + 1];
 #pragma unroll
-                    for (int i = kLmax; i >= 2; i--) {
-                        if (i <= c.nq + 1) hot.tau(i) = hot.tau(i - 1);
+                        for (int i = 1; i < kLmax; i++) tv[i] = hot.tau(i);
+                        hot.sync();
+#pragma unroll
+                        for (int i = kLmax; i >= 2; i--) {
+                            if (i <= c.nq + 1) hot.tau(i) = tv[i - 1];
+                        }
+                        hot.tau(1) = c.h;
+                        hot.sync();
                     }
-                    hot.tau(1) = c.h;
 #pragma unroll
                     for (int j = 1; j <= kLmax; j++) {
                         const real elj = hot.el(j);

@@ -14,6 +14,8 @@
 !!     header slots (optional inputs read from column 1, optional outputs written per system);
 !!     the reference's rwork(21:) lives in GPU memory owned by the handle.
 !!   * f / jac are __device__ functors compiled into the library and chosen by name.
+!!   * REAL32 (the reference's -DREAL32, dvode_kinds_module.F90:29-31): link libbvode32.so and replace c_double
+!!     by c_float throughout this file (every `bvode_real` of include/bvode.h).
 module bvode_module
    use, intrinsic :: iso_c_binding
    implicit none
@@ -23,6 +25,7 @@ module bvode_module
                                         BVODE_ECUDA = -3, BVODE_ENOMEM = -4, BVODE_EISTATE = -5
    integer(c_int), parameter, public :: BVODE_FLAG_STRICT = 1
    integer(c_int), parameter, public :: BVODE_FLAG_COMPACT = 2
+   integer(c_int), parameter, public :: BVODE_FLAG_PER_SYSTEM = 4   !! rtol / atol / optional inputs per system
 
    interface
       !> A user problem library (csrc/bvode_user_problem.cuh) loaded by the application: pass what its
@@ -114,6 +117,99 @@ module bvode_module
          integer(c_int), value :: job
          integer(c_int) :: rc
       end function
+      function bvode_dvsrco_n(handle, sav, nbytes, job) bind(C, name='bvode_dvsrco_n') result(rc)
+         import :: c_int, c_ptr, c_long_long
+         type(c_ptr), value :: handle, sav
+         integer(c_long_long), value :: nbytes        !! length of sav, checked against bvode_state_bytes()
+         integer(c_int), value :: job
+         integer(c_int) :: rc
+      end function
+      function bvode_reset(handle) bind(C, name='bvode_reset') result(rc)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int) :: rc
+      end function
+      !> ---- multi-GPU (include/bvode.h): index sharding and the final gather over NCCL ----
+      subroutine bvode_shard_range(nsys_total, rank, world, first, last) bind(C, name='bvode_shard_range')
+         import :: c_int, c_long_long
+         integer(c_long_long), value :: nsys_total
+         integer(c_int), value :: rank, world
+         integer(c_long_long), intent(out) :: first, last   !! 0-based [first, last)
+      end subroutine
+      function bvode_comm_unique_id(id) bind(C, name='bvode_comm_unique_id') result(rc)
+         import :: c_int, c_char
+         character(kind=c_char), intent(out) :: id(128)     !! rank 0 creates it; MPI_Bcast it to the others
+         integer(c_int) :: rc
+      end function
+      function bvode_comm_create(comm, id, world, rank, device) bind(C, name='bvode_comm_create') result(rc)
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), intent(out) :: comm
+         character(kind=c_char), intent(in) :: id(128)
+         integer(c_int), value :: world, rank, device
+         integer(c_int) :: rc
+      end function
+      function bvode_comm_adopt(comm, nccl_comm, world, rank, device) bind(C, name='bvode_comm_adopt') result(rc)
+         import :: c_int, c_ptr
+         type(c_ptr), intent(out) :: comm
+         type(c_ptr), value :: nccl_comm                   !! an ncclComm_t the application made itself
+         integer(c_int), value :: world, rank, device
+         integer(c_int) :: rc
+      end function
+      subroutine bvode_comm_destroy(comm) bind(C, name='bvode_comm_destroy')
+         import :: c_ptr
+         type(c_ptr), value :: comm
+      end subroutine
+      !> Host arrays on the root: y_all(neq, nsys_total), t_all, istate_all, rout_all(4, :), iout_all(12, :)
+      function bvode_gather(handle, comm, root, nsys_total, y_all, t_all, istate_all, rout_all, iout_all) &
+            bind(C, name='bvode_gather') result(rc)
+         import :: c_int, c_ptr, c_long_long
+         type(c_ptr), value :: handle, comm
+         integer(c_int), value :: root
+         integer(c_long_long), value :: nsys_total
+         type(c_ptr), value :: y_all, t_all, istate_all, rout_all, iout_all   !! c_loc(array) or c_null_ptr
+         integer(c_int) :: rc
+      end function
+      !> One process, several GPUs: arrays of nsys_total columns, the arguments of bvode_solve[_schedule]
+      function bvode_multi_create(multi, problem, nsys_total, ndev, devices, flags) bind(C, name='bvode_multi_create') result(rc)
+         import :: c_int, c_ptr, c_long_long
+         type(c_ptr), intent(out) :: multi
+         integer(c_int), value :: problem, ndev, flags
+         integer(c_long_long), value :: nsys_total
+         integer(c_int), intent(in) :: devices(*)
+         integer(c_int) :: rc
+      end function
+      subroutine bvode_multi_destroy(multi) bind(C, name='bvode_multi_destroy')
+         import :: c_ptr
+         type(c_ptr), value :: multi
+      end subroutine
+      function bvode_multi_set_params(multi, params) bind(C, name='bvode_multi_set_params') result(rc)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: multi
+         real(c_double), intent(in) :: params(*)
+         integer(c_int) :: rc
+      end function
+      function bvode_multi_solve(multi, neq, y, t, tout, tout_per_system, itol, rtol, atol, itask, &
+                                 istate, iopt, rwork, lrw, iwork, liw, mf) bind(C, name='bvode_multi_solve') result(rc)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: multi
+         integer(c_int), value :: neq, tout_per_system, itol, itask, iopt, lrw, liw, mf
+         real(c_double), intent(inout) :: y(*), t(*), rwork(*)
+         real(c_double), intent(in) :: tout(*), rtol(*), atol(*)
+         integer(c_int), intent(inout) :: istate(*), iwork(*)
+         integer(c_int) :: rc
+      end function
+      function bvode_multi_solve_schedule(multi, neq, y, t, nout, touts, itol, rtol, atol, itask, istate, &
+                                          iopt, rwork, lrw, iwork, liw, mf, y_out) &
+            bind(C, name='bvode_multi_solve_schedule') result(rc)
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: multi
+         integer(c_int), value :: neq, nout, itol, itask, iopt, lrw, liw, mf
+         real(c_double), intent(inout) :: y(*), t(*), rwork(*)
+         real(c_double), intent(in) :: touts(*), rtol(*), atol(*)
+         integer(c_int), intent(inout) :: istate(*), iwork(*)
+         real(c_double), intent(out) :: y_out(*)
+         integer(c_int) :: rc
+      end function
       !> xerrwd (dvode_module.F90:3351) as a host-side message stream
       function bvode_istate_summary(handle, counts) bind(C, name='bvode_istate_summary') result(rc)
          import :: c_int, c_ptr
@@ -132,8 +228,10 @@ module bvode_module
 
    public :: bvode_register_problem, bvode_problem_lookup, bvode_problem_info, bvode_create, bvode_destroy, &
              bvode_last_error, bvode_set_params, bvode_solve, bvode_solve_schedule, &
-             bvode_dvindy, bvode_get_stats, bvode_state_bytes, bvode_dvsrco, &
-             bvode_istate_summary, bvode_format_message
+             bvode_dvindy, bvode_get_stats, bvode_state_bytes, bvode_dvsrco, bvode_dvsrco_n, bvode_reset, &
+             bvode_istate_summary, bvode_format_message, bvode_shard_range, bvode_comm_unique_id, &
+             bvode_comm_create, bvode_comm_adopt, bvode_comm_destroy, bvode_gather, bvode_multi_create, &
+             bvode_multi_destroy, bvode_multi_set_params, bvode_multi_solve, bvode_multi_solve_schedule
 
    !> Batched counterpart of `type(dvode_t)` (dvode_module.F90:251-314).
    type, public :: bvode_t
