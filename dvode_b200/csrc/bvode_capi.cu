@@ -265,6 +265,7 @@ void bvode_destroy(bvode_solver *s) {
     if (s->h_iout) cudaFreeHost(s->h_iout);
     for (cudaEvent_t ev : s->chunk_done) cudaEventDestroy(ev);
     if (s->stream2) cudaStreamDestroy(s->stream2);
+    if (s->stream3) cudaStreamDestroy(s->stream3);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -521,7 +522,7 @@ static int run_device(bvode_solver *s, const Checked &c, int mf, real *d_y, real
             a.general = 1;
         }
         if (s->pe->mode == 0 && (s->flags & BVODE_FLAG_COMPACT) && !a.general) {
-            if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, 2 * sizeof(int)));
+            if (!s->d_next) CUDA_TRY(cudaMalloc(&s->d_next, 4 * sizeof(int)));
             CUDA_TRY(cudaMemsetAsync(s->d_next + lane, 0, sizeof(int), st));
             a.next_sys = s->d_next + lane;
         }
@@ -651,18 +652,28 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
         if (!s->h_rout) CUDA_TRY(cudaMallocHost(&s->h_rout, sizeof(real) * 4 * ns));
         if (!s->h_iout) CUDA_TRY(cudaMallocHost(&s->h_iout, sizeof(int) * 12 * ns));
     }
-    // The batch goes through in chunks on two streams: the copies of one chunk (inputs in, every
+    // The batch goes through in chunks on three streams: the copies of one chunk (inputs in, every
     // output point out) run under the kernels of its neighbours, and a chunk's kernel fills the
     // SMs the previous one's tail leaves idle.  One chunk for small batches.
-    const int kChunk = 1 << 17;
+    // (measured on 2^20 Robertson systems, e2e ms: 2^15 / 2^16 / 2^17 / 2^18 systems per chunk on 3 streams 115.1 / 115.7 /
+    // 117.3 / 123.4, on 2 streams 116.5 (2^16) / 117.9 (2^17); 2^14: 139 -- launch-bound; the kernel alone: 110.4)
+    int chunk_log2 = 16, nstreams = 3;
+    if (const char *ev = getenv("BVODE_CHUNK_LOG2")) chunk_log2 = atoi(ev);   // experiments
+    if (const char *ev = getenv("BVODE_HOST_STREAMS")) nstreams = atoi(ev);
+    if (chunk_log2 < 10) chunk_log2 = 10;
+    if (chunk_log2 > 24) chunk_log2 = 24;
+    if (nstreams < 1) nstreams = 1;
+    if (nstreams > 3) nstreams = 3;
+    const int kChunk = 1 << chunk_log2;
     const int nchunks = (nsys >= 2 * kChunk && nout <= BVODE_MAX_NOUT) ? cdiv(nsys, kChunk) : 1;
     if (nchunks > 1 && !s->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    if (nchunks > 1 && !s->stream3) CUDA_TRY(cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking));
     const real tout1 = BV_R(0.0);
     for (int ch = 0; ch < nchunks; ch++) {
         const int s0 = (int)((long long)nsys * ch / nchunks), s1 = (int)((long long)nsys * (ch + 1) / nchunks);
         const int cnt = s1 - s0;
-        const int lane = ch & 1;
-        cudaStream_t cs = lane ? s->stream2 : s->stream;
+        const int lane = ch % nstreams;
+        cudaStream_t cs = lane == 0 ? s->stream : (lane == 1 ? s->stream2 : s->stream3);
         // host -> device.  On continuation calls y and t are outputs only (M:608-618).
         CUDA_TRY(cudaMemcpyAsync(s->d_istate + s0, istate + s0, sizeof(int) * cnt, cudaMemcpyHostToDevice, cs));
         if (any_first) {
@@ -679,6 +690,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
         if (rc != BVODE_OK) {  // nothing may still be writing into the caller's buffers when we return
             cudaStreamSynchronize(s->stream);
             if (s->stream2) cudaStreamSynchronize(s->stream2);
+            if (s->stream3) cudaStreamSynchronize(s->stream3);
             return rc;
         }
         // device -> host
@@ -729,6 +741,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
         }
     }
     if (s->stream2) CUDA_TRY(cudaStreamSynchronize(s->stream2));
+    if (s->stream3) CUDA_TRY(cudaStreamSynchronize(s->stream3));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     return BVODE_OK;

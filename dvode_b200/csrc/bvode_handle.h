@@ -23,6 +23,7 @@ struct bvode_solver {
     int *d_istate = nullptr, *d_iout = nullptr, *d_iaos = nullptr;
     int *d_next = nullptr;  // hands out the systems beyond the grid (thread-per-system kernels); one per stream
     cudaStream_t stream2 = nullptr;  // second stream of the pipelined host-buffer path
+    cudaStream_t stream3 = nullptr;  // third
     real *d_yout_aos = nullptr;    // [nout][nsys][neq] staging of the output points in host layout
     size_t yout_aos_cap = 0;
     size_t aos_cap = 0, yout_cap = 0;

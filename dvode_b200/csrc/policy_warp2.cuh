@@ -178,7 +178,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
 #define BVODE_DENSE2_TPB 64
 #endif
 #ifndef BVODE_DENSE2_MINBLOCKS
-#define BVODE_DENSE2_MINBLOCKS 3
+#define BVODE_DENSE2_MINBLOCKS 4
 #endif
     static constexpr int kTPB = BVODE_DENSE2_TPB;  // 2 systems per CTA: 2 x (64 x 65 doubles) of shared memory
     static constexpr int kMinBlocks = BVODE_DENSE2_MINBLOCKS;
