@@ -197,6 +197,7 @@ class dvode_t:
         """y[nsys,neq], t[nsys], istate[nsys] (int32) are updated in place.  tout: scalar or
         array[nsys].  rwork[nsys,lrw] / iwork[nsys,liw] (or None) carry the optional
         inputs (row 0) and receive the optional outputs (every row)."""
+        self._neq_of_call(neq, istate)
         self._chk_arrays(y, t, istate, rwork, iwork, lrw, liw)
         tout = _f64(tout).reshape(-1)
         per = 1 if tout.size > 1 else 0
@@ -211,6 +212,7 @@ class dvode_t:
                        iwork, liw, mf, y_out=None):
         """The reference's `do iout = 1, nout; call solve(...); tout = ...` loop as one call.
         y_out[nout,nsys,neq] (optional) receives every output point."""
+        self._neq_of_call(neq, istate)
         self._chk_arrays(y, t, istate, rwork, iwork, lrw, liw)
         touts = _f64(touts).reshape(-1)
         rtol, atol = _f64(rtol).reshape(-1), _f64(atol).reshape(-1)
@@ -317,6 +319,12 @@ class dvode_t:
         if n < 0:
             _check(n)
         return buf.value.decode()
+
+    def _neq_of_call(self, neq, istate):
+        """An istate = 3 call may pass a smaller neq (M:1127-1135): y, y_out and dky then have that many columns."""
+        if self._h is not None and isinstance(istate, np.ndarray) and istate.size and int(neq) < self.neq and \
+                (istate == 3).all() and int(neq) >= 1:
+            self.neq = int(neq)
 
     def _chk_arrays(self, y, t, istate, rwork, iwork, lrw, liw):
         if self._h is None:

@@ -110,11 +110,12 @@ __global__ void k_aos_to_soa_range(const real *__restrict__ aos, real *__restric
     for (int i = 0; i < n; i++) soa[(size_t)i * nsys + g] = aos[g * n + i];
 }
 __global__ void k_soa_to_aos_range(const real *__restrict__ soa, real *__restrict__ aos, int nsys,
-                                   int n, int s0, int count) {
+                                   int n, int s0, int count, int nfull = 0) {
+    // nfull: rows of one [.][nsys] array on the device when the host layout carries only the first n of them
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= count) return;
     const size_t g = (size_t)s0 + s, v = blockIdx.y;
-    const real *src = soa + v * (size_t)n * nsys;
+    const real *src = soa + v * (size_t)(nfull > 0 ? nfull : n) * nsys;
     real *dst = aos + v * (size_t)n * nsys;
     for (int i = 0; i < n; i++) dst[g * n + i] = src[(size_t)i * nsys + g];
 }
@@ -300,7 +301,8 @@ struct Checked {
 };
 
 // Work-array lengths the reference would need, M:1246-1273 (reported in iwork(17:18)).
-static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, int *leniw) {
+static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, int *leniw, int nyh = 0) {
+    if (nyh <= 0) nyh = neq;  // nyh = the neq of the first call (M:1247): yh keeps its leading dimension
     const int jsv = mf >= 0 ? 1 : -1, mfa = mf < 0 ? -mf : mf, meth = mfa / 10,
               miter = mfa - 10 * meth, jco = jsv > 0 ? 1 : 0;
     int lenwm = 0;
@@ -310,7 +312,7 @@ static void work_sizes(int neq, int mf, int ml, int mu, int maxord, int *lenrw, 
     case 3: lenwm = 2 + neq; break;
     default: lenwm = 2 + (2 * ml + mu + 1) * neq + jco * (ml + mu + 1) * neq; break;
     }
-    *lenrw = 20 + neq * (maxord + 1) + lenwm + 3 * neq;
+    *lenrw = 20 + nyh * (maxord + 1) + lenwm + 3 * neq;
     *leniw = (miter == 0 || miter == 3) ? 30 : 30 + neq;
 }
 
@@ -351,8 +353,19 @@ static const char *read_optional_inputs(int meth, int itask, int iopt, const rea
 static int check_args(const bvode_solver *s, int neq, int itol, const real *rtol,
                       const real *atol, int itask, int iopt, const real *rwork0,
                       const int *iwork0, int lrw, int liw, bool have_headers, int mf,
-                      Checked *c) {
-    if (neq != s->neq) { g_err = "neq does not match the problem"; return BVODE_EINVAL; }
+                      Checked *c, bool restart3 = false) {
+    {   // neq: the problem's, or -- from an istate = 3 call on -- a smaller one (M:1127-1135; never larger again)
+        const int cur = s->nact > 0 ? s->nact : s->neq;
+        if (neq != cur && !(restart3 && neq >= 1 && neq < cur)) {
+            g_err = (neq > cur) ? "neq larger than the problem's (or than the neq of the last istate = 3 call)"
+                                : "neq may only be reduced by an istate = 3 call";
+            return BVODE_EINVAL;
+        }
+        if (neq < s->neq && s->neq > 32) {
+            g_err = "a smaller neq is not built for problems mapped two components per lane (n > 32)";
+            return BVODE_ENOTIMPL;
+        }
+    }
     if (itask < 1 || itask > 5) { g_err = "itask illegal"; return BVODE_EINVAL; }
     if ((itask == 4 || itask == 5) && !rwork0) { g_err = "itask 4/5 needs rwork(1) = tcrit"; return BVODE_EINVAL; }
     if (itol < 1 || itol > 4) { g_err = "itol illegal"; return BVODE_EINVAL; }
@@ -381,6 +394,7 @@ static int check_args(const bvode_solver *s, int neq, int itol, const real *rtol
     o.jreset = 0;
     o.stash = 0;
     o.lmaxchg = 0;
+    o.nact = 0;
     if (iopt == 1 && (!rwork0 || !iwork0)) { g_err = "iopt = 1 needs rwork and iwork"; return BVODE_EINVAL; }
     if (const char *msg = read_optional_inputs(meth, itask, iopt, rwork0, iwork0, &o)) { g_err = msg; return BVODE_EINVAL; }
     c->tol.resize(2 * (size_t)neq);
@@ -392,7 +406,8 @@ static int check_args(const bvode_solver *s, int neq, int itol, const real *rtol
         c->tol[i] = r;
         c->tol[neq + i] = a;
     }
-    work_sizes(neq, mf, ml, mu, o.maxord, &c->lenrw, &c->leniw);
+    o.nact = (neq < s->neq) ? neq : 0;
+    work_sizes(neq, mf, ml, mu, o.maxord, &c->lenrw, &c->leniw, s->neq);
     return BVODE_OK;
 }
 
@@ -561,7 +576,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
     const bool array_shrinks = mf_changed && (abs(s->mf) / 10 == 1) && (abs(mf) / 10 == 2);  // Adams -> BDF: lmax 13 -> 6
     Checked c;
     const bool have_headers = rwork && iwork;
-    int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c);
+    int rc = check_args(s, neq, itol, rtol, atol, itask, iopt, rwork, iwork, lrw, liw, have_headers, mf, &c, n3 != 0);
     if (rc != BVODE_OK) {
         if (rc == BVODE_EINVAL) for (int j = 0; j < nsys; j++) istate[j] = -3;
         return rc;
@@ -576,6 +591,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
     }
     if (!(s->flags & BVODE_FLAG_PER_SYSTEM) && n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
     if (n3 != 0 && (c.o.maxord != s->maxord || abs(s->mf) / 10 != abs(mf) / 10)) c.o.lmaxchg = 1;
+    if (n3 != 0 && c.o.nact != s->nact) c.o.jreset = 1;  // a smaller neq: the saved Jacobian had another leading dimension
     if (mf_changed) {
         // M:999-1046 at istate = 3: a new miter / jsv.  The state moves into the layout of the new
         // method flag; the Newton matrix and the saved Jacobian are rebuilt at the restart.
@@ -619,7 +635,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
     const real *d_tout_ps = tout_ps ? s->d_tout_ps : nullptr;
     real *d_yout = nullptr;
     if (y_out) {
-        const size_t need = ns * neq * nout;
+        const size_t need = ns * (size_t)s->neq * nout;  // the kernels write all neq rows of every output point
         if (need > s->yout_cap) {
             cudaFree(s->d_yout);
             s->d_yout = nullptr;
@@ -686,7 +702,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
         if (tout_ps)
             CUDA_TRY(cudaMemcpyAsync(s->d_tout_ps + s0, tout_ps + s0, sizeof(real) * cnt, cudaMemcpyHostToDevice, cs));
         rc = run_device(s, c, mf, s->d_y, s->d_t, s->d_istate, nout, touts ? touts : &tout1, d_tout_ps, d_yout, cs,
-                        itask != 1 || n3 != 0, s0, cnt, lane, false);
+                        itask != 1 || n3 != 0 || c.o.nact != 0, s0, cnt, lane, false);
         if (rc != BVODE_OK) {  // nothing may still be writing into the caller's buffers when we return
             cudaStreamSynchronize(s->stream);
             if (s->stream2) cudaStreamSynchronize(s->stream2);
@@ -710,7 +726,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
                                      cudaMemcpyDeviceToHost, cs));
         }
         if (y_out) {
-            k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), nout), TB, 0, cs>>>(d_yout, s->d_yout_aos, nsys, neq, s0, cnt);
+            k_soa_to_aos_range<<<dim3(cdiv(cnt, TB), nout), TB, 0, cs>>>(d_yout, s->d_yout_aos, nsys, neq, s0, cnt, s->neq);
             s->last_launches++;
             const size_t hs = yout_sys_stride > 0 ? (size_t)yout_sys_stride : ns;  // systems per output slab of y_out
             for (int k = 0; k < nout; k++) {
@@ -730,6 +746,7 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
     }
     s->maxord = c.o.maxord;
     s->mxstep = c.o.mxstep;
+    s->nact = c.o.nact;
     if (have_headers) {
         for (int ch = 0; ch < nchunks; ch++) {
             const size_t s0 = (size_t)((long long)nsys * ch / nchunks), s1 = (size_t)((long long)nsys * (ch + 1) / nchunks);
@@ -783,6 +800,7 @@ static int device_path_prepare(bvode_solver *s, const Checked &c, int neq, int i
 }
 
 int bvode_reset(bvode_solver *s) {
+    if (s) s->nact = 0;
     if (!s) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -821,7 +839,7 @@ int bvode_solve_schedule_device(bvode_solver *s, int neq, real *y_device, real *
     rc = device_path_prepare(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, mf, st);
     if (rc != BVODE_OK) return rc;
     rc = run_device(s, c, mf, y_device, t_device, istate_device, nout, touts, nullptr,
-                    y_out_device, st, itask != 1);
+                    y_out_device, st, itask != 1 || c.o.nact != 0);
     if (rc != BVODE_OK) return rc;
     s->maxord = c.o.maxord;
     s->mxstep = c.o.mxstep;
@@ -844,7 +862,7 @@ int bvode_solve_device(bvode_solver *s, int neq, real *y_device, real *t_device,
     rc = device_path_prepare(s, c, neq, itol, rtol, atol, itask, iopt, rwork_opts, iwork_opts, mf, (cudaStream_t)stream);
     if (rc != BVODE_OK) return rc;
     rc = run_device(s, c, mf, y_device, t_device, istate_device, 1, &tout1, tout_device, nullptr,
-                    (cudaStream_t)stream, itask != 1);
+                    (cudaStream_t)stream, itask != 1 || c.o.nact != 0);
     if (rc != BVODE_OK) return rc;
     s->maxord = c.o.maxord;
     s->mxstep = c.o.mxstep;
@@ -906,8 +924,9 @@ int bvode_dvindy(bvode_solver *s, const real *t, int t_per_system, int k, real *
     a.iflag = s->d_iaos;
     const int e = s->pe->launch_dky(s->mf, a, st);
     if (e != 0) { g_err = "dvindy kernel launch failed"; return e == -1000 ? BVODE_ENOTIMPL : BVODE_ECUDA; }
-    k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, st>>>(s->d_yout, s->d_aos, s->nsys, s->neq);
-    CUDA_TRY(cudaMemcpyAsync(dky, s->d_aos, sizeof(real) * ns * s->neq, cudaMemcpyDeviceToHost, st));
+    const int nhost = s->nact > 0 ? s->nact : s->neq;  // dky[nsys][neq of the last call]
+    k_soa_to_aos<<<cdiv(s->nsys, TB), TB, 0, st>>>(s->d_yout, s->d_aos, s->nsys, nhost);
+    CUDA_TRY(cudaMemcpyAsync(dky, s->d_aos, sizeof(real) * ns * nhost, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(iflag, s->d_iaos, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
@@ -941,7 +960,7 @@ int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job) {
     if (job == 1) {
         if (!s->d_state) { g_err = "dvsrco(job = 1) before any successful solve"; return BVODE_EINVAL; }
         if (nbytes >= 0 && (size_t)nbytes < sav_bytes(s, s->nd, s->ni)) { g_err = "dvsrco: buffer shorter than bvode_state_bytes()"; return BVODE_EINVAL; }
-        SavHeader h{kSavMagic, s->problem, s->nsys, s->mf, s->ml, s->mu, s->maxord, s->mxstep, s->neq, 0,
+        SavHeader h{kSavMagic, s->problem, s->nsys, s->mf, s->ml, s->mu, s->maxord, s->mxstep, s->neq, s->nact,
                     (unsigned long long)s->nd, (unsigned long long)s->ni};
         memcpy(p, &h, sizeof(h));
     } else {
@@ -961,6 +980,7 @@ int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job) {
         if (rc) return rc;
         s->maxord = h.maxord;
         s->mxstep = h.mxstep;
+        s->nact = h.reserved;  // neq of the last call when an istate = 3 call had reduced it
     }
     p += sizeof(SavHeader);
     const size_t ns = (size_t)s->nsys;

@@ -14,6 +14,7 @@ struct bvode_solver {
     int mf = 0, ml = 0, mu = 0;
     int maxord = 0;  // of the last call (istate = 3 may change it)
     int mxstep = 500;
+    int nact = 0;    // equations actually integrated after an istate = 3 call with a smaller neq (0 = all neq)
     size_t nd = 0, ni = 0;  // doubles / ints of persistent state for the whole batch
     real *d_state = nullptr;
     int *i_state = nullptr;

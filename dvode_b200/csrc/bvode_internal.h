@@ -21,6 +21,8 @@ struct BvOpts {
     int lmaxchg;                 // istate = 3 with another lmax = maxord + 1 (maxord or the method family changed): the
                                  // reference parks the acor copy in yh(:, lmax) (M:2259, 2298), so a pending order
                                  // increase now finds the Nordsieck column yh(:, lmax_new) there instead
+    int nact;                    // equations actually integrated (0 = all neq): an istate = 3 call may pass a smaller
+                                 // neq (M:1127-1135); the dropped components stay frozen in the state
     int stash;                   // istate = 3 from Adams to BDF: the Nordsieck array shrinks from 13 to 6 columns; the
                                  // old column maxord + 2, which the order reduction of M:1385, 2044-2079 reads, travels
                                  // in the acor slot of the converted state

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
     Engine<POL> e;
     e.hot.bind(smem_thread, threadIdx.x);
     e.o = a.o;
+    if constexpr (GENERAL) e.nact = (a.o.nact > 0 && a.o.nact < N) ? a.o.nact : N;
 #pragma unroll
     for (int i = 0; i < N; i++) {  // N <= 8: by-value kernel parameters; larger: the [neq] arrays in HBM
         e.tol.rv[i] = (N <= 8) ? a.rtolv[i < 8 ? i : 0] : a.rtol[i];
@@ -205,6 +206,15 @@ __global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kerne
         if (e.hot.si(SI_INIT) != 1) {  // M:1102-1106
             a.istate[sys] = IST_ILLEGAL;
             return 0;
+        }
+        if constexpr (GENERAL) {
+            if (e.nact != N) {
+                // neq was reduced (M:1127-1135): the dropped components are what the caller's y array holds for
+                // them -- the last output values -- and stay that: f of the kept equations may read them
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    if (i >= e.nact) e.hot.yh(0, i) = a.y[(size_t)i * ns + sys];
+            }
         }
         if (GENERAL && ist == 3) e.restart_istate3(true);  // M:1383-1390
         return 2;
@@ -385,6 +395,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
 
     Engine<POL> e;
     e.o = a.o;
+    if constexpr (GENERAL) e.nact = (a.o.nact > 0 && a.o.nact < N) ? a.o.nact : N;
     constexpr int NL = POL::NLOC;  // components per lane: component ln + 32*i in slot i
     if constexpr (NL == 1) {
         e.tol.r = (ln < N) ? a.rtol[ln] : BV_R(0.0);
@@ -456,6 +467,13 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
         if (e.hot.si(SI_INIT) != 1) {
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
             return 0;
+        }
+        if constexpr (GENERAL) {
+            if (e.nact != N) {  // neq was reduced: see the thread kernel
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                    if (ln + 32 * i >= e.nact && ln + 32 * i < N) e.hot.yh(0, i) = a.y[(size_t)(ln + 32 * i) * nsys + sys];
+            }
         }
         if (GENERAL && ist == 3) e.restart_istate3(ln == 0);
         return 2;

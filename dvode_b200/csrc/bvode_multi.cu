@@ -213,7 +213,7 @@ int bvode_gather_device(bvode_solver *s, bvode_comm *c, int root, long long nsys
     if (!s->last_y || !s->last_t || !s->last_istate) { bvode_set_error("bvode_gather before any solve"); return BVODE_EINVAL; }
     CUDA_TRY(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;  // as in bvode_solve_*_device: 0 = the legacy default stream
-    const int n = s->nsys, neq = s->neq;
+    const int n = s->nsys, neq = s->nact > 0 ? s->nact : s->neq;  // host layout: the neq of the last call
     const bool is_root = (c->rank == root);
     const int TB = 256, grid = (n + TB - 1) / TB;
     if (is_root) {
@@ -275,7 +275,7 @@ int bvode_gather(bvode_solver *s, bvode_comm *c, int root, long long nsys_total,
     if (!s || !c || root < 0 || root >= c->world) return BVODE_EINVAL;
     CUDA_TRY(cudaSetDevice(s->device));
     const bool is_root = (c->rank == root);
-    const int neq = s->neq;
+    const int neq = s->nact > 0 ? s->nact : s->neq;
     char *scratch = nullptr;
     const PackLayout L = pack_layout((size_t)nsys_total, neq);
     real *dy = nullptr, *dt = nullptr, *dr = nullptr;

@@ -156,7 +156,10 @@ struct ThreadPolicy {
     }
     // dvnorm_default, M:3295-3311: sequential sum in index order, like the reference
     // (or the problem's own norm, M:468-503).
-    BV_DEV static real norm(const real (&v)[N], const real (&w)[N]) {
+    BV_DEV static int comp(int i) { return i; }  // the equation that vector element i of this thread holds
+    // (nact: equations in the system, M:3295 `n` -- N unless an istate = 3 call reduced neq; the dropped
+    // components carry zeros, so only the divisor changes)
+    BV_DEV static real norm(const real (&v)[N], const real (&w)[N], int nact = N) {
         if constexpr (HasUserNorm<PROB>::value) return PROB::norm(v, w);
         real sum = BV_R(0.0);
 #pragma unroll
@@ -165,14 +168,14 @@ struct ThreadPolicy {
             sum = sum + p * p;
         }
 #if BVODE_STRICT
-        return sqrt(sum / (real)N);
+        return sqrt(sum / (real)nact);
 #else
-        return sqrt(sum * (BV_R(1.0) / (real)N));
+        return sqrt((nact == N) ? sum * (BV_R(1.0) / (real)N) : sum / (real)nact);
 #endif
     }
 #if !BVODE_STRICT
     // mean square (norm^2) -- the fast build tests squares and keeps sqrt off the main path
-    BV_DEV static real msq(const real (&v)[N], const real (&w)[N]) {
+    BV_DEV static real msq(const real (&v)[N], const real (&w)[N], int nact = N) {
         if constexpr (HasUserNorm<PROB>::value) {  // a user norm is only known as a norm
             const real nv = PROB::norm(v, w);
             return nv * nv;
@@ -183,7 +186,7 @@ struct ThreadPolicy {
             const real p = v[i] * w[i];
             sum = sum + p * p;
         }
-        return sum * (BV_R(1.0) / (real)N);
+        return (nact == N) ? sum * (BV_R(1.0) / (real)N) : sum / (real)nact;
     }
 #endif
     BV_DEV static bool any_le_zero(const real (&v)[N]) {
@@ -362,11 +365,11 @@ struct ThreadPolicy {
 #pragma unroll
         for (int i = 0; i < N; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
         real w[N];
-        f(c.tn, e.y, w, e.par);
+        e.feval(c.tn, e.y, w);
         e.hot.si_add(SI_NFE, 1);
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            if (ierpj == 0) {
+            if (ierpj == 0 && i < e.nact) {
                 const real r0 = c.h * e.savf[i] - e.hot.yh(1, i);
                 const real di = BV_R(0.1) * r0 - c.h * (w[i] - e.savf[i]);
                 real wi = BV_R(1.0);
@@ -408,24 +411,36 @@ struct ThreadPolicy {
 #pragma unroll
                     for (int j = 0; j < N; j++) P[i][j] = BV_R(0.0);  // M:2947-2949
                 PROB::jac(c.tn, e.y, P, e.par);
+                if (e.nact != N) {  // the Jacobian of the first nact equations in their own unknowns
+#pragma unroll
+                    for (int i = 0; i < N; i++)
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+                            if (i >= e.nact || j >= e.nact) P[i][j] = BV_R(0.0);
+                }
             } else {
                 // finite differences, M:2959-2976 (ftem = acor)
-                real fac = norm(e.savf, e.ewt);
-                real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)N * fac;
+                real fac = norm(e.savf, e.ewt, e.nact);
+                real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)e.nact * fac;
                 if (r0 == BV_R(0.0)) r0 = BV_R(1.0);
                 const real srur = sqrt(kUround);  // wm(1), M:1326
 #pragma unroll
                 for (int j = 0; j < N; j++) {
-                    const real yj = e.y[j];
-                    const real r = dmax2(srur * fabs(yj), qdiv(r0, e.ewt[j]));
-                    e.y[j] = e.y[j] + r;
-                    fac = qrcp(r);
-                    f(c.tn, e.y, e.acor, e.par);
+                    if (j < e.nact) {
+                        const real yj = e.y[j];
+                        const real r = dmax2(srur * fabs(yj), qdiv(r0, e.ewt[j]));
+                        e.y[j] = e.y[j] + r;
+                        fac = qrcp(r);
+                        e.feval(c.tn, e.y, e.acor);
 #pragma unroll
-                    for (int i = 0; i < N; i++) P[i][j] = (e.acor[i] - e.savf[i]) * fac;
-                    e.y[j] = yj;
+                        for (int i = 0; i < N; i++) P[i][j] = (e.acor[i] - e.savf[i]) * fac;
+                        e.y[j] = yj;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; i++) P[i][j] = BV_R(0.0);
+                    }
                 }
-                e.hot.si_add(SI_NFE, N);
+                e.hot.si_add(SI_NFE, e.nact);
             }
             if (SAVEJ) {
 #pragma unroll

@@ -189,7 +189,8 @@ struct WarpCommon {
         return PROB::norm_final(acc);
     }
     // dvnorm_default, M:3295-3311.  Lanes >= N carry v = 0.
-    BV_DEV static real norm(const real (&v)[1], const real (&w)[1]) {
+    BV_DEV static int comp(int) { return lane(); }  // the equation this lane holds
+    BV_DEV static real norm(const real (&v)[1], const real (&w)[1], int nact = N) {  // nact: see ThreadPolicy::norm
         if constexpr (HasLaneNorm<PROB>::value) return user_norm(v[0], w[0]);
         const real p = v[0] * w[0];
         const real p2 = p * p;
@@ -197,16 +198,16 @@ struct WarpCommon {
         real sum = BV_R(0.0);
 #pragma unroll
         for (int i = 0; i < N; i++) sum = sum + shfl_d(p2, i);
-        return sqrt(sum / (real)N);
+        return sqrt(sum / (real)nact);
 #else
         real sum = (lane() < N) ? p2 : BV_R(0.0);
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
-        return sqrt(sum * (BV_R(1.0) / (real)N));
+        return sqrt((nact == N) ? sum * (BV_R(1.0) / (real)N) : sum / (real)nact);
 #endif
     }
 #if !BVODE_STRICT
-    BV_DEV static real msq(const real (&v)[1], const real (&w)[1]) {
+    BV_DEV static real msq(const real (&v)[1], const real (&w)[1], int nact = N) {
         if constexpr (HasLaneNorm<PROB>::value) {  // a user norm is only known as a norm
             const real nv = user_norm(v[0], w[0]);
             return nv * nv;
@@ -215,7 +216,7 @@ struct WarpCommon {
         real sum = (lane() < N) ? p * p : BV_R(0.0);
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) sum = sum + shfl_xor_d(sum, m);
-        return sum * (BV_R(1.0) / (real)N);
+        return (nact == N) ? sum * (BV_R(1.0) / (real)N) : sum / (real)nact;
     }
 #endif
     BV_DEV static bool any_le_zero(const real (&v)[1]) {
@@ -274,9 +275,9 @@ struct WarpCommon {
         return idx;
     }
     // FD increment of component `lane`, M:2966 / M:3065: r = max(srur*|y|, r0/ewt)
-    BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[1], const real (&ewt)[1]) {
-        const real fac = norm(savf, ewt);
-        real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)N * fac;
+    BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[1], const real (&ewt)[1], int nact = N) {
+        const real fac = norm(savf, ewt, nact);
+        real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)nact * fac;
         if (r0 == BV_R(0.0)) r0 = BV_R(1.0);
         return r0;
     }
@@ -748,22 +749,34 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     PROB::jac_dense_full(c.tn, e.y[0], l.p, LDP, e.par, ln);
                 else
                     PROB::jac_row(c.tn, e.y[0], row, e.par, ln);  // every lane calls (it may shuffle); lanes >= N must not write
+                if (e.nact != N) {  // neq was reduced: the Jacobian of the first nact equations in their own unknowns
+                    __syncwarp();
+                    if (ln < N) {
+#pragma unroll 1
+                        for (int j = 0; j < N; j++)
+                            if (ln >= e.nact || j >= e.nact) row[j] = BV_R(0.0);
+                    }
+                }
             } else {
                 // finite differences, M:2959-2976: column j for all rows at once
-                const real r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const real r0 = Base::fd_r0(c, e.savf, e.ewt, e.nact);
                 const real srur = sqrt(kUround);
                 const real rmine = dmax2(srur * fabs(e.y[0]), qdiv(r0, e.ewt[0]));
                 const real ysave = e.y[0];
 #pragma unroll 1
                 for (int j = 0; j < N; j++) {
-                    const real r = shfl_d(rmine, j);
-                    if (ln == j) e.y[0] = ysave + r;
-                    const real fac = qrcp(r);
-                    Base::f(c.tn, e.y, e.acor, e.par);
-                    if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
-                    e.y[0] = ysave;
+                    if (j < e.nact) {  // (warp-uniform)
+                        const real r = shfl_d(rmine, j);
+                        if (ln == j) e.y[0] = ysave + r;
+                        const real fac = qrcp(r);
+                        e.feval(c.tn, e.y, e.acor);
+                        if (ln < N) row[j] = (e.acor[0] - e.savf[0]) * fac;
+                        e.y[0] = ysave;
+                    } else if (ln < N) {
+                        row[j] = BV_R(0.0);
+                    }
                 }
-                e.hot.si_add(SI_NFE, N);
+                e.hot.si_add(SI_NFE, e.nact);
             }
             if (SAVEJ && ln < N) {
 #pragma unroll 4
@@ -864,7 +877,7 @@ struct WarpPlainPolicy : WarpCommon<PROB, METH_> {
         const real r = c.rl1 * BV_R(0.1);
         e.y[0] = e.y[0] + r * (c.h * e.savf[0] - e.hot.yh(1, 0));
         real w[1];
-        Base::f(c.tn, e.y, w, e.par);
+        e.feval(c.tn, e.y, w);
         e.hot.si_add(SI_NFE, 1);
         const real r0 = c.h * e.savf[0] - e.hot.yh(1, 0);
         const real di = BV_R(0.1) * r0 - c.h * (w[0] - e.savf[0]);
@@ -1129,17 +1142,17 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                     PROB::jac_band_col(c.tn, e.y[0], &ABD(ml + 1, ln + 1), ml, mu, e.par, ln);
             } else {
                 // banded finite differences, M:3056-3081
-                const int mba = (mband < n) ? mband : n;
-                const real r0 = Base::fd_r0(c, e.savf, e.ewt);
+                const int mba = (mband < e.nact) ? mband : e.nact;
+                const real r0 = Base::fd_r0(c, e.savf, e.ewt, e.nact);
                 const real srur = sqrt(kUround);
                 const real ysave = e.y[0];
                 // yh(:,1) is what the reference restores y from (M:3070); identical to ysave
                 const real rmine = dmax2(srur * fabs(ysave), qdiv(r0, e.ewt[0]));
 #pragma unroll 1
                 for (int j = 1; j <= mba; j++) {
-                    const bool mine = (ln < n) && (((ln + 1 - j) % mband) == 0) && (ln + 1 >= j);
+                    const bool mine = (ln < e.nact) && (((ln + 1 - j) % mband) == 0) && (ln + 1 >= j);
                     if (mine) e.y[0] = ysave + rmine;
-                    Base::f(c.tn, e.y, e.acor, e.par);
+                    e.feval(c.tn, e.y, e.acor);
                     e.y[0] = ysave;
                     // column jj = j, j+mband, ...: rows i1..i2, stored at abd(i - jj + mband, jj)
                     const real diff = e.acor[0] - e.savf[0];  // row ln+1
@@ -1157,6 +1170,12 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                 e.hot.si_add(SI_NFE, mba);
             }
             __syncwarp();
+            if (e.nact != N) {  // neq was reduced: nothing of the dropped rows / columns (abd(i, j) holds a(i + j - mband, j), LP:230-260)
+                if (ln < n)
+                    for (int i = ml + 1; i <= meband; i++)
+                        if (ln + 1 > e.nact || i + (ln + 1) - mband > e.nact) ABD(i, ln + 1) = BV_R(0.0);
+                __syncwarp();
+            }
             if (SAVEJ) {  // dacopy(mband, n, wm(ml3), meband, wm(locjs), mband)
                 if (ln < n)
                     for (int i = 1; i <= mband; i++) l.wjs[ln * mband + (i - 1)] = ABD(ml + i, ln + 1);

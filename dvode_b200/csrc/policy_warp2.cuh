@@ -95,7 +95,8 @@ struct WarpCommon2 {
         return sum;
 #endif
     }
-    BV_DEV static real norm(const real (&v)[2], const real (&w)[2]) {
+    BV_DEV static int comp(int i) { return lane() + 32 * i; }
+    BV_DEV static real norm(const real (&v)[2], const real (&w)[2], int = N) {  // (a smaller neq is refused for this mapping)
 #if BVODE_STRICT
         return sqrt(sumsq(v, w) / (real)N);
 #else
@@ -103,7 +104,7 @@ struct WarpCommon2 {
 #endif
     }
 #if !BVODE_STRICT
-    BV_DEV static real msq(const real (&v)[2], const real (&w)[2]) { return sumsq(v, w) * (BV_R(1.0) / (real)N); }
+    BV_DEV static real msq(const real (&v)[2], const real (&w)[2], int = N) { return sumsq(v, w) * (BV_R(1.0) / (real)N); }
 #endif
     BV_DEV static bool any_le_zero(const real (&v)[2]) {
         return __any_sync(kFull, (v[0] <= BV_R(0.0)) || (valid(1) && v[1] <= BV_R(0.0))) != 0;

@@ -430,12 +430,28 @@ struct Engine {
     typename POL::Tol tol;
     typename POL::Lin lin;
     Opts o;
+    // Equations actually integrated: N, or fewer after an istate = 3 call with a smaller neq (M:1127-1135; the
+    // full-driver kernels only).  Components >= nact are frozen: f is masked to zero for them, their history is
+    // cleared at the restart, they carry unit weight and zero error, and the norms divide by nact.
+    int nact = N;
+    BV_DEV bool active(int i) const { return POL::comp(i) < nact; }
+    BV_DEV void feval(real t, const real (&yy)[NLOC], real (&out)[NLOC]) {  // the user's f for the first nact equations
+        POL::f(t, yy, out, par);
+        if (nact != N) {
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) out[i] = active(i) ? out[i] : BV_R(0.0);
+        }
+    }
 
     // ---- small vector helpers --------------------------------------------------
     BV_DEV void dewset_invert(bool &bad) {  // M:3238-3273 then M:1351-1360 / 1516-1523
         real e[NLOC];
 #pragma unroll
         for (int i = 0; i < NLOC; i++) e[i] = POL::ewt_of(i, hot.yh(0, i), tol.rtol(i), tol.atol(i));
+        if (nact != N) {
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) e[i] = active(i) ? e[i] : BV_R(1.0);
+        }
         bad = POL::any_le_zero(e);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) ewt[i] = qrcp(e[i]);
@@ -445,15 +461,15 @@ struct Engine {
     BV_DEV real msq_y0() {
         real y0v[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
-        return POL::msq(y0v, ewt);
+        for (int i = 0; i < NLOC; i++) y0v[i] = active(i) ? hot.yh(0, i) : BV_R(0.0);
+        return POL::msq(y0v, ewt, nact);
     }
 #endif
     BV_DEV real norm_y0() {  // dvnorm(yh(:,1), ewt), M:1525
         real y0v[NLOC];
 #pragma unroll
-        for (int i = 0; i < NLOC; i++) y0v[i] = hot.yh(0, i);
-        return POL::norm(y0v, ewt);
+        for (int i = 0; i < NLOC; i++) y0v[i] = active(i) ? hot.yh(0, i) : BV_R(0.0);
+        return POL::norm(y0v, ewt, nact);
     }
 
     BV_DEV void predict() {  // M:2148-2154 at full order (zero-column invariant)
@@ -516,6 +532,17 @@ struct Engine {
     BV_DEV void restart_istate3(bool first_comp) {
         c.jstart = -1;
         xcol_mode = 0;
+        if (nact != N) {  // neq was reduced (M:1127-1135, 2040-2049): the dropped equations take no further part
+#pragma unroll
+            for (int j = 1; j < kLmax; j++) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) hot.yh(j, i) = active(i) ? hot.yh(j, i) : BV_R(0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < NLOC; i++) {
+                if (!active(i)) { acor[i] = BV_R(0.0); POL::acsav_set(*this, i, BV_R(0.0)); }
+            }
+        }
         if (c.nq > o.maxord) {
             // What dvjust(-1) will find in yh(:, maxord + 2) (case maxord = nq - 1, M:2060-2068) is decided by the
             // reference's work-array layout: the segments after yh start at lwm = lyh + (maxord+1)*nyh, i.e. ON that
@@ -696,10 +723,10 @@ struct Engine {
                 const real t1 = t0 + h;
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + h * hot.yh(1, i);
-                POL::f(t1, y, acor, par);
+                feval(t1, y, acor);
 #pragma unroll
                 for (int i = 0; i < NLOC; i++) acor[i] = (acor[i] - hot.yh(1, i)) / h;
-                const real yddnrm = POL::norm(acor, ewt);
+                const real yddnrm = POL::norm(acor, ewt, nact);
                 if (yddnrm * hub * hub > BV_R(2.0)) hnew = sqrt(BV_R(2.0) / yddnrm);
                 else hnew = sqrt(hg * hub);
                 iter = iter + 1;
@@ -751,7 +778,7 @@ struct Engine {
 #pragma unroll
         for (int i = 0; i < NLOC; i++) { POL::acsav_set(*this, i, BV_R(0.0)); acor[i] = BV_R(0.0); savf[i] = BV_R(0.0); }
         POL::lin_init(*this);
-        POL::f(t, y, savf, par);
+        feval(t, y, savf);
 #pragma unroll
         for (int i = 0; i < NLOC; i++) hot.yh(1, i) = savf[i];
         hot.si(SI_NFE) = 1;
@@ -810,7 +837,7 @@ struct Engine {
             bool converged = false, singular = false;
 #pragma unroll
             for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i);
-            POL::f(c.tn, y, savf, par);
+            feval(c.tn, y, savf);
             hot.si_add(SI_NFE, 1);
             if constexpr (MITER != 0) {
                 if (c.ipup > 0) {
@@ -854,11 +881,11 @@ struct Engine {
                             for (int i = 0; i < NLOC; i++) y[i] = cscale * y[i];
                         }
 #if BVODE_STRICT
-                        del = POL::norm(y, ewt);
+                        del = POL::norm(y, ewt, nact);
 #else
                         // fast build: `del` and `delp` hold the MEAN SQUARE (norm^2); the tests
                         // of M:2842-2855 are applied to squares, sqrt only for the rate estimate
-                        del = POL::msq(y, ewt);
+                        del = POL::msq(y, ewt, nact);
 #endif
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) acor[i] = acor[i] + y[i];
@@ -871,9 +898,9 @@ struct Engine {
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) y[i] = savf[i] - acor[i];
 #if BVODE_STRICT
-                        del = POL::norm(y, ewt);
+                        del = POL::norm(y, ewt, nact);
 #else
-                        del = POL::msq(y, ewt);
+                        del = POL::msq(y, ewt, nact);
 #endif
 #pragma unroll
                         for (int i = 0; i < NLOC; i++) y[i] = hot.yh(0, i) + savf[i];
@@ -899,7 +926,7 @@ struct Engine {
                             iterate = false;
                         } else {
                             delp = del;
-                            POL::f(c.tn, y, savf, par);
+                            feval(c.tn, y, savf);
                             hot.si_add(SI_NFE, 1);
                         }
                     }
@@ -909,9 +936,9 @@ struct Engine {
                 c.jcur = 0;
                 c.icf = 0;
 #if BVODE_STRICT
-                c.acnrm = (m == 0) ? del : POL::norm(acor, ewt);
+                c.acnrm = (m == 0) ? del : POL::norm(acor, ewt, nact);
 #else
-                c.acnrm = (m == 0) ? del : POL::msq(acor, ewt);  // squared, see above
+                c.acnrm = (m == 0) ? del : POL::msq(acor, ewt, nact);  // squared, see above
 #endif
                 result = 0;
             } else if (MITER != 0 && !singular && c.jcur != 1) {
@@ -1209,7 +1236,7 @@ struct Engine {
                                     if (c.newq > maxord) {
                                         const real flotl = (real)lmax;
                                         if (maxord < c.nq - 1 || (maxord == c.nq - 1 && c.newq == c.nq)) {
-                                            const real ddn = POL::norm(savf, ewt) / hot.tq(1);
+                                            const real ddn = POL::norm(savf, ewt, nact) / hot.tq(1);
                                             c.eta = BV_R(1.0) / (rpow(bias1 * ddn, BV_R(1.0) / flotl) + addon);
                                         }
 #if BVODE_STRICT
@@ -1346,7 +1373,7 @@ struct Engine {
                             c.h = c.h * c.eta;
                             c.hscal = c.h;
                             hot.tau(1) = c.h;
-                            POL::f(c.tn, y, savf, par);
+                            feval(c.tn, y, savf);
                             hot.si_add(SI_NFE, 1);
 #pragma unroll
                             for (int i = 0; i < NLOC; i++) hot.yh(1, i) = c.h * savf[i];
@@ -1419,11 +1446,11 @@ struct Engine {
                                 real top[NLOC];
                                 get_col(c.L, top);
 #if BVODE_STRICT
-                                ddn = qdiv(POL::norm(top, ewt), hot.tq(1));
+                                ddn = qdiv(POL::norm(top, ewt, nact), hot.tq(1));
 #else
                                 {
                                     const real r1 = qrcp(hot.tq(1));
-                                    ddn = POL::msq(top, ewt) * (r1 * r1);  // ddn^2
+                                    ddn = POL::msq(top, ewt, nact) * (r1 * r1);  // ddn^2
                                 }
 #endif
                             }
@@ -1434,11 +1461,11 @@ struct Engine {
                                 for (int i = 0; i < NLOC; i++)
                                     savf[i] = acor[i] - cnquot * POL::acsav_get(*this, i);
 #if BVODE_STRICT
-                                dup = qdiv(POL::norm(savf, ewt), hot.tq(3));
+                                dup = qdiv(POL::norm(savf, ewt, nact), hot.tq(3));
 #else
                                 {
                                     const real r3 = qrcp(hot.tq(3));
-                                    dup = POL::msq(savf, ewt) * (r3 * r3);  // dup^2
+                                    dup = POL::msq(savf, ewt, nact) * (r3 * r3);  // dup^2
                                 }
 #endif
                             }

@@ -30,6 +30,9 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const real *params, cons
                     const real *atol, real *y_out, real *t_out, int *istate_out,
                     real *rstats, int *istats, int nthreads);
 
+/* neq of the calls from the istate = 3 call on in dvo_batch_solve2 (0 = unchanged; M:1127-1135) */
+void dvo_set_neq2(int neq2);
+
 int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int nsplit, int nsys,
                      const real *params, const real *y0, real t0, int nout,
                      const real *touts, const real *rtol, const real *atol,

@@ -112,10 +112,11 @@ static real vdpm_dvnorm(void *ctx, int n, const real *v, const real *w)
 static void adv_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
     const real *p = (const real *)ctx;
-    (void)neq; (void)t;
+    (void)t;
     for (int j = 1; j <= NG; j++)
         for (int i = 1; i <= NG; i++) {
             int k = i + (j - 1) * NG;
+            if (k > neq) continue;  /* (a call with a reduced neq, M:1127-1135: ydot has neq entries) */
             real d = -DVO_R(2.0) * y[k - 1];
             if (i != 1) d = d + y[k - 2] * p[0];
             if (j != 1) d = d + y[k - NG - 1] * p[1];
@@ -143,13 +144,13 @@ static void mech_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
     const real *k = (const real *)ctx;
     real rate[BVODE_MECH_NR];
-    (void)neq; (void)t;
+    (void)t;
     for (int r = 0; r < BVODE_MECH_NR; r++) {
         real q = k[r] * y[bvode_mech_ra[r]];
         if (bvode_mech_rb[r] >= 0) q = q * y[bvode_mech_rb[r]];
         rate[r] = q;
     }
-    for (int i = 0; i < BVODE_MECH_NS; i++) {
+    for (int i = 0; i < BVODE_MECH_NS && i < neq; i++) {  /* (neq may have been reduced: ydot has neq entries) */
         real d = DVO_R(0.0);
         for (int e = 0; e < BVODE_MECH_MAXE; e++) {
             int r = bvode_mech_ent_r[i][e];
@@ -180,18 +181,18 @@ int dvo_problem_info(int problem, int *neq, int *npar)
 static void mech_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *pd, int nrowpd)
 {
     const real *k = (const real *)ctx;
-    (void)neq; (void)t; (void)ml; (void)mu;
-    for (int i = 0; i < BVODE_MECH_NS; i++) {
+    (void)t; (void)ml; (void)mu;
+    for (int i = 0; i < BVODE_MECH_NS && i < neq; i++) {  /* (neq may have been reduced: pd is neq x neq) */
         for (int e = 0; e < BVODE_MECH_MAXE; e++) {
             int r = bvode_mech_ent_r[i][e];
             if (r < 0) break;
             real s = bvode_mech_ent_s[i][e];
             int a = bvode_mech_ra[r], b = bvode_mech_rb[r];
             if (b < 0) {
-                pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * k[r];
+                if (a < neq) pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * k[r];
             } else {
-                pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * (k[r] * y[b]);
-                pd[i + b * nrowpd] = pd[i + b * nrowpd] + s * (k[r] * y[a]);
+                if (a < neq) pd[i + a * nrowpd] = pd[i + a * nrowpd] + s * (k[r] * y[b]);
+                if (b < neq) pd[i + b * nrowpd] = pd[i + b * nrowpd] + s * (k[r] * y[a]);
             }
         }
     }
@@ -327,6 +328,11 @@ int dvo_batch_solve(const dvo_batch_cfg *cfg, int nsys, const real *params, cons
     return fail;
 }
 
+/* neq of the calls from the istate = 3 call on in dvo_batch_solve2 (0 = unchanged): the reference allows a
+ * smaller neq there (M:1127-1135); the dropped components keep their last values in the output rows. */
+static int g_neq2 = 0;
+void dvo_set_neq2(int neq2) { g_neq2 = neq2; }
+
 /* Two-phase run: outputs [0, nsplit) with cfg / rtol / atol, then ONE call with istate = 3 and
  * cfg2 / rtol2 / atol2 (same mf; the reference's "parameter change" restart, M:1382-1390) and
  * ordinary continuation calls for the remaining outputs. */
@@ -387,7 +393,7 @@ int dvo_batch_solve2(const dvo_batch_cfg *cfg, const dvo_batch_cfg *cfg2, int ns
                 iwork[4] = c->maxord; iwork[5] = c->mxstep; iwork[6] = c->mxhnil;
                 rwork[0] = c->tcrit;
                 if (istate >= 0)
-                    dvo_solve(&sol, neq, y, &t, touts[io], c->itol, rt, at, c->itask, &istate,
+                    dvo_solve(&sol, (io >= nsplit && g_neq2 > 0) ? g_neq2 : neq, y, &t, touts[io], c->itol, rt, at, c->itask, &istate,
                               c->iopt, rwork, lrw, iwork, liw, c->mf);
                 size_t o = (size_t)s * nout + io;
                 memcpy(y_out + o * neq, y, sizeof(real) * (size_t)neq);

@@ -160,7 +160,7 @@ def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1,
 def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, atol2, itol=1,
                  itol2=None, itask=1, itask2=None, iopt=0, iopt2=None, ml=0, mu=0, maxord=0,
                  maxord2=0, mxstep=0, mxstep2=0, hmax=0.0, hmax2=0.0, hmin=0.0, hmin2=0.0,
-                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant="", mf2=None):
+                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant="", mf2=None, neq2=0):
     """Outputs [0, nsplit) with the first parameter set, then an istate = 3 call with the second
     set (and method flag mf2, default the same) and continuation calls: the reference's
     parameter-change restart."""
@@ -184,10 +184,14 @@ def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, 
     ista = np.zeros((nsys, nout, 12), dtype=np.int32)
     L = lib(variant)
     L.dvo_batch_solve2.restype = C.c_int
+    L.dvo_set_neq2.argtypes = [C.c_int]
+    L.dvo_set_neq2.restype = None
+    L.dvo_set_neq2(int(neq2))  # neq of the calls from the istate = 3 call on (0 = unchanged)
     nfail = L.dvo_batch_solve2(C.byref(cfg), C.byref(cfg2), int(nsplit), nsys, _dp(params), _dp(y0),
                                C.c_double(float(t0)), nout, _dp(touts), _dp(rtol), _dp(atol),
                                _dp(rtol2), _dp(atol2), _dp(y), _dp(t), _ip(ist), _dp(rst), _ip(ista),
                                nthreads)
+    L.dvo_set_neq2(0)
     assert nfail >= 0
     return {"y": y, "t": t, "istate": ist, "rstats": rst, "istats": ista, "nfail": nfail}
 

@@ -599,3 +599,54 @@ def test_istate3_changes_the_method_family(problem, mf, mf2):
     if problem == "vdp" and mf in (10, 12):
         nqu = ref["istats"][:, nsplit - 1, 3]
         assert (nqu == 6).any() and (nqu >= 7).any() and (nqu <= 5).any()
+
+
+# ------------------------------------------------------------------ istate = 3 with a smaller neq ----
+@pytest.mark.parametrize("problem,mf,neq2", [("advection", -24, 20), ("advection", -25, 20), ("advection", 10, 13),
+                                             ("advection", 23, 20), ("advection", 13, 7), ("mech32", -22, 24),
+                                             ("mech32", -21, 24), ("mech32", 13, 17)])
+def test_istate3_reduces_neq(problem, mf, neq2):
+    """`neq` may be reduced (never raised) by an istate = 3 call (M:1127-1135): the solver goes on with the first
+    neq equations; the dropped components stay what the caller's y array held for them (for mech32 the kept
+    equations read them).  y, the output points and the work-array lengths follow the new neq.  Strict, bit for bit
+    (jsv = -1 where the flag has a Jacobian: the reference's saved copy would change its leading dimension)."""
+    B = _B()
+    nsys = 40
+    kw, iw = {}, np.zeros(30, dtype=np.int32)
+    if problem == "advection":
+        par, y0, touts = B.batches.advection_batch(nsys), B.batches.advection_y0(), B.batches.advection_touts()
+        rtol, atol, nsplit = [0.0], [1e-6], 2
+        kw = dict(ml=5, mu=0, iopt=1, mxstep=5000, iopt2=1, mxstep2=5000)
+        iw[0], iw[5] = 5, 5000
+    else:
+        par, y0, touts = B.batches.mech32_batch(nsys), B.batches.mech32_y0(), [1e-6, 1e-5, 1e-4, 1e-3]
+        rtol, atol, nsplit = [1e-6], [1e-12], 2
+        kw = dict(iopt=1, mxstep=50000, iopt2=1, mxstep2=50000)
+        iw[5] = 50000
+    ref = O.batch_solve2(problem, par, y0, 0.0, touts, nsplit, rtol, atol, mf, rtol, atol, itol=1, pow_mode=1, neq2=neq2, **kw)
+    s = B.dvode_t().initialize(problem, nsys, par, strict=True)
+    n0 = s.neq
+    y = np.ascontiguousarray(np.broadcast_to(np.asarray(y0, dtype=np.float64), (nsys, n0))).copy()
+    t = np.zeros(nsys)
+    ist = np.ones(nsys, dtype=np.int32)
+    rw = np.zeros((nsys, 20))
+    iwk = np.zeros((nsys, 30), dtype=np.int32)
+    iwk[0] = iw
+    for k, to in enumerate(touts):
+        neq = n0 if k < nsplit else neq2
+        if k == nsplit:
+            ist[:] = 3
+            y = np.ascontiguousarray(y[:, :neq2])  # the caller's y now has neq2 entries per system
+        s.solve(neq, y, t, to, 1, rtol, atol, 1, ist, 1, rw, 20, iwk, 30, mf)
+        assert (ist == 2).all(), (k, ist)
+        assert np.array_equal(y, ref["y"][:, k, :neq]), k
+        assert np.array_equal(t, ref["t"][:, k]) and np.array_equal(iwk[:, 10:22], ref["istats"][:, k]), k
+        assert np.array_equal(rw[:, 10:14], ref["rstats"][:, k]), k
+    assert ref["istats"][0, -1, 6] < ref["istats"][0, 0, 6]  # lenrw follows neq (M:1246-1268)
+    # a larger neq afterwards is illegal input; dvindy has the new width
+    dky, iflag = s.dvindy(t, 0)
+    assert dky.shape == (nsys, neq2) and (iflag == 0).all() and np.array_equal(dky, ref["y"][:, -1, :neq2])
+    with pytest.raises(B.BvodeError):
+        ist[:] = 3
+        s.solve(n0, np.zeros((nsys, n0)), t, touts[-1] * 2, 1, rtol, atol, 1, ist, 1, rw, 20, iwk, 30, mf)
+    s.close()
