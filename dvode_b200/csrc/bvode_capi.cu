@@ -581,19 +581,19 @@ static int solve_host(bvode_solver *s, int neq, real *y, real *t, int nout,
         if (rc == BVODE_EINVAL) for (int j = 0; j < nsys; j++) istate[j] = -3;
         return rc;
     }
-    {   // ml / mu only mean something for the banded method flags (miter 4, 5)
+    // ml / mu are re-read on every istate = 3 call (M:1136-1148) and only mean something for the banded method
+    // flags (miter 4, 5): another bandwidth is another band image in the state, handled like another mf below
+    bool band_changed = false;
+    {
         const int mo = abs(s->mf) % 10, mn = abs(mf) % 10;
         const bool band_old = (mo == 4 || mo == 5), band_new = (mn == 4 || mn == 5);
-        if (n3 != 0 && band_old && band_new && (c.o.ml != s->ml || c.o.mu != s->mu)) {
-            g_err = "istate = 3 with different ml / mu is not built";
-            return BVODE_ENOTIMPL;
-        }
+        band_changed = (n3 != 0 && band_old && band_new && (c.o.ml != s->ml || c.o.mu != s->mu));
     }
     if (!(s->flags & BVODE_FLAG_PER_SYSTEM) && n3 != 0 && mf > 0 && c.o.maxord != s->maxord) c.o.jreset = 1;
     if (n3 != 0 && (c.o.maxord != s->maxord || abs(s->mf) / 10 != abs(mf) / 10)) c.o.lmaxchg = 1;
     if (n3 != 0 && c.o.nact != s->nact) c.o.jreset = 1;  // a smaller neq: the saved Jacobian had another leading dimension
-    if (mf_changed) {
-        // M:999-1046 at istate = 3: a new miter / jsv.  The state moves into the layout of the new
+    if (mf_changed || band_changed) {
+        // M:999-1046 at istate = 3: a new miter / jsv (or, M:1136-1148, another ml / mu).  The state moves into the layout of the new
         // method flag; the Newton matrix and the saved Jacobian are rebuilt at the restart.
         size_t nd = 0, ni = 0;
         s->pe->state_size(mf, c.o.ml, c.o.mu, (size_t)nsys, &nd, &ni);

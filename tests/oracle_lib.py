@@ -160,7 +160,7 @@ def batch_solve(problem, params, y0, t0, touts, rtol, atol, mf, itol=1, itask=1,
 def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, atol2, itol=1,
                  itol2=None, itask=1, itask2=None, iopt=0, iopt2=None, ml=0, mu=0, maxord=0,
                  maxord2=0, mxstep=0, mxstep2=0, hmax=0.0, hmax2=0.0, hmin=0.0, hmin2=0.0,
-                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant="", mf2=None, neq2=0):
+                 tcrit=0.0, tcrit2=0.0, pow_mode=0, nthreads=0, variant="", mf2=None, neq2=0, ml2=None, mu2=None):
     """Outputs [0, nsplit) with the first parameter set, then an istate = 3 call with the second
     set (and method flag mf2, default the same) and continuation calls: the reference's
     parameter-change restart."""
@@ -176,7 +176,7 @@ def batch_solve2(problem, params, y0, t0, touts, nsplit, rtol, atol, mf, rtol2, 
     cfg = BatchCfg(PROBLEMS[problem], mf, itol, itask, iopt, ml, mu, maxord, mxstep, 0, 0.0, hmax,
                    hmin, tcrit, pow_mode)
     cfg2 = BatchCfg(PROBLEMS[problem], mf if mf2 is None else mf2, pick(itol, itol2), pick(itask, itask2), pick(iopt, iopt2),
-                    ml, mu, maxord2, mxstep2, 0, 0.0, hmax2, hmin2, tcrit2, pow_mode)
+                    pick(ml, ml2), pick(mu, mu2), maxord2, mxstep2, 0, 0.0, hmax2, hmin2, tcrit2, pow_mode)
     y = np.zeros((nsys, nout, neq))
     t = np.zeros((nsys, nout))
     ist = np.zeros((nsys, nout), dtype=np.int32)

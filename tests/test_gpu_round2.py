@@ -650,3 +650,43 @@ def test_istate3_reduces_neq(problem, mf, neq2):
         ist[:] = 3
         s.solve(n0, np.zeros((nsys, n0)), t, touts[-1] * 2, 1, rtol, atol, 1, ist, 1, rw, 20, iwk, 30, mf)
     s.close()
+
+
+# ------------------------------------------------------------------ istate = 3 with another ml / mu ----
+@pytest.mark.parametrize("mf,band,band2", [(-25, (5, 0), (5, 5)), (-25, (5, 5), (5, 0)), (-25, (5, 0), (7, 2)),
+                                           (-25, (5, 0), (3, 0)), (-24, (5, 0), (5, 5)), (-24, (5, 5), (5, 0)),
+                                           (25, (5, 0), (5, 5)), (24, (5, 5), (5, 0))])
+def test_istate3_changes_the_bandwidth(mf, band, band2):
+    """ml / mu are re-read from iwork(1:2) on every istate = 3 call (M:1136-1148 inside block B): the band image of
+    the state takes the new shape, the Newton matrix is rebuilt at the restart, lenrw follows.  Widening, narrowing
+    back, a band wider than the Jacobian's, and one that cuts entries off (ml = 3 < 5: a chord iteration with an
+    incomplete matrix).  Strict build, bit for bit.  With jsv = +1 the reference's dvjac would read its "saved copy"
+    with the new leading dimension from words written with the old one (M:1246-1268) -- not mirrored: the Jacobian is
+    re-evaluated at the restart, so those runs are compared with the oracle's jsv = -1 run of the second phase."""
+    B = _B()
+    nsys = 40
+    par, y0, touts = B.batches.advection_batch(nsys), B.batches.advection_y0(), B.batches.advection_touts()
+    rtol, atol, nsplit = [0.0], [1e-6], 2
+    (ml, mu), (ml2, mu2) = band, band2
+    iw, iw2 = np.zeros(30, dtype=np.int32), np.zeros(30, dtype=np.int32)
+    iw[0], iw[1], iw2[0], iw2[1] = ml, mu, ml2, mu2
+    ref = O.batch_solve2("advection", par, y0, 0.0, touts, nsplit, rtol, atol, mf, rtol, atol, itol=1, pow_mode=1,
+                         ml=ml, mu=mu, ml2=ml2, mu2=mu2, mf2=-abs(mf))
+    assert (ref["istate"] == 2).all()
+    got = gpu_schedule("advection", par, y0, 0.0, touts, rtol, atol, mf, 1, strict=True, per_call=True,
+                       iwork_opts=iw, rwork_opts=np.zeros(20),
+                       phase2=dict(nsplit=nsplit, rtol=rtol, atol=atol, itol=1, itask=1, iopt=0, mf=mf,
+                                   iwork_opts=iw2, rwork_opts=np.zeros(20)))
+    if mf < 0:
+        for k in ("y", "t", "istate", "istats", "rstats"):
+            assert np.array_equal(got[k], ref[k]), k
+    else:  # a saved copy against none: not comparable call for call (see test_istate3_maxord_change_with_saved_jacobian)
+        assert (got["istate"] == 2).all()
+        assert np.array_equal(got["y"][:, :nsplit], ref["y"][:, :nsplit])
+        err = np.abs(got["y"][:, nsplit:] - ref["y"][:, nsplit:]) / 1e-6
+        assert np.percentile(err, 99) <= 10.0, float(np.percentile(err, 99))
+        a = got["istats"][:, -1, O.ISTAT["nst"]].astype(np.int64).sum()
+        b = ref["istats"][:, -1, O.ISTAT["nst"]].astype(np.int64).sum()
+        assert abs(a - b) <= 0.03 * b, (a, b)
+        assert (got["istats"][:, nsplit:, O.ISTAT["lenrw"]] == O.work_sizes(25, mf, ml2, mu2)[0]).all()
+    assert ref["istats"][0, -1, O.ISTAT["lenrw"]] != ref["istats"][0, 0, O.ISTAT["lenrw"]]
