@@ -345,7 +345,7 @@ struct WarpRegions {
         dl = dstate + (size_t)scalar_d<POL>() * nsys;
         db = dl + (size_t)POL::kLaneSlots * nsys * 32;
         il = istore + (size_t)kScalarI * nsys;
-        if constexpr (POL::kBand) nblock = POL::block_doubles(ml, mu, POL::SAVEJ);
+        if constexpr (POL::kBand) nblock = POL::band_ld(ml, mu) * POL::N + (POL::SAVEJ ? (ml + mu + 1) * POL::N : 0);
         else if constexpr (POL::kPlain) nblock = 0;
         else nblock = POL::kBlockDoubles;
     }

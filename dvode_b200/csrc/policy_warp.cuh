@@ -96,6 +96,11 @@ template <int OFF = 0>
 BV_DEV void sts_d2(unsigned a, real v0, real v1) {
     asm volatile("st.shared.v2.f64 [%0+%1], {%2,%3};" ::"r"(a), "n"(OFF), "d"(v0), "d"(v1) : "memory");
 }
+// an 8-byte store that ptxas must leave alone: adjacent plain stores get merged into 16-byte ones, and when the two
+// values do not sit in an aligned register quad that costs four moves per store
+BV_DEV void sts_d_single(unsigned a, real v) {
+    asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
 BV_DEV void sts_i(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // Common pieces of the two warp policies.
@@ -588,20 +593,23 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                 const real rp = qrcp(piv);
                 const bool mine = (ln == l);
                 if (mine) {
-                    // the pivot row publishes its entries of the other columns UNSCALED, rotated, with a 1 in the
-                    // place of column k, and clears them in its registers: every lane then forms
-                    //     r'[j] = a[j+1] + t * P[j],    t = -v/pivot  (pivot row: t = 1/pivot on a cleared row)
-                    // so the new pivot row is P/pivot, the others lose their column-k entry, and the last place
-                    // (column k of the inverse) receives t itself.  The single-lane section is the stores only.
+                    // the pivot row scales its entries of the other columns by 1/pivot and publishes them, rotated,
+                    // with 1/pivot itself in the place of column k; every lane then forms
+                    //     r'[j] = a[j+1] + t * P[j],    t = -v  (pivot row: t = 0, its scaled entries just rotate)
+                    // so the others lose their column-k entry and the last place (column k of the inverse) receives
+                    // -v/pivot.  The single-lane section is N-1 multiplications and N 8-byte (volatile: not merged) stores: 16-byte stores
+                    // of the rotated row need their register pairs moved into aligned quads first, and clearing the
+                    // row instead of scaling it (t = 1/pivot on the unscaled buffer) costs two moves per entry --
+                    // together 150 single-lane instructions per step, a quarter of the kernel's instructions (ncu r2j).
 #pragma unroll
-                    for (int j = 0; j + 1 < N; j += 2) sts_d2(bufa + j * 8, r[j + 1], (j + 2 < N) ? r[j + 2] : BV_R(1.0));
-                    if (N & 1) sts_d(bufa + (N - 1) * 8, BV_R(1.0));
+                    for (int j = 1; j < N; j++) r[j] = r[j] * rp;
 #pragma unroll
-                    for (int j = 1; j < N; j++) r[j] = BV_R(0.0);
+                    for (int j = 0; j + 1 < N; j++) sts_d_single(bufa + j * 8, r[j + 1]);
+                    sts_d_single(bufa + (N - 1) * 8, rp);
                     unused = false;
                 }
                 __syncwarp();
-                const real t = mine ? rp : -v * rp;
+                const real t = mine ? BV_R(0.0) : -v;
 #pragma unroll
                 for (int j = 0; j < NE; j += 2) {
                     real p0, p1;
@@ -611,6 +619,7 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
                     r[j] = fma(t, p0, a0);
                     if (j + 1 < N) r[j + 1] = fma(t, p1, a1);
                 }
+                if (mine) r[N - 1] = rp;
                 __syncwarp();
             }
         }
@@ -922,36 +931,14 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         int ipv;       // lane k holds ipvt(k+1) as a 0-based row of the full matrix
     };
     template <class ENG>
-    BV_DEV static void lin_init(ENG &e) {
-        e.lin.ipv = lane();
-        if (blk_ok(e.lin.ml, e.lin.mu)) {  // blk_setup reads finite memory whatever it reads: the whole image starts as zeros
-            const int nb = block_doubles(e.lin.ml, e.lin.mu, SAVEJ);
-            for (int i = lane(); i < nb; i += 32) e.lin.abd[i] = BV_R(0.0);
-            __syncwarp();
-        }
-    }
+    BV_DEV static void lin_init(ENG &e) { e.lin.ipv = lane(); }
 
-    __host__ __device__ static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
-    // Fast build: the two triangular solves of dgbsl run BLOCKED when the factorisation interchanged no rows (see
-    // blk_setup / solve): per lane a row of block coefficients (blk_row), odd stride
-    __host__ __device__ static bool blk_ok(int ml, int mu) {
-#if BVODE_STRICT
-        (void)ml; (void)mu;
-        return false;
-#else
-        return ml <= 5 && ml + mu >= 1 && ml + mu <= 10;
-#endif
+    BV_DEV static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
+    // doubles of shared memory one system needs
+    static int smem_doubles(int ml, int mu, bool savej) {
+        const int ld = (2 * ml + mu + 1) | 1;
+        return ld * N + (savej ? (ml + mu + 1) * N : 0);
     }
-    // block sizes: the bandwidth rounded up to a size the code is unrolled for (a block may be wider than the band)
-    __host__ __device__ static int blk_cbl(int ml) { return ml == 0 ? 0 : 5; }
-    __host__ __device__ static int blk_cbu(int ml, int mu) { return ml + mu <= 5 ? 5 : 10; }
-    __host__ __device__ static int blk_stride(int ml, int mu) { return (2 * blk_cbl(ml) + 2 * blk_cbu(ml, mu) + 1) | 1; }  // + a zero slot, odd
-    // doubles of shared memory one system needs (= its block image in the HBM state): abd, the saved Jacobian,
-    // the block coefficients
-    __host__ __device__ static int block_doubles(int ml, int mu, bool savej) {
-        return band_ld(ml, mu) * N + (savej ? (ml + mu + 1) * N : 0) + (blk_ok(ml, mu) ? 32 * blk_stride(ml, mu) : 0);
-    }
-    static int smem_doubles(int ml, int mu, bool savej) { return block_doubles(ml, mu, savej); }
     static constexpr int kLaneSlots = kLmax + 2;  // yh[6], acsav, acor; the band arrays follow
     static constexpr int kLaneIntSlots = 1;
     template <class ENG, class V>
@@ -960,124 +947,10 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     BV_DEV static void visit_lin(ENG &e, V &v) {
         Lin &l = e.lin;
         // band arrays: the whole shared-memory image of this system, cooperatively
-        v.block(l.abd, block_doubles(l.ml, l.mu, SAVEJ));
+        const int nb = l.ld * N + (SAVEJ ? (l.ml + l.mu + 1) * N : 0);
+        v.block(l.abd, nb);
         v.iv(l.ipv);
     }
-
-    // this lane's row of block coefficients: TL[cbl], GL[cbl], TU[cbu], GU[cbu], 0.0
-    BV_DEV static real *blk_row(const Lin &l) {
-        return l.abd + l.ld * N + (SAVEJ ? (l.ml + l.mu + 1) * N : 0) + lane() * blk_stride(l.ml, l.mu);
-    }
-#if !BVODE_STRICT
-    // ---- blocked triangular solves (fast build; a factorisation without row interchanges) --------------------
-    // dgbsl's forward loop (LP:494-506) is  w = y + A w  with A(k+i, k) = abd(m+i, k), strictly lower, bandwidth ml;
-    // its back substitution, in the scaled form of dgbfa's epilogue below, is  w = y + S w  with
-    // S(i, k) = abd(m-(k-i), k), strictly upper, bandwidth ml+mu.  With the rows grouped in blocks of CB >= bandwidth
-    // a block couples to ONE neighbour only:
-    //     w_i = T_i y_i + G_i w_(i-1),     T_i = (I - A_ii)^-1 (unit triangular),  G_i = T_i A_(i,i-1)
-    // so a solve is one block-local product for all blocks at once and then n/CB - 1 dependent block steps of CB
-    // independent fmas each, instead of n - 1 dependent shuffle -> fma steps.  Lane r keeps row r of T and G
-    // (registers while they are built, then its row of the shared-memory scratch).  bw = the factor's bandwidth.
-    // Every term reads its matrix entry through ONE load: an entry outside the band (the block may be wider than
-    // the band) is read from the row's zero slot instead, and what a lane has no business with (rows / columns beyond
-    // n, the block before the first) is read from finite memory -- the whole image is zeroed at lin_init -- and
-    // multiplied by a zero of T or cleared by one select per entry of the result.
-    template <int CB, bool UPPER>
-    BV_DEV static void blk_setup_one(const Lin &l, unsigned rowa, unsigned za, int bw) {
-        const int ln = lane();
-        const int n = N, m = l.ml + l.mu + 1;
-        const int ib = ln / CB, p = ln - ib * CB, base = ib * CB;
-        const bool rowok = ln < n;
-        const int ld8 = l.ld * 8;
-        // byte address of the diagonal entry abd(m, base + 1) of this lane's block
-        const unsigned dg = sm_addr(l.abd) + base * ld8 + (m - 1) * 8;
-        real t[CB], g[CB];
-        if constexpr (!UPPER) {
-#pragma unroll
-            for (int q = CB - 1; q >= 0; q--) {
-                real s = (q == p && rowok) ? BV_R(1.0) : BV_R(0.0);
-#pragma unroll
-                for (int j = q + 1; j < CB; j++)  // A_ii(j, q) = abd(m + j - q, base + q)
-                    s = s + t[j] * lds_d((j - q <= bw) ? dg + q * ld8 + (j - q) * 8 : za);
-                t[q] = s;
-            }
-            const unsigned dgm = (ib > 0) ? dg - CB * ld8 : dg;
-#pragma unroll
-            for (int q = 0; q < CB; q++) {
-                real s = BV_R(0.0);
-#pragma unroll
-                for (int j = 0; j <= q; j++)  // A_(i,i-1)(j, q) = abd(m + CB + j - q, base - CB + q)
-                    s = s + t[j] * lds_d((CB + j - q <= bw) ? dgm + q * ld8 + (CB + j - q) * 8 : za);
-                g[q] = (ib > 0) ? s : BV_R(0.0);
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < CB; q++) {
-                real s = (q == p && rowok) ? BV_R(1.0) : BV_R(0.0);
-#pragma unroll
-                for (int j = 0; j < q; j++)  // S_ii(j, q) = abd(m - (q - j), base + q)
-                    s = s + t[j] * lds_d((q - j <= bw) ? dg + q * ld8 - (q - j) * 8 : za);
-                t[q] = (base + q < n) ? s : BV_R(0.0);
-            }
-#pragma unroll
-            for (int q = 0; q < CB; q++) {
-                real s = BV_R(0.0);
-#pragma unroll
-                for (int j = q; j < CB; j++)  // S_(i,i+1)(j, q) = abd(m - (CB + q - j), base + CB + q)
-                    s = s + t[j] * lds_d((CB + q - j <= bw) ? dg + (CB + q) * ld8 - (CB + q - j) * 8 : za);
-                g[q] = (base + CB + q < n) ? s : BV_R(0.0);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < CB; q++) {
-            sts_d(rowa + q * 8, t[q]);
-            sts_d(rowa + (CB + q) * 8, g[q]);
-        }
-    }
-    BV_DEV static void blk_setup(const Lin &l) {
-        const unsigned rowa = sm_addr(blk_row(l));
-        const unsigned urow = rowa + 2 * blk_cbl(l.ml) * 8;
-        const unsigned za = urow + 2 * blk_cbu(l.ml, l.mu) * 8;  // the row's zero slot
-        if (l.ml != 0) blk_setup_one<5, false>(l, rowa, za, l.ml);
-        if (l.ml + l.mu <= 5) blk_setup_one<5, true>(l, urow, za, l.ml + l.mu);
-        else blk_setup_one<10, true>(l, urow, za, l.ml + l.mu);
-        __syncwarp();
-    }
-    // one triangular pass: trow = shared address of this lane's T row (CB entries; its G row follows); the blocks
-    // that receive from a neighbour start at lo0, lo0 + dlo, ... while inside [0, n) (lower factor: lo0 = CB,
-    // dlo = CB; upper factor: lo0 = last block - CB, dlo = -CB)
-    template <int Q, int CB>
-    struct BlkUnroll {
-        BV_DEV static void z(real &w, real y, unsigned trow, int src) {
-            if constexpr (Q < CB) {
-                w = w + lds_d<Q * 8>(trow) * shfl_d(y, src + Q);
-                BlkUnroll<Q + 1, CB>::z(w, y, trow, src);
-            }
-        }
-        BV_DEV static void step(real &w, unsigned trow, int src, int x) {
-            if constexpr (Q < CB) {
-                fma_if_ltu(w, shfl_d(w, src + Q), lds_d<(CB + Q) * 8>(trow), x, CB);
-                BlkUnroll<Q + 1, CB>::step(w, trow, src, x);
-            }
-        }
-    };
-    template <int CB, bool UPPER>
-    BV_DEV static real blk_pass(real y, unsigned trow) {
-        const int ln = lane();
-        const int base = (ln / CB) * CB;
-        constexpr int last = ((N - 1) / CB) * CB;  // first row of the last block
-        real w = BV_R(0.0);
-        BlkUnroll<0, CB>::z(w, y, trow, base);
-        if constexpr (!UPPER) {
-#pragma unroll 1
-            for (int lo = CB; lo < N; lo += CB) BlkUnroll<0, CB>::step(w, trow, lo - CB, ln - lo);
-        } else {
-#pragma unroll 1
-            for (int lo = last - CB; lo >= 0; lo -= CB) BlkUnroll<0, CB>::step(w, trow, lo + CB, ln - lo);
-        }
-        return w;
-    }
-#endif
 
 #define ABD(i, j) l.abd[((j)-1) * l.ld + ((i)-1)]
     // ---- dgbfa, LP:275-396 (1-based indices as in the reference) ------------------------
@@ -1086,7 +959,6 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         const int n = N, ml = l.ml, mu = l.mu;
         const int m = ml + mu + 1;
         int info = 0;
-        [[maybe_unused]] bool anyswap = false;
         // zero initial fill-in columns, LP:299-308: column jz = lane+1
         const int j0 = mu + 2, j1 = (n < m ? n : m) - 1;
         {
@@ -1119,7 +991,6 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                 info = k;
             } else {
                 const bool swap = (lofs != 0);  // warp-uniform
-                anyswap = anyswap || swap;
                 if (swap) {  // interchange, LP:335-339, in registers
                     const real akk = shfl_d(v, 0);
                     if (ln == lofs) v = akk;
@@ -1175,7 +1046,6 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
             for (int i = 1; i <= lmj; i++) ABD(m - i, j) = -rp * ABD(m - i, j);
         }
         __syncwarp();
-        if (info == 0 && !anyswap && blk_ok(ml, mu)) blk_setup(l);
 #endif
         return info;
     }
@@ -1193,27 +1063,11 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         const int step = (l.ld - 1) * 8;
         const unsigned a1 = sm_addr(l.abd) + (m - 1 + (live ? ln : 0)) * 8;  // column 1
         real b = x[0];
-        // any row interchange at all?  (warp-uniform; none for diagonally dominant P)
-        const bool swaps = (ml != 0) && __any_sync(kFull, live && (l.ipv != ln)) != 0;
-#if !BVODE_STRICT
-        if (!swaps && blk_ok(ml, mu)) {  // the blocked form (blk_setup)
-            const unsigned row = sm_addr(blk_row(l));
-            if (ml != 0) b = blk_pass<5, false>(b, row);
-            const unsigned urow = row + 2 * blk_cbl(ml) * 8;
-            if (ml + mu <= 5) b = blk_pass<5, true>(b, urow);
-            else b = blk_pass<10, true>(b, urow);
-            if (live) b = b * lds_d(a1 + ln * step);  // x_k = w_k / u_kk
-            x[0] = b;
-            return 0;
-        }
-#endif
         if (ml != 0) {
+            // any row interchange at all?  (warp-uniform; none for diagonally dominant P)
+            const bool swaps = __any_sync(kFull, live && (l.ipv != ln)) != 0;
             unsigned a = a1;
-#if BVODE_STRICT
 #pragma unroll 4
-#else
-#pragma unroll 1  // (fast build: the rare path -- a factorisation that interchanged rows, or a band the blocked form is not unrolled for)
-#endif
             for (int k = 1; k <= n - 1; k++, a += step) {
                 real t;
                 if (swaps) {
@@ -1251,7 +1105,7 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
                 if (part) b = b + t * mv;
             }
 #else
-#pragma unroll 1
+#pragma unroll 4
             for (int k = n; k >= 2; k--, a -= step) {
                 const real mv = lds_d(a);
                 const real t = shfl_d(b, k - 1);
