@@ -333,6 +333,15 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
 #ifndef BVODE_DENSE_INVERSE
 #define BVODE_DENSE_INVERSE 1
 #endif
+#ifndef BVODE_DGINV_EARLY_RCP
+#define BVODE_DGINV_EARLY_RCP 0
+#endif
+#ifndef BVODE_DGINV_BATCH
+#define BVODE_DGINV_BATCH 4
+#endif
+#ifndef BVODE_DGINV_FENCE
+#define BVODE_DGINV_FENCE 1
+#endif
     static constexpr bool kInverse = (BVODE_STRICT == 0) && (BVODE_DENSE_INVERSE != 0);
     // row stride in doubles.  LU: odd (own-row and broadcast 8-byte accesses are conflict-free).  Inverse:
     // = 2 (mod 4), so that rows are 16-byte aligned and the 8 lanes of a quarter-warp hit disjoint banks
@@ -560,12 +569,13 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     BVODE_DGINV_INLINE static int dginv(Lin &lin) {
         // The lane's row lives in REGISTERS for the whole inversion, rotated by one entry per step so that
         // "column k" is always r[0] and every register index is static inside a run-time loop over k:
-        // step k reads r[0] (the pivot candidate), lane l (the pivot row) scales its row and publishes it to
-        // a 32-double buffer in shared memory, and every lane forms r'[j-1] = r[j] + t * P[j-1] from 16-byte
+        // step k reads r[0] (the pivot candidate), lane l (the pivot row) publishes its row as it stands to a
+        // 32-double buffer in shared memory, and every lane forms r'[j] = r[j+1] + t * P[j+1] from 16-byte
         // broadcast loads of that buffer; the entry of column k itself (the inverse's column) goes to the
-        // end, r'[N-1].  After N steps the rotation is complete.  Shared-memory traffic per step: one
-        // single-lane store and one broadcast load of the pivot row, instead of a load and a store of every
-        // lane's own row (the shared-memory data pipe is what bounds this kernel, ncu r1o).
+        // end, r'[N-1].  After N steps the rotation is complete and every row is scaled by 1 / its pivot.
+        // Shared-memory traffic per step: one single-lane store and one broadcast load of the pivot row,
+        // instead of a load and a store of every lane's own row (the shared-memory data pipe is what bounds
+        // the LINPACK form of this kernel, ncu r1o).
         const int ln = lane();
         const bool live = real_lane();
         const unsigned pa = sm_addr(lin.p);
@@ -579,9 +589,13 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         for (int j = 0; j < NE; j += 2) lds_d2(rowa + j * 8, r[j], r[j + 1]);
         bool unused = live;  // this lane's row has not been a pivot row yet
         int info = 0;
+        real myrp = BV_R(1.0);  // 1 / (the pivot this lane's row supplied)
 #pragma unroll 1
         for (int k = 0; k < N && info == 0; k++) {
             const real v = r[0];
+#if BVODE_DGINV_EARLY_RCP
+            const real rv = qrcp(v);  // off the ballot -> shuffle chain: every lane inverts its own candidate
+#endif
             const unsigned b = Base::max_abs_ballot(v, unused);
             const int l = __ffs((int)b) - 1;  // ties: the lowest row
             const real piv = shfl_d(v, l);
@@ -590,40 +604,58 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
             if (piv == BV_R(0.0)) {
                 info = k + 1;
             } else {
+#if BVODE_DGINV_EARLY_RCP
+                const real rp = shfl_d(rv, l);
+#else
                 const real rp = qrcp(piv);
+#endif
                 const bool mine = (ln == l);
+                // The pivot row is NOT scaled during the elimination: row operations commute with a scaling of
+                // the pivot row as long as the multipliers are formed from the entries as they stand
+                // (t = -v / pivot), so every row is scaled once, by 1 / its own pivot, after the last step.
+                // The single-lane section of a step is then just the publication of the row as it lies in the
+                // registers -- N / 2 16-byte stores of aligned pairs, no arithmetic, no moves (150 single-lane
+                // instructions per step in r2j, 63 with the row scaled and rotated by the pivot lane).  Every
+                // lane forms
+                //     r'[j] = r[j+1] + t * P[j+1]  (j < N-1),    r'[N-1] = t        (pivot row: t = 0, r'[N-1] = 1)
+                // i.e. the buffer is read one entry ahead of the register it lands in.
                 if (mine) {
-                    // the pivot row scales its entries of the other columns by 1/pivot and publishes them, rotated,
-                    // with 1/pivot itself in the place of column k; every lane then forms
-                    //     r'[j] = a[j+1] + t * P[j],    t = -v  (pivot row: t = 0, its scaled entries just rotate)
-                    // so the others lose their column-k entry and the last place (column k of the inverse) receives
-                    // -v/pivot.  The single-lane section is N-1 multiplications and N 8-byte (volatile: not merged) stores: 16-byte stores
-                    // of the rotated row need their register pairs moved into aligned quads first, and clearing the
-                    // row instead of scaling it (t = 1/pivot on the unscaled buffer) costs two moves per entry --
-                    // together 150 single-lane instructions per step, a quarter of the kernel's instructions (ncu r2j).
 #pragma unroll
-                    for (int j = 1; j < N; j++) r[j] = r[j] * rp;
-#pragma unroll
-                    for (int j = 0; j + 1 < N; j++) sts_d_single(bufa + j * 8, r[j + 1]);
-                    sts_d_single(bufa + (N - 1) * 8, rp);
+                    for (int j = 0; j < NE; j += 2) sts_d2(bufa + j * 8, r[j], r[j + 1]);
                     unused = false;
+                    myrp = rp;
                 }
                 __syncwarp();
-                const real t = mine ? BV_R(0.0) : -v;
+                const real t = mine ? BV_R(0.0) : -(v * rp);
+                // kB 16-byte loads of the buffer are in flight before their fmas: with one (the compiler's choice
+                // under register pressure: every load lands in the same register quad) a step is N / 2 exposed
+                // shared-memory latencies
+                constexpr int kB = BVODE_DGINV_BATCH;
 #pragma unroll
-                for (int j = 0; j < NE; j += 2) {
-                    real p0, p1;
-                    lds_d2(bufa + j * 8, p0, p1);
-                    const real a0 = (j + 1 < N) ? r[j + 1] : BV_R(0.0);
-                    const real a1 = (j + 2 < N) ? r[j + 2] : BV_R(0.0);
-                    r[j] = fma(t, p0, a0);
-                    if (j + 1 < N) r[j + 1] = fma(t, p1, a1);
+                for (int j0 = 0; j0 < NE; j0 += 2 * kB) {
+                    real p[2 * kB];
+#pragma unroll
+                    for (int q = 0; q < kB; q++)
+                        if (j0 + 2 * q < NE) lds_d2(bufa + (j0 + 2 * q) * 8, p[2 * q], p[2 * q + 1]);
+#if BVODE_DGINV_FENCE
+                    if (kB > 1) __syncwarp();  // ptxas otherwise sinks each load to its first use again
+#endif
+#pragma unroll
+                    for (int q = 0; q < kB; q++) {
+                        const int j = j0 + 2 * q;
+                        if (j < NE) {
+                            if (j >= 1 && j <= N - 1) r[j - 1] = fma(t, p[2 * q], r[j]);
+                            if (j + 1 <= N - 1) r[j] = fma(t, p[2 * q + 1], r[j + 1]);
+                        }
+                    }
                 }
-                if (mine) r[N - 1] = rp;
+                r[N - 1] = mine ? BV_R(1.0) : t;
                 __syncwarp();
             }
         }
         if (live) {
+#pragma unroll
+            for (int j = 0; j < N; j++) r[j] = r[j] * myrp;
 #pragma unroll
             for (int j = 0; j < NE; j += 2) sts_d2(rowa + j * 8, r[j], r[j + 1]);
         }

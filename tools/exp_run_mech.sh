@@ -1,0 +1,6 @@
+#!/bin/bash
+# time mech32 (2^16 systems) with every experimental library under exp_libs/ (and the in-tree one)
+for lib in dvode_b200/libbvode.so exp_libs/*.so; do
+  echo "== $lib"
+  BVODE_LIB=$PWD/$lib python tools/time_configs.py --nsys 65536 --reps 2 --which mech32 2>&1 | grep "rep 1"
+done
