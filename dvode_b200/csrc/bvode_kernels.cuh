@@ -93,8 +93,14 @@ constexpr int kThreadTPB = BVODE_THREAD_TPB;
 // compacting one is chosen by BVODE_FLAG_COMPACT: it pays off when the systems of a batch differ
 // widely in cost (measured: see DESIGN.md), and loses ~15 % on the homogeneous headline batch,
 // where replacing lanes at different times de-correlates the rare paths of a warp's 32 systems.
+// BVODE_THREAD_MAXNREG (experiments): a register cap between ptxas's own steps (168 at 12 warps / SM, 128 above)
+#ifdef BVODE_THREAD_MAXNREG
+#define BVODE_THREAD_BOUNDS __maxnreg__(BVODE_THREAD_MAXNREG)
+#else
+#define BVODE_THREAD_BOUNDS __launch_bounds__(kThreadTPB, POL::kMinBlocks)
+#endif
 template <class POL, bool GENERAL, bool REFILL>
-__global__ void __launch_bounds__(kThreadTPB, POL::kMinBlocks) vode_thread_kernel(const __grid_constant__ KArgs a) {
+__global__ void BVODE_THREAD_BOUNDS vode_thread_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ real smem_thread[];
     constexpr int N = POL::N;
     using Prob = typename POL::Prob;

@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
-"""Summarise an .ncu-rep (one profiled kernel) into the text committed under profiles/.
-usage: ncu_summary.py <report.ncu-rep> [title]"""
+"""Summarise an .ncu-rep (one profiled kernel) -- or its `--page raw --csv` export, made on the GPU box so that only
+the small CSV travels back -- into the text committed under profiles/.
+usage: ncu_summary.py <report.ncu-rep | raw.csv> [title]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 title = sys.argv[2] if len(sys.argv) > 2 else rep
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
