@@ -333,7 +333,13 @@ struct WarpStorer {
 template <class POL>
 struct WarpLayout {
     static constexpr int N = POL::N;
-    static int nblock(int ml, int mu) { return POL::smem_doubles(ml, mu, POL::SAVEJ); }
+    // doubles of one system's saved block (band policy: the band image without the scratch of the inverse)
+    static int nblock(int ml, int mu) {
+        if constexpr (POL::kBand) return POL::image_doubles(ml, mu, POL::SAVEJ);
+        else return POL::smem_doubles(ml, mu, POL::SAVEJ);
+    }
+    // doubles of shared memory per system
+    static int nsmem(int ml, int mu) { return POL::smem_doubles(ml, mu, POL::SAVEJ); }
     static void sizes(int ml, int mu, size_t nsys, size_t *nd, size_t *ni) {
         *nd = nsys * ((size_t)scalar_d<POL>() + (size_t)POL::kLaneSlots * 32 + (size_t)nblock(ml, mu));
         *ni = nsys * ((size_t)kScalarI + (size_t)POL::kLaneIntSlots * 32);
@@ -361,7 +367,8 @@ template <class POL>
 BV_DEV void warp_bind(Engine<POL> &e, const real *dstate, const int *istore, size_t nsys,
                       size_t sys, int ln, int warp, int ml, int mu, real *smem) {
     const WarpRegions<POL> rg(dstate, istore, nsys, ml, mu);
-    const int nb = rg.nblock;
+    int nb = rg.nblock;  // shared-memory doubles per system
+    if constexpr (POL::kBand) nb = POL::smem_doubles(ml, mu, POL::SAVEJ);
     // per-warp control state: after the kWarpTPB/32 matrix images of the CTA
     e.hot.bind(smem + (size_t)(WarpTpb<POL>::value / 32) * nb + (size_t)warp * POL::kWarpHotDoubles, ln);
     if constexpr (POL::kBand) {
@@ -370,6 +377,7 @@ BV_DEV void warp_bind(Engine<POL> &e, const real *dstate, const int *istore, siz
         e.lin.ld = POL::band_ld(ml, mu);
         e.lin.abd = smem + (size_t)warp * nb;
         e.lin.wjs = e.lin.abd + e.lin.ld * POL::N;
+        e.lin.inv = e.lin.abd + ((POL::image_doubles(ml, mu, POL::SAVEJ) + 1) & ~1);
     } else if constexpr (POL::kPlain) {
         (void)ml; (void)mu; (void)smem; (void)warp; (void)sys; (void)ln;
     } else {
@@ -474,6 +482,7 @@ vode_warp_kernel(const __grid_constant__ KArgs a) {
             if (ln == 0) a.istate[sys] = IST_ILLEGAL;
             return 0;
         }
+        if constexpr (POL::kBand) POL::after_load(e);  // fast build: the inverse is not part of the saved state
         if constexpr (GENERAL) {
             if (e.nact != N) {  // neq was reduced: see the thread kernel
 #pragma unroll
@@ -637,7 +646,7 @@ template <class POL>
 static int launch_warp(const KArgs &a, cudaStream_t st) {
     const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.count + spb - 1) / spb;
-    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nblock(a.o.ml, a.o.mu) + POL::kWarpHotDoubles +
+    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nsmem(a.o.ml, a.o.mu) + POL::kWarpHotDoubles +
                                                ScratchDoublesOf<typename POL::Prob>::value);
     // Shared memory / L1 split: ask for just what POL::kMinBlocks resident CTAs need (+1 KB each that the
     // system reserves), so that the rest of the 256 KB stays L1 -- the kernels' register spills and the
@@ -662,7 +671,7 @@ template <class POL>
 static int launch_dky_warp(const DkyArgs &a, cudaStream_t st) {
     const int spb = WarpTpb<POL>::value / 32;
     const int grid = (a.nsys + spb - 1) / spb;
-    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nblock(a.ml, a.mu) + POL::kWarpHotDoubles);
+    const size_t smem = sizeof(real) * spb * ((size_t)WarpLayout<POL>::nsmem(a.ml, a.mu) + POL::kWarpHotDoubles);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(dvindy_warp_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dvindy_warp_kernel<POL><<<grid, WarpTpb<POL>::value, smem, st>>>(a);

@@ -118,11 +118,12 @@ __global__ void k_lu_band(int nmat, int ml, int mu, const real *a, const real *b
     e.lin.ld = POL::band_ld(ml, mu);
     e.lin.abd = smem;
     e.lin.wjs = nullptr;
+    e.lin.inv = smem + ((POL::image_doubles(ml, mu, false) + 1) & ~1);  // fast build: the inverse, next to the band array
     if (ln < N)
         for (int i = 0; i < lda; i++) e.lin.abd[ln * e.lin.ld + i] = a[((size_t)m * N + ln) * lda + i];
     POL::lin_init(e);
     __syncwarp();
-    const int inf = POL::dgbfa(e.lin);
+    const int inf = POL::factor(e.lin);
     real xv[1] = {(ln < N) ? b[(size_t)m * N + ln] : BV_R(0.0)};
     if (inf == 0) POL::solve(e, xv);
     __syncwarp();
@@ -173,7 +174,8 @@ static int lu_test(int kind, int n, int ml, int mu, int nmat, const real *a, con
     }
     if (kind == 3) {
         if (n != 25 || ml < 0 || mu < 0 || ml >= n || mu >= n || ml + mu + 1 > 32) return -1000;
-        k_lu_band<25><<<nmat, 32, sizeof(real) * ((2 * ml + mu + 1) | 1) * 25>>>(nmat, ml, mu, a, b, afac, ipvt, x, info);
+        using POL = WarpBandPolicy<LuProb<25>, 4, false, 2>;
+        k_lu_band<25><<<nmat, 32, sizeof(real) * POL::smem_doubles(ml, mu, false)>>>(nmat, ml, mu, a, b, afac, ipvt, x, info);
         return (int)cudaGetLastError();
     }
     return -1000;

@@ -31,6 +31,16 @@ constexpr unsigned kFull = 0xffffffffu;
 #else
 #define BVODE_DGINV_INLINE BV_DEV
 #endif
+// knobs of the inversion (measured): buffer loads in flight, the barrier that keeps them there
+#ifndef BVODE_DGINV_EARLY_RCP
+#define BVODE_DGINV_EARLY_RCP 0
+#endif
+#ifndef BVODE_DGINV_BATCH
+#define BVODE_DGINV_BATCH 4
+#endif
+#ifndef BVODE_DGINV_FENCE
+#define BVODE_DGINV_FENCE 1
+#endif
 
 // optional members of a warp problem (bvode_ref_problem.cuh: callbacks in the reference's whole-vector form)
 template <class P, class = void>
@@ -279,6 +289,132 @@ struct WarpCommon {
         }
         return idx;
     }
+    // ---- the pivoted inverse of N rows held one per lane (fast builds of the dense and the band policy; the
+    // method is described at WarpDensePolicy::dginv) ----------------------------------------------------------
+    // pa: the N rows (stride LD doubles, 16-byte aligned); perma: perm[32] (ints); bufa: 32 doubles of scratch;
+    // ipv: lane k receives perm[k].  N = PROB::N.
+    template <int LD>
+    BVODE_DGINV_INLINE static int dginv_rows(const unsigned pa, const unsigned perma, const unsigned bufa, int &ipv) {
+        constexpr int N = PROB::N;
+        // The lane's row lives in REGISTERS for the whole inversion, rotated by one entry per step so that
+        // "column k" is always r[0] and every register index is static inside a run-time loop over k:
+        // step k reads r[0] (the pivot candidate), lane l (the pivot row) publishes its row as it stands to a
+        // 32-double buffer in shared memory, and every lane forms r'[j] = r[j+1] + t * P[j+1] from 16-byte
+        // broadcast loads of that buffer; the entry of column k itself (the inverse's column) goes to the
+        // end, r'[N-1].  After N steps the rotation is complete and every row is scaled by 1 / its pivot.
+        // Shared-memory traffic per step: one single-lane store and one broadcast load of the pivot row,
+        // instead of a load and a store of every lane's own row (the shared-memory data pipe is what bounds
+        // the LINPACK form of this kernel, ncu r1o).
+        const int ln = lane();
+        const bool live = (N == 32) || (ln < N);
+        const unsigned rowa = pa + (live ? ln : 0) * (LD * 8);
+        constexpr int NE = (N + 1) & ~1;  // entries moved in pairs; r[N] (N odd) is a dummy
+        real r[NE];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NE; j += 2) lds_d2(rowa + j * 8, r[j], r[j + 1]);
+        bool unused = live;  // this lane's row has not been a pivot row yet
+        int info = 0;
+        real myrp = BV_R(1.0);  // 1 / (the pivot this lane's row supplied)
+#pragma unroll 1
+        for (int k = 0; k < N && info == 0; k++) {
+            const real v = r[0];
+#if BVODE_DGINV_EARLY_RCP
+            const real rv = qrcp(v);  // off the ballot -> shuffle chain: every lane inverts its own candidate
+#endif
+            const unsigned b = max_abs_ballot(v, unused);
+            const int l = __ffs((int)b) - 1;  // ties: the lowest row
+            const real piv = shfl_d(v, l);
+            if (ln == k) ipv = l;
+            sts_i(perma + k * 4, l);
+            if (piv == BV_R(0.0)) {
+                info = k + 1;
+            } else {
+#if BVODE_DGINV_EARLY_RCP
+                const real rp = shfl_d(rv, l);
+#else
+                const real rp = qrcp(piv);
+#endif
+                const bool mine = (ln == l);
+                // The pivot row is NOT scaled during the elimination: row operations commute with a scaling of
+                // the pivot row as long as the multipliers are formed from the entries as they stand
+                // (t = -v / pivot), so every row is scaled once, by 1 / its own pivot, after the last step.
+                // The single-lane section of a step is then just the publication of the row as it lies in the
+                // registers -- N / 2 16-byte stores of aligned pairs, no arithmetic, no moves (150 single-lane
+                // instructions per step in r2j, 63 with the row scaled and rotated by the pivot lane).  Every
+                // lane forms
+                //     r'[j] = r[j+1] + t * P[j+1]  (j < N-1),    r'[N-1] = t        (pivot row: t = 0, r'[N-1] = 1)
+                // i.e. the buffer is read one entry ahead of the register it lands in.
+                if (mine) {
+#pragma unroll
+                    for (int j = 0; j < NE; j += 2) sts_d2(bufa + j * 8, r[j], r[j + 1]);
+                    unused = false;
+                    myrp = rp;
+                }
+                __syncwarp();
+                const real t = mine ? BV_R(0.0) : -(v * rp);
+                // kB 16-byte loads of the buffer are in flight before their fmas: with one (the compiler's choice
+                // under register pressure: every load lands in the same register quad) a step is N / 2 exposed
+                // shared-memory latencies
+                constexpr int kB = BVODE_DGINV_BATCH;
+#pragma unroll
+                for (int j0 = 0; j0 < NE; j0 += 2 * kB) {
+                    real p[2 * kB];
+#pragma unroll
+                    for (int q = 0; q < kB; q++)
+                        if (j0 + 2 * q < NE) lds_d2(bufa + (j0 + 2 * q) * 8, p[2 * q], p[2 * q + 1]);
+#if BVODE_DGINV_FENCE
+                    if (kB > 1) __syncwarp();  // ptxas otherwise sinks each load to its first use again
+#endif
+#pragma unroll
+                    for (int q = 0; q < kB; q++) {
+                        const int j = j0 + 2 * q;
+                        if (j < NE) {
+                            if (j >= 1 && j <= N - 1) r[j - 1] = fma(t, p[2 * q], r[j]);
+                            if (j + 1 <= N - 1) r[j] = fma(t, p[2 * q + 1], r[j + 1]);
+                        }
+                    }
+                }
+                r[N - 1] = mine ? BV_R(1.0) : t;
+                __syncwarp();
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < N; j++) r[j] = r[j] * myrp;
+#pragma unroll
+            for (int j = 0; j < NE; j += 2) sts_d2(rowa + j * 8, r[j], r[j + 1]);
+        }
+        __syncwarp();
+        return info;
+    }
+    // x = P^-1 b from the rows dginv_rows left at pa (veca: 32 doubles of scratch; ipv as returned by dginv_rows)
+    template <int LD>
+    BV_DEV static void solve_inverse_rows(const unsigned pa, const unsigned veca, const int ipv, real (&x)[1]) {
+        constexpr int N = PROB::N;
+        const bool live = (N == 32) || (lane() < N);
+        const unsigned rowa = pa + (live ? lane() : 0) * (LD * 8);
+        // b[perm[j]] to lane j, then to shared memory: every lane needs all of them
+        const real bp = shfl_d(x[0], ipv);
+        __syncwarp();
+        sts_d(veca + lane() * 8, live ? bp : BV_R(0.0));
+        __syncwarp();
+        real s0 = BV_R(0.0), s1 = BV_R(0.0);
+        constexpr int NP = N & ~1;
+#pragma unroll 8
+        for (int j = 0; j < NP; j += 2) {
+            real a0, a1, b0, b1;
+            lds_d2(rowa + j * 8, a0, a1);
+            lds_d2(veca + j * 8, b0, b1);
+            s0 = fma(a0, b0, s0);
+            s1 = fma(a1, b1, s1);
+        }
+        if (N & 1) s0 = fma(lds_d(rowa + (N - 1) * 8), lds_d(veca + (N - 1) * 8), s0);
+        const real s = live ? s0 + s1 : BV_R(0.0);
+        x[0] = shfl_d(s, ipv);  // x_k is the sum of row perm[k]
+    }
+
+
     // FD increment of component `lane`, M:2966 / M:3065: r = max(srur*|y|, r0/ewt)
     BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[1], const real (&ewt)[1], int nact = N) {
         const real fac = norm(savf, ewt, nact);
@@ -332,15 +468,6 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // strict build keeps LINPACK's factors and solves (bit for bit).
 #ifndef BVODE_DENSE_INVERSE
 #define BVODE_DENSE_INVERSE 1
-#endif
-#ifndef BVODE_DGINV_EARLY_RCP
-#define BVODE_DGINV_EARLY_RCP 0
-#endif
-#ifndef BVODE_DGINV_BATCH
-#define BVODE_DGINV_BATCH 4
-#endif
-#ifndef BVODE_DGINV_FENCE
-#define BVODE_DGINV_FENCE 1
 #endif
     static constexpr bool kInverse = (BVODE_STRICT == 0) && (BVODE_DENSE_INVERSE != 0);
     // row stride in doubles.  LU: odd (own-row and broadcast 8-byte accesses are conflict-free).  Inverse:
@@ -566,128 +693,16 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
     // cond(P)*uround; the batch statistics stay inside the reference's +-2 % (tests).  Every lane works in
     // every elimination step, so the inversion costs about the instructions of the factorisation it
     // replaces (N^3 lane-fmas at full occupancy against N^3/3 at a third of it).
-    BVODE_DGINV_INLINE static int dginv(Lin &lin) {
-        // The lane's row lives in REGISTERS for the whole inversion, rotated by one entry per step so that
-        // "column k" is always r[0] and every register index is static inside a run-time loop over k:
-        // step k reads r[0] (the pivot candidate), lane l (the pivot row) publishes its row as it stands to a
-        // 32-double buffer in shared memory, and every lane forms r'[j] = r[j+1] + t * P[j+1] from 16-byte
-        // broadcast loads of that buffer; the entry of column k itself (the inverse's column) goes to the
-        // end, r'[N-1].  After N steps the rotation is complete and every row is scaled by 1 / its pivot.
-        // Shared-memory traffic per step: one single-lane store and one broadcast load of the pivot row,
-        // instead of a load and a store of every lane's own row (the shared-memory data pipe is what bounds
-        // the LINPACK form of this kernel, ncu r1o).
-        const int ln = lane();
-        const bool live = real_lane();
+    BV_DEV static int dginv(Lin &lin) {
         const unsigned pa = sm_addr(lin.p);
-        const unsigned rowa = pa + (live ? ln : 0) * (LDP * 8);
-        const unsigned perma = pa + kPermOff * 8;
-        const unsigned bufa = pa + kVecOff * 8;
-        constexpr int NE = (N + 1) & ~1;  // entries moved in pairs; r[N] (N odd) is a dummy
-        real r[NE];
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < NE; j += 2) lds_d2(rowa + j * 8, r[j], r[j + 1]);
-        bool unused = live;  // this lane's row has not been a pivot row yet
-        int info = 0;
-        real myrp = BV_R(1.0);  // 1 / (the pivot this lane's row supplied)
-#pragma unroll 1
-        for (int k = 0; k < N && info == 0; k++) {
-            const real v = r[0];
-#if BVODE_DGINV_EARLY_RCP
-            const real rv = qrcp(v);  // off the ballot -> shuffle chain: every lane inverts its own candidate
-#endif
-            const unsigned b = Base::max_abs_ballot(v, unused);
-            const int l = __ffs((int)b) - 1;  // ties: the lowest row
-            const real piv = shfl_d(v, l);
-            if (ln == k) lin.ipv = l;
-            sts_i(perma + k * 4, l);
-            if (piv == BV_R(0.0)) {
-                info = k + 1;
-            } else {
-#if BVODE_DGINV_EARLY_RCP
-                const real rp = shfl_d(rv, l);
-#else
-                const real rp = qrcp(piv);
-#endif
-                const bool mine = (ln == l);
-                // The pivot row is NOT scaled during the elimination: row operations commute with a scaling of
-                // the pivot row as long as the multipliers are formed from the entries as they stand
-                // (t = -v / pivot), so every row is scaled once, by 1 / its own pivot, after the last step.
-                // The single-lane section of a step is then just the publication of the row as it lies in the
-                // registers -- N / 2 16-byte stores of aligned pairs, no arithmetic, no moves (150 single-lane
-                // instructions per step in r2j, 63 with the row scaled and rotated by the pivot lane).  Every
-                // lane forms
-                //     r'[j] = r[j+1] + t * P[j+1]  (j < N-1),    r'[N-1] = t        (pivot row: t = 0, r'[N-1] = 1)
-                // i.e. the buffer is read one entry ahead of the register it lands in.
-                if (mine) {
-#pragma unroll
-                    for (int j = 0; j < NE; j += 2) sts_d2(bufa + j * 8, r[j], r[j + 1]);
-                    unused = false;
-                    myrp = rp;
-                }
-                __syncwarp();
-                const real t = mine ? BV_R(0.0) : -(v * rp);
-                // kB 16-byte loads of the buffer are in flight before their fmas: with one (the compiler's choice
-                // under register pressure: every load lands in the same register quad) a step is N / 2 exposed
-                // shared-memory latencies
-                constexpr int kB = BVODE_DGINV_BATCH;
-#pragma unroll
-                for (int j0 = 0; j0 < NE; j0 += 2 * kB) {
-                    real p[2 * kB];
-#pragma unroll
-                    for (int q = 0; q < kB; q++)
-                        if (j0 + 2 * q < NE) lds_d2(bufa + (j0 + 2 * q) * 8, p[2 * q], p[2 * q + 1]);
-#if BVODE_DGINV_FENCE
-                    if (kB > 1) __syncwarp();  // ptxas otherwise sinks each load to its first use again
-#endif
-#pragma unroll
-                    for (int q = 0; q < kB; q++) {
-                        const int j = j0 + 2 * q;
-                        if (j < NE) {
-                            if (j >= 1 && j <= N - 1) r[j - 1] = fma(t, p[2 * q], r[j]);
-                            if (j + 1 <= N - 1) r[j] = fma(t, p[2 * q + 1], r[j + 1]);
-                        }
-                    }
-                }
-                r[N - 1] = mine ? BV_R(1.0) : t;
-                __syncwarp();
-            }
-        }
-        if (live) {
-#pragma unroll
-            for (int j = 0; j < N; j++) r[j] = r[j] * myrp;
-#pragma unroll
-            for (int j = 0; j < NE; j += 2) sts_d2(rowa + j * 8, r[j], r[j + 1]);
-        }
+        const int info = Base::template dginv_rows<LDP>(pa, pa + kPermOff * 8, pa + kVecOff * 8, lin.ipv);
         lin.pos = 0;
-        __syncwarp();
         return info;
     }
     template <class ENG>
     BV_DEV static int solve_inverse(ENG &e, real (&x)[1]) {
-        const Lin &lin = e.lin;
-        const bool live = real_lane();
-        const unsigned pa = sm_addr(lin.p);
-        const unsigned rowa = pa + (live ? lane() : 0) * (LDP * 8);
-        const unsigned veca = pa + kVecOff * 8;
-        // b[perm[j]] to lane j, then to shared memory: every lane needs all of them
-        const real bp = shfl_d(x[0], lin.ipv);
-        __syncwarp();
-        sts_d(veca + lane() * 8, live ? bp : BV_R(0.0));
-        __syncwarp();
-        real s0 = BV_R(0.0), s1 = BV_R(0.0);
-        constexpr int NP = N & ~1;
-#pragma unroll 8
-        for (int j = 0; j < NP; j += 2) {
-            real a0, a1, b0, b1;
-            lds_d2(rowa + j * 8, a0, a1);
-            lds_d2(veca + j * 8, b0, b1);
-            s0 = fma(a0, b0, s0);
-            s1 = fma(a1, b1, s1);
-        }
-        if (N & 1) s0 = fma(lds_d(rowa + (N - 1) * 8), lds_d(veca + (N - 1) * 8), s0);
-        const real s = live ? s0 + s1 : BV_R(0.0);
-        x[0] = shfl_d(s, lin.ipv);  // x_k is the sum of row perm[k]
+        const unsigned pa = sm_addr(e.lin.p);
+        Base::template solve_inverse_rows<LDP>(pa, pa + kVecOff * 8, e.lin.ipv, x);
         return 0;
     }
 
@@ -955,21 +970,42 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
 #endif
     static constexpr int kMinBlocks = BVODE_BAND_MINBLOCKS;
     static_assert(MITER == 4 || MITER == 5, "band policy");
+    // Fast build: like the dense policy, the Newton matrix is INVERTED at dvjac time (WarpCommon::dginv_rows on
+    // the dense rows expanded from the band array, one row per lane) and dvsol is one matrix-vector product.
+    // dgbsl with b_i on lane i is 2n - 1 dependent "shuffle -> predicated fma" steps whatever the band width
+    // (~11 instructions each with run-time ml / mu: 28 % of the samples of this kernel in ncu r2m, dgbfa another
+    // 10 %); the product is ~60 instructions.  The band array keeps P = I - h*rl1*J UNFACTORED (it is what is
+    // saved with the system's state); the inverse is scratch in shared memory and is rebuilt from it when a
+    // system is loaded again.  The strict build keeps LINPACK's dgbfa / dgbsl (bit for bit).
+#ifndef BVODE_BAND_INVERSE
+#define BVODE_BAND_INVERSE 1
+#endif
+    static constexpr bool kInverse = (BVODE_STRICT == 0) && (BVODE_BAND_INVERSE != 0);
+    static constexpr int LDI = N + ((6 - (N & 3)) & 3);  // row stride of the inverse: = 2 (mod 4) doubles, see WarpDensePolicy::LDP
+    static constexpr int kInvPermOff = N * LDI + ((N * LDI) & 1);
+    static constexpr int kInvVecOff = kInvPermOff + 16;
+    static constexpr int kInvDoubles = kInverse ? kInvVecOff + 32 : 0;
 
     struct Lin {
         real *abd;   // shared memory, ld x N
         real *wjs;   // shared memory, mband x N (mf > 0)
+        real *inv;   // shared memory, N x LDI + perm[32] + 32 doubles (fast build): the pivoted inverse of abd
         int ml, mu, ld;
         int ipv;       // lane k holds ipvt(k+1) as a 0-based row of the full matrix
     };
     template <class ENG>
     BV_DEV static void lin_init(ENG &e) { e.lin.ipv = lane(); }
 
-    BV_DEV static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
-    // doubles of shared memory one system needs
-    static int smem_doubles(int ml, int mu, bool savej) {
+    __host__ __device__ static int band_ld(int ml, int mu) { return (2 * ml + mu + 1) | 1; }
+    // doubles of one system's SAVED image: the band array and the saved Jacobian
+    __host__ __device__ static int image_doubles(int ml, int mu, bool savej) {
         const int ld = (2 * ml + mu + 1) | 1;
         return ld * N + (savej ? (ml + mu + 1) * N : 0);
+    }
+    // doubles of shared memory one system needs: the image (rounded to 16 bytes) + the scratch of the inverse
+    __host__ __device__ static int smem_doubles(int ml, int mu, bool savej) {
+        const int img = image_doubles(ml, mu, savej);
+        return kInverse ? ((img + 1) & ~1) + kInvDoubles : img;
     }
     static constexpr int kLaneSlots = kLmax + 2;  // yh[6], acsav, acor; the band arrays follow
     static constexpr int kLaneIntSlots = 1;
@@ -982,6 +1018,29 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         const int nb = l.ld * N + (SAVEJ ? (l.ml + l.mu + 1) * N : 0);
         v.block(l.abd, nb);
         v.iv(l.ipv);
+    }
+    // ---- fast build: expand the band array into one dense row per lane and invert (see kInverse above) ----
+    // a(i, j) = abd(i - j + m, j), m = ml + mu + 1, for max(1, j - mu) <= i <= min(n, j + ml) (LP:230-260);
+    // abd is left as it is.  Returns dgbfa's info (the pivot sequence is dgefa's = dgbfa's: the rows outside the
+    // band hold zeros in the pivot column).
+    BV_DEV static int invert(Lin &l) {
+        const int ln = lane();
+        const int ml = l.ml, mu = l.mu, m = ml + mu + 1;
+        __syncwarp();
+        if (ln < N) {
+            const real *col = l.abd + (m - 1 + ln);  // abd[(j)*ld + (i - j + m - 1)], i = ln, 0-based j: advances by ld - 1
+            real *row = l.inv + ln * LDI;
+            for (int j = 0; j < LDI; j++, col += l.ld - 1)
+                row[j] = (j < N && j >= ln - ml && j <= ln + mu) ? *col : BV_R(0.0);
+        }
+        __syncwarp();
+        const unsigned pa = sm_addr(l.inv);
+        return Base::template dginv_rows<LDI>(pa, pa + kInvPermOff * 8, pa + kInvVecOff * 8, l.ipv);
+    }
+    // factor (dvjac, the LU known-answer tests): LINPACK's band factors in place, or the inverse next to the band array
+    BV_DEV static int factor(Lin &l) {
+        if constexpr (kInverse) return invert(l);
+        else return dgbfa(l);
     }
 
 #define ABD(i, j) l.abd[((j)-1) * l.ld + ((i)-1)]
@@ -1089,6 +1148,11 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
     template <class ENG>
     BV_DEV static int solve(ENG &e, real (&x)[1]) {
         const Lin &l = e.lin;
+        if constexpr (kInverse) {
+            const unsigned pa = sm_addr(l.inv);
+            Base::template solve_inverse_rows<LDI>(pa, pa + kInvVecOff * 8, l.ipv, x);
+            return 0;
+        }
         const int ln = lane();
         const int n = N, ml = l.ml, mu = l.mu, m = mu + ml + 1;
         const bool live = (N == 32) || (ln < n);
@@ -1237,8 +1301,13 @@ struct WarpBandPolicy : WarpCommon<PROB, METH_> {
         }
         __syncwarp();
         e.hot.si_add(SI_NLU, 1);
-        const int ier = dgbfa(l);
+        const int ier = factor(l);
         if (ier != 0) ierpj = 1;
+    }
+    // a system whose state was loaded for a continuation call: the band array holds P; rebuild its inverse
+    template <class ENG>
+    BV_DEV static void after_load(ENG &e) {
+        if constexpr (kInverse) (void)invert(e.lin);
     }
 #undef ABD
 };

@@ -200,6 +200,51 @@ def test_band_lu_known_answers_strict(ml, mu):
 
 
 # ------------------------------------------------------------------ failure exits of the driver ----
+@pytest.mark.parametrize("ml,mu", [(5, 0), (5, 5), (1, 1), (0, 3)])
+def test_band_lu_fast_build_solves(ml, mu):
+    """Fast build of the band policy: the band matrix is expanded to one dense row per lane and inverted with dgbfa's
+    pivot sequence, the solve is a matrix-vector product (policy_warp.cuh, WarpBandPolicy::invert).  The solution
+    agrees with LINPACK's to rounding (1e-13 * cond), info reports the same singular matrix, and the band array is
+    left unfactored (it is what the solver saves with a system's state)."""
+    B = _B()
+    n = 25
+    rng = np.random.default_rng(100 + 10 * ml + mu)
+    L = O.lib()
+    fulls, mats = [], []
+    for k in range(24):
+        f = rng.standard_normal((n, n))
+        if k % 3 == 0:
+            f = f + 10.0 * np.eye(n)
+        if k % 3 == 1:
+            f[np.arange(n), np.arange(n)] *= 0.01  # interchanges
+        if k == 20:
+            f[:, 3] = 0.0  # singular
+        band = np.zeros((n, n))
+        for j in range(n):
+            lo, hi = max(0, j - mu), min(n, j + ml + 1)
+            band[lo:hi, j] = f[lo:hi, j]
+        fulls.append(band)
+        mats.append(_band_storage(f, ml, mu))
+    a = np.array(mats)
+    b = rng.standard_normal((a.shape[0], n))
+    lda = 2 * ml + mu + 1
+    gfac, _, gx, ginfo = B.api.lu_test(3, a, b, ml=ml, mu=mu, strict=False)
+    for m in range(a.shape[0]):
+        abd = np.ascontiguousarray(a[m]).copy()
+        ip = np.zeros(n, dtype=np.int32)
+        inf = C.c_int()
+        L.dvo_dgbfa(abd.ctypes.data_as(C.POINTER(C.c_double)), lda, n, ml, mu, ip.ctypes.data_as(C.POINTER(C.c_int)), C.byref(inf))
+        assert (ginfo[m] != 0) == (inf.value != 0), (m, ginfo[m], inf.value)
+        assert np.array_equal(gfac[m], a[m]), m  # unfactored
+        if inf.value != 0:
+            continue
+        x = b[m].copy()
+        L.dvo_dgbsl(abd.ctypes.data_as(C.POINTER(C.c_double)), lda, n, ml, mu, ip.ctypes.data_as(C.POINTER(C.c_int)),
+                    x.ctypes.data_as(C.POINTER(C.c_double)))
+        cond = np.linalg.cond(fulls[m])
+        assert np.abs(gx[m] - x).max() <= 1e-13 * cond * max(1.0, np.abs(x).max()), (m, cond)
+
+
 def _strict_vs_oracle(problem, par, y0, touts, rtol, atol, mf, itol, want, iopt=0, rw=None, iw=None, okw=None):
     """Run the strict build and the oracle (pow_mode = 1); everything must be identical; `want` is the set of
     istate values that must occur."""
