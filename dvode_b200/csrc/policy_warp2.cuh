@@ -96,15 +96,19 @@ struct WarpCommon2 {
 #endif
     }
     BV_DEV static int comp(int i) { return lane() + 32 * i; }
-    BV_DEV static real norm(const real (&v)[2], const real (&w)[2], int = N) {  // (a smaller neq is refused for this mapping)
+    // nact: the equations integrated after an istate = 3 call with a smaller neq (M:1127-1135); the frozen components
+    // carry v = 0, so the sum over all N is the reference's sum over the first nact (see ThreadPolicy::norm)
+    BV_DEV static real norm(const real (&v)[2], const real (&w)[2], int nact = N) {
 #if BVODE_STRICT
-        return sqrt(sumsq(v, w) / (real)N);
+        return sqrt(sumsq(v, w) / (real)nact);
 #else
-        return sqrt(sumsq(v, w) * (BV_R(1.0) / (real)N));
+        return sqrt((nact == N) ? sumsq(v, w) * (BV_R(1.0) / (real)N) : sumsq(v, w) / (real)nact);
 #endif
     }
 #if !BVODE_STRICT
-    BV_DEV static real msq(const real (&v)[2], const real (&w)[2], int = N) { return sumsq(v, w) * (BV_R(1.0) / (real)N); }
+    BV_DEV static real msq(const real (&v)[2], const real (&w)[2], int nact = N) {
+        return (nact == N) ? sumsq(v, w) * (BV_R(1.0) / (real)N) : sumsq(v, w) / (real)nact;
+    }
 #endif
     BV_DEV static bool any_le_zero(const real (&v)[2]) {
         return __any_sync(kFull, (v[0] <= BV_R(0.0)) || (valid(1) && v[1] <= BV_R(0.0))) != 0;
@@ -151,9 +155,9 @@ struct WarpCommon2 {
         const int idx = (m1 > m0) ? l1 + 32 : l0;
         return (big > BV_R(0.0)) ? idx + 1 : 1;
     }
-    BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[2], const real (&ewt)[2]) {
-        const real fac = norm(savf, ewt);
-        real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)N * fac;
+    BV_DEV static real fd_r0(const Ctl &c, const real (&savf)[2], const real (&ewt)[2], int nact = N) {
+        const real fac = norm(savf, ewt, nact);
+        real r0 = BV_R(1000.0) * fabs(c.h) * kUround * (real)nact * fac;
         if (r0 == BV_R(0.0)) r0 = BV_R(1.0);
         return r0;
     }
@@ -419,19 +423,23 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
             e.hot.si(SI_NSLJ) = e.hot.si(SI_NST);
             c.jcur = 1;
             // finite differences, M:2959-2976: column j for all rows at once
-            const real r0 = Base::fd_r0(c, e.savf, e.ewt);
+            const real r0 = Base::fd_r0(c, e.savf, e.ewt, e.nact);
             const real srur = sqrt(kUround);
             const real rmine[2] = {dmax2(srur * fabs(e.y[0]), qdiv(r0, e.ewt[0])),
                                      dmax2(srur * fabs(e.y[1]), qdiv(r0, e.ewt[1]))};
             const real ysave[2] = {e.y[0], e.y[1]};
 #pragma unroll 1
             for (int j = 0; j < N; j++) {
-                const int jl = j & 31, js = j >> 5;
-                const real r = shfl_d(js ? rmine[1] : rmine[0], jl);
-                if (ln == jl) { if (js) e.y[1] = ysave[1] + r; else e.y[0] = ysave[0] + r; }
-                const real fac = qrcp(r);
-                Base::f(c.tn, e.y, e.acor, e.par);
-                const real d0 = (e.acor[0] - e.savf[0]) * fac, d1 = (e.acor[1] - e.savf[1]) * fac;
+                real d0 = BV_R(0.0), d1 = BV_R(0.0);  // neq was reduced: nothing in the columns of the dropped unknowns
+                if (j < e.nact) {                   // (warp-uniform; the rows of the dropped equations are zero through feval)
+                    const int jl = j & 31, js = j >> 5;
+                    const real r = shfl_d(js ? rmine[1] : rmine[0], jl);
+                    if (ln == jl) { if (js) e.y[1] = ysave[1] + r; else e.y[0] = ysave[0] + r; }
+                    const real fac = qrcp(r);
+                    e.feval(c.tn, e.y, e.acor);
+                    d0 = (e.acor[0] - e.savf[0]) * fac;
+                    d1 = (e.acor[1] - e.savf[1]) * fac;
+                }
                 if (SAVEJ) {
                     l.wjs.set(j, d0);
                     if (ok[1]) l.wjs.set(N + j, d1);
@@ -441,7 +449,7 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
                 e.y[0] = ysave[0];
                 e.y[1] = ysave[1];
             }
-            e.hot.si_add(SI_NFE, N);
+            e.hot.si_add(SI_NFE, e.nact);
         } else {
             c.jcur = 0;
             if (SAVEJ) {
@@ -541,7 +549,7 @@ struct WarpPlain2Policy : WarpCommon2<PROB, METH_> {
 #pragma unroll
         for (int i = 0; i < 2; i++) e.y[i] = e.y[i] + r * (c.h * e.savf[i] - e.hot.yh(1, i));
         real w[2];
-        Base::f(c.tn, e.y, w, e.par);
+        e.feval(c.tn, e.y, w);
         e.hot.si_add(SI_NFE, 1);
         real r0[2], di[2];
         bool big[2];

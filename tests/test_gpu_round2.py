@@ -649,7 +649,11 @@ def test_istate3_changes_the_method_family(problem, mf, mf2):
 # ------------------------------------------------------------------ istate = 3 with a smaller neq ----
 @pytest.mark.parametrize("problem,mf,neq2", [("advection", -24, 20), ("advection", -25, 20), ("advection", 10, 13),
                                              ("advection", 23, 20), ("advection", 13, 7), ("mech32", -22, 24),
-                                             ("mech32", -21, 24), ("mech32", 13, 17)])
+                                             ("mech32", -21, 24), ("mech32", 13, 17),
+                                             # two components per lane (32 < n <= 64): the cut inside the second slot,
+                                             # at the slot boundary and inside the first slot
+                                             ("diffusion48", -22, 40), ("diffusion48", -22, 32), ("diffusion48", 13, 33),
+                                             ("diffusion48", 23, 40), ("diffusion48", 10, 20)])
 def test_istate3_reduces_neq(problem, mf, neq2):
     """`neq` may be reduced (never raised) by an istate = 3 call (M:1127-1135): the solver goes on with the first
     neq equations; the dropped components stay what the caller's y array held for them (for mech32 the kept
@@ -663,6 +667,13 @@ def test_istate3_reduces_neq(problem, mf, neq2):
         rtol, atol, nsplit = [0.0], [1e-6], 2
         kw = dict(ml=5, mu=0, iopt=1, mxstep=5000, iopt2=1, mxstep2=5000)
         iw[0], iw[5] = 5, 5000
+    elif problem == "diffusion48":
+        par, y0, touts = B.batches.diffusion48_batch(nsys), B.batches.diffusion48_y0(), list(B.batches.diffusion48_touts())
+        rtol, atol, nsplit = [1e-6], [1e-9], 2
+        if mf in (10, 13, 23):
+            touts = touts[:3]
+        kw = dict(iopt=1, mxstep=50000, iopt2=1, mxstep2=50000)
+        iw[5] = 50000
     else:
         par, y0, touts = B.batches.mech32_batch(nsys), B.batches.mech32_y0(), [1e-6, 1e-5, 1e-4, 1e-3]
         rtol, atol, nsplit = [1e-6], [1e-12], 2
