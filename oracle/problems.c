@@ -203,8 +203,10 @@ static void mech_jac(void *ctx, int neq, real t, real *y, int ml, int mu, real *
 static void dif_f(void *ctx, int neq, real t, const real *y, real *ydot)
 {
     const real *p = (const real *)ctx;
-    (void)neq; (void)t;
-    for (int i = 0; i < 48; i++) {
+    (void)t;
+    /* ydot has neq entries (fewer than 48 after an istate = 3 call with a smaller neq, M:1127-1135: savf is followed
+       by acor in rwork); y is the caller's array and keeps all 48 */
+    for (int i = 0; i < neq; i++) {
         real l = (i > 0) ? y[i - 1] : DVO_R(0.0), r = (i + 1 < 48) ? y[i + 1] : DVO_R(0.0);
         real s = (i < 4) ? DVO_R(1.0) : DVO_R(0.0);
         ydot[i] = p[0] * ((l - DVO_R(2.0) * y[i]) + r) - p[1] * y[i] * y[i] + s;
