@@ -361,13 +361,6 @@ static int check_args(const bvode_solver *s, int neq, int itol, const real *rtol
                                 : "neq may only be reduced by an istate = 3 call";
             return BVODE_EINVAL;
         }
-        const int mfa0 = mf < 0 ? -mf : mf;
-        if (neq < s->neq && s->neq > 32 && mfa0 % 10 == 3) {
-            // two components per lane: dense (FD) and functional iteration are bit-exact against the oracle after the
-            // restart; with the diagonal approximation one system in 40 separates (open) -- refused rather than wrong
-            g_err = "a smaller neq with miter = 3 is not built for problems mapped two components per lane (n > 32)";
-            return BVODE_ENOTIMPL;
-        }
     }
     if (itask < 1 || itask > 5) { g_err = "itask illegal"; return BVODE_EINVAL; }
     if ((itask == 4 || itask == 5) && !rwork0) { g_err = "itask 4/5 needs rwork(1) = tcrit"; return BVODE_EINVAL; }

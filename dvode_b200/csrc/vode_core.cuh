@@ -565,6 +565,27 @@ struct Engine {
             }
             if (MITER == 0) xcol_mode = 2;
         }
+        if (nact != N) {
+            // M:2045-2053: while n differs from the leading dimension of yh -- on every istate = 3 call from the
+            // reduction on -- dvstep first clears yh(:, newq+2 : maxord+1), ALL components, "to avoid undefined
+            // references".  Above the order these columns are zero here anyway; but with an order DECREASE pending
+            // (newq = nq - 1) the cleared range starts at column nq + 1, the top Nordsieck column, which the
+            // dvjust(-1) that follows (M:2114) would have folded into the lower ones, and it always takes in
+            // yh(:, lmax), the acor copy of a pending order increase.  (Found on the one system in 40 of the n = 48
+            // batch that restarts with an order decrease pending; the corrector then fails on the first step.)
+            const bool top = (c.newq < c.nq) && (c.newq + 2 <= o.maxord + 1);
+#pragma unroll
+            for (int j = 2; j <= kLmax; j++) {
+                if (top && j == c.nq + 1) {
+#pragma unroll
+                    for (int i = 0; i < NLOC; i++) hot.yh(j - 1, i) = BV_R(0.0);
+                }
+            }
+            if (c.newq + 2 <= o.maxord + 1) {
+#pragma unroll
+                for (int i = 0; i < NLOC; i++) POL::acsav_set(*this, i, BV_R(0.0));
+            }
+        }
         if (o.jreset) hot.si(SI_NSLJ) = hot.si(SI_NST) - 51;  // forces jok = -1 (msbj = 50)
         // The acor copy of a pending order increase is parked in yh(:, lmax) (M:2259, 2298); with another lmax the
         // reference's dvjust(+1) / order test read yh(:, lmax_new) -- a Nordsieck column (zero above the order)

@@ -651,11 +651,11 @@ def test_istate3_changes_the_method_family(problem, mf, mf2):
                                              ("advection", 23, 20), ("advection", 13, 7), ("mech32", -22, 24),
                                              ("mech32", -21, 24), ("mech32", 13, 17),
                                              # two components per lane (32 < n <= 64): the cut inside the second slot,
-                                             # at the slot boundary and inside the first slot.  (With the diagonal
-                                             # approximation, mf 13 / 23, ONE system of this batch separates from the
-                                             # oracle after the restart -- open, DESIGN.md section 8 -- so those flags
-                                             # are not claimed for n > 32.)
-                                             ("diffusion48", -22, 40), ("diffusion48", -22, 32), ("diffusion48", 10, 20)])
+                                             # at the slot boundary and inside the first slot.  System 17 of the
+                                             # diagonal-approximation runs restarts with an order DECREASE pending: the
+                                             # reference then clears the top Nordsieck column (M:2045-2053).
+                                             ("diffusion48", -22, 40), ("diffusion48", -22, 32), ("diffusion48", 10, 20),
+                                             ("diffusion48", 13, 33), ("diffusion48", 13, 47), ("diffusion48", 23, 40)])
 def test_istate3_reduces_neq(problem, mf, neq2):
     """`neq` may be reduced (never raised) by an istate = 3 call (M:1127-1135): the solver goes on with the first
     neq equations; the dropped components stay what the caller's y array held for them (for mech32 the kept
