@@ -109,9 +109,9 @@ BVODE_API int bvode_set_params(bvode_solver *s, const bvode_real *params);
  *   istate 1 (first call), 2 (continue), 3 (continue with changed itol / rtol / atol / itask /
  *          optional inputs incl. a lower maxord; must then be 3 for every system; mf may change
  *          -- miter, jsv and meth (Adams <-> BDF): the state moves into the new kernel's layout and
- *          the Jacobian is re-evaluated -- and neq may be reduced (M:1127-1135; n <= 32: y then has
- *          neq entries per system, the dropped components stay what y held for them); not ml / mu
- *          of a banded flag).
+ *          the Jacobian is re-evaluated -- ml / mu of a banded flag may change, and neq may be
+ *          reduced (M:1127-1135: y then has neq entries per system, the dropped components stay
+ *          what y held for them; never raised again).
  *   mf     jsv*(10*meth + miter), M:999-1046: meth 1 (Adams) or 2 (BDF); miter 0 (functional
  *          iteration), 1 / 2 (dense analytic / finite-difference J; thread-per-system problems,
  *          miter 2 also for the dense warp problem), 3 (diagonal approximation), 4 / 5 (banded
