@@ -956,14 +956,20 @@ int bvode_dvsrco_n(bvode_solver *s, void *sav, long long nbytes, int job) {
     if (job == 1) {
         if (!s->d_state) { g_err = "dvsrco(job = 1) before any successful solve"; return BVODE_EINVAL; }
         if (nbytes >= 0 && (size_t)nbytes < sav_bytes(s, s->nd, s->ni)) { g_err = "dvsrco: buffer shorter than bvode_state_bytes()"; return BVODE_EINVAL; }
-        SavHeader h{kSavMagic, s->problem, s->nsys, s->mf, s->ml, s->mu, s->maxord, s->mxstep, s->neq, s->nact,
+        SavHeader h{kSavMagic + ((s->flags & BVODE_FLAG_STRICT) ? 1 : 0), s->problem, s->nsys, s->mf, s->ml, s->mu, s->maxord, s->mxstep, s->neq, s->nact,
                     (unsigned long long)s->nd, (unsigned long long)s->ni};
         memcpy(p, &h, sizeof(h));
     } else {
         if (nbytes >= 0 && (size_t)nbytes < sizeof(SavHeader)) { g_err = "dvsrco: buffer shorter than its header"; return BVODE_EINVAL; }
         SavHeader h;
         memcpy(&h, p, sizeof(h));
-        if (h.magic != kSavMagic || h.problem != s->problem || h.nsys != s->nsys || h.neq != s->neq) {
+        // the two builds keep different things in the saved matrix image (LINPACK's factors in the strict build; the
+        // pivoted inverse / the unfactored band matrix in the fast one), so a state goes back into the build it came from
+        if (h.magic == kSavMagic + ((s->flags & BVODE_FLAG_STRICT) ? 0 : 1)) {
+            g_err = "dvsrco(job = 2): the buffer was saved by the other build (BVODE_FLAG_STRICT differs)";
+            return BVODE_EINVAL;
+        }
+        if (h.magic != kSavMagic + ((s->flags & BVODE_FLAG_STRICT) ? 1 : 0) || h.problem != s->problem || h.nsys != s->nsys || h.neq != s->neq) {
             g_err = "dvsrco(job = 2): the buffer was not saved from a handle of this problem and batch size";
             return BVODE_EINVAL;
         }

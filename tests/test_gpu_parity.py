@@ -390,6 +390,11 @@ def test_checkpoint_resume_dvsrco():
                       0, 21, yo)
     assert (istate == 2).all()
     assert np.array_equal(yo.transpose(1, 0, 2), full["y"][:, 6:])
+    # a state goes back into the build it came from (the saved matrix image differs between the builds)
+    s3 = B.dvode_t().initialize("robertson", nsys, par, strict=True)
+    with pytest.raises(B.BvodeError):
+        s3.dvsrco(sav, 2)
+    s3.close()
 
 
 def test_error_paths_match_reference_semantics():
