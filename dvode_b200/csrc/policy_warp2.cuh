@@ -179,13 +179,18 @@ struct WarpDense2Policy : WarpCommon2<PROB, METH_> {
     static constexpr bool SAVEJ = SAVEJ_;
     static constexpr bool kBand = false;
     static constexpr bool kPlain = false;
+    // One system per CTA, 10 CTAs per SM: a system's matrix is N x (N | 1) doubles of shared memory (18.8 KB for
+    // n = 48, 33 KB for n = 64: the carve-out then admits 6), the kernel needs ~80 registers, and it is bound by
+    // per-warp latency (issue 33 % at 8 warps / SM, ncu r2q) -- measured on diffusion48: 2 systems x 4 CTAs 274 k,
+    // 2 x 5 302 k, 1 x 10 and 1 x 11 309 k, 3 x 3 276 k systems/s.  (Reading the pivot lanes of dgesl four steps
+    // ahead, to take the load out of the load -> shuffle -> fma chain of a step: 286 k -- withdrawn.)
 #ifndef BVODE_DENSE2_TPB
-#define BVODE_DENSE2_TPB 64
+#define BVODE_DENSE2_TPB 32
 #endif
 #ifndef BVODE_DENSE2_MINBLOCKS
-#define BVODE_DENSE2_MINBLOCKS 4
+#define BVODE_DENSE2_MINBLOCKS 10
 #endif
-    static constexpr int kTPB = BVODE_DENSE2_TPB;  // 2 systems per CTA: 2 x (64 x 65 doubles) of shared memory
+    static constexpr int kTPB = BVODE_DENSE2_TPB;
     static constexpr int kMinBlocks = BVODE_DENSE2_MINBLOCKS;
     static constexpr int LDP = N | 1;
     static constexpr int kPermOff = N * LDP + ((N * LDP) & 1);
