@@ -396,8 +396,14 @@ BV_DEV void warp_bind(Engine<POL> &e, const real *dstate, const int *istore, siz
 //   advection mf=24   1.37M    1.41M    1.60M    1.75M
 // (the replicated control state lives once per warp in shared memory, see WarpCommon::Hot;
 // before that: 6 CTAs 88.8k / 1.53M).
+// BVODE_WARP_MAXNREG (experiments): a register cap between ptxas's own steps (see BVODE_THREAD_MAXNREG)
+#ifdef BVODE_WARP_MAXNREG
+#define BVODE_WARP_BOUNDS __maxnreg__(BVODE_WARP_MAXNREG)
+#else
+#define BVODE_WARP_BOUNDS __launch_bounds__(WarpTpb<POL>::value, POL::kMinBlocks)
+#endif
 template <class POL, bool GENERAL>
-__global__ void __launch_bounds__(WarpTpb<POL>::value, POL::kMinBlocks)
+__global__ void BVODE_WARP_BOUNDS
 vode_warp_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ real smem[];
     const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
