@@ -848,8 +848,21 @@ struct WarpDensePolicy : WarpCommon<PROB, METH_> {
         }
         const real con = -hrl1;
         if (ln < N) {
+            if constexpr (kInverse) {
+                // rows are 16-byte aligned in this layout: pairs, four loads in flight (the element-by-element loop
+                // exposed one shared-memory latency per entry: 2.5 % of the samples of the kernel, ncu r2o)
+                const unsigned ra = sm_addr(row);
+                constexpr int NE = (N + 1) & ~1;  // (N odd: the pad entry of the row is scaled as well)
+#pragma unroll 4
+                for (int j = 0; j < NE; j += 2) {
+                    real a0, a1;
+                    lds_d2(ra + j * 8, a0, a1);
+                    sts_d2(ra + j * 8, con * a0, con * a1);
+                }
+            } else {
 #pragma unroll 1
-            for (int j = 0; j < N; j++) row[j] = con * row[j];
+                for (int j = 0; j < N; j++) row[j] = con * row[j];
+            }
             row[ln] = row[ln] + BV_R(1.0);
         }
         e.hot.si_add(SI_NLU, 1);
